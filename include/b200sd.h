@@ -1,0 +1,178 @@
+/* b200sd.h -- C ABI of libb200sd.so: the sm_100a (B200) kernels behind the SD v1.x UNet denoise
+ * hot path (UNet2DConditionModel.forward, scheduler.step / add_noise, CFG combine, MSE loss).
+ *
+ * The reference (Edenzzzz/Stable-Diffusion-for-book-cover-generation) has no FFI of its own: the
+ * boundary is the diffusers 0.7.2 Python class surface.  Every entry point below names the
+ * reference call site whose arithmetic it replaces; the Python facade in
+ * `stable-diffusion-for-book-cover-generation_b200/` (import name `b200sd`) binds them with ctypes
+ * (INTEGRATION.md shows the binding a maintainer would add).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all pointers are DEVICE pointers unless stated otherwise;
+ *   - every call enqueues work on `stream` (a cudaStream_t passed as void*), never synchronises,
+ *     never allocates: scratch is caller-provided (`*_workspace_bytes` says how much);
+ *   - return 0 on success, non-zero (B200SD_ERR_*) on error; b200sd_last_error() gives the text;
+ *   - activations are NHWC ("channels last"): a (N,C,H,W) tensor is stored as [N*H*W][C];
+ *   - dtype codes: B200SD_F32 = 0, B200SD_BF16 = 1.
+ */
+#ifndef B200SD_H_
+#define B200SD_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200SD_OK 0
+#define B200SD_ERR_INVALID 1
+#define B200SD_ERR_CUDA 2
+#define B200SD_ERR_UNSUPPORTED 3
+
+#define B200SD_F32 0
+#define B200SD_BF16 1
+
+typedef void* b200sd_stream_t; /* cudaStream_t */
+
+/* ---- library ---------------------------------------------------------------------------- */
+const char* b200sd_last_error(void);
+int b200sd_version(void);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+int64_t b200sd_launch_count(void);
+
+/* ---- scheduler / loss elementwise kernels (HBM-bound) ------------------------------------- */
+
+/* Classifier-free-guidance combine fused with the DDIM update (eta = 0):
+ *   eps = eps_u + g (eps_c - eps_u);  x0 = (x - sb_t eps) / sa_t;  out = sa_p x0 + sb_p eps
+ * Replaces the pipeline's `noise_pred_uncond + guidance_scale * (...)` and DDIMScheduler.step
+ * (reference call sites inference.py:175-176, 386-387).
+ * eps_c == NULL -> no CFG (eps = eps_u).  eps_out (optional) receives the combined eps.
+ * x_dtype / eps_dtype: B200SD_F32 or B200SD_BF16; out has x_dtype, eps_out has eps_dtype.
+ * Algorithmic bytes: 4 * n * elem (3 reads + 1 write). */
+int b200sd_cfg_ddim_step(const void* eps_u, const void* eps_c, const void* x, void* out, void* eps_out,
+                         int64_t n, float guidance, float sa_t, float sb_t, float sa_p, float sb_p,
+                         int eps_dtype, int x_dtype, b200sd_stream_t stream);
+
+/* CFG combine fused with the PLMS (PNDM skip_prk_steps=True) linear-multistep update:
+ *   eps = eps_u + g (eps_c - eps_u);  e = w[0] eps + sum_{i<nhist} w[1+i] hist[i];
+ *   out = cx * x - ce * e
+ * Replaces PNDMScheduler.step_plms/_get_prev_sample (reference call site utils.py:222-224;
+ * SURVEY.md App. B.3).  eps_out (optional) receives eps so the host can keep the 4-deep history.
+ * hist pointers are device pointers with eps_dtype elements. */
+int b200sd_cfg_plms_step(const void* eps_u, const void* eps_c, const void* x, void* out, void* eps_out,
+                         const void* hist0, const void* hist1, const void* hist2, const void* hist3,
+                         int nhist, const float* w_host5, int64_t n, float guidance, float cx, float ce,
+                         int eps_dtype, int x_dtype, b200sd_stream_t stream);
+
+/* DDPMScheduler.add_noise (finetune_sd.py:473-474): out[b] = sa[t[b]] x0[b] + sb[t[b]] noise[b].
+ * timesteps: int64[batch] (device); sa_table / sb_table: float[num_train_timesteps] (device). */
+int b200sd_add_noise(const void* x0, const void* noise, const int64_t* timesteps, const float* sa_table,
+                     const float* sb_table, void* out, int batch, int64_t per_sample, int num_train_timesteps,
+                     int dtype, b200sd_stream_t stream);
+
+/* F.mse_loss(pred, target, "none").mean([1,2,3]).mean() (finetune_sd.py:483-484) == global mean.
+ * loss_out: float[1]; workspace: float[b200sd_mse_workspace_floats()]. */
+int b200sd_mse_workspace_floats(void);
+int b200sd_mse_loss_fwd(const void* pred, const void* target, float* loss_out, float* workspace, int64_t n,
+                        int pred_dtype, int target_dtype, b200sd_stream_t stream);
+/* grad_pred = grad_loss[0] * 2 (pred - target) / n ; grad_loss: device float[1] */
+int b200sd_mse_loss_bwd(const void* pred, const void* target, const float* grad_loss, void* grad_pred, int64_t n,
+                        int pred_dtype, int target_dtype, b200sd_stream_t stream);
+
+/* ---- UNet building blocks ----------------------------------------------------------------- */
+
+/* diffusers Timesteps (flip_sin_to_cos=True, freq_shift=0):
+ * out[b, 0:dim/2] = cos(t_b f_i), out[b, dim/2:] = sin(t_b f_i), f_i = exp(-ln(1e4) i / (dim/2)).
+ * timesteps: float[batch] (device). out: float[batch, dim]. */
+int b200sd_timestep_embedding(const float* timesteps, float* out, int batch, int dim, b200sd_stream_t stream);
+
+/* Small-M linear for the time-embedding MLP and the 22 time_emb_proj heads:
+ *   out[b, n] = bias[n] + sum_k act(in[b, k]) * W[n, k],  act = SiLU if silu_in else identity,
+ *   optional SiLU on the output.  in/out fp32, W bf16 [N,K] row-major, bias fp32. */
+int b200sd_small_linear(const float* in, const void* w_bf16, const float* bias, float* out, int batch, int N, int K,
+                        int silu_in, int silu_out, b200sd_stream_t stream);
+
+/* GEMM / implicit-GEMM conv on tcgen05 tensor cores (TMA -> smem -> tcgen05.mma -> TMEM).
+ *   out[M, N] = A[M, K] * W[N, K]^T  (+ bias[N]) (+ rowbias[row / rows_per_image, N]) (+ residual[M, N])
+ * A and W are bf16, accumulation fp32, out bf16 (or fp32 when out_dtype == B200SD_F32).
+ * Replaces nn.Linear / Conv2d 1x1 / Conv2d 3x3 (cuBLAS / cuDNN in the reference stack;
+ * SURVEY.md section 2.3 K1, K2, K3, K5).
+ *
+ * A operand:
+ *   conv_taps == 1 : plain GEMM. A is [M, C0] (lda0 elements between rows); if a1 != NULL the K
+ *                    dimension is the channel concat [a0 | a1] (C0 + C1), i.e. torch.cat fused.
+ *   conv_taps == 9 : 3x3 stride-1 pad-1 conv over NHWC [batch, H, W, C0(+C1)];
+ *                    K = 9 * (C0 + C1), W is [N][ky][kx][C0+C1]; M = batch * H * W.
+ * epilogue:
+ *   B200SD_EPI_LINEAR : bias / rowbias / residual as above.
+ *   B200SD_EPI_GEGLU  : W rows are tile-interleaved [value | gate] (see b200sd_geglu_tile());
+ *                       out[M, N/2] = value * gelu_erf(gate), bias likewise interleaved.
+ * split_k > 1 needs workspace (b200sd_gemm_workspace_bytes) and is reduced deterministically.
+ */
+#define B200SD_EPI_LINEAR 0
+#define B200SD_EPI_GEGLU 1
+
+typedef struct b200sd_gemm_args {
+    const void* a0;        /* bf16 */
+    const void* a1;        /* bf16 or NULL */
+    const void* w;         /* bf16 [N, K] */
+    const float* bias;     /* [N] or NULL */
+    const float* rowbias;  /* [batch, N] or NULL (time-embedding add) */
+    const void* residual;  /* bf16 [M, ldr] or NULL */
+    void* out;             /* [M, ldc] */
+    int M, N, K;
+    int C0, C1;            /* channels of a0 / a1 */
+    int lda0, lda1;        /* row pitch (elements) of a0 / a1 in plain-GEMM mode */
+    int ldc, ldr;
+    int conv_taps;         /* 1 or 9 */
+    int batch, H, W;       /* conv geometry (conv_taps == 9) */
+    int rows_per_image;    /* for rowbias: image index = row / rows_per_image */
+    int epilogue;          /* B200SD_EPI_* */
+    int out_dtype;         /* B200SD_BF16 or B200SD_F32 */
+    int block_n;           /* 0 = auto */
+    int split_k;           /* 0 = auto */
+    void* workspace;       /* split-K scratch (may be NULL when split_k == 1) */
+    size_t workspace_bytes;
+} b200sd_gemm_args;
+
+size_t b200sd_gemm_workspace_bytes(void);
+int b200sd_geglu_tile(int N); /* tile width used to interleave GEGLU weights for a given N (= 8C) */
+int b200sd_gemm(const b200sd_gemm_args* args, b200sd_stream_t stream);
+
+/* Direct 3x3 convs at the ends of the UNet (degenerate GEMM shapes, CUDA cores):
+ * conv_in : NCHW fp32 (batch, Cin=4, H, W) -> NHWC bf16 (batch*H*W, Cout); w fp32 packed [Cout][ky][kx][Cin].
+ * conv_out: NHWC bf16 (batch*H*W, Cin) -> NCHW fp32 (batch, Cout<=4, H, W); w fp32 packed [Cout][ky][kx][Cin]. */
+int b200sd_conv_in(const float* x_nchw, const float* w, const float* bias, void* out_nhwc, int batch, int Cin,
+                   int Cout, int H, int W, b200sd_stream_t stream);
+int b200sd_conv_out(const void* x_nhwc, const float* w, const float* bias, float* out_nchw, int batch, int Cin,
+                    int Cout, int H, int W, b200sd_stream_t stream);
+
+/* GroupNorm over NHWC input, optionally over the channel concat [x0 | x1] (torch.cat fused),
+ * optional SiLU, bf16 output [rows, C0+C1].  stats_ws: float[2 * batch * groups] scratch.
+ * Replaces nn.GroupNorm + SiLU (+ torch.cat) in ResnetBlock2D / Transformer2DModel. */
+int b200sd_groupnorm_silu(const void* x0, const void* x1, int C0, int C1, const float* gamma, const float* beta,
+                          void* out, float* stats_ws, int batch, int hw, int groups, float eps, int silu,
+                          b200sd_stream_t stream);
+
+/* LayerNorm over the last dim of [rows, C] bf16 -> bf16 (eps 1e-5, affine). */
+int b200sd_groupnorm_workspace_floats(int batch);
+int b200sd_layernorm(const void* x, const float* gamma, const float* beta, void* out, int rows, int C, float eps,
+                     b200sd_stream_t stream);
+
+/* Fused (flash-style) attention: out = softmax(scale * Q K^T) V per (batch, head).
+ * q: [batch*Sq, ldq] with head h at columns [h*d, (h+1)*d); k, v likewise with ldk / ldv;
+ * out: [batch*Sq, ldo].  All bf16, fp32 softmax/accumulate.  d in {40, 80, 160} (+ 32, 64, 128).
+ * Replaces CrossAttention._attention (baddbmm + softmax + bmm). */
+int b200sd_attention(const void* q, const void* k, const void* v, void* out, int batch, int heads, int Sq, int Skv,
+                     int d, int ldq, int ldk, int ldv, int ldo, float scale, b200sd_stream_t stream);
+
+/* nearest x2 upsample NHWC bf16: (batch,H,W,C) -> (batch,2H,2W,C)  (Upsample2D's F.interpolate) */
+int b200sd_upsample2x(const void* x, void* out, int batch, int H, int W, int C, b200sd_stream_t stream);
+/* im2col for the three stride-2 Downsample2D convs: NHWC (batch,H,W,C) -> [batch*(H/2)*(W/2)][9*C] */
+int b200sd_im2col_s2(const void* x, void* out, int batch, int H, int W, int C, b200sd_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200SD_H_ */

@@ -1,0 +1,341 @@
+"""ORACLE (test infrastructure, not product code) -- SD v1.x UNet2DConditionModel restated in
+plain fp32 PyTorch.
+
+PARITY UNPINNED: the arithmetic of this path lives in the un-vendored third-party package
+`diffusers==0.7.2` (pinned at /root/reference/env.yaml:112) which is neither installed nor
+installable here, and the reference repository holds no tests, golden vectors or fixtures
+(SURVEY.md section 4 / 8c).  This module restates the published diffusers 0.7.2 algorithm
+(models/unet_2d_condition.py, unet_2d_blocks.py, resnet.py, attention.py, embeddings.py) and is
+anchored on the reference's call sites:
+
+  * `unet(noisy_latents, timesteps, encoder_hidden_states).sample`  -- finetune_sd.py:480-481
+  * every `pipeline(...)` call                                        -- inference.py:175, 342, 349
+  * `UNet2DConditionModel.from_pretrained(..., subfolder="unet")`     -- finetune_sd.py:328-330
+
+Self-checks standing in for the missing pins (tests/test_oracle_unet.py): 859 520 964 parameters,
+686 state-dict tensors with the diffusers key names, timestep-embedding
+known answers (App. B.5), explicit-softmax attention vs torch SDPA, conv vs unfold+matmul.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import
+this file.  The product path (package `b200sd`) never does.
+"""
+from __future__ import annotations
+
+import math
+from types import SimpleNamespace
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+# SD v1.4 / v1.5 unet/config.json
+SD15_CONFIG = dict(
+    sample_size=64,
+    in_channels=4,
+    out_channels=4,
+    center_input_sample=False,
+    flip_sin_to_cos=True,
+    freq_shift=0,
+    down_block_types=("CrossAttnDownBlock2D", "CrossAttnDownBlock2D", "CrossAttnDownBlock2D", "DownBlock2D"),
+    up_block_types=("UpBlock2D", "CrossAttnUpBlock2D", "CrossAttnUpBlock2D", "CrossAttnUpBlock2D"),
+    block_out_channels=(320, 640, 1280, 1280),
+    layers_per_block=2,
+    downsample_padding=1,
+    mid_block_scale_factor=1,
+    act_fn="silu",
+    norm_num_groups=32,
+    norm_eps=1e-5,
+    cross_attention_dim=768,
+    attention_head_dim=8,  # diffusers 0.7.2 uses this as the NUMBER of heads
+)
+
+
+def timestep_embedding(timesteps: torch.Tensor, dim: int = 320, flip_sin_to_cos: bool = True,
+                       freq_shift: float = 0.0, max_period: int = 10000) -> torch.Tensor:
+    """diffusers embeddings.get_timestep_embedding: fp32 sinusoid."""
+    half = dim // 2
+    exponent = -math.log(max_period) * torch.arange(half, dtype=torch.float32, device=timesteps.device)
+    exponent = exponent / (half - freq_shift)
+    emb = timesteps[:, None].float() * torch.exp(exponent)[None, :]
+    emb = torch.cat([torch.sin(emb), torch.cos(emb)], dim=-1)
+    if flip_sin_to_cos:
+        emb = torch.cat([emb[:, half:], emb[:, :half]], dim=-1)
+    return emb
+
+
+class TimestepEmbedding(nn.Module):
+    def __init__(self, in_dim: int, dim: int):
+        super().__init__()
+        self.linear_1 = nn.Linear(in_dim, dim)
+        self.linear_2 = nn.Linear(dim, dim)
+
+    def forward(self, x):
+        return self.linear_2(F.silu(self.linear_1(x)))
+
+
+class ResnetBlock2D(nn.Module):
+    """GN-SiLU-conv3x3 (+temb) GN-SiLU-conv3x3 + shortcut (SURVEY.md App. A.2 'Res')."""
+
+    def __init__(self, cin: int, cout: int, temb_ch: int = 1280, groups: int = 32, eps: float = 1e-5):
+        super().__init__()
+        self.norm1 = nn.GroupNorm(groups, cin, eps=eps, affine=True)
+        self.conv1 = nn.Conv2d(cin, cout, 3, padding=1)
+        self.time_emb_proj = nn.Linear(temb_ch, cout)
+        self.norm2 = nn.GroupNorm(groups, cout, eps=eps, affine=True)
+        self.conv2 = nn.Conv2d(cout, cout, 3, padding=1)
+        self.conv_shortcut = nn.Conv2d(cin, cout, 1) if cin != cout else None
+
+    def forward(self, x, temb):
+        h = self.conv1(F.silu(self.norm1(x)))
+        h = h + self.time_emb_proj(F.silu(temb))[:, :, None, None]
+        h = self.conv2(F.silu(self.norm2(h)))
+        if self.conv_shortcut is not None:
+            x = self.conv_shortcut(x)
+        return x + h  # output_scale_factor = 1.0
+
+
+class CrossAttention(nn.Module):
+    """to_q/to_k/to_v without bias, softmax(q k^T d^-1/2) v, to_out.0 with bias."""
+
+    def __init__(self, query_dim: int, context_dim: int | None, heads: int):
+        super().__init__()
+        context_dim = context_dim or query_dim
+        self.heads = heads
+        self.scale = (query_dim // heads) ** -0.5
+        self.to_q = nn.Linear(query_dim, query_dim, bias=False)
+        self.to_k = nn.Linear(context_dim, query_dim, bias=False)
+        self.to_v = nn.Linear(context_dim, query_dim, bias=False)
+        self.to_out = nn.ModuleList([nn.Linear(query_dim, query_dim), nn.Dropout(0.0)])
+
+    def forward(self, x, context=None):
+        context = x if context is None else context
+        b, s, c = x.shape
+        h = self.heads
+        q = self.to_q(x).view(b, s, h, c // h).transpose(1, 2)
+        k = self.to_k(context).view(b, -1, h, c // h).transpose(1, 2)
+        v = self.to_v(context).view(b, -1, h, c // h).transpose(1, 2)
+        scores = torch.matmul(q, k.transpose(-1, -2)) * self.scale   # materialised, like baddbmm
+        probs = scores.softmax(dim=-1)
+        o = torch.matmul(probs, v).transpose(1, 2).reshape(b, s, c)
+        return self.to_out[0](o)
+
+
+class GEGLU(nn.Module):
+    def __init__(self, dim: int, inner: int):
+        super().__init__()
+        self.proj = nn.Linear(dim, inner * 2)
+
+    def forward(self, x):
+        h, gate = self.proj(x).chunk(2, dim=-1)
+        return h * F.gelu(gate)  # exact erf GELU
+
+
+class FeedForward(nn.Module):
+    def __init__(self, dim: int):
+        super().__init__()
+        self.net = nn.ModuleList([GEGLU(dim, dim * 4), nn.Dropout(0.0), nn.Linear(dim * 4, dim)])
+
+    def forward(self, x):
+        for m in self.net:
+            x = m(x)
+        return x
+
+
+class BasicTransformerBlock(nn.Module):
+    def __init__(self, dim: int, heads: int, context_dim: int):
+        super().__init__()
+        self.attn1 = CrossAttention(dim, None, heads)
+        self.ff = FeedForward(dim)
+        self.attn2 = CrossAttention(dim, context_dim, heads)
+        self.norm1 = nn.LayerNorm(dim)
+        self.norm2 = nn.LayerNorm(dim)
+        self.norm3 = nn.LayerNorm(dim)
+
+    def forward(self, x, context):
+        x = self.attn1(self.norm1(x)) + x
+        x = self.attn2(self.norm2(x), context) + x
+        x = self.ff(self.norm3(x)) + x
+        return x
+
+
+class Transformer2DModel(nn.Module):
+    """`SpatialTransformer` in diffusers 0.7.2 (same math / same keys)."""
+
+    def __init__(self, ch: int, heads: int, context_dim: int, groups: int = 32):
+        super().__init__()
+        self.norm = nn.GroupNorm(groups, ch, eps=1e-6, affine=True)
+        self.proj_in = nn.Conv2d(ch, ch, 1)
+        self.transformer_blocks = nn.ModuleList([BasicTransformerBlock(ch, heads, context_dim)])
+        self.proj_out = nn.Conv2d(ch, ch, 1)
+
+    def forward(self, x, context):
+        b, c, hh, ww = x.shape
+        r = x
+        x = self.proj_in(self.norm(x))
+        x = x.permute(0, 2, 3, 1).reshape(b, hh * ww, c)
+        for blk in self.transformer_blocks:
+            x = blk(x, context)
+        x = x.reshape(b, hh, ww, c).permute(0, 3, 1, 2)
+        return self.proj_out(x) + r
+
+
+class Downsample2D(nn.Module):
+    def __init__(self, ch: int):
+        super().__init__()
+        self.conv = nn.Conv2d(ch, ch, 3, stride=2, padding=1)
+
+    def forward(self, x):
+        return self.conv(x)
+
+
+class Upsample2D(nn.Module):
+    def __init__(self, ch: int):
+        super().__init__()
+        self.conv = nn.Conv2d(ch, ch, 3, padding=1)
+
+    def forward(self, x):
+        return self.conv(F.interpolate(x, scale_factor=2.0, mode="nearest"))
+
+
+class DownBlock(nn.Module):
+    def __init__(self, cin, cout, temb_ch, layers, attn: bool, heads, ctx_dim, add_down: bool):
+        super().__init__()
+        self.resnets = nn.ModuleList([ResnetBlock2D(cin if i == 0 else cout, cout, temb_ch) for i in range(layers)])
+        if attn:
+            self.attentions = nn.ModuleList([Transformer2DModel(cout, heads, ctx_dim) for _ in range(layers)])
+        else:
+            self.attentions = None
+        self.downsamplers = nn.ModuleList([Downsample2D(cout)]) if add_down else None
+
+    def forward(self, x, temb, ctx):
+        outs = []
+        for i, res in enumerate(self.resnets):
+            x = res(x, temb)
+            if self.attentions is not None:
+                x = self.attentions[i](x, ctx)
+            outs.append(x)
+        if self.downsamplers is not None:
+            x = self.downsamplers[0](x)
+            outs.append(x)
+        return x, outs
+
+
+class MidBlock(nn.Module):
+    def __init__(self, ch, temb_ch, heads, ctx_dim):
+        super().__init__()
+        self.resnets = nn.ModuleList([ResnetBlock2D(ch, ch, temb_ch), ResnetBlock2D(ch, ch, temb_ch)])
+        self.attentions = nn.ModuleList([Transformer2DModel(ch, heads, ctx_dim)])
+
+    def forward(self, x, temb, ctx):
+        x = self.resnets[0](x, temb)
+        x = self.attentions[0](x, ctx)
+        return self.resnets[1](x, temb)
+
+
+class UpBlock(nn.Module):
+    def __init__(self, cin, cout, prev, temb_ch, layers, attn: bool, heads, ctx_dim, add_up: bool):
+        super().__init__()
+        res = []
+        for i in range(layers):
+            skip = cin if i == layers - 1 else cout
+            rin = prev if i == 0 else cout
+            res.append(ResnetBlock2D(rin + skip, cout, temb_ch))
+        self.resnets = nn.ModuleList(res)
+        if attn:
+            self.attentions = nn.ModuleList([Transformer2DModel(cout, heads, ctx_dim) for _ in range(layers)])
+        else:
+            self.attentions = None
+        self.upsamplers = nn.ModuleList([Upsample2D(cout)]) if add_up else None
+
+    def forward(self, x, skips, temb, ctx):
+        for i, res in enumerate(self.resnets):
+            x = torch.cat([x, skips.pop()], dim=1)
+            x = res(x, temb)
+            if self.attentions is not None:
+                x = self.attentions[i](x, ctx)
+        if self.upsamplers is not None:
+            x = self.upsamplers[0](x)
+        return x
+
+
+class UNet2DConditionModelRef(nn.Module):
+    """fp32 CPU oracle of diffusers.UNet2DConditionModel (SD v1.x config)."""
+
+    def __init__(self, **overrides):
+        super().__init__()
+        cfg = dict(SD15_CONFIG)
+        cfg.update(overrides)
+        self.config = SimpleNamespace(**cfg)
+        boc = cfg["block_out_channels"]
+        temb_ch = boc[0] * 4
+        heads = cfg["attention_head_dim"]
+        ctx_dim = cfg["cross_attention_dim"]
+        L = cfg["layers_per_block"]
+        self.in_channels = cfg["in_channels"]
+
+        self.conv_in = nn.Conv2d(cfg["in_channels"], boc[0], 3, padding=1)
+        self.time_embedding = TimestepEmbedding(boc[0], temb_ch)
+
+        downs = []
+        out_ch = boc[0]
+        for i, typ in enumerate(cfg["down_block_types"]):
+            in_ch, out_ch = out_ch, boc[i]
+            downs.append(DownBlock(in_ch, out_ch, temb_ch, L, typ.startswith("CrossAttn"), heads, ctx_dim,
+                                   add_down=(i != len(boc) - 1)))
+        self.down_blocks = nn.ModuleList(downs)
+        self.mid_block = MidBlock(boc[-1], temb_ch, heads, ctx_dim)
+
+        ups = []
+        rev = list(reversed(boc))
+        out_ch = rev[0]
+        for i, typ in enumerate(cfg["up_block_types"]):
+            prev, out_ch = out_ch, rev[i]
+            in_ch = rev[min(i + 1, len(boc) - 1)]
+            ups.append(UpBlock(in_ch, out_ch, prev, temb_ch, L + 1, typ.startswith("CrossAttn"), heads, ctx_dim,
+                               add_up=(i != len(boc) - 1)))
+        self.up_blocks = nn.ModuleList(ups)
+
+        self.conv_norm_out = nn.GroupNorm(cfg["norm_num_groups"], boc[0], eps=cfg["norm_eps"])
+        self.conv_out = nn.Conv2d(boc[0], cfg["out_channels"], 3, padding=1)
+
+    def forward(self, sample, timestep, encoder_hidden_states, return_dict: bool = True):
+        if not torch.is_tensor(timestep):
+            timestep = torch.tensor([timestep], dtype=torch.long, device=sample.device)
+        elif timestep.dim() == 0:
+            timestep = timestep[None].to(sample.device)
+        timestep = timestep.expand(sample.shape[0])
+        cfg = self.config
+        t_emb = timestep_embedding(timestep, cfg.block_out_channels[0], cfg.flip_sin_to_cos, cfg.freq_shift)
+        emb = self.time_embedding(t_emb.to(sample.dtype))
+
+        x = self.conv_in(sample)
+        skips = [x]
+        for blk in self.down_blocks:
+            x, outs = blk(x, emb, encoder_hidden_states)
+            skips.extend(outs)
+        x = self.mid_block(x, emb, encoder_hidden_states)
+        for blk in self.up_blocks:
+            x = blk(x, skips, emb, encoder_hidden_states)
+        x = self.conv_out(F.silu(self.conv_norm_out(x)))
+        if not return_dict:
+            return (x,)
+        return SimpleNamespace(sample=x)
+
+
+def make_oracle_unet(seed: int = 0, sharpen_attention: float = 4.0, **overrides) -> UNet2DConditionModelRef:
+    """Seeded random-init oracle UNet: default torch init, then to_q / to_k scaled by
+    `sharpen_attention` so the softmax is not near-uniform (a near-uniform softmax would make the
+    attention parity check vacuous).  The recipe and seed are part of every parity test."""
+    g = torch.random.get_rng_state()
+    torch.manual_seed(seed)
+    m = UNet2DConditionModelRef(**overrides)
+    with torch.no_grad():
+        for name, p in m.named_parameters():
+            if name.endswith("to_q.weight") or name.endswith("to_k.weight"):
+                p.mul_(sharpen_attention)
+    torch.random.set_rng_state(g)
+    return m.eval()
+
+
+# A reduced-width variant (same topology, fewer channels) for fast CPU-side tests.
+TINY_OVERRIDES = dict(block_out_channels=(64, 128, 128, 128), cross_attention_dim=64, attention_head_dim=2)

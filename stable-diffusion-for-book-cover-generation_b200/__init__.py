@@ -1,0 +1,21 @@
+"""b200sd -- B200-native (sm_100a) SD v1.x UNet denoise hot path behind the diffusers class surface.
+
+Public surface (mirrors what finetune_sd.py / inference.py / StableDiffusionPipeline touch):
+    UNet2DConditionModel, DDIMScheduler, PNDMScheduler, DDPMScheduler, denoise_loop, mse_loss
+"""
+__version__ = "0.1.0"
+
+
+def __getattr__(name):  # lazy: importing the package must not require torch.cuda or the .so
+    import importlib
+    table = {
+        "UNet2DConditionModel": "b200sd.unet",
+        "DDIMScheduler": "b200sd.schedulers",
+        "PNDMScheduler": "b200sd.schedulers",
+        "DDPMScheduler": "b200sd.schedulers",
+        "denoise_loop": "b200sd.pipeline",
+        "mse_loss": "b200sd.ops",
+    }
+    if name in table:
+        return getattr(importlib.import_module(table[name]), name)
+    raise AttributeError(name)

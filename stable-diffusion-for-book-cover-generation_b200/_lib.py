@@ -1,0 +1,80 @@
+"""ctypes binding of libb200sd.so (include/b200sd.h).  There is NO fallback: a missing library or a
+failing call raises -- the product path never routes through PyTorch eager or the oracle."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200sd.so")
+
+_lib = None
+
+
+class B200SDError(RuntimeError):
+    pass
+
+
+class GemmArgs(C.Structure):
+    _fields_ = [
+        ("a0", C.c_void_p), ("a1", C.c_void_p), ("w", C.c_void_p), ("bias", C.c_void_p), ("rowbias", C.c_void_p),
+        ("residual", C.c_void_p), ("out", C.c_void_p),
+        ("M", C.c_int), ("N", C.c_int), ("K", C.c_int), ("C0", C.c_int), ("C1", C.c_int),
+        ("lda0", C.c_int), ("lda1", C.c_int), ("ldc", C.c_int), ("ldr", C.c_int), ("conv_taps", C.c_int),
+        ("batch", C.c_int), ("H", C.c_int), ("W", C.c_int), ("rows_per_image", C.c_int), ("epilogue", C.c_int),
+        ("out_dtype", C.c_int), ("block_n", C.c_int), ("split_k", C.c_int),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+    ]
+
+
+_vp, _i, _i64, _f, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_size_t
+
+# name -> (restype, argtypes); must list EVERY symbol include/b200sd.h declares (tests check this)
+SIGNATURES = {
+    "b200sd_last_error": (C.c_char_p, []),
+    "b200sd_version": (_i, []),
+    "b200sd_launch_count": (_i64, []),
+    "b200sd_cfg_ddim_step": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _f, _f, _f, _f, _f, _i, _i, _vp]),
+    "b200sd_cfg_plms_step": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, C.POINTER(C.c_float), _i64, _f, _f,
+                                  _f, _i, _i, _vp]),
+    "b200sd_add_noise": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i64, _i, _i, _vp]),
+    "b200sd_mse_workspace_floats": (_i, []),
+    "b200sd_mse_loss_fwd": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i, _vp]),
+    "b200sd_mse_loss_bwd": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i, _vp]),
+    "b200sd_timestep_embedding": (_i, [_vp, _vp, _i, _i, _vp]),
+    "b200sd_small_linear": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "b200sd_gemm_workspace_bytes": (_sz, []),
+    "b200sd_geglu_tile": (_i, [_i]),
+    "b200sd_gemm": (_i, [C.POINTER(GemmArgs), _vp]),
+    "b200sd_conv_in": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "b200sd_conv_out": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "b200sd_groupnorm_silu": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _i, _vp]),
+    "b200sd_groupnorm_workspace_floats": (_i, [_i]),
+    "b200sd_layernorm": (_i, [_vp, _vp, _vp, _vp, _i, _i, _f, _vp]),
+    "b200sd_attention": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _vp]),
+    "b200sd_upsample2x": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "b200sd_im2col_s2": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+}
+
+
+def lib() -> C.CDLL:
+    """Load (once) and return the CUDA library; raise loudly if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise B200SDError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(b200sd has no CPU / eager fallback)")
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = lib().b200sd_last_error().decode("utf-8", "replace")
+        raise B200SDError(f"{what or 'b200sd call'} failed (code {rc}): {msg}")

@@ -1,0 +1,296 @@
+// b200sd -- the small kernels around the GEMMs: timestep embedding, time-MLP linears, the two
+// degenerate convs at the ends of the UNet (4 -> 320 and 320 -> 4 channels), nearest x2 upsample
+// and the stride-2 im2col of the three Downsample2D convs.
+#include <atomic>
+
+#include "common.cuh"
+
+extern std::atomic<long long> g_b200sd_launches;
+#define COUNT_LAUNCH() g_b200sd_launches.fetch_add(1, std::memory_order_relaxed)
+
+namespace {
+
+// ---- sinusoidal timestep embedding (fp32, accurate sin/cos: arguments reach ~1000 rad) -----------
+__global__ void temb_kernel(const float* __restrict__ t, float* __restrict__ out, int batch, int dim) {
+    const int half = dim / 2;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= batch * half) return;
+    const int b = i / half, j = i % half;
+    const float expo = (-9.210340371976184f * (float)j) / (float)half;  // -ln(10000) * j / half
+    const float arg = t[b] * expf(expo);
+    out[(size_t)b * dim + j] = cosf(arg);         // flip_sin_to_cos = True: cos first
+    out[(size_t)b * dim + half + j] = sinf(arg);
+}
+
+// ---- small-M linear: one warp per output feature, up to 8 batch rows at a time --------------------
+constexpr int kSlRows = 8;
+__global__ void __launch_bounds__(256) small_linear_kernel(const float* __restrict__ in, const bf16* __restrict__ w,
+                                                           const float* __restrict__ bias, float* __restrict__ out,
+                                                           int batch, int N, int K, int silu_in, int silu_out) {
+    extern __shared__ float s_in[];  // [kSlRows][K]
+    const int b0 = blockIdx.y * kSlRows;
+    const int nb = min(kSlRows, batch - b0);
+    for (int i = threadIdx.x; i < kSlRows * K; i += blockDim.x) {
+        const int r = i / K, k = i % K;
+        float v = 0.f;
+        if (r < nb) {
+            v = in[(size_t)(b0 + r) * K + k];
+            if (silu_in) v = v / (1.0f + expf(-v));
+        }
+        s_in[i] = v;
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warps_total = gridDim.x * 8;
+    for (int n = blockIdx.x * 8 + warp; n < N; n += warps_total) {
+        float acc[kSlRows];
+#pragma unroll
+        for (int r = 0; r < kSlRows; ++r) acc[r] = 0.f;
+        const uint4* wr = reinterpret_cast<const uint4*>(w + (size_t)n * K);
+        for (int v8 = lane; v8 < K / 8; v8 += 32) {
+            const uint4 u = __ldg(wr + v8);
+            float wf[8];
+            float2 f;
+            f = unpack_bf16x2(u.x); wf[0] = f.x; wf[1] = f.y;
+            f = unpack_bf16x2(u.y); wf[2] = f.x; wf[3] = f.y;
+            f = unpack_bf16x2(u.z); wf[4] = f.x; wf[5] = f.y;
+            f = unpack_bf16x2(u.w); wf[6] = f.x; wf[7] = f.y;
+#pragma unroll
+            for (int r = 0; r < kSlRows; ++r) {
+                const float* xr = s_in + r * K + v8 * 8;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[r] += wf[j] * xr[j];
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < kSlRows; ++r) acc[r] = warp_sum(acc[r]);
+        if (lane == 0) {
+            const float bv = bias ? bias[n] : 0.f;
+            for (int r = 0; r < nb; ++r) {
+                float v = acc[r] + bv;
+                if (silu_out) v = v / (1.0f + expf(-v));
+                out[(size_t)(b0 + r) * N + n] = v;
+            }
+        }
+    }
+}
+
+// ---- conv_in: NCHW fp32 (Cin = 4) -> NHWC bf16; thread = output-channel pair, block = 32 pixels ---
+constexpr int kCinPix = 32;
+__global__ void conv_in_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                               bf16* __restrict__ out, int batch, int Cout, int H, int W) {
+    constexpr int Cin = 4;
+    __shared__ float patch[kCinPix][9 * Cin];
+    const int hw = H * W;
+    const int pix0 = blockIdx.x * kCinPix;
+    const int total = batch * hw;
+    for (int i = threadIdx.x; i < kCinPix * 9 * Cin; i += blockDim.x) {
+        const int pl = i / (9 * Cin), r = i % (9 * Cin);
+        const int tap = r / Cin, c = r % Cin;
+        const int pix = pix0 + pl;
+        float v = 0.f;
+        if (pix < total) {
+            const int b = pix / hw, rem = pix % hw;
+            const int y = rem / W + tap / 3 - 1, xx = rem % W + tap % 3 - 1;
+            if (y >= 0 && y < H && xx >= 0 && xx < W) v = x[((size_t)(b * Cin + c) * H + y) * W + xx];
+        }
+        patch[pl][r] = v;
+    }
+    __syncthreads();
+    for (int co2 = threadIdx.x; co2 < Cout / 2; co2 += blockDim.x) {
+        const int co = co2 * 2;
+        float w0[9 * Cin], w1[9 * Cin];
+#pragma unroll
+        for (int r = 0; r < 9 * Cin; ++r) {  // packed [Cout][tap][Cin]
+            w0[r] = __ldg(w + (size_t)co * 9 * Cin + r);
+            w1[r] = __ldg(w + (size_t)(co + 1) * 9 * Cin + r);
+        }
+        const float b0 = bias[co], b1 = bias[co + 1];
+        for (int pl = 0; pl < kCinPix; ++pl) {
+            const int pix = pix0 + pl;
+            if (pix >= total) break;
+            float a0 = b0, a1 = b1;
+#pragma unroll
+            for (int r = 0; r < 9 * Cin; ++r) {
+                const float v = patch[pl][r];
+                a0 += w0[r] * v;
+                a1 += w1[r] * v;
+            }
+            *reinterpret_cast<uint32_t*>(out + (size_t)pix * Cout + co) = pack_bf16x2(a0, a1);
+        }
+    }
+}
+
+// ---- conv_out: NHWC bf16 (Cin = 320) -> NCHW fp32 (Cout = 4); warp per pixel, lanes over channels -
+constexpr int kCoutMax = 4;
+__global__ void __launch_bounds__(256) conv_out_kernel(const bf16* __restrict__ x, const float* __restrict__ w,
+                                                       const float* __restrict__ bias, float* __restrict__ out,
+                                                       int batch, int Cin, int Cout, int H, int W, int pix_per_warp) {
+    extern __shared__ float s_w[];  // packed [Cout][tap][Cin]
+    for (int i = threadIdx.x; i < Cout * 9 * Cin; i += blockDim.x) s_w[i] = __ldg(w + i);
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int hw = H * W, total = batch * hw;
+    const int first = (blockIdx.x * 8 + warp) * pix_per_warp;
+    for (int pix = first; pix < min(first + pix_per_warp, total); ++pix) {
+        const int b = pix / hw, rem = pix % hw, y = rem / W, xx = rem % W;
+        float acc[kCoutMax] = {0.f, 0.f, 0.f, 0.f};
+        for (int tap = 0; tap < 9; ++tap) {
+            const int yy = y + tap / 3 - 1, xs = xx + tap % 3 - 1;
+            if (yy < 0 || yy >= H || xs < 0 || xs >= W) continue;
+            const uint32_t* src = reinterpret_cast<const uint32_t*>(x + ((size_t)(b * H + yy) * W + xs) * Cin);
+            for (int c2 = lane; c2 < Cin / 2; c2 += 32) {
+                const float2 f = unpack_bf16x2(__ldg(src + c2));
+#pragma unroll
+                for (int co = 0; co < kCoutMax; ++co) {
+                    if (co < Cout) {
+                        const float* wp = s_w + (size_t)(co * 9 + tap) * Cin + 2 * c2;
+                        acc[co] += f.x * wp[0] + f.y * wp[1];
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int co = 0; co < kCoutMax; ++co) acc[co] = warp_sum(acc[co]);
+        if (lane == 0)
+            for (int co = 0; co < Cout; ++co) out[((size_t)(b * Cout + co) * H + y) * W + xx] = acc[co] + bias[co];
+    }
+}
+
+// ---- nearest x2 upsample, NHWC, 16-byte vectors ----------------------------------------------------
+__global__ void upsample2x_kernel(const uint4* __restrict__ x, uint4* __restrict__ out, int batch, int H, int W, int C8) {
+    const int64_t total = (int64_t)batch * 4 * H * W * C8;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int c = (int)(i % C8);
+        int64_t p = i / C8;
+        const int ox = (int)(p % (2 * W));
+        p /= (2 * W);
+        const int oy = (int)(p % (2 * H));
+        const int b = (int)(p / (2 * H));
+        out[i] = __ldg(x + ((int64_t)(b * H + (oy >> 1)) * W + (ox >> 1)) * C8 + c);
+    }
+}
+
+// ---- im2col for the stride-2 pad-1 3x3 Downsample2D conv --------------------------------------------
+__global__ void im2col_s2_kernel(const uint4* __restrict__ x, uint4* __restrict__ out, int batch, int H, int W, int C8) {
+    const int OH = H / 2, OW = W / 2;
+    const int64_t total = (int64_t)batch * OH * OW * 9 * C8;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int c = (int)(i % C8);
+        int64_t p = i / C8;
+        const int tap = (int)(p % 9);
+        p /= 9;
+        const int ox = (int)(p % OW);
+        p /= OW;
+        const int oy = (int)(p % OH);
+        const int b = (int)(p / OH);
+        const int y = 2 * oy + tap / 3 - 1, xx = 2 * ox + tap % 3 - 1;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (y >= 0 && y < H && xx >= 0 && xx < W) v = __ldg(x + ((int64_t)(b * H + y) * W + xx) * C8 + c);
+        out[i] = v;
+    }
+}
+
+int ew_grid(int64_t total, int threads) {
+    int64_t blocks = (total + threads - 1) / threads;
+    const int64_t cap = (int64_t)b200sd_num_sms() * 8;
+    if (blocks > cap) blocks = cap;
+    return (int)(blocks < 1 ? 1 : blocks);
+}
+
+}  // namespace
+
+extern "C" int b200sd_timestep_embedding(const float* timesteps, float* out, int batch, int dim,
+                                         b200sd_stream_t stream) {
+    B200SD_REQUIRE(timesteps && out, "timestep_embedding: null pointer");
+    B200SD_REQUIRE(batch > 0 && dim > 0 && dim % 2 == 0, "timestep_embedding: bad sizes");
+    const int total = batch * dim / 2;
+    temb_kernel<<<ceil_div(total, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(timesteps, out, batch, dim);
+    COUNT_LAUNCH();
+    B200SD_LAUNCH_CHECK();
+    return B200SD_OK;
+}
+
+extern "C" int b200sd_small_linear(const float* in, const void* w_bf16, const float* bias, float* out, int batch, int N,
+                                   int K, int silu_in, int silu_out, b200sd_stream_t stream) {
+    B200SD_REQUIRE(in && w_bf16 && out, "small_linear: null pointer");
+    B200SD_REQUIRE(batch > 0 && N > 0 && K > 0 && K % 8 == 0, "small_linear: bad sizes (K must be a multiple of 8)");
+    const size_t smem = (size_t)kSlRows * K * sizeof(float);
+    B200SD_REQUIRE(smem <= 96 * 1024, "small_linear: K=%d too large", K);
+    static bool configured = false;
+    if (!configured) {
+        B200SD_CUDA(cudaFuncSetAttribute(small_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        configured = true;
+    }
+    int gx = ceil_div(N, 8);
+    const int cap = b200sd_num_sms() * 4;
+    if (gx > cap) gx = cap;
+    dim3 grid(gx, ceil_div(batch, kSlRows));
+    small_linear_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(in, static_cast<const bf16*>(w_bf16), bias,
+                                                                               out, batch, N, K, silu_in, silu_out);
+    COUNT_LAUNCH();
+    B200SD_LAUNCH_CHECK();
+    return B200SD_OK;
+}
+
+extern "C" int b200sd_conv_in(const float* x_nchw, const float* w, const float* bias, void* out_nhwc, int batch, int Cin,
+                              int Cout, int H, int W, b200sd_stream_t stream) {
+    B200SD_REQUIRE(x_nchw && w && bias && out_nhwc, "conv_in: null pointer");
+    B200SD_REQUIRE(Cin == 4, "conv_in: only Cin == 4 (SD latent) is supported, got %d", Cin);
+    B200SD_REQUIRE(Cout % 2 == 0 && batch > 0 && H > 0 && W > 0, "conv_in: bad sizes");
+    const int total = batch * H * W;
+    int threads = Cout / 2;
+    if (threads > 256) threads = 256;
+    threads = ceil_div(threads, 32) * 32;
+    conv_in_kernel<<<ceil_div(total, kCinPix), threads, 0, static_cast<cudaStream_t>(stream)>>>(
+        x_nchw, w, bias, static_cast<bf16*>(out_nhwc), batch, Cout, H, W);
+    COUNT_LAUNCH();
+    B200SD_LAUNCH_CHECK();
+    return B200SD_OK;
+}
+
+extern "C" int b200sd_conv_out(const void* x_nhwc, const float* w, const float* bias, float* out_nchw, int batch, int Cin,
+                               int Cout, int H, int W, b200sd_stream_t stream) {
+    B200SD_REQUIRE(x_nhwc && w && bias && out_nchw, "conv_out: null pointer");
+    B200SD_REQUIRE(Cout >= 1 && Cout <= kCoutMax && Cin % 2 == 0, "conv_out: Cout must be <= 4 and Cin even");
+    const size_t smem = (size_t)Cout * 9 * Cin * sizeof(float);
+    B200SD_REQUIRE(smem <= 96 * 1024, "conv_out: Cin=%d too large", Cin);
+    static bool configured = false;
+    if (!configured) {
+        B200SD_CUDA(cudaFuncSetAttribute(conv_out_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        configured = true;
+    }
+    const int total = batch * H * W;
+    int ppw = ceil_div(total, b200sd_num_sms() * 2 * 8);
+    if (ppw < 4) ppw = 4;
+    const int blocks = ceil_div(total, ppw * 8);
+    conv_out_kernel<<<blocks, 256, smem, static_cast<cudaStream_t>(stream)>>>(static_cast<const bf16*>(x_nhwc), w, bias,
+                                                                             out_nchw, batch, Cin, Cout, H, W, ppw);
+    COUNT_LAUNCH();
+    B200SD_LAUNCH_CHECK();
+    return B200SD_OK;
+}
+
+extern "C" int b200sd_upsample2x(const void* x, void* out, int batch, int H, int W, int C, b200sd_stream_t stream) {
+    B200SD_REQUIRE(x && out, "upsample2x: null pointer");
+    B200SD_REQUIRE(C % 8 == 0 && batch > 0 && H > 0 && W > 0, "upsample2x: bad sizes");
+    const int64_t total = (int64_t)batch * 4 * H * W * (C / 8);
+    upsample2x_kernel<<<ew_grid(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const uint4*>(x), static_cast<uint4*>(out), batch, H, W, C / 8);
+    COUNT_LAUNCH();
+    B200SD_LAUNCH_CHECK();
+    return B200SD_OK;
+}
+
+extern "C" int b200sd_im2col_s2(const void* x, void* out, int batch, int H, int W, int C, b200sd_stream_t stream) {
+    B200SD_REQUIRE(x && out, "im2col_s2: null pointer");
+    B200SD_REQUIRE(C % 8 == 0 && batch > 0 && H % 2 == 0 && W % 2 == 0, "im2col_s2: bad sizes");
+    const int64_t total = (int64_t)batch * (H / 2) * (W / 2) * 9 * (C / 8);
+    im2col_s2_kernel<<<ew_grid(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const uint4*>(x), static_cast<uint4*>(out), batch, H, W, C / 8);
+    COUNT_LAUNCH();
+    B200SD_LAUNCH_CHECK();
+    return B200SD_OK;
+}

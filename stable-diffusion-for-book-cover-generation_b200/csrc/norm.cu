@@ -1,0 +1,209 @@
+// b200sd -- GroupNorm(+SiLU, + fused channel concat) and LayerNorm over NHWC bf16 activations.
+// Both are bandwidth-bound passes over L2-resident activations (<= 21 MB at CFG batch 2).
+#include <atomic>
+
+#include "common.cuh"
+
+extern std::atomic<long long> g_b200sd_launches;
+#define COUNT_LAUNCH() g_b200sd_launches.fetch_add(1, std::memory_order_relaxed)
+
+namespace {
+
+constexpr int kGnThreads = 256;
+constexpr int kMaxSlabs = 64;
+constexpr int kMaxGroups = 32;
+
+// ---- pass 1: per-(image, slab, group) partial sum / sum of squares -----------------------------
+// grid (slabs, batch); thread owns channel PAIRS (a pair never straddles a group: cpg is even).
+__global__ void __launch_bounds__(kGnThreads) gn_stats_kernel(const bf16* __restrict__ x0, const bf16* __restrict__ x1,
+                                                              int C0, int C1, float* __restrict__ partial, int hw,
+                                                              int groups, int pix_per_slab) {
+    __shared__ float s_sum[kMaxGroups], s_sq[kMaxGroups];
+    const int C = C0 + C1;
+    const int cpg = C / groups;
+    const int b = blockIdx.y, slab = blockIdx.x;
+    if (threadIdx.x < kMaxGroups) { s_sum[threadIdx.x] = 0.f; s_sq[threadIdx.x] = 0.f; }
+    __syncthreads();
+    const int p_begin = slab * pix_per_slab;
+    const int p_end = min(p_begin + pix_per_slab, hw);
+    for (int c2 = threadIdx.x; c2 < C / 2; c2 += blockDim.x) {
+        const int c = 2 * c2;
+        const bf16* src;
+        int pitch, cc;
+        if (c < C0) { src = x0; pitch = C0; cc = c; }
+        else { src = x1; pitch = C1; cc = c - C0; }
+        src += (size_t)b * hw * pitch + cc;
+        float s = 0.f, ss = 0.f;
+#pragma unroll 4
+        for (int p = p_begin; p < p_end; ++p) {
+            float2 f = unpack_bf16x2(__ldg(reinterpret_cast<const uint32_t*>(src + (size_t)p * pitch)));
+            s += f.x + f.y;
+            ss += f.x * f.x + f.y * f.y;
+        }
+        const int g = c / cpg;
+        atomicAdd(&s_sum[g], s);
+        atomicAdd(&s_sq[g], ss);
+    }
+    __syncthreads();
+    if (threadIdx.x < groups) {
+        float* dst = partial + (((size_t)b * gridDim.x + slab) * groups + threadIdx.x) * 2;
+        dst[0] = s_sum[threadIdx.x];
+        dst[1] = s_sq[threadIdx.x];
+    }
+}
+
+// ---- pass 2: normalise + affine (+ SiLU), write the concatenated bf16 tensor --------------------
+__global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const bf16* __restrict__ x0, const bf16* __restrict__ x1,
+                                                              int C0, int C1, const float* __restrict__ gamma,
+                                                              const float* __restrict__ beta, bf16* __restrict__ out,
+                                                              const float* __restrict__ partial, int slabs, int hw,
+                                                              int groups, float eps, int silu, int pix_per_block) {
+    extern __shared__ float2 s_ab[];  // per-channel (scale, shift)
+    __shared__ float s_mean[kMaxGroups], s_rstd[kMaxGroups];
+    const int C = C0 + C1;
+    const int cpg = C / groups;
+    const int b = blockIdx.y;
+    if (threadIdx.x < groups) {
+        double s = 0.0, ss = 0.0;
+        for (int i = 0; i < slabs; ++i) {
+            const float* src = partial + (((size_t)b * slabs + i) * groups + threadIdx.x) * 2;
+            s += (double)src[0];
+            ss += (double)src[1];
+        }
+        const double cnt = (double)hw * cpg;
+        const double mean = s / cnt;
+        double var = ss / cnt - mean * mean;
+        if (var < 0.0) var = 0.0;
+        s_mean[threadIdx.x] = (float)mean;
+        s_rstd[threadIdx.x] = (float)(1.0 / sqrt(var + (double)eps));
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const int g = c / cpg;
+        const float a = s_rstd[g] * __ldg(gamma + c);
+        s_ab[c] = make_float2(a, __ldg(beta + c) - s_mean[g] * a);
+    }
+    __syncthreads();
+    const int vec_per_pix = C / 8;
+    const int p_begin = blockIdx.x * pix_per_block;
+    const int p_end = min(p_begin + pix_per_block, hw);
+    const int total = (p_end - p_begin) * vec_per_pix;
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+        const int p = p_begin + i / vec_per_pix;
+        const int c = (i % vec_per_pix) * 8;
+        const bf16* src = (c < C0) ? x0 + ((size_t)b * hw + p) * C0 + c : x1 + ((size_t)b * hw + p) * C1 + (c - C0);
+        uint4 u = __ldg(reinterpret_cast<const uint4*>(src));
+        uint32_t w[4] = {u.x, u.y, u.z, u.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float2 f = unpack_bf16x2(w[j]);
+            const float2 ab0 = s_ab[c + 2 * j], ab1 = s_ab[c + 2 * j + 1];
+            float y0 = f.x * ab0.x + ab0.y;
+            float y1 = f.y * ab1.x + ab1.y;
+            if (silu) { y0 = silu_f(y0); y1 = silu_f(y1); }
+            o[j] = pack_bf16x2(y0, y1);
+        }
+        *reinterpret_cast<uint4*>(out + ((size_t)b * hw + p) * C + c) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+}
+
+// ---- LayerNorm: one warp per row, row held in registers (C <= 1280) ------------------------------
+template <int PAIRS_PER_LANE>
+__global__ void __launch_bounds__(256) layernorm_kernel(const bf16* __restrict__ x, const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, bf16* __restrict__ out,
+                                                        int rows, int C, float eps) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= rows) return;
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(x + (size_t)warp * C);
+    float2 v[PAIRS_PER_LANE];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < PAIRS_PER_LANE; ++i) {
+        v[i] = unpack_bf16x2(__ldg(src + lane + 32 * i));
+        s += v[i].x + v[i].y;
+    }
+    const float mean = warp_sum(s) / (float)C;
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < PAIRS_PER_LANE; ++i) {
+        const float a = v[i].x - mean, b = v[i].y - mean;
+        ss += a * a + b * b;
+    }
+    const float rstd = rsqrtf(warp_sum(ss) / (float)C + eps);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(out + (size_t)warp * C);
+    const float2* g2 = reinterpret_cast<const float2*>(gamma);
+    const float2* b2 = reinterpret_cast<const float2*>(beta);
+#pragma unroll
+    for (int i = 0; i < PAIRS_PER_LANE; ++i) {
+        const float2 g = __ldg(g2 + lane + 32 * i), bb = __ldg(b2 + lane + 32 * i);
+        dst[lane + 32 * i] = pack_bf16x2((v[i].x - mean) * rstd * g.x + bb.x, (v[i].y - mean) * rstd * g.y + bb.y);
+    }
+}
+
+}  // namespace
+
+extern "C" int b200sd_groupnorm_silu(const void* x0, const void* x1, int C0, int C1, const float* gamma,
+                                     const float* beta, void* out, float* stats_ws, int batch, int hw, int groups,
+                                     float eps, int silu, b200sd_stream_t stream) {
+    B200SD_REQUIRE(x0 && gamma && beta && out && stats_ws, "groupnorm: null pointer");
+    if (!x1) C1 = 0;
+    const int C = C0 + C1;
+    B200SD_REQUIRE(batch > 0 && hw > 0 && batch <= 65535, "groupnorm: bad batch/hw");
+    B200SD_REQUIRE(groups > 0 && groups <= kMaxGroups && C % groups == 0 && (C / groups) % 2 == 0,
+                   "groupnorm: C=%d groups=%d unsupported (channels per group must be even)", C, groups);
+    B200SD_REQUIRE(C0 % 8 == 0 && C1 % 8 == 0, "groupnorm: channel counts must be multiples of 8");
+    B200SD_REQUIRE(C * sizeof(float2) <= 48 * 1024, "groupnorm: C=%d too large", C);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    // slabs: enough blocks to fill the machine, but at least 32 pixels per slab
+    int slabs = ceil_div(b200sd_num_sms() * 2, batch);
+    if (slabs > kMaxSlabs) slabs = kMaxSlabs;
+    if (slabs > ceil_div(hw, 32)) slabs = ceil_div(hw, 32);
+    if (slabs < 1) slabs = 1;
+    const int pps = ceil_div(hw, slabs);
+    slabs = ceil_div(hw, pps);
+    gn_stats_kernel<<<dim3(slabs, batch), kGnThreads, 0, s>>>(static_cast<const bf16*>(x0), static_cast<const bf16*>(x1),
+                                                             C0, C1, stats_ws, hw, groups, pps);
+    COUNT_LAUNCH();
+    B200SD_LAUNCH_CHECK();
+    int blocks = ceil_div(b200sd_num_sms() * 4, batch);
+    int ppb = ceil_div(hw, blocks);
+    const int min_ppb = ceil_div(kGnThreads * 4, C / 8);  // >= 4 vectors per thread
+    if (ppb < min_ppb) ppb = min_ppb;
+    blocks = ceil_div(hw, ppb);
+    gn_apply_kernel<<<dim3(blocks, batch), kGnThreads, C * sizeof(float2), s>>>(
+        static_cast<const bf16*>(x0), static_cast<const bf16*>(x1), C0, C1, gamma, beta, static_cast<bf16*>(out), stats_ws,
+        slabs, hw, groups, eps, silu, ppb);
+    COUNT_LAUNCH();
+    B200SD_LAUNCH_CHECK();
+    return B200SD_OK;
+}
+
+// workspace floats needed by b200sd_groupnorm_silu for a given batch: 2 * batch * kMaxSlabs * kMaxGroups
+extern "C" int b200sd_groupnorm_workspace_floats(int batch) { return 2 * batch * kMaxSlabs * kMaxGroups; }
+
+extern "C" int b200sd_layernorm(const void* x, const float* gamma, const float* beta, void* out, int rows, int C,
+                                float eps, b200sd_stream_t stream) {
+    B200SD_REQUIRE(x && gamma && beta && out, "layernorm: null pointer");
+    B200SD_REQUIRE(rows > 0, "layernorm: rows must be positive");
+    B200SD_REQUIRE(C % 64 == 0 && C >= 64 && C <= 1280, "layernorm: C=%d unsupported (multiple of 64, <= 1280)", C);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int blocks = ceil_div(rows, 8);
+    const bf16* xi = static_cast<const bf16*>(x);
+    bf16* xo = static_cast<bf16*>(out);
+#define LN_CASE(P)                                                                                     \
+    case P:                                                                                            \
+        layernorm_kernel<P><<<blocks, 256, 0, s>>>(xi, gamma, beta, xo, rows, C, eps);                  \
+        break;
+    switch (C / 64) {
+        LN_CASE(1) LN_CASE(2) LN_CASE(3) LN_CASE(4) LN_CASE(5) LN_CASE(6) LN_CASE(7) LN_CASE(8) LN_CASE(9) LN_CASE(10)
+        LN_CASE(11) LN_CASE(12) LN_CASE(13) LN_CASE(14) LN_CASE(15) LN_CASE(16) LN_CASE(17) LN_CASE(18) LN_CASE(19) LN_CASE(20)
+        default:
+            B200SD_REQUIRE(false, "layernorm: C=%d unsupported", C);
+    }
+#undef LN_CASE
+    COUNT_LAUNCH();
+    B200SD_LAUNCH_CHECK();
+    return B200SD_OK;
+}

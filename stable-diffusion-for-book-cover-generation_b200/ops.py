@@ -1,0 +1,258 @@
+"""Thin torch-tensor wrappers over the C ABI (include/b200sd.h).  Tensors are torch-owned device
+memory; every call goes to libb200sd.so on torch's current CUDA stream.  No CPU / eager fallback:
+a non-CUDA tensor is an error."""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from ._lib import GemmArgs, B200SDError, check, lib
+
+F32, BF16 = 0, 1
+EPI_LINEAR, EPI_GEGLU = 0, 1
+
+
+def _dt(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.bfloat16:
+        return BF16
+    raise B200SDError(f"unsupported dtype {t.dtype} (float32 / bfloat16 only)")
+
+
+def _chk(*ts):
+    for t in ts:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise B200SDError("b200sd ops need CUDA tensors (there is no CPU fallback)")
+        if not t.is_contiguous():
+            raise B200SDError("b200sd ops need contiguous tensors")
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+_ws_cache: dict = {}
+
+
+def _workspace(key, nbytes, device, zero=True):
+    k = (key, device.index if device.index is not None else torch.cuda.current_device())
+    t = _ws_cache.get(k)
+    if t is None or t.numel() < nbytes:
+        t = (torch.zeros if zero else torch.empty)(nbytes, dtype=torch.uint8, device=device)
+        _ws_cache[k] = t
+    return t
+
+
+def launch_count() -> int:
+    return int(lib().b200sd_launch_count())
+
+
+# ---------------------------------------------------------------------------------------------
+# scheduler / loss elementwise
+# ---------------------------------------------------------------------------------------------
+def cfg_ddim_step(eps_u, eps_c, x, guidance, sa_t, sb_t, sa_p, sb_p, out=None, eps_out=None):
+    _chk(eps_u, eps_c, x, out, eps_out)
+    if out is None:
+        out = torch.empty_like(x)
+    if eps_c is not None and eps_c.shape != eps_u.shape:
+        raise ValueError("eps_u / eps_c shape mismatch")
+    if eps_u.numel() != x.numel():
+        raise ValueError(f"model_output {tuple(eps_u.shape)} and sample {tuple(x.shape)} sizes differ")
+    check(lib().b200sd_cfg_ddim_step(_p(eps_u), _p(eps_c), _p(x), _p(out), _p(eps_out), x.numel(), float(guidance),
+                                     float(sa_t), float(sb_t), float(sa_p), float(sb_p), _dt(eps_u), _dt(x), _stream()),
+          "cfg_ddim_step")
+    return out
+
+
+def cfg_plms_step(eps_u, eps_c, x, hist, weights, guidance, cx, ce, out=None, eps_out=None):
+    _chk(eps_u, eps_c, x, out, eps_out, *hist)
+    if out is None:
+        out = torch.empty_like(x)
+    if eps_u.numel() != x.numel():
+        raise ValueError(f"model_output {tuple(eps_u.shape)} and sample {tuple(x.shape)} sizes differ")
+    w = (C.c_float * 5)(*([float(v) for v in weights] + [0.0] * (5 - len(weights))))
+    hp = [_p(h) for h in hist] + [None] * (4 - len(hist))
+    check(lib().b200sd_cfg_plms_step(_p(eps_u), _p(eps_c), _p(x), _p(out), _p(eps_out), hp[0], hp[1], hp[2], hp[3],
+                                     len(hist), w, x.numel(), float(guidance), float(cx), float(ce), _dt(eps_u), _dt(x),
+                                     _stream()), "cfg_plms_step")
+    return out
+
+
+def add_noise(x0, noise, timesteps, sa_table, sb_table, out=None):
+    _chk(x0, noise, timesteps, sa_table, sb_table, out)
+    if x0.shape != noise.shape:
+        raise ValueError("original_samples / noise shape mismatch")
+    if timesteps.dtype != torch.int64 or timesteps.numel() != x0.shape[0]:
+        raise ValueError("timesteps must be int64 of shape (batch,)")
+    if noise.dtype != x0.dtype:
+        noise = noise.to(x0.dtype)
+    if out is None:
+        out = torch.empty_like(x0)
+    B = x0.shape[0]
+    check(lib().b200sd_add_noise(_p(x0), _p(noise), _p(timesteps), _p(sa_table), _p(sb_table), _p(out), B,
+                                 x0.numel() // max(B, 1), sa_table.numel(), _dt(x0), _stream()), "add_noise")
+    return out
+
+
+def mse_loss_fwd(pred, target):
+    _chk(pred, target)
+    if pred.shape != target.shape:
+        raise ValueError("pred / target shape mismatch")
+    ws = _workspace("mse", lib().b200sd_mse_workspace_floats() * 4, pred.device)
+    out = torch.empty(1, dtype=torch.float32, device=pred.device)
+    check(lib().b200sd_mse_loss_fwd(_p(pred), _p(target), _p(out), _p(ws), pred.numel(), _dt(pred), _dt(target),
+                                    _stream()), "mse_loss_fwd")
+    return out
+
+
+def mse_loss_bwd(pred, target, grad_loss):
+    _chk(pred, target, grad_loss)
+    g = torch.empty_like(pred)
+    gl = grad_loss.reshape(1).to(torch.float32)
+    check(lib().b200sd_mse_loss_bwd(_p(pred), _p(target), _p(gl), _p(g), pred.numel(), _dt(pred), _dt(target),
+                                    _stream()), "mse_loss_bwd")
+    return g
+
+
+class _MSELoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pred, target):
+        ctx.save_for_backward(pred, target)
+        return mse_loss_fwd(pred.contiguous(), target.contiguous()).reshape(())
+
+    @staticmethod
+    def backward(ctx, grad):
+        pred, target = ctx.saved_tensors
+        return mse_loss_bwd(pred.contiguous(), target.contiguous(), grad.contiguous()), None
+
+
+def mse_loss(pred, target):
+    """== F.mse_loss(pred, target, reduction="none").mean([1,2,3]).mean() (finetune_sd.py:483-484)."""
+    return _MSELoss.apply(pred, target)
+
+
+# ---------------------------------------------------------------------------------------------
+# UNet building blocks
+# ---------------------------------------------------------------------------------------------
+def timestep_embedding(t_f32, dim, out=None):
+    _chk(t_f32, out)
+    B = t_f32.numel()
+    if out is None:
+        out = torch.empty(B, dim, dtype=torch.float32, device=t_f32.device)
+    check(lib().b200sd_timestep_embedding(_p(t_f32), _p(out), B, dim, _stream()), "timestep_embedding")
+    return out
+
+
+def small_linear(x, w_bf16, bias, silu_in=False, silu_out=False, out=None):
+    _chk(x, w_bf16, bias, out)
+    B, K = x.shape
+    N = w_bf16.shape[0]
+    if out is None:
+        out = torch.empty(B, N, dtype=torch.float32, device=x.device)
+    check(lib().b200sd_small_linear(_p(x), _p(w_bf16), _p(bias), _p(out), B, N, K, int(silu_in), int(silu_out),
+                                    _stream()), "small_linear")
+    return out
+
+
+def gemm_workspace(device):
+    return _workspace("gemm", lib().b200sd_gemm_workspace_bytes(), device)
+
+
+def gemm(a0, w, out, *, a1=None, bias=None, rowbias=None, residual=None, conv=None, rows_per_image=0,
+         epilogue=EPI_LINEAR, block_n=0, split_k=0, M=None):
+    """out[M, N] = [a0 | a1] @ w^T (+bias +rowbias +residual); conv=(batch, H, W) -> 3x3 pad-1 conv (NHWC)."""
+    _chk(a0, a1, w, bias, rowbias, residual, out)
+    N, K = w.shape
+    C0 = a0.shape[-1]
+    C1 = a1.shape[-1] if a1 is not None else 0
+    if M is None:
+        M = a0.numel() // C0
+    ws = gemm_workspace(a0.device)
+    args = GemmArgs()
+    args.a0, args.a1, args.w = _p(a0), _p(a1), _p(w)
+    args.bias, args.rowbias, args.residual, args.out = _p(bias), _p(rowbias), _p(residual), _p(out)
+    args.M, args.N, args.K, args.C0, args.C1 = M, N, K, C0, C1
+    args.lda0, args.lda1 = C0, C1
+    args.ldc = out.shape[-1]
+    args.ldr = residual.shape[-1] if residual is not None else 0
+    if conv is not None:
+        args.conv_taps = 9
+        args.batch, args.H, args.W = conv
+    else:
+        args.conv_taps = 1
+    args.rows_per_image = rows_per_image
+    args.epilogue = epilogue
+    args.out_dtype = _dt(out)
+    args.block_n, args.split_k = block_n, split_k
+    args.workspace, args.workspace_bytes = _p(ws), ws.numel()
+    check(lib().b200sd_gemm(C.byref(args), _stream()), "gemm")
+    return out
+
+
+def geglu_tile(N):
+    return int(lib().b200sd_geglu_tile(N))
+
+
+def conv_in(x_nchw, w_packed, bias, out):
+    _chk(x_nchw, w_packed, bias, out)
+    B, Cin, H, W = x_nchw.shape
+    check(lib().b200sd_conv_in(_p(x_nchw), _p(w_packed), _p(bias), _p(out), B, Cin, w_packed.shape[0], H, W, _stream()),
+          "conv_in")
+    return out
+
+
+def conv_out(x_nhwc, w_packed, bias, out_nchw):
+    _chk(x_nhwc, w_packed, bias, out_nchw)
+    B, Cout, H, W = out_nchw.shape
+    check(lib().b200sd_conv_out(_p(x_nhwc), _p(w_packed), _p(bias), _p(out_nchw), B, x_nhwc.shape[-1], Cout, H, W,
+                                _stream()), "conv_out")
+    return out_nchw
+
+
+def groupnorm_silu(x0, x1, gamma, beta, out, batch, hw, groups=32, eps=1e-5, silu=True):
+    _chk(x0, x1, gamma, beta, out)
+    ws = _workspace("gn", lib().b200sd_groupnorm_workspace_floats(batch) * 4, x0.device, zero=False)
+    C0 = x0.shape[-1]
+    C1 = x1.shape[-1] if x1 is not None else 0
+    check(lib().b200sd_groupnorm_silu(_p(x0), _p(x1), C0, C1, _p(gamma), _p(beta), _p(out), _p(ws), batch, hw, groups,
+                                      float(eps), int(silu), _stream()), "groupnorm_silu")
+    return out
+
+
+def layernorm(x, gamma, beta, out, eps=1e-5):
+    _chk(x, gamma, beta, out)
+    Cc = x.shape[-1]
+    check(lib().b200sd_layernorm(_p(x), _p(gamma), _p(beta), _p(out), x.numel() // Cc, Cc, float(eps), _stream()),
+          "layernorm")
+    return out
+
+
+def attention(q, k, v, out, batch, heads, Sq, Skv, d, scale, ldq=None, ldk=None, ldv=None, ldo=None,
+              q_off=0, k_off=0, v_off=0):
+    """q/k/v may be column slices of wider row-major buffers: pass the buffer plus an element offset."""
+    _chk(q, k, v, out)
+    es = 2
+    check(lib().b200sd_attention(q.data_ptr() + q_off * es, k.data_ptr() + k_off * es, v.data_ptr() + v_off * es,
+                                 _p(out), batch, heads, Sq, Skv, d, ldq or q.shape[-1], ldk or k.shape[-1],
+                                 ldv or v.shape[-1], ldo or out.shape[-1], float(scale), _stream()), "attention")
+    return out
+
+
+def upsample2x(x, out, batch, H, W):
+    _chk(x, out)
+    check(lib().b200sd_upsample2x(_p(x), _p(out), batch, H, W, x.shape[-1], _stream()), "upsample2x")
+    return out
+
+
+def im2col_s2(x, out, batch, H, W):
+    _chk(x, out)
+    check(lib().b200sd_im2col_s2(_p(x), _p(out), batch, H, W, x.shape[-1], _stream()), "im2col_s2")
+    return out

@@ -1,0 +1,35 @@
+"""Host-side weight repacking from diffusers (OIHW / [out,in]) layouts into the kernels' layouts.
+Pure torch tensor reshuffles, done once at load time."""
+from __future__ import annotations
+
+import torch
+
+
+def pack_conv3x3(w: torch.Tensor) -> torch.Tensor:
+    """(Cout, Cin, 3, 3) -> bf16 [Cout][ky][kx][Cin] flattened to (Cout, 9*Cin): K index = tap*Cin + c."""
+    co, ci, kh, kw = w.shape
+    return w.permute(0, 2, 3, 1).reshape(co, kh * kw * ci).contiguous().to(torch.bfloat16)
+
+
+def pack_conv3x3_f32(w: torch.Tensor) -> torch.Tensor:
+    co, ci, kh, kw = w.shape
+    return w.permute(0, 2, 3, 1).reshape(co, kh * kw * ci).contiguous().float()
+
+
+def pack_linear(w: torch.Tensor) -> torch.Tensor:
+    """(out, in) or (out, in, 1, 1) -> bf16 (out, in)."""
+    return w.reshape(w.shape[0], -1).contiguous().to(torch.bfloat16)
+
+
+def pack_geglu(w: torch.Tensor, b: torch.Tensor, tile: int):
+    """GEGLU proj (8C, C): rows [0,4C) = value, [4C,8C) = gate.  Interleave per `tile` columns so each
+    output tile of the GEMM holds [tile/2 values | the matching tile/2 gates]."""
+    n2 = w.shape[0]
+    half = n2 // 2
+    h = tile // 2
+    assert half % h == 0
+    wv, wg = w[:half].reshape(half // h, h, -1), w[half:].reshape(half // h, h, -1)
+    bv, bg = b[:half].reshape(half // h, h), b[half:].reshape(half // h, h)
+    wp = torch.cat([wv, wg], dim=1).reshape(n2, -1).contiguous().to(torch.bfloat16)
+    bp = torch.cat([bv, bg], dim=1).reshape(n2).contiguous().float()
+    return wp, bp
