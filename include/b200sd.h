@@ -125,6 +125,7 @@ typedef struct b200sd_gemm_args {
     int C0, C1;            /* channels of a0 / a1 */
     int lda0, lda1;        /* row pitch (elements) of a0 / a1 in plain-GEMM mode */
     int ldc, ldr;
+    int ldrb;              /* row pitch of rowbias (0 = N) */
     int conv_taps;         /* 1 or 9 */
     int batch, H, W;       /* conv geometry (conv_taps == 9) */
     int rows_per_image;    /* for rowbias: image index = row / rows_per_image */

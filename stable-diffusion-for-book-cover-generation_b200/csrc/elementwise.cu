@@ -90,9 +90,8 @@ template <int EDT, int XDT>
 __global__ void __launch_bounds__(kThreads) cfg_ddim_kernel(const void* __restrict__ eps_u,
                                                             const void* __restrict__ eps_c,
                                                             const void* __restrict__ x, void* __restrict__ out,
-                                                            void* __restrict__ eps_out, int64_t n, DdimCoef c) {
+                                                            void* __restrict__ eps_out, int64_t n, int64_t nvec, DdimCoef c) {
     const bool cfg = eps_c != nullptr;
-    const int64_t nvec = n / 8;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
         float eu[8], ec[8], xv[8], o[8], e[8];
@@ -105,8 +104,8 @@ __global__ void __launch_bounds__(kThreads) cfg_ddim_kernel(const void* __restri
         if (eps_out) store8<EDT>(eps_out, i * 8, e);
     }
     // scalar tail (n % 8)
-    if (blockIdx.x == 0) {
-        for (int64_t i = nvec * 8 + threadIdx.x; i < n; i += blockDim.x) {
+    {
+        for (int64_t i = nvec * 8 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
             float e;
             float eu = load1<EDT>(eps_u, i);
             float ec = cfg ? load1<EDT>(eps_c, i) : 0.f;
@@ -131,9 +130,8 @@ template <int EDT, int XDT>
 __global__ void __launch_bounds__(kThreads) cfg_plms_kernel(const void* __restrict__ eps_u,
                                                             const void* __restrict__ eps_c,
                                                             const void* __restrict__ x, void* __restrict__ out,
-                                                            void* __restrict__ eps_out, int64_t n, PlmsArgs a) {
+                                                            void* __restrict__ eps_out, int64_t n, int64_t nvec, PlmsArgs a) {
     const bool cfg = eps_c != nullptr;
-    const int64_t nvec = n / 8;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
         float eu[8], ec[8], xv[8], e[8], acc[8], o[8];
@@ -156,8 +154,8 @@ __global__ void __launch_bounds__(kThreads) cfg_plms_kernel(const void* __restri
         store8<XDT>(out, i * 8, o);
         if (eps_out) store8<EDT>(eps_out, i * 8, e);
     }
-    if (blockIdx.x == 0) {
-        for (int64_t i = nvec * 8 + threadIdx.x; i < n; i += blockDim.x) {
+    {
+        for (int64_t i = nvec * 8 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
             float eu = load1<EDT>(eps_u, i);
             float e = cfg ? (eu + a.g * (load1<EDT>(eps_c, i) - eu)) : eu;
             float acc = a.w[0] * e;
@@ -177,13 +175,12 @@ __global__ void __launch_bounds__(kThreads) add_noise_kernel(const void* __restr
                                                              const int64_t* __restrict__ timesteps,
                                                              const float* __restrict__ sa_table,
                                                              const float* __restrict__ sb_table,
-                                                             void* __restrict__ out, int64_t per_sample, int T) {
+                                                             void* __restrict__ out, int64_t per_sample, int64_t nvec, int T) {
     const int b = blockIdx.y;
     int64_t t = timesteps[b];
     t = t < 0 ? 0 : (t >= T ? T - 1 : t);
     const float sa = __ldg(sa_table + t), sb = __ldg(sb_table + t);
     const int64_t base = (int64_t)b * per_sample;
-    const int64_t nvec = per_sample / 8;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
         float a[8], e[8], o[8];
@@ -193,8 +190,8 @@ __global__ void __launch_bounds__(kThreads) add_noise_kernel(const void* __restr
         for (int j = 0; j < 8; ++j) o[j] = sa * a[j] + sb * e[j];
         store8<DT>(out, base + i * 8, o);
     }
-    if (blockIdx.x == 0) {
-        for (int64_t i = nvec * 8 + threadIdx.x; i < per_sample; i += blockDim.x)
+    {
+        for (int64_t i = nvec * 8 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < per_sample; i += stride)
             store1<DT>(out, base + i, sa * load1<DT>(x0, base + i) + sb * load1<DT>(noise, base + i));
     }
 }
@@ -221,11 +218,10 @@ template <int PDT, int TDT>
 __global__ void __launch_bounds__(kThreads) mse_fwd_kernel(const void* __restrict__ pred,
                                                            const void* __restrict__ target,
                                                            float* __restrict__ loss_out, float* __restrict__ ws,
-                                                           int64_t n) {
+                                                           int64_t n, int64_t nvec) {
     __shared__ float sm[32];
     __shared__ bool is_last;
     float acc = 0.f;
-    const int64_t nvec = n / 8;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
         float p[8], t[8];
@@ -237,8 +233,8 @@ __global__ void __launch_bounds__(kThreads) mse_fwd_kernel(const void* __restric
             acc += d * d;
         }
     }
-    if (blockIdx.x == 0) {
-        for (int64_t i = nvec * 8 + threadIdx.x; i < n; i += blockDim.x) {
+    {
+        for (int64_t i = nvec * 8 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
             float d = load1<PDT>(pred, i) - load1<TDT>(target, i);
             acc += d * d;
         }
@@ -275,9 +271,8 @@ template <int PDT, int TDT>
 __global__ void __launch_bounds__(kThreads) mse_bwd_kernel(const void* __restrict__ pred,
                                                            const void* __restrict__ target,
                                                            const float* __restrict__ grad_loss,
-                                                           void* __restrict__ grad_pred, int64_t n) {
+                                                           void* __restrict__ grad_pred, int64_t n, int64_t nvec) {
     const float s = __ldg(grad_loss) * 2.0f / (float)n;
-    const int64_t nvec = n / 8;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
         float p[8], t[8], g[8];
@@ -287,8 +282,8 @@ __global__ void __launch_bounds__(kThreads) mse_bwd_kernel(const void* __restric
         for (int j = 0; j < 8; ++j) g[j] = s * (p[j] - t[j]);
         store8<PDT>(grad_pred, i * 8, g);
     }
-    if (blockIdx.x == 0) {
-        for (int64_t i = nvec * 8 + threadIdx.x; i < n; i += blockDim.x)
+    {
+        for (int64_t i = nvec * 8 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
             store1<PDT>(grad_pred, i, s * (load1<PDT>(pred, i) - load1<TDT>(target, i)));
     }
 }
@@ -313,13 +308,13 @@ extern "C" int b200sd_cfg_ddim_step(const void* eps_u, const void* eps_c, const 
     B200SD_REQUIRE(eps_u && x && out, "cfg_ddim_step: null pointer");
     B200SD_REQUIRE(n >= 0, "cfg_ddim_step: negative n");
     B200SD_REQUIRE(dtype_ok(eps_dtype) && dtype_ok(x_dtype), "cfg_ddim_step: bad dtype");
-    B200SD_REQUIRE(aligned16(eps_u) && aligned16(eps_c) && aligned16(x) && aligned16(out) && aligned16(eps_out),
-                   "cfg_ddim_step: pointers must be 16-byte aligned");
+    const bool vec = aligned16(eps_u) && aligned16(eps_c) && aligned16(x) && aligned16(out) && aligned16(eps_out);
+    const int64_t nvec = vec ? n / 8 : 0;  // unaligned views (odd slices) take the scalar path
     B200SD_REQUIRE(sa_t != 0.f, "cfg_ddim_step: sa_t == 0");
     if (n == 0) return B200SD_OK;
     DdimCoef c{guidance, sa_t, sb_t, sa_p, sb_p};
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    DISPATCH2(eps_dtype, x_dtype, cfg_ddim_kernel, <<<grid_for(n / 8), kThreads, 0, s>>>(eps_u, eps_c, x, out, eps_out, n, c));
+    DISPATCH2(eps_dtype, x_dtype, cfg_ddim_kernel, <<<grid_for(vec ? n / 8 : n), kThreads, 0, s>>>(eps_u, eps_c, x, out, eps_out, n, nvec, c));
     COUNT_LAUNCH();
     B200SD_LAUNCH_CHECK();
     return B200SD_OK;
@@ -334,14 +329,17 @@ extern "C" int b200sd_cfg_plms_step(const void* eps_u, const void* eps_c, const 
     B200SD_REQUIRE(dtype_ok(eps_dtype) && dtype_ok(x_dtype), "cfg_plms_step: bad dtype");
     PlmsArgs a;
     a.hist[0] = hist0; a.hist[1] = hist1; a.hist[2] = hist2; a.hist[3] = hist3;
-    for (int i = 0; i < nhist; ++i) B200SD_REQUIRE(a.hist[i] && aligned16(a.hist[i]), "cfg_plms_step: bad history pointer");
-    B200SD_REQUIRE(aligned16(eps_u) && aligned16(eps_c) && aligned16(x) && aligned16(out) && aligned16(eps_out),
-                   "cfg_plms_step: pointers must be 16-byte aligned");
+    bool vec = aligned16(eps_u) && aligned16(eps_c) && aligned16(x) && aligned16(out) && aligned16(eps_out);
+    for (int i = 0; i < nhist; ++i) {
+        B200SD_REQUIRE(a.hist[i] != nullptr, "cfg_plms_step: null history pointer");
+        vec = vec && aligned16(a.hist[i]);
+    }
+    const int64_t nvec = vec ? n / 8 : 0;
     for (int i = 0; i < 5; ++i) a.w[i] = w_host5[i];
     a.nhist = nhist; a.g = guidance; a.cx = cx; a.ce = ce;
     if (n == 0) return B200SD_OK;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    DISPATCH2(eps_dtype, x_dtype, cfg_plms_kernel, <<<grid_for(n / 8), kThreads, 0, s>>>(eps_u, eps_c, x, out, eps_out, n, a));
+    DISPATCH2(eps_dtype, x_dtype, cfg_plms_kernel, <<<grid_for(vec ? n / 8 : n), kThreads, 0, s>>>(eps_u, eps_c, x, out, eps_out, n, nvec, a));
     COUNT_LAUNCH();
     B200SD_LAUNCH_CHECK();
     return B200SD_OK;
@@ -353,19 +351,19 @@ extern "C" int b200sd_add_noise(const void* x0, const void* noise, const int64_t
     B200SD_REQUIRE(x0 && noise && timesteps && sa_table && sb_table && out, "add_noise: null pointer");
     B200SD_REQUIRE(batch >= 0 && per_sample >= 0 && batch <= 65535, "add_noise: bad sizes");
     B200SD_REQUIRE(dtype_ok(dtype), "add_noise: bad dtype");
-    B200SD_REQUIRE(aligned16(x0) && aligned16(noise) && aligned16(out), "add_noise: pointers must be 16-byte aligned");
-    B200SD_REQUIRE(per_sample % 8 == 0 || batch <= 1, "add_noise: per_sample must be a multiple of 8 for batch > 1");
+    const bool vec = aligned16(x0) && aligned16(noise) && aligned16(out) && (per_sample % 8 == 0 || batch <= 1);
+    const int64_t nvec = vec ? per_sample / 8 : 0;
     if (batch == 0 || per_sample == 0) return B200SD_OK;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    int gx = grid_for(per_sample / 8);
+    int gx = grid_for(vec ? per_sample / 8 : per_sample);
     int cap = b200sd_num_sms() * 8 / batch;
     if (cap < 1) cap = 1;
     if (gx > cap) gx = cap;
     dim3 grid(gx, batch);
     if (dtype == B200SD_F32)
-        add_noise_kernel<B200SD_F32><<<grid, kThreads, 0, s>>>(x0, noise, timesteps, sa_table, sb_table, out, per_sample, num_train_timesteps);
+        add_noise_kernel<B200SD_F32><<<grid, kThreads, 0, s>>>(x0, noise, timesteps, sa_table, sb_table, out, per_sample, nvec, num_train_timesteps);
     else
-        add_noise_kernel<B200SD_BF16><<<grid, kThreads, 0, s>>>(x0, noise, timesteps, sa_table, sb_table, out, per_sample, num_train_timesteps);
+        add_noise_kernel<B200SD_BF16><<<grid, kThreads, 0, s>>>(x0, noise, timesteps, sa_table, sb_table, out, per_sample, nvec, num_train_timesteps);
     COUNT_LAUNCH();
     B200SD_LAUNCH_CHECK();
     return B200SD_OK;
@@ -378,11 +376,12 @@ extern "C" int b200sd_mse_loss_fwd(const void* pred, const void* target, float* 
     B200SD_REQUIRE(pred && target && loss_out && workspace, "mse_loss_fwd: null pointer");
     B200SD_REQUIRE(n > 0, "mse_loss_fwd: n must be positive");
     B200SD_REQUIRE(dtype_ok(pred_dtype) && dtype_ok(target_dtype), "mse_loss_fwd: bad dtype");
-    B200SD_REQUIRE(aligned16(pred) && aligned16(target), "mse_loss_fwd: pointers must be 16-byte aligned");
+    const bool vec = aligned16(pred) && aligned16(target);
+    const int64_t nvec = vec ? n / 8 : 0;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    int grid = grid_for(n / 8);
+    int grid = grid_for(vec ? n / 8 : n);
     if (grid > kMsePartials) grid = kMsePartials;
-    DISPATCH2(pred_dtype, target_dtype, mse_fwd_kernel, <<<grid, kThreads, 0, s>>>(pred, target, loss_out, workspace, n));
+    DISPATCH2(pred_dtype, target_dtype, mse_fwd_kernel, <<<grid, kThreads, 0, s>>>(pred, target, loss_out, workspace, n, nvec));
     COUNT_LAUNCH();
     B200SD_LAUNCH_CHECK();
     return B200SD_OK;
@@ -393,9 +392,10 @@ extern "C" int b200sd_mse_loss_bwd(const void* pred, const void* target, const f
     B200SD_REQUIRE(pred && target && grad_loss && grad_pred, "mse_loss_bwd: null pointer");
     B200SD_REQUIRE(n > 0, "mse_loss_bwd: n must be positive");
     B200SD_REQUIRE(dtype_ok(pred_dtype) && dtype_ok(target_dtype), "mse_loss_bwd: bad dtype");
-    B200SD_REQUIRE(aligned16(pred) && aligned16(target) && aligned16(grad_pred), "mse_loss_bwd: pointers must be 16-byte aligned");
+    const bool vec = aligned16(pred) && aligned16(target) && aligned16(grad_pred);
+    const int64_t nvec = vec ? n / 8 : 0;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    DISPATCH2(pred_dtype, target_dtype, mse_bwd_kernel, <<<grid_for(n / 8), kThreads, 0, s>>>(pred, target, grad_loss, grad_pred, n));
+    DISPATCH2(pred_dtype, target_dtype, mse_bwd_kernel, <<<grid_for(vec ? n / 8 : n), kThreads, 0, s>>>(pred, target, grad_loss, grad_pred, n, nvec));
     COUNT_LAUNCH();
     B200SD_LAUNCH_CHECK();
     return B200SD_OK;

@@ -54,7 +54,7 @@ struct KParams {
     int tiles_y;         // H / tile_h (conv, tile_n == 1)
     int rows_valid;      // valid rows in a tile (<= 128)
     int a_bytes;         // bytes TMA delivers for A per stage
-    int ldc, ldr;
+    int ldc, ldr, ldrb;
     int rows_per_image;
     int epilogue;
     int out_f32;
@@ -72,7 +72,7 @@ __device__ __forceinline__ void epilogue_store16(const KParams& p, int row, int 
         }
     }
     if (p.rowbias) {
-        const float4* b = reinterpret_cast<const float4*>(p.rowbias + (size_t)(row / p.rows_per_image) * p.N + col);
+        const float4* b = reinterpret_cast<const float4*>(p.rowbias + (size_t)(row / p.rows_per_image) * p.ldrb + col);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             float4 t = __ldg(b + i);
@@ -359,7 +359,7 @@ extern "C" int b200sd_gemm(const b200sd_gemm_args* a, b200sd_stream_t stream) {
                        (reinterpret_cast<uintptr_t>(a->residual) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->bias) & 15) == 0 &&
                        (reinterpret_cast<uintptr_t>(a->rowbias) & 15) == 0,
                    "gemm: pointers must be 16-byte aligned");
-    B200SD_REQUIRE(!a->rowbias || a->rows_per_image > 0, "gemm: rowbias needs rows_per_image");
+    B200SD_REQUIRE(!a->rowbias || (a->rows_per_image > 0 && a->ldrb % 4 == 0), "gemm: rowbias needs rows_per_image and ldrb %% 4 == 0");
 
     KParams p;
     memset(&p, 0, sizeof(p));
@@ -375,6 +375,7 @@ extern "C" int b200sd_gemm(const b200sd_gemm_args* a, b200sd_stream_t stream) {
     p.out = a->out;
     p.ldc = a->ldc;
     p.ldr = a->ldr;
+    p.ldrb = a->ldrb > 0 ? a->ldrb : a->N;
     p.rows_per_image = a->rows_per_image > 0 ? a->rows_per_image : 1;
     p.epilogue = a->epilogue;
     p.out_f32 = a->out_dtype == B200SD_F32;

@@ -1,0 +1,286 @@
+"""Static launch plan of one UNet forward for a fixed (batch, H, W, ctx_len) geometry.
+
+The plan is a flat list of C-ABI calls over pre-allocated NHWC bf16 activation buffers (an
+(N,C,H,W) tensor is stored as [N*H*W][C], which is also the transformer's (N, H*W, C) token layout,
+so no permutes exist).  Buffers are recycled through a liveness-aware pool at plan-build time; at
+run time nothing is allocated, so the whole plan can be captured once into a CUDA graph and
+replayed (one cudaGraphLaunch per denoising step).
+
+Data flow per block, each arrow = one kernel:
+  resnet : [x|skip] -GN+SiLU(+cat)-> t1 -conv3x3(+bias+temb)-> h -GN+SiLU-> t2
+           [x|skip] -1x1 shortcut-> sc ; t2 -conv3x3(+bias+sc)-> y
+  xformer: x -GN-> t -proj_in-> hs -LN-> n -QKV-> qkv -flash attn-> a -out proj(+hs)-> hs
+           -LN-> n -Q-> q ; ctx -KV-> kv (hoisted: once per context) ; flash attn -> a -out proj(+hs)-> hs
+           -LN-> n -FF1+GEGLU-> f -FF2(+hs)-> hs -proj_out(+x)-> y
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import ops
+from ._lib import check, lib
+
+
+class _Pool:
+    """Size-keyed free lists of bf16 row-major buffers; safe because all work is stream-ordered."""
+
+    def __init__(self, device):
+        self.device = device
+        self.free = {}
+        self.total = 0
+
+    def get(self, rows, cols, dtype=torch.bfloat16):
+        key = (rows * cols, dtype)
+        lst = self.free.get(key)
+        if lst:
+            return lst.pop().view(rows, cols)
+        self.total += rows * cols * (2 if dtype == torch.bfloat16 else 4)
+        return torch.empty(rows, cols, dtype=dtype, device=self.device)
+
+    def put(self, t):
+        self.free.setdefault((t.numel(), t.dtype), []).append(t)
+
+
+class Engine:
+    def __init__(self, model, N, H, W, S_ctx, device):
+        self.model, self.N, self.H, self.W, self.S = model, N, H, W, S_ctx
+        self.device = device
+        cfg = model.config
+        self.heads = cfg.attention_head_dim
+        self.ctx_dim = cfg.cross_attention_dim
+        self.plan = []          # main plan (per step)
+        self.ctx_plan = []      # context K/V projections (once per context)
+        self.pool = _Pool(device)
+        self.graph = None
+        self._ctx_key = None
+        self._keep = []
+        with torch.cuda.device(device):
+            self._build()
+
+    # -- plan-building helpers --------------------------------------------------------------------
+    def _gemm(self, plan, a0, w, out, **kw):
+        rb = kw.pop("rowbias_ptr", None)
+        args = ops.gemm(a0, w, out, launch=False, **kw)
+        if rb is not None:
+            args.rowbias, args.ldrb, args.rows_per_image = rb[0], rb[1], rb[2]
+        self._keep.append((a0, w, out, kw))
+        plan.append(lambda a=args: ops.gemm_run(a))
+
+    def _build(self):
+        m, Wp, N, dev = self.model, self.model._packed, self.N, self.device
+        cfg = m.config
+        boc = cfg.block_out_channels
+        P, pool = self.plan, self.pool
+        f32 = dict(dtype=torch.float32, device=dev)
+
+        # static inputs
+        self.in_sample = torch.zeros(N, cfg.in_channels, self.H, self.W, **f32)
+        self.in_t = torch.zeros(N, **f32)
+        self.in_ctx = torch.zeros(N * self.S, self.ctx_dim, dtype=torch.bfloat16, device=dev)
+        self.out = torch.zeros(N, cfg.out_channels, self.H, self.W, **f32)
+
+        # ---- time embedding: sinusoid -> MLP -> all 22 time_emb_proj heads in one launch ----
+        temb_dim = boc[0] * 4
+        t_sin = torch.empty(N, boc[0], **f32)
+        t_h = torch.empty(N, temb_dim, **f32)
+        t_emb = torch.empty(N, temb_dim, **f32)
+        n_tp = Wp["tproj"]["n"]
+        self.tproj = torch.empty(N, n_tp, **f32)
+        te = Wp["temb"]
+        P.append(lambda: ops.timestep_embedding(self.in_t, boc[0], out=t_sin))
+        P.append(lambda: ops.small_linear(t_sin, te["w1"], te["b1"], silu_out=True, out=t_h))
+        P.append(lambda: ops.small_linear(t_h, te["w2"], te["b2"], out=t_emb))
+        P.append(lambda: ops.small_linear(t_emb, Wp["tproj"]["w"], Wp["tproj"]["b"], silu_in=True, out=self.tproj))
+
+        # ---- conv_in ----
+        h, w = self.H, self.W
+        x = pool.get(N * h * w, boc[0])
+        P.append(lambda x=x: ops.conv_in(self.in_sample, Wp["conv_in"]["w"], Wp["conv_in"]["b"], x))
+
+        skips = [(x, boc[0])]
+        skip_refs = {id(x): 1}
+
+        def release(t):
+            # a buffer may be both the running activation and a pending skip
+            if skip_refs.get(id(t), 0) > 0:
+                return
+            pool.put(t)
+
+        def resnet(prefix, r, x, skip, h, w):
+            wr = Wp[prefix]
+            M = N * h * w
+            cin, cout = r.cin, r.cout
+            t1 = pool.get(M, cin)
+            P.append(lambda: ops.groupnorm_silu(x, skip, wr["g1"], wr["b1"], t1, N, h * w, 32, cfg.norm_eps, True))
+            hbuf = pool.get(M, cout)
+            rb = (self.tproj.data_ptr() + m._tproj_off[prefix] * 4, n_tp, h * w)
+            self._gemm(P, t1, wr["w1"], hbuf, bias=wr["cb1"], conv=(N, h, w), rowbias_ptr=rb)
+            pool.put(t1)
+            t2 = pool.get(M, cout)
+            P.append(lambda: ops.groupnorm_silu(hbuf, None, wr["g2"], wr["b2"], t2, N, h * w, 32, cfg.norm_eps, True))
+            pool.put(hbuf)
+            if "wsc" in wr:
+                sc = pool.get(M, cout)
+                self._gemm(P, x, wr["wsc"], sc, a1=skip, bias=wr["bsc"])
+            else:
+                sc = x
+            y = pool.get(M, cout)
+            self._gemm(P, t2, wr["w2"], y, bias=wr["cb2"], residual=sc, conv=(N, h, w))
+            pool.put(t2)
+            if sc is not x:
+                pool.put(sc)
+            return y
+
+        def xformer(prefix, a, x, h, w):
+            wa = Wp[prefix]
+            Cc = a.ch
+            M = N * h * w
+            d = Cc // self.heads
+            scale = d ** -0.5
+            # context K/V: hoisted out of the per-step plan
+            kv = torch.empty(N * self.S, 2 * Cc, dtype=torch.bfloat16, device=dev)
+            self._gemm(self.ctx_plan, self.in_ctx, wa["w_kv2"], kv)
+            t = pool.get(M, Cc)
+            P.append(lambda: ops.groupnorm_silu(x, None, wa["gn_g"], wa["gn_b"], t, N, h * w, 32, 1e-6, False))
+            hs = pool.get(M, Cc)
+            self._gemm(P, t, wa["w_in"], hs, bias=wa["b_in"])
+            # self attention
+            P.append(lambda: ops.layernorm(hs, wa["ln1_g"], wa["ln1_b"], t))
+            qkv = pool.get(M, 3 * Cc)
+            self._gemm(P, t, wa["w_qkv"], qkv)
+            P.append(lambda: ops.attention(qkv, qkv, qkv, t, N, self.heads, h * w, h * w, d, scale, ldq=3 * Cc,
+                                           ldk=3 * Cc, ldv=3 * Cc, ldo=Cc, q_off=0, k_off=Cc, v_off=2 * Cc))
+            pool.put(qkv)
+            self._gemm(P, t, wa["w_o1"], hs, bias=wa["b_o1"], residual=hs)
+            # cross attention
+            P.append(lambda: ops.layernorm(hs, wa["ln2_g"], wa["ln2_b"], t))
+            q = pool.get(M, Cc)
+            self._gemm(P, t, wa["w_q2"], q)
+            P.append(lambda: ops.attention(q, kv, kv, t, N, self.heads, h * w, self.S, d, scale, ldq=Cc, ldk=2 * Cc,
+                                           ldv=2 * Cc, ldo=Cc, k_off=0, v_off=Cc))
+            pool.put(q)
+            self._gemm(P, t, wa["w_o2"], hs, bias=wa["b_o2"], residual=hs)
+            # GEGLU feed-forward
+            P.append(lambda: ops.layernorm(hs, wa["ln3_g"], wa["ln3_b"], t))
+            ff = pool.get(M, 4 * Cc)
+            self._gemm(P, t, wa["w_ff1"], ff, bias=wa["b_ff1"], epilogue=ops.EPI_GEGLU, block_n=wa["ff_tile"])
+            self._gemm(P, ff, wa["w_ff2"], hs, bias=wa["b_ff2"], residual=hs)
+            pool.put(ff)
+            pool.put(t)
+            y = pool.get(M, Cc)
+            self._gemm(P, hs, wa["w_out"], y, bias=wa["b_out"], residual=x)
+            pool.put(hs)
+            return y
+
+        def push_skip(t, c):
+            skips.append((t, c))
+            skip_refs[id(t)] = skip_refs.get(id(t), 0) + 1
+
+        # ---- down ----
+        for i, b in enumerate(m.down_blocks):
+            for j, r in enumerate(b.resnets):
+                y = resnet(f"down{i}.res{j}", r, x, None, h, w)
+                release(x)
+                x = y
+                if hasattr(b, "attentions"):
+                    y = xformer(f"down{i}.attn{j}", b.attentions[j], x, h, w)
+                    release(x)
+                    x = y
+                push_skip(x, r.cout)
+            if hasattr(b, "downsamplers"):
+                wd = Wp[f"down{i}.ds"]
+                Cc = boc[i]
+                col = pool.get(N * (h // 2) * (w // 2), 9 * Cc)
+                P.append(lambda x=x, col=col, h=h, w=w: ops.im2col_s2(x, col, N, h, w))
+                h, w = h // 2, w // 2
+                y = pool.get(N * h * w, Cc)
+                self._gemm(P, col, wd["w"], y, bias=wd["b"])
+                pool.put(col)
+                release(x)
+                x = y
+                push_skip(x, Cc)
+
+        # ---- mid ----
+        y = resnet("mid.res0", m.mid_block.resnets[0], x, None, h, w)
+        release(x)
+        x = y
+        y = xformer("mid.attn0", m.mid_block.attentions[0], x, h, w)
+        release(x)
+        x = y
+        y = resnet("mid.res1", m.mid_block.resnets[1], x, None, h, w)
+        release(x)
+        x = y
+
+        # ---- up ----
+        for i, b in enumerate(m.up_blocks):
+            for j, r in enumerate(b.resnets):
+                skip, _c = skips.pop()
+                y = resnet(f"up{i}.res{j}", r, x, skip, h, w)
+                skip_refs[id(skip)] -= 1
+                release(skip)
+                release(x)
+                x = y
+                if hasattr(b, "attentions"):
+                    y = xformer(f"up{i}.attn{j}", b.attentions[j], x, h, w)
+                    release(x)
+                    x = y
+            if hasattr(b, "upsamplers"):
+                wu = Wp[f"up{i}.us"]
+                Cc = x.shape[1]
+                up = pool.get(N * 4 * h * w, Cc)
+                P.append(lambda x=x, up=up, h=h, w=w: ops.upsample2x(x, up, N, h, w))
+                release(x)
+                h, w = 2 * h, 2 * w
+                y = pool.get(N * h * w, Cc)
+                self._gemm(P, up, wu["w"], y, bias=wu["b"], conv=(N, h, w))
+                pool.put(up)
+                x = y
+
+        # ---- out ----
+        wo = Wp["conv_out"]
+        t = pool.get(N * h * w, boc[0])
+        P.append(lambda x=x, t=t: ops.groupnorm_silu(x, None, wo["g"], wo["beta"], t, N, h * w, 32, cfg.norm_eps, True))
+        P.append(lambda t=t: ops.conv_out(t, wo["w"], wo["b"], self.out))
+        self.activation_bytes = pool.total
+
+    # -- execution --------------------------------------------------------------------------------
+    def set_context(self, ctx):
+        """Project the (constant-over-steps) text context to every cross-attention's K/V once."""
+        key = (ctx.data_ptr(), ctx._version, tuple(ctx.shape), ctx.dtype)
+        if key == self._ctx_key:
+            return
+        self.in_ctx.copy_(ctx.reshape(self.N * self.S, self.ctx_dim))
+        for op in self.ctx_plan:
+            op()
+        self._ctx_key = key
+
+    def _run_plan(self):
+        for op in self.plan:
+            op()
+
+    def run(self, sample, timestep, ctx, use_graph=True):
+        with torch.cuda.device(self.device):
+            self.set_context(ctx)
+            self.in_sample.copy_(sample)
+            if torch.is_tensor(timestep):
+                self.in_t.copy_(timestep.to(device=self.device, dtype=torch.float32).reshape(-1).expand(self.N))
+            else:
+                self.in_t.fill_(float(timestep))
+            if not use_graph:
+                self._run_plan()
+            else:
+                if self.graph is None:
+                    self._run_plan()  # warm-up: lazy one-time setup (func attributes, workspaces) outside capture
+                    torch.cuda.current_stream().synchronize()
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        self._run_plan()
+                    self.graph = g
+                self.graph.replay()
+            return self.out.clone()
+
+    @property
+    def launches_per_step(self):
+        return len(self.plan)

@@ -167,7 +167,7 @@ def gemm_workspace(device):
 
 
 def gemm(a0, w, out, *, a1=None, bias=None, rowbias=None, residual=None, conv=None, rows_per_image=0,
-         epilogue=EPI_LINEAR, block_n=0, split_k=0, M=None):
+         epilogue=EPI_LINEAR, block_n=0, split_k=0, M=None, ldrb=0, launch=True):
     """out[M, N] = [a0 | a1] @ w^T (+bias +rowbias +residual); conv=(batch, H, W) -> 3x3 pad-1 conv (NHWC)."""
     _chk(a0, a1, w, bias, rowbias, residual, out)
     N, K = w.shape
@@ -183,6 +183,7 @@ def gemm(a0, w, out, *, a1=None, bias=None, rowbias=None, residual=None, conv=No
     args.lda0, args.lda1 = C0, C1
     args.ldc = out.shape[-1]
     args.ldr = residual.shape[-1] if residual is not None else 0
+    args.ldrb = ldrb
     if conv is not None:
         args.conv_taps = 9
         args.batch, args.H, args.W = conv
@@ -193,8 +194,14 @@ def gemm(a0, w, out, *, a1=None, bias=None, rowbias=None, residual=None, conv=No
     args.out_dtype = _dt(out)
     args.block_n, args.split_k = block_n, split_k
     args.workspace, args.workspace_bytes = _p(ws), ws.numel()
+    if not launch:
+        return args
     check(lib().b200sd_gemm(C.byref(args), _stream()), "gemm")
     return out
+
+
+def gemm_run(args):
+    check(lib().b200sd_gemm(C.byref(args), _stream()), "gemm")
 
 
 def geglu_tile(N):

@@ -1,0 +1,138 @@
+"""GPU parity of the whole UNet forward and of the 50-step CFG sampling loop against the fp32 oracle
+on identical random-init weights (seed 0; default torch init, to_q/to_k x4 -- oracle.unet_ref
+make_oracle_unet), latents, timesteps and context.
+
+Tolerances (BASELINE.json north_star): bf16 noise prediction max|x-ref|/max|ref| <= 1e-2;
+50-step sampled latents cosine >= 0.999."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _rel(got, want):
+    return float((got.float().cpu() - want.float().cpu()).abs().max() / want.float().abs().max())
+
+
+@pytest.fixture(scope="module")
+def models():
+    from b200sd.unet import UNet2DConditionModel
+    from oracle.unet_ref import make_oracle_unet
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    oracle = make_oracle_unet(seed=0)
+    ours = UNet2DConditionModel()
+    ours.load_state_dict(oracle.state_dict(), strict=True)
+    ours = ours.to(DEV).eval()
+    return oracle, ours
+
+
+def test_config1_single_forward_vs_cpu_oracle(models):
+    """BASELINE config 1: batch 1, 4x64x64 latent, 77x768 context, oracle fp32 on CPU."""
+    oracle, ours = models
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(1, 4, 64, 64, generator=g)
+    ctx = torch.randn(1, 77, 768, generator=g)
+    for t in (1, 500, 981):
+        with torch.no_grad():
+            want = oracle(x, t, ctx).sample
+            got = ours(x.to(DEV), t, ctx.to(DEV)).sample
+        assert got.shape == want.shape and got.dtype == torch.float32
+        r = _rel(got, want)
+        assert r <= 1e-2, f"t={t}: max-rel {r:.4g}"
+
+
+def test_batch2_per_sample_timesteps_and_graph_equivalence(models):
+    oracle, ours = models
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(2, 4, 64, 64, generator=g)
+    ctx = torch.randn(2, 77, 768, generator=g)
+    t = torch.tensor([980, 20])
+    oc = oracle.to(DEV)
+    try:
+        with torch.no_grad():
+            want = oc(x.to(DEV), t.to(DEV), ctx.to(DEV)).sample
+            ours.use_cuda_graph = False
+            eager = ours(x.to(DEV), t.to(DEV), ctx.to(DEV)).sample
+            ours.use_cuda_graph = True
+            g1 = ours(x.to(DEV), t.to(DEV), ctx.to(DEV)).sample
+            g2 = ours(x.to(DEV), t.to(DEV), ctx.to(DEV)).sample
+    finally:
+        oracle.to("cpu")
+        ours.use_cuda_graph = True
+    assert _rel(eager, want) <= 1e-2
+    assert torch.equal(eager, g1) and torch.equal(g1, g2), "graph replay must be bit-identical to eager launches"
+
+
+def test_portrait_latent_96x64(models):
+    """BASELINE config 5 geometry (512 wide x 768 high -> 4x96x64 latent)."""
+    oracle, ours = models
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(2, 4, 96, 64, generator=g)
+    ctx = torch.randn(2, 77, 768, generator=g)
+    oc = oracle.to(DEV)
+    try:
+        with torch.no_grad():
+            want = oc(x.to(DEV), 500, ctx.to(DEV)).sample
+            got = ours(x.to(DEV), 500, ctx.to(DEV)).sample
+    finally:
+        oracle.to("cpu")
+    assert _rel(got, want) <= 1e-2
+
+
+def test_50_step_cfg_ddim_sampling_cosine(models):
+    """BASELINE config 2: 50-step DDIM, CFG 7.5, batch-1 image (UNet batch 2).  The oracle loop runs in
+    fp32 on the GPU (same oracle module, moved to CUDA with TF32 off) so the test finishes in seconds."""
+    from b200sd.pipeline import denoise_loop
+    from b200sd.schedulers import DDIMScheduler
+    from oracle import schedulers_ref as R
+    oracle, ours = models
+    g = torch.Generator().manual_seed(42)
+    lat = torch.randn(1, 4, 64, 64, generator=g)
+    ctx2 = torch.randn(2, 77, 768, generator=g)
+    oc = oracle.to(DEV)
+    try:
+        with torch.no_grad():
+            rec_ref, rec = [], []
+            ref_s = R.DDIMSchedulerRef(clip_sample=False, set_alpha_to_one=False)
+            want = R.denoise_loop(oc, ref_s, lat.to(DEV), ctx2.to(DEV), 50, 7.5, record=rec_ref)
+            sch = DDIMScheduler(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear", clip_sample=False,
+                                set_alpha_to_one=False)
+            got = denoise_loop(ours, sch, lat.to(DEV), ctx2.to(DEV), 50, 7.5, record=rec)
+    finally:
+        oracle.to("cpu")
+    cos = float(torch.nn.functional.cosine_similarity(got.flatten().float(), want.flatten().float(), dim=0))
+    assert cos >= 0.999, f"50-step latents cosine {cos:.6f}"
+    assert _rel(rec[0], rec_ref[0]) <= 1e-2
+
+
+def test_50_step_cfg_plms_sampling_cosine(models):
+    from b200sd.pipeline import denoise_loop
+    from b200sd.schedulers import PNDMScheduler
+    from oracle import schedulers_ref as R
+    oracle, ours = models
+    g = torch.Generator().manual_seed(43)
+    lat = torch.randn(1, 4, 64, 64, generator=g)
+    ctx2 = torch.randn(2, 77, 768, generator=g)
+    oc = oracle.to(DEV)
+    try:
+        with torch.no_grad():
+            want = R.denoise_loop(oc, R.PNDMSchedulerRef(skip_prk_steps=True, steps_offset=1), lat.to(DEV), ctx2.to(DEV), 50, 7.5)
+            sch = PNDMScheduler(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear", skip_prk_steps=True,
+                                steps_offset=1)
+            got = denoise_loop(ours, sch, lat.to(DEV), ctx2.to(DEV), 50, 7.5)
+    finally:
+        oracle.to("cpu")
+    cos = float(torch.nn.functional.cosine_similarity(got.flatten().float(), want.flatten().float(), dim=0))
+    assert cos >= 0.999, f"51-call PLMS latents cosine {cos:.6f}"
+
+
+def test_forward_rejects_bad_inputs(models):
+    _, ours = models
+    with pytest.raises(ValueError):
+        ours(torch.randn(1, 3, 64, 64, device=DEV), 1, torch.randn(1, 77, 768, device=DEV))
+    with pytest.raises(ValueError):
+        ours(torch.randn(1, 4, 60, 64, device=DEV), 1, torch.randn(1, 77, 768, device=DEV))
+    with pytest.raises(ValueError):
+        ours(torch.randn(2, 4, 64, 64, device=DEV), 1, torch.randn(1, 77, 768, device=DEV))
