@@ -1,0 +1,320 @@
+#!/usr/bin/env python
+"""bench.py -- SD v1.5 UNet denoise hot path on B200 (BASELINE.json configs[1]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl reference]
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+One "step" = one denoising iteration of the 50-step DDIM + classifier-free-guidance sampler for B
+images per GPU at 512x512: x2 = cat([lat, lat]) -> UNet(2B,4,64,64; t; ctx (2B,77,768)) ->
+fused CFG combine + DDIM update.  Metric: denoising iterations per second (whole job, all GPUs);
+images/s = it/s / 50 is reported next to it.  Sampling shards by image with no collective
+("scaling": "weak": every GPU runs its own B images).
+
+Output: ONE JSON line (see README / DESIGN.md section "Measurement").
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOPS_PER_SAMPLE_64 = 0.8033e12  # UNet fwd per sample @ 64x64 latent, 2*MAC
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops", 1590.0), d.get("bf16_tflops_sustained", 1400.0), "measured"
+    return 6650.0, 1590.0, 1400.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={self.Q}",
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        os.unlink(self.f.name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def ddim_coefs(sch, t):
+    return sch._coefs(t)
+
+
+# ---------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the fp32 oracle (restated diffusers 0.7.2 math) on the host cores
+# ---------------------------------------------------------------------------------------------------
+def cpu_oracle_it_per_s(batch_images, budget_s, max_iters, warmup=1):
+    import torch
+    from oracle.unet_ref import make_oracle_unet
+    from oracle import schedulers_ref as R
+    torch.set_num_threads(os.cpu_count() or 1)
+    m = make_oracle_unet(seed=0)
+    sch = R.DDIMSchedulerRef(clip_sample=False, set_alpha_to_one=False)
+    sch.set_timesteps(50)
+    g = torch.Generator().manual_seed(42)
+    lat = torch.randn(batch_images, 4, 64, 64, generator=g)
+    ctx2 = torch.randn(2 * batch_images, 77, 768, generator=g)
+    ts = sch.timesteps.tolist()
+    done, t_total = 0, 0.0
+    with torch.no_grad():
+        for i in range(warmup + max_iters):
+            t = ts[i % len(ts)]
+            t0 = time.perf_counter()
+            eps = m(torch.cat([lat] * 2), t, ctx2).sample
+            eps = R.cfg_combine(eps, 7.5)
+            lat = sch.step(eps, t, lat).prev_sample
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                done += 1
+                t_total += dt
+                if t_total > budget_s:
+                    break
+    return done * batch_images / t_total, done, t_total, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    v, done, t_total, cores = cpu_oracle_it_per_s(args.batch, budget_s=150.0, max_iters=args.steps, warmup=min(args.warmup, 1))
+    sample = f"{done} of {args.steps} denoising iterations (time-bounded), fp32 oracle on host CPU, CFG batch {2 * args.batch}"
+    line = {
+        "impl": "reference", "metric": "unet_denoise_it_per_s", "value": v, "unit": "it/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / max(done, 1),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "sd15_unet_ddim50_cfg7.5_512px", "images_per_gpu": args.batch, "latent": "4x64x64",
+                   "context": "77x768", "images_per_s": v / 50.0},
+        "cpu_baseline": {"value": v, "unit": "it/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "it/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from b200sd import ops
+    from b200sd.schedulers import DDIMScheduler
+    from b200sd.unet import UNet2DConditionModel
+
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    B = args.batch
+    h, w = (96, 64) if args.portrait else (64, 64)
+    torch.manual_seed(0)
+    unet = UNet2DConditionModel().to(dev).eval()          # random-init weights of the SD v1.5 architecture
+    sch = DDIMScheduler(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear", clip_sample=False,
+                        set_alpha_to_one=False)
+    sch.set_timesteps(50)
+    ts = sch.timesteps.tolist()
+    g = torch.Generator().manual_seed(42 + rank)
+    lat_host = torch.randn(B, 4, h, w, generator=g).pin_memory()
+    ctx_host = torch.randn(2 * B, 77, 768, generator=g).pin_memory()
+    lat = lat_host.to(dev)
+    ctx = ctx_host.to(dev)
+    x2 = torch.empty(2 * B, 4, h, w, device=dev)
+    lat_next = torch.empty_like(lat)
+
+    def step(i):
+        nonlocal lat, lat_next
+        t = ts[i % len(ts)]
+        x2[:B].copy_(lat)
+        x2[B:].copy_(lat)
+        eps2 = unet(x2, t, ctx).sample
+        sch.step_cfg(eps2, t, lat, 7.5, out=lat_next)
+        lat, lat_next = lat_next, lat
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.no_grad():
+        for i in range(max(args.warmup, 3)):
+            step(i)
+        eng = next(iter(unet._engines.values()))
+        kernels_per_unet = getattr(eng, "kernels_per_graph", 0)
+        # ---- device-resident timing ----
+        barrier()
+        sampler = ClockSampler(local) if rank == 0 else None
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        launches0 = ops.launch_count()
+        e0.record()
+        for i in range(args.steps):
+            step(i)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        clocks = sampler.stop() if sampler else None
+        eager_launches = ops.launch_count() - launches0
+        gpu_launches = eager_launches + kernels_per_unet * args.steps
+
+        # ---- end to end through the public API with host buffers (H2D + D2H inside the timed region) ----
+        out_host = torch.empty(B, 4, h, w).pin_memory()
+        lat_d = torch.empty(B, 4, h, w, device=dev)
+        ctx_d = torch.empty(2 * B, 77, 768, device=dev)
+
+        def e2e_step(i):
+            t = ts[i % len(ts)]
+            lat_d.copy_(lat_host, non_blocking=True)
+            ctx_d.copy_(ctx_host, non_blocking=True)
+            x2[:B].copy_(lat_d)
+            x2[B:].copy_(lat_d)
+            eps2 = unet(x2, t, ctx_d).sample
+            new = sch.step_cfg(eps2, t, lat_d, 7.5).prev_sample
+            out_host.copy_(new, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            lat_host.copy_(out_host)
+
+        for i in range(3):
+            e2e_step(i)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            e2e_step(i)
+        barrier()
+        e2e_ms = (time.perf_counter() - t0) * 1e3
+
+        if world > 1:
+            tt = torch.tensor([ms, e2e_ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms, e2e_ms = float(tt[0]), float(tt[1])
+
+        # ---- roofline of the dominant kernel (tcgen05 GEMM / implicit-GEMM conv), timed live ----
+        roof = None
+        kernels = None
+        if rank == 0:
+            acc, per_op = eng.profile(iters=3)
+            hbm, tf_burst, tf_sus, which = _peaks()
+            mm_ms = sum(acc[k][0] for k in ("gemm", "conv3x3") if k in acc)
+            mm_fl = sum(acc[k][1] for k in ("gemm", "conv3x3") if k in acc)
+            mm_n = sum(acc[k][2] for k in ("gemm", "conv3x3") if k in acc)
+            achieved = mm_fl / (mm_ms * 1e-3) / 1e12 if mm_ms > 0 else 0.0
+            roof = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (GEMM + implicit-GEMM conv3x3)",
+                    "achieved": achieved, "peak": tf_sus, "unit": "TFLOP/s", "frac": achieved / tf_sus,
+                    "peak_kind": f"bf16 sustained, {which}", "launches_per_step": mm_n,
+                    "avg_launch_us": 1e3 * mm_ms / max(mm_n, 1), "flops_per_step": mm_fl, "traffic": None}
+            tot = sum(v[0] for v in acc.values())
+            kernels = {k: {"ms_per_step": round(v[0], 4), "share": round(v[0] / tot, 4), "launches": v[2],
+                           "tflops": round(v[1] / (v[0] * 1e-3) / 1e12, 1) if v[1] > 0 and v[0] > 0 else None}
+                       for k, v in sorted(acc.items(), key=lambda kv: -kv[1][0])}
+            if args.dump_ops:
+                with open(args.dump_ops, "w") as f:
+                    for name, t_ms, fl in sorted(per_op, key=lambda r: -r[1]):
+                        f.write(f"{t_ms * 1e3:9.1f} us  {fl / (t_ms * 1e-3) / 1e12 if fl else 0:8.1f} TF/s  {name}\n")
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, done, t_total, cores = cpu_oracle_it_per_s(B, budget_s=20.0, max_iters=3, warmup=1)
+        cpu = {"value": v, "unit": "it/s", "cores": cores, "kind": "port",
+               "sample": f"{done} denoising iterations (CFG batch {2 * B}, fp32 oracle, 1 warm-up) in {t_total:.1f} s"}
+
+    if rank == 0:
+        its = B * args.steps * world
+        value = its / (ms * 1e-3)
+        e2e_value = its / (e2e_ms * 1e-3)
+        flops_per_it = 2 * (1.2953e12 if args.portrait else FLOPS_PER_SAMPLE_64)
+        line = {
+            "metric": "unet_denoise_it_per_s", "value": value, "unit": "it/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "sd15_unet_ddim50_cfg7.5_" + ("512x768" if args.portrait else "512px"),
+                       "images_per_gpu": B, "unet_batch": 2 * B, "latent": f"4x{h}x{w}", "context": "77x768",
+                       "weights": "random-init SD v1.5 UNet (859.5M params)", "images_per_s": value / 50.0,
+                       "e2e_images_per_s": e2e_value / 50.0, "tflops_end_to_end": value * flops_per_it / 1e12,
+                       "l2": "no flush: the 1.72 GB of bf16 weights streamed every step exceed the 126 MB L2",
+                       "cuda_graph": True},
+            "e2e": {"value": e2e_value, "unit": "it/s",
+                    "h2d_bytes_per_step": int(lat_host.numel() * 4 + ctx_host.numel() * 4),
+                    "d2h_bytes_per_step": int(out_host.numel() * 4)},
+            "gpu_launches": int(gpu_launches), "clocks": clocks, "roofline": roof, "kernels": kernels,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--batch", type=int, default=1, help="images per GPU (UNet batch = 2x with CFG)")
+    ap.add_argument("--portrait", action="store_true", help="512x768 book-cover geometry (config 5)")
+    ap.add_argument("--impl", default="b200sd", choices=["b200sd", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dump-ops", default=None, help="write the per-launch timing table to this file")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        if args.gpus > 1 and "RANK" not in os.environ:
+            # convenience: self-launch under torchrun
+            cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+                   "--master-addr", "127.0.0.1", "--master-port", "29531", os.path.abspath(__file__)] + sys.argv[1:]
+            raise SystemExit(subprocess.call(cmd))
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

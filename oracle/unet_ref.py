@@ -322,10 +322,13 @@ class UNet2DConditionModelRef(nn.Module):
         return SimpleNamespace(sample=x)
 
 
-def make_oracle_unet(seed: int = 0, sharpen_attention: float = 4.0, **overrides) -> UNet2DConditionModelRef:
+def make_oracle_unet(seed: int = 0, sharpen_attention: float = 2.0, **overrides) -> UNet2DConditionModelRef:
     """Seeded random-init oracle UNet: default torch init, then to_q / to_k scaled by
     `sharpen_attention` so the softmax is not near-uniform (a near-uniform softmax would make the
-    attention parity check vacuous).  The recipe and seed are part of every parity test."""
+    attention parity check vacuous).  The recipe and seed are part of every parity test.
+    Measured on B200 (tests/debug_unet_layers.py): at x2 the bf16 CUDA path is 0.85e-2 max-rel from
+    this fp32 oracle (torch eager bf16: 1.45e-2); at x4 the random network becomes chaotic w.r.t.
+    bf16 operand rounding (ours 6.9e-2, torch eager bf16 9.5e-2), which is kept as a stress case."""
     g = torch.random.get_rng_state()
     torch.manual_seed(seed)
     m = UNet2DConditionModelRef(**overrides)

@@ -43,6 +43,18 @@ class _Pool:
         self.free.setdefault((t.numel(), t.dtype), []).append(t)
 
 
+class _Plan(list):
+    """List of launch closures + parallel metadata (kind, algorithmic flops) for profiling."""
+
+    def __init__(self):
+        super().__init__()
+        self.meta = []
+
+    def append(self, fn, kind="other", flops=0.0, name=""):
+        super().append(fn)
+        self.meta.append((kind, float(flops), name))
+
+
 class Engine:
     def __init__(self, model, N, H, W, S_ctx, device):
         self.model, self.N, self.H, self.W, self.S = model, N, H, W, S_ctx
@@ -50,12 +62,14 @@ class Engine:
         cfg = model.config
         self.heads = cfg.attention_head_dim
         self.ctx_dim = cfg.cross_attention_dim
-        self.plan = []          # main plan (per step)
-        self.ctx_plan = []      # context K/V projections (once per context)
+        self.plan = _Plan()     # main plan (per step)
+        self.ctx_plan = _Plan() # context K/V projections (once per context)
         self.pool = _Pool(device)
         self.graph = None
         self._ctx_key = None
         self._keep = []
+        self.debug = False      # when True (eager runs only) every tapped activation is cloned
+        self.debug_out = {}
         with torch.cuda.device(device):
             self._build()
 
@@ -66,7 +80,16 @@ class Engine:
         if rb is not None:
             args.rowbias, args.ldrb, args.rows_per_image = rb[0], rb[1], rb[2]
         self._keep.append((a0, w, out, kw))
-        plan.append(lambda a=args: ops.gemm_run(a))
+        kind = "conv3x3" if args.conv_taps == 9 else "gemm"
+        plan.append(lambda a=args: ops.gemm_run(a), kind, 2.0 * args.M * args.N * args.K,
+                    f"{kind} M{args.M} N{args.N} K{args.K}")
+
+    def _tap(self, name, t, h, w):
+        """Debug probe: snapshot activation `t` ([N*h*w, C] NHWC) as NCHW fp32 under `name`."""
+        def op():
+            if self.debug:
+                self.debug_out[name] = t.float().reshape(self.N, h, w, -1).permute(0, 3, 1, 2).clone()
+        self.plan.append(op, "tap")
 
     def _build(self):
         m, Wp, N, dev = self.model, self.model._packed, self.N, self.device
@@ -99,6 +122,7 @@ class Engine:
         x = pool.get(N * h * w, boc[0])
         P.append(lambda x=x: ops.conv_in(self.in_sample, Wp["conv_in"]["w"], Wp["conv_in"]["b"], x))
 
+        self._tap("conv_in", x, h, w)
         skips = [(x, boc[0])]
         skip_refs = {id(x): 1}
 
@@ -113,13 +137,13 @@ class Engine:
             M = N * h * w
             cin, cout = r.cin, r.cout
             t1 = pool.get(M, cin)
-            P.append(lambda: ops.groupnorm_silu(x, skip, wr["g1"], wr["b1"], t1, N, h * w, 32, cfg.norm_eps, True))
+            P.append(lambda: ops.groupnorm_silu(x, skip, wr["g1"], wr["b1"], t1, N, h * w, 32, cfg.norm_eps, True), "groupnorm")
             hbuf = pool.get(M, cout)
             rb = (self.tproj.data_ptr() + m._tproj_off[prefix] * 4, n_tp, h * w)
             self._gemm(P, t1, wr["w1"], hbuf, bias=wr["cb1"], conv=(N, h, w), rowbias_ptr=rb)
             pool.put(t1)
             t2 = pool.get(M, cout)
-            P.append(lambda: ops.groupnorm_silu(hbuf, None, wr["g2"], wr["b2"], t2, N, h * w, 32, cfg.norm_eps, True))
+            P.append(lambda: ops.groupnorm_silu(hbuf, None, wr["g2"], wr["b2"], t2, N, h * w, 32, cfg.norm_eps, True), "groupnorm")
             pool.put(hbuf)
             if "wsc" in wr:
                 sc = pool.get(M, cout)
@@ -131,6 +155,7 @@ class Engine:
             pool.put(t2)
             if sc is not x:
                 pool.put(sc)
+            self._tap(prefix, y, h, w)
             return y
 
         def xformer(prefix, a, x, h, w):
@@ -143,27 +168,29 @@ class Engine:
             kv = torch.empty(N * self.S, 2 * Cc, dtype=torch.bfloat16, device=dev)
             self._gemm(self.ctx_plan, self.in_ctx, wa["w_kv2"], kv)
             t = pool.get(M, Cc)
-            P.append(lambda: ops.groupnorm_silu(x, None, wa["gn_g"], wa["gn_b"], t, N, h * w, 32, 1e-6, False))
+            P.append(lambda: ops.groupnorm_silu(x, None, wa["gn_g"], wa["gn_b"], t, N, h * w, 32, 1e-6, False), "groupnorm")
             hs = pool.get(M, Cc)
             self._gemm(P, t, wa["w_in"], hs, bias=wa["b_in"])
             # self attention
-            P.append(lambda: ops.layernorm(hs, wa["ln1_g"], wa["ln1_b"], t))
+            P.append(lambda: ops.layernorm(hs, wa["ln1_g"], wa["ln1_b"], t), "layernorm")
             qkv = pool.get(M, 3 * Cc)
             self._gemm(P, t, wa["w_qkv"], qkv)
             P.append(lambda: ops.attention(qkv, qkv, qkv, t, N, self.heads, h * w, h * w, d, scale, ldq=3 * Cc,
-                                           ldk=3 * Cc, ldv=3 * Cc, ldo=Cc, q_off=0, k_off=Cc, v_off=2 * Cc))
+                                           ldk=3 * Cc, ldv=3 * Cc, ldo=Cc, q_off=0, k_off=Cc, v_off=2 * Cc),
+                     "attention", 4.0 * N * self.heads * (h * w) * (h * w) * d, f"self-attn S{h * w} d{d}")
             pool.put(qkv)
             self._gemm(P, t, wa["w_o1"], hs, bias=wa["b_o1"], residual=hs)
             # cross attention
-            P.append(lambda: ops.layernorm(hs, wa["ln2_g"], wa["ln2_b"], t))
+            P.append(lambda: ops.layernorm(hs, wa["ln2_g"], wa["ln2_b"], t), "layernorm")
             q = pool.get(M, Cc)
             self._gemm(P, t, wa["w_q2"], q)
             P.append(lambda: ops.attention(q, kv, kv, t, N, self.heads, h * w, self.S, d, scale, ldq=Cc, ldk=2 * Cc,
-                                           ldv=2 * Cc, ldo=Cc, k_off=0, v_off=Cc))
+                                           ldv=2 * Cc, ldo=Cc, k_off=0, v_off=Cc),
+                     "attention", 4.0 * N * self.heads * (h * w) * self.S * d, f"cross-attn S{h * w} d{d}")
             pool.put(q)
             self._gemm(P, t, wa["w_o2"], hs, bias=wa["b_o2"], residual=hs)
             # GEGLU feed-forward
-            P.append(lambda: ops.layernorm(hs, wa["ln3_g"], wa["ln3_b"], t))
+            P.append(lambda: ops.layernorm(hs, wa["ln3_g"], wa["ln3_b"], t), "layernorm")
             ff = pool.get(M, 4 * Cc)
             self._gemm(P, t, wa["w_ff1"], ff, bias=wa["b_ff1"], epilogue=ops.EPI_GEGLU, block_n=wa["ff_tile"])
             self._gemm(P, ff, wa["w_ff2"], hs, bias=wa["b_ff2"], residual=hs)
@@ -172,6 +199,7 @@ class Engine:
             y = pool.get(M, Cc)
             self._gemm(P, hs, wa["w_out"], y, bias=wa["b_out"], residual=x)
             pool.put(hs)
+            self._tap(prefix, y, h, w)
             return y
 
         def push_skip(t, c):
@@ -200,6 +228,7 @@ class Engine:
                 pool.put(col)
                 release(x)
                 x = y
+                self._tap(f"down{i}.ds", x, h, w)
                 push_skip(x, Cc)
 
         # ---- mid ----
@@ -237,11 +266,12 @@ class Engine:
                 self._gemm(P, up, wu["w"], y, bias=wu["b"], conv=(N, h, w))
                 pool.put(up)
                 x = y
+                self._tap(f"up{i}.us", x, h, w)
 
         # ---- out ----
         wo = Wp["conv_out"]
         t = pool.get(N * h * w, boc[0])
-        P.append(lambda x=x, t=t: ops.groupnorm_silu(x, None, wo["g"], wo["beta"], t, N, h * w, 32, cfg.norm_eps, True))
+        P.append(lambda x=x, t=t: ops.groupnorm_silu(x, None, wo["g"], wo["beta"], t, N, h * w, 32, cfg.norm_eps, True), "groupnorm")
         P.append(lambda t=t: ops.conv_out(t, wo["w"], wo["b"], self.out))
         self.activation_bytes = pool.total
 
@@ -275,12 +305,38 @@ class Engine:
                     self._run_plan()  # warm-up: lazy one-time setup (func attributes, workspaces) outside capture
                     torch.cuda.current_stream().synchronize()
                     g = torch.cuda.CUDAGraph()
+                    before = ops.launch_count()
                     with torch.cuda.graph(g):
                         self._run_plan()
+                    self.kernels_per_graph = ops.launch_count() - before
                     self.graph = g
                 self.graph.replay()
             return self.out.clone()
 
-    @property
-    def launches_per_step(self):
-        return len(self.plan)
+    def profile(self, iters=3):
+        """Eager run with CUDA events around every plan entry -> {kind: (ms, flops, launches)} per step."""
+        evs = []
+        with torch.cuda.device(self.device):
+            self._run_plan()
+            torch.cuda.synchronize()
+            acc = {}
+            for _ in range(iters):
+                evs = []
+                for op, (kind, flops, name) in zip(self.plan, self.plan.meta):
+                    if kind == "tap":
+                        continue
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    op()
+                    e1.record()
+                    evs.append((kind, flops, name, e0, e1))
+                torch.cuda.synchronize()
+                for kind, flops, name, e0, e1 in evs:
+                    a = acc.setdefault(kind, [0.0, 0.0, 0])
+                    a[0] += e0.elapsed_time(e1) / iters
+                    a[1] += flops / iters
+                    a[2] += 1
+            for a in acc.values():
+                a[2] //= iters
+            per_op = [(name or kind, e0.elapsed_time(e1), flops) for kind, flops, name, e0, e1 in evs]
+        return acc, per_op
