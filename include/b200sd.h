@@ -108,7 +108,9 @@ int b200sd_small_linear(const float* in, const void* w_bf16, const float* bias, 
  *   B200SD_EPI_LINEAR : bias / rowbias / residual as above.
  *   B200SD_EPI_GEGLU  : W rows are tile-interleaved [value | gate] (see b200sd_geglu_tile());
  *                       out[M, N/2] = value * gelu_erf(gate), bias likewise interleaved.
- * split_k > 1 needs workspace (b200sd_gemm_workspace_bytes) and is reduced deterministically.
+ * split_k > 1 needs the workspace (b200sd_gemm_workspace_bytes; ZERO before first use, left zeroed):
+ * every split adds its tile into an L2-resident fp32 accumulator with vector reds and the last CTA of
+ * a tile runs the epilogue (fp32 summation order is not fixed: last-bit run-to-run differences).
  */
 #define B200SD_EPI_LINEAR 0
 #define B200SD_EPI_GEGLU 1
@@ -150,7 +152,8 @@ int b200sd_conv_out(const void* x_nhwc, const float* w, const float* bias, float
                     int Cout, int H, int W, b200sd_stream_t stream);
 
 /* GroupNorm over NHWC input, optionally over the channel concat [x0 | x1] (torch.cat fused),
- * optional SiLU, bf16 output [rows, C0+C1].  stats_ws: float[2 * batch * groups] scratch.
+ * optional SiLU, bf16 output [rows, C0+C1].  stats_ws: float[b200sd_groupnorm_workspace_floats(batch)]
+ * scratch that must be ZERO before its first use (arrival counters; the kernels leave them zeroed).
  * Replaces nn.GroupNorm + SiLU (+ torch.cat) in ResnetBlock2D / Transformer2DModel. */
 int b200sd_groupnorm_silu(const void* x0, const void* x1, int C0, int C1, const float* gamma, const float* beta,
                           void* out, float* stats_ws, int batch, int hw, int groups, float eps, int silu,

@@ -12,7 +12,7 @@
 // activation source (a1) extends the channel axis, which fuses the up-block torch.cat.
 // With <= 113 KB of smem and <= 256 TMEM columns per CTA two CTAs share an SM, so one CTA's
 // epilogue overlaps the other's main loop.  Small-M / deep-K layers are split along K with a
-// deterministic last-CTA reduction through an L2-resident fp32 workspace.
+// vector-red accumulation into an L2-resident fp32 workspace; the last CTA of a tile runs the epilogue.
 #include <atomic>
 #include <cstring>
 #include <cstdio>
@@ -30,7 +30,7 @@ constexpr int kNumThreads = 192;
 constexpr int kMaxStages = 8;
 constexpr int kABytes = BLOCK_M * BLOCK_K * 2;  // 16 KB (always reserved in full)
 
-constexpr size_t kSplitWsBytes = 64ull << 20;  // fp32 partial tiles
+constexpr size_t kSplitWsBytes = 64ull << 20;  // fp32 accumulator tiles (always left zeroed)
 constexpr int kMaxSplitTiles = 4096;           // per-tile arrival counters live after the partials
 
 struct KParams {
@@ -61,51 +61,44 @@ struct KParams {
     uint32_t tmem_cols;
 };
 
-__device__ __forceinline__ void epilogue_store16(const KParams& p, int row, int col, float (&v)[16]) {
-    // v holds out[row, col .. col+15] before bias / residual
+__device__ __forceinline__ void red_add_v4(float* addr, float4 v) {
+    asm volatile("red.global.v4.f32.add [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                 : "memory");
+}
+
+// Final epilogue for 8 consecutive output columns of one row: v = accumulators (fp32).
+__device__ __forceinline__ void epilogue_store8(const KParams& p, int row, int col, float (&v)[8]) {
     if (p.bias) {
         const float4* b = reinterpret_cast<const float4*>(p.bias + col);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            float4 t = __ldg(b + i);
-            v[4 * i + 0] += t.x; v[4 * i + 1] += t.y; v[4 * i + 2] += t.z; v[4 * i + 3] += t.w;
-        }
+        const float4 t0 = __ldg(b), t1 = __ldg(b + 1);
+        v[0] += t0.x; v[1] += t0.y; v[2] += t0.z; v[3] += t0.w;
+        v[4] += t1.x; v[5] += t1.y; v[6] += t1.z; v[7] += t1.w;
     }
     if (p.rowbias) {
         const float4* b = reinterpret_cast<const float4*>(p.rowbias + (size_t)(row / p.rows_per_image) * p.ldrb + col);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            float4 t = __ldg(b + i);
-            v[4 * i + 0] += t.x; v[4 * i + 1] += t.y; v[4 * i + 2] += t.z; v[4 * i + 3] += t.w;
-        }
+        const float4 t0 = __ldg(b), t1 = __ldg(b + 1);
+        v[0] += t0.x; v[1] += t0.y; v[2] += t0.z; v[3] += t0.w;
+        v[4] += t1.x; v[5] += t1.y; v[6] += t1.z; v[7] += t1.w;
     }
     if (p.residual) {
-        const uint4* r = reinterpret_cast<const uint4*>(p.residual + (size_t)row * p.ldr + col);
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            uint4 u = __ldg(r + i);
-            float2 f;
-            f = unpack_bf16x2(u.x); v[8 * i + 0] += f.x; v[8 * i + 1] += f.y;
-            f = unpack_bf16x2(u.y); v[8 * i + 2] += f.x; v[8 * i + 3] += f.y;
-            f = unpack_bf16x2(u.z); v[8 * i + 4] += f.x; v[8 * i + 5] += f.y;
-            f = unpack_bf16x2(u.w); v[8 * i + 6] += f.x; v[8 * i + 7] += f.y;
-        }
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(p.residual + (size_t)row * p.ldr + col));
+        float2 f;
+        f = unpack_bf16x2(u.x); v[0] += f.x; v[1] += f.y;
+        f = unpack_bf16x2(u.y); v[2] += f.x; v[3] += f.y;
+        f = unpack_bf16x2(u.z); v[4] += f.x; v[5] += f.y;
+        f = unpack_bf16x2(u.w); v[6] += f.x; v[7] += f.y;
     }
     if (p.out_f32) {
         float4* o = reinterpret_cast<float4*>(static_cast<float*>(p.out) + (size_t)row * p.ldc + col);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) o[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        o[0] = make_float4(v[0], v[1], v[2], v[3]);
+        o[1] = make_float4(v[4], v[5], v[6], v[7]);
     } else {
-        uint4* o = reinterpret_cast<uint4*>(static_cast<bf16*>(p.out) + (size_t)row * p.ldc + col);
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            uint4 u;
-            u.x = pack_bf16x2(v[8 * i + 0], v[8 * i + 1]);
-            u.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
-            u.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]);
-            u.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
-            o[i] = u;
-        }
+        uint4 u;
+        u.x = pack_bf16x2(v[0], v[1]);
+        u.y = pack_bf16x2(v[2], v[3]);
+        u.z = pack_bf16x2(v[4], v[5]);
+        u.w = pack_bf16x2(v[6], v[7]);
+        *reinterpret_cast<uint4*>(static_cast<bf16*>(p.out) + (size_t)row * p.ldc + col) = u;
     }
 }
 
@@ -207,35 +200,65 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tcgen05_kernel(const __gr
         }
     } else {
         // ================= epilogue warps =================
+        // Phase A: TMEM -> registers -> fp32 staging tile in the (now idle) smem ring, one row per thread.
+        // Phase B: each warp re-reads ITS 32 rows with lanes running along the columns, so every global
+        //          access (residual load, output store, split-K reduction) is a coalesced 16/32-byte vector.
         const int q = warp & 3;              // TMEM lane quarter this warp may access
         const int r_in_tile = q * 32 + lane;
-        const int row = m0 + r_in_tile;
-        const bool row_ok = (r_in_tile < p.rows_valid) && (row < p.M);
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
         const int epi_tid = threadIdx.x - 64;  // 0..127
+        const int pitch_f = p.block_n + 4;     // +16 B: conflict-free 16-byte row-strided stores
+        float* stage = reinterpret_cast<float*>(smem);
+        const int tile_id = m_tile * gridDim.y + n_tile;
 
         ptx::mbar_wait(tmem_full_bar, 0);
         ptx::tc_fence_after();
 
-        bool do_final = true;
-        if (p.split_k > 1) {
-            // write fp32 partial tile, then the last-arriving CTA of this tile reduces all splits
-            const int tile_id = m_tile * gridDim.y + n_tile;
-            float* my = p.ws_partials + ((size_t)(tile_id * p.split_k + split) * BLOCK_M + r_in_tile) * p.block_n;
-            for (int c = 0; c < p.block_n; c += 16) {
-                uint32_t r[16];
-                ptx::tmem_ld_32x32b_x16(taddr + c, r);
+        {
+            float4* my_row = reinterpret_cast<float4*>(stage + (size_t)r_in_tile * pitch_f);
+            for (int c = 0; c < p.block_n; c += 32) {
+                uint32_t r0[16], r1[16];
+                const bool two = (c + 16 < p.block_n);
+                ptx::tmem_ld_32x32b_x16(taddr + c, r0);
+                if (two) ptx::tmem_ld_32x32b_x16(taddr + c + 16, r1);
                 ptx::tmem_ld_wait();
-                float4* o = reinterpret_cast<float4*>(my + c);
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
-                    __stcg(o + i, make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]),
-                                              __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3])));
+                    my_row[c / 4 + i] = make_float4(__uint_as_float(r0[4 * i]), __uint_as_float(r0[4 * i + 1]),
+                                                    __uint_as_float(r0[4 * i + 2]), __uint_as_float(r0[4 * i + 3]));
+                if (two) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        my_row[c / 4 + 4 + i] = make_float4(__uint_as_float(r1[4 * i]), __uint_as_float(r1[4 * i + 1]),
+                                                            __uint_as_float(r1[4 * i + 2]), __uint_as_float(r1[4 * i + 3]));
+                }
+            }
+        }
+        ptx::tc_fence_before();
+        __syncwarp();
+
+        const float* wstage = stage + (size_t)(q * 32) * pitch_f;
+        const int rows_here = min(32, min(p.rows_valid, p.M - m0) - q * 32);  // valid rows of this warp (may be <= 0)
+        bool do_final = true;
+        const float* src = wstage;
+        int src_pitch = pitch_f;
+
+        if (p.split_k > 1) {
+            // every split adds its partial tile into the L2-resident fp32 accumulator (vector reds);
+            // the last-arriving CTA of the tile then runs the real epilogue from it and re-zeroes it.
+            float* acc = p.ws_partials + ((size_t)tile_id * BLOCK_M + q * 32) * p.block_n;
+            const int groups4 = p.block_n / 4;
+            const int items = rows_here * groups4;
+#pragma unroll 4
+            for (int idx = lane; idx < items; idx += 32) {
+                const int rl = idx / groups4, c4 = idx - rl * groups4;
+                const float4 v = *reinterpret_cast<const float4*>(wstage + (size_t)rl * pitch_f + c4 * 4);
+                red_add_v4(acc + (size_t)rl * p.block_n + c4 * 4, v);
             }
             __threadfence();
             ptx::named_bar_sync(1, 128);
             if (epi_tid == 0) {
-                unsigned int prev = atomicAdd(p.ws_counters + tile_id, 1u);
+                const unsigned int prev = atomicAdd(p.ws_counters + tile_id, 1u);
                 const bool last = (prev == (unsigned int)p.split_k - 1);
                 if (last) p.ws_counters[tile_id] = 0;  // self-cleaning
                 __threadfence();
@@ -243,60 +266,52 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tcgen05_kernel(const __gr
             }
             ptx::named_bar_sync(1, 128);
             do_final = (*last_flag != 0);
+            src = acc;
+            src_pitch = p.block_n;
         }
 
-        if (do_final) {
-            const int tile_id = m_tile * gridDim.y + n_tile;
-            const int ncols = (p.epilogue == B200SD_EPI_GEGLU) ? p.block_n / 2 : p.block_n;
-            for (int c = 0; c < ncols; c += 16) {
-                float v[16];
-                if (p.split_k > 1) {
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) v[i] = 0.f;
-                    for (int s = 0; s < p.split_k; ++s) {
-                        const float4* src = reinterpret_cast<const float4*>(
-                            p.ws_partials + ((size_t)(tile_id * p.split_k + s) * BLOCK_M + r_in_tile) * p.block_n + c);
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            float4 t = __ldcg(src + i);
-                            v[4 * i] += t.x; v[4 * i + 1] += t.y; v[4 * i + 2] += t.z; v[4 * i + 3] += t.w;
-                        }
-                    }
-                } else {
-                    uint32_t r[16];
-                    ptx::tmem_ld_32x32b_x16(taddr + c, r);
-                    ptx::tmem_ld_wait();
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+        if (do_final && rows_here > 0) {
+            const bool from_ws = p.split_k > 1;
+            if (p.epilogue == B200SD_EPI_GEGLU) {
+                const int half = p.block_n / 2;
+                const int groups = half / 8;
+                const int items = rows_here * groups;
+#pragma unroll 2
+                for (int idx = lane; idx < items; idx += 32) {
+                    const int rl = idx / groups, c8 = idx - rl * groups;
+                    const float* sp = src + (size_t)rl * src_pitch + c8 * 8;
+                    const float4 a0 = *reinterpret_cast<const float4*>(sp), a1 = *reinterpret_cast<const float4*>(sp + 4);
+                    const float4 g0 = *reinterpret_cast<const float4*>(sp + half), g1 = *reinterpret_cast<const float4*>(sp + half + 4);
+                    const float4* bv = reinterpret_cast<const float4*>(p.bias + n0 + c8 * 8);
+                    const float4* bg = reinterpret_cast<const float4*>(p.bias + n0 + half + c8 * 8);
+                    const float4 bv0 = __ldg(bv), bv1 = __ldg(bv + 1), bg0 = __ldg(bg), bg1 = __ldg(bg + 1);
+                    uint4 u;
+                    u.x = pack_bf16x2((a0.x + bv0.x) * gelu_erf_f(g0.x + bg0.x), (a0.y + bv0.y) * gelu_erf_f(g0.y + bg0.y));
+                    u.y = pack_bf16x2((a0.z + bv0.z) * gelu_erf_f(g0.z + bg0.z), (a0.w + bv0.w) * gelu_erf_f(g0.w + bg0.w));
+                    u.z = pack_bf16x2((a1.x + bv1.x) * gelu_erf_f(g1.x + bg1.x), (a1.y + bv1.y) * gelu_erf_f(g1.y + bg1.y));
+                    u.w = pack_bf16x2((a1.z + bv1.z) * gelu_erf_f(g1.z + bg1.z), (a1.w + bv1.w) * gelu_erf_f(g1.w + bg1.w));
+                    const int row = m0 + q * 32 + rl;
+                    *reinterpret_cast<uint4*>(static_cast<bf16*>(p.out) + (size_t)row * p.ldc + n_tile * half + c8 * 8) = u;
                 }
-                if (p.epilogue == B200SD_EPI_GEGLU) {
-                    // columns [0, bn/2) = value, [bn/2, bn) = gate (weights interleaved per tile on the host)
-                    uint32_t g[16];
-                    ptx::tmem_ld_32x32b_x16(taddr + p.block_n / 2 + c, g);
-                    ptx::tmem_ld_wait();
-                    const float* bv = p.bias + n0 + c;
-                    const float* bg = p.bias + n0 + p.block_n / 2 + c;
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        float val = v[i] + __ldg(bv + i);
-                        float gate = __uint_as_float(g[i]) + __ldg(bg + i);
-                        v[i] = val * gelu_erf_f(gate);
+            } else {
+                const int groups = p.block_n / 8;
+                const int items = rows_here * groups;
+#pragma unroll 4
+                for (int idx = lane; idx < items; idx += 32) {
+                    const int rl = idx / groups, c8 = idx - rl * groups;
+                    float v[8];
+                    if (from_ws) {
+                        float4* ap = reinterpret_cast<float4*>(const_cast<float*>(src) + (size_t)rl * src_pitch + c8 * 8);
+                        const float4 a0 = __ldcg(ap), a1 = __ldcg(ap + 1);
+                        __stcg(ap, make_float4(0.f, 0.f, 0.f, 0.f));   // leave the accumulator clean for the next launch
+                        __stcg(ap + 1, make_float4(0.f, 0.f, 0.f, 0.f));
+                        v[0] = a0.x; v[1] = a0.y; v[2] = a0.z; v[3] = a0.w; v[4] = a1.x; v[5] = a1.y; v[6] = a1.z; v[7] = a1.w;
+                    } else {
+                        const float* sp = src + (size_t)rl * src_pitch + c8 * 8;
+                        const float4 a0 = *reinterpret_cast<const float4*>(sp), a1 = *reinterpret_cast<const float4*>(sp + 4);
+                        v[0] = a0.x; v[1] = a0.y; v[2] = a0.z; v[3] = a0.w; v[4] = a1.x; v[5] = a1.y; v[6] = a1.z; v[7] = a1.w;
                     }
-                    if (row_ok) {
-                        const int col = n_tile * (p.block_n / 2) + c;
-                        uint4* o = reinterpret_cast<uint4*>(static_cast<bf16*>(p.out) + (size_t)row * p.ldc + col);
-#pragma unroll
-                        for (int i = 0; i < 2; ++i) {
-                            uint4 u;
-                            u.x = pack_bf16x2(v[8 * i + 0], v[8 * i + 1]);
-                            u.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
-                            u.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]);
-                            u.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
-                            o[i] = u;
-                        }
-                    }
-                } else if (row_ok) {
-                    epilogue_store16(p, row, n0 + c, v);
+                    epilogue_store8(p, m0 + q * 32 + rl, n0 + c8 * 8, v);
                 }
             }
         }
@@ -438,7 +453,7 @@ extern "C" int b200sd_gemm(const b200sd_gemm_args* a, b200sd_stream_t stream) {
     split = ceil_div(p.num_k_blocks, p.kb_per_split);  // no empty splits
     p.split_k = split;
     if (split > 1) {
-        const size_t need = (size_t)m_tiles * n_tiles * split * BLOCK_M * bn * sizeof(float);
+        const size_t need = (size_t)m_tiles * n_tiles * BLOCK_M * bn * sizeof(float);
         B200SD_REQUIRE(a->workspace != nullptr && a->workspace_bytes >= b200sd_gemm_workspace_bytes(), "gemm: split-K needs the workspace");
         B200SD_REQUIRE(need <= kSplitWsBytes && m_tiles * n_tiles <= kMaxSplitTiles, "gemm: split-K workspace too small (%zu B)", need);
         p.ws_partials = static_cast<float*>(a->workspace);
@@ -451,6 +466,7 @@ extern "C" int b200sd_gemm(const b200sd_gemm_args* a, b200sd_stream_t stream) {
     if (stages > kMaxStages) stages = kMaxStages;
     if (stages < 2) stages = 2;
     p.stages = stages;
+    B200SD_REQUIRE((size_t)stages * stage_bytes >= (size_t)BLOCK_M * (bn + 4) * sizeof(float), "gemm: smem ring smaller than the epilogue staging tile");
     const size_t smem_bytes = (size_t)stages * stage_bytes + 1024 /*align slack*/ + 256 /*barriers*/;
 
     // ---- tensor maps ----

@@ -42,34 +42,54 @@ __global__ void __launch_bounds__(256) small_linear_kernel(const float* __restri
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int warps_total = gridDim.x * 8;
-    for (int n = blockIdx.x * 8 + warp; n < N; n += warps_total) {
-        float acc[kSlRows];
+    constexpr int NF = 4;  // output features per warp pass: NF independent 16-byte weight loads in flight per lane
+    for (int n0 = (blockIdx.x * 8 + warp) * NF; n0 < N; n0 += warps_total * NF) {
+        float acc[NF][kSlRows];
 #pragma unroll
-        for (int r = 0; r < kSlRows; ++r) acc[r] = 0.f;
-        const uint4* wr = reinterpret_cast<const uint4*>(w + (size_t)n * K);
+        for (int f = 0; f < NF; ++f)
+#pragma unroll
+            for (int r = 0; r < kSlRows; ++r) acc[f][r] = 0.f;
         for (int v8 = lane; v8 < K / 8; v8 += 32) {
-            const uint4 u = __ldg(wr + v8);
-            float wf[8];
-            float2 f;
-            f = unpack_bf16x2(u.x); wf[0] = f.x; wf[1] = f.y;
-            f = unpack_bf16x2(u.y); wf[2] = f.x; wf[3] = f.y;
-            f = unpack_bf16x2(u.z); wf[4] = f.x; wf[5] = f.y;
-            f = unpack_bf16x2(u.w); wf[6] = f.x; wf[7] = f.y;
+            uint4 u[NF];
+#pragma unroll
+            for (int f = 0; f < NF; ++f) {
+                const int n = min(n0 + f, N - 1);
+                u[f] = __ldg(reinterpret_cast<const uint4*>(w + (size_t)n * K) + v8);
+            }
+            float xr[kSlRows][8];
 #pragma unroll
             for (int r = 0; r < kSlRows; ++r) {
-                const float* xr = s_in + r * K + v8 * 8;
+                const float4 x0 = *reinterpret_cast<const float4*>(s_in + r * K + v8 * 8);
+                const float4 x1 = *reinterpret_cast<const float4*>(s_in + r * K + v8 * 8 + 4);
+                xr[r][0] = x0.x; xr[r][1] = x0.y; xr[r][2] = x0.z; xr[r][3] = x0.w;
+                xr[r][4] = x1.x; xr[r][5] = x1.y; xr[r][6] = x1.z; xr[r][7] = x1.w;
+            }
 #pragma unroll
-                for (int j = 0; j < 8; ++j) acc[r] += wf[j] * xr[j];
+            for (int f = 0; f < NF; ++f) {
+                float wf[8];
+                float2 t;
+                t = unpack_bf16x2(u[f].x); wf[0] = t.x; wf[1] = t.y;
+                t = unpack_bf16x2(u[f].y); wf[2] = t.x; wf[3] = t.y;
+                t = unpack_bf16x2(u[f].z); wf[4] = t.x; wf[5] = t.y;
+                t = unpack_bf16x2(u[f].w); wf[6] = t.x; wf[7] = t.y;
+#pragma unroll
+                for (int r = 0; r < kSlRows; ++r)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[f][r] += wf[j] * xr[r][j];
             }
         }
 #pragma unroll
-        for (int r = 0; r < kSlRows; ++r) acc[r] = warp_sum(acc[r]);
+        for (int f = 0; f < NF; ++f)
+#pragma unroll
+            for (int r = 0; r < kSlRows; ++r) acc[f][r] = warp_sum(acc[f][r]);
         if (lane == 0) {
-            const float bv = bias ? bias[n] : 0.f;
-            for (int r = 0; r < nb; ++r) {
-                float v = acc[r] + bv;
-                if (silu_out) v = v / (1.0f + expf(-v));
-                out[(size_t)(b0 + r) * N + n] = v;
+            for (int f = 0; f < NF && n0 + f < N; ++f) {
+                const float bv = bias ? bias[n0 + f] : 0.f;
+                for (int r = 0; r < nb; ++r) {
+                    float v = acc[f][r] + bv;
+                    if (silu_out) v = v / (1.0f + expf(-v));
+                    out[(size_t)(b0 + r) * N + n0 + f] = v;
+                }
             }
         }
     }
@@ -224,7 +244,7 @@ extern "C" int b200sd_small_linear(const float* in, const void* w_bf16, const fl
         B200SD_CUDA(cudaFuncSetAttribute(small_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
         configured = true;
     }
-    int gx = ceil_div(N, 8);
+    int gx = ceil_div(N, 8 * 4);
     const int cap = b200sd_num_sms() * 4;
     if (gx > cap) gx = cap;
     dim3 grid(gx, ceil_div(batch, kSlRows));

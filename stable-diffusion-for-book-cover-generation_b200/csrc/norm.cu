@@ -10,45 +10,98 @@ extern std::atomic<long long> g_b200sd_launches;
 namespace {
 
 constexpr int kGnThreads = 256;
-constexpr int kMaxSlabs = 64;
+constexpr int kMaxSlabs = 512;
+constexpr int kCounterFloats = 1024;  // per-image arrival counters (batch <= 1024), must start zeroed
 constexpr int kMaxGroups = 32;
 
-// ---- pass 1: per-(image, slab, group) partial sum / sum of squares -----------------------------
-// grid (slabs, batch); thread owns channel PAIRS (a pair never straddles a group: cpg is even).
-__global__ void __launch_bounds__(kGnThreads) gn_stats_kernel(const bf16* __restrict__ x0, const bf16* __restrict__ x1,
-                                                              int C0, int C1, float* __restrict__ partial, int hw,
-                                                              int groups, int pix_per_slab) {
+// ---- pass 1: per-(image, group) mean / rstd ---------------------------------------------------------
+// grid (slabs, batch).  Each thread owns ONE 16-byte channel vector (8 channels) and walks down the
+// pixels of its slab with several independent loads in flight; per-thread sums are folded into
+// shared per-group accumulators once at the end, each block publishes its partials, and the
+// last block of an image (arrival counter, self-cleaning) reduces the slabs in a fixed order
+// (deterministic) and writes mean / rstd.
+__global__ void __launch_bounds__(1024) gn_stats_kernel(const bf16* __restrict__ x0, const bf16* __restrict__ x1,
+                                                        int C0, int C1, float* __restrict__ partial,
+                                                        float* __restrict__ mean_rstd, unsigned int* __restrict__ counters,
+                                                        int hw, int groups, int pix_per_slab, int rows_per_pass,
+                                                        float eps) {
     __shared__ float s_sum[kMaxGroups], s_sq[kMaxGroups];
+    __shared__ bool s_last;
     const int C = C0 + C1;
+    const int C8 = C / 8;
     const int cpg = C / groups;
-    const int b = blockIdx.y, slab = blockIdx.x;
+    const int b = blockIdx.y, slab = blockIdx.x, slabs = gridDim.x;
     if (threadIdx.x < kMaxGroups) { s_sum[threadIdx.x] = 0.f; s_sq[threadIdx.x] = 0.f; }
     __syncthreads();
+    const int vec = threadIdx.x % C8;
+    const int prow = threadIdx.x / C8;
+    const int c = vec * 8;
+    const bf16* src;
+    int pitch;
+    if (c < C0) { src = x0 + (size_t)b * hw * C0 + c; pitch = C0; }
+    else { src = x1 + (size_t)b * hw * C1 + (c - C0); pitch = C1; }
     const int p_begin = slab * pix_per_slab;
     const int p_end = min(p_begin + pix_per_slab, hw);
-    for (int c2 = threadIdx.x; c2 < C / 2; c2 += blockDim.x) {
-        const int c = 2 * c2;
-        const bf16* src;
-        int pitch, cc;
-        if (c < C0) { src = x0; pitch = C0; cc = c; }
-        else { src = x1; pitch = C1; cc = c - C0; }
-        src += (size_t)b * hw * pitch + cc;
-        float s = 0.f, ss = 0.f;
+    float s[8], ss[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s[j] = 0.f; ss[j] = 0.f; }
+    if (prow < rows_per_pass) {
 #pragma unroll 4
-        for (int p = p_begin; p < p_end; ++p) {
-            float2 f = unpack_bf16x2(__ldg(reinterpret_cast<const uint32_t*>(src + (size_t)p * pitch)));
-            s += f.x + f.y;
-            ss += f.x * f.x + f.y * f.y;
+        for (int pp = p_begin + prow; pp < p_end; pp += rows_per_pass) {
+            const uint4 u = __ldg(reinterpret_cast<const uint4*>(src + (size_t)pp * pitch));
+            const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 f = unpack_bf16x2(w[j]);
+                s[2 * j] += f.x; ss[2 * j] += f.x * f.x;
+                s[2 * j + 1] += f.y; ss[2 * j + 1] += f.y * f.y;
+            }
         }
-        const int g = c / cpg;
-        atomicAdd(&s_sum[g], s);
-        atomicAdd(&s_sq[g], ss);
+        // fold the 8 channels into their groups (runs of equal group id), one shared atomic per run
+        int g = c / cpg;
+        float a = 0.f, q = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int gj = (c + j) / cpg;
+            if (gj != g) {
+                atomicAdd(&s_sum[g], a);
+                atomicAdd(&s_sq[g], q);
+                a = 0.f; q = 0.f; g = gj;
+            }
+            a += s[j];
+            q += ss[j];
+        }
+        atomicAdd(&s_sum[g], a);
+        atomicAdd(&s_sq[g], q);
     }
     __syncthreads();
     if (threadIdx.x < groups) {
-        float* dst = partial + (((size_t)b * gridDim.x + slab) * groups + threadIdx.x) * 2;
-        dst[0] = s_sum[threadIdx.x];
-        dst[1] = s_sq[threadIdx.x];
+        float* dst = partial + (((size_t)b * slabs + slab) * groups + threadIdx.x) * 2;
+        __stcg(dst, s_sum[threadIdx.x]);
+        __stcg(dst + 1, s_sq[threadIdx.x]);
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int prev = atomicAdd(counters + b, 1u);
+        s_last = (prev == (unsigned int)slabs - 1);
+        if (s_last) counters[b] = 0;
+    }
+    __syncthreads();
+    if (s_last && threadIdx.x < groups) {
+        __threadfence();
+        double sum = 0.0, sq = 0.0;
+        for (int i = 0; i < slabs; ++i) {
+            const float* srcp = partial + (((size_t)b * slabs + i) * groups + threadIdx.x) * 2;
+            sum += (double)__ldcg(srcp);
+            sq += (double)__ldcg(srcp + 1);
+        }
+        const double cnt = (double)hw * cpg;
+        const double mean = sum / cnt;
+        double var = sq / cnt - mean * mean;
+        if (var < 0.0) var = 0.0;
+        mean_rstd[((size_t)b * groups + threadIdx.x) * 2] = (float)mean;
+        mean_rstd[((size_t)b * groups + threadIdx.x) * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
     }
 }
 
@@ -56,38 +109,25 @@ __global__ void __launch_bounds__(kGnThreads) gn_stats_kernel(const bf16* __rest
 __global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const bf16* __restrict__ x0, const bf16* __restrict__ x1,
                                                               int C0, int C1, const float* __restrict__ gamma,
                                                               const float* __restrict__ beta, bf16* __restrict__ out,
-                                                              const float* __restrict__ partial, int slabs, int hw,
-                                                              int groups, float eps, int silu, int pix_per_block) {
+                                                              const float* __restrict__ mean_rstd, int hw,
+                                                              int groups, int silu, int pix_per_block) {
     extern __shared__ float2 s_ab[];  // per-channel (scale, shift)
-    __shared__ float s_mean[kMaxGroups], s_rstd[kMaxGroups];
     const int C = C0 + C1;
     const int cpg = C / groups;
     const int b = blockIdx.y;
-    if (threadIdx.x < groups) {
-        double s = 0.0, ss = 0.0;
-        for (int i = 0; i < slabs; ++i) {
-            const float* src = partial + (((size_t)b * slabs + i) * groups + threadIdx.x) * 2;
-            s += (double)src[0];
-            ss += (double)src[1];
-        }
-        const double cnt = (double)hw * cpg;
-        const double mean = s / cnt;
-        double var = ss / cnt - mean * mean;
-        if (var < 0.0) var = 0.0;
-        s_mean[threadIdx.x] = (float)mean;
-        s_rstd[threadIdx.x] = (float)(1.0 / sqrt(var + (double)eps));
-    }
-    __syncthreads();
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         const int g = c / cpg;
-        const float a = s_rstd[g] * __ldg(gamma + c);
-        s_ab[c] = make_float2(a, __ldg(beta + c) - s_mean[g] * a);
+        const float mean = __ldg(mean_rstd + ((size_t)b * groups + g) * 2);
+        const float rstd = __ldg(mean_rstd + ((size_t)b * groups + g) * 2 + 1);
+        const float a = rstd * __ldg(gamma + c);
+        s_ab[c] = make_float2(a, __ldg(beta + c) - mean * a);
     }
     __syncthreads();
     const int vec_per_pix = C / 8;
     const int p_begin = blockIdx.x * pix_per_block;
     const int p_end = min(p_begin + pix_per_block, hw);
     const int total = (p_end - p_begin) * vec_per_pix;
+#pragma unroll 4
     for (int i = threadIdx.x; i < total; i += blockDim.x) {
         const int p = p_begin + i / vec_per_pix;
         const int c = (i % vec_per_pix) * 8;
@@ -150,21 +190,27 @@ extern "C" int b200sd_groupnorm_silu(const void* x0, const void* x1, int C0, int
     B200SD_REQUIRE(x0 && gamma && beta && out && stats_ws, "groupnorm: null pointer");
     if (!x1) C1 = 0;
     const int C = C0 + C1;
-    B200SD_REQUIRE(batch > 0 && hw > 0 && batch <= 65535, "groupnorm: bad batch/hw");
+    B200SD_REQUIRE(batch > 0 && hw > 0 && batch <= kCounterFloats, "groupnorm: bad batch/hw");
     B200SD_REQUIRE(groups > 0 && groups <= kMaxGroups && C % groups == 0 && (C / groups) % 2 == 0,
                    "groupnorm: C=%d groups=%d unsupported (channels per group must be even)", C, groups);
     B200SD_REQUIRE(C0 % 8 == 0 && C1 % 8 == 0, "groupnorm: channel counts must be multiples of 8");
     B200SD_REQUIRE(C * sizeof(float2) <= 48 * 1024, "groupnorm: C=%d too large", C);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    // slabs: enough blocks to fill the machine, but at least 32 pixels per slab
-    int slabs = ceil_div(b200sd_num_sms() * 2, batch);
+    const int C8 = C / 8;
+    B200SD_REQUIRE(C8 <= 1024, "groupnorm: C=%d too large", C);
+    const int rows_per_pass = (C8 >= 256) ? 1 : 256 / C8;
+    const int threads = ((C8 * rows_per_pass + 31) / 32) * 32;
+    // workspace layout: [batch counters (as uint)] [mean/rstd 2*batch*groups] [partials 2*batch*slabs*groups]
+    unsigned int* counters = reinterpret_cast<unsigned int*>(stats_ws);
+    float* mean_rstd = stats_ws + kCounterFloats;
+    float* partial = mean_rstd + 2 * (size_t)batch * kMaxGroups;
+    int slabs = ceil_div(b200sd_num_sms() * 4, batch);
     if (slabs > kMaxSlabs) slabs = kMaxSlabs;
-    if (slabs > ceil_div(hw, 32)) slabs = ceil_div(hw, 32);
-    if (slabs < 1) slabs = 1;
-    const int pps = ceil_div(hw, slabs);
+    int pps = ceil_div(hw, slabs);
+    pps = ceil_div(pps, rows_per_pass) * rows_per_pass;
     slabs = ceil_div(hw, pps);
-    gn_stats_kernel<<<dim3(slabs, batch), kGnThreads, 0, s>>>(static_cast<const bf16*>(x0), static_cast<const bf16*>(x1),
-                                                             C0, C1, stats_ws, hw, groups, pps);
+    gn_stats_kernel<<<dim3(slabs, batch), threads, 0, s>>>(static_cast<const bf16*>(x0), static_cast<const bf16*>(x1), C0, C1,
+                                                          partial, mean_rstd, counters, hw, groups, pps, rows_per_pass, eps);
     COUNT_LAUNCH();
     B200SD_LAUNCH_CHECK();
     int blocks = ceil_div(b200sd_num_sms() * 4, batch);
@@ -173,15 +219,17 @@ extern "C" int b200sd_groupnorm_silu(const void* x0, const void* x1, int C0, int
     if (ppb < min_ppb) ppb = min_ppb;
     blocks = ceil_div(hw, ppb);
     gn_apply_kernel<<<dim3(blocks, batch), kGnThreads, C * sizeof(float2), s>>>(
-        static_cast<const bf16*>(x0), static_cast<const bf16*>(x1), C0, C1, gamma, beta, static_cast<bf16*>(out), stats_ws,
-        slabs, hw, groups, eps, silu, ppb);
+        static_cast<const bf16*>(x0), static_cast<const bf16*>(x1), C0, C1, gamma, beta, static_cast<bf16*>(out), mean_rstd,
+        hw, groups, silu, ppb);
     COUNT_LAUNCH();
     B200SD_LAUNCH_CHECK();
     return B200SD_OK;
 }
 
 // workspace floats needed by b200sd_groupnorm_silu for a given batch: 2 * batch * kMaxSlabs * kMaxGroups
-extern "C" int b200sd_groupnorm_workspace_floats(int batch) { return 2 * batch * kMaxSlabs * kMaxGroups; }
+extern "C" int b200sd_groupnorm_workspace_floats(int batch) {
+    return kCounterFloats + 2 * batch * kMaxGroups + 2 * batch * kMaxSlabs * kMaxGroups;
+}
 
 extern "C" int b200sd_layernorm(const void* x, const float* gamma, const float* beta, void* out, int rows, int C,
                                 float eps, b200sd_stream_t stream) {

@@ -226,7 +226,7 @@ def conv_out(x_nhwc, w_packed, bias, out_nchw):
 
 def groupnorm_silu(x0, x1, gamma, beta, out, batch, hw, groups=32, eps=1e-5, silu=True):
     _chk(x0, x1, gamma, beta, out)
-    ws = _workspace("gn", lib().b200sd_groupnorm_workspace_floats(batch) * 4, x0.device, zero=False)
+    ws = _workspace("gn", lib().b200sd_groupnorm_workspace_floats(batch) * 4, x0.device)
     C0 = x0.shape[-1]
     C1 = x1.shape[-1] if x1 is not None else 0
     check(lib().b200sd_groupnorm_silu(_p(x0), _p(x1), C0, C1, _p(gamma), _p(beta), _p(out), _p(ws), batch, hw, groups,
