@@ -10,7 +10,7 @@ extern std::atomic<long long> g_b200sd_launches;
 namespace {
 
 constexpr int kGnThreads = 256;
-constexpr int kMaxSlabs = 512;
+constexpr int kMaxSlabs = 128;
 constexpr int kCounterFloats = 1024;  // per-image arrival counters (batch <= 1024), must start zeroed
 constexpr int kMaxGroups = 32;
 
@@ -88,20 +88,31 @@ __global__ void __launch_bounds__(1024) gn_stats_kernel(const bf16* __restrict__
         if (s_last) counters[b] = 0;
     }
     __syncthreads();
-    if (s_last && threadIdx.x < groups) {
+    if (s_last) {
+        // 8 threads per group walk the slabs (fixed assignment -> deterministic), then a shuffle tree
         __threadfence();
+        const int g = threadIdx.x >> 3, part = threadIdx.x & 7;
         double sum = 0.0, sq = 0.0;
-        for (int i = 0; i < slabs; ++i) {
-            const float* srcp = partial + (((size_t)b * slabs + i) * groups + threadIdx.x) * 2;
-            sum += (double)__ldcg(srcp);
-            sq += (double)__ldcg(srcp + 1);
+        if (g < groups) {
+            for (int i = part; i < slabs; i += 8) {
+                const float* srcp = partial + (((size_t)b * slabs + i) * groups + g) * 2;
+                sum += (double)__ldcg(srcp);
+                sq += (double)__ldcg(srcp + 1);
+            }
         }
-        const double cnt = (double)hw * cpg;
-        const double mean = sum / cnt;
-        double var = sq / cnt - mean * mean;
-        if (var < 0.0) var = 0.0;
-        mean_rstd[((size_t)b * groups + threadIdx.x) * 2] = (float)mean;
-        mean_rstd[((size_t)b * groups + threadIdx.x) * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {
+            sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            sq += __shfl_xor_sync(0xffffffffu, sq, o);
+        }
+        if (g < groups && part == 0) {
+            const double cnt = (double)hw * cpg;
+            const double mean = sum / cnt;
+            double var = sq / cnt - mean * mean;
+            if (var < 0.0) var = 0.0;
+            mean_rstd[((size_t)b * groups + g) * 2] = (float)mean;
+            mean_rstd[((size_t)b * groups + g) * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
+        }
     }
 }
 
@@ -199,12 +210,13 @@ extern "C" int b200sd_groupnorm_silu(const void* x0, const void* x1, int C0, int
     const int C8 = C / 8;
     B200SD_REQUIRE(C8 <= 1024, "groupnorm: C=%d too large", C);
     const int rows_per_pass = (C8 >= 256) ? 1 : 256 / C8;
-    const int threads = ((C8 * rows_per_pass + 31) / 32) * 32;
+    int threads = ((C8 * rows_per_pass + 31) / 32) * 32;
+    if (threads < 256) threads = 256;  // the final reduce uses 8 threads per group
     // workspace layout: [batch counters (as uint)] [mean/rstd 2*batch*groups] [partials 2*batch*slabs*groups]
     unsigned int* counters = reinterpret_cast<unsigned int*>(stats_ws);
     float* mean_rstd = stats_ws + kCounterFloats;
     float* partial = mean_rstd + 2 * (size_t)batch * kMaxGroups;
-    int slabs = ceil_div(b200sd_num_sms() * 4, batch);
+    int slabs = ceil_div(b200sd_num_sms() * 2, batch);
     if (slabs > kMaxSlabs) slabs = kMaxSlabs;
     int pps = ceil_div(hw, slabs);
     pps = ceil_div(pps, rows_per_pass) * rows_per_pass;

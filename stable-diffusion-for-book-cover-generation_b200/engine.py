@@ -112,15 +112,15 @@ class Engine:
         n_tp = Wp["tproj"]["n"]
         self.tproj = torch.empty(N, n_tp, **f32)
         te = Wp["temb"]
-        P.append(lambda: ops.timestep_embedding(self.in_t, boc[0], out=t_sin))
-        P.append(lambda: ops.small_linear(t_sin, te["w1"], te["b1"], silu_out=True, out=t_h))
-        P.append(lambda: ops.small_linear(t_h, te["w2"], te["b2"], out=t_emb))
-        P.append(lambda: ops.small_linear(t_emb, Wp["tproj"]["w"], Wp["tproj"]["b"], silu_in=True, out=self.tproj))
+        P.append(lambda: ops.timestep_embedding(self.in_t, boc[0], out=t_sin), "time_embed")
+        P.append(lambda: ops.small_linear(t_sin, te["w1"], te["b1"], silu_out=True, out=t_h), "time_embed")
+        P.append(lambda: ops.small_linear(t_h, te["w2"], te["b2"], out=t_emb), "time_embed")
+        P.append(lambda: ops.small_linear(t_emb, Wp["tproj"]["w"], Wp["tproj"]["b"], silu_in=True, out=self.tproj), "time_embed", 0, "time_emb_proj x22")
 
         # ---- conv_in ----
         h, w = self.H, self.W
         x = pool.get(N * h * w, boc[0])
-        P.append(lambda x=x: ops.conv_in(self.in_sample, Wp["conv_in"]["w"], Wp["conv_in"]["b"], x))
+        P.append(lambda x=x: ops.conv_in(self.in_sample, Wp["conv_in"]["w"], Wp["conv_in"]["b"], x), "conv_io", 0, "conv_in")
 
         self._tap("conv_in", x, h, w)
         skips = [(x, boc[0])]
@@ -221,7 +221,7 @@ class Engine:
                 wd = Wp[f"down{i}.ds"]
                 Cc = boc[i]
                 col = pool.get(N * (h // 2) * (w // 2), 9 * Cc)
-                P.append(lambda x=x, col=col, h=h, w=w: ops.im2col_s2(x, col, N, h, w))
+                P.append(lambda x=x, col=col, h=h, w=w: ops.im2col_s2(x, col, N, h, w), "resample", 0, "im2col_s2")
                 h, w = h // 2, w // 2
                 y = pool.get(N * h * w, Cc)
                 self._gemm(P, col, wd["w"], y, bias=wd["b"])
@@ -259,7 +259,7 @@ class Engine:
                 wu = Wp[f"up{i}.us"]
                 Cc = x.shape[1]
                 up = pool.get(N * 4 * h * w, Cc)
-                P.append(lambda x=x, up=up, h=h, w=w: ops.upsample2x(x, up, N, h, w))
+                P.append(lambda x=x, up=up, h=h, w=w: ops.upsample2x(x, up, N, h, w), "resample", 0, "upsample2x")
                 release(x)
                 h, w = 2 * h, 2 * w
                 y = pool.get(N * h * w, Cc)
@@ -272,7 +272,7 @@ class Engine:
         wo = Wp["conv_out"]
         t = pool.get(N * h * w, boc[0])
         P.append(lambda x=x, t=t: ops.groupnorm_silu(x, None, wo["g"], wo["beta"], t, N, h * w, 32, cfg.norm_eps, True), "groupnorm")
-        P.append(lambda t=t: ops.conv_out(t, wo["w"], wo["b"], self.out))
+        P.append(lambda t=t: ops.conv_out(t, wo["w"], wo["b"], self.out), "conv_io", 0, "conv_out")
         self.activation_bytes = pool.total
 
     # -- execution --------------------------------------------------------------------------------
@@ -313,30 +313,45 @@ class Engine:
                 self.graph.replay()
             return self.out.clone()
 
-    def profile(self, iters=3):
-        """Eager run with CUDA events around every plan entry -> {kind: (ms, flops, launches)} per step."""
-        evs = []
+    def profile(self, iters=3, reps=4):
+        """Per-launch device time of every plan entry, measured warm and without host launch gaps:
+        each entry is captured into its own CUDA graph holding `reps` back-to-back launches and
+        the replay is timed with CUDA events.  Returns ({kind: [ms, flops, launches]} per step,
+        [(name, ms, flops)] per entry)."""
         with torch.cuda.device(self.device):
             self._run_plan()
             torch.cuda.synchronize()
-            acc = {}
+            graphs = []
+            side = torch.cuda.Stream()
+            for op, (kind, flops, name) in zip(self.plan, self.plan.meta):
+                if kind == "tap":
+                    continue
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=side):
+                    for _ in range(reps):
+                        op()
+                graphs.append((g, kind, flops, name))
+            torch.cuda.synchronize()
+            times = [0.0] * len(graphs)
             for _ in range(iters):
+                self._run_plan()   # restore a coherent activation state, warm L2 with the real data flow
                 evs = []
-                for op, (kind, flops, name) in zip(self.plan, self.plan.meta):
-                    if kind == "tap":
-                        continue
+                for g, kind, flops, name in graphs:
                     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                     e0.record()
-                    op()
+                    g.replay()
                     e1.record()
-                    evs.append((kind, flops, name, e0, e1))
+                    evs.append((e0, e1))
                 torch.cuda.synchronize()
-                for kind, flops, name, e0, e1 in evs:
-                    a = acc.setdefault(kind, [0.0, 0.0, 0])
-                    a[0] += e0.elapsed_time(e1) / iters
-                    a[1] += flops / iters
-                    a[2] += 1
-            for a in acc.values():
-                a[2] //= iters
-            per_op = [(name or kind, e0.elapsed_time(e1), flops) for kind, flops, name, e0, e1 in evs]
+                for i, (e0, e1) in enumerate(evs):
+                    times[i] += e0.elapsed_time(e1) / reps / iters
+            acc, per_op = {}, []
+            for t, (g, kind, flops, name) in zip(times, graphs):
+                a = acc.setdefault(kind, [0.0, 0.0, 0])
+                a[0] += t
+                a[1] += flops
+                a[2] += 1
+                per_op.append((name or kind, t, flops))
+            self._run_plan()
+            torch.cuda.synchronize()
         return acc, per_op
