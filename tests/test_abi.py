@@ -1,0 +1,83 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads, exports every symbol include/b200sd.h
+declares, the ctypes table covers exactly those symbols, and the product package never touches the
+oracle.  No compute calls (no GPU needed)."""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HDR = os.path.join(ROOT, "include", "b200sd.h")
+PKG = os.path.join(ROOT, "stable-diffusion-for-book-cover-generation_b200")
+
+
+def _header_symbols():
+    src = open(HDR).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(b200sd_[a-z0-9_]+)\s*\(", src)))
+
+
+@pytest.fixture(scope="module")
+def built():
+    import __graft_entry__ as g
+    g.build()
+    from b200sd import _lib
+    return _lib
+
+
+def test_header_declares_expected_entry_points():
+    syms = _header_symbols()
+    for s in ("b200sd_gemm", "b200sd_attention", "b200sd_cfg_ddim_step", "b200sd_cfg_plms_step", "b200sd_add_noise",
+              "b200sd_mse_loss_fwd", "b200sd_mse_loss_bwd", "b200sd_groupnorm_silu", "b200sd_layernorm", "b200sd_last_error"):
+        assert s in syms
+
+
+def test_library_exports_every_declared_symbol(built):
+    L = ctypes.CDLL(built.LIB_PATH)
+    for s in _header_symbols():
+        assert hasattr(L, s), f"{s} declared in include/b200sd.h but not exported by libb200sd.so"
+
+
+def test_ctypes_table_matches_header(built):
+    assert sorted(built.SIGNATURES) == _header_symbols()
+    lib = built.lib()
+    assert lib.b200sd_version() >= 100
+    assert lib.b200sd_gemm_workspace_bytes() > 0
+    assert lib.b200sd_geglu_tile(2560) % 32 == 0
+    assert isinstance(lib.b200sd_last_error(), bytes)
+
+
+def test_gemm_args_struct_layout_matches_header(built):
+    src = re.sub(r"/\*.*?\*/", "", open(HDR).read(), flags=re.S)
+    body = re.search(r"typedef struct b200sd_gemm_args \{(.*?)\} b200sd_gemm_args;", src, flags=re.S).group(1)
+    names = []
+    for decl in body.split(";"):
+        decl = decl.strip()
+        if not decl:
+            continue
+        for part in decl.split(","):
+            names.append(re.findall(r"[A-Za-z_][A-Za-z0-9_]*", part)[-1])
+    assert names == [f[0] for f in built.GemmArgs._fields_]
+
+
+def test_sass_is_blackwell_native(built):
+    out = subprocess.run(["cuobjdump", "-sass", built.LIB_PATH], capture_output=True, text=True).stdout
+    for mnem in ("UTCHMMA", "UTMALDG", "LDTM"):   # tcgen05.mma, TMA load, tcgen05.ld
+        assert mnem in out, mnem
+
+
+def test_product_package_never_imports_oracle():
+    for dirpath, _, files in os.walk(PKG):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f"{f} imports the oracle"
+
+
+def test_missing_library_fails_loudly(built, monkeypatch):
+    monkeypatch.setattr(built, "_lib", None)
+    monkeypatch.setattr(built, "LIB_PATH", "/nonexistent/libb200sd.so")
+    with pytest.raises(built.B200SDError):
+        built.lib()

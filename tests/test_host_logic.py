@@ -1,0 +1,114 @@
+"""CPU tests of the host-side mirror of the diffusers surface: state-dict compatibility, scheduler
+timestep tables and configuration behaviour, weight packing.  No GPU."""
+import json
+import os
+
+import pytest
+import torch
+
+from oracle import schedulers_ref as R
+from oracle import unet_ref as U
+
+
+def test_facade_state_dict_is_diffusers_compatible():
+    from b200sd.unet import UNet2DConditionModel
+    ref = U.make_oracle_unet(seed=0, **U.TINY_OVERRIDES)
+    m = UNet2DConditionModel(**U.TINY_OVERRIDES)
+    sd, msd = ref.state_dict(), m.state_dict()
+    assert list(sd.keys()) == list(msd.keys()) or set(sd) == set(msd)
+    for k in sd:
+        assert sd[k].shape == msd[k].shape, k
+    m.load_state_dict(sd, strict=True)
+    assert m.in_channels == 4 and m.config.cross_attention_dim == 64 and m.config["attention_head_dim"] == 2
+
+
+def test_facade_full_size_key_set():
+    from b200sd.unet import UNet2DConditionModel
+    with torch.device("meta"):
+        ref = U.UNet2DConditionModelRef()
+    m = UNet2DConditionModel.__new__(UNet2DConditionModel)
+    torch.nn.Module.__init__(m)
+    # build on the meta device to avoid allocating 3.4 GB
+    with torch.device("meta"):
+        orig = UNet2DConditionModel.reset_parameters
+        UNet2DConditionModel.reset_parameters = lambda self: None
+        try:
+            m = UNet2DConditionModel()
+        finally:
+            UNet2DConditionModel.reset_parameters = orig
+    assert set(m.state_dict()) == set(ref.state_dict())
+    assert sum(p.numel() for p in m.parameters()) == 859_520_964
+
+
+def test_save_and_from_pretrained_roundtrip(tmp_path):
+    from b200sd.unet import UNet2DConditionModel
+    m = UNet2DConditionModel(**U.TINY_OVERRIDES)
+    m.save_pretrained(str(tmp_path / "unet"))
+    cfg = json.load(open(tmp_path / "unet" / "config.json"))
+    assert cfg["_class_name"] == "UNet2DConditionModel" and cfg["cross_attention_dim"] == 64
+    m2 = UNet2DConditionModel.from_pretrained(str(tmp_path), subfolder="unet")
+    for (k, a), (_, b) in zip(m.state_dict().items(), m2.state_dict().items()):
+        assert torch.equal(a, b), k
+
+
+def test_unet_rejects_cpu_inputs_and_bad_config():
+    from b200sd._lib import B200SDError
+    from b200sd.unet import UNet2DConditionModel
+    m = UNet2DConditionModel(**U.TINY_OVERRIDES).eval()
+    with pytest.raises(B200SDError):
+        m(torch.randn(1, 4, 16, 16), 1, torch.randn(1, 77, 64))      # CPU tensors: there is no CPU fallback
+    with pytest.raises(TypeError):
+        UNet2DConditionModel(not_a_field=1)
+    with pytest.raises(NotImplementedError):
+        UNet2DConditionModel(block_out_channels=(48, 96, 96, 96))
+
+
+def test_scheduler_tables_match_oracle():
+    from b200sd.schedulers import DDIMScheduler, DDPMScheduler, PNDMScheduler
+    kw = dict(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear")
+    d = DDIMScheduler(clip_sample=False, set_alpha_to_one=False, **kw)
+    r = R.DDIMSchedulerRef(clip_sample=False, set_alpha_to_one=False)
+    assert torch.equal(d.alphas_cumprod, r.alphas_cumprod)
+    for n in (50, 75, 20, 1000):
+        d.set_timesteps(n)
+        r.set_timesteps(n)
+        assert d.timesteps.tolist() == r.timesteps.tolist()
+    assert d.init_noise_sigma == 1.0 and d.num_train_timesteps == 1000 and d.config.num_train_timesteps == 1000
+    x = torch.randn(2, 3)
+    assert d.scale_model_input(x, 5) is x
+    for off in (0, 1):
+        p = PNDMScheduler(skip_prk_steps=True, steps_offset=off, **kw)
+        rp = R.PNDMSchedulerRef(skip_prk_steps=True, steps_offset=off)
+        p.set_timesteps(50)
+        rp.set_timesteps(50)
+        assert p.timesteps.tolist() == rp.timesteps.tolist() and len(p.timesteps) == 51
+    assert DDPMScheduler(**kw).num_train_timesteps == 1000
+
+
+def test_scheduler_config_errors_and_roundtrip(tmp_path):
+    from b200sd.schedulers import DDIMScheduler, PNDMScheduler
+    with pytest.raises(NotImplementedError):
+        PNDMScheduler(skip_prk_steps=False)
+    with pytest.raises(NotImplementedError):
+        DDIMScheduler(clip_sample=True)
+    with pytest.raises(TypeError):
+        DDIMScheduler(bogus=1)
+    d = DDIMScheduler(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear", clip_sample=False,
+                      set_alpha_to_one=False)
+    with pytest.raises(ValueError):
+        d.step(torch.zeros(1), 10, torch.zeros(1))       # set_timesteps not called
+    d.save_config(str(tmp_path / "scheduler"))
+    d2 = DDIMScheduler.from_config(str(tmp_path), subfolder="scheduler")
+    assert vars(d2.config) == vars(d.config)
+
+
+def test_packing_layouts():
+    from b200sd import packing
+    w = torch.randn(6, 4, 3, 3)
+    p = packing.pack_conv3x3(w).float()
+    assert p.shape == (6, 36)
+    assert torch.allclose(p[2, (1 * 3 + 2) * 4 + 3], w[2, 3, 1, 2].bfloat16().float())
+    wg, bg = packing.pack_geglu(torch.arange(16.)[:, None].repeat(1, 2), torch.arange(16.), 8)
+    # tile 8 -> [4 values | 4 gates] per tile: rows 0-3, 8-11, 4-7, 12-15
+    assert bg.tolist() == [0, 1, 2, 3, 8, 9, 10, 11, 4, 5, 6, 7, 12, 13, 14, 15]
+    assert wg[:, 0].float().tolist() == bg.tolist()
