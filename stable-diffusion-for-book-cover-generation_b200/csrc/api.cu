@@ -2,6 +2,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <mutex>
 
 #include "common.cuh"
@@ -19,6 +20,15 @@ void b200sd_set_error(const char* fmt, ...) {
 extern "C" const char* b200sd_last_error(void) { return g_err; }
 extern "C" int b200sd_version(void) { return 100; }
 extern "C" int64_t b200sd_launch_count(void) { return g_b200sd_launches.load(); }
+
+bool b200sd_pdl_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("B200SD_PDL");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v != 0;
+}
 
 int b200sd_num_sms() {
     static int sms = 0;

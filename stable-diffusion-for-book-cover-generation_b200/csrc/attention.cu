@@ -72,6 +72,7 @@ __global__ void __launch_bounds__(kThreads, (DP <= 80) ? 2 : 1)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int chunks = D / 8;
 
+    ptx::pdl_trigger();
     // zero the head-dim padding once (cp.async never touches it)
     {
         constexpr int PAD16 = PITCH / 16;  // 16-byte slots per row incl. the bank-skew slot
@@ -82,6 +83,7 @@ __global__ void __launch_bounds__(kThreads, (DP <= 80) ? 2 : 1)
         }
     }
 
+    ptx::pdl_wait();
     const bf16* qg = q + ((size_t)b * Sq + q0) * ldq + h * D;
     const bf16* kg = k + (size_t)b * Skv * ldk + h * D;
     const bf16* vg = v + (size_t)b * Skv * ldv + h * D;
@@ -225,8 +227,8 @@ int launch_attention(const bf16* q, const bf16* k, const bf16* v, bf16* out, int
         configured = true;
     }
     dim3 grid(ceil_div(Sq, kBM), heads, batch);
-    attention_kernel<DP><<<grid, kThreads, smem, s>>>(q, k, v, out, Sq, Skv, D, ldq, ldk, ldv, ldo,
-                                                      scale * 1.4426950408889634f);
+    B200SD_CUDA(b200sd_launch(attention_kernel<DP>, dim3(grid), dim3(kThreads), smem, s, q, k, v, out, Sq, Skv, D, ldq, ldk, ldv, ldo,
+                                                      scale * 1.4426950408889634f));
     g_b200sd_launches.fetch_add(1, std::memory_order_relaxed);
     B200SD_LAUNCH_CHECK();
     return B200SD_OK;

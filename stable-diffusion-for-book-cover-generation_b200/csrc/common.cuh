@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <utility>
 
 #include "../../include/b200sd.h"
 
@@ -41,6 +42,8 @@ static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
 // number of SMs of the current device (cached)
 int b200sd_num_sms();
+// programmatic dependent launch (PDL) between consecutive kernels of a stream (B200SD_PDL=0 disables)
+bool b200sd_pdl_enabled();
 
 // Encode a tiled TMA descriptor (driver entry point fetched through the runtime; no -lcuda needed).
 // dims/strides are innermost-first; strides are in bytes for dims 1..rank-1.
@@ -49,10 +52,35 @@ int b200sd_make_tmap(CUtensorMap* out, const void* base, int rank, const uint64_
                      CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
 
 #ifdef __CUDACC__
+// Launch with the programmatic-stream-serialization attribute: the next kernel's CTAs may become
+// resident (and run their prologue up to ptx::pdl_wait()) while this kernel drains.  Every kernel of
+// the library calls ptx::pdl_wait() before its first dependent global access, which keeps the
+// stream's transitive ordering intact.
+template <typename... KArgs, typename... Args>
+static inline cudaError_t b200sd_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                        cudaStream_t stream, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = b200sd_pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
 // ----------------------------------------------------------------------------------------------
 // device helpers
 // ----------------------------------------------------------------------------------------------
 namespace ptx {
+
+// PDL: wait until the preceding kernel of the stream has completed and its writes are visible
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// PDL: allow the next kernel of the stream to start launching
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));

@@ -91,6 +91,8 @@ __global__ void __launch_bounds__(kThreads) cfg_ddim_kernel(const void* __restri
                                                             const void* __restrict__ eps_c,
                                                             const void* __restrict__ x, void* __restrict__ out,
                                                             void* __restrict__ eps_out, int64_t n, int64_t nvec, DdimCoef c) {
+    ptx::pdl_trigger();
+    ptx::pdl_wait();
     const bool cfg = eps_c != nullptr;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
@@ -131,6 +133,8 @@ __global__ void __launch_bounds__(kThreads) cfg_plms_kernel(const void* __restri
                                                             const void* __restrict__ eps_c,
                                                             const void* __restrict__ x, void* __restrict__ out,
                                                             void* __restrict__ eps_out, int64_t n, int64_t nvec, PlmsArgs a) {
+    ptx::pdl_trigger();
+    ptx::pdl_wait();
     const bool cfg = eps_c != nullptr;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
@@ -176,6 +180,8 @@ __global__ void __launch_bounds__(kThreads) add_noise_kernel(const void* __restr
                                                              const float* __restrict__ sa_table,
                                                              const float* __restrict__ sb_table,
                                                              void* __restrict__ out, int64_t per_sample, int64_t nvec, int T) {
+    ptx::pdl_trigger();
+    ptx::pdl_wait();
     const int b = blockIdx.y;
     int64_t t = timesteps[b];
     t = t < 0 ? 0 : (t >= T ? T - 1 : t);
@@ -221,6 +227,8 @@ __global__ void __launch_bounds__(kThreads) mse_fwd_kernel(const void* __restric
                                                            int64_t n, int64_t nvec) {
     __shared__ float sm[32];
     __shared__ bool is_last;
+    ptx::pdl_trigger();
+    ptx::pdl_wait();
     float acc = 0.f;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
@@ -272,6 +280,8 @@ __global__ void __launch_bounds__(kThreads) mse_bwd_kernel(const void* __restric
                                                            const void* __restrict__ target,
                                                            const float* __restrict__ grad_loss,
                                                            void* __restrict__ grad_pred, int64_t n, int64_t nvec) {
+    ptx::pdl_trigger();
+    ptx::pdl_wait();
     const float s = __ldg(grad_loss) * 2.0f / (float)n;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
@@ -292,12 +302,16 @@ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 
 
 }  // namespace
 
-#define DISPATCH2(E, X, KERNEL, ...)                                                            \
-    do {                                                                                        \
-        if ((E) == B200SD_F32 && (X) == B200SD_F32) KERNEL<B200SD_F32, B200SD_F32> __VA_ARGS__; \
-        else if ((E) == B200SD_BF16 && (X) == B200SD_F32) KERNEL<B200SD_BF16, B200SD_F32> __VA_ARGS__; \
-        else if ((E) == B200SD_F32 && (X) == B200SD_BF16) KERNEL<B200SD_F32, B200SD_BF16> __VA_ARGS__; \
-        else KERNEL<B200SD_BF16, B200SD_BF16> __VA_ARGS__;                                      \
+#define DISPATCH2(E, X, KERNEL, GRID, STREAM, ...)                                                                   \
+    do {                                                                                                              \
+        if ((E) == B200SD_F32 && (X) == B200SD_F32)                                                                   \
+            B200SD_CUDA(b200sd_launch(KERNEL<B200SD_F32, B200SD_F32>, dim3(GRID), dim3(kThreads), 0, STREAM, __VA_ARGS__));  \
+        else if ((E) == B200SD_BF16 && (X) == B200SD_F32)                                                             \
+            B200SD_CUDA(b200sd_launch(KERNEL<B200SD_BF16, B200SD_F32>, dim3(GRID), dim3(kThreads), 0, STREAM, __VA_ARGS__)); \
+        else if ((E) == B200SD_F32 && (X) == B200SD_BF16)                                                             \
+            B200SD_CUDA(b200sd_launch(KERNEL<B200SD_F32, B200SD_BF16>, dim3(GRID), dim3(kThreads), 0, STREAM, __VA_ARGS__)); \
+        else                                                                                                          \
+            B200SD_CUDA(b200sd_launch(KERNEL<B200SD_BF16, B200SD_BF16>, dim3(GRID), dim3(kThreads), 0, STREAM, __VA_ARGS__)); \
     } while (0)
 
 static bool dtype_ok(int d) { return d == B200SD_F32 || d == B200SD_BF16; }
@@ -314,7 +328,7 @@ extern "C" int b200sd_cfg_ddim_step(const void* eps_u, const void* eps_c, const 
     if (n == 0) return B200SD_OK;
     DdimCoef c{guidance, sa_t, sb_t, sa_p, sb_p};
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    DISPATCH2(eps_dtype, x_dtype, cfg_ddim_kernel, <<<grid_for(vec ? n / 8 : n), kThreads, 0, s>>>(eps_u, eps_c, x, out, eps_out, n, nvec, c));
+    DISPATCH2(eps_dtype, x_dtype, cfg_ddim_kernel, grid_for(vec ? n / 8 : n), s, eps_u, eps_c, x, out, eps_out, n, nvec, c);
     COUNT_LAUNCH();
     B200SD_LAUNCH_CHECK();
     return B200SD_OK;
@@ -339,7 +353,7 @@ extern "C" int b200sd_cfg_plms_step(const void* eps_u, const void* eps_c, const 
     a.nhist = nhist; a.g = guidance; a.cx = cx; a.ce = ce;
     if (n == 0) return B200SD_OK;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    DISPATCH2(eps_dtype, x_dtype, cfg_plms_kernel, <<<grid_for(vec ? n / 8 : n), kThreads, 0, s>>>(eps_u, eps_c, x, out, eps_out, n, nvec, a));
+    DISPATCH2(eps_dtype, x_dtype, cfg_plms_kernel, grid_for(vec ? n / 8 : n), s, eps_u, eps_c, x, out, eps_out, n, nvec, a);
     COUNT_LAUNCH();
     B200SD_LAUNCH_CHECK();
     return B200SD_OK;
@@ -361,9 +375,9 @@ extern "C" int b200sd_add_noise(const void* x0, const void* noise, const int64_t
     if (gx > cap) gx = cap;
     dim3 grid(gx, batch);
     if (dtype == B200SD_F32)
-        add_noise_kernel<B200SD_F32><<<grid, kThreads, 0, s>>>(x0, noise, timesteps, sa_table, sb_table, out, per_sample, nvec, num_train_timesteps);
+        B200SD_CUDA(b200sd_launch(add_noise_kernel<B200SD_F32>, dim3(grid), dim3(kThreads), 0, s, x0, noise, timesteps, sa_table, sb_table, out, per_sample, nvec, num_train_timesteps));
     else
-        add_noise_kernel<B200SD_BF16><<<grid, kThreads, 0, s>>>(x0, noise, timesteps, sa_table, sb_table, out, per_sample, nvec, num_train_timesteps);
+        B200SD_CUDA(b200sd_launch(add_noise_kernel<B200SD_BF16>, dim3(grid), dim3(kThreads), 0, s, x0, noise, timesteps, sa_table, sb_table, out, per_sample, nvec, num_train_timesteps));
     COUNT_LAUNCH();
     B200SD_LAUNCH_CHECK();
     return B200SD_OK;
@@ -381,7 +395,7 @@ extern "C" int b200sd_mse_loss_fwd(const void* pred, const void* target, float* 
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     int grid = grid_for(vec ? n / 8 : n);
     if (grid > kMsePartials) grid = kMsePartials;
-    DISPATCH2(pred_dtype, target_dtype, mse_fwd_kernel, <<<grid, kThreads, 0, s>>>(pred, target, loss_out, workspace, n, nvec));
+    DISPATCH2(pred_dtype, target_dtype, mse_fwd_kernel, grid, s, pred, target, loss_out, workspace, n, nvec);
     COUNT_LAUNCH();
     B200SD_LAUNCH_CHECK();
     return B200SD_OK;
@@ -395,7 +409,7 @@ extern "C" int b200sd_mse_loss_bwd(const void* pred, const void* target, const f
     const bool vec = aligned16(pred) && aligned16(target) && aligned16(grad_pred);
     const int64_t nvec = vec ? n / 8 : 0;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    DISPATCH2(pred_dtype, target_dtype, mse_bwd_kernel, <<<grid_for(vec ? n / 8 : n), kThreads, 0, s>>>(pred, target, grad_loss, grad_pred, n, nvec));
+    DISPATCH2(pred_dtype, target_dtype, mse_bwd_kernel, grid_for(vec ? n / 8 : n), s, pred, target, grad_loss, grad_pred, n, nvec);
     COUNT_LAUNCH();
     B200SD_LAUNCH_CHECK();
     return B200SD_OK;

@@ -126,6 +126,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tcgen05_kernel(const __gr
     const int n0 = n_tile * p.block_n;
     const int m0 = m_tile * p.rows_valid;
 
+    ptx::pdl_trigger();
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tmap(&p.tmA0);
         ptx::prefetch_tmap(&p.tmB);
@@ -145,6 +146,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tcgen05_kernel(const __gr
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    ptx::pdl_wait();  // everything above overlapped the previous kernel's tail
 
     if (warp == 0) {
         // ================= TMA producer =================
@@ -460,14 +462,23 @@ extern "C" int b200sd_gemm(const b200sd_gemm_args* a, b200sd_stream_t stream) {
         p.ws_counters = reinterpret_cast<unsigned int*>(static_cast<uint8_t*>(a->workspace) + kSplitWsBytes);
     }
 
-    // ---- pipeline depth: keep <= ~110 KB so two CTAs fit per SM when the tile allows it ----
+    // ---- pipeline depth ----
+    // Grids that fit in one wave keep every k-block of a short K loop in flight (deep ring, 1 CTA/SM);
+    // larger grids stay <= ~110 KB so two CTAs share an SM and overlap epilogue with main loop.
     const int stage_bytes = kABytes + bn * BLOCK_K * 2;
-    int stages = (bn <= 160) ? (110 * 1024) / stage_bytes : (200 * 1024) / stage_bytes;
+    const long total_ctas = (long)m_tiles * n_tiles * split;
+    int stages;
+    if (total_ctas <= sms || bn > 160) stages = (200 * 1024) / stage_bytes;
+    else stages = (110 * 1024) / stage_bytes;
     if (stages > kMaxStages) stages = kMaxStages;
+    if (stages > p.kb_per_split && total_ctas <= sms) stages = p.kb_per_split;
+    const int min_stages = ceil_div(BLOCK_M * (bn + 4) * (int)sizeof(float), stage_bytes);  // epilogue staging tile
+    if (stages < min_stages) stages = min_stages;
     if (stages < 2) stages = 2;
     p.stages = stages;
     B200SD_REQUIRE((size_t)stages * stage_bytes >= (size_t)BLOCK_M * (bn + 4) * sizeof(float), "gemm: smem ring smaller than the epilogue staging tile");
     const size_t smem_bytes = (size_t)stages * stage_bytes + 1024 /*align slack*/ + 256 /*barriers*/;
+    B200SD_REQUIRE(smem_bytes <= 227 * 1024, "gemm: smem budget exceeded (%zu B)", smem_bytes);
 
     // ---- tensor maps ----
     if (!p.conv) {
@@ -509,7 +520,7 @@ extern "C" int b200sd_gemm(const b200sd_gemm_args* a, b200sd_stream_t stream) {
         configured_smem = 227 * 1024;
     }
     dim3 grid(m_tiles, n_tiles, split);
-    gemm_tcgen05_kernel<<<grid, kNumThreads, smem_bytes, static_cast<cudaStream_t>(stream)>>>(p);
+    B200SD_CUDA(b200sd_launch(gemm_tcgen05_kernel, dim3(grid), dim3(kNumThreads), smem_bytes, static_cast<cudaStream_t>(stream), p));
     g_b200sd_launches.fetch_add(1, std::memory_order_relaxed);
     B200SD_LAUNCH_CHECK();
     return B200SD_OK;

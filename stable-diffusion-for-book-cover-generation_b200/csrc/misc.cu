@@ -12,6 +12,8 @@ namespace {
 
 // ---- sinusoidal timestep embedding (fp32, accurate sin/cos: arguments reach ~1000 rad) -----------
 __global__ void temb_kernel(const float* __restrict__ t, float* __restrict__ out, int batch, int dim) {
+    ptx::pdl_trigger();
+    ptx::pdl_wait();
     const int half = dim / 2;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= batch * half) return;
@@ -28,6 +30,8 @@ __global__ void __launch_bounds__(256) small_linear_kernel(const float* __restri
                                                            const float* __restrict__ bias, float* __restrict__ out,
                                                            int batch, int N, int K, int silu_in, int silu_out) {
     extern __shared__ float s_in[];  // [kSlRows][K]
+    ptx::pdl_trigger();
+    ptx::pdl_wait();
     const int b0 = blockIdx.y * kSlRows;
     const int nb = min(kSlRows, batch - b0);
     for (int i = threadIdx.x; i < kSlRows * K; i += blockDim.x) {
@@ -101,6 +105,8 @@ __global__ void conv_in_kernel(const float* __restrict__ x, const float* __restr
                                bf16* __restrict__ out, int batch, int Cout, int H, int W) {
     constexpr int Cin = 4;
     __shared__ float patch[kCinPix][9 * Cin];
+    ptx::pdl_trigger();
+    ptx::pdl_wait();
     const int hw = H * W;
     const int pix0 = blockIdx.x * kCinPix;
     const int total = batch * hw;
@@ -147,8 +153,10 @@ __global__ void __launch_bounds__(256) conv_out_kernel(const bf16* __restrict__ 
                                                        const float* __restrict__ bias, float* __restrict__ out,
                                                        int batch, int Cin, int Cout, int H, int W, int pix_per_warp) {
     extern __shared__ float s_w[];  // packed [Cout][tap][Cin]
-    for (int i = threadIdx.x; i < Cout * 9 * Cin; i += blockDim.x) s_w[i] = __ldg(w + i);
+    ptx::pdl_trigger();
+    for (int i = threadIdx.x; i < Cout * 9 * Cin; i += blockDim.x) s_w[i] = __ldg(w + i);  // static weights: before the wait
     __syncthreads();
+    ptx::pdl_wait();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int hw = H * W, total = batch * hw;
     const int first = (blockIdx.x * 8 + warp) * pix_per_warp;
@@ -179,6 +187,8 @@ __global__ void __launch_bounds__(256) conv_out_kernel(const bf16* __restrict__ 
 
 // ---- nearest x2 upsample, NHWC, 16-byte vectors ----------------------------------------------------
 __global__ void upsample2x_kernel(const uint4* __restrict__ x, uint4* __restrict__ out, int batch, int H, int W, int C8) {
+    ptx::pdl_trigger();
+    ptx::pdl_wait();
     const int64_t total = (int64_t)batch * 4 * H * W * C8;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
@@ -194,6 +204,8 @@ __global__ void upsample2x_kernel(const uint4* __restrict__ x, uint4* __restrict
 
 // ---- im2col for the stride-2 pad-1 3x3 Downsample2D conv --------------------------------------------
 __global__ void im2col_s2_kernel(const uint4* __restrict__ x, uint4* __restrict__ out, int batch, int H, int W, int C8) {
+    ptx::pdl_trigger();
+    ptx::pdl_wait();
     const int OH = H / 2, OW = W / 2;
     const int64_t total = (int64_t)batch * OH * OW * 9 * C8;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -227,7 +239,7 @@ extern "C" int b200sd_timestep_embedding(const float* timesteps, float* out, int
     B200SD_REQUIRE(timesteps && out, "timestep_embedding: null pointer");
     B200SD_REQUIRE(batch > 0 && dim > 0 && dim % 2 == 0, "timestep_embedding: bad sizes");
     const int total = batch * dim / 2;
-    temb_kernel<<<ceil_div(total, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(timesteps, out, batch, dim);
+    B200SD_CUDA(b200sd_launch(temb_kernel, dim3(ceil_div(total, 128)), dim3(128), 0, static_cast<cudaStream_t>(stream), timesteps, out, batch, dim));
     COUNT_LAUNCH();
     B200SD_LAUNCH_CHECK();
     return B200SD_OK;
@@ -248,8 +260,8 @@ extern "C" int b200sd_small_linear(const float* in, const void* w_bf16, const fl
     const int cap = b200sd_num_sms() * 4;
     if (gx > cap) gx = cap;
     dim3 grid(gx, ceil_div(batch, kSlRows));
-    small_linear_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(in, static_cast<const bf16*>(w_bf16), bias,
-                                                                               out, batch, N, K, silu_in, silu_out);
+    B200SD_CUDA(b200sd_launch(small_linear_kernel, dim3(grid), dim3(256), smem, static_cast<cudaStream_t>(stream), in, static_cast<const bf16*>(w_bf16), bias,
+                                                                               out, batch, N, K, silu_in, silu_out));
     COUNT_LAUNCH();
     B200SD_LAUNCH_CHECK();
     return B200SD_OK;
@@ -264,8 +276,8 @@ extern "C" int b200sd_conv_in(const float* x_nchw, const float* w, const float* 
     int threads = Cout / 2;
     if (threads > 256) threads = 256;
     threads = ceil_div(threads, 32) * 32;
-    conv_in_kernel<<<ceil_div(total, kCinPix), threads, 0, static_cast<cudaStream_t>(stream)>>>(
-        x_nchw, w, bias, static_cast<bf16*>(out_nhwc), batch, Cout, H, W);
+    B200SD_CUDA(b200sd_launch(conv_in_kernel, dim3(ceil_div(total, kCinPix)), dim3(threads), 0, static_cast<cudaStream_t>(stream), 
+        x_nchw, w, bias, static_cast<bf16*>(out_nhwc), batch, Cout, H, W));
     COUNT_LAUNCH();
     B200SD_LAUNCH_CHECK();
     return B200SD_OK;
@@ -286,8 +298,8 @@ extern "C" int b200sd_conv_out(const void* x_nhwc, const float* w, const float* 
     int ppw = ceil_div(total, b200sd_num_sms() * 2 * 8);
     if (ppw < 4) ppw = 4;
     const int blocks = ceil_div(total, ppw * 8);
-    conv_out_kernel<<<blocks, 256, smem, static_cast<cudaStream_t>(stream)>>>(static_cast<const bf16*>(x_nhwc), w, bias,
-                                                                             out_nchw, batch, Cin, Cout, H, W, ppw);
+    B200SD_CUDA(b200sd_launch(conv_out_kernel, dim3(blocks), dim3(256), smem, static_cast<cudaStream_t>(stream), static_cast<const bf16*>(x_nhwc), w, bias,
+                                                                             out_nchw, batch, Cin, Cout, H, W, ppw));
     COUNT_LAUNCH();
     B200SD_LAUNCH_CHECK();
     return B200SD_OK;
@@ -297,8 +309,8 @@ extern "C" int b200sd_upsample2x(const void* x, void* out, int batch, int H, int
     B200SD_REQUIRE(x && out, "upsample2x: null pointer");
     B200SD_REQUIRE(C % 8 == 0 && batch > 0 && H > 0 && W > 0, "upsample2x: bad sizes");
     const int64_t total = (int64_t)batch * 4 * H * W * (C / 8);
-    upsample2x_kernel<<<ew_grid(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const uint4*>(x), static_cast<uint4*>(out), batch, H, W, C / 8);
+    B200SD_CUDA(b200sd_launch(upsample2x_kernel, dim3(ew_grid(total, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
+        static_cast<const uint4*>(x), static_cast<uint4*>(out), batch, H, W, C / 8));
     COUNT_LAUNCH();
     B200SD_LAUNCH_CHECK();
     return B200SD_OK;
@@ -308,8 +320,8 @@ extern "C" int b200sd_im2col_s2(const void* x, void* out, int batch, int H, int 
     B200SD_REQUIRE(x && out, "im2col_s2: null pointer");
     B200SD_REQUIRE(C % 8 == 0 && batch > 0 && H % 2 == 0 && W % 2 == 0, "im2col_s2: bad sizes");
     const int64_t total = (int64_t)batch * (H / 2) * (W / 2) * 9 * (C / 8);
-    im2col_s2_kernel<<<ew_grid(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const uint4*>(x), static_cast<uint4*>(out), batch, H, W, C / 8);
+    B200SD_CUDA(b200sd_launch(im2col_s2_kernel, dim3(ew_grid(total, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
+        static_cast<const uint4*>(x), static_cast<uint4*>(out), batch, H, W, C / 8));
     COUNT_LAUNCH();
     B200SD_LAUNCH_CHECK();
     return B200SD_OK;

@@ -31,8 +31,10 @@ __global__ void __launch_bounds__(1024) gn_stats_kernel(const bf16* __restrict__
     const int C8 = C / 8;
     const int cpg = C / groups;
     const int b = blockIdx.y, slab = blockIdx.x, slabs = gridDim.x;
+    ptx::pdl_trigger();
     if (threadIdx.x < kMaxGroups) { s_sum[threadIdx.x] = 0.f; s_sq[threadIdx.x] = 0.f; }
     __syncthreads();
+    ptx::pdl_wait();
     const int vec = threadIdx.x % C8;
     const int prow = threadIdx.x / C8;
     const int c = vec * 8;
@@ -123,6 +125,8 @@ __global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const bf16* __rest
                                                               const float* __restrict__ mean_rstd, int hw,
                                                               int groups, int silu, int pix_per_block) {
     extern __shared__ float2 s_ab[];  // per-channel (scale, shift)
+    ptx::pdl_trigger();
+    ptx::pdl_wait();
     const int C = C0 + C1;
     const int cpg = C / groups;
     const int b = blockIdx.y;
@@ -164,6 +168,8 @@ template <int PAIRS_PER_LANE>
 __global__ void __launch_bounds__(256) layernorm_kernel(const bf16* __restrict__ x, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, bf16* __restrict__ out,
                                                         int rows, int C, float eps) {
+    ptx::pdl_trigger();
+    ptx::pdl_wait();
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (warp >= rows) return;
@@ -221,8 +227,8 @@ extern "C" int b200sd_groupnorm_silu(const void* x0, const void* x1, int C0, int
     int pps = ceil_div(hw, slabs);
     pps = ceil_div(pps, rows_per_pass) * rows_per_pass;
     slabs = ceil_div(hw, pps);
-    gn_stats_kernel<<<dim3(slabs, batch), threads, 0, s>>>(static_cast<const bf16*>(x0), static_cast<const bf16*>(x1), C0, C1,
-                                                          partial, mean_rstd, counters, hw, groups, pps, rows_per_pass, eps);
+    B200SD_CUDA(b200sd_launch(gn_stats_kernel, dim3(dim3(slabs, batch)), dim3(threads), 0, s, static_cast<const bf16*>(x0), static_cast<const bf16*>(x1), C0, C1,
+                                                          partial, mean_rstd, counters, hw, groups, pps, rows_per_pass, eps));
     COUNT_LAUNCH();
     B200SD_LAUNCH_CHECK();
     int blocks = ceil_div(b200sd_num_sms() * 4, batch);
@@ -230,9 +236,9 @@ extern "C" int b200sd_groupnorm_silu(const void* x0, const void* x1, int C0, int
     const int min_ppb = ceil_div(kGnThreads * 4, C / 8);  // >= 4 vectors per thread
     if (ppb < min_ppb) ppb = min_ppb;
     blocks = ceil_div(hw, ppb);
-    gn_apply_kernel<<<dim3(blocks, batch), kGnThreads, C * sizeof(float2), s>>>(
+    B200SD_CUDA(b200sd_launch(gn_apply_kernel, dim3(dim3(blocks, batch)), dim3(kGnThreads), C * sizeof(float2), s, 
         static_cast<const bf16*>(x0), static_cast<const bf16*>(x1), C0, C1, gamma, beta, static_cast<bf16*>(out), mean_rstd,
-        hw, groups, silu, ppb);
+        hw, groups, silu, ppb));
     COUNT_LAUNCH();
     B200SD_LAUNCH_CHECK();
     return B200SD_OK;
@@ -254,7 +260,7 @@ extern "C" int b200sd_layernorm(const void* x, const float* gamma, const float* 
     bf16* xo = static_cast<bf16*>(out);
 #define LN_CASE(P)                                                                                     \
     case P:                                                                                            \
-        layernorm_kernel<P><<<blocks, 256, 0, s>>>(xi, gamma, beta, xo, rows, C, eps);                  \
+        B200SD_CUDA(b200sd_launch(layernorm_kernel<P>, dim3(blocks), dim3(256), 0, s, xi, gamma, beta, xo, rows, C, eps));                  \
         break;
     switch (C / 64) {
         LN_CASE(1) LN_CASE(2) LN_CASE(3) LN_CASE(4) LN_CASE(5) LN_CASE(6) LN_CASE(7) LN_CASE(8) LN_CASE(9) LN_CASE(10)
