@@ -108,9 +108,9 @@ int b200sd_small_linear(const float* in, const void* w_bf16, const float* bias, 
  *   B200SD_EPI_LINEAR : bias / rowbias / residual as above.
  *   B200SD_EPI_GEGLU  : W rows are tile-interleaved [value | gate] (see b200sd_geglu_tile());
  *                       out[M, N/2] = value * gelu_erf(gate), bias likewise interleaved.
- * split_k > 1 needs the workspace (b200sd_gemm_workspace_bytes; ZERO before first use, left zeroed):
- * every split adds its tile into an L2-resident fp32 accumulator with vector reds and the last CTA of
- * a tile runs the epilogue (fp32 summation order is not fixed: last-bit run-to-run differences).
+ * split_k > 1 needs the workspace (b200sd_gemm_workspace_bytes; ZERO before first use: arrival counters,
+ * left zeroed): every split publishes its fp32 partial tile there and the last CTA of a tile sums the
+ * splits in a fixed order (bit-deterministic) and runs the epilogue.
  */
 #define B200SD_EPI_LINEAR 0
 #define B200SD_EPI_GEGLU 1

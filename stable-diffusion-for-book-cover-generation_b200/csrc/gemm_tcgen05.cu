@@ -12,10 +12,12 @@
 // activation source (a1) extends the channel axis, which fuses the up-block torch.cat.
 // With <= 113 KB of smem and <= 256 TMEM columns per CTA two CTAs share an SM, so one CTA's
 // epilogue overlaps the other's main loop.  Small-M / deep-K layers are split along K with a
-// vector-red accumulation into an L2-resident fp32 workspace; the last CTA of a tile runs the epilogue.
+// fp32 partial tiles in an L2-resident workspace; the last CTA of a tile sums them in a fixed order
+// (deterministic) and runs the epilogue.
 #include <atomic>
 #include <cstring>
 #include <cstdio>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -30,7 +32,7 @@ constexpr int kNumThreads = 192;
 constexpr int kMaxStages = 8;
 constexpr int kABytes = BLOCK_M * BLOCK_K * 2;  // 16 KB (always reserved in full)
 
-constexpr size_t kSplitWsBytes = 64ull << 20;  // fp32 accumulator tiles (always left zeroed)
+constexpr size_t kSplitWsBytes = 64ull << 20;  // fp32 partial tiles [tile][split][128][block_n]
 constexpr int kMaxSplitTiles = 4096;           // per-tile arrival counters live after the partials
 
 struct KParams {
@@ -60,11 +62,6 @@ struct KParams {
     int out_f32;
     uint32_t tmem_cols;
 };
-
-__device__ __forceinline__ void red_add_v4(float* addr, float4 v) {
-    asm volatile("red.global.v4.f32.add [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
-                 : "memory");
-}
 
 // Final epilogue for 8 consecutive output columns of one row: v = accumulators (fp32).
 __device__ __forceinline__ void epilogue_store8(const KParams& p, int row, int col, float (&v)[8]) {
@@ -246,16 +243,16 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tcgen05_kernel(const __gr
         int src_pitch = pitch_f;
 
         if (p.split_k > 1) {
-            // every split adds its partial tile into the L2-resident fp32 accumulator (vector reds);
-            // the last-arriving CTA of the tile then runs the real epilogue from it and re-zeroes it.
-            float* acc = p.ws_partials + ((size_t)tile_id * BLOCK_M + q * 32) * p.block_n;
+            // every split publishes its fp32 partial tile (coalesced, L2-resident); the last-arriving CTA
+            // of the tile sums the splits in a FIXED order (deterministic) and runs the epilogue.
+            float* mine = p.ws_partials + (((size_t)tile_id * p.split_k + split) * BLOCK_M + q * 32) * p.block_n;
             const int groups4 = p.block_n / 4;
             const int items = rows_here * groups4;
 #pragma unroll 4
             for (int idx = lane; idx < items; idx += 32) {
                 const int rl = idx / groups4, c4 = idx - rl * groups4;
                 const float4 v = *reinterpret_cast<const float4*>(wstage + (size_t)rl * pitch_f + c4 * 4);
-                red_add_v4(acc + (size_t)rl * p.block_n + c4 * 4, v);
+                __stcg(reinterpret_cast<float4*>(mine + (size_t)rl * p.block_n + c4 * 4), v);
             }
             __threadfence();
             ptx::named_bar_sync(1, 128);
@@ -268,7 +265,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tcgen05_kernel(const __gr
             }
             ptx::named_bar_sync(1, 128);
             do_final = (*last_flag != 0);
-            src = acc;
+            src = p.ws_partials + ((size_t)tile_id * p.split_k * BLOCK_M + q * 32) * p.block_n;
             src_pitch = p.block_n;
         }
 
@@ -303,11 +300,17 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tcgen05_kernel(const __gr
                     const int rl = idx / groups, c8 = idx - rl * groups;
                     float v[8];
                     if (from_ws) {
-                        float4* ap = reinterpret_cast<float4*>(const_cast<float*>(src) + (size_t)rl * src_pitch + c8 * 8);
-                        const float4 a0 = __ldcg(ap), a1 = __ldcg(ap + 1);
-                        __stcg(ap, make_float4(0.f, 0.f, 0.f, 0.f));   // leave the accumulator clean for the next launch
-                        __stcg(ap + 1, make_float4(0.f, 0.f, 0.f, 0.f));
-                        v[0] = a0.x; v[1] = a0.y; v[2] = a0.z; v[3] = a0.w; v[4] = a1.x; v[5] = a1.y; v[6] = a1.z; v[7] = a1.w;
+                        const size_t split_stride = (size_t)BLOCK_M * p.block_n;
+                        const float* ap = src + (size_t)rl * src_pitch + c8 * 8;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) v[i] = 0.f;
+#pragma unroll 4
+                        for (int sp_i = 0; sp_i < p.split_k; ++sp_i) {
+                            const float4 a0 = __ldcg(reinterpret_cast<const float4*>(ap + sp_i * split_stride));
+                            const float4 a1 = __ldcg(reinterpret_cast<const float4*>(ap + sp_i * split_stride) + 1);
+                            v[0] += a0.x; v[1] += a0.y; v[2] += a0.z; v[3] += a0.w;
+                            v[4] += a1.x; v[5] += a1.y; v[6] += a1.z; v[7] += a1.w;
+                        }
                     } else {
                         const float* sp = src + (size_t)rl * src_pitch + c8 * 8;
                         const float4 a0 = *reinterpret_cast<const float4*>(sp), a1 = *reinterpret_cast<const float4*>(sp + 4);
@@ -334,19 +337,22 @@ uint32_t pow2_cols(int n) {
 }
 
 int pick_block_n(int N, int m_tiles, int epilogue) {
-    // Largest legal tile width (multiple of 16, <= 256, divides N; multiple of 32 for GEGLU).
+    // Legal tile widths: multiple of 16 (32 for GEGLU), <= 256, dividing N.  Prefer 160 (two CTAs per SM,
+    // 90 % of the smem read bandwidth the MMA needs); when that leaves the machine more than half empty
+    // (small-M layers) fall to a narrower tile so more CTAs stream operands concurrently.
     const int step = (epilogue == B200SD_EPI_GEGLU) ? 32 : 16;
+    const int sms = b200sd_num_sms();
     int best = 0;
-    for (int bn = 256; bn >= step; bn -= step)
+    for (int bn = 160; bn >= 64; bn -= step)
         if (N % bn == 0) { best = bn; break; }
-    if (best == 0) return 0;
-    // prefer <= 160 columns when it lets two CTAs share an SM and still fills the machine
-    if (best > 160) {
-        for (int bn = 160; bn >= 64; bn -= step)
-            if (N % bn == 0) {
-                (void)m_tiles;
-                return bn;
-            }
+    if (best == 0) {
+        for (int bn = 256; bn >= step; bn -= step)
+            if (N % bn == 0) { best = bn; break; }
+        return best;
+    }
+    if (epilogue == B200SD_EPI_LINEAR && (long)m_tiles * (N / best) * 2 <= sms) {
+        for (int bn = 80; bn < best; bn += step)  // narrowest tile (>= 80) that still fits one wave
+            if (N % bn == 0 && (long)m_tiles * (N / bn) <= sms) { best = bn; break; }
     }
     return best;
 }
@@ -439,14 +445,15 @@ extern "C" int b200sd_gemm(const b200sd_gemm_args* a, b200sd_stream_t stream) {
     // ---- split-K ----
     const int sms = b200sd_num_sms();
     int split = a->split_k;
+    static const bool no_split = getenv("B200SD_SPLITK") && getenv("B200SD_SPLITK")[0] == '0';
     if (split <= 0) {
         split = 1;
         const int tiles = m_tiles * n_tiles;
-        if (a->epilogue == B200SD_EPI_LINEAR && tiles < sms && p.num_k_blocks >= 16) {
+        if (!no_split && a->epilogue == B200SD_EPI_LINEAR && tiles * 2 <= sms && p.num_k_blocks >= 32) {
             split = sms / tiles;
-            const int max_by_k = p.num_k_blocks / 8;  // keep >= 8 k-blocks per split
+            const int max_by_k = p.num_k_blocks / 16;  // keep >= 16 k-blocks per split
             if (split > max_by_k) split = max_by_k;
-            if (split > 16) split = 16;
+            if (split > 8) split = 8;
             if (split < 1) split = 1;
         }
     }
@@ -455,7 +462,7 @@ extern "C" int b200sd_gemm(const b200sd_gemm_args* a, b200sd_stream_t stream) {
     split = ceil_div(p.num_k_blocks, p.kb_per_split);  // no empty splits
     p.split_k = split;
     if (split > 1) {
-        const size_t need = (size_t)m_tiles * n_tiles * BLOCK_M * bn * sizeof(float);
+        const size_t need = (size_t)m_tiles * n_tiles * split * BLOCK_M * bn * sizeof(float);
         B200SD_REQUIRE(a->workspace != nullptr && a->workspace_bytes >= b200sd_gemm_workspace_bytes(), "gemm: split-K needs the workspace");
         B200SD_REQUIRE(need <= kSplitWsBytes && m_tiles * n_tiles <= kMaxSplitTiles, "gemm: split-K workspace too small (%zu B)", need);
         p.ws_partials = static_cast<float*>(a->workspace);

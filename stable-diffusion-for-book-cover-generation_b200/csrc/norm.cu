@@ -27,13 +27,12 @@ __global__ void __launch_bounds__(1024) gn_stats_kernel(const bf16* __restrict__
                                                         float eps) {
     __shared__ float s_sum[kMaxGroups], s_sq[kMaxGroups];
     __shared__ bool s_last;
+    extern __shared__ float s_part[];  // [2][rows_per_pass][C] per-thread channel sums (deterministic fold)
     const int C = C0 + C1;
     const int C8 = C / 8;
     const int cpg = C / groups;
     const int b = blockIdx.y, slab = blockIdx.x, slabs = gridDim.x;
     ptx::pdl_trigger();
-    if (threadIdx.x < kMaxGroups) { s_sum[threadIdx.x] = 0.f; s_sq[threadIdx.x] = 0.f; }
-    __syncthreads();
     ptx::pdl_wait();
     const int vec = threadIdx.x % C8;
     const int prow = threadIdx.x / C8;
@@ -59,22 +58,22 @@ __global__ void __launch_bounds__(1024) gn_stats_kernel(const bf16* __restrict__
                 s[2 * j + 1] += f.y; ss[2 * j + 1] += f.y * f.y;
             }
         }
-        // fold the 8 channels into their groups (runs of equal group id), one shared atomic per run
-        int g = c / cpg;
-        float a = 0.f, q = 0.f;
+        float* ps = s_part + (size_t)prow * C + c;
+        float* pq = s_part + (size_t)(rows_per_pass + prow) * C + c;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int gj = (c + j) / cpg;
-            if (gj != g) {
-                atomicAdd(&s_sum[g], a);
-                atomicAdd(&s_sq[g], q);
-                a = 0.f; q = 0.f; g = gj;
-            }
-            a += s[j];
-            q += ss[j];
+        for (int j = 0; j < 8; ++j) { ps[j] = s[j]; pq[j] = ss[j]; }
+    }
+    __syncthreads();
+    if (threadIdx.x < groups) {
+        // fixed-order fold of the group's channels over the pixel rows of this block
+        float a = 0.f, q = 0.f;
+        for (int r = 0; r < rows_per_pass; ++r) {
+            const float* ps = s_part + (size_t)r * C + threadIdx.x * cpg;
+            const float* pq = s_part + (size_t)(rows_per_pass + r) * C + threadIdx.x * cpg;
+            for (int j = 0; j < cpg; ++j) { a += ps[j]; q += pq[j]; }
         }
-        atomicAdd(&s_sum[g], a);
-        atomicAdd(&s_sq[g], q);
+        s_sum[threadIdx.x] = a;
+        s_sq[threadIdx.x] = q;
     }
     __syncthreads();
     if (threadIdx.x < groups) {
@@ -227,7 +226,7 @@ extern "C" int b200sd_groupnorm_silu(const void* x0, const void* x1, int C0, int
     int pps = ceil_div(hw, slabs);
     pps = ceil_div(pps, rows_per_pass) * rows_per_pass;
     slabs = ceil_div(hw, pps);
-    B200SD_CUDA(b200sd_launch(gn_stats_kernel, dim3(dim3(slabs, batch)), dim3(threads), 0, s, static_cast<const bf16*>(x0), static_cast<const bf16*>(x1), C0, C1,
+    B200SD_CUDA(b200sd_launch(gn_stats_kernel, dim3(dim3(slabs, batch)), dim3(threads), (size_t)2 * rows_per_pass * C * sizeof(float), s, static_cast<const bf16*>(x0), static_cast<const bf16*>(x1), C0, C1,
                                                           partial, mean_rstd, counters, hw, groups, pps, rows_per_pass, eps));
     COUNT_LAUNCH();
     B200SD_LAUNCH_CHECK();

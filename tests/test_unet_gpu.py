@@ -62,9 +62,8 @@ def test_batch2_per_sample_timesteps_and_graph_equivalence(models):
         oracle.to("cpu")
         ours.use_cuda_graph = True
     assert _rel(eager, want) <= 1e-2
-    # split-K GEMMs accumulate with fp32 reds (order not fixed): replay == eager up to last-bit effects
-    scale = float(eager.abs().max())
-    assert float((eager - g1).abs().max()) <= 2e-3 * scale and float((g1 - g2).abs().max()) <= 2e-3 * scale
+    # every kernel (incl. split-K and GroupNorm reductions) sums in a fixed order: bit-reproducible
+    assert torch.equal(eager, g1) and torch.equal(g1, g2), "graph replay must be bit-identical to eager launches"
 
 
 def test_portrait_latent_96x64(models):
