@@ -121,7 +121,7 @@ typedef struct b200sd_gemm_args {
     const void* w;         /* bf16 [N, K] */
     const float* bias;     /* [N] or NULL */
     const float* rowbias;  /* [batch, N] or NULL (time-embedding add) */
-    const void* residual;  /* bf16 [M, ldr] or NULL */
+    const void* residual;  /* [M, ldr] (residual_dtype) or NULL */
     void* out;             /* [M, ldc] */
     int M, N, K;
     int C0, C1;            /* channels of a0 / a1 */
@@ -133,6 +133,7 @@ typedef struct b200sd_gemm_args {
     int rows_per_image;    /* for rowbias: image index = row / rows_per_image */
     int epilogue;          /* B200SD_EPI_* */
     int out_dtype;         /* B200SD_BF16 or B200SD_F32 */
+    int residual_dtype;    /* B200SD_BF16 or B200SD_F32 */
     int block_n;           /* 0 = auto */
     int split_k;           /* 0 = auto */
     void* workspace;       /* split-K scratch (may be NULL when split_k == 1) */
@@ -147,22 +148,24 @@ int b200sd_gemm(const b200sd_gemm_args* args, b200sd_stream_t stream);
  * conv_in : NCHW fp32 (batch, Cin=4, H, W) -> NHWC bf16 (batch*H*W, Cout); w fp32 packed [Cout][ky][kx][Cin].
  * conv_out: NHWC bf16 (batch*H*W, Cin) -> NCHW fp32 (batch, Cout<=4, H, W); w fp32 packed [Cout][ky][kx][Cin]. */
 int b200sd_conv_in(const float* x_nchw, const float* w, const float* bias, void* out_nhwc, int batch, int Cin,
-                   int Cout, int H, int W, b200sd_stream_t stream);
+                   int Cout, int H, int W, int out_dtype, b200sd_stream_t stream);
 int b200sd_conv_out(const void* x_nhwc, const float* w, const float* bias, float* out_nchw, int batch, int Cin,
                     int Cout, int H, int W, b200sd_stream_t stream);
 
 /* GroupNorm over NHWC input, optionally over the channel concat [x0 | x1] (torch.cat fused),
  * optional SiLU, bf16 output [rows, C0+C1].  stats_ws: float[b200sd_groupnorm_workspace_floats(batch)]
  * scratch that must be ZERO before its first use (arrival counters; the kernels leave them zeroed).
+ * x0 / x1 have in_dtype (fp32 residual stream or bf16); raw_out (optional, bf16 [rows, C0+C1]) receives the
+ * un-normalised concat, the operand of the 1x1 shortcut conv.
  * Replaces nn.GroupNorm + SiLU (+ torch.cat) in ResnetBlock2D / Transformer2DModel. */
 int b200sd_groupnorm_silu(const void* x0, const void* x1, int C0, int C1, const float* gamma, const float* beta,
-                          void* out, float* stats_ws, int batch, int hw, int groups, float eps, int silu,
-                          b200sd_stream_t stream);
+                          void* out, void* raw_out, float* stats_ws, int batch, int hw, int groups, float eps,
+                          int silu, int in_dtype, b200sd_stream_t stream);
 
-/* LayerNorm over the last dim of [rows, C] bf16 -> bf16 (eps 1e-5, affine). */
+/* LayerNorm over the last dim of [rows, C] (in_dtype: fp32 or bf16) -> bf16 (affine). */
 int b200sd_groupnorm_workspace_floats(int batch);
 int b200sd_layernorm(const void* x, const float* gamma, const float* beta, void* out, int rows, int C, float eps,
-                     b200sd_stream_t stream);
+                     int in_dtype, b200sd_stream_t stream);
 
 /* Fused (flash-style) attention: out = softmax(scale * Q K^T) V per (batch, head).
  * q: [batch*Sq, ldq] with head h at columns [h*d, (h+1)*d); k, v likewise with ldk / ldv;
@@ -172,9 +175,9 @@ int b200sd_attention(const void* q, const void* k, const void* v, void* out, int
                      int d, int ldq, int ldk, int ldv, int ldo, float scale, b200sd_stream_t stream);
 
 /* nearest x2 upsample NHWC bf16: (batch,H,W,C) -> (batch,2H,2W,C)  (Upsample2D's F.interpolate) */
-int b200sd_upsample2x(const void* x, void* out, int batch, int H, int W, int C, b200sd_stream_t stream);
+int b200sd_upsample2x(const void* x, void* out, int batch, int H, int W, int C, int in_dtype, b200sd_stream_t stream);
 /* im2col for the three stride-2 Downsample2D convs: NHWC (batch,H,W,C) -> [batch*(H/2)*(W/2)][9*C] */
-int b200sd_im2col_s2(const void* x, void* out, int batch, int H, int W, int C, b200sd_stream_t stream);
+int b200sd_im2col_s2(const void* x, void* out, int batch, int H, int W, int C, int in_dtype, b200sd_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -22,7 +22,7 @@ class GemmArgs(C.Structure):
         ("M", C.c_int), ("N", C.c_int), ("K", C.c_int), ("C0", C.c_int), ("C1", C.c_int),
         ("lda0", C.c_int), ("lda1", C.c_int), ("ldc", C.c_int), ("ldr", C.c_int), ("ldrb", C.c_int), ("conv_taps", C.c_int),
         ("batch", C.c_int), ("H", C.c_int), ("W", C.c_int), ("rows_per_image", C.c_int), ("epilogue", C.c_int),
-        ("out_dtype", C.c_int), ("block_n", C.c_int), ("split_k", C.c_int),
+        ("out_dtype", C.c_int), ("residual_dtype", C.c_int), ("block_n", C.c_int), ("split_k", C.c_int),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
     ]
 
@@ -46,14 +46,14 @@ SIGNATURES = {
     "b200sd_gemm_workspace_bytes": (_sz, []),
     "b200sd_geglu_tile": (_i, [_i]),
     "b200sd_gemm": (_i, [C.POINTER(GemmArgs), _vp]),
-    "b200sd_conv_in": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "b200sd_conv_in": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "b200sd_conv_out": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
-    "b200sd_groupnorm_silu": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _i, _vp]),
+    "b200sd_groupnorm_silu": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _i, _i, _vp]),
     "b200sd_groupnorm_workspace_floats": (_i, [_i]),
-    "b200sd_layernorm": (_i, [_vp, _vp, _vp, _vp, _i, _i, _f, _vp]),
+    "b200sd_layernorm": (_i, [_vp, _vp, _vp, _vp, _i, _i, _f, _i, _vp]),
     "b200sd_attention": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _vp]),
-    "b200sd_upsample2x": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
-    "b200sd_im2col_s2": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "b200sd_upsample2x": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "b200sd_im2col_s2": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
 }
 
 

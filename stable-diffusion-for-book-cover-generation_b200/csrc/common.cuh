@@ -249,6 +249,38 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
     __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
     return __bfloat1622float2(v);
 }
+// 8 consecutive elements <-> float[8]; DT = B200SD_F32 (2 x 16 B) or B200SD_BF16 (16 B)
+template <int DT>
+__device__ __forceinline__ void ld8(const void* p, size_t i, float (&v)[8]) {
+    if constexpr (DT == B200SD_F32) {
+        const float4* q = reinterpret_cast<const float4*>(static_cast<const float*>(p) + i);
+        const float4 a = __ldg(q), b = __ldg(q + 1);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+        v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(static_cast<const bf16*>(p) + i));
+        float2 f;
+        f = unpack_bf16x2(u.x); v[0] = f.x; v[1] = f.y;
+        f = unpack_bf16x2(u.y); v[2] = f.x; v[3] = f.y;
+        f = unpack_bf16x2(u.z); v[4] = f.x; v[5] = f.y;
+        f = unpack_bf16x2(u.w); v[6] = f.x; v[7] = f.y;
+    }
+}
+template <int DT>
+__device__ __forceinline__ void st8(void* p, size_t i, const float (&v)[8]) {
+    if constexpr (DT == B200SD_F32) {
+        float4* q = reinterpret_cast<float4*>(static_cast<float*>(p) + i);
+        q[0] = make_float4(v[0], v[1], v[2], v[3]);
+        q[1] = make_float4(v[4], v[5], v[6], v[7]);
+    } else {
+        uint4 u;
+        u.x = pack_bf16x2(v[0], v[1]);
+        u.y = pack_bf16x2(v[2], v[3]);
+        u.z = pack_bf16x2(v[4], v[5]);
+        u.w = pack_bf16x2(v[6], v[7]);
+        *reinterpret_cast<uint4*>(static_cast<bf16*>(p) + i) = u;
+    }
+}
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
 __device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 

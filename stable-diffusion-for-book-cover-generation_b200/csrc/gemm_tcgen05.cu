@@ -39,7 +39,7 @@ struct KParams {
     CUtensorMap tmA0, tmA1, tmB;
     const float* bias;
     const float* rowbias;
-    const bf16* residual;
+    const void* residual;
     void* out;
     float* ws_partials;
     unsigned int* ws_counters;
@@ -60,6 +60,7 @@ struct KParams {
     int rows_per_image;
     int epilogue;
     int out_f32;
+    int res_f32;
     uint32_t tmem_cols;
 };
 
@@ -78,12 +79,11 @@ __device__ __forceinline__ void epilogue_store8(const KParams& p, int row, int c
         v[4] += t1.x; v[5] += t1.y; v[6] += t1.z; v[7] += t1.w;
     }
     if (p.residual) {
-        const uint4 u = __ldg(reinterpret_cast<const uint4*>(p.residual + (size_t)row * p.ldr + col));
-        float2 f;
-        f = unpack_bf16x2(u.x); v[0] += f.x; v[1] += f.y;
-        f = unpack_bf16x2(u.y); v[2] += f.x; v[3] += f.y;
-        f = unpack_bf16x2(u.z); v[4] += f.x; v[5] += f.y;
-        f = unpack_bf16x2(u.w); v[6] += f.x; v[7] += f.y;
+        float r[8];
+        if (p.res_f32) ld8<B200SD_F32>(p.residual, (size_t)row * p.ldr + col, r);
+        else ld8<B200SD_BF16>(p.residual, (size_t)row * p.ldr + col, r);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] += r[i];
     }
     if (p.out_f32) {
         float4* o = reinterpret_cast<float4*>(static_cast<float*>(p.out) + (size_t)row * p.ldc + col);
@@ -376,6 +376,7 @@ extern "C" int b200sd_gemm(const b200sd_gemm_args* a, b200sd_stream_t stream) {
     B200SD_REQUIRE(a->epilogue != B200SD_EPI_GEGLU || (a->bias && !a->residual && !a->rowbias && a->out_dtype == B200SD_BF16),
                    "gemm: GEGLU epilogue needs bias, bf16 out and no residual/rowbias");
     B200SD_REQUIRE(a->out_dtype == B200SD_BF16 || a->out_dtype == B200SD_F32, "gemm: bad out dtype");
+    B200SD_REQUIRE(a->residual_dtype == B200SD_BF16 || a->residual_dtype == B200SD_F32, "gemm: bad residual dtype");
     B200SD_REQUIRE(a->ldc % 8 == 0 && (!a->residual || a->ldr % 8 == 0), "gemm: ldc/ldr must be multiples of 8");
     B200SD_REQUIRE((reinterpret_cast<uintptr_t>(a->out) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->a0) & 15) == 0 &&
                        (reinterpret_cast<uintptr_t>(a->w) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->a1) & 15) == 0 &&
@@ -394,7 +395,8 @@ extern "C" int b200sd_gemm(const b200sd_gemm_args* a, b200sd_stream_t stream) {
     p.cblocks = C / BLOCK_K;
     p.bias = a->bias;
     p.rowbias = a->rowbias;
-    p.residual = static_cast<const bf16*>(a->residual);
+    p.residual = a->residual;
+    p.res_f32 = a->residual_dtype == B200SD_F32;
     p.out = a->out;
     p.ldc = a->ldc;
     p.ldr = a->ldr;

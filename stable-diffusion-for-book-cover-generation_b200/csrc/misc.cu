@@ -101,8 +101,9 @@ __global__ void __launch_bounds__(256) small_linear_kernel(const float* __restri
 
 // ---- conv_in: NCHW fp32 (Cin = 4) -> NHWC bf16; thread = output-channel pair, block = 32 pixels ---
 constexpr int kCinPix = 32;
+template <int ODT>
 __global__ void conv_in_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
-                               bf16* __restrict__ out, int batch, int Cout, int H, int W) {
+                               void* __restrict__ out, int batch, int Cout, int H, int W) {
     constexpr int Cin = 4;
     __shared__ float patch[kCinPix][9 * Cin];
     ptx::pdl_trigger();
@@ -142,7 +143,10 @@ __global__ void conv_in_kernel(const float* __restrict__ x, const float* __restr
                 a0 += w0[r] * v;
                 a1 += w1[r] * v;
             }
-            *reinterpret_cast<uint32_t*>(out + (size_t)pix * Cout + co) = pack_bf16x2(a0, a1);
+            if constexpr (ODT == B200SD_F32)
+                *reinterpret_cast<float2*>(static_cast<float*>(out) + (size_t)pix * Cout + co) = make_float2(a0, a1);
+            else
+                *reinterpret_cast<uint32_t*>(static_cast<bf16*>(out) + (size_t)pix * Cout + co) = pack_bf16x2(a0, a1);
         }
     }
 }
@@ -185,8 +189,9 @@ __global__ void __launch_bounds__(256) conv_out_kernel(const bf16* __restrict__ 
     }
 }
 
-// ---- nearest x2 upsample, NHWC, 16-byte vectors ----------------------------------------------------
-__global__ void upsample2x_kernel(const uint4* __restrict__ x, uint4* __restrict__ out, int batch, int H, int W, int C8) {
+// ---- nearest x2 upsample, NHWC, 8-channel vectors (fp32 or bf16 in, bf16 out) -----------------------
+template <int DT>
+__global__ void upsample2x_kernel(const void* __restrict__ x, bf16* __restrict__ out, int batch, int H, int W, int C8) {
     ptx::pdl_trigger();
     ptx::pdl_wait();
     const int64_t total = (int64_t)batch * 4 * H * W * C8;
@@ -198,12 +203,15 @@ __global__ void upsample2x_kernel(const uint4* __restrict__ x, uint4* __restrict
         p /= (2 * W);
         const int oy = (int)(p % (2 * H));
         const int b = (int)(p / (2 * H));
-        out[i] = __ldg(x + ((int64_t)(b * H + (oy >> 1)) * W + (ox >> 1)) * C8 + c);
+        float v[8];
+        ld8<DT>(x, (size_t)(((int64_t)(b * H + (oy >> 1)) * W + (ox >> 1)) * C8 + c) * 8, v);
+        st8<B200SD_BF16>(out, (size_t)i * 8, v);
     }
 }
 
 // ---- im2col for the stride-2 pad-1 3x3 Downsample2D conv --------------------------------------------
-__global__ void im2col_s2_kernel(const uint4* __restrict__ x, uint4* __restrict__ out, int batch, int H, int W, int C8) {
+template <int DT>
+__global__ void im2col_s2_kernel(const void* __restrict__ x, bf16* __restrict__ out, int batch, int H, int W, int C8) {
     ptx::pdl_trigger();
     ptx::pdl_wait();
     const int OH = H / 2, OW = W / 2;
@@ -219,9 +227,9 @@ __global__ void im2col_s2_kernel(const uint4* __restrict__ x, uint4* __restrict_
         const int oy = (int)(p % OH);
         const int b = (int)(p / OH);
         const int y = 2 * oy + tap / 3 - 1, xx = 2 * ox + tap % 3 - 1;
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (y >= 0 && y < H && xx >= 0 && xx < W) v = __ldg(x + ((int64_t)(b * H + y) * W + xx) * C8 + c);
-        out[i] = v;
+        float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (y >= 0 && y < H && xx >= 0 && xx < W) ld8<DT>(x, (size_t)(((int64_t)(b * H + y) * W + xx) * C8 + c) * 8, v);
+        st8<B200SD_BF16>(out, (size_t)i * 8, v);
     }
 }
 
@@ -268,7 +276,7 @@ extern "C" int b200sd_small_linear(const float* in, const void* w_bf16, const fl
 }
 
 extern "C" int b200sd_conv_in(const float* x_nchw, const float* w, const float* bias, void* out_nhwc, int batch, int Cin,
-                              int Cout, int H, int W, b200sd_stream_t stream) {
+                              int Cout, int H, int W, int out_dtype, b200sd_stream_t stream) {
     B200SD_REQUIRE(x_nchw && w && bias && out_nhwc, "conv_in: null pointer");
     B200SD_REQUIRE(Cin == 4, "conv_in: only Cin == 4 (SD latent) is supported, got %d", Cin);
     B200SD_REQUIRE(Cout % 2 == 0 && batch > 0 && H > 0 && W > 0, "conv_in: bad sizes");
@@ -276,8 +284,12 @@ extern "C" int b200sd_conv_in(const float* x_nchw, const float* w, const float* 
     int threads = Cout / 2;
     if (threads > 256) threads = 256;
     threads = ceil_div(threads, 32) * 32;
-    B200SD_CUDA(b200sd_launch(conv_in_kernel, dim3(ceil_div(total, kCinPix)), dim3(threads), 0, static_cast<cudaStream_t>(stream), 
-        x_nchw, w, bias, static_cast<bf16*>(out_nhwc), batch, Cout, H, W));
+    if (out_dtype == B200SD_F32)
+        B200SD_CUDA(b200sd_launch(conv_in_kernel<B200SD_F32>, dim3(ceil_div(total, kCinPix)), dim3(threads), 0,
+                                  static_cast<cudaStream_t>(stream), x_nchw, w, bias, out_nhwc, batch, Cout, H, W));
+    else
+        B200SD_CUDA(b200sd_launch(conv_in_kernel<B200SD_BF16>, dim3(ceil_div(total, kCinPix)), dim3(threads), 0,
+                                  static_cast<cudaStream_t>(stream), x_nchw, w, bias, out_nhwc, batch, Cout, H, W));
     COUNT_LAUNCH();
     B200SD_LAUNCH_CHECK();
     return B200SD_OK;
@@ -305,23 +317,33 @@ extern "C" int b200sd_conv_out(const void* x_nhwc, const float* w, const float* 
     return B200SD_OK;
 }
 
-extern "C" int b200sd_upsample2x(const void* x, void* out, int batch, int H, int W, int C, b200sd_stream_t stream) {
+extern "C" int b200sd_upsample2x(const void* x, void* out, int batch, int H, int W, int C, int in_dtype,
+                                 b200sd_stream_t stream) {
     B200SD_REQUIRE(x && out, "upsample2x: null pointer");
     B200SD_REQUIRE(C % 8 == 0 && batch > 0 && H > 0 && W > 0, "upsample2x: bad sizes");
     const int64_t total = (int64_t)batch * 4 * H * W * (C / 8);
-    B200SD_CUDA(b200sd_launch(upsample2x_kernel, dim3(ew_grid(total, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
-        static_cast<const uint4*>(x), static_cast<uint4*>(out), batch, H, W, C / 8));
+    if (in_dtype == B200SD_F32)
+        B200SD_CUDA(b200sd_launch(upsample2x_kernel<B200SD_F32>, dim3(ew_grid(total, 256)), dim3(256), 0,
+                                  static_cast<cudaStream_t>(stream), x, static_cast<bf16*>(out), batch, H, W, C / 8));
+    else
+        B200SD_CUDA(b200sd_launch(upsample2x_kernel<B200SD_BF16>, dim3(ew_grid(total, 256)), dim3(256), 0,
+                                  static_cast<cudaStream_t>(stream), x, static_cast<bf16*>(out), batch, H, W, C / 8));
     COUNT_LAUNCH();
     B200SD_LAUNCH_CHECK();
     return B200SD_OK;
 }
 
-extern "C" int b200sd_im2col_s2(const void* x, void* out, int batch, int H, int W, int C, b200sd_stream_t stream) {
+extern "C" int b200sd_im2col_s2(const void* x, void* out, int batch, int H, int W, int C, int in_dtype,
+                                b200sd_stream_t stream) {
     B200SD_REQUIRE(x && out, "im2col_s2: null pointer");
     B200SD_REQUIRE(C % 8 == 0 && batch > 0 && H % 2 == 0 && W % 2 == 0, "im2col_s2: bad sizes");
     const int64_t total = (int64_t)batch * (H / 2) * (W / 2) * 9 * (C / 8);
-    B200SD_CUDA(b200sd_launch(im2col_s2_kernel, dim3(ew_grid(total, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
-        static_cast<const uint4*>(x), static_cast<uint4*>(out), batch, H, W, C / 8));
+    if (in_dtype == B200SD_F32)
+        B200SD_CUDA(b200sd_launch(im2col_s2_kernel<B200SD_F32>, dim3(ew_grid(total, 256)), dim3(256), 0,
+                                  static_cast<cudaStream_t>(stream), x, static_cast<bf16*>(out), batch, H, W, C / 8));
+    else
+        B200SD_CUDA(b200sd_launch(im2col_s2_kernel<B200SD_BF16>, dim3(ew_grid(total, 256)), dim3(256), 0,
+                                  static_cast<cudaStream_t>(stream), x, static_cast<bf16*>(out), batch, H, W, C / 8));
     COUNT_LAUNCH();
     B200SD_LAUNCH_CHECK();
     return B200SD_OK;

@@ -20,7 +20,8 @@ constexpr int kMaxGroups = 32;
 // shared per-group accumulators once at the end, each block publishes its partials, and the
 // last block of an image (arrival counter, self-cleaning) reduces the slabs in a fixed order
 // (deterministic) and writes mean / rstd.
-__global__ void __launch_bounds__(1024) gn_stats_kernel(const bf16* __restrict__ x0, const bf16* __restrict__ x1,
+template <int DT>
+__global__ void __launch_bounds__(1024) gn_stats_kernel(const void* __restrict__ x0, const void* __restrict__ x1,
                                                         int C0, int C1, float* __restrict__ partial,
                                                         float* __restrict__ mean_rstd, unsigned int* __restrict__ counters,
                                                         int hw, int groups, int pix_per_slab, int rows_per_pass,
@@ -37,10 +38,11 @@ __global__ void __launch_bounds__(1024) gn_stats_kernel(const bf16* __restrict__
     const int vec = threadIdx.x % C8;
     const int prow = threadIdx.x / C8;
     const int c = vec * 8;
-    const bf16* src;
+    const void* src;
+    size_t off;
     int pitch;
-    if (c < C0) { src = x0 + (size_t)b * hw * C0 + c; pitch = C0; }
-    else { src = x1 + (size_t)b * hw * C1 + (c - C0); pitch = C1; }
+    if (c < C0) { src = x0; off = (size_t)b * hw * C0 + c; pitch = C0; }
+    else { src = x1; off = (size_t)b * hw * C1 + (c - C0); pitch = C1; }
     const int p_begin = slab * pix_per_slab;
     const int p_end = min(p_begin + pix_per_slab, hw);
     float s[8], ss[8];
@@ -49,14 +51,10 @@ __global__ void __launch_bounds__(1024) gn_stats_kernel(const bf16* __restrict__
     if (prow < rows_per_pass) {
 #pragma unroll 4
         for (int pp = p_begin + prow; pp < p_end; pp += rows_per_pass) {
-            const uint4 u = __ldg(reinterpret_cast<const uint4*>(src + (size_t)pp * pitch));
-            const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+            float f[8];
+            ld8<DT>(src, off + (size_t)pp * pitch, f);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float2 f = unpack_bf16x2(w[j]);
-                s[2 * j] += f.x; ss[2 * j] += f.x * f.x;
-                s[2 * j + 1] += f.y; ss[2 * j + 1] += f.y * f.y;
-            }
+            for (int j = 0; j < 8; ++j) { s[j] += f[j]; ss[j] += f[j] * f[j]; }
         }
         float* ps = s_part + (size_t)prow * C + c;
         float* pq = s_part + (size_t)(rows_per_pass + prow) * C + c;
@@ -118,9 +116,11 @@ __global__ void __launch_bounds__(1024) gn_stats_kernel(const bf16* __restrict__
 }
 
 // ---- pass 2: normalise + affine (+ SiLU), write the concatenated bf16 tensor --------------------
-__global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const bf16* __restrict__ x0, const bf16* __restrict__ x1,
+template <int DT>
+__global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const void* __restrict__ x0, const void* __restrict__ x1,
                                                               int C0, int C1, const float* __restrict__ gamma,
                                                               const float* __restrict__ beta, bf16* __restrict__ out,
+                                                              bf16* __restrict__ raw_out,
                                                               const float* __restrict__ mean_rstd, int hw,
                                                               int groups, int silu, int pix_per_block) {
     extern __shared__ float2 s_ab[];  // per-channel (scale, shift)
@@ -145,26 +145,23 @@ __global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const bf16* __rest
     for (int i = threadIdx.x; i < total; i += blockDim.x) {
         const int p = p_begin + i / vec_per_pix;
         const int c = (i % vec_per_pix) * 8;
-        const bf16* src = (c < C0) ? x0 + ((size_t)b * hw + p) * C0 + c : x1 + ((size_t)b * hw + p) * C1 + (c - C0);
-        uint4 u = __ldg(reinterpret_cast<const uint4*>(src));
-        uint32_t w[4] = {u.x, u.y, u.z, u.w};
-        uint32_t o[4];
+        float f[8], y[8];
+        if (c < C0) ld8<DT>(x0, ((size_t)b * hw + p) * C0 + c, f);
+        else ld8<DT>(x1, ((size_t)b * hw + p) * C1 + (c - C0), f);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            float2 f = unpack_bf16x2(w[j]);
-            const float2 ab0 = s_ab[c + 2 * j], ab1 = s_ab[c + 2 * j + 1];
-            float y0 = f.x * ab0.x + ab0.y;
-            float y1 = f.y * ab1.x + ab1.y;
-            if (silu) { y0 = silu_f(y0); y1 = silu_f(y1); }
-            o[j] = pack_bf16x2(y0, y1);
+        for (int j = 0; j < 8; ++j) {
+            const float2 ab = s_ab[c + j];
+            y[j] = f[j] * ab.x + ab.y;
+            if (silu) y[j] = silu_f(y[j]);
         }
-        *reinterpret_cast<uint4*>(out + ((size_t)b * hw + p) * C + c) = make_uint4(o[0], o[1], o[2], o[3]);
+        st8<B200SD_BF16>(out, ((size_t)b * hw + p) * C + c, y);
+        if (raw_out) st8<B200SD_BF16>(raw_out, ((size_t)b * hw + p) * C + c, f);  // bf16 copy of [x0|x1] (1x1 shortcut operand)
     }
 }
 
 // ---- LayerNorm: one warp per row, row held in registers (C <= 1280) ------------------------------
-template <int PAIRS_PER_LANE>
-__global__ void __launch_bounds__(256) layernorm_kernel(const bf16* __restrict__ x, const float* __restrict__ gamma,
+template <int PAIRS_PER_LANE, int DT>
+__global__ void __launch_bounds__(256) layernorm_kernel(const void* __restrict__ x, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, bf16* __restrict__ out,
                                                         int rows, int C, float eps) {
     ptx::pdl_trigger();
@@ -172,12 +169,14 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const bf16* __restrict__
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (warp >= rows) return;
-    const uint32_t* src = reinterpret_cast<const uint32_t*>(x + (size_t)warp * C);
     float2 v[PAIRS_PER_LANE];
     float s = 0.f;
 #pragma unroll
     for (int i = 0; i < PAIRS_PER_LANE; ++i) {
-        v[i] = unpack_bf16x2(__ldg(src + lane + 32 * i));
+        if constexpr (DT == B200SD_F32)
+            v[i] = __ldg(reinterpret_cast<const float2*>(static_cast<const float*>(x) + (size_t)warp * C) + lane + 32 * i);
+        else
+            v[i] = unpack_bf16x2(__ldg(reinterpret_cast<const uint32_t*>(static_cast<const bf16*>(x) + (size_t)warp * C) + lane + 32 * i));
         s += v[i].x + v[i].y;
     }
     const float mean = warp_sum(s) / (float)C;
@@ -201,8 +200,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const bf16* __restrict__
 }  // namespace
 
 extern "C" int b200sd_groupnorm_silu(const void* x0, const void* x1, int C0, int C1, const float* gamma,
-                                     const float* beta, void* out, float* stats_ws, int batch, int hw, int groups,
-                                     float eps, int silu, b200sd_stream_t stream) {
+                                     const float* beta, void* out, void* raw_out, float* stats_ws, int batch, int hw,
+                                     int groups, float eps, int silu, int in_dtype, b200sd_stream_t stream) {
     B200SD_REQUIRE(x0 && gamma && beta && out && stats_ws, "groupnorm: null pointer");
     if (!x1) C1 = 0;
     const int C = C0 + C1;
@@ -226,8 +225,14 @@ extern "C" int b200sd_groupnorm_silu(const void* x0, const void* x1, int C0, int
     int pps = ceil_div(hw, slabs);
     pps = ceil_div(pps, rows_per_pass) * rows_per_pass;
     slabs = ceil_div(hw, pps);
-    B200SD_CUDA(b200sd_launch(gn_stats_kernel, dim3(dim3(slabs, batch)), dim3(threads), (size_t)2 * rows_per_pass * C * sizeof(float), s, static_cast<const bf16*>(x0), static_cast<const bf16*>(x1), C0, C1,
-                                                          partial, mean_rstd, counters, hw, groups, pps, rows_per_pass, eps));
+    B200SD_REQUIRE(in_dtype == B200SD_BF16 || in_dtype == B200SD_F32, "groupnorm: bad input dtype");
+    const size_t st_smem = (size_t)2 * rows_per_pass * C * sizeof(float);
+    if (in_dtype == B200SD_F32)
+        B200SD_CUDA(b200sd_launch(gn_stats_kernel<B200SD_F32>, dim3(slabs, batch), dim3(threads), st_smem, s, x0, x1, C0, C1, partial,
+                                  mean_rstd, counters, hw, groups, pps, rows_per_pass, eps));
+    else
+        B200SD_CUDA(b200sd_launch(gn_stats_kernel<B200SD_BF16>, dim3(slabs, batch), dim3(threads), st_smem, s, x0, x1, C0, C1, partial,
+                                  mean_rstd, counters, hw, groups, pps, rows_per_pass, eps));
     COUNT_LAUNCH();
     B200SD_LAUNCH_CHECK();
     int blocks = ceil_div(b200sd_num_sms() * 4, batch);
@@ -235,9 +240,12 @@ extern "C" int b200sd_groupnorm_silu(const void* x0, const void* x1, int C0, int
     const int min_ppb = ceil_div(kGnThreads * 4, C / 8);  // >= 4 vectors per thread
     if (ppb < min_ppb) ppb = min_ppb;
     blocks = ceil_div(hw, ppb);
-    B200SD_CUDA(b200sd_launch(gn_apply_kernel, dim3(dim3(blocks, batch)), dim3(kGnThreads), C * sizeof(float2), s, 
-        static_cast<const bf16*>(x0), static_cast<const bf16*>(x1), C0, C1, gamma, beta, static_cast<bf16*>(out), mean_rstd,
-        hw, groups, silu, ppb));
+    if (in_dtype == B200SD_F32)
+        B200SD_CUDA(b200sd_launch(gn_apply_kernel<B200SD_F32>, dim3(blocks, batch), dim3(kGnThreads), C * sizeof(float2), s, x0, x1, C0, C1,
+                                  gamma, beta, static_cast<bf16*>(out), static_cast<bf16*>(raw_out), mean_rstd, hw, groups, silu, ppb));
+    else
+        B200SD_CUDA(b200sd_launch(gn_apply_kernel<B200SD_BF16>, dim3(blocks, batch), dim3(kGnThreads), C * sizeof(float2), s, x0, x1, C0, C1,
+                                  gamma, beta, static_cast<bf16*>(out), static_cast<bf16*>(raw_out), mean_rstd, hw, groups, silu, ppb));
     COUNT_LAUNCH();
     B200SD_LAUNCH_CHECK();
     return B200SD_OK;
@@ -249,17 +257,21 @@ extern "C" int b200sd_groupnorm_workspace_floats(int batch) {
 }
 
 extern "C" int b200sd_layernorm(const void* x, const float* gamma, const float* beta, void* out, int rows, int C,
-                                float eps, b200sd_stream_t stream) {
+                                float eps, int in_dtype, b200sd_stream_t stream) {
     B200SD_REQUIRE(x && gamma && beta && out, "layernorm: null pointer");
     B200SD_REQUIRE(rows > 0, "layernorm: rows must be positive");
     B200SD_REQUIRE(C % 64 == 0 && C >= 64 && C <= 1280, "layernorm: C=%d unsupported (multiple of 64, <= 1280)", C);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const int blocks = ceil_div(rows, 8);
-    const bf16* xi = static_cast<const bf16*>(x);
+    const void* xi = x;
+    B200SD_REQUIRE(in_dtype == B200SD_BF16 || in_dtype == B200SD_F32, "layernorm: bad input dtype");
     bf16* xo = static_cast<bf16*>(out);
 #define LN_CASE(P)                                                                                     \
     case P:                                                                                            \
-        B200SD_CUDA(b200sd_launch(layernorm_kernel<P>, dim3(blocks), dim3(256), 0, s, xi, gamma, beta, xo, rows, C, eps));                  \
+        if (in_dtype == B200SD_F32)                                                                         \
+            B200SD_CUDA(b200sd_launch(layernorm_kernel<P, B200SD_F32>, dim3(blocks), dim3(256), 0, s, xi, gamma, beta, xo, rows, C, eps)); \
+        else                                                                                                \
+            B200SD_CUDA(b200sd_launch(layernorm_kernel<P, B200SD_BF16>, dim3(blocks), dim3(256), 0, s, xi, gamma, beta, xo, rows, C, eps)); \
         break;
     switch (C / 64) {
         LN_CASE(1) LN_CASE(2) LN_CASE(3) LN_CASE(4) LN_CASE(5) LN_CASE(6) LN_CASE(7) LN_CASE(8) LN_CASE(9) LN_CASE(10)

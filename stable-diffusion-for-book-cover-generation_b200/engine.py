@@ -119,7 +119,9 @@ class Engine:
 
         # ---- conv_in ----
         h, w = self.H, self.W
-        x = pool.get(N * h * w, boc[0])
+        F32 = torch.float32   # the residual stream (block inputs/outputs, hs, conv1 -> norm2) stays fp32;
+        #                       bf16 appears only where a tensor is a tensor-core operand
+        x = pool.get(N * h * w, boc[0], F32)
         P.append(lambda x=x: ops.conv_in(self.in_sample, Wp["conv_in"]["w"], Wp["conv_in"]["b"], x), "conv_io", 0, "conv_in")
 
         self._tap("conv_in", x, h, w)
@@ -137,8 +139,10 @@ class Engine:
             M = N * h * w
             cin, cout = r.cin, r.cout
             t1 = pool.get(M, cin)
-            P.append(lambda: ops.groupnorm_silu(x, skip, wr["g1"], wr["b1"], t1, N, h * w, 32, cfg.norm_eps, True), "groupnorm")
-            hbuf = pool.get(M, cout)
+            raw = pool.get(M, cin) if "wsc" in wr else None   # bf16 copy of [x|skip]: operand of the 1x1 shortcut
+            P.append(lambda: ops.groupnorm_silu(x, skip, wr["g1"], wr["b1"], t1, N, h * w, 32, cfg.norm_eps, True,
+                                                raw_out=raw), "groupnorm")
+            hbuf = pool.get(M, cout, F32)
             rb = (self.tproj.data_ptr() + m._tproj_off[prefix] * 4, n_tp, h * w)
             self._gemm(P, t1, wr["w1"], hbuf, bias=wr["cb1"], conv=(N, h, w), rowbias_ptr=rb)
             pool.put(t1)
@@ -146,11 +150,12 @@ class Engine:
             P.append(lambda: ops.groupnorm_silu(hbuf, None, wr["g2"], wr["b2"], t2, N, h * w, 32, cfg.norm_eps, True), "groupnorm")
             pool.put(hbuf)
             if "wsc" in wr:
-                sc = pool.get(M, cout)
-                self._gemm(P, x, wr["wsc"], sc, a1=skip, bias=wr["bsc"])
+                sc = pool.get(M, cout, F32)
+                self._gemm(P, raw, wr["wsc"], sc, bias=wr["bsc"])
+                pool.put(raw)
             else:
                 sc = x
-            y = pool.get(M, cout)
+            y = pool.get(M, cout, F32)
             self._gemm(P, t2, wr["w2"], y, bias=wr["cb2"], residual=sc, conv=(N, h, w))
             pool.put(t2)
             if sc is not x:
@@ -169,7 +174,7 @@ class Engine:
             self._gemm(self.ctx_plan, self.in_ctx, wa["w_kv2"], kv)
             t = pool.get(M, Cc)
             P.append(lambda: ops.groupnorm_silu(x, None, wa["gn_g"], wa["gn_b"], t, N, h * w, 32, 1e-6, False), "groupnorm")
-            hs = pool.get(M, Cc)
+            hs = pool.get(M, Cc, F32)
             self._gemm(P, t, wa["w_in"], hs, bias=wa["b_in"])
             # self attention
             P.append(lambda: ops.layernorm(hs, wa["ln1_g"], wa["ln1_b"], t), "layernorm")
@@ -193,11 +198,12 @@ class Engine:
             P.append(lambda: ops.layernorm(hs, wa["ln3_g"], wa["ln3_b"], t), "layernorm")
             ff = pool.get(M, 4 * Cc)
             self._gemm(P, t, wa["w_ff1"], ff, bias=wa["b_ff1"], epilogue=ops.EPI_GEGLU, block_n=wa["ff_tile"])
-            self._gemm(P, ff, wa["w_ff2"], hs, bias=wa["b_ff2"], residual=hs)
+            # last residual add of the block: its only consumer is proj_out's A operand -> write bf16 directly
+            self._gemm(P, ff, wa["w_ff2"], t, bias=wa["b_ff2"], residual=hs)
             pool.put(ff)
+            y = pool.get(M, Cc, F32)
+            self._gemm(P, t, wa["w_out"], y, bias=wa["b_out"], residual=x)
             pool.put(t)
-            y = pool.get(M, Cc)
-            self._gemm(P, hs, wa["w_out"], y, bias=wa["b_out"], residual=x)
             pool.put(hs)
             self._tap(prefix, y, h, w)
             return y
@@ -223,7 +229,7 @@ class Engine:
                 col = pool.get(N * (h // 2) * (w // 2), 9 * Cc)
                 P.append(lambda x=x, col=col, h=h, w=w: ops.im2col_s2(x, col, N, h, w), "resample", 0, "im2col_s2")
                 h, w = h // 2, w // 2
-                y = pool.get(N * h * w, Cc)
+                y = pool.get(N * h * w, Cc, F32)
                 self._gemm(P, col, wd["w"], y, bias=wd["b"])
                 pool.put(col)
                 release(x)
@@ -262,7 +268,7 @@ class Engine:
                 P.append(lambda x=x, up=up, h=h, w=w: ops.upsample2x(x, up, N, h, w), "resample", 0, "upsample2x")
                 release(x)
                 h, w = 2 * h, 2 * w
-                y = pool.get(N * h * w, Cc)
+                y = pool.get(N * h * w, Cc, F32)
                 self._gemm(P, up, wu["w"], y, bias=wu["b"], conv=(N, h, w))
                 pool.put(up)
                 x = y

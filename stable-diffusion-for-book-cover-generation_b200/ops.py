@@ -192,6 +192,7 @@ def gemm(a0, w, out, *, a1=None, bias=None, rowbias=None, residual=None, conv=No
     args.rows_per_image = rows_per_image
     args.epilogue = epilogue
     args.out_dtype = _dt(out)
+    args.residual_dtype = _dt(residual) if residual is not None else BF16
     args.block_n, args.split_k = block_n, split_k
     args.workspace, args.workspace_bytes = _p(ws), ws.numel()
     if not launch:
@@ -211,7 +212,7 @@ def geglu_tile(N):
 def conv_in(x_nchw, w_packed, bias, out):
     _chk(x_nchw, w_packed, bias, out)
     B, Cin, H, W = x_nchw.shape
-    check(lib().b200sd_conv_in(_p(x_nchw), _p(w_packed), _p(bias), _p(out), B, Cin, w_packed.shape[0], H, W, _stream()),
+    check(lib().b200sd_conv_in(_p(x_nchw), _p(w_packed), _p(bias), _p(out), B, Cin, w_packed.shape[0], H, W, _dt(out), _stream()),
           "conv_in")
     return out
 
@@ -224,20 +225,22 @@ def conv_out(x_nhwc, w_packed, bias, out_nchw):
     return out_nchw
 
 
-def groupnorm_silu(x0, x1, gamma, beta, out, batch, hw, groups=32, eps=1e-5, silu=True):
-    _chk(x0, x1, gamma, beta, out)
+def groupnorm_silu(x0, x1, gamma, beta, out, batch, hw, groups=32, eps=1e-5, silu=True, raw_out=None):
+    _chk(x0, x1, gamma, beta, out, raw_out)
+    if x1 is not None and x1.dtype != x0.dtype:
+        raise B200SDError("groupnorm: both sources must have the same dtype")
     ws = _workspace("gn", lib().b200sd_groupnorm_workspace_floats(batch) * 4, x0.device)
     C0 = x0.shape[-1]
     C1 = x1.shape[-1] if x1 is not None else 0
-    check(lib().b200sd_groupnorm_silu(_p(x0), _p(x1), C0, C1, _p(gamma), _p(beta), _p(out), _p(ws), batch, hw, groups,
-                                      float(eps), int(silu), _stream()), "groupnorm_silu")
+    check(lib().b200sd_groupnorm_silu(_p(x0), _p(x1), C0, C1, _p(gamma), _p(beta), _p(out), _p(raw_out), _p(ws), batch, hw,
+                                      groups, float(eps), int(silu), _dt(x0), _stream()), "groupnorm_silu")
     return out
 
 
 def layernorm(x, gamma, beta, out, eps=1e-5):
     _chk(x, gamma, beta, out)
     Cc = x.shape[-1]
-    check(lib().b200sd_layernorm(_p(x), _p(gamma), _p(beta), _p(out), x.numel() // Cc, Cc, float(eps), _stream()),
+    check(lib().b200sd_layernorm(_p(x), _p(gamma), _p(beta), _p(out), x.numel() // Cc, Cc, float(eps), _dt(x), _stream()),
           "layernorm")
     return out
 
@@ -255,11 +258,11 @@ def attention(q, k, v, out, batch, heads, Sq, Skv, d, scale, ldq=None, ldk=None,
 
 def upsample2x(x, out, batch, H, W):
     _chk(x, out)
-    check(lib().b200sd_upsample2x(_p(x), _p(out), batch, H, W, x.shape[-1], _stream()), "upsample2x")
+    check(lib().b200sd_upsample2x(_p(x), _p(out), batch, H, W, x.shape[-1], _dt(x), _stream()), "upsample2x")
     return out
 
 
 def im2col_s2(x, out, batch, H, W):
     _chk(x, out)
-    check(lib().b200sd_im2col_s2(_p(x), _p(out), batch, H, W, x.shape[-1], _stream()), "im2col_s2")
+    check(lib().b200sd_im2col_s2(_p(x), _p(out), batch, H, W, x.shape[-1], _dt(x), _stream()), "im2col_s2")
     return out

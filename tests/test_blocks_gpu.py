@@ -135,3 +135,45 @@ def test_upsample_and_im2col():
     unf = F.unfold(x.permute(0, 3, 1, 2).float(), 3, padding=1, stride=2)  # (B, C*9, L), index c*9 + tap
     unf = unf.reshape(B, C, 9, -1).permute(0, 3, 2, 1).reshape(B * (H // 2) * (W // 2), 9 * C)
     assert torch.equal(col.float(), unf)
+
+
+def test_fp32_residual_stream_variants():
+    """fp32 inputs (the engine's residual stream) for the norm / resample kernels + the raw bf16 copy."""
+    from b200sd import ops
+    from b200sd.packing import pack_conv3x3_f32
+    torch.manual_seed(6)
+    B, hw, C0, C1 = 2, 256, 1280, 640
+    x0 = torch.randn(B * hw, C0, device=DEV) * 2 + 0.5
+    x1 = torch.randn(B * hw, C1, device=DEV) - 1.0
+    g, b = torch.randn(C0 + C1, device=DEV), torch.randn(C0 + C1, device=DEV)
+    out = torch.empty(B * hw, C0 + C1, device=DEV, dtype=torch.bfloat16)
+    raw = torch.empty_like(out)
+    ops.groupnorm_silu(x0, x1, g, b, out, B, hw, 32, 1e-5, True, raw_out=raw)
+    xc = torch.cat([x0, x1], 1)
+    want = F.silu(F.group_norm(xc.reshape(B, hw, -1).permute(0, 2, 1), 32, g, b, 1e-5)).permute(0, 2, 1).reshape(B * hw, -1)
+    _close(out, want, 1.0 / 128)
+    assert torch.equal(raw, xc.bfloat16())
+
+    x = torch.randn(2048, 640, device=DEV) * 3 + 1
+    gg, bb = torch.randn(640, device=DEV), torch.randn(640, device=DEV)
+    o = torch.empty(2048, 640, device=DEV, dtype=torch.bfloat16)
+    ops.layernorm(x, gg, bb, o)
+    _close(o, F.layer_norm(x, (640,), gg, bb, 1e-5), 1.0 / 128)
+
+    Bn, H, W, C = 2, 16, 16, 640
+    xf = torch.randn(Bn, H, W, C, device=DEV)
+    up = torch.empty(Bn, 2 * H, 2 * W, C, device=DEV, dtype=torch.bfloat16)
+    ops.upsample2x(xf.reshape(-1, C), up.reshape(-1, C), Bn, H, W)
+    want = F.interpolate(xf.permute(0, 3, 1, 2), scale_factor=2.0, mode="nearest").permute(0, 2, 3, 1).bfloat16()
+    assert torch.equal(up, want)
+    col = torch.empty(Bn * (H // 2) * (W // 2), 9 * C, device=DEV, dtype=torch.bfloat16)
+    ops.im2col_s2(xf.reshape(-1, C), col, Bn, H, W)
+    unf = F.unfold(xf.permute(0, 3, 1, 2), 3, padding=1, stride=2).reshape(Bn, C, 9, -1).permute(0, 3, 2, 1)
+    assert torch.equal(col, unf.reshape(col.shape).bfloat16())
+
+    xin = torch.randn(2, 4, 32, 32, device=DEV)
+    w = torch.randn(320, 4, 3, 3, device=DEV) / 6
+    bi = torch.randn(320, device=DEV)
+    o32 = torch.empty(2 * 32 * 32, 320, device=DEV)
+    ops.conv_in(xin, pack_conv3x3_f32(w), bi, o32)
+    _close(o32, F.conv2d(xin, w, bi, padding=1).permute(0, 2, 3, 1).reshape(-1, 320), 1e-5)

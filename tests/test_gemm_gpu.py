@@ -140,3 +140,22 @@ def test_gemm_rejects_bad_shapes():
     out = torch.empty(128, 64, device=DEV, dtype=torch.bfloat16)
     with pytest.raises(B200SDError):
         ops.gemm(a, w, out)
+
+
+@pytest.mark.parametrize("M,N,K,split", [(8192, 320, 320, 1), (512, 1280, 5120, 0), (128, 1280, 2560, 4)])
+def test_gemm_fp32_residual_and_output(M, N, K, split):
+    """fp32 residual stream: out(fp32) = A W^T + bias + residual(fp32), incl. in-place (out is residual)."""
+    from b200sd import ops
+    _setup()
+    torch.manual_seed(M + K)
+    a = torch.randn(M, K, device=DEV).bfloat16()
+    w = (torch.randn(N, K, device=DEV) / K ** 0.5).bfloat16()
+    bias = torch.randn(N, device=DEV)
+    res = torch.randn(M, N, device=DEV)
+    want = a.float() @ w.float().t() + bias + res
+    out = res.clone()
+    ops.gemm(a, w, out, bias=bias, residual=out, split_k=split)
+    _close(out, want, rel=2e-5)
+    outb = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+    ops.gemm(a, w, outb, bias=bias, residual=res, split_k=split)
+    _close(outb, want)
