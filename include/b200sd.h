@@ -108,9 +108,9 @@ int b200sd_small_linear(const float* in, const void* w_bf16, const float* bias, 
  *   B200SD_EPI_LINEAR : bias / rowbias / residual as above.
  *   B200SD_EPI_GEGLU  : W rows are tile-interleaved [value | gate] (see b200sd_geglu_tile());
  *                       out[M, N/2] = value * gelu_erf(gate), bias likewise interleaved.
- * split_k > 1 needs the workspace (b200sd_gemm_workspace_bytes; ZERO before first use: arrival counters,
- * left zeroed): every split publishes its fp32 partial tile there and the last CTA of a tile sums the
- * splits in a fixed order (bit-deterministic) and runs the epilogue.
+ * split_k in {1, 2, 4, 8}: the split CTAs of a tile form a thread-block cluster, exchange their fp32
+ * partial tiles through distributed shared memory and each reduces + stores 128/split_k rows in a fixed
+ * order (bit-deterministic).  No scratch is needed (workspace may be NULL).
  */
 #define B200SD_EPI_LINEAR 0
 #define B200SD_EPI_GEGLU 1

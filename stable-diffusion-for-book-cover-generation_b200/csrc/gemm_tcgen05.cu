@@ -12,8 +12,8 @@
 // activation source (a1) extends the channel axis, which fuses the up-block torch.cat.
 // With <= 113 KB of smem and <= 256 TMEM columns per CTA two CTAs share an SM, so one CTA's
 // epilogue overlaps the other's main loop.  Small-M / deep-K layers are split along K with a
-// fp32 partial tiles in an L2-resident workspace; the last CTA of a tile sums them in a fixed order
-// (deterministic) and runs the epilogue.
+// the split CTAs of a tile form a thread-block cluster, exchange their fp32 partial tiles through
+// distributed shared memory, and each reduces + stores 128/split rows in a fixed order (deterministic).
 #include <atomic>
 #include <cstring>
 #include <cstdio>
@@ -23,7 +23,20 @@
 
 extern std::atomic<long long> g_b200sd_launches;
 
+static unsigned long long* g_gemm_trace = nullptr;
+extern "C" void b200sd_debug_gemm_trace(void* buf) { g_gemm_trace = static_cast<unsigned long long*>(buf); }
+
 namespace {
+
+__device__ __forceinline__ unsigned long long gtimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#define TRACE(slot)                                                                                   \
+    do {                                                                                              \
+        if (p.trace) p.trace[((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 8 + (slot)] = gtimer(); \
+    } while (0)
 
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;  // 64 bf16 = 128 B = one swizzle row
@@ -32,8 +45,6 @@ constexpr int kNumThreads = 192;
 constexpr int kMaxStages = 8;
 constexpr int kABytes = BLOCK_M * BLOCK_K * 2;  // 16 KB (always reserved in full)
 
-constexpr size_t kSplitWsBytes = 64ull << 20;  // fp32 partial tiles [tile][split][128][block_n]
-constexpr int kMaxSplitTiles = 4096;           // per-tile arrival counters live after the partials
 
 struct KParams {
     CUtensorMap tmA0, tmA1, tmB;
@@ -41,8 +52,6 @@ struct KParams {
     const float* rowbias;
     const void* residual;
     void* out;
-    float* ws_partials;
-    unsigned int* ws_counters;
     int M, N;
     int num_k_blocks;    // total K / 64
     int kb_per_split;
@@ -62,41 +71,24 @@ struct KParams {
     int out_f32;
     int res_f32;
     uint32_t tmem_cols;
+    unsigned long long* trace;  // optional [ctas][8] globaltimer stamps (debug)
 };
 
-// Final epilogue for 8 consecutive output columns of one row: v = accumulators (fp32).
-__device__ __forceinline__ void epilogue_store8(const KParams& p, int row, int col, float (&v)[8]) {
-    if (p.bias) {
-        const float4* b = reinterpret_cast<const float4*>(p.bias + col);
-        const float4 t0 = __ldg(b), t1 = __ldg(b + 1);
-        v[0] += t0.x; v[1] += t0.y; v[2] += t0.z; v[3] += t0.w;
-        v[4] += t1.x; v[5] += t1.y; v[6] += t1.z; v[7] += t1.w;
-    }
-    if (p.rowbias) {
-        const float4* b = reinterpret_cast<const float4*>(p.rowbias + (size_t)(row / p.rows_per_image) * p.ldrb + col);
-        const float4 t0 = __ldg(b), t1 = __ldg(b + 1);
-        v[0] += t0.x; v[1] += t0.y; v[2] += t0.z; v[3] += t0.w;
-        v[4] += t1.x; v[5] += t1.y; v[6] += t1.z; v[7] += t1.w;
-    }
-    if (p.residual) {
-        float r[8];
-        if (p.res_f32) ld8<B200SD_F32>(p.residual, (size_t)row * p.ldr + col, r);
-        else ld8<B200SD_BF16>(p.residual, (size_t)row * p.ldr + col, r);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] += r[i];
-    }
-    if (p.out_f32) {
-        float4* o = reinterpret_cast<float4*>(static_cast<float*>(p.out) + (size_t)row * p.ldc + col);
-        o[0] = make_float4(v[0], v[1], v[2], v[3]);
-        o[1] = make_float4(v[4], v[5], v[6], v[7]);
-    } else {
-        uint4 u;
-        u.x = pack_bf16x2(v[0], v[1]);
-        u.y = pack_bf16x2(v[2], v[3]);
-        u.z = pack_bf16x2(v[4], v[5]);
-        u.w = pack_bf16x2(v[6], v[7]);
-        *reinterpret_cast<uint4*>(static_cast<bf16*>(p.out) + (size_t)row * p.ldc + col) = u;
-    }
+// cluster helpers (split-K reduction over distributed shared memory)
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ float4 ld_dsmem_v4(uint32_t local_smem_addr, uint32_t cta_rank) {
+    uint32_t raddr;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(local_smem_addr), "r"(cta_rank));
+    float4 v;
+    asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(raddr) : "memory");
+    return v;
 }
 
 __global__ void __launch_bounds__(kNumThreads, 1) gemm_tcgen05_kernel(const __grid_constant__ KParams p) {
@@ -111,7 +103,6 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tcgen05_kernel(const __gr
     uint64_t* empty_bar = bars + kMaxStages;
     uint64_t* tmem_full_bar = bars + 2 * kMaxStages;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 1);
-    uint32_t* last_flag = tmem_slot + 1;
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -124,6 +115,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tcgen05_kernel(const __gr
     const int m0 = m_tile * p.rows_valid;
 
     ptx::pdl_trigger();
+    if (threadIdx.x == 0) TRACE(0);
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tmap(&p.tmA0);
         ptx::prefetch_tmap(&p.tmB);
@@ -144,6 +136,21 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tcgen05_kernel(const __gr
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     ptx::pdl_wait();  // everything above overlapped the previous kernel's tail
+    if (threadIdx.x == 0) TRACE(1);
+
+    // epilogue-side shared state (also visible to part 2 after the role dispatch)
+    const int epi_tid = threadIdx.x - 64;  // 0..127 for the epilogue warps
+    const int pitch_f = p.block_n + 4;     // +16 B: conflict-free 16-byte row-strided stores
+    float* stage = reinterpret_cast<float*>(smem);
+    float* s_bias = reinterpret_cast<float*>(bars + 32);   // [256]
+    float* s_rb = s_bias + 256;                            // [2][256] row-bias of the (at most two) images of this tile
+    int img0 = 0, img1 = 0;
+    bool rb_smem = false;
+    if (p.rowbias) {
+        img0 = m0 / p.rows_per_image;
+        img1 = (min(m0 + p.rows_valid, p.M) - 1) / p.rows_per_image;
+        rb_smem = (img1 - img0) <= 1;
+    }
 
     if (warp == 0) {
         // ================= TMA producer =================
@@ -185,6 +192,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tcgen05_kernel(const __gr
             for (int kb = kb_begin; kb < kb_end; ++kb) {
                 ptx::mbar_wait(&full_bar[stage], phase);
                 ptx::tc_fence_after();
+                if (kb == kb_begin) TRACE(2);
                 const uint64_t da = ptx::umma_desc_k_sw128(ptx::smem_u32(smem_a + (size_t)stage * kABytes));
                 const uint64_t db = ptx::umma_desc_k_sw128(ptx::smem_u32(smem_b + (size_t)stage * b_bytes));
 #pragma unroll
@@ -196,23 +204,25 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tcgen05_kernel(const __gr
                 if (++stage == p.stages) { stage = 0; phase ^= 1; }
             }
             ptx::umma_commit(tmem_full_bar);
+            TRACE(3);
         }
     } else {
-        // ================= epilogue warps =================
-        // Phase A: TMEM -> registers -> fp32 staging tile in the (now idle) smem ring, one row per thread.
-        // Phase B: each warp re-reads ITS 32 rows with lanes running along the columns, so every global
-        //          access (residual load, output store, split-K reduction) is a coalesced 16/32-byte vector.
+        // ================= epilogue warps, part 1 =================
+        // While the main loop runs: park this tile's bias (and time-embedding row bias) in smem.
+        // Then TMEM -> registers -> fp32 staging tile in the (by then idle) smem ring, one row per thread.
         const int q = warp & 3;              // TMEM lane quarter this warp may access
         const int r_in_tile = q * 32 + lane;
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
-        const int epi_tid = threadIdx.x - 64;  // 0..127
-        const int pitch_f = p.block_n + 4;     // +16 B: conflict-free 16-byte row-strided stores
-        float* stage = reinterpret_cast<float*>(smem);
-        const int tile_id = m_tile * gridDim.y + n_tile;
-
+        for (int c = epi_tid; c < p.block_n; c += 128) {
+            s_bias[c] = p.bias ? __ldg(p.bias + n0 + c) : 0.f;
+            if (rb_smem) {
+                s_rb[c] = __ldg(p.rowbias + (size_t)img0 * p.ldrb + n0 + c);
+                s_rb[256 + c] = __ldg(p.rowbias + (size_t)img1 * p.ldrb + n0 + c);
+            }
+        }
         ptx::mbar_wait(tmem_full_bar, 0);
         ptx::tc_fence_after();
-
+        if (epi_tid == 0) TRACE(4);
         {
             float4* my_row = reinterpret_cast<float4*>(stage + (size_t)r_in_tile * pitch_f);
             for (int c = 0; c < p.block_n; c += 32) {
@@ -234,100 +244,115 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tcgen05_kernel(const __gr
             }
         }
         ptx::tc_fence_before();
-        __syncwarp();
-
-        const float* wstage = stage + (size_t)(q * 32) * pitch_f;
-        const int rows_here = min(32, min(p.rows_valid, p.M - m0) - q * 32);  // valid rows of this warp (may be <= 0)
-        bool do_final = true;
-        const float* src = wstage;
-        int src_pitch = pitch_f;
-
-        if (p.split_k > 1) {
-            // every split publishes its fp32 partial tile (coalesced, L2-resident); the last-arriving CTA
-            // of the tile sums the splits in a FIXED order (deterministic) and runs the epilogue.
-            float* mine = p.ws_partials + (((size_t)tile_id * p.split_k + split) * BLOCK_M + q * 32) * p.block_n;
-            const int groups4 = p.block_n / 4;
-            const int items = rows_here * groups4;
-#pragma unroll 4
-            for (int idx = lane; idx < items; idx += 32) {
-                const int rl = idx / groups4, c4 = idx - rl * groups4;
-                const float4 v = *reinterpret_cast<const float4*>(wstage + (size_t)rl * pitch_f + c4 * 4);
-                __stcg(reinterpret_cast<float4*>(mine + (size_t)rl * p.block_n + c4 * 4), v);
-            }
-            __threadfence();
-            ptx::named_bar_sync(1, 128);
-            if (epi_tid == 0) {
-                const unsigned int prev = atomicAdd(p.ws_counters + tile_id, 1u);
-                const bool last = (prev == (unsigned int)p.split_k - 1);
-                if (last) p.ws_counters[tile_id] = 0;  // self-cleaning
-                __threadfence();
-                *last_flag = last ? 1u : 0u;
-            }
-            ptx::named_bar_sync(1, 128);
-            do_final = (*last_flag != 0);
-            src = p.ws_partials + ((size_t)tile_id * p.split_k * BLOCK_M + q * 32) * p.block_n;
-            src_pitch = p.block_n;
-        }
-
-        if (do_final && rows_here > 0) {
-            const bool from_ws = p.split_k > 1;
-            if (p.epilogue == B200SD_EPI_GEGLU) {
-                const int half = p.block_n / 2;
-                const int groups = half / 8;
-                const int items = rows_here * groups;
-#pragma unroll 2
-                for (int idx = lane; idx < items; idx += 32) {
-                    const int rl = idx / groups, c8 = idx - rl * groups;
-                    const float* sp = src + (size_t)rl * src_pitch + c8 * 8;
-                    const float4 a0 = *reinterpret_cast<const float4*>(sp), a1 = *reinterpret_cast<const float4*>(sp + 4);
-                    const float4 g0 = *reinterpret_cast<const float4*>(sp + half), g1 = *reinterpret_cast<const float4*>(sp + half + 4);
-                    const float4* bv = reinterpret_cast<const float4*>(p.bias + n0 + c8 * 8);
-                    const float4* bg = reinterpret_cast<const float4*>(p.bias + n0 + half + c8 * 8);
-                    const float4 bv0 = __ldg(bv), bv1 = __ldg(bv + 1), bg0 = __ldg(bg), bg1 = __ldg(bg + 1);
-                    uint4 u;
-                    u.x = pack_bf16x2((a0.x + bv0.x) * gelu_erf_f(g0.x + bg0.x), (a0.y + bv0.y) * gelu_erf_f(g0.y + bg0.y));
-                    u.y = pack_bf16x2((a0.z + bv0.z) * gelu_erf_f(g0.z + bg0.z), (a0.w + bv0.w) * gelu_erf_f(g0.w + bg0.w));
-                    u.z = pack_bf16x2((a1.x + bv1.x) * gelu_erf_f(g1.x + bg1.x), (a1.y + bv1.y) * gelu_erf_f(g1.y + bg1.y));
-                    u.w = pack_bf16x2((a1.z + bv1.z) * gelu_erf_f(g1.z + bg1.z), (a1.w + bv1.w) * gelu_erf_f(g1.w + bg1.w));
-                    const int row = m0 + q * 32 + rl;
-                    *reinterpret_cast<uint4*>(static_cast<bf16*>(p.out) + (size_t)row * p.ldc + n_tile * half + c8 * 8) = u;
-                }
-            } else {
-                const int groups = p.block_n / 8;
-                const int items = rows_here * groups;
-#pragma unroll 4
-                for (int idx = lane; idx < items; idx += 32) {
-                    const int rl = idx / groups, c8 = idx - rl * groups;
-                    float v[8];
-                    if (from_ws) {
-                        const size_t split_stride = (size_t)BLOCK_M * p.block_n;
-                        const float* ap = src + (size_t)rl * src_pitch + c8 * 8;
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) v[i] = 0.f;
-#pragma unroll 4
-                        for (int sp_i = 0; sp_i < p.split_k; ++sp_i) {
-                            const float4 a0 = __ldcg(reinterpret_cast<const float4*>(ap + sp_i * split_stride));
-                            const float4 a1 = __ldcg(reinterpret_cast<const float4*>(ap + sp_i * split_stride) + 1);
-                            v[0] += a0.x; v[1] += a0.y; v[2] += a0.z; v[3] += a0.w;
-                            v[4] += a1.x; v[5] += a1.y; v[6] += a1.z; v[7] += a1.w;
-                        }
-                    } else {
-                        const float* sp = src + (size_t)rl * src_pitch + c8 * 8;
-                        const float4 a0 = *reinterpret_cast<const float4*>(sp), a1 = *reinterpret_cast<const float4*>(sp + 4);
-                        v[0] = a0.x; v[1] = a0.y; v[2] = a0.z; v[3] = a0.w; v[4] = a1.x; v[5] = a1.y; v[6] = a1.z; v[7] = a1.w;
-                    }
-                    epilogue_store8(p, m0 + q * 32 + rl, n0 + c8 * 8, v);
-                }
-            }
-        }
-        ptx::tc_fence_before();
+        ptx::named_bar_sync(1, 128);  // whole staging tile (and the bias tiles) written
+        if (epi_tid == 0) TRACE(5);
     }
+
+    // Split-K: the `split_k` CTAs of a tile form one thread-block cluster; after this barrier every CTA can
+    // read its peers' staging tiles through distributed shared memory.
+    if (p.split_k > 1) cluster_sync_all();
+
+    if (warp >= 2) {
+        // ================= epilogue, part 2: reduce (split-K) + fused epilogue + coalesced stores =================
+        // The 128 epilogue threads walk (row, 8-column group) items with consecutive threads on consecutive
+        // 16/32-byte vectors of a row.  With split-K each CTA of the cluster owns 128/split_k rows of the tile and
+        // sums the split partials in a fixed order (deterministic).  Loads of a batch are issued before any
+        // store so that (possibly aliasing, in-place) residual reads are not serialised behind the stores.
+        const int rank = p.split_k > 1 ? (int)cluster_ctarank() : 0;
+        const int rows_per_cta = BLOCK_M / p.split_k;
+        const int row_begin = rank * rows_per_cta;
+        int valid = min(p.rows_valid, p.M - m0) - row_begin;
+        valid = max(0, min(valid, rows_per_cta));
+        const uint32_t stage_u32 = ptx::smem_u32(stage);
+        const bool geglu = p.epilogue == B200SD_EPI_GEGLU;
+        const int half = p.block_n / 2;
+        const int groups = (geglu ? half : p.block_n) / 8;
+        const int items = valid * groups;
+        const uint32_t ginv = ((1u << 20) + groups - 1) / groups;  // idx / groups == (idx * ginv) >> 20 for idx < 4160
+        constexpr int U = 4;
+        for (int base = epi_tid; base < items; base += 128 * U) {
+            float v[U][8], r[U][8];
+            int rl[U], c8[U];
+            bool ok[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int idx = base + 128 * u;
+                ok[u] = idx < items;
+                const int id = ok[u] ? idx : 0;
+                rl[u] = row_begin + (int)(((uint32_t)id * ginv) >> 20);
+                c8[u] = id - (rl[u] - row_begin) * groups;
+                const uint32_t off = (uint32_t)(rl[u] * pitch_f + c8[u] * 8) * 4u;
+                if (p.split_k > 1) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v[u][i] = 0.f;
+                    for (int sp = 0; sp < p.split_k; ++sp) {
+                        const float4 a0 = ld_dsmem_v4(stage_u32 + off, sp), a1 = ld_dsmem_v4(stage_u32 + off + 16, sp);
+                        v[u][0] += a0.x; v[u][1] += a0.y; v[u][2] += a0.z; v[u][3] += a0.w;
+                        v[u][4] += a1.x; v[u][5] += a1.y; v[u][6] += a1.z; v[u][7] += a1.w;
+                    }
+                } else {
+                    const float* sp = stage + (size_t)rl[u] * pitch_f + c8[u] * 8;
+                    const float4 a0 = *reinterpret_cast<const float4*>(sp), a1 = *reinterpret_cast<const float4*>(sp + 4);
+                    v[u][0] = a0.x; v[u][1] = a0.y; v[u][2] = a0.z; v[u][3] = a0.w;
+                    v[u][4] = a1.x; v[u][5] = a1.y; v[u][6] = a1.z; v[u][7] = a1.w;
+                }
+                if (geglu) {
+                    const float* sp = stage + (size_t)rl[u] * pitch_f + half + c8[u] * 8;
+                    const float4 g0 = *reinterpret_cast<const float4*>(sp), g1 = *reinterpret_cast<const float4*>(sp + 4);
+                    r[u][0] = g0.x; r[u][1] = g0.y; r[u][2] = g0.z; r[u][3] = g0.w;
+                    r[u][4] = g1.x; r[u][5] = g1.y; r[u][6] = g1.z; r[u][7] = g1.w;
+                } else if (p.residual) {
+                    const size_t ro = (size_t)(m0 + rl[u]) * p.ldr + n0 + c8[u] * 8;
+                    if (p.res_f32) ld8<B200SD_F32>(p.residual, ro, r[u]);
+                    else ld8<B200SD_BF16>(p.residual, ro, r[u]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) r[u][i] = 0.f;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (!ok[u]) continue;
+                const int row = m0 + rl[u];
+                const int cb = c8[u] * 8;  // column within the tile
+                float o[8];
+                if (geglu) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        o[i] = (v[u][i] + s_bias[cb + i]) * gelu_erf_f(r[u][i] + s_bias[half + cb + i]);
+                    st8<B200SD_BF16>(p.out, (size_t)row * p.ldc + n_tile * half + cb, o);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) o[i] = v[u][i] + s_bias[cb + i] + r[u][i];
+                    if (p.rowbias) {
+                        const int img = row / p.rows_per_image;
+                        if (rb_smem) {
+                            const float* rb = s_rb + (img == img0 ? 0 : 256) + cb;
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) o[i] += rb[i];
+                        } else {
+                            float t[8];
+                            ld8<B200SD_F32>(p.rowbias, (size_t)img * p.ldrb + n0 + cb, t);
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) o[i] += t[i];
+                        }
+                    }
+                    if (p.out_f32) st8<B200SD_F32>(p.out, (size_t)row * p.ldc + n0 + cb, o);
+                    else st8<B200SD_BF16>(p.out, (size_t)row * p.ldc + n0 + cb, o);
+                }
+            }
+        }
+        if (epi_tid == 0) TRACE(6);
+    }
+    // peers may still be reading this CTA's staging tile
+    if (p.split_k > 1) cluster_sync_all();
 
     __syncthreads();
     if (warp == 1) {
         ptx::tc_fence_after();
         ptx::tmem_dealloc(tmem_base, p.tmem_cols);
     }
+    if (threadIdx.x == 0) TRACE(7);
 }
 
 uint32_t pow2_cols(int n) {
@@ -359,7 +384,7 @@ int pick_block_n(int N, int m_tiles, int epilogue) {
 
 }  // namespace
 
-extern "C" size_t b200sd_gemm_workspace_bytes(void) { return kSplitWsBytes + kMaxSplitTiles * sizeof(unsigned int); }
+extern "C" size_t b200sd_gemm_workspace_bytes(void) { return 0; }  // split-K reduces over DSMEM: no scratch needed
 
 extern "C" int b200sd_geglu_tile(int N) { return pick_block_n(N, 1, B200SD_EPI_GEGLU); }
 
@@ -444,7 +469,7 @@ extern "C" int b200sd_gemm(const b200sd_gemm_args* a, b200sd_stream_t stream) {
     const int n_tiles = a->N / bn;
     p.tmem_cols = pow2_cols(bn);
 
-    // ---- split-K ----
+    // ---- split-K: the splits of a tile form a thread-block cluster (<= 8 CTAs) and reduce over DSMEM ----
     const int sms = b200sd_num_sms();
     int split = a->split_k;
     static const bool no_split = getenv("B200SD_SPLITK") && getenv("B200SD_SPLITK")[0] == '0';
@@ -452,24 +477,14 @@ extern "C" int b200sd_gemm(const b200sd_gemm_args* a, b200sd_stream_t stream) {
         split = 1;
         const int tiles = m_tiles * n_tiles;
         if (!no_split && a->epilogue == B200SD_EPI_LINEAR && tiles * 2 <= sms && p.num_k_blocks >= 32) {
-            split = sms / tiles;
-            const int max_by_k = p.num_k_blocks / 16;  // keep >= 16 k-blocks per split
-            if (split > max_by_k) split = max_by_k;
-            if (split > 8) split = 8;
-            if (split < 1) split = 1;
+            while (split < 8 && tiles * split * 2 <= sms && p.num_k_blocks / (split * 2) >= 16) split *= 2;
         }
     }
     B200SD_REQUIRE(split == 1 || a->epilogue == B200SD_EPI_LINEAR, "gemm: split-K only with the linear epilogue");
+    B200SD_REQUIRE(split == 1 || split == 2 || split == 4 || split == 8, "gemm: split_k must be 1, 2, 4 or 8 (cluster size)");
     p.kb_per_split = ceil_div(p.num_k_blocks, split);
-    split = ceil_div(p.num_k_blocks, p.kb_per_split);  // no empty splits
+    B200SD_REQUIRE((split - 1) * p.kb_per_split < p.num_k_blocks, "gemm: split_k=%d leaves an empty split for K=%d", split, a->K);
     p.split_k = split;
-    if (split > 1) {
-        const size_t need = (size_t)m_tiles * n_tiles * split * BLOCK_M * bn * sizeof(float);
-        B200SD_REQUIRE(a->workspace != nullptr && a->workspace_bytes >= b200sd_gemm_workspace_bytes(), "gemm: split-K needs the workspace");
-        B200SD_REQUIRE(need <= kSplitWsBytes && m_tiles * n_tiles <= kMaxSplitTiles, "gemm: split-K workspace too small (%zu B)", need);
-        p.ws_partials = static_cast<float*>(a->workspace);
-        p.ws_counters = reinterpret_cast<unsigned int*>(static_cast<uint8_t*>(a->workspace) + kSplitWsBytes);
-    }
 
     // ---- pipeline depth ----
     // Grids that fit in one wave keep every k-block of a short K loop in flight (deep ring, 1 CTA/SM);
@@ -478,7 +493,7 @@ extern "C" int b200sd_gemm(const b200sd_gemm_args* a, b200sd_stream_t stream) {
     const long total_ctas = (long)m_tiles * n_tiles * split;
     int stages;
     if (total_ctas <= sms || bn > 160) stages = (200 * 1024) / stage_bytes;
-    else stages = (110 * 1024) / stage_bytes;
+    else stages = (108 * 1024) / stage_bytes;
     if (stages > kMaxStages) stages = kMaxStages;
     if (stages > p.kb_per_split && total_ctas <= sms) stages = p.kb_per_split;
     const int min_stages = ceil_div(BLOCK_M * (bn + 4) * (int)sizeof(float), stage_bytes);  // epilogue staging tile
@@ -486,7 +501,7 @@ extern "C" int b200sd_gemm(const b200sd_gemm_args* a, b200sd_stream_t stream) {
     if (stages < 2) stages = 2;
     p.stages = stages;
     B200SD_REQUIRE((size_t)stages * stage_bytes >= (size_t)BLOCK_M * (bn + 4) * sizeof(float), "gemm: smem ring smaller than the epilogue staging tile");
-    const size_t smem_bytes = (size_t)stages * stage_bytes + 1024 /*align slack*/ + 256 /*barriers*/;
+    const size_t smem_bytes = (size_t)stages * stage_bytes + 1024 /*align slack*/ + 256 /*barriers*/ + 3072 /*bias tiles*/;
     B200SD_REQUIRE(smem_bytes <= 227 * 1024, "gemm: smem budget exceeded (%zu B)", smem_bytes);
 
     // ---- tensor maps ----
@@ -528,8 +543,31 @@ extern "C" int b200sd_gemm(const b200sd_gemm_args* a, b200sd_stream_t stream) {
         B200SD_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
         configured_smem = 227 * 1024;
     }
-    dim3 grid(m_tiles, n_tiles, split);
-    B200SD_CUDA(b200sd_launch(gemm_tcgen05_kernel, dim3(grid), dim3(kNumThreads), smem_bytes, static_cast<cudaStream_t>(stream), p));
+    p.trace = g_gemm_trace;
+    {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(m_tiles, n_tiles, split);
+        cfg.blockDim = dim3(kNumThreads);
+        cfg.dynamicSmemBytes = smem_bytes;
+        cfg.stream = static_cast<cudaStream_t>(stream);
+        cudaLaunchAttribute attr[2];
+        int na = 0;
+        if (split > 1) {
+            attr[na].id = cudaLaunchAttributeClusterDimension;
+            attr[na].val.clusterDim.x = 1;
+            attr[na].val.clusterDim.y = 1;
+            attr[na].val.clusterDim.z = split;
+            ++na;
+        }
+        if (b200sd_pdl_enabled()) {
+            attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[na].val.programmaticStreamSerializationAllowed = 1;
+            ++na;
+        }
+        cfg.attrs = attr;
+        cfg.numAttrs = na;
+        B200SD_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel, p));
+    }
     g_b200sd_launches.fetch_add(1, std::memory_order_relaxed);
     B200SD_LAUNCH_CHECK();
     return B200SD_OK;

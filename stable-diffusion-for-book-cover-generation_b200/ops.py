@@ -163,7 +163,7 @@ def small_linear(x, w_bf16, bias, silu_in=False, silu_out=False, out=None):
 
 
 def gemm_workspace(device):
-    return _workspace("gemm", lib().b200sd_gemm_workspace_bytes(), device)
+    return _workspace("gemm", max(16, lib().b200sd_gemm_workspace_bytes()), device)
 
 
 def gemm(a0, w, out, *, a1=None, bias=None, rowbias=None, residual=None, conv=None, rows_per_image=0,

@@ -47,7 +47,7 @@ def test_gemm_f32_out_no_bias():
     _close(out, a.float() @ w.float().t(), rel=1e-4)
 
 
-@pytest.mark.parametrize("split", [2, 4, 7])
+@pytest.mark.parametrize("split", [2, 4, 8])
 def test_gemm_split_k(split):
     from b200sd import ops
     _setup()

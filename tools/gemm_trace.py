@@ -1,0 +1,61 @@
+"""Timeline of the GEMM kernel's phases (globaltimer stamps written by every CTA): where do the
+microseconds of a small GEMM go?"""
+import ctypes, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from b200sd import ops
+from b200sd._lib import lib
+from b200sd.packing import pack_conv3x3
+DEV = "cuda:0"
+L = lib()
+L.b200sd_debug_gemm_trace.argtypes = [ctypes.c_void_p]
+trace = torch.zeros(4096 * 8, dtype=torch.int64, device=DEV)
+names = ["start", "prologue done", "first tile landed", "all MMA issued", "accum ready (epi)", "phaseA done", "phaseB done", "exit"]
+
+def run(label, fn, nctas):
+    for _ in range(3): fn()
+    torch.cuda.synchronize()
+    trace.zero_()
+    L.b200sd_debug_gemm_trace(trace.data_ptr())
+    fn(); torch.cuda.synchronize()
+    L.b200sd_debug_gemm_trace(None)
+    t = trace[: nctas * 8].view(nctas, 8).cpu().double()
+    t0 = t[:, 0].min()
+    rel = (t - t0) / 1e3
+    print(f"== {label}: {nctas} CTAs; kernel span {float(rel[:, 7].max()):.2f} us")
+    print("   phase                  median   min     max  (us since first CTA start)")
+    for i, n in enumerate(names):
+        c = rel[:, i]
+        print(f"   {n:20s} {float(c.median()):7.2f} {float(c.min()):7.2f} {float(c.max()):7.2f}")
+
+def gemm_case(M, N, K, res=True, f32=True):
+    a = torch.randn(M, K, device=DEV).bfloat16(); w = (torch.randn(N, K, device=DEV) / K ** 0.5).bfloat16()
+    bias = torch.randn(N, device=DEV)
+    out = torch.randn(M, N, device=DEV) if f32 else torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+    r = out if res else None
+    args = ops.gemm(a, w, out, bias=bias, residual=r, launch=False)
+    return (lambda: ops.gemm_run(args)), (a, w, bias, out)
+
+for (M, N, K) in [(8192, 320, 320), (512, 1280, 1280), (2048, 640, 640), (8192, 320, 1280)]:
+    fn, keep = gemm_case(M, N, K)
+    # ask the library how many CTAs: replicate heuristics crudely by reading the trace afterwards
+    trace.zero_(); L.b200sd_debug_gemm_trace(trace.data_ptr()); fn(); torch.cuda.synchronize(); L.b200sd_debug_gemm_trace(None)
+    n = int((trace.view(-1, 8)[:, 0] != 0).sum())
+    run(f"gemm M{M} N{N} K{K} (+bias +fp32 residual, fp32 out)", fn, n)
+
+B, H, W, Cin, Cout = 2, 8, 8, 1280, 1280
+x = torch.randn(B * H * W, Cin, device=DEV).bfloat16()
+w = pack_conv3x3(torch.randn(Cout, Cin, 3, 3, device=DEV) / (9 * Cin) ** 0.5); bias = torch.randn(Cout, device=DEV)
+out = torch.randn(B * H * W, Cout, device=DEV)
+args = ops.gemm(x, w, out, bias=bias, residual=out, conv=(B, H, W), launch=False)
+fn = lambda: ops.gemm_run(args)
+trace.zero_(); L.b200sd_debug_gemm_trace(trace.data_ptr()); fn(); torch.cuda.synchronize(); L.b200sd_debug_gemm_trace(None)
+run("conv3x3 8x8 1280->1280 (M128 N1280 K11520)", fn, int((trace.view(-1, 8)[:, 0] != 0).sum()))
+B, H, W, Cin, Cout = 2, 64, 64, 320, 320
+x = torch.randn(B * H * W, Cin, device=DEV).bfloat16()
+w = pack_conv3x3(torch.randn(Cout, Cin, 3, 3, device=DEV) / (9 * Cin) ** 0.5); bias = torch.randn(Cout, device=DEV)
+out = torch.randn(B * H * W, Cout, device=DEV)
+args2 = ops.gemm(x, w, out, bias=bias, residual=out, conv=(B, H, W), launch=False)
+fn2 = lambda: ops.gemm_run(args2)
+trace.zero_(); L.b200sd_debug_gemm_trace(trace.data_ptr()); fn2(); torch.cuda.synchronize(); L.b200sd_debug_gemm_trace(None)
+run("conv3x3 64x64 320->320 (M8192 N320 K2880)", fn2, int((trace.view(-1, 8)[:, 0] != 0).sum()))
