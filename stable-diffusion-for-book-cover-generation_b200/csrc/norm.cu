@@ -159,6 +159,129 @@ __global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const void* __rest
     }
 }
 
+
+// ---- fused GroupNorm: ONE kernel, one thread-block cluster per (image, set of G adjacent groups) ------------
+// The CL CTAs of a cluster split the pixels.  Pass 1: every thread owns one 8-channel vector column and
+// walks its pixels accumulating per-channel sums; a fixed-order fold gives this CTA's per-group partials,
+// which the cluster exchanges through distributed shared memory (fixed rank order: deterministic).
+// Pass 2 re-reads the same slab (L1/L2-hot), normalises, applies affine (+SiLU) and writes bf16 (+ the raw copy).
+__device__ __forceinline__ void gn_cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float gn_ld_dsmem(const float* local, uint32_t rank) {
+    uint32_t raddr;
+    float v;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(ptx::smem_u32(local)), "r"(rank));
+    asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(raddr) : "memory");
+    return v;
+}
+
+template <int DT>
+__global__ void __launch_bounds__(512) gn_fused_kernel(const void* __restrict__ x0, const void* __restrict__ x1, int C0,
+                                                       int C1, const float* __restrict__ gamma,
+                                                       const float* __restrict__ beta, bf16* __restrict__ out,
+                                                       bf16* __restrict__ raw_out, int hw, int groups, int G, int CL,
+                                                       int pix_per_cta, int R, float eps, int silu) {
+    extern __shared__ float gsm[];  // [2][R][Cg] per-thread channel sums | [Cg] scale | [Cg] shift
+    __shared__ float s_cta[2 * kMaxGroups];   // this CTA's (sum, sumsq) per group of the set
+    __shared__ float s_mr[2 * kMaxGroups];    // (mean, rstd) per group of the set
+    const int C = C0 + C1;
+    const int cpg = C / groups;
+    const int Cg = G * cpg;          // channels of this group set (multiple of 8)
+    const int VC = Cg / 8;
+    const int rank = blockIdx.x;     // cluster spans gridDim.x == CL
+    const int set = blockIdx.y, b = blockIdx.z;
+    const int c_base = set * Cg;
+    float* s_part = gsm;
+    float2* s_ab = reinterpret_cast<float2*>(gsm + 2 * R * Cg);
+    ptx::pdl_trigger();
+    ptx::pdl_wait();
+    const int vec = threadIdx.x % VC, prow = threadIdx.x / VC;
+    const bool active = prow < R;
+    const int c = c_base + vec * 8;  // global channel of this thread's vector
+    const void* src;
+    size_t off;
+    int pitch;
+    if (c < C0) { src = x0; off = (size_t)b * hw * C0 + c; pitch = C0; }
+    else { src = x1; off = (size_t)b * hw * C1 + (c - C0); pitch = C1; }
+    const int p_begin = rank * pix_per_cta;
+    const int p_end = min(p_begin + pix_per_cta, hw);
+
+    // ---- pass 1 ----
+    if (active) {
+        float s[8], ss[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { s[j] = 0.f; ss[j] = 0.f; }
+#pragma unroll 4
+        for (int pp = p_begin + prow; pp < p_end; pp += R) {
+            float f[8];
+            ld8<DT>(src, off + (size_t)pp * pitch, f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { s[j] += f[j]; ss[j] += f[j] * f[j]; }
+        }
+        float* ps = s_part + (size_t)prow * Cg + vec * 8;
+        float* pq = s_part + (size_t)(R + prow) * Cg + vec * 8;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { ps[j] = s[j]; pq[j] = ss[j]; }
+    }
+    __syncthreads();
+    if (threadIdx.x < G) {
+        float a = 0.f, q = 0.f;
+        for (int r = 0; r < R; ++r) {
+            const float* ps = s_part + (size_t)r * Cg + threadIdx.x * cpg;
+            const float* pq = s_part + (size_t)(R + r) * Cg + threadIdx.x * cpg;
+            for (int j = 0; j < cpg; ++j) { a += ps[j]; q += pq[j]; }
+        }
+        s_cta[2 * threadIdx.x] = a;
+        s_cta[2 * threadIdx.x + 1] = q;
+    }
+    if (CL > 1) gn_cluster_sync(); else __syncthreads();
+    if (threadIdx.x < G) {
+        double sum = 0.0, sq = 0.0;
+        if (CL > 1) {
+            for (int r = 0; r < CL; ++r) {
+                sum += (double)gn_ld_dsmem(&s_cta[2 * threadIdx.x], r);
+                sq += (double)gn_ld_dsmem(&s_cta[2 * threadIdx.x + 1], r);
+            }
+        } else {
+            sum = s_cta[2 * threadIdx.x];
+            sq = s_cta[2 * threadIdx.x + 1];
+        }
+        const double cnt = (double)hw * cpg;
+        const double mean = sum / cnt;
+        double var = sq / cnt - mean * mean;
+        if (var < 0.0) var = 0.0;
+        s_mr[2 * threadIdx.x] = (float)mean;
+        s_mr[2 * threadIdx.x + 1] = (float)(1.0 / sqrt(var + (double)eps));
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < Cg; i += blockDim.x) {
+        const int g = i / cpg;
+        const float a = s_mr[2 * g + 1] * __ldg(gamma + c_base + i);
+        s_ab[i] = make_float2(a, __ldg(beta + c_base + i) - s_mr[2 * g] * a);
+    }
+    __syncthreads();
+
+    // ---- pass 2 ----
+    if (active) {
+#pragma unroll 4
+        for (int pp = p_begin + prow; pp < p_end; pp += R) {
+            float f[8], y[8];
+            ld8<DT>(src, off + (size_t)pp * pitch, f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float2 ab = s_ab[vec * 8 + j];
+                y[j] = f[j] * ab.x + ab.y;
+                if (silu) y[j] = silu_f(y[j]);
+            }
+            const size_t o = ((size_t)b * hw + pp) * C + c;
+            st8<B200SD_BF16>(out, o, y);
+            if (raw_out) st8<B200SD_BF16>(raw_out, o, f);
+        }
+    }
+    if (CL > 1) gn_cluster_sync();  // peers may still be reading s_cta
+}
+
 // ---- LayerNorm: one warp per row, row held in registers (C <= 1280) ------------------------------
 template <int PAIRS_PER_LANE, int DT>
 __global__ void __launch_bounds__(256) layernorm_kernel(const void* __restrict__ x, const float* __restrict__ gamma,
@@ -211,6 +334,59 @@ extern "C" int b200sd_groupnorm_silu(const void* x0, const void* x1, int C0, int
     B200SD_REQUIRE(C0 % 8 == 0 && C1 % 8 == 0, "groupnorm: channel counts must be multiples of 8");
     B200SD_REQUIRE(C * sizeof(float2) <= 48 * 1024, "groupnorm: C=%d too large", C);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    B200SD_REQUIRE(in_dtype == B200SD_BF16 || in_dtype == B200SD_F32, "groupnorm: bad input dtype");
+    {
+        // fused single-kernel path
+        const int cpg = C / groups;
+        int G = 1;
+        while ((G * cpg) % 8 != 0 && G < groups) G *= 2;
+        while (G * 2 <= groups && groups % (G * 2) == 0 && G * cpg < 32) G *= 2;   // >= 32 channels per pixel segment
+        const int Cg = G * cpg;
+        if ((Cg % 8) == 0 && groups % G == 0 && Cg / 8 <= 512) {
+            const int VC = Cg / 8;
+            const int sets = groups / G;
+            int CL = 1;
+            while (CL < 8 && (long)batch * sets * CL < b200sd_num_sms() && hw / (CL * 2) >= 32) CL *= 2;
+            const int ppc = ceil_div(hw, CL);
+            int R = 256 / VC;
+            if (R < 1) R = 1;
+            if (R > ppc) R = ppc;
+            int threads = ((VC * R + 31) / 32) * 32;
+            if (threads < 32) threads = 32;
+            const size_t smem = ((size_t)2 * R * Cg + 2 * Cg) * sizeof(float);
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(CL, sets, batch);
+            cfg.blockDim = dim3(threads);
+            cfg.dynamicSmemBytes = smem;
+            cfg.stream = s;
+            cudaLaunchAttribute attr[2];
+            int na = 0;
+            if (CL > 1) {
+                attr[na].id = cudaLaunchAttributeClusterDimension;
+                attr[na].val.clusterDim.x = CL;
+                attr[na].val.clusterDim.y = 1;
+                attr[na].val.clusterDim.z = 1;
+                ++na;
+            }
+            if (b200sd_pdl_enabled()) {
+                attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+                attr[na].val.programmaticStreamSerializationAllowed = 1;
+                ++na;
+            }
+            cfg.attrs = attr;
+            cfg.numAttrs = na;
+            if (in_dtype == B200SD_F32)
+                B200SD_CUDA(cudaLaunchKernelEx(&cfg, gn_fused_kernel<B200SD_F32>, x0, x1, C0, C1, gamma, beta, static_cast<bf16*>(out),
+                                               static_cast<bf16*>(raw_out), hw, groups, G, CL, ppc, R, eps, silu));
+            else
+                B200SD_CUDA(cudaLaunchKernelEx(&cfg, gn_fused_kernel<B200SD_BF16>, x0, x1, C0, C1, gamma, beta, static_cast<bf16*>(out),
+                                               static_cast<bf16*>(raw_out), hw, groups, G, CL, ppc, R, eps, silu));
+            COUNT_LAUNCH();
+            B200SD_LAUNCH_CHECK();
+            return B200SD_OK;
+        }
+    }
+    // two-kernel fallback (stats + apply) for channel layouts the fused kernel does not cover
     const int C8 = C / 8;
     B200SD_REQUIRE(C8 <= 1024, "groupnorm: C=%d too large", C);
     const int rows_per_pass = (C8 >= 256) ? 1 : 256 / C8;
@@ -225,7 +401,6 @@ extern "C" int b200sd_groupnorm_silu(const void* x0, const void* x1, int C0, int
     int pps = ceil_div(hw, slabs);
     pps = ceil_div(pps, rows_per_pass) * rows_per_pass;
     slabs = ceil_div(hw, pps);
-    B200SD_REQUIRE(in_dtype == B200SD_BF16 || in_dtype == B200SD_F32, "groupnorm: bad input dtype");
     const size_t st_smem = (size_t)2 * rows_per_pass * C * sizeof(float);
     if (in_dtype == B200SD_F32)
         B200SD_CUDA(b200sd_launch(gn_stats_kernel<B200SD_F32>, dim3(slabs, batch), dim3(threads), st_smem, s, x0, x1, C0, C1, partial,
