@@ -170,9 +170,14 @@ int b200sd_layernorm(const void* x, const float* gamma, const float* beta, void*
 /* Fused (flash-style) attention: out = softmax(scale * Q K^T) V per (batch, head).
  * q: [batch*Sq, ldq] with head h at columns [h*d, (h+1)*d); k, v likewise with ldk / ldv;
  * out: [batch*Sq, ldo].  All bf16, fp32 softmax/accumulate.  d in {40, 80, 160} (+ 32, 64, 128).
+ * workspace (optional, b200sd_attention_workspace_bytes, 128-byte aligned): with it, head dims 40 / 80 and
+ * S_q, S_kv multiples of 128 run on the tcgen05/TMEM kernel (V is transposed into the workspace first);
+ * every other shape, or workspace == NULL, runs the register-resident mma.sync kernel.
  * Replaces CrossAttention._attention (baddbmm + softmax + bmm). */
+size_t b200sd_attention_workspace_bytes(int batch, int heads, int Skv, int d);
 int b200sd_attention(const void* q, const void* k, const void* v, void* out, int batch, int heads, int Sq, int Skv,
-                     int d, int ldq, int ldk, int ldv, int ldo, float scale, b200sd_stream_t stream);
+                     int d, int ldq, int ldk, int ldv, int ldo, float scale, void* workspace, size_t workspace_bytes,
+                     b200sd_stream_t stream);
 
 /* nearest x2 upsample NHWC bf16: (batch,H,W,C) -> (batch,2H,2W,C)  (Upsample2D's F.interpolate) */
 int b200sd_upsample2x(const void* x, void* out, int batch, int H, int W, int C, int in_dtype, b200sd_stream_t stream);

@@ -51,7 +51,8 @@ SIGNATURES = {
     "b200sd_groupnorm_silu": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _i, _i, _vp]),
     "b200sd_groupnorm_workspace_floats": (_i, [_i]),
     "b200sd_layernorm": (_i, [_vp, _vp, _vp, _vp, _i, _i, _f, _i, _vp]),
-    "b200sd_attention": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _vp]),
+    "b200sd_attention_workspace_bytes": (_sz, [_i, _i, _i, _i]),
+    "b200sd_attention": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _vp, _sz, _vp]),
     "b200sd_upsample2x": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "b200sd_im2col_s2": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
 }

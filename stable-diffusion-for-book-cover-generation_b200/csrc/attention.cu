@@ -7,6 +7,7 @@
 // shared memory (zero-filled), key tails (S_kv = 77) are masked to -inf.  The tcgen05/TMEM version
 // of this kernel is the next step for this row.
 #include <atomic>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -236,9 +237,17 @@ int launch_attention(const bf16* q, const bf16* k, const bf16* v, bf16* out, int
 
 }  // namespace
 
+int b200sd_attention_tc(const void* q, const void* k, const void* v, void* out, int batch, int heads, int Sq, int Skv,
+                        int d, int ldq, int ldk, int ldv, int ldo, float scale, void* workspace, size_t ws_bytes,
+                        cudaStream_t s);
+
+extern "C" size_t b200sd_attention_workspace_bytes(int batch, int heads, int Skv, int d) {
+    return (size_t)batch * heads * d * Skv * sizeof(bf16);
+}
+
 extern "C" int b200sd_attention(const void* q, const void* k, const void* v, void* out, int batch, int heads, int Sq,
                                 int Skv, int d, int ldq, int ldk, int ldv, int ldo, float scale,
-                                b200sd_stream_t stream) {
+                                void* workspace, size_t workspace_bytes, b200sd_stream_t stream) {
     B200SD_REQUIRE(q && k && v && out, "attention: null pointer");
     B200SD_REQUIRE(batch > 0 && heads > 0 && Sq > 0 && Skv > 0, "attention: bad sizes");
     B200SD_REQUIRE(batch <= 65535 && heads <= 65535, "attention: batch/heads too large");
@@ -248,6 +257,15 @@ extern "C" int b200sd_attention(const void* q, const void* k, const void* v, voi
                        (reinterpret_cast<uintptr_t>(out) & 3) == 0,
                    "attention: pointers must be 16-byte aligned");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    {
+        // tensor-core (tcgen05/TMEM) path for the self-attention-sized shapes
+        static const bool no_tc = getenv("B200SD_ATTN_TC") && getenv("B200SD_ATTN_TC")[0] == '0';
+        if (!no_tc) {
+            const int rc = b200sd_attention_tc(q, k, v, out, batch, heads, Sq, Skv, d, ldq, ldk, ldv, ldo, scale, workspace,
+                                               workspace_bytes, s);
+            if (rc != B200SD_ERR_UNSUPPORTED) return rc;
+        }
+    }
     const bf16* qq = static_cast<const bf16*>(q);
     const bf16* kk = static_cast<const bf16*>(k);
     const bf16* vv = static_cast<const bf16*>(v);

@@ -225,15 +225,30 @@ __global__ void __launch_bounds__(512) gn_fused_kernel(const void* __restrict__ 
         for (int j = 0; j < 8; ++j) { ps[j] = s[j]; pq[j] = ss[j]; }
     }
     __syncthreads();
-    if (threadIdx.x < G) {
-        float a = 0.f, q = 0.f;
-        for (int r = 0; r < R; ++r) {
-            const float* ps = s_part + (size_t)r * Cg + threadIdx.x * cpg;
-            const float* pq = s_part + (size_t)(R + r) * Cg + threadIdx.x * cpg;
-            for (int j = 0; j < cpg; ++j) { a += ps[j]; q += pq[j]; }
+    // fixed-order parallel fold: rows -> K row-chunks -> channels -> groups
+    {
+        const int K = max(1, min(R, (int)blockDim.x / (2 * Cg)));      // row chunks reduced in parallel
+        float* s_red = reinterpret_cast<float*>(s_ab);                  // [2][K][Cg] scratch (s_ab is built later)
+        for (int t = threadIdx.x; t < 2 * K * Cg; t += blockDim.x) {
+            const int which = t / (K * Cg), k = (t / Cg) % K, i = t % Cg;
+            float a = 0.f;
+            for (int r = k; r < R; r += K) a += s_part[(size_t)(which * R + r) * Cg + i];
+            s_red[t] = a;
         }
-        s_cta[2 * threadIdx.x] = a;
-        s_cta[2 * threadIdx.x + 1] = q;
+        __syncthreads();
+        for (int t = threadIdx.x; t < 2 * Cg; t += blockDim.x) {
+            const int which = t / Cg, i = t % Cg;
+            float a = 0.f;
+            for (int k = 0; k < K; ++k) a += s_red[(which * K + k) * Cg + i];
+            s_part[which * Cg + i] = a;   // reuse row 0 of s_part: per-channel totals [2][Cg]
+        }
+        __syncthreads();
+        for (int t = threadIdx.x; t < 2 * G; t += blockDim.x) {
+            const int which = t / G, g = t % G;
+            float a = 0.f;
+            for (int j = 0; j < cpg; ++j) a += s_part[which * Cg + g * cpg + j];
+            s_cta[2 * g + which] = a;
+        }
     }
     if (CL > 1) gn_cluster_sync(); else __syncthreads();
     if (threadIdx.x < G) {
@@ -353,7 +368,7 @@ extern "C" int b200sd_groupnorm_silu(const void* x0, const void* x1, int C0, int
             if (R > ppc) R = ppc;
             int threads = ((VC * R + 31) / 32) * 32;
             if (threads < 32) threads = 32;
-            const size_t smem = ((size_t)2 * R * Cg + 2 * Cg) * sizeof(float);
+            const size_t smem = ((size_t)2 * R * Cg + 2 * Cg + threads) * sizeof(float);
             cudaLaunchConfig_t cfg = {};
             cfg.gridDim = dim3(CL, sets, batch);
             cfg.blockDim = dim3(threads);

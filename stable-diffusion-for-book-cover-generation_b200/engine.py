@@ -117,6 +117,10 @@ class Engine:
         P.append(lambda: ops.small_linear(t_h, te["w2"], te["b2"], out=t_emb), "time_embed")
         P.append(lambda: ops.small_linear(t_emb, Wp["tproj"]["w"], Wp["tproj"]["b"], silu_in=True, out=self.tproj), "time_embed", 0, "time_emb_proj x22")
 
+        # scratch for the tensor-core attention (V^T of the largest self-attention), owned by this engine
+        self.attn_ws = torch.empty(ops.attention_workspace_bytes(N, self.heads, self.H * self.W, boc[0] // self.heads) + 256,
+                                   dtype=torch.uint8, device=dev)
+
         # ---- conv_in ----
         h, w = self.H, self.W
         F32 = torch.float32   # the residual stream (block inputs/outputs, hs, conv1 -> norm2) stays fp32;
@@ -181,7 +185,7 @@ class Engine:
             qkv = pool.get(M, 3 * Cc)
             self._gemm(P, t, wa["w_qkv"], qkv)
             P.append(lambda: ops.attention(qkv, qkv, qkv, t, N, self.heads, h * w, h * w, d, scale, ldq=3 * Cc,
-                                           ldk=3 * Cc, ldv=3 * Cc, ldo=Cc, q_off=0, k_off=Cc, v_off=2 * Cc),
+                                           ldk=3 * Cc, ldv=3 * Cc, ldo=Cc, q_off=0, k_off=Cc, v_off=2 * Cc, ws=self.attn_ws),
                      "attention", 4.0 * N * self.heads * (h * w) * (h * w) * d, f"self-attn S{h * w} d{d}")
             pool.put(qkv)
             self._gemm(P, t, wa["w_o1"], hs, bias=wa["b_o1"], residual=hs)
@@ -190,7 +194,7 @@ class Engine:
             q = pool.get(M, Cc)
             self._gemm(P, t, wa["w_q2"], q)
             P.append(lambda: ops.attention(q, kv, kv, t, N, self.heads, h * w, self.S, d, scale, ldq=Cc, ldk=2 * Cc,
-                                           ldv=2 * Cc, ldo=Cc, k_off=0, v_off=Cc),
+                                           ldv=2 * Cc, ldo=Cc, k_off=0, v_off=Cc, ws=self.attn_ws),
                      "attention", 4.0 * N * self.heads * (h * w) * self.S * d, f"cross-attn S{h * w} d{d}")
             pool.put(q)
             self._gemm(P, t, wa["w_o2"], hs, bias=wa["b_o2"], residual=hs)

@@ -51,6 +51,10 @@ def _workspace(key, nbytes, device, zero=True):
     return t
 
 
+def attention_workspace_bytes(batch, heads, Skv, d) -> int:
+    return int(lib().b200sd_attention_workspace_bytes(batch, heads, Skv, d))
+
+
 def launch_count() -> int:
     return int(lib().b200sd_launch_count())
 
@@ -246,13 +250,16 @@ def layernorm(x, gamma, beta, out, eps=1e-5):
 
 
 def attention(q, k, v, out, batch, heads, Sq, Skv, d, scale, ldq=None, ldk=None, ldv=None, ldo=None,
-              q_off=0, k_off=0, v_off=0):
+              q_off=0, k_off=0, v_off=0, ws=None):
     """q/k/v may be column slices of wider row-major buffers: pass the buffer plus an element offset."""
     _chk(q, k, v, out)
     es = 2
+    if ws is None:
+        ws = _workspace("attn", lib().b200sd_attention_workspace_bytes(batch, heads, Skv, d) + 128, q.device, zero=False)
     check(lib().b200sd_attention(q.data_ptr() + q_off * es, k.data_ptr() + k_off * es, v.data_ptr() + v_off * es,
                                  _p(out), batch, heads, Sq, Skv, d, ldq or q.shape[-1], ldk or k.shape[-1],
-                                 ldv or v.shape[-1], ldo or out.shape[-1], float(scale), _stream()), "attention")
+                                 ldv or v.shape[-1], ldo or out.shape[-1], float(scale), _p(ws), ws.numel(), _stream()),
+          "attention")
     return out
 
 
