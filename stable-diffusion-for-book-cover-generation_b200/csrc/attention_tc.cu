@@ -66,6 +66,11 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* m, uin
         ::"r"(ptx::smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(ptx::smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
+__device__ __forceinline__ float fast_exp2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -80,7 +85,7 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)
 
 // D = head dim (40 or 80); DKB = number of 64-wide blocks covering it (1 or 2)
 template <int D, int DKB>
-__global__ void __launch_bounds__(kThreads, 1) attention_tc_kernel(const __grid_constant__ AttnParams p) {
+__global__ void __launch_bounds__(kThreads, (D <= 40) ? 2 : 1) attention_tc_kernel(const __grid_constant__ AttnParams p) {
     constexpr int DN = (D + 15) / 16 * 16;    // MMA N of the PV product (48 / 80)
     constexpr int KSTEPS = (D + 15) / 16;     // UMMA K steps of the QK^T product
     constexpr int VBLK = D * 128;             // bytes of one V^T block [D rows x 64 keys]
@@ -194,28 +199,45 @@ __global__ void __launch_bounds__(kThreads, 1) attention_tc_kernel(const __grid_
         }
     } else {
         // ================= softmax warps: one thread per query row =================
+        // Software-pipelined: the fold of O_{j-1} into the register accumulator happens AFTER P_j has been
+        // handed to the tensor core, so the P_{j-1} V_{j-1} product overlaps the softmax of tile j.
         const int qd = warp & 3;
         const int row = qd * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(qd * 32) << 16;
-        float m = -INFINITY, l = 0.f;
+        float m = -INFINITY, l = 0.f, corr_prev = 1.f;
         float o[DN];
 #pragma unroll
         for (int i = 0; i < DN; ++i) o[i] = 0.f;
+        auto fold_o = [&](int jj, float corr) {
+            ptx::mbar_wait(o_full, jj & 1);
+            ptx::tc_fence_after();
+#pragma unroll
+            for (int c = 0; c < DN; c += 16) {
+                uint32_t r[16];
+                ptx::tmem_ld_32x32b_x16(tmem_O + lane_addr + c, r);
+                ptx::tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 16; ++i) o[c + i] = o[c + i] * corr + __uint_as_float(r[i]);
+            }
+            ptx::tc_fence_before();
+            ptx::mbar_arrive(o_empty);
+        };
         for (int j = 0; j < num_tiles; ++j) {
             ptx::mbar_wait(s_full, j & 1);
             ptx::tc_fence_after();
-            // pass 1: row max of this tile
+            // pass 1: row max of this tile (two TMEM loads in flight per wait)
             float mx = -INFINITY;
 #pragma unroll
-            for (int c = 0; c < 128; c += 32) {
-                uint32_t r[32];
-                tmem_ld_32x32b_x32(tmem_S + lane_addr + c, r);
+            for (int c = 0; c < 128; c += 64) {
+                uint32_t r0[32], r1[32];
+                tmem_ld_32x32b_x32(tmem_S + lane_addr + c, r0);
+                tmem_ld_32x32b_x32(tmem_S + lane_addr + c + 32, r1);
                 ptx::tmem_ld_wait();
 #pragma unroll
-                for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
+                for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fmaxf(__uint_as_float(r0[i]), __uint_as_float(r1[i])));
             }
             const float mn = fmaxf(m, mx);
-            const float corr = exp2f((m - mn) * p.scale_log2);
+            const float corr = fast_exp2((m - mn) * p.scale_log2);
             const float off = mn * p.scale_log2;
             m = mn;
             // pass 2: P = exp2(S * scale - off) -> bf16 -> swizzled smem tile; row sum in fp32
@@ -228,8 +250,8 @@ __global__ void __launch_bounds__(kThreads, 1) attention_tc_kernel(const __grid_
                 uint32_t pk[16];
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
-                    const float a = exp2f(__uint_as_float(r[2 * i]) * p.scale_log2 - off);
-                    const float bb = exp2f(__uint_as_float(r[2 * i + 1]) * p.scale_log2 - off);
+                    const float a = fast_exp2(fmaf(__uint_as_float(r[2 * i]), p.scale_log2, -off));
+                    const float bb = fast_exp2(fmaf(__uint_as_float(r[2 * i + 1]), p.scale_log2, -off));
                     rs += a + bb;
                     pk[i] = pack_bf16x2(a, bb);
                 }
@@ -244,20 +266,10 @@ __global__ void __launch_bounds__(kThreads, 1) attention_tc_kernel(const __grid_
             ptx::tc_fence_before();
             ptx::fence_proxy_async();   // generic-proxy smem writes -> visible to the tensor core (async proxy)
             ptx::mbar_arrive(p_full);
-            // fold O_j into the register accumulator
-            ptx::mbar_wait(o_full, j & 1);
-            ptx::tc_fence_after();
-#pragma unroll
-            for (int c = 0; c < DN; c += 16) {
-                uint32_t r[16];
-                ptx::tmem_ld_32x32b_x16(tmem_O + lane_addr + c, r);
-                ptx::tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 16; ++i) o[c + i] = o[c + i] * corr + __uint_as_float(r[i]);
-            }
-            ptx::tc_fence_before();
-            ptx::mbar_arrive(o_empty);
+            if (j > 0) fold_o(j - 1, corr_prev);   // P_{j-1} V_{j-1} ran while this tile's softmax was computed
+            corr_prev = corr;
         }
+        fold_o(num_tiles - 1, corr_prev);
         // ---- normalise and store ----
         const float inv = 1.0f / l;
         bf16* dst = p.out + ((size_t)b * p.Sq + q0 + row) * p.ldo + h * D;
@@ -318,6 +330,7 @@ int launch_tc(const bf16* q, const bf16* k, const bf16* vt, bf16* out, int batch
     static bool configured = false;
     if (!configured) {
         B200SD_CUDA(cudaFuncSetAttribute(attention_tc_kernel<D, DKB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        B200SD_CUDA(cudaFuncSetAttribute(attention_tc_kernel<D, DKB>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         configured = true;
     }
     B200SD_CUDA(b200sd_launch(attention_tc_kernel<D, DKB>, dim3(Sq / kQ, heads, batch), dim3(kThreads), smem, s, p));
