@@ -42,7 +42,7 @@ static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
 // number of SMs of the current device (cached)
 int b200sd_num_sms();
-// programmatic dependent launch (PDL) between consecutive kernels of a stream (B200SD_PDL=0 disables)
+// programmatic dependent launch (PDL) between consecutive kernels of a stream (opt-in: B200SD_PDL=1)
 bool b200sd_pdl_enabled();
 
 // Encode a tiled TMA descriptor (driver entry point fetched through the runtime; no -lcuda needed).
