@@ -144,6 +144,47 @@ size_t b200sd_gemm_workspace_bytes(void);
 int b200sd_geglu_tile(int N); /* tile width used to interleave GEGLU weights for a given N (= 8C) */
 int b200sd_gemm(const b200sd_gemm_args* args, b200sd_stream_t stream);
 
+/* ---- backward GEMMs (autograd.backward through the UNet, finetune_sd.py:494) ----
+ * Same tcgen05 pipeline as b200sd_gemm; the operands that the forward read K-major are read MN-major
+ * here (UMMA "transpose" descriptors over 64-column SWIZZLE_128B TMA boxes), so neither a transposed
+ * weight copy nor a transposed activation copy exists.
+ *
+ * Data gradient of out = X W^T (conv_taps == 1) or of the 3x3 pad-1 conv (conv_taps == 9):
+ *   dX[M, Cin] = sum_tap dY[p - d(tap), :] * W[:, tap, :]   (+ residual)
+ * dy: bf16 [M, ldy] (dense NHWC for conv); w: the FORWARD weight, bf16 [Cout][taps][Cin];
+ * out: [M, ldc] bf16 / fp32; residual (optional, [M, ldr]) is added -- pass residual == out to accumulate.
+ * Cout must be a multiple of 64, Cin a multiple of 8.  Replaces cuBLAS / cuDNN dgrad. */
+typedef struct b200sd_dgrad_args {
+    const void* dy;
+    const void* w;
+    const void* residual;
+    void* out;
+    int M, Cout, Cin;
+    int conv_taps;        /* 1 or 9 */
+    int batch, H, W;      /* conv geometry */
+    int ldy, ldc, ldr;    /* 0 = dense */
+    int out_dtype, residual_dtype;
+    int block_n;          /* 0 = auto (64 / 128 / 192 / 256) */
+} b200sd_dgrad_args;
+int b200sd_gemm_dgrad(const b200sd_dgrad_args* args, b200sd_stream_t stream);
+
+/* Weight gradient, ACCUMULATED into fp32 (red.global.add: split-K partials and gradient accumulation
+ * share the mechanism, so dw must hold the running gradient -- zero it at the start of a step):
+ *   dW[Cout][tap][Cin] += sum_p dY[p, co] * X[p + d(tap), ci]
+ * dy: bf16 [rows, ldy]; x: bf16 [rows, ldx] (dense NHWC [batch,H,W,Cin] for conv, W | 64);
+ * dw: fp32 [Cout][lddw] (lddw = taps * Cin when 0).  Replaces cuBLAS / cuDNN wgrad. */
+typedef struct b200sd_wgrad_args {
+    const void* dy;
+    const void* x;
+    float* dw;
+    int rows, Cout, Cin;
+    int conv_taps;
+    int batch, H, W;
+    int ldy, ldx, lddw;
+    int block_n, split_k; /* 0 = auto */
+} b200sd_wgrad_args;
+int b200sd_gemm_wgrad(const b200sd_wgrad_args* args, b200sd_stream_t stream);
+
 /* Direct 3x3 convs at the ends of the UNet (degenerate GEMM shapes, CUDA cores):
  * conv_in : NCHW fp32 (batch, Cin=4, H, W) -> NHWC bf16 (batch*H*W, Cout); w fp32 packed [Cout][ky][kx][Cin].
  * conv_out: NHWC bf16 (batch*H*W, Cin) -> NCHW fp32 (batch, Cout<=4, H, W); w fp32 packed [Cout][ky][kx][Cin]. */

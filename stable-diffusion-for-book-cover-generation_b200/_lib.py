@@ -27,6 +27,24 @@ class GemmArgs(C.Structure):
     ]
 
 
+class DgradArgs(C.Structure):
+    _fields_ = [
+        ("dy", C.c_void_p), ("w", C.c_void_p), ("residual", C.c_void_p), ("out", C.c_void_p),
+        ("M", C.c_int), ("Cout", C.c_int), ("Cin", C.c_int), ("conv_taps", C.c_int),
+        ("batch", C.c_int), ("H", C.c_int), ("W", C.c_int), ("ldy", C.c_int), ("ldc", C.c_int), ("ldr", C.c_int),
+        ("out_dtype", C.c_int), ("residual_dtype", C.c_int), ("block_n", C.c_int),
+    ]
+
+
+class WgradArgs(C.Structure):
+    _fields_ = [
+        ("dy", C.c_void_p), ("x", C.c_void_p), ("dw", C.c_void_p),
+        ("rows", C.c_int), ("Cout", C.c_int), ("Cin", C.c_int), ("conv_taps", C.c_int),
+        ("batch", C.c_int), ("H", C.c_int), ("W", C.c_int), ("ldy", C.c_int), ("ldx", C.c_int), ("lddw", C.c_int),
+        ("block_n", C.c_int), ("split_k", C.c_int),
+    ]
+
+
 _vp, _i, _i64, _f, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_size_t
 
 # name -> (restype, argtypes); must list EVERY symbol include/b200sd.h declares (tests check this)
@@ -46,6 +64,8 @@ SIGNATURES = {
     "b200sd_gemm_workspace_bytes": (_sz, []),
     "b200sd_geglu_tile": (_i, [_i]),
     "b200sd_gemm": (_i, [C.POINTER(GemmArgs), _vp]),
+    "b200sd_gemm_dgrad": (_i, [C.POINTER(DgradArgs), _vp]),
+    "b200sd_gemm_wgrad": (_i, [C.POINTER(WgradArgs), _vp]),
     "b200sd_conv_in": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "b200sd_conv_out": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "b200sd_groupnorm_silu": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _i, _i, _vp]),

@@ -71,6 +71,14 @@ struct KParams {
     int out_f32;
     int res_f32;
     uint32_t tmem_cols;
+    // ---- backward (dgrad / wgrad) operand modes ----
+    int a_mn;            // 1: A is MN-major (wgrad: A = dY [rows = K][M channels]), two 64-channel boxes per stage
+    int b_mode;          // 0 K-major [N][K]; 1 MN-major weights [K][N] (dgrad; 3-D (ci, tap, co) for conv);
+                         // 2 MN-major activations [rows = K][N] (wgrad); 3 same, 3x3-shifted 4-D boxes (conv wgrad)
+    int conv_sign;       // +1 forward taps, -1 dgrad (A sampled at p - d(tap))
+    int n_valid;         // output columns that exist (tiles may overhang when block_n does not divide N)
+    int tiles_per_tap;   // conv wgrad: n-tiles per tap (output column = tap * n_valid + c)
+    int atomic_out;      // fp32 red.add into `out` (wgrad: split-K partials and gradient accumulation)
     unsigned long long* trace;  // optional [ctas][8] globaltimer stamps (debug)
 };
 
@@ -89,6 +97,10 @@ __device__ __forceinline__ float4 ld_dsmem_v4(uint32_t local_smem_addr, uint32_t
     float4 v;
     asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(raddr) : "memory");
     return v;
+}
+
+__device__ __forceinline__ void red_add_v4(float* dst, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
 __global__ void __launch_bounds__(kNumThreads, 1) gemm_tcgen05_kernel(const __grid_constant__ KParams p) {
@@ -111,7 +123,11 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tcgen05_kernel(const __gr
     const int split = blockIdx.z;
     const int kb_begin = split * p.kb_per_split;
     const int kb_end = min(kb_begin + p.kb_per_split, p.num_k_blocks);
-    const int n0 = n_tile * p.block_n;
+    // conv wgrad: the N axis is (tap, input channel); a tile never straddles taps
+    const int w_tap = p.b_mode == 3 ? n_tile / p.tiles_per_tap : 0;
+    const int n0 = (p.b_mode == 3 ? n_tile - w_tap * p.tiles_per_tap : n_tile) * p.block_n;   // column within the (per-tap) N axis
+    const int col_base = w_tap * p.n_valid + n0;                                             // output column of tile column 0
+    const int col_valid = min(p.block_n, p.n_valid - n0);
     const int m0 = m_tile * p.rows_valid;
 
     ptx::pdl_trigger();
@@ -162,43 +178,75 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tcgen05_kernel(const __gr
                 if (p.tile_n > 1) { img = m_tile * p.tile_n; y0 = 0; }
                 else { img = m_tile / p.tiles_y; y0 = (m_tile % p.tiles_y) * p.tile_h; }
             }
+            const int nboxb = p.block_n >> 6;   // 64-column boxes of an MN-major B tile
             for (int kb = kb_begin; kb < kb_end; ++kb) {
                 ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
                 ptx::mbar_expect_tx(&full_bar[stage], (uint32_t)(p.a_bytes + b_bytes));
                 uint8_t* dst_a = smem_a + (size_t)stage * kABytes;
                 uint8_t* dst_b = smem_b + (size_t)stage * b_bytes;
-                if (!p.conv) {
+                // ---- A ----
+                if (p.a_mn) {
+                    ptx::tma_load_2d(dst_a, &p.tmA0, &full_bar[stage], m0, kb * BLOCK_K);
+                    ptx::tma_load_2d(dst_a + kABytes / 2, &p.tmA0, &full_bar[stage], m0 + 64, kb * BLOCK_K);
+                } else if (!p.conv) {
                     if (kb < p.cblocks0) ptx::tma_load_2d(dst_a, &p.tmA0, &full_bar[stage], kb * BLOCK_K, m0);
                     else ptx::tma_load_2d(dst_a, &p.tmA1, &full_bar[stage], (kb - p.cblocks0) * BLOCK_K, m0);
                 } else {
                     const int tap = kb / p.cblocks;
                     const int cb = kb - tap * p.cblocks;
-                    const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+                    const int dy = (tap / 3 - 1) * p.conv_sign, dx = (tap % 3 - 1) * p.conv_sign;
                     if (cb < p.cblocks0)
                         ptx::tma_load_4d(dst_a, &p.tmA0, &full_bar[stage], cb * BLOCK_K, dx, y0 + dy, img);
                     else
                         ptx::tma_load_4d(dst_a, &p.tmA1, &full_bar[stage], (cb - p.cblocks0) * BLOCK_K, dx, y0 + dy, img);
                 }
-                ptx::tma_load_2d(dst_b, &p.tmB, &full_bar[stage], kb * BLOCK_K, n0);
+                // ---- B ----
+                if (p.b_mode == 0) {
+                    ptx::tma_load_2d(dst_b, &p.tmB, &full_bar[stage], kb * BLOCK_K, n0);
+                } else if (p.b_mode == 1) {
+                    if (!p.conv) {
+                        for (int j = 0; j < nboxb; ++j)
+                            ptx::tma_load_2d(dst_b + j * 8192, &p.tmB, &full_bar[stage], n0 + j * 64, kb * BLOCK_K);
+                    } else {
+                        const int tap = kb / p.cblocks;
+                        const int cb = kb - tap * p.cblocks;
+                        for (int j = 0; j < nboxb; ++j)
+                            ptx::tma_load_3d(dst_b + j * 8192, &p.tmB, &full_bar[stage], n0 + j * 64, tap, cb * BLOCK_K);
+                    }
+                } else if (p.b_mode == 2) {
+                    for (int j = 0; j < nboxb; ++j)
+                        ptx::tma_load_2d(dst_b + j * 8192, &p.tmB, &full_bar[stage], n0 + j * 64, kb * BLOCK_K);
+                } else {
+                    // conv wgrad: k-block kb = 64 pixels = box (64 ch, W, tile_h, tile_n) shifted by the tap
+                    int bimg, by0;
+                    if (p.tile_n > 1) { bimg = kb * p.tile_n; by0 = 0; }
+                    else { bimg = kb / p.tiles_y; by0 = (kb - bimg * p.tiles_y) * p.tile_h; }
+                    const int dy = w_tap / 3 - 1, dx = w_tap % 3 - 1;
+                    for (int j = 0; j < nboxb; ++j)
+                        ptx::tma_load_4d(dst_b + j * 8192, &p.tmB, &full_bar[stage], n0 + j * 64, dx, by0 + dy, bimg);
+                }
                 if (++stage == p.stages) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
         // ================= MMA issuer (one elected thread) =================
         if (ptx::elect_one()) {
-            const uint32_t idesc = ptx::umma_idesc_bf16(BLOCK_M, (uint32_t)p.block_n);
+            const uint32_t b_mn = p.b_mode != 0;
+            const uint32_t idesc = ptx::umma_idesc_bf16(BLOCK_M, (uint32_t)p.block_n) | ((uint32_t)p.a_mn << 15) | (b_mn << 16);
+            // K-major: +32 B per UMMA_K inside the swizzle atom; MN-major: 16 k-rows = two 1024-byte atoms further
+            const uint32_t a_step = p.a_mn ? (2048 >> 4) : 2, b_step = b_mn ? (2048 >> 4) : 2;
             int stage = 0;
             uint32_t phase = 0;
             for (int kb = kb_begin; kb < kb_end; ++kb) {
                 ptx::mbar_wait(&full_bar[stage], phase);
                 ptx::tc_fence_after();
                 if (kb == kb_begin) TRACE(2);
-                const uint64_t da = ptx::umma_desc_k_sw128(ptx::smem_u32(smem_a + (size_t)stage * kABytes));
-                const uint64_t db = ptx::umma_desc_k_sw128(ptx::smem_u32(smem_b + (size_t)stage * b_bytes));
+                const uint32_t sa = ptx::smem_u32(smem_a + (size_t)stage * kABytes), sb = ptx::smem_u32(smem_b + (size_t)stage * b_bytes);
+                const uint64_t da = p.a_mn ? ptx::umma_desc_mn_sw128(sa, 8192) : ptx::umma_desc_k_sw128(sa);
+                const uint64_t db = b_mn ? ptx::umma_desc_mn_sw128(sb, 8192) : ptx::umma_desc_k_sw128(sb);
 #pragma unroll
                 for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-                    // advance 32 B (= 16 bf16) along K inside the swizzle atom: +2 in 16-byte units
-                    ptx::umma_bf16_ss(tmem_base, da + 2 * k, db + 2 * k, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
+                    ptx::umma_bf16_ss(tmem_base, da + a_step * k, db + b_step * k, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
                 }
                 ptx::umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
                 if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -214,7 +262,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tcgen05_kernel(const __gr
         const int r_in_tile = q * 32 + lane;
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
         for (int c = epi_tid; c < p.block_n; c += 128) {
-            s_bias[c] = p.bias ? __ldg(p.bias + n0 + c) : 0.f;
+            s_bias[c] = (p.bias && c < col_valid) ? __ldg(p.bias + n0 + c) : 0.f;
             if (rb_smem) {
                 s_rb[c] = __ldg(p.rowbias + (size_t)img0 * p.ldrb + n0 + c);
                 s_rb[256 + c] = __ldg(p.rowbias + (size_t)img1 * p.ldrb + n0 + c);
@@ -281,6 +329,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tcgen05_kernel(const __gr
                 const int id = ok[u] ? idx : 0;
                 rl[u] = row_begin + (int)(((uint32_t)id * ginv) >> 20);
                 c8[u] = id - (rl[u] - row_begin) * groups;
+                ok[u] = ok[u] && (c8[u] * 8 < col_valid);
                 const uint32_t off = (uint32_t)(rl[u] * pitch_f + c8[u] * 8) * 4u;
                 if (p.split_k > 1) {
 #pragma unroll
@@ -301,8 +350,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tcgen05_kernel(const __gr
                     const float4 g0 = *reinterpret_cast<const float4*>(sp), g1 = *reinterpret_cast<const float4*>(sp + 4);
                     r[u][0] = g0.x; r[u][1] = g0.y; r[u][2] = g0.z; r[u][3] = g0.w;
                     r[u][4] = g1.x; r[u][5] = g1.y; r[u][6] = g1.z; r[u][7] = g1.w;
-                } else if (p.residual) {
-                    const size_t ro = (size_t)(m0 + rl[u]) * p.ldr + n0 + c8[u] * 8;
+                } else if (p.residual && ok[u]) {
+                    const size_t ro = (size_t)(m0 + rl[u]) * p.ldr + col_base + c8[u] * 8;
                     if (p.res_f32) ld8<B200SD_F32>(p.residual, ro, r[u]);
                     else ld8<B200SD_BF16>(p.residual, ro, r[u]);
                 } else {
@@ -337,8 +386,12 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tcgen05_kernel(const __gr
                             for (int i = 0; i < 8; ++i) o[i] += t[i];
                         }
                     }
-                    if (p.out_f32) st8<B200SD_F32>(p.out, (size_t)row * p.ldc + n0 + cb, o);
-                    else st8<B200SD_BF16>(p.out, (size_t)row * p.ldc + n0 + cb, o);
+                    if (p.atomic_out) {
+                        float* dst = static_cast<float*>(p.out) + (size_t)row * p.ldc + col_base + cb;
+                        red_add_v4(dst, o[0], o[1], o[2], o[3]);
+                        red_add_v4(dst + 4, o[4], o[5], o[6], o[7]);
+                    } else if (p.out_f32) st8<B200SD_F32>(p.out, (size_t)row * p.ldc + col_base + cb, o);
+                    else st8<B200SD_BF16>(p.out, (size_t)row * p.ldc + col_base + cb, o);
                 }
             }
         }
@@ -380,6 +433,97 @@ int pick_block_n(int N, int m_tiles, int epilogue) {
             if (N % bn == 0 && (long)m_tiles * (N / bn) <= sms) { best = bn; break; }
     }
     return best;
+}
+
+
+// Shared tail of every entry point: pipeline depth, smem budget, launch.
+// Grids that fit in one wave keep every k-block of a short K loop in flight (deep ring, 1 CTA/SM);
+// larger grids stay <= ~110 KB so two CTAs share an SM and overlap epilogue with main loop.
+int launch_gemm(KParams& p, int m_tiles, int n_tiles, int grid_z, bool cluster, b200sd_stream_t stream) {
+    const int sms = b200sd_num_sms();
+    const int bn = p.block_n;
+    const int stage_bytes = kABytes + bn * BLOCK_K * 2;
+    const long total_ctas = (long)m_tiles * n_tiles * grid_z;
+    int stages;
+    if (total_ctas <= sms || bn > 160) stages = (200 * 1024) / stage_bytes;
+    else stages = (108 * 1024) / stage_bytes;
+    if (stages > kMaxStages) stages = kMaxStages;
+    if (stages > p.kb_per_split && total_ctas <= sms) stages = p.kb_per_split;
+    const int min_stages = ceil_div(BLOCK_M * (bn + 4) * (int)sizeof(float), stage_bytes);  // epilogue staging tile
+    if (stages < min_stages) stages = min_stages;
+    if (stages < 2) stages = 2;
+    p.stages = stages;
+    B200SD_REQUIRE((size_t)stages * stage_bytes >= (size_t)BLOCK_M * (bn + 4) * sizeof(float), "gemm: smem ring smaller than the epilogue staging tile");
+    const size_t smem_bytes = (size_t)stages * stage_bytes + 1024 /*align slack*/ + 256 /*barriers*/ + 3072 /*bias tiles*/;
+    B200SD_REQUIRE(smem_bytes <= 227 * 1024, "gemm: smem budget exceeded (%zu B)", smem_bytes);
+
+    static bool configured = false;
+    if (!configured) {
+        B200SD_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
+        configured = true;
+    }
+    p.trace = g_gemm_trace;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(m_tiles, n_tiles, grid_z);
+    cfg.blockDim = dim3(kNumThreads);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = static_cast<cudaStream_t>(stream);
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (cluster && grid_z > 1) {
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = 1;
+        attr[na].val.clusterDim.y = 1;
+        attr[na].val.clusterDim.z = grid_z;
+        ++na;
+    }
+    if (b200sd_pdl_enabled()) {
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    cfg.attrs = attr;
+    cfg.numAttrs = na;
+    B200SD_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel, p));
+    g_b200sd_launches.fetch_add(1, std::memory_order_relaxed);
+    B200SD_LAUNCH_CHECK();
+    return B200SD_OK;
+}
+
+// tile width for MN-major B operands (64-column TMA boxes): least padded columns, then the widest
+int pick_block_n_mn(int N, int m_tiles) {
+    int best = 64, best_pad = ceil_div(N, 64) * 64;
+    for (int bn = 128; bn <= 256; bn += 64) {
+        const int pad = ceil_div(N, bn) * bn;
+        if (pad <= best_pad) { best = bn; best_pad = pad; }
+    }
+    // small grids: narrower tiles put more CTAs in flight (64 always has the least padding)
+    if ((long)m_tiles * ceil_div(N, best) * 2 <= b200sd_num_sms()) best = 64;
+    return best;
+}
+
+// conv geometry shared by forward / dgrad: M tile = (tile_w x tile_h x tile_n) pixels <= 128
+int conv_m_tiling(KParams& p, int NB, int H, int W, int M, int* m_tiles) {
+    B200SD_REQUIRE(NB > 0 && H > 0 && W > 0 && M == NB * H * W, "gemm(conv): M=%d != batch*H*W", M);
+    B200SD_REQUIRE(W <= BLOCK_M, "gemm(conv): W=%d > 128 unsupported", W);
+    const int max_h = BLOCK_M / W;
+    if (H <= max_h) {
+        p.tile_h = H;
+        p.tile_n = max_h / H;
+        if (p.tile_n < 1) p.tile_n = 1;
+        if (p.tile_n > NB) p.tile_n = NB;
+    } else {
+        p.tile_n = 1;
+        p.tile_h = 1;
+        for (int h = max_h; h >= 1; --h)
+            if (H % h == 0) { p.tile_h = h; break; }
+    }
+    p.tile_w = W;
+    p.tiles_y = H / p.tile_h;
+    p.rows_valid = p.tile_w * p.tile_h * p.tile_n;
+    p.a_bytes = p.rows_valid * BLOCK_K * 2;
+    *m_tiles = (p.tile_n > 1) ? ceil_div(NB, p.tile_n) : NB * p.tiles_y;
+    return B200SD_OK;
 }
 
 }  // namespace
@@ -429,6 +573,9 @@ extern "C" int b200sd_gemm(const b200sd_gemm_args* a, b200sd_stream_t stream) {
     p.rows_per_image = a->rows_per_image > 0 ? a->rows_per_image : 1;
     p.epilogue = a->epilogue;
     p.out_f32 = a->out_dtype == B200SD_F32;
+    p.conv_sign = 1;
+    p.n_valid = a->N;
+    p.tiles_per_tap = 1;
 
     // ---- M tiling ----
     int m_tiles;
@@ -439,26 +586,8 @@ extern "C" int b200sd_gemm(const b200sd_gemm_args* a, b200sd_stream_t stream) {
         p.tiles_y = 1;
         m_tiles = ceil_div(a->M, BLOCK_M);
     } else {
-        const int H = a->H, W = a->W, NB = a->batch;
-        B200SD_REQUIRE(NB > 0 && H > 0 && W > 0 && a->M == NB * H * W, "gemm(conv): M=%d != batch*H*W", a->M);
-        B200SD_REQUIRE(W <= BLOCK_M, "gemm(conv): W=%d > 128 unsupported", W);
-        const int max_h = BLOCK_M / W;
-        if (H <= max_h) {
-            p.tile_h = H;
-            p.tile_n = max_h / H;
-            if (p.tile_n < 1) p.tile_n = 1;
-            if (p.tile_n > NB) p.tile_n = NB;
-        } else {
-            p.tile_n = 1;
-            p.tile_h = 1;
-            for (int h = max_h; h >= 1; --h)
-                if (H % h == 0) { p.tile_h = h; break; }
-        }
-        p.tile_w = W;
-        p.tiles_y = H / p.tile_h;
-        p.rows_valid = p.tile_w * p.tile_h * p.tile_n;
-        p.a_bytes = p.rows_valid * BLOCK_K * 2;
-        m_tiles = (p.tile_n > 1) ? ceil_div(NB, p.tile_n) : NB * p.tiles_y;
+        const int rc = conv_m_tiling(p, a->batch, a->H, a->W, a->M, &m_tiles);
+        if (rc) return rc;
     }
 
     // ---- N tiling ----
@@ -485,24 +614,6 @@ extern "C" int b200sd_gemm(const b200sd_gemm_args* a, b200sd_stream_t stream) {
     p.kb_per_split = ceil_div(p.num_k_blocks, split);
     B200SD_REQUIRE((split - 1) * p.kb_per_split < p.num_k_blocks, "gemm: split_k=%d leaves an empty split for K=%d", split, a->K);
     p.split_k = split;
-
-    // ---- pipeline depth ----
-    // Grids that fit in one wave keep every k-block of a short K loop in flight (deep ring, 1 CTA/SM);
-    // larger grids stay <= ~110 KB so two CTAs share an SM and overlap epilogue with main loop.
-    const int stage_bytes = kABytes + bn * BLOCK_K * 2;
-    const long total_ctas = (long)m_tiles * n_tiles * split;
-    int stages;
-    if (total_ctas <= sms || bn > 160) stages = (200 * 1024) / stage_bytes;
-    else stages = (108 * 1024) / stage_bytes;
-    if (stages > kMaxStages) stages = kMaxStages;
-    if (stages > p.kb_per_split && total_ctas <= sms) stages = p.kb_per_split;
-    const int min_stages = ceil_div(BLOCK_M * (bn + 4) * (int)sizeof(float), stage_bytes);  // epilogue staging tile
-    if (stages < min_stages) stages = min_stages;
-    if (stages < 2) stages = 2;
-    p.stages = stages;
-    B200SD_REQUIRE((size_t)stages * stage_bytes >= (size_t)BLOCK_M * (bn + 4) * sizeof(float), "gemm: smem ring smaller than the epilogue staging tile");
-    const size_t smem_bytes = (size_t)stages * stage_bytes + 1024 /*align slack*/ + 256 /*barriers*/ + 3072 /*bias tiles*/;
-    B200SD_REQUIRE(smem_bytes <= 227 * 1024, "gemm: smem budget exceeded (%zu B)", smem_bytes);
 
     // ---- tensor maps ----
     if (!p.conv) {
@@ -538,37 +649,163 @@ extern "C" int b200sd_gemm(const b200sd_gemm_args* a, b200sd_stream_t stream) {
         if (rc) return rc;
     }
 
-    static size_t configured_smem = 0;
-    if (smem_bytes > configured_smem) {
-        B200SD_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
-        configured_smem = 227 * 1024;
+    return launch_gemm(p, m_tiles, n_tiles, split, /*cluster=*/true, stream);
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward entry points (same kernel, MN-major operand modes)
+// ------------------------------------------------------------------------------------------------
+extern "C" int b200sd_gemm_dgrad(const b200sd_dgrad_args* a, b200sd_stream_t stream) {
+    B200SD_REQUIRE(a != nullptr && a->dy && a->w && a->out, "dgrad: null pointer");
+    B200SD_REQUIRE(a->conv_taps == 1 || a->conv_taps == 9, "dgrad: conv_taps must be 1 or 9");
+    B200SD_REQUIRE(a->M > 0 && a->Cout > 0 && a->Cout % BLOCK_K == 0, "dgrad: Cout=%d must be a positive multiple of 64", a->Cout);
+    B200SD_REQUIRE(a->Cin > 0 && a->Cin % 8 == 0, "dgrad: Cin=%d must be a multiple of 8", a->Cin);
+    B200SD_REQUIRE(a->out_dtype == B200SD_BF16 || a->out_dtype == B200SD_F32, "dgrad: bad out dtype");
+    const int ldy = a->ldy > 0 ? a->ldy : a->Cout;
+    const int ldc = a->ldc > 0 ? a->ldc : a->Cin;
+    const int ldr = a->ldr > 0 ? a->ldr : a->Cin;
+    B200SD_REQUIRE(ldc % 8 == 0 && ldr % 8 == 0 && ldy % 8 == 0, "dgrad: pitches must be multiples of 8");
+    B200SD_REQUIRE(((reinterpret_cast<uintptr_t>(a->dy) | reinterpret_cast<uintptr_t>(a->w) | reinterpret_cast<uintptr_t>(a->out) |
+                     reinterpret_cast<uintptr_t>(a->residual)) & 15) == 0, "dgrad: pointers must be 16-byte aligned");
+    KParams p;
+    memset(&p, 0, sizeof(p));
+    p.M = a->M;
+    p.N = a->Cin;
+    p.n_valid = a->Cin;
+    p.tiles_per_tap = 1;
+    p.conv = a->conv_taps == 9;
+    p.conv_sign = -1;
+    p.b_mode = 1;
+    p.cblocks0 = p.cblocks = a->Cout / BLOCK_K;
+    p.num_k_blocks = a->conv_taps * p.cblocks;
+    p.residual = a->residual;
+    p.res_f32 = a->residual_dtype == B200SD_F32;
+    p.out = a->out;
+    p.ldc = ldc;
+    p.ldr = ldr;
+    p.ldrb = a->Cin;
+    p.rows_per_image = 1;
+    p.epilogue = B200SD_EPI_LINEAR;
+    p.out_f32 = a->out_dtype == B200SD_F32;
+    int m_tiles;
+    if (!p.conv) {
+        p.rows_valid = BLOCK_M;
+        p.a_bytes = kABytes;
+        p.tile_w = p.tile_h = p.tile_n = p.tiles_y = 1;
+        m_tiles = ceil_div(a->M, BLOCK_M);
+    } else {
+        B200SD_REQUIRE(ldy == a->Cout, "dgrad(conv): dy must be dense NHWC");
+        const int rc = conv_m_tiling(p, a->batch, a->H, a->W, a->M, &m_tiles);
+        if (rc) return rc;
     }
-    p.trace = g_gemm_trace;
+    const int bn = a->block_n > 0 ? a->block_n : pick_block_n_mn(a->Cin, m_tiles);
+    B200SD_REQUIRE(bn % 64 == 0 && bn >= 64 && bn <= 256, "dgrad: block_n %d must be 64, 128, 192 or 256", bn);
+    p.block_n = bn;
+    const int n_tiles = ceil_div(a->Cin, bn);
+    p.tmem_cols = pow2_cols(bn);
+    p.split_k = 1;
+    p.kb_per_split = p.num_k_blocks;
+    int rc;
+    if (!p.conv) {
+        const uint64_t dimsA[2] = {(uint64_t)a->Cout, (uint64_t)a->M};
+        const uint64_t strA[2] = {0, (uint64_t)ldy * 2};
+        const uint32_t boxA[2] = {BLOCK_K, BLOCK_M};
+        if ((rc = b200sd_make_tmap(&p.tmA0, a->dy, 2, dimsA, strA, boxA, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+        const uint64_t dimsB[2] = {(uint64_t)a->Cin, (uint64_t)a->Cout};
+        const uint64_t strB[2] = {0, (uint64_t)a->Cin * 2};
+        const uint32_t boxB[2] = {64, BLOCK_K};
+        if ((rc = b200sd_make_tmap(&p.tmB, a->w, 2, dimsB, strB, boxB, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+    } else {
+        const uint32_t boxA[4] = {BLOCK_K, (uint32_t)p.tile_w, (uint32_t)p.tile_h, (uint32_t)p.tile_n};
+        const uint64_t dims0[4] = {(uint64_t)a->Cout, (uint64_t)a->W, (uint64_t)a->H, (uint64_t)a->batch};
+        const uint64_t str0[4] = {0, (uint64_t)a->Cout * 2, (uint64_t)a->W * a->Cout * 2, (uint64_t)a->H * a->W * a->Cout * 2};
+        if ((rc = b200sd_make_tmap(&p.tmA0, a->dy, 4, dims0, str0, boxA, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+        const uint64_t dimsB[3] = {(uint64_t)a->Cin, 9, (uint64_t)a->Cout};
+        const uint64_t strB[3] = {0, (uint64_t)a->Cin * 2, (uint64_t)9 * a->Cin * 2};
+        const uint32_t boxB[3] = {64, 1, BLOCK_K};
+        if ((rc = b200sd_make_tmap(&p.tmB, a->w, 3, dimsB, strB, boxB, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+    }
+    return launch_gemm(p, m_tiles, n_tiles, 1, false, stream);
+}
+
+extern "C" int b200sd_gemm_wgrad(const b200sd_wgrad_args* a, b200sd_stream_t stream) {
+    B200SD_REQUIRE(a != nullptr && a->dy && a->x && a->dw, "wgrad: null pointer");
+    B200SD_REQUIRE(a->conv_taps == 1 || a->conv_taps == 9, "wgrad: conv_taps must be 1 or 9");
+    B200SD_REQUIRE(a->rows > 0 && a->Cout > 0 && a->Cin > 0 && a->Cout % 8 == 0 && a->Cin % 8 == 0,
+                   "wgrad: rows=%d Cout=%d Cin=%d (channel counts must be multiples of 8)", a->rows, a->Cout, a->Cin);
+    const int ldy = a->ldy > 0 ? a->ldy : a->Cout;
+    const int ldx = a->ldx > 0 ? a->ldx : a->Cin;
+    const int lddw = a->lddw > 0 ? a->lddw : a->conv_taps * a->Cin;
+    B200SD_REQUIRE(ldy % 8 == 0 && ldx % 8 == 0 && lddw % 4 == 0, "wgrad: pitches must be multiples of 8 (dw: 4)");
+    B200SD_REQUIRE(((reinterpret_cast<uintptr_t>(a->dy) | reinterpret_cast<uintptr_t>(a->x) | reinterpret_cast<uintptr_t>(a->dw)) & 15) == 0,
+                   "wgrad: pointers must be 16-byte aligned");
+    KParams p;
+    memset(&p, 0, sizeof(p));
+    p.M = a->Cout;
+    p.N = a->conv_taps * a->Cin;
+    p.n_valid = a->Cin;
+    p.a_mn = 1;
+    p.b_mode = a->conv_taps == 9 ? 3 : 2;
+    p.conv = 0;
+    p.conv_sign = 1;
+    p.rows_valid = BLOCK_M;
+    p.a_bytes = kABytes;
+    p.out = a->dw;
+    p.ldc = lddw;
+    p.ldrb = p.N;
+    p.rows_per_image = 1;
+    p.epilogue = B200SD_EPI_LINEAR;
+    p.out_f32 = 1;
+    p.atomic_out = 1;
+    p.split_k = 1;
+    const int m_tiles = ceil_div(a->Cout, BLOCK_M);
+    int rc;
+    if (a->conv_taps == 9) {
+        const int H = a->H, W = a->W, NB = a->batch;
+        B200SD_REQUIRE(NB > 0 && H > 0 && W > 0 && a->rows == NB * H * W, "wgrad(conv): rows=%d != batch*H*W", a->rows);
+        B200SD_REQUIRE(W <= 64 && 64 % W == 0, "wgrad(conv): W=%d must divide 64", W);
+        B200SD_REQUIRE(ldy == a->Cout && ldx == a->Cin, "wgrad(conv): dy / x must be dense NHWC");
+        p.tile_w = W;
+        p.tile_h = (64 / W < H) ? 64 / W : H;
+        B200SD_REQUIRE(H % p.tile_h == 0, "wgrad(conv): H=%d not a multiple of the %d-row pixel block", H, p.tile_h);
+        p.tile_n = 64 / (W * p.tile_h);
+        p.tiles_y = H / p.tile_h;
+        p.num_k_blocks = p.tile_n > 1 ? ceil_div(NB, p.tile_n) : NB * p.tiles_y;
+        const uint32_t boxB[4] = {64, (uint32_t)p.tile_w, (uint32_t)p.tile_h, (uint32_t)p.tile_n};
+        const uint64_t dims[4] = {(uint64_t)a->Cin, (uint64_t)W, (uint64_t)H, (uint64_t)NB};
+        const uint64_t str[4] = {0, (uint64_t)a->Cin * 2, (uint64_t)W * a->Cin * 2, (uint64_t)H * W * a->Cin * 2};
+        if ((rc = b200sd_make_tmap(&p.tmB, a->x, 4, dims, str, boxB, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+    } else {
+        p.tile_w = p.tile_h = p.tile_n = p.tiles_y = 1;
+        p.num_k_blocks = ceil_div(a->rows, BLOCK_K);
+        const uint64_t dimsB[2] = {(uint64_t)a->Cin, (uint64_t)a->rows};
+        const uint64_t strB[2] = {0, (uint64_t)ldx * 2};
+        const uint32_t boxB[2] = {64, BLOCK_K};
+        if ((rc = b200sd_make_tmap(&p.tmB, a->x, 2, dimsB, strB, boxB, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+    }
     {
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(m_tiles, n_tiles, split);
-        cfg.blockDim = dim3(kNumThreads);
-        cfg.dynamicSmemBytes = smem_bytes;
-        cfg.stream = static_cast<cudaStream_t>(stream);
-        cudaLaunchAttribute attr[2];
-        int na = 0;
-        if (split > 1) {
-            attr[na].id = cudaLaunchAttributeClusterDimension;
-            attr[na].val.clusterDim.x = 1;
-            attr[na].val.clusterDim.y = 1;
-            attr[na].val.clusterDim.z = split;
-            ++na;
-        }
-        if (b200sd_pdl_enabled()) {
-            attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-            attr[na].val.programmaticStreamSerializationAllowed = 1;
-            ++na;
-        }
-        cfg.attrs = attr;
-        cfg.numAttrs = na;
-        B200SD_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel, p));
+        const uint64_t dimsA[2] = {(uint64_t)a->Cout, (uint64_t)a->rows};
+        const uint64_t strA[2] = {0, (uint64_t)ldy * 2};
+        const uint32_t boxA[2] = {64, BLOCK_K};
+        if ((rc = b200sd_make_tmap(&p.tmA0, a->dy, 2, dimsA, strA, boxA, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
     }
-    g_b200sd_launches.fetch_add(1, std::memory_order_relaxed);
-    B200SD_LAUNCH_CHECK();
-    return B200SD_OK;
+    const int bn = a->block_n > 0 ? a->block_n : pick_block_n_mn(a->Cin, m_tiles * a->conv_taps);
+    B200SD_REQUIRE(bn % 64 == 0 && bn >= 64 && bn <= 256, "wgrad: block_n %d must be 64, 128, 192 or 256", bn);
+    p.block_n = bn;
+    p.tiles_per_tap = ceil_div(a->Cin, bn);
+    const int n_tiles = a->conv_taps * p.tiles_per_tap;
+    p.tmem_cols = pow2_cols(bn);
+    // split-K over grid.z (fp32 red.add combines the partials): aim at >= 2 CTAs per SM, >= 8 k-blocks per split
+    int split = a->split_k;
+    if (split <= 0) {
+        const int tiles = m_tiles * n_tiles;
+        split = ceil_div(2 * b200sd_num_sms(), tiles);
+        const int max_split = p.num_k_blocks / 8 > 0 ? p.num_k_blocks / 8 : 1;
+        if (split > max_split) split = max_split;
+        if (split < 1) split = 1;
+    }
+    if (split > p.num_k_blocks) split = p.num_k_blocks;
+    p.kb_per_split = ceil_div(p.num_k_blocks, split);
+    split = ceil_div(p.num_k_blocks, p.kb_per_split);   // no empty splits
+    return launch_gemm(p, m_tiles, n_tiles, split, false, stream);
 }

@@ -7,7 +7,7 @@ import ctypes as C
 
 import torch
 
-from ._lib import GemmArgs, B200SDError, check, lib
+from ._lib import DgradArgs, GemmArgs, WgradArgs, B200SDError, check, lib
 
 F32, BF16 = 0, 1
 EPI_LINEAR, EPI_GEGLU = 0, 1
@@ -207,6 +207,49 @@ def gemm(a0, w, out, *, a1=None, bias=None, rowbias=None, residual=None, conv=No
 
 def gemm_run(args):
     check(lib().b200sd_gemm(C.byref(args), _stream()), "gemm")
+
+
+def gemm_dgrad(dy, w, out, *, residual=None, conv=None, Cin=None, block_n=0, launch=True):
+    """out[M, Cin] = dy[M, Cout] (*) w  (+ residual): data gradient of gemm(); w is the FORWARD weight
+    [Cout][taps*Cin]; conv=(batch, H, W) -> gradient of the 3x3 pad-1 conv."""
+    _chk(dy, w, residual, out)
+    Cout = w.shape[0]
+    taps = 9 if conv is not None else 1
+    if Cin is None:
+        Cin = w.shape[1] // taps
+    a = DgradArgs()
+    a.dy, a.w, a.residual, a.out = _p(dy), _p(w), _p(residual), _p(out)
+    a.M, a.Cout, a.Cin, a.conv_taps = dy.numel() // dy.shape[-1], Cout, Cin, taps
+    if conv is not None:
+        a.batch, a.H, a.W = conv
+    a.ldy, a.ldc = dy.shape[-1], out.shape[-1]
+    a.ldr = residual.shape[-1] if residual is not None else 0
+    a.out_dtype = _dt(out)
+    a.residual_dtype = _dt(residual) if residual is not None else BF16
+    a.block_n = block_n
+    if not launch:
+        return a
+    check(lib().b200sd_gemm_dgrad(C.byref(a), _stream()), "gemm_dgrad")
+    return out
+
+
+def gemm_wgrad(dy, x, dw, *, conv=None, lddw=0, block_n=0, split_k=0, launch=True):
+    """dw[Cout][taps*Cin] += dy[rows, Cout]^T (*) x[rows, Cin]  (fp32, accumulated with red.add)."""
+    _chk(dy, x, dw)
+    if dw.dtype != torch.float32:
+        raise B200SDError("gemm_wgrad: dw must be float32")
+    a = WgradArgs()
+    a.dy, a.x, a.dw = _p(dy), _p(x), _p(dw)
+    a.rows, a.Cout, a.Cin = dy.numel() // dy.shape[-1], dy.shape[-1], x.shape[-1]
+    a.conv_taps = 9 if conv is not None else 1
+    if conv is not None:
+        a.batch, a.H, a.W = conv
+    a.ldy, a.ldx, a.lddw = dy.shape[-1], x.shape[-1], lddw
+    a.block_n, a.split_k = block_n, split_k
+    if not launch:
+        return a
+    check(lib().b200sd_gemm_wgrad(C.byref(a), _stream()), "gemm_wgrad")
+    return dw
 
 
 def geglu_tile(N):
