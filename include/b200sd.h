@@ -220,6 +220,71 @@ int b200sd_attention(const void* q, const void* k, const void* v, void* out, int
                      int d, int ldq, int ldk, int ldv, int ldo, float scale, void* workspace, size_t workspace_bytes,
                      b200sd_stream_t stream);
 
+/* Same as b200sd_attention, additionally writing lse[batch][heads][Sq] (fp32): the log2-domain
+ * log-sum-exp of the scaled scores, log2(sum_j exp(scale q.k_j)), which b200sd_attention_bwd needs.
+ * lse may be NULL. */
+int b200sd_attention_lse(const void* q, const void* k, const void* v, void* out, float* lse, int batch, int heads, int Sq,
+                         int Skv, int d, int ldq, int ldk, int ldv, int ldo, float scale, void* workspace,
+                         size_t workspace_bytes, b200sd_stream_t stream);
+
+/* Backward of the fused attention (autograd through CrossAttention._attention):
+ *   dV = P^T dO;  dS = P o (dO V^T - rowsum(dO o O)) * scale;  dQ = dS K;  dK = dS^T Q
+ * with P recomputed from lse (never materialised).  q/k/v/out/dout and dq/dk/dv are bf16 row-major
+ * buffers addressed like b200sd_attention (head h at columns [h*d, (h+1)*d), own leading dims), so the
+ * gradients can be written straight into the column slices of a fused [M, 3C] / [M, 2C] buffer.
+ * workspace: b200sd_attention_bwd_workspace_bytes (delta). Deterministic (no atomics). */
+size_t b200sd_attention_bwd_workspace_bytes(int batch, int heads, int Sq);
+int b200sd_attention_bwd(const void* q, const void* k, const void* v, const void* out, const void* dout,
+                         const float* lse, void* dq, void* dk, void* dv, int batch, int heads, int Sq, int Skv, int d,
+                         int ldq, int ldk, int ldv, int ldo, int lddo, int lddq, int lddk, int lddv, float scale,
+                         void* workspace, size_t workspace_bytes, b200sd_stream_t stream);
+
+/* ---- non-GEMM kernels of the backward pass ----------------------------------- */
+
+/* Gradient prep: optional bf16 copy of a [rows, N] (pitch ld) gradient (the tensor-core operand of
+ * dgrad / wgrad) and optional column sums ACCUMULATED into colsum (the bias gradient).  With
+ * rows_per_image > 0 the sums are kept per image: colsum[image * ldcs + n] (time-embedding gradient). */
+int b200sd_grad_prep(const void* in, int in_dtype, void* out_bf16, float* colsum, int rows, int N, int ld,
+                     int rows_per_image, int ldcs, b200sd_stream_t stream);
+
+/* Backward of b200sd_groupnorm_silu.  dy: bf16 [rows, C0+C1] gradient of the (activated) output.
+ * out0 [rows, C0] / out1 [rows, C1] (out_dtype) receive dx (+ add_src, an optional fp32 [rows, C0+C1]
+ * addend: the residual path), overwritten or accumulated per the accumulate flags.  dgamma / dbeta
+ * (fp32 [C0+C1]) are ACCUMULATED; pass NULL for both when the parameters are frozen.
+ * workspace: float[b200sd_groupnorm_bwd_workspace_floats(batch)]. */
+int b200sd_groupnorm_bwd_workspace_floats(int batch);
+int b200sd_groupnorm_silu_bwd(const void* x0, const void* x1, int C0, int C1, int in_dtype, const float* gamma,
+                              const float* beta, const void* dy, const float* add_src, void* out0, void* out1,
+                              int out_dtype, int accumulate0, int accumulate1, float* dgamma, float* dbeta,
+                              float* workspace, int batch, int hw, int groups, float eps, int silu,
+                              b200sd_stream_t stream);
+
+/* Backward of b200sd_layernorm: dres[rows, C] (fp32) += dx;  dgamma / dbeta accumulated (or both NULL). */
+int b200sd_layernorm_bwd(const void* x, int in_dtype, const float* gamma, const void* dy, float* dres, float* dgamma,
+                         float* dbeta, int rows, int C, float eps, b200sd_stream_t stream);
+
+/* GEGLU of the training path (pre-activation kept): u bf16 [rows, 2*C_half] = [values | gates];
+ * out[rows, C_half] = values * gelu_erf(gates);  du = d/du of that given dff [rows, C_half]. */
+int b200sd_geglu_fwd(const void* u, void* out, int64_t rows, int C_half, b200sd_stream_t stream);
+int b200sd_geglu_bwd(const void* u, const void* dff, void* du, int64_t rows, int C_half, b200sd_stream_t stream);
+
+/* Transposes of the resamplers: dy bf16 (batch,2H,2W,C) -> dx fp32 (batch,H,W,C) (sum of 2x2 blocks);
+ * dcol bf16 [batch*(H/2)*(W/2)][9*C] -> dx fp32 (batch,H,W,C).  accumulate != 0: dx += . */
+int b200sd_upsample2x_bwd(const void* dy, float* dx, int batch, int H, int W, int C, int accumulate, b200sd_stream_t stream);
+int b200sd_col2im_s2(const void* dcol, float* dx, int batch, int H, int W, int C, int accumulate, b200sd_stream_t stream);
+
+/* Backward of b200sd_conv_out: dx_nhwc (bf16 [batch*H*W, Cin]) = data gradient; when dw != NULL also
+ * dw[Cout][9][Cin] += weight gradient (needs x_nhwc, the forward input) and dbias[Cout] += sum(dout). */
+int b200sd_conv_out_bwd(const float* dout_nchw, const void* x_nhwc, const float* w, void* dx_nhwc, float* dw,
+                        float* dbias, int batch, int Cin, int Cout, int H, int W, b200sd_stream_t stream);
+/* Weight gradient of b200sd_conv_in: dw[Cout][9][Cin] += sum_p dy[p, co] x[b, ci, p + d(tap)]. */
+int b200sd_conv_in_wgrad(const void* dy_nhwc, int dy_dtype, const float* x_nchw, float* dw, int batch, int Cin, int Cout,
+                         int H, int W, b200sd_stream_t stream);
+
+/* out_bf16[i] = act(in[i]) (act = SiLU when silu != 0);  grad[i] *= silu'(pre[i])  (time-embedding MLP backward) */
+int b200sd_cast_act(const float* in, void* out_bf16, int64_t n, int silu, b200sd_stream_t stream);
+int b200sd_silu_bwd_mul(const float* pre, float* grad, int64_t n, b200sd_stream_t stream);
+
 /* nearest x2 upsample NHWC bf16: (batch,H,W,C) -> (batch,2H,2W,C)  (Upsample2D's F.interpolate) */
 int b200sd_upsample2x(const void* x, void* out, int batch, int H, int W, int C, int in_dtype, b200sd_stream_t stream);
 /* im2col for the three stride-2 Downsample2D convs: NHWC (batch,H,W,C) -> [batch*(H/2)*(W/2)][9*C] */

@@ -73,6 +73,22 @@ SIGNATURES = {
     "b200sd_layernorm": (_i, [_vp, _vp, _vp, _vp, _i, _i, _f, _i, _vp]),
     "b200sd_attention_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "b200sd_attention": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _vp, _sz, _vp]),
+    "b200sd_attention_lse": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _vp, _sz, _vp]),
+    "b200sd_attention_bwd_workspace_bytes": (_sz, [_i, _i, _i]),
+    "b200sd_attention_bwd": (_i, [_vp] * 9 + [_i] * 13 + [_f, _vp, _sz, _vp]),
+    "b200sd_grad_prep": (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "b200sd_groupnorm_bwd_workspace_floats": (_i, [_i]),
+    "b200sd_groupnorm_silu_bwd": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _i, _i,
+                                       _i, _f, _i, _vp]),
+    "b200sd_layernorm_bwd": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp]),
+    "b200sd_geglu_fwd": (_i, [_vp, _vp, _i64, _i, _vp]),
+    "b200sd_geglu_bwd": (_i, [_vp, _vp, _vp, _i64, _i, _vp]),
+    "b200sd_upsample2x_bwd": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "b200sd_col2im_s2": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "b200sd_conv_out_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "b200sd_conv_in_wgrad": (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "b200sd_cast_act": (_i, [_vp, _vp, _i64, _i, _vp]),
+    "b200sd_silu_bwd_mul": (_i, [_vp, _vp, _i64, _vp]),
     "b200sd_upsample2x": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "b200sd_im2col_s2": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
 }

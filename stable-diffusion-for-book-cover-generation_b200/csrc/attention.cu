@@ -60,8 +60,8 @@ __device__ __forceinline__ void load_tile(uint8_t* smem, const bf16* g, int ld, 
 template <int DP>
 __global__ void __launch_bounds__(kThreads, (DP <= 80) ? 2 : 1)
     attention_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, const bf16* __restrict__ v,
-                     bf16* __restrict__ out, int Sq, int Skv, int D, int ldq, int ldk, int ldv, int ldo,
-                     float scale_log2) {
+                     bf16* __restrict__ out, float* __restrict__ lse, int Sq, int Skv, int D, int ldq, int ldk, int ldv,
+                     int ldo, float scale_log2) {
     constexpr int PITCH = DP * 2 + 16;
     constexpr int KS = DP / 16;  // k-steps over the head dim
     extern __shared__ __align__(16) uint8_t smem[];
@@ -203,6 +203,11 @@ __global__ void __launch_bounds__(kThreads, (DP <= 80) ? 2 : 1)
     l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
     const float inv0 = 1.0f / l0, inv1 = 1.0f / l1;
     const int r0 = q0 + warp * 16 + (lane >> 2), r1 = r0 + 8;
+    if (lse != nullptr && (lane & 3) == 0) {   // log2-domain log-sum-exp of the scaled scores (saved for the backward)
+        float* dst = lse + ((size_t)b * gridDim.y + h) * Sq;
+        if (r0 < Sq) dst[r0] = m0 * scale_log2 + log2f(l0);
+        if (r1 < Sq) dst[r1] = m1 * scale_log2 + log2f(l1);
+    }
 #pragma unroll
     for (int nt = 0; nt < 2 * KS; ++nt) {
         const int col = nt * 8 + (lane & 3) * 2;
@@ -218,7 +223,7 @@ __global__ void __launch_bounds__(kThreads, (DP <= 80) ? 2 : 1)
 }
 
 template <int DP>
-int launch_attention(const bf16* q, const bf16* k, const bf16* v, bf16* out, int batch, int heads, int Sq, int Skv,
+int launch_attention(const bf16* q, const bf16* k, const bf16* v, bf16* out, float* lse, int batch, int heads, int Sq, int Skv,
                      int D, int ldq, int ldk, int ldv, int ldo, float scale, cudaStream_t s) {
     constexpr int PITCH = DP * 2 + 16;
     const size_t smem = (size_t)(kBM + 4 * kBN) * PITCH;
@@ -228,7 +233,7 @@ int launch_attention(const bf16* q, const bf16* k, const bf16* v, bf16* out, int
         configured = true;
     }
     dim3 grid(ceil_div(Sq, kBM), heads, batch);
-    B200SD_CUDA(b200sd_launch(attention_kernel<DP>, dim3(grid), dim3(kThreads), smem, s, q, k, v, out, Sq, Skv, D, ldq, ldk, ldv, ldo,
+    B200SD_CUDA(b200sd_launch(attention_kernel<DP>, dim3(grid), dim3(kThreads), smem, s, q, k, v, out, lse, Sq, Skv, D, ldq, ldk, ldv, ldo,
                                                       scale * 1.4426950408889634f));
     g_b200sd_launches.fetch_add(1, std::memory_order_relaxed);
     B200SD_LAUNCH_CHECK();
@@ -237,7 +242,7 @@ int launch_attention(const bf16* q, const bf16* k, const bf16* v, bf16* out, int
 
 }  // namespace
 
-int b200sd_attention_tc(const void* q, const void* k, const void* v, void* out, int batch, int heads, int Sq, int Skv,
+int b200sd_attention_tc(const void* q, const void* k, const void* v, void* out, float* lse, int batch, int heads, int Sq, int Skv,
                         int d, int ldq, int ldk, int ldv, int ldo, float scale, void* workspace, size_t ws_bytes,
                         cudaStream_t s);
 
@@ -245,9 +250,9 @@ extern "C" size_t b200sd_attention_workspace_bytes(int batch, int heads, int Skv
     return (size_t)batch * heads * d * Skv * sizeof(bf16);
 }
 
-extern "C" int b200sd_attention(const void* q, const void* k, const void* v, void* out, int batch, int heads, int Sq,
-                                int Skv, int d, int ldq, int ldk, int ldv, int ldo, float scale,
-                                void* workspace, size_t workspace_bytes, b200sd_stream_t stream) {
+extern "C" int b200sd_attention_lse(const void* q, const void* k, const void* v, void* out, float* lse, int batch, int heads,
+                                    int Sq, int Skv, int d, int ldq, int ldk, int ldv, int ldo, float scale,
+                                    void* workspace, size_t workspace_bytes, b200sd_stream_t stream) {
     B200SD_REQUIRE(q && k && v && out, "attention: null pointer");
     B200SD_REQUIRE(batch > 0 && heads > 0 && Sq > 0 && Skv > 0, "attention: bad sizes");
     B200SD_REQUIRE(batch <= 65535 && heads <= 65535, "attention: batch/heads too large");
@@ -261,7 +266,7 @@ extern "C" int b200sd_attention(const void* q, const void* k, const void* v, voi
         // tensor-core (tcgen05/TMEM) path for the self-attention-sized shapes
         static const bool no_tc = getenv("B200SD_ATTN_TC") && getenv("B200SD_ATTN_TC")[0] == '0';
         if (!no_tc) {
-            const int rc = b200sd_attention_tc(q, k, v, out, batch, heads, Sq, Skv, d, ldq, ldk, ldv, ldo, scale, workspace,
+            const int rc = b200sd_attention_tc(q, k, v, out, lse, batch, heads, Sq, Skv, d, ldq, ldk, ldv, ldo, scale, workspace,
                                                workspace_bytes, s);
             if (rc != B200SD_ERR_UNSUPPORTED) return rc;
         }
@@ -272,11 +277,18 @@ extern "C" int b200sd_attention(const void* q, const void* k, const void* v, voi
     bf16* oo = static_cast<bf16*>(out);
     const int dp = (d + 15) / 16 * 16;
 #define ATT_CASE(DP) \
-    case DP: return launch_attention<DP>(qq, kk, vv, oo, batch, heads, Sq, Skv, d, ldq, ldk, ldv, ldo, scale, s);
+    case DP: return launch_attention<DP>(qq, kk, vv, oo, lse, batch, heads, Sq, Skv, d, ldq, ldk, ldv, ldo, scale, s);
     switch (dp) {
         ATT_CASE(16) ATT_CASE(32) ATT_CASE(48) ATT_CASE(64) ATT_CASE(80) ATT_CASE(96) ATT_CASE(112) ATT_CASE(128)
         ATT_CASE(144) ATT_CASE(160)
     }
 #undef ATT_CASE
     B200SD_REQUIRE(false, "attention: head dim %d unsupported", d);
+}
+
+extern "C" int b200sd_attention(const void* q, const void* k, const void* v, void* out, int batch, int heads, int Sq,
+                                int Skv, int d, int ldq, int ldk, int ldv, int ldo, float scale,
+                                void* workspace, size_t workspace_bytes, b200sd_stream_t stream) {
+    return b200sd_attention_lse(q, k, v, out, nullptr, batch, heads, Sq, Skv, d, ldq, ldk, ldv, ldo, scale, workspace,
+                                workspace_bytes, stream);
 }

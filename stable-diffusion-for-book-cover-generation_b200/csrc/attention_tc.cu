@@ -31,6 +31,7 @@ constexpr int kBlk = kQ * 128;  // bytes of one [128 rows x 64 bf16] swizzled bl
 struct AttnParams {
     CUtensorMap tmQ, tmK, tmVt;
     bf16* out;
+    float* lse;   // optional [batch][heads][Sq]: log2-domain log-sum-exp of the scaled scores (for the backward)
     int Sq, Skv, heads, ldo;
     float scale_log2;
 };
@@ -272,6 +273,7 @@ __global__ void __launch_bounds__(kThreads, (D <= 40) ? 2 : 1) attention_tc_kern
         fold_o(num_tiles - 1, corr_prev);
         // ---- normalise and store ----
         const float inv = 1.0f / l;
+        if (p.lse != nullptr) p.lse[((size_t)b * p.heads + h) * p.Sq + q0 + row] = m * p.scale_log2 + log2f(l);
         bf16* dst = p.out + ((size_t)b * p.Sq + q0 + row) * p.ldo + h * D;
 #pragma unroll
         for (int c = 0; c < D; c += 8) {
@@ -293,7 +295,7 @@ __global__ void __launch_bounds__(kThreads, (D <= 40) ? 2 : 1) attention_tc_kern
 }
 
 template <int D, int DKB>
-int launch_tc(const bf16* q, const bf16* k, const bf16* vt, bf16* out, int batch, int heads, int Sq, int Skv, int ldq,
+int launch_tc(const bf16* q, const bf16* k, const bf16* vt, bf16* out, float* lse, int batch, int heads, int Sq, int Skv, int ldq,
               int ldk, int ldo, float scale, cudaStream_t s) {
     constexpr int DN = (D + 15) / 16 * 16;
     constexpr int VBLK_PAD = ((DN * 128 + 1023) / 1024) * 1024;
@@ -321,6 +323,7 @@ int launch_tc(const bf16* q, const bf16* k, const bf16* vt, bf16* out, int batch
         if (rc) return rc;
     }
     p.out = out;
+    p.lse = lse;
     p.Sq = Sq;
     p.Skv = Skv;
     p.heads = heads;
@@ -342,7 +345,7 @@ int launch_tc(const bf16* q, const bf16* k, const bf16* vt, bf16* out, int batch
 }  // namespace
 
 // Returns B200SD_ERR_UNSUPPORTED when the shape is not covered (the caller falls back to attention.cu's kernel).
-int b200sd_attention_tc(const void* q, const void* k, const void* v, void* out, int batch, int heads, int Sq, int Skv,
+int b200sd_attention_tc(const void* q, const void* k, const void* v, void* out, float* lse, int batch, int heads, int Sq, int Skv,
                         int d, int ldq, int ldk, int ldv, int ldo, float scale, void* workspace, size_t ws_bytes,
                         cudaStream_t s) {
     if (!(d == 40 || d == 80) || Sq % kQ != 0 || Skv % kKV != 0) return B200SD_ERR_UNSUPPORTED;
@@ -354,8 +357,8 @@ int b200sd_attention_tc(const void* q, const void* k, const void* v, void* out, 
                               static_cast<const bf16*>(v), vt, Skv, heads, d, ldv));
     g_b200sd_launches.fetch_add(1, std::memory_order_relaxed);
     if (d == 40)
-        return launch_tc<40, 1>(static_cast<const bf16*>(q), static_cast<const bf16*>(k), vt, static_cast<bf16*>(out), batch,
+        return launch_tc<40, 1>(static_cast<const bf16*>(q), static_cast<const bf16*>(k), vt, static_cast<bf16*>(out), lse, batch,
                                 heads, Sq, Skv, ldq, ldk, ldo, scale, s);
-    return launch_tc<80, 2>(static_cast<const bf16*>(q), static_cast<const bf16*>(k), vt, static_cast<bf16*>(out), batch, heads,
+    return launch_tc<80, 2>(static_cast<const bf16*>(q), static_cast<const bf16*>(k), vt, static_cast<bf16*>(out), lse, batch, heads,
                             Sq, Skv, ldq, ldk, ldo, scale, s);
 }

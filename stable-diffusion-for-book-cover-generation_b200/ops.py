@@ -316,3 +316,113 @@ def im2col_s2(x, out, batch, H, W):
     _chk(x, out)
     check(lib().b200sd_im2col_s2(_p(x), _p(out), batch, H, W, x.shape[-1], _dt(x), _stream()), "im2col_s2")
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# backward-pass kernels
+# ---------------------------------------------------------------------------------------------
+def attention_lse(q, k, v, out, lse, batch, heads, Sq, Skv, d, scale, ldq=None, ldk=None, ldv=None, ldo=None,
+                  q_off=0, k_off=0, v_off=0, ws=None):
+    """attention() that also writes lse[batch, heads, Sq] (log2-domain log-sum-exp) for attention_bwd()."""
+    _chk(q, k, v, out, lse)
+    if ws is None:
+        ws = _workspace("attn", lib().b200sd_attention_workspace_bytes(batch, heads, Skv, d) + 128, q.device, zero=False)
+    check(lib().b200sd_attention_lse(q.data_ptr() + q_off * 2, k.data_ptr() + k_off * 2, v.data_ptr() + v_off * 2,
+                                     _p(out), _p(lse), batch, heads, Sq, Skv, d, ldq or q.shape[-1], ldk or k.shape[-1],
+                                     ldv or v.shape[-1], ldo or out.shape[-1], float(scale), _p(ws), ws.numel(),
+                                     _stream()), "attention_lse")
+    return out
+
+
+def attention_bwd(q, k, v, out, dout, lse, dq, dk, dv, batch, heads, Sq, Skv, d, scale, *, ldq=None, ldk=None,
+                  ldv=None, lddq=None, lddk=None, lddv=None, q_off=0, k_off=0, v_off=0, dq_off=0, dk_off=0, dv_off=0,
+                  ws=None):
+    """dq/dk/dv (bf16) of attention(); q/k/v and dq/dk/dv may be column slices (buffer + element offset)."""
+    _chk(q, k, v, out, dout, lse, dq, dk, dv)
+    need = int(lib().b200sd_attention_bwd_workspace_bytes(batch, heads, Sq))
+    if ws is None or ws.numel() < need:
+        ws = _workspace("attn_bwd", need, q.device, zero=False)
+    check(lib().b200sd_attention_bwd(q.data_ptr() + q_off * 2, k.data_ptr() + k_off * 2, v.data_ptr() + v_off * 2,
+                                     _p(out), _p(dout), _p(lse), dq.data_ptr() + dq_off * 2, dk.data_ptr() + dk_off * 2,
+                                     dv.data_ptr() + dv_off * 2, batch, heads, Sq, Skv, d, ldq or q.shape[-1],
+                                     ldk or k.shape[-1], ldv or v.shape[-1], out.shape[-1], dout.shape[-1],
+                                     lddq or dq.shape[-1], lddk or dk.shape[-1], lddv or dv.shape[-1], float(scale),
+                                     _p(ws), ws.numel(), _stream()), "attention_bwd")
+
+
+def grad_prep(g, out_bf16=None, colsum=None, rows_per_image=0, ldcs=0):
+    """optional bf16 copy of gradient g [rows, N] + column sums accumulated into colsum (bias gradient)."""
+    _chk(g, out_bf16, colsum)
+    N = g.shape[-1]
+    check(lib().b200sd_grad_prep(_p(g), _dt(g), _p(out_bf16), _p(colsum), g.numel() // N, N, N, rows_per_image, ldcs,
+                                 _stream()), "grad_prep")
+    return out_bf16
+
+
+def groupnorm_silu_bwd(x0, x1, gamma, beta, dy, out0, out1, batch, hw, *, add_src=None, acc0=False, acc1=False,
+                       dgamma=None, dbeta=None, groups=32, eps=1e-5, silu=True):
+    _chk(x0, x1, gamma, beta, dy, out0, out1, add_src, dgamma, dbeta)
+    ws = _workspace("gn_bwd", lib().b200sd_groupnorm_bwd_workspace_floats(batch) * 4, x0.device, zero=False)
+    C0 = x0.shape[-1]
+    C1 = x1.shape[-1] if x1 is not None else 0
+    check(lib().b200sd_groupnorm_silu_bwd(_p(x0), _p(x1), C0, C1, _dt(x0), _p(gamma), _p(beta), _p(dy), _p(add_src),
+                                          _p(out0), _p(out1), _dt(out0), int(acc0), int(acc1), _p(dgamma), _p(dbeta),
+                                          _p(ws), batch, hw, groups, float(eps), int(silu), _stream()),
+          "groupnorm_silu_bwd")
+
+
+def layernorm_bwd(x, gamma, dy, dres, dgamma=None, dbeta=None, eps=1e-5):
+    _chk(x, gamma, dy, dres, dgamma, dbeta)
+    Cc = x.shape[-1]
+    check(lib().b200sd_layernorm_bwd(_p(x), _dt(x), _p(gamma), _p(dy), _p(dres), _p(dgamma), _p(dbeta), x.numel() // Cc,
+                                     Cc, float(eps), _stream()), "layernorm_bwd")
+
+
+def geglu_fwd(u, out):
+    _chk(u, out)
+    check(lib().b200sd_geglu_fwd(_p(u), _p(out), u.numel() // u.shape[-1], u.shape[-1] // 2, _stream()), "geglu_fwd")
+    return out
+
+
+def geglu_bwd(u, dff, du):
+    _chk(u, dff, du)
+    check(lib().b200sd_geglu_bwd(_p(u), _p(dff), _p(du), u.numel() // u.shape[-1], u.shape[-1] // 2, _stream()),
+          "geglu_bwd")
+    return du
+
+
+def upsample2x_bwd(dy, dx, batch, H, W, accumulate=False):
+    _chk(dy, dx)
+    check(lib().b200sd_upsample2x_bwd(_p(dy), _p(dx), batch, H, W, dx.shape[-1], int(accumulate), _stream()),
+          "upsample2x_bwd")
+
+
+def col2im_s2(dcol, dx, batch, H, W, accumulate=False):
+    _chk(dcol, dx)
+    check(lib().b200sd_col2im_s2(_p(dcol), _p(dx), batch, H, W, dx.shape[-1], int(accumulate), _stream()), "col2im_s2")
+
+
+def conv_out_bwd(dout_nchw, x_nhwc, w_packed, dx_nhwc, dw=None, dbias=None):
+    _chk(dout_nchw, x_nhwc, w_packed, dx_nhwc, dw, dbias)
+    B, Cout, H, W = dout_nchw.shape
+    check(lib().b200sd_conv_out_bwd(_p(dout_nchw), _p(x_nhwc), _p(w_packed), _p(dx_nhwc), _p(dw), _p(dbias), B,
+                                    dx_nhwc.shape[-1], Cout, H, W, _stream()), "conv_out_bwd")
+
+
+def conv_in_wgrad(dy_nhwc, x_nchw, dw):
+    _chk(dy_nhwc, x_nchw, dw)
+    B, Cin, H, W = x_nchw.shape
+    check(lib().b200sd_conv_in_wgrad(_p(dy_nhwc), _dt(dy_nhwc), _p(x_nchw), _p(dw), B, Cin, dy_nhwc.shape[-1], H, W,
+                                     _stream()), "conv_in_wgrad")
+
+
+def cast_act(x, out_bf16, silu=False):
+    _chk(x, out_bf16)
+    check(lib().b200sd_cast_act(_p(x), _p(out_bf16), x.numel(), int(silu), _stream()), "cast_act")
+    return out_bf16
+
+
+def silu_bwd_mul(pre, grad):
+    _chk(pre, grad)
+    check(lib().b200sd_silu_bwd_mul(_p(pre), _p(grad), grad.numel(), _stream()), "silu_bwd_mul")
+    return grad
