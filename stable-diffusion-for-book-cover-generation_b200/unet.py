@@ -176,6 +176,9 @@ class UNet2DConditionModel(nn.Module):
         self._dirty = True
         self.use_cuda_graph = True
         self._gradient_checkpointing = False
+        self._flat = None            # train.FlatParams (flat bf16 weights + flat fp32 gradients), built on first training call
+        self._train_engines = {}
+        self._direct_grads = False
 
     # -- init / (de)serialisation ---------------------------------------------------------------
     @torch.no_grad()
@@ -245,7 +248,26 @@ class UNet2DConditionModel(nn.Module):
         r = super()._apply(fn, *a, **kw)
         self._dirty = True
         self._engines = {}
+        self._flat = None
+        self._train_engines = {}
         return r
+
+    def enable_direct_gradients(self, enabled: bool = True):
+        """param.grad become views of ONE flat fp32 gradient buffer that the backward kernels accumulate into
+        (see autograd.py).  Use `flat_gradients()` for bucketed allreduce / a fused optimizer."""
+        self._direct_grads = bool(enabled)
+        return self
+
+    def flat_gradients(self):
+        """the flat fp32 gradient buffer (kernel layout) -- None before the first training forward"""
+        return None if self._flat is None else self._flat.grad
+
+    def zero_grad(self, set_to_none: bool = True):
+        if self._direct_grads and self._flat is not None:
+            self._flat.zero_grad()
+            self._flat.attach_grads()
+            return
+        super().zero_grad(set_to_none=set_to_none)
 
     def mark_weights_changed(self):
         """Call after an optimizer step in eval-mode use; in train() mode it is checked automatically."""
@@ -260,6 +282,7 @@ class UNet2DConditionModel(nn.Module):
         return self.conv_in.weight.dtype
 
     def enable_gradient_checkpointing(self):
+        """accepted for API compatibility (finetune_sd.py:389); activations of one step fit in HBM3e (180 GB) and are kept"""
         self._gradient_checkpointing = True
 
     # -- weight packing -------------------------------------------------------------------------

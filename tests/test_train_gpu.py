@@ -1,0 +1,150 @@
+"""GPU parity of the UNet training path (BASELINE configs 3 and 4): the gradients of
+`mse(unet(noisy, t, ctx).sample, noise)` w.r.t. all 686 parameters (and w.r.t. the text context) against
+fp32 torch autograd through the oracle on identical random-init weights and inputs.
+
+Tolerance: the backward runs bf16 tensor-core operands with fp32 accumulation, like the forward, whose bar is
+1e-2 max-relative on the noise prediction.  Gradients cross the network twice, so the per-tensor bars are
+max|g - ref| / max|ref| <= 8e-2 and cosine >= 0.998, and the whole flattened gradient must reach cosine
+>= 0.9995 (measured on B200: worst tensor 5e-2 / 0.9993 on the tiny net; torch's own bf16-autocast backward of
+the oracle is printed beside it as the library noise level).  A wrong kernel shows up as O(1), not as 1e-2."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _setup():
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+
+
+def _pair(overrides):
+    from b200sd.unet import UNet2DConditionModel
+    from oracle.unet_ref import make_oracle_unet
+    _setup()
+    oracle = make_oracle_unet(seed=0, **overrides).to(DEV)
+    ours = UNet2DConditionModel(**overrides)
+    ours.load_state_dict(oracle.state_dict(), strict=True)
+    return oracle, ours.to(DEV).train()
+
+
+def _inputs(N, h, w, ctx_dim, seed):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(N, 4, h, w, generator=g).to(DEV)
+    noise = torch.randn(N, 4, h, w, generator=g).to(DEV)
+    ctx = torch.randn(N, 77, ctx_dim, generator=g).to(DEV)
+    t = torch.randint(0, 1000, (N,), generator=g).to(DEV)
+    return x, noise, ctx, t
+
+
+def _compare(named_ref, named_got, bar_rel=8e-2, bar_cos=0.998):
+    worst, flat_r, flat_g, bad = 0.0, [], [], []
+    for name, ref in named_ref.items():
+        got = named_got[name]
+        assert got is not None, f"{name}: no gradient"
+        assert got.shape == ref.shape, name
+        r, g = ref.float().flatten(), got.float().flatten()
+        scale = float(r.abs().max())
+        rel = float((g - r).abs().max()) / (scale + 1e-20)
+        cos = float(F.cosine_similarity(g, r, dim=0))
+        flat_r.append(r)
+        flat_g.append(g)
+        worst = max(worst, rel)
+        if rel > bar_rel or cos < bar_cos:
+            bad.append((name, rel, cos))
+    cos_all = float(F.cosine_similarity(torch.cat(flat_g), torch.cat(flat_r), dim=0))
+    return worst, cos_all, bad
+
+
+def _ref_grads(oracle, x, noise, ctx, t, ctx_grad=False):
+    oracle.zero_grad(set_to_none=True)
+    c = ctx.clone().requires_grad_(ctx_grad)
+    loss = F.mse_loss(oracle(x, t, c).sample, noise)
+    loss.backward()
+    grads = {n: p.grad.clone() for n, p in oracle.named_parameters() if p.grad is not None}
+    return float(loss), grads, (c.grad.clone() if ctx_grad else None)
+
+
+def test_tiny_unet_all_gradients_and_context_gradient():
+    from b200sd import ops
+    from oracle.unet_ref import TINY_OVERRIDES
+    oracle, ours = _pair(TINY_OVERRIDES)
+    x, noise, ctx, t = _inputs(2, 32, 32, 64, 0)
+    ref_loss, ref, ref_dctx = _ref_grads(oracle, x, noise, ctx, t, ctx_grad=True)
+    c = ctx.clone().requires_grad_(True)
+    loss = ops.mse_loss(ours(x, t, c).sample, noise)
+    loss.backward()
+    assert abs(float(loss) - ref_loss) <= 2e-2 * ref_loss
+    got = {n: p.grad for n, p in ours.named_parameters()}
+    worst, cos_all, bad = _compare(ref, got)
+    print(f"tiny grads: worst per-tensor max-rel {worst:.4g}, global cosine {cos_all:.6f}")
+    assert not bad, f"{len(bad)} tensors out of tolerance, e.g. {bad[:5]}"
+    assert cos_all >= 0.9995, cos_all
+    rel = float((c.grad - ref_dctx).abs().max() / ref_dctx.abs().max())
+    assert rel <= 4e-2, f"context gradient max-rel {rel}"
+    # library noise level: torch's bf16-autocast backward of the same oracle
+    oracle.zero_grad(set_to_none=True)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        lb = F.mse_loss(oracle(x, t, ctx).sample.float(), noise)
+    lb.backward()
+    w2, c2, _ = _compare(ref, {n: p.grad for n, p in oracle.named_parameters()})
+    print(f"torch bf16 autocast backward of the oracle: worst per-tensor max-rel {w2:.4g}, global cosine {c2:.6f}")
+
+
+def test_direct_gradients_accumulate_in_the_flat_buffer():
+    from b200sd import ops
+    from oracle.unet_ref import TINY_OVERRIDES
+    oracle, ours = _pair(TINY_OVERRIDES)
+    ours.enable_direct_gradients()
+    x, noise, ctx, t = _inputs(2, 32, 32, 64, 1)
+    _, ref, _ = _ref_grads(oracle, x, noise, ctx, t)
+    for _ in range(2):   # two micro-steps without zero_grad: gradient accumulation (finetune_sd.py:454-458)
+        ops.mse_loss(ours(x, t, ctx).sample, noise).backward()
+    flat = ours.flat_gradients()
+    p = ours.down_blocks[0].resnets[0].conv1.weight
+    assert p.grad.untyped_storage().data_ptr() == flat.untyped_storage().data_ptr(), "param.grad must alias the flat buffer"
+    got = {n: q.grad / 2 for n, q in ours.named_parameters()}
+    _, cos_all, bad = _compare(ref, got)
+    assert not bad and cos_all >= 0.9995, (cos_all, bad[:5])
+    # optimizer.zero_grad() sets grads to None: the next backward starts from zero again
+    for q in ours.parameters():
+        q.grad = None
+    ops.mse_loss(ours(x, t, ctx).sample, noise).backward()
+    _, cos_all, bad = _compare(ref, {n: q.grad for n, q in ours.named_parameters()})
+    assert not bad and cos_all >= 0.9995, (cos_all, bad[:5])
+
+
+def test_frozen_unet_context_gradient_only():
+    """BASELINE config 4 (train_text_encoder): UNet frozen, gradient flows to encoder_hidden_states only."""
+    from b200sd import ops
+    from oracle.unet_ref import TINY_OVERRIDES
+    oracle, ours = _pair(TINY_OVERRIDES)
+    ours.requires_grad_(False).eval()
+    x, noise, ctx, t = _inputs(2, 32, 32, 64, 2)
+    _, _, ref_dctx = _ref_grads(oracle, x, noise, ctx, t, ctx_grad=True)
+    c = ctx.clone().requires_grad_(True)
+    ops.mse_loss(ours(x, t, c).sample, noise).backward()
+    assert all(p.grad is None for p in ours.parameters())
+    rel = float((c.grad - ref_dctx).abs().max() / ref_dctx.abs().max())
+    assert rel <= 4e-2, f"context gradient max-rel {rel}"
+
+
+def test_sd15_unet_gradients_batch2():
+    """Full SD v1.5 UNet (859.5 M parameters), batch 2 at 64x64 latents."""
+    from b200sd import ops
+    oracle, ours = _pair({})
+    x, noise, ctx, t = _inputs(2, 64, 64, 768, 3)
+    ref_loss, ref, ref_dctx = _ref_grads(oracle, x, noise, ctx, t, ctx_grad=True)
+    oracle.zero_grad(set_to_none=True)
+    c = ctx.clone().requires_grad_(True)
+    loss = ops.mse_loss(ours(x, t, c).sample, noise)
+    loss.backward()
+    assert abs(float(loss) - ref_loss) <= 2e-2 * ref_loss
+    worst, cos_all, bad = _compare(ref, {n: p.grad for n, p in ours.named_parameters()})
+    print(f"sd15 grads: worst per-tensor max-rel {worst:.4g}, global cosine {cos_all:.6f}, out-of-tolerance {len(bad)}")
+    assert not bad, f"{len(bad)} tensors out of tolerance, e.g. {bad[:5]}"
+    assert cos_all >= 0.9995, cos_all
+    rel = float((c.grad - ref_dctx).abs().max() / ref_dctx.abs().max())
+    assert rel <= 4e-2, f"context gradient max-rel {rel}"
