@@ -285,6 +285,17 @@ int b200sd_conv_in_wgrad(const void* dy_nhwc, int dy_dtype, const float* x_nchw,
 int b200sd_cast_act(const float* in, void* out_bf16, int64_t n, int silu, b200sd_stream_t stream);
 int b200sd_silu_bwd_mul(const float* pre, float* grad, int64_t n, b200sd_stream_t stream);
 
+/* ---- optimizer step over the flat kernel-layout buffers (finetune_sd.py:407-420, 569-570) ------ */
+/* out_bf16[i] = in[i] for n (multiple of 8) elements: fp32 master weights -> bf16 tensor-core copy. */
+int b200sd_cast_flat(const float* in, void* out_bf16, int64_t n, b200sd_stream_t stream);
+/* torch.optim.AdamW semantics (decoupled weight decay, bias correction with `step` >= 1) over n
+ * (multiple of 4) parameters, fused with: gradient scaling (grad_scale = 1 / world averages a SUM
+ * allreduce), the bf16 re-cast of the updated weights, and optional zeroing of grad for the next step.
+ * HBM-bound: 16 B read + 14 B (18 B with zero_grad) written per parameter. */
+int b200sd_adamw_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, void* weights_bf16, int64_t n,
+                      float lr, float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
+                      int zero_grad, b200sd_stream_t stream);
+
 /* nearest x2 upsample NHWC bf16: (batch,H,W,C) -> (batch,2H,2W,C)  (Upsample2D's F.interpolate) */
 int b200sd_upsample2x(const void* x, void* out, int batch, int H, int W, int C, int in_dtype, b200sd_stream_t stream);
 /* im2col for the three stride-2 Downsample2D convs: NHWC (batch,H,W,C) -> [batch*(H/2)*(W/2)][9*C] */

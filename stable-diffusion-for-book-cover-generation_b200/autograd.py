@@ -42,7 +42,7 @@ class _UNetFn(torch.autograd.Function):
                      for r in flat.order):
                 flat.zero_grad()
                 flat.attach_grads()
-        d_ctx = eng.run_backward(d_out.contiguous().float())
+        d_ctx = eng.run_backward(d_out.contiguous().float(), on_ready=model._grad_ready_hook if direct else None)
         if eng.train_weights and not direct:
             grads = tuple(flat.regs[i].gview if flat.regs[i].param.requires_grad else None for i in ctx.param_ids)
         else:
@@ -50,13 +50,20 @@ class _UNetFn(torch.autograd.Function):
         return (None, None, None, d_ctx if ctx.need_ctx else None) + grads
 
 
+def ensure_flat(model, dev):
+    """(Re)build the flat kernel-layout state when it does not exist, sits on another device, or the parameters were
+    replaced (a .to() / load of new tensors un-homes them)."""
+    if getattr(model, "_flat", None) is None or model._flat.device != dev or not model._flat.owns(model):
+        model._flat = FlatParams(model, dev)
+        model._train_engines = {}
+    return model._flat
+
+
 def unet_forward_train(model, sample, timestep, ctx):
     if sample.requires_grad:
         raise NotImplementedError("b200sd: gradients w.r.t. the latent input are not implemented (the reference never needs them)")
     dev = sample.device
-    if getattr(model, "_flat", None) is None or model._flat.device != dev:
-        model._flat = FlatParams(model, dev)
-        model._train_engines = {}
+    ensure_flat(model, dev)
     N, _, H, W = sample.shape
     train_weights = any(p.requires_grad for p in model.parameters())
     key = (N, H, W, ctx.shape[1], dev.index, train_weights, bool(ctx.requires_grad))

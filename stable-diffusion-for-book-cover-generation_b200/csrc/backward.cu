@@ -5,6 +5,7 @@
 // All are bandwidth-bound passes; parameter gradients are ACCUMULATED into fp32 with atomics (the flat
 // gradient buffer is zeroed once per optimizer step), activation gradients are written or accumulated as asked.
 #include <atomic>
+#include <cmath>
 
 #include "common.cuh"
 
@@ -513,6 +514,51 @@ __global__ void silu_bwd_mul_kernel(const float* __restrict__ pre, float* __rest
         g[i] *= silu_grad_f(pre[i]);
 }
 
+// ---- flat-buffer kernels of the optimizer step ----------------------------------------------------------------
+// fp32 master -> bf16 tensor-core copy, 8 elements per thread
+__global__ void cast_flat_kernel(const float* __restrict__ in, bf16* __restrict__ out, int64_t n8) {
+    ptx::pdl_trigger();
+    ptx::pdl_wait();
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+        float v[8];
+        ld8<B200SD_F32>(in, (size_t)i * 8, v);
+        st8<B200SD_BF16>(out, (size_t)i * 8, v);
+    }
+}
+
+// AdamW (decoupled weight decay, torch.optim.AdamW semantics) over the flat kernel-layout buffers, fused with the
+// gradient averaging of data parallelism (grad_scale = 1 / world), the bf16 re-cast of the updated weights and
+// (optionally) the zeroing of the gradient buffer for the next step: one pass, 16 B read + 14 B written per parameter.
+__global__ void __launch_bounds__(256) adamw_flat_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
+                                                         float* __restrict__ v, bf16* __restrict__ wb, int64_t n4, float lr,
+                                                         float beta1, float beta2, float eps, float wd, float bc1, float rsqrt_bc2,
+                                                         float grad_scale, int zero_grad) {
+    ptx::pdl_trigger();
+    ptx::pdl_wait();
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        float4 P = reinterpret_cast<float4*>(p)[i], G = reinterpret_cast<float4*>(g)[i];
+        float4 M = reinterpret_cast<float4*>(m)[i], V = reinterpret_cast<float4*>(v)[i];
+        float* pp = &P.x; float* gg = &G.x; float* mm = &M.x; float* vv = &V.x;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float gr = gg[j] * grad_scale;
+            pp[j] *= (1.0f - lr * wd);
+            mm[j] = beta1 * mm[j] + (1.0f - beta1) * gr;
+            vv[j] = beta2 * vv[j] + (1.0f - beta2) * gr * gr;
+            const float denom = sqrtf(vv[j]) * rsqrt_bc2 + eps;
+            pp[j] -= (lr / bc1) * (mm[j] / denom);
+        }
+        reinterpret_cast<float4*>(p)[i] = P;
+        reinterpret_cast<float4*>(m)[i] = M;
+        reinterpret_cast<float4*>(v)[i] = V;
+        if (zero_grad) reinterpret_cast<float4*>(g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        uint2 u;
+        u.x = pack_bf16x2(P.x, P.y);
+        u.y = pack_bf16x2(P.z, P.w);
+        reinterpret_cast<uint2*>(wb)[i] = u;
+    }
+}
+
 }  // namespace
 
 // ================================================================================================
@@ -730,6 +776,34 @@ extern "C" int b200sd_cast_act(const float* in, void* out_bf16, int64_t n, int s
 extern "C" int b200sd_silu_bwd_mul(const float* pre, float* grad, int64_t n, b200sd_stream_t stream) {
     B200SD_REQUIRE(pre && grad && n > 0, "silu_bwd_mul: bad arguments");
     B200SD_CUDA(b200sd_launch(silu_bwd_mul_kernel, dim3(ew_grid(n, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), pre, grad, n));
+    COUNT_LAUNCH();
+    B200SD_LAUNCH_CHECK();
+    return B200SD_OK;
+}
+
+extern "C" int b200sd_cast_flat(const float* in, void* out_bf16, int64_t n, b200sd_stream_t stream) {
+    B200SD_REQUIRE(in && out_bf16 && n > 0 && n % 8 == 0, "cast_flat: n must be a positive multiple of 8");
+    B200SD_REQUIRE(((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out_bf16)) & 15) == 0, "cast_flat: pointers must be 16-byte aligned");
+    B200SD_CUDA(b200sd_launch(cast_flat_kernel, dim3(ew_grid(n / 8, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), in,
+                              static_cast<bf16*>(out_bf16), n / 8));
+    COUNT_LAUNCH();
+    B200SD_LAUNCH_CHECK();
+    return B200SD_OK;
+}
+
+extern "C" int b200sd_adamw_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, void* weights_bf16, int64_t n,
+                                 float lr, float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
+                                 int zero_grad, b200sd_stream_t stream) {
+    B200SD_REQUIRE(param && grad && exp_avg && exp_avg_sq && weights_bf16, "adamw_step: null pointer");
+    B200SD_REQUIRE(n > 0 && n % 4 == 0 && step >= 1, "adamw_step: n must be a positive multiple of 4 and step >= 1");
+    B200SD_REQUIRE(((reinterpret_cast<uintptr_t>(param) | reinterpret_cast<uintptr_t>(grad) | reinterpret_cast<uintptr_t>(exp_avg) |
+                     reinterpret_cast<uintptr_t>(exp_avg_sq)) & 15) == 0 && (reinterpret_cast<uintptr_t>(weights_bf16) & 7) == 0,
+                   "adamw_step: pointers must be 16-byte aligned");
+    const double bc1 = 1.0 - pow((double)beta1, (double)step);
+    const double bc2 = 1.0 - pow((double)beta2, (double)step);
+    B200SD_CUDA(b200sd_launch(adamw_flat_kernel, dim3(ew_grid(n / 4, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), param, grad,
+                              exp_avg, exp_avg_sq, static_cast<bf16*>(weights_bf16), n / 4, lr, beta1, beta2, eps, weight_decay,
+                              (float)bc1, (float)(1.0 / sqrt(bc2)), grad_scale, zero_grad));
     COUNT_LAUNCH();
     B200SD_LAUNCH_CHECK();
     return B200SD_OK;

@@ -350,13 +350,31 @@ def attention_bwd(q, k, v, out, dout, lse, dq, dk, dv, batch, heads, Sq, Skv, d,
                                      _p(ws), ws.numel(), _stream()), "attention_bwd")
 
 
-def grad_prep(g, out_bf16=None, colsum=None, rows_per_image=0, ldcs=0):
-    """optional bf16 copy of gradient g [rows, N] + column sums accumulated into colsum (bias gradient)."""
+def grad_prep(g, out_bf16=None, colsum=None, rows_per_image=0, ldcs=0, rows=None, N=None, ld=None):
+    """optional bf16 copy of gradient g [rows, N] + column sums accumulated into colsum (bias gradient).
+    rows / N / ld describe a column window of a wider row-major buffer when g is a flat slice."""
     _chk(g, out_bf16, colsum)
-    N = g.shape[-1]
-    check(lib().b200sd_grad_prep(_p(g), _dt(g), _p(out_bf16), _p(colsum), g.numel() // N, N, N, rows_per_image, ldcs,
+    if N is None:
+        N = g.shape[-1]
+    if rows is None:
+        rows = g.numel() // N
+    check(lib().b200sd_grad_prep(_p(g), _dt(g), _p(out_bf16), _p(colsum), rows, N, ld or N, rows_per_image, ldcs,
                                  _stream()), "grad_prep")
     return out_bf16
+
+
+def cast_flat(src_f32, dst_bf16):
+    _chk(src_f32, dst_bf16)
+    check(lib().b200sd_cast_flat(_p(src_f32), _p(dst_bf16), src_f32.numel(), _stream()), "cast_flat")
+    return dst_bf16
+
+
+def adamw_step(param, grad, exp_avg, exp_avg_sq, weights_bf16, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0,
+               zero_grad=False):
+    _chk(param, grad, exp_avg, exp_avg_sq, weights_bf16)
+    check(lib().b200sd_adamw_step(_p(param), _p(grad), _p(exp_avg), _p(exp_avg_sq), _p(weights_bf16), param.numel(),
+                                  float(lr), float(beta1), float(beta2), float(eps), float(weight_decay), int(step),
+                                  float(grad_scale), int(zero_grad), _stream()), "adamw_step")
 
 
 def groupnorm_silu_bwd(x0, x1, gamma, beta, dy, out0, out1, batch, hw, *, add_src=None, acc0=False, acc1=False,

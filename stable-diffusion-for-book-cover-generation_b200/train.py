@@ -32,15 +32,18 @@ _ALIGN = 64  # elements: every region starts 128-byte aligned in the bf16 buffer
 
 class _Reg:
     """One parameter inside the flat buffers."""
-    __slots__ = ("param", "kind", "off", "numel", "shape2d", "g", "gview", "wb", "wb_view", "wf", "wf_view")
+    __slots__ = ("param", "kind", "off", "numel", "shape2d", "g", "gview", "wb", "wf", "pview")
 
 
 class FlatParams:
-    """Flat kernel-layout buffers for a UNet2DConditionModel:
-       wb   bf16  GEMM weights ([Cout][ky][kx][Cin] for 3x3 convs, [out][in] for linears; fused q|k|v, k|v and the
-                  22 time_emb_proj heads are adjacent so one GEMM reads them as one matrix)
-       wf   fp32  the two 4-channel end convs (CUDA-core kernels read fp32 weights) + concatenated tproj bias
-       grad fp32  every parameter's gradient, same order (kernel layout)."""
+    """Flat kernel-layout state of a UNet2DConditionModel, all in ONE order (execution order of the forward, the
+    time-embedding parameters first -- their gradients complete last in the backward):
+       master fp32  the parameters themselves: every `nn.Parameter.data` is re-homed to a view of this buffer
+                    ([Cout][ky][kx][Cin] for 3x3 convs, i.e. a permuted view of the diffusers OIHW shape; fused q|k|v,
+                    k|v and the 22 time_emb_proj heads are adjacent so one GEMM reads them as one matrix)
+       wb     bf16  tensor-core copy of master (one cast kernel, or written by the fused AdamW step)
+       grad   fp32  every parameter's gradient (accumulated by the backward kernels)
+    state_dict() / load_state_dict() / torch optimizers keep working on the re-homed parameters."""
 
     def __init__(self, model, device):
         self.model, self.device = model, device
@@ -50,6 +53,8 @@ class FlatParams:
 
         def add(p, kind):
             nonlocal off
+            if p.dtype != F32:
+                raise B200SDError("training needs fp32 master parameters (the kernels compute in bf16 on their own copy)")
             r = _Reg()
             r.param, r.kind, r.numel = p, kind, p.numel()
             r.off = off
@@ -65,22 +70,15 @@ class FlatParams:
                     raise B200SDError("fused weight regions must be multiples of 64 elements")
                 add(p, kind)
 
-        m = model
-        add(m.conv_in.weight, "conv_f32"); add(m.conv_in.bias, "vec")
-        te = m.time_embedding
-        add(te.linear_1.weight, "lin"); add(te.linear_1.bias, "vec")
-        add(te.linear_2.weight, "lin"); add(te.linear_2.bias, "vec")
-        resnets = list(m._iter_resnets())
-        add_adjacent([r.time_emb_proj.weight for _, r in resnets], "lin")
-        add_adjacent([r.time_emb_proj.bias for _, r in resnets], "vec_cat")
-        for _, r in resnets:
+        def add_resnet(r):
             add(r.norm1.weight, "vec"); add(r.norm1.bias, "vec")
             add(r.conv1.weight, "conv3"); add(r.conv1.bias, "vec")
             add(r.norm2.weight, "vec"); add(r.norm2.bias, "vec")
             add(r.conv2.weight, "conv3"); add(r.conv2.bias, "vec")
             if hasattr(r, "conv_shortcut"):
                 add(r.conv_shortcut.weight, "lin"); add(r.conv_shortcut.bias, "vec")
-        for _, a in m._iter_xformers():
+
+        def add_xformer(a):
             blk = a.transformer_blocks[0]
             add(a.norm.weight, "vec"); add(a.norm.bias, "vec")
             add(a.proj_in.weight, "lin"); add(a.proj_in.bias, "vec")
@@ -94,85 +92,87 @@ class FlatParams:
             add(blk.ff.net[0].proj.weight, "lin"); add(blk.ff.net[0].proj.bias, "vec")
             add(blk.ff.net[2].weight, "lin"); add(blk.ff.net[2].bias, "vec")
             add(a.proj_out.weight, "lin"); add(a.proj_out.bias, "vec")
-        for b in list(m.down_blocks) + list(m.up_blocks):
-            for s in (getattr(b, "downsamplers", None), getattr(b, "upsamplers", None)):
-                if s is not None:
-                    add(s[0].conv.weight, "conv3"); add(s[0].conv.bias, "vec")
+
+        def add_sampler(s):
+            add(s.conv.weight, "conv3"); add(s.conv.bias, "vec")
+
+        m = model
+        te = m.time_embedding
+        add(te.linear_1.weight, "lin"); add(te.linear_1.bias, "vec")
+        add(te.linear_2.weight, "lin"); add(te.linear_2.bias, "vec")
+        resnets = list(m._iter_resnets())
+        add_adjacent([r.time_emb_proj.weight for _, r in resnets], "lin")
+        add_adjacent([r.time_emb_proj.bias for _, r in resnets], "vec")
+        add(m.conv_in.weight, "conv_f32"); add(m.conv_in.bias, "vec")
+        for b in m.down_blocks:
+            for j, r in enumerate(b.resnets):
+                add_resnet(r)
+                if hasattr(b, "attentions"):
+                    add_xformer(b.attentions[j])
+            if hasattr(b, "downsamplers"):
+                add_sampler(b.downsamplers[0])
+        add_resnet(m.mid_block.resnets[0]); add_xformer(m.mid_block.attentions[0]); add_resnet(m.mid_block.resnets[1])
+        for b in m.up_blocks:
+            for j, r in enumerate(b.resnets):
+                add_resnet(r)
+                if hasattr(b, "attentions"):
+                    add_xformer(b.attentions[j])
+            if hasattr(b, "upsamplers"):
+                add_sampler(b.upsamplers[0])
         add(m.conv_norm_out.weight, "vec"); add(m.conv_norm_out.bias, "vec")
         add(m.conv_out.weight, "conv_f32"); add(m.conv_out.bias, "vec")
         missing = [n for n, p in m.named_parameters() if id(p) not in self.regs]
         if missing:
             raise B200SDError(f"FlatParams: parameters not laid out: {missing[:4]}...")
         self.total = off
+        self.master = torch.zeros(off, dtype=F32, device=device)
         self.grad = torch.zeros(off, dtype=F32, device=device)
         self.wb = torch.zeros(off, dtype=BF16, device=device)
-        # fp32 side buffer only for the regions that need it (end convs + concatenated tproj bias)
-        f_off = 0
-        self._f_off = {}
-        for r in self.order:
-            if r.kind in ("conv_f32", "vec_cat"):
-                self._f_off[id(r.param)] = f_off
-                f_off += (r.numel + _ALIGN - 1) // _ALIGN * _ALIGN if r.kind == "conv_f32" else r.numel
-        self.wf = torch.zeros(max(f_off, 1), dtype=F32, device=device)
         for r in self.order:
             p = r.param
-            g = self.grad[r.off:r.off + r.numel]
-            r.wb = r.wb_view = r.wf = r.wf_view = None
+            sl = slice(r.off, r.off + r.numel)
+            g, w, mst = self.grad[sl], self.wb[sl], self.master[sl]
+            r.wb = r.wf = None
             if r.kind in ("conv3", "conv_f32"):
                 co, ci, kh, kw = p.shape
                 r.shape2d = (co, kh * kw * ci)
-                r.g = g.view(co, kh * kw * ci)
+                r.g = g.view(r.shape2d)
                 r.gview = g.view(co, kh, kw, ci).permute(0, 3, 1, 2)
+                r.pview = mst.view(co, kh, kw, ci).permute(0, 3, 1, 2)
                 if r.kind == "conv3":
-                    w = self.wb[r.off:r.off + r.numel]
-                    r.wb, r.wb_view = w.view(co, kh * kw * ci), w.view(co, kh, kw, ci).permute(0, 3, 1, 2)
+                    r.wb = w.view(r.shape2d)
                 else:
-                    fo = self._f_off[id(p)]
-                    w = self.wf[fo:fo + r.numel]
-                    r.wf, r.wf_view = w.view(co, kh * kw * ci), w.view(co, kh, kw, ci).permute(0, 3, 1, 2)
+                    r.wf = mst.view(r.shape2d)       # the CUDA-core end convs read the fp32 master directly
             elif r.kind == "lin":
                 r.shape2d = (p.shape[0], p.numel() // p.shape[0])
-                r.g = g.view(r.shape2d)
-                r.gview = g.view(p.shape)
-                w = self.wb[r.off:r.off + r.numel]
-                r.wb, r.wb_view = w.view(r.shape2d), w.view(p.shape)
+                r.g, r.gview, r.pview, r.wb = g.view(r.shape2d), g.view(p.shape), mst.view(p.shape), w.view(r.shape2d)
             else:
                 r.shape2d = (p.numel(),)
-                r.g = g
-                r.gview = g.view(p.shape)
-                if r.kind == "vec_cat":
-                    fo = self._f_off[id(p)]
-                    r.wf = r.wf_view = self.wf[fo:fo + r.numel]
+                r.g, r.gview, r.pview = g, g.view(p.shape), mst.view(p.shape)
+        # re-home the parameters into the flat master buffer (Parameter identity is preserved)
+        with torch.no_grad():
+            for r in self.order:
+                r.pview.copy_(r.param.data)
+                r.param.data = r.pview
         self._versions = None
 
     def reg(self, p) -> _Reg:
         return self.regs[id(p)]
 
     def span(self, ps, buf):
-        """one 2-D view over the adjacent regions of `ps` in flat buffer `buf` ("wb" | "grad" | "wf")"""
+        """one view over the adjacent regions of `ps` in flat buffer `buf` ("wb" | "grad" | "master")"""
         r0 = self.reg(ps[0])
         n = sum(p.numel() for p in ps)
-        t = getattr(self, buf)
-        if buf == "wf":
-            fo = self._f_off[id(ps[0])]
-            return t[fo:fo + n]
-        cols = r0.shape2d[-1] if len(r0.shape2d) == 2 else None
-        flat = t[r0.off:r0.off + n]
-        return flat.view(-1, cols) if cols else flat
+        flat = getattr(self, buf)[r0.off:r0.off + n]
+        return flat.view(-1, r0.shape2d[-1]) if len(r0.shape2d) == 2 else flat
 
     @torch.no_grad()
     def refresh_weights(self, force=False):
-        """fp32 parameters -> bf16 / fp32 kernel-layout buffers (multi-tensor copies), only when they changed."""
+        """fp32 master -> bf16 tensor-core copy (one cast kernel over the flat buffer), only when a parameter changed."""
         ver = sum(r.param._version for r in self.order)
         if not force and ver == self._versions:
             return False
-        dst, src = [], []
-        for r in self.order:
-            if r.wb_view is not None:
-                dst.append(r.wb_view); src.append(r.param.detach())
-            if r.wf_view is not None:
-                dst.append(r.wf_view); src.append(r.param.detach())
-        torch._foreach_copy_(dst, src)
+        ops.cast_flat(self.master, self.wb)
         self._versions = ver
         return True
 
@@ -180,10 +180,15 @@ class FlatParams:
         self.grad.zero_()
 
     def attach_grads(self):
-        """param.grad = view of the flat gradient buffer (kernel layout; permuted for 3x3 conv weights)."""
+        """param.grad = view of the flat gradient buffer (same strides as the re-homed parameter)."""
         for r in self.order:
             if r.param.requires_grad:
                 r.param.grad = r.gview
+
+    def owns(self, model) -> bool:
+        """True while every parameter still lives in the flat master buffer (a .to() / load of new tensors breaks it)."""
+        base = self.master.untyped_storage().data_ptr()
+        return all(r.param.data.untyped_storage().data_ptr() == base for r in self.order[:4] + self.order[-4:])
 
 
 class _Pool:
@@ -213,6 +218,7 @@ class TrainEngine:
         cfg = model.config
         self.heads, self.ctx_dim = cfg.attention_head_dim, cfg.cross_attention_dim
         self.fwd, self.bwd = [], []
+        self.ready_marks = []   # (number of backward entries executed, offset): flat.grad[offset:] is final
         self.saved_bytes = 0
         self._keep = []
         self._gi = {}      # id(activation) -> [grad buffer, initialised?]
@@ -300,7 +306,7 @@ class TrainEngine:
         te = m.time_embedding
         resnets = list(m._iter_resnets())
         tp_w = flat.span([r.time_emb_proj.weight for _, r in resnets], "wb")
-        tp_b = flat.span([r.time_emb_proj.bias for _, r in resnets], "wf")
+        tp_b = flat.span([r.time_emb_proj.bias for _, r in resnets], "master")
         n_tp = tp_w.shape[0]
         tp_off, o = {}, 0
         for prefix, r in resnets:
@@ -358,6 +364,8 @@ class TrainEngine:
                 # time-embedding gradient: per-image column sums of dh (conv1.bias gets the same sums, folded at the end)
                 dtp = self.d_tproj.view(-1)[tp_off[prefix]:]
                 Bp.append(lambda: ops.grad_prep(dh16, None, dtp, rows_per_image=hw, ldcs=n_tp))
+                if tw:   # conv1.bias is added at the same place as the time embedding: its gradient is the sum over images
+                    Bp.append(lambda: ops.grad_prep(dtp, None, self.G(r.conv1.bias), rows=N, N=cout, ld=n_tp))
                 self._wgrad(dh16, t1, self.G(r.conv1.weight), conv=(N, h, w))
                 dt1 = pool.get(M, cin)
                 self._dgrad(dh16, self.Wb(r.conv1.weight), dt1, conv=(N, h, w))
@@ -377,7 +385,7 @@ class TrainEngine:
                                                          dbeta=self.G(r.norm1.bias), eps=eps, silu=True))
                 pool.put(dt1, dy16 if dy16 is not dy else None, add if add is not dy else None)
 
-            blocks.append(backward)
+            blocks.append((backward, r.norm1.weight))
             return y
 
         def xformer(prefix, a, x, h, w):
@@ -500,7 +508,7 @@ class TrainEngine:
                                                          eps=1e-6, silu=False))
                 pool.put(dn)
 
-            blocks.append(backward)
+            blocks.append((backward, a.norm.weight))
             return y
 
         def downsample(ds, x, h, w):
@@ -520,7 +528,7 @@ class TrainEngine:
                 Bp.append(lambda: ops.col2im_s2(dcol, gx, N, h, w, accumulate=accx))
                 self.pool.put(dcol, dy16)
 
-            blocks.append(backward)
+            blocks.append((backward, ds.conv.weight))
             return y
 
         def upsample(us, x, h, w):
@@ -540,7 +548,7 @@ class TrainEngine:
                 Bp.append(lambda: ops.upsample2x_bwd(dup, gx, N, h, w, accumulate=accx))
                 self.pool.put(dup, dy16)
 
-            blocks.append(backward)
+            blocks.append((backward, us.conv.weight))
             return y
 
         # ---- forward graph ----
@@ -556,7 +564,7 @@ class TrainEngine:
             Bp.append(lambda: ops.conv_in_wgrad(g, self.in_sample, ci_w.g))
             Bp.append(lambda: ops.grad_prep(g, None, self.G(m.conv_in.bias)))
 
-        blocks.append(conv_in_backward)
+        blocks.append((conv_in_backward, m.conv_in.weight))
         x = x0
         skips = [x]
         for i, b in enumerate(m.down_blocks):
@@ -596,10 +604,15 @@ class TrainEngine:
                                                  dgamma=self.G(m.conv_norm_out.weight), dbeta=self.G(m.conv_norm_out.bias),
                                                  eps=eps, silu=True))
         self.pool.put(dt_out)
-        for bw in reversed(blocks):
+        if tw:
+            self.ready_marks.append((len(Bp), flat.reg(m.conv_norm_out.weight).off))
+        for bw, first_param in reversed(blocks):
             bw()
+            if tw:
+                self.ready_marks.append((len(Bp), flat.reg(first_param).off))
         if tw:
             self._time_mlp_backward(t_sin, t_h1, t_emb, tp_w, resnets, tp_off, n_tp)
+            self.ready_marks.append((len(Bp), 0))
 
     def _time_mlp_backward(self, t_sin, t_h1, t_emb, tp_w, resnets, tp_off, n_tp):
         """d_tproj [N, n_tp] (per-image sums of every resnet's dh) -> time_emb_proj / linear_2 / linear_1 gradients.
@@ -610,13 +623,7 @@ class TrainEngine:
         g_tpb = flat.span([r.time_emb_proj.bias for _, r in resnets], "grad")
         g_tpw = flat.span([r.time_emb_proj.weight for _, r in resnets], "grad")
         dtp16 = torch.empty(N, n_tp, dtype=BF16, device=dev)
-        self.d_tpb = torch.zeros(n_tp, dtype=F32, device=dev)   # this backward's column sums (zeroed per backward)
-        Bp.append(lambda: ops.grad_prep(self.d_tproj, dtp16, self.d_tpb))
-        Bp.append(lambda: g_tpb.add_(self.d_tpb))
-        # conv1.bias is added at the same place as time_emb_proj.bias: identical gradient
-        cb1 = [flat.reg(r.conv1.bias).g for _, r in resnets]
-        slices = [self.d_tpb[tp_off[p]:tp_off[p] + r.cout] for p, r in resnets]
-        Bp.append(lambda: torch._foreach_add_(cb1, slices))
+        Bp.append(lambda: ops.grad_prep(self.d_tproj, dtp16, g_tpb))
         a_emb = torch.empty(N, temb_dim, dtype=BF16, device=dev)
         Bp.append(lambda: ops.cast_act(t_emb, a_emb, silu=True))
         self._wgrad(dtp16, a_emb, g_tpw)
@@ -651,13 +658,19 @@ class TrainEngine:
                 op()
             return self.out.clone()
 
-    def run_backward(self, d_out):
-        """d_out (N, C, H, W) fp32 -> parameter gradients ACCUMULATED into flat.grad (and d_ctx when asked)."""
+    def run_backward(self, d_out, on_ready=None):
+        """d_out (N, C, H, W) fp32 -> parameter gradients ACCUMULATED into flat.grad (and d_ctx when asked).
+        on_ready(offset) is called whenever flat.grad[offset:] has become final (the backward completes the flat
+        buffer from its end towards its start), which is what a bucketed gradient allreduce overlaps on."""
         with torch.cuda.device(self.device):
             self.d_out.copy_(d_out)
             self.d_tproj.zero_()
-            if self.train_weights:
-                self.d_tpb.zero_()
-            for op in self.bwd:
+            marks = iter(self.ready_marks)
+            nxt = next(marks, None)
+            for i, op in enumerate(self.bwd):
                 op()
+                while nxt is not None and nxt[0] == i + 1:
+                    if on_ready is not None:
+                        on_ready(nxt[1])
+                    nxt = next(marks, None)
             return self.d_ctx.view(self.N, self.S, self.ctx_dim) if self.ctx_grad else None

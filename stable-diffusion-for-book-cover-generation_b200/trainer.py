@@ -1,0 +1,116 @@
+"""Data-parallel fine-tuning step of the UNet (BASELINE config 3; the loop body of finetune_sd.py:453-494, 569-570):
+
+    noisy = noise_scheduler.add_noise(latents, noise, timesteps)          finetune_sd.py:473-474
+    pred  = unet(noisy, timesteps, encoder_hidden_states).sample          finetune_sd.py:480-481
+    loss  = F.mse_loss(pred, noise, "none").mean([1,2,3]).mean()          finetune_sd.py:483-484
+    accelerator.backward(loss); optimizer.step(); optimizer.zero_grad()   finetune_sd.py:494, 569-570
+
+One process per GPU.  The backward kernels accumulate every parameter gradient into ONE flat fp32 buffer and
+complete it from its end towards its start; `BucketReducer` allreduces finished address ranges (NCCL over NVLink,
+SUM) while the rest of the backward is still running, and `FlatAdamW` does the whole optimizer step -- gradient
+averaging, AdamW, the bf16 re-cast of the weights and the zeroing of the gradients -- in one pass over the flat
+buffers.  Gradient accumulation (`sync=False` micro-steps, accelerate's no_sync, finetune_sd.py:454-458) simply
+skips the reduction: the kernels keep accumulating.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+from . import ops
+
+
+class BucketReducer:
+    """Allreduce of a flat gradient buffer in address ranges that become final back to front.
+
+    on_ready(offset) announces that flat[offset:] is final; whenever at least `bucket_bytes` are pending (or offset
+    reaches 0) the pending range is reduced asynchronously.  finish() waits for all of them."""
+
+    def __init__(self, flat: torch.Tensor, group=None, bucket_bytes: int = 64 << 20):
+        self.flat, self.group, self.bucket_bytes = flat, group, int(bucket_bytes)
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.esize = flat.element_size()
+        self.begin()
+
+    def begin(self):
+        self.hi = self.flat.numel()
+        self.works = []
+        self.ranges = []
+
+    def on_ready(self, offset: int):
+        if offset >= self.hi:
+            return
+        if (self.hi - offset) * self.esize >= self.bucket_bytes or offset == 0:
+            self._launch(offset, self.hi)
+            self.hi = offset
+
+    def _launch(self, a: int, b: int):
+        self.ranges.append((a, b))
+        if self.world > 1:
+            self.works.append(dist.all_reduce(self.flat[a:b], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+
+    def finish(self):
+        if self.hi > 0:
+            self._launch(0, self.hi)
+            self.hi = 0
+        for w in self.works:
+            w.wait()
+        self.works = []
+
+
+class FlatAdamW:
+    """torch.optim.AdamW semantics over train.FlatParams (one fused kernel per step)."""
+
+    def __init__(self, flat, lr=1e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2):
+        self.flat, self.lr, self.betas, self.eps, self.weight_decay = flat, lr, betas, eps, weight_decay
+        self.exp_avg = torch.zeros_like(flat.master)
+        self.exp_avg_sq = torch.zeros_like(flat.master)
+        self.steps = 0
+
+    def step(self, grad_scale=1.0, zero_grad=True):
+        self.steps += 1
+        f = self.flat
+        ops.adamw_step(f.master, f.grad, self.exp_avg, self.exp_avg_sq, f.wb, self.lr, self.betas[0], self.betas[1], self.eps,
+                       self.weight_decay, self.steps, grad_scale=grad_scale, zero_grad=zero_grad)
+        # the kernel wrote the bf16 copy itself: the version bookkeeping of refresh_weights() stays valid
+        return self
+
+
+class Trainer:
+    def __init__(self, unet, noise_scheduler, lr=1e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, group=None,
+                 bucket_bytes: int = 64 << 20):
+        self.unet, self.sched, self.group = unet.train(), noise_scheduler, group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.bucket_bytes = bucket_bytes
+        self.opt_args = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
+        unet.enable_direct_gradients()
+        self.reducer = None
+        self.opt = None
+
+    def _prepare(self, device):
+        from .autograd import ensure_flat
+        flat = ensure_flat(self.unet, device)
+        if self.reducer is None or self.reducer.flat is not flat.grad:
+            self.reducer = BucketReducer(flat.grad, self.group, self.bucket_bytes)
+            self.opt = FlatAdamW(flat, **self.opt_args)
+            flat.zero_grad()
+            flat.attach_grads()
+
+    def train_step(self, latents, noise, timesteps, encoder_hidden_states, sync=True):
+        """one micro-step; with sync=True (the default) also allreduce + optimizer step.  Returns the loss (0-d tensor)."""
+        unet = self.unet
+        self._prepare(latents.device)
+        reduce_now = sync and self.world > 1
+        if reduce_now:
+            self.reducer.begin()
+        unet._grad_ready_hook = self.reducer.on_ready if reduce_now else None
+        noisy = self.sched.add_noise(latents, noise, timesteps)
+        pred = unet(noisy, timesteps, encoder_hidden_states).sample
+        loss = ops.mse_loss(pred, noise)
+        loss.backward()
+        unet._grad_ready_hook = None
+        if sync:
+            if reduce_now:
+                self.reducer.finish()
+            self.opt.step(grad_scale=1.0 / self.world, zero_grad=True)
+        return loss.detach()

@@ -179,6 +179,7 @@ class UNet2DConditionModel(nn.Module):
         self._flat = None            # train.FlatParams (flat bf16 weights + flat fp32 gradients), built on first training call
         self._train_engines = {}
         self._direct_grads = False
+        self._grad_ready_hook = None   # direct mode: called with `offset` when flat_gradients()[offset:] is final (trainer.py)
 
     # -- init / (de)serialisation ---------------------------------------------------------------
     @torch.no_grad()

@@ -148,3 +148,64 @@ def test_sd15_unet_gradients_batch2():
     assert cos_all >= 0.9995, cos_all
     rel = float((c.grad - ref_dctx).abs().max() / ref_dctx.abs().max())
     assert rel <= 4e-2, f"context gradient max-rel {rel}"
+
+
+def test_flat_adamw_matches_torch_adamw():
+    """One fused kernel over the flat buffers == torch.optim.AdamW on the individual parameters (fp32, 3 steps)."""
+    from b200sd.train import FlatParams
+    from b200sd.trainer import FlatAdamW
+    from b200sd.unet import UNet2DConditionModel
+    from oracle.unet_ref import TINY_OVERRIDES
+    _setup()
+    torch.manual_seed(0)
+    ours = UNet2DConditionModel(**TINY_OVERRIDES).to(DEV)
+    ref_params = [p.detach().clone().requires_grad_(True) for p in ours.parameters()]
+    flat = FlatParams(ours, torch.device(DEV))
+    flat.attach_grads()
+    opt = FlatAdamW(flat, lr=1e-3, betas=(0.9, 0.99), eps=1e-8, weight_decay=0.1)
+    ref = torch.optim.AdamW(ref_params, lr=1e-3, betas=(0.9, 0.99), eps=1e-8, weight_decay=0.1)
+    for step in range(3):
+        for p, q in zip(ours.parameters(), ref_params):
+            g = torch.randn_like(q)
+            q.grad = g
+            p.grad.copy_(g * 2)             # the fused step averages a SUM over 2 ranks
+        opt.step(grad_scale=0.5, zero_grad=True)
+        ref.step()
+    assert float(flat.grad.abs().max()) == 0.0
+    for (n, p), q in zip(ours.named_parameters(), ref_params):
+        err = float((p.detach() - q.detach()).abs().max())
+        assert err <= 2e-6 * (1 + float(q.abs().max())), (n, err)
+    assert torch.equal(flat.wb, flat.master.bfloat16())
+
+
+def test_trainer_steps_reduce_the_loss():
+    """finetune_sd.py:453-494 loop body through b200sd.trainer.Trainer on one GPU: a fixed batch is (over)fitted."""
+    from b200sd.schedulers import DDPMScheduler
+    from b200sd.trainer import Trainer
+    from b200sd.unet import UNet2DConditionModel
+    from oracle.unet_ref import TINY_OVERRIDES
+    _setup()
+    torch.manual_seed(0)
+    unet = UNet2DConditionModel(**TINY_OVERRIDES).to(DEV)
+    sched = DDPMScheduler(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear", num_train_timesteps=1000)
+    tr = Trainer(unet, sched, lr=2e-4, weight_decay=0.0)
+    x, noise, ctx, t = _inputs(4, 32, 32, 64, 5)
+    before = unet.conv_out.weight.detach().clone()
+    losses = [float(tr.train_step(x, noise, t, ctx)) for _ in range(12)]
+    assert losses[-1] < 0.7 * losses[0], losses
+    assert not torch.equal(before, unet.conv_out.weight.detach())
+    # gradient accumulation: two sync=False micro-steps + one sync step == one step on the 3x gradient
+    g0 = unet.flat_gradients()
+    assert float(g0.abs().max()) == 0.0
+    tr.train_step(x, noise, t, ctx, sync=False)
+    g1 = g0.clone()
+    tr.train_step(x, noise, t, ctx, sync=False)
+    assert torch.allclose(g0, 2 * g1, rtol=1e-3, atol=1e-6 * float(g1.abs().max()))
+    # the inference engine picks the updated weights up (eval forward == training forward on the same weights)
+    unet.eval()
+    with torch.no_grad():
+        a = unet(x, t, ctx).sample
+    unet.train()
+    b = unet(x, t, ctx).sample.detach()
+    rel = float((a - b).abs().max() / b.abs().max())
+    assert rel <= 2e-2, rel

@@ -1,0 +1,115 @@
+"""CPU tests of the training path's host logic: the flat kernel-layout parameter state (re-homing keeps the
+diffusers state-dict surface intact) and the bucketed gradient allreduce over a 2-rank gloo group
+(the N>1 path of BASELINE config 3; NCCL on the GPU box, gloo here)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _tiny():
+    from b200sd.unet import UNet2DConditionModel
+    from oracle.unet_ref import TINY_OVERRIDES
+    torch.manual_seed(0)
+    return UNet2DConditionModel(**TINY_OVERRIDES)
+
+
+def test_flat_params_rehoming_keeps_the_module_surface():
+    from b200sd.train import FlatParams
+    m = _tiny()
+    before = {k: v.clone() for k, v in m.state_dict().items()}
+    n_params = sum(p.numel() for p in m.parameters())
+    flat = FlatParams(m, torch.device("cpu"))
+    assert flat.total >= n_params and flat.total % 64 == 0
+    assert flat.owns(m)
+    after = m.state_dict()
+    assert list(after) == list(before)
+    for k in before:
+        assert after[k].shape == before[k].shape and torch.equal(after[k], before[k]), k
+    # every parameter is a view of the ONE master buffer; 3x3 conv weights are stored [Cout][ky][kx][Cin]
+    base = flat.master.untyped_storage().data_ptr()
+    assert all(p.data.untyped_storage().data_ptr() == base for p in m.parameters())
+    w = m.down_blocks[0].resnets[0].conv1.weight
+    r = flat.reg(w)
+    assert torch.equal(flat.master[r.off:r.off + r.numel].view(w.shape[0], 3, 3, w.shape[1]), w.detach().permute(0, 2, 3, 1))
+    # fused regions are adjacent
+    a = m.down_blocks[0].attentions[0].transformer_blocks[0].attn1
+    qkv = flat.span([a.to_q.weight, a.to_k.weight, a.to_v.weight], "master")
+    assert torch.equal(qkv, torch.cat([a.to_q.weight, a.to_k.weight, a.to_v.weight]).detach())
+    tp = flat.span([r_.time_emb_proj.bias for _, r_ in m._iter_resnets()], "master")
+    assert torch.equal(tp, torch.cat([r_.time_emb_proj.bias for _, r_ in m._iter_resnets()]).detach())
+    # gradients: views of the flat buffer with the parameter's own strides; an in-place optimizer update
+    # of the re-homed parameter lands in the master buffer
+    flat.attach_grads()
+    assert w.grad.shape == w.shape and w.grad.stride() == w.stride()
+    flat.grad.fill_(1.0)
+    opt = torch.optim.SGD(m.parameters(), lr=0.5)
+    opt.step()
+    assert torch.allclose(flat.master[r.off:r.off + r.numel], (before["down_blocks.0.resnets.0.conv1.weight"] - 0.5)
+                          .permute(0, 2, 3, 1).reshape(-1))
+    # load_state_dict writes through the views
+    m.load_state_dict(before)
+    assert flat.owns(m) and torch.equal(m.state_dict()["conv_out.weight"], before["conv_out.weight"])
+    # layout order = forward execution order (the backward completes the buffer back to front)
+    offs = [flat.reg(p).off for p in (m.time_embedding.linear_1.weight, m.conv_in.weight, m.down_blocks[0].resnets[0].norm1.weight,
+                                      m.down_blocks[0].attentions[0].norm.weight, m.down_blocks[0].resnets[1].norm1.weight,
+                                      m.mid_block.resnets[0].norm1.weight, m.up_blocks[3].attentions[2].proj_out.bias,
+                                      m.conv_norm_out.weight, m.conv_out.bias)]
+    assert offs == sorted(offs) and offs[0] == 0
+
+
+def test_bucket_reducer_single_process_ranges():
+    from b200sd.trainer import BucketReducer
+    flat = torch.ones(1000)
+    r = BucketReducer(flat, bucket_bytes=1000)      # 250 floats per bucket
+    for off in (900, 800, 650, 640, 300, 0):
+        r.on_ready(off)
+    r.finish()
+    assert r.ranges == [(650, 1000), (300, 650), (0, 300)]
+    r.begin()
+    r.on_ready(990)
+    r.finish()                                       # the tail is flushed by finish()
+    assert r.ranges == [(0, 1000)]
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from b200sd.trainer import BucketReducer
+        flat = torch.arange(1000, dtype=torch.float32) * (rank + 1)
+        red = BucketReducer(flat, bucket_bytes=1200)
+        for off in (700, 500, 200, 0):
+            red.on_ready(off)
+        red.finish()
+        want = torch.arange(1000, dtype=torch.float32) * sum(range(1, world + 1))
+        q.put((rank, bool(torch.equal(flat, want)), red.ranges))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_bucket_reducer_two_ranks_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, ok, ranges in res:
+        assert ok, f"rank {rank}: allreduce result wrong"
+        assert ranges == [(700, 1000), (200, 700), (0, 200)]
