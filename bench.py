@@ -418,6 +418,99 @@ def run_train(args):
         dist.destroy_process_group()
 
 
+# ---------------------------------------------------------------------------------------------------
+# text-encoder fine-tuning (BASELINE config 4): UNet frozen (our forward + dgrad-only backward down to the context),
+# CLIP text encoder = stock transformers / torch (a neighbour of the hot path), DDP over NCCL
+# ---------------------------------------------------------------------------------------------------
+def run_train_text(args):
+    import torch
+    import torch.distributed as dist
+    from transformers import CLIPTextConfig, CLIPTextModel
+    from b200sd import ops
+    from b200sd.schedulers import DDPMScheduler
+    from b200sd.unet import UNet2DConditionModel
+
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.batch if args.batch > 1 else 8
+    torch.manual_seed(0)
+    unet = UNet2DConditionModel().to(dev).eval().requires_grad_(False)            # finetune_sd.py:391-395
+    clip = CLIPTextModel(CLIPTextConfig(hidden_size=768, intermediate_size=3072, num_hidden_layers=12, num_attention_heads=12,
+                                        vocab_size=49408, max_position_embeddings=77, hidden_act="quick_gelu")).to(dev).train()
+    model = torch.nn.parallel.DistributedDataParallel(clip, device_ids=[local]) if world > 1 else clip
+    opt = torch.optim.AdamW(clip.parameters(), lr=1e-5, weight_decay=1e-2, fused=True)
+    sched = DDPMScheduler(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear", num_train_timesteps=1000)
+    g = torch.Generator().manual_seed(1000 + rank)
+    host = dict(x0=torch.randn(B, 4, 64, 64, generator=g).pin_memory(), noise=torch.randn(B, 4, 64, 64, generator=g).pin_memory(),
+                t=torch.randint(0, 1000, (B,), generator=g).pin_memory(), ids=torch.randint(0, 49408, (B, 77), generator=g).pin_memory())
+    d = {k: v.to(dev) for k, v in host.items()}
+
+    def step(b):
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            ctx = model(b["ids"])[0]                                                # finetune_sd.py:477
+        noisy = sched.add_noise(b["x0"], b["noise"], b["t"])
+        loss = ops.mse_loss(unet(noisy, b["t"], ctx.float()).sample, b["noise"])
+        loss.backward()
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+        return loss.detach()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step(d)
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = ops.launch_count()
+    e0.record()
+    for _ in range(args.steps):
+        step(d)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if sampler else None
+    launches = ops.launch_count() - l0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        loss_val = float(step({k: v.to(dev, non_blocking=True) for k, v in host.items()}))
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    if world > 1:
+        tt = torch.tensor([ms, e2e_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms, e2e_ms = float(tt[0]), float(tt[1])
+    if rank == 0:
+        hbm, tf_burst, tf_sus, which = _peaks()
+        samples = B * args.steps * world
+        step_ms = ms / args.steps
+        flops_step = 2 * B * FLOPS_PER_SAMPLE_64          # UNet fwd + dgrad (CLIP ~0.3 % on top)
+        achieved = flops_step / (step_ms * 1e-3) / 1e12
+        print(json.dumps({
+            "metric": "text_encoder_finetune_samples_per_s", "value": samples / (ms * 1e-3), "unit": "samples/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "sd15_text_encoder_finetune_512px", "batch_per_gpu": B, "latent": "4x64x64", "tokens": 77,
+                       "step": "CLIP fwd (torch) + add_noise + frozen UNet fwd + MSE + UNet dgrad-only bwd -> d ctx + CLIP bwd (torch) + DDP allreduce + AdamW",
+                       "last_loss": loss_val},
+            "e2e": {"value": samples / (e2e_ms * 1e-3), "unit": "samples/s",
+                    "h2d_bytes_per_step": int(sum(v.numel() * v.element_size() for v in host.values())), "d2h_bytes_per_step": 4},
+            "gpu_launches": int(launches), "clocks": clocks,
+            "roofline": {"bound": "tensor", "kernel": "whole step (UNet forward + data-gradient backward)", "achieved": achieved,
+                         "peak": tf_sus, "unit": "TFLOP/s", "frac": achieved / tf_sus, "peak_kind": f"bf16 sustained, {which}",
+                         "flops_per_step": flops_step, "traffic": None}}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -426,17 +519,17 @@ def main():
     ap.add_argument("--batch", type=int, default=1, help="images per GPU (UNet batch = 2x with CFG)")
     ap.add_argument("--portrait", action="store_true", help="512x768 book-cover geometry (config 5)")
     ap.add_argument("--impl", default="b200sd", choices=["b200sd", "reference"])
-    ap.add_argument("--workload", default="sample", choices=["sample", "train"],
+    ap.add_argument("--workload", default="sample", choices=["sample", "train", "train_text"],
                     help="sample = 50-step DDIM + CFG denoising (BASELINE configs[1], the headline); train = fine-tuning step (configs[2])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--dump-ops", default=None, help="write the per-launch timing table to this file")
     args = ap.parse_args()
-    if args.workload == "train":
+    if args.workload in ("train", "train_text"):
         if args.impl != "reference" and args.gpus > 1 and "RANK" not in os.environ:
             cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                    "--master-addr", "127.0.0.1", "--master-port", "29532", os.path.abspath(__file__)] + sys.argv[1:]
             raise SystemExit(subprocess.call(cmd))
-        run_train(args)
+        run_train_text(args) if args.workload == "train_text" and args.impl != "reference" else run_train(args)
     elif args.impl == "reference":
         run_reference(args)
     else:
