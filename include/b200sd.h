@@ -138,6 +138,7 @@ typedef struct b200sd_gemm_args {
     int split_k;           /* 0 = auto */
     void* workspace;       /* split-K scratch (may be NULL when split_k == 1) */
     size_t workspace_bytes;
+    int pair;              /* CTA pairs (tcgen05 cta_group::2, 256-row MMA tiles): 0 = auto, 1 = on, -1 = off */
 } b200sd_gemm_args;
 
 size_t b200sd_gemm_workspace_bytes(void);
@@ -165,6 +166,7 @@ typedef struct b200sd_dgrad_args {
     int ldy, ldc, ldr;    /* 0 = dense */
     int out_dtype, residual_dtype;
     int block_n;          /* 0 = auto (64 / 128 / 192 / 256) */
+    int pair;             /* CTA pairs: 0 = auto, 1 = on, -1 = off */
 } b200sd_dgrad_args;
 int b200sd_gemm_dgrad(const b200sd_dgrad_args* args, b200sd_stream_t stream);
 

@@ -23,7 +23,7 @@ class GemmArgs(C.Structure):
         ("lda0", C.c_int), ("lda1", C.c_int), ("ldc", C.c_int), ("ldr", C.c_int), ("ldrb", C.c_int), ("conv_taps", C.c_int),
         ("batch", C.c_int), ("H", C.c_int), ("W", C.c_int), ("rows_per_image", C.c_int), ("epilogue", C.c_int),
         ("out_dtype", C.c_int), ("residual_dtype", C.c_int), ("block_n", C.c_int), ("split_k", C.c_int),
-        ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t), ("pair", C.c_int),
     ]
 
 
@@ -32,7 +32,7 @@ class DgradArgs(C.Structure):
         ("dy", C.c_void_p), ("w", C.c_void_p), ("residual", C.c_void_p), ("out", C.c_void_p),
         ("M", C.c_int), ("Cout", C.c_int), ("Cin", C.c_int), ("conv_taps", C.c_int),
         ("batch", C.c_int), ("H", C.c_int), ("W", C.c_int), ("ldy", C.c_int), ("ldc", C.c_int), ("ldr", C.c_int),
-        ("out_dtype", C.c_int), ("residual_dtype", C.c_int), ("block_n", C.c_int),
+        ("out_dtype", C.c_int), ("residual_dtype", C.c_int), ("block_n", C.c_int), ("pair", C.c_int),
     ]
 
 

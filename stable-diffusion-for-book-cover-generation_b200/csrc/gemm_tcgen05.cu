@@ -79,6 +79,8 @@ struct KParams {
     int n_valid;         // output columns that exist (tiles may overhang when block_n does not divide N)
     int tiles_per_tap;   // conv wgrad: n-tiles per tap (output column = tap * n_valid + c)
     int atomic_out;      // fp32 red.add into `out` (wgrad: split-K partials and gradient accumulation)
+    int pair;            // CTA pair (cta_group::2): two CTAs adjacent in M form one 256 x block_n MMA tile; each loads its own
+                         // 128 A rows and HALF of the B tile, so the L2 -> smem traffic per FLOP drops by ~1/3
     unsigned long long* trace;  // optional [ctas][8] globaltimer stamps (debug)
 };
 
@@ -103,11 +105,96 @@ __device__ __forceinline__ void red_add_v4(float* dst, float a, float b, float c
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
+// ---- store phase of the epilogue: one thread = one 8-column group, walking down the rows of the staging tile ----
+struct EpiCtx {
+    uint32_t stage_u32;
+    int pitch_f, row_end, R, cb, half, m0, col_out, img0, n0cb;
+    const float* s_rb;
+    bool multi_img, rb_smem;
+};
+__device__ __forceinline__ void lds8(uint32_t addr, float (&v)[8]) {
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(addr));
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "r"(addr + 16));
+}
+// OUT: 0 bf16, 1 fp32, 2 fp32 red.add;  RES: 0 none, 1 bf16, 2 fp32;  SPLIT: sum the cluster's partial tiles over DSMEM
+template <int OUT, int RES, bool SPLIT, bool GEGLU>
+__device__ __forceinline__ void epilogue_rows(const KParams& p, const EpiCtx& e, int row0, const float (&b)[8], const float (&bg)[8]) {
+    constexpr int U = 4;
+    for (int row = row0; row < e.row_end; row += e.R * U) {
+        float v[U][8], r[U][8];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int rl = min(row + u * e.R, e.row_end - 1);   // clamped: loads of a masked-off row stay in bounds
+            const uint32_t addr = e.stage_u32 + (uint32_t)(rl * e.pitch_f + e.cb) * 4u;
+            if constexpr (SPLIT) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[u][i] = 0.f;
+                for (int sp = 0; sp < p.split_k; ++sp) {
+                    const float4 a0 = ld_dsmem_v4(addr, sp), a1 = ld_dsmem_v4(addr + 16, sp);
+                    v[u][0] += a0.x; v[u][1] += a0.y; v[u][2] += a0.z; v[u][3] += a0.w;
+                    v[u][4] += a1.x; v[u][5] += a1.y; v[u][6] += a1.z; v[u][7] += a1.w;
+                }
+            } else {
+                lds8(addr, v[u]);
+            }
+            if constexpr (GEGLU) lds8(addr + (uint32_t)e.half * 4u, r[u]);
+            else if constexpr (RES == 2) ld8<B200SD_F32>(p.residual, (size_t)(e.m0 + rl) * p.ldr + e.col_out, r[u]);
+            else if constexpr (RES == 1) ld8<B200SD_BF16>(p.residual, (size_t)(e.m0 + rl) * p.ldr + e.col_out, r[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int rl = row + u * e.R;
+            if (rl >= e.row_end) break;
+            const int grow = e.m0 + rl;
+            float o[8];
+            if constexpr (GEGLU) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) o[i] = (v[u][i] + b[i]) * gelu_erf_f(r[u][i] + bg[i]);
+                st8<B200SD_BF16>(p.out, (size_t)grow * p.ldc + e.col_out, o);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) o[i] = v[u][i] + b[i];
+                if constexpr (RES != 0) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) o[i] += r[u][i];
+                }
+                if (e.multi_img) {   // tile spans several images (8x8 / 4x4 levels): per-row time-embedding bias
+                    const int img = grow / p.rows_per_image;
+                    if (e.rb_smem) {
+                        const float* rb = e.s_rb + (img == e.img0 ? 0 : 256) + e.cb;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) o[i] += rb[i];
+                    } else {
+                        float t[8];
+                        ld8<B200SD_F32>(p.rowbias, (size_t)img * p.ldrb + e.n0cb, t);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) o[i] += t[i];
+                    }
+                }
+                if constexpr (OUT == 2) {
+                    float* dst = static_cast<float*>(p.out) + (size_t)grow * p.ldc + e.col_out;
+                    red_add_v4(dst, o[0], o[1], o[2], o[3]);
+                    red_add_v4(dst + 4, o[4], o[5], o[6], o[7]);
+                } else if constexpr (OUT == 1) st8<B200SD_F32>(p.out, (size_t)grow * p.ldc + e.col_out, o);
+                else st8<B200SD_BF16>(p.out, (size_t)grow * p.ldc + e.col_out, o);
+            }
+        }
+    }
+}
+
+// PAIR is a compile-time switch: a kernel that contains cta_group::2 instructions can only be launched as CTA pairs
+// OP selects the operand modes at compile time (0 forward: both K-major; 1 dgrad: B = weights MN-major; 2 / 3 wgrad
+// plain / conv3x3: A and B MN-major), so the forward instantiation carries none of the backward's branches.
+template <bool PAIR, int OP>
 __global__ void __launch_bounds__(kNumThreads, 1) gemm_tcgen05_kernel(const __grid_constant__ KParams p) {
+    constexpr bool a_mn = OP >= 2;
+    constexpr int b_mode = OP;
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte alignment for the 128B swizzle atoms
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const int b_bytes = p.block_n * BLOCK_K * 2;
+    constexpr bool pair = PAIR;
+    const uint32_t crank = pair ? cluster_ctarank() : 0;          // pair = cluster (2,1,1): rank 0 is the MMA leader
+    const int b_bytes = (p.block_n * BLOCK_K * 2) >> (pair ? 1 : 0);   // B bytes held by THIS CTA per stage
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + (size_t)p.stages * kABytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + (size_t)p.stages * b_bytes);
@@ -124,8 +211,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tcgen05_kernel(const __gr
     const int kb_begin = split * p.kb_per_split;
     const int kb_end = min(kb_begin + p.kb_per_split, p.num_k_blocks);
     // conv wgrad: the N axis is (tap, input channel); a tile never straddles taps
-    const int w_tap = p.b_mode == 3 ? n_tile / p.tiles_per_tap : 0;
-    const int n0 = (p.b_mode == 3 ? n_tile - w_tap * p.tiles_per_tap : n_tile) * p.block_n;   // column within the (per-tap) N axis
+    const int w_tap = b_mode == 3 ? n_tile / p.tiles_per_tap : 0;
+    const int n0 = (b_mode == 3 ? n_tile - w_tap * p.tiles_per_tap : n_tile) * p.block_n;   // column within the (per-tap) N axis
     const int col_base = w_tap * p.n_valid + n0;                                             // output column of tile column 0
     const int col_valid = min(p.block_n, p.n_valid - n0);
     const int m0 = m_tile * p.rows_valid;
@@ -144,11 +231,12 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tcgen05_kernel(const __gr
         ptx::fence_barrier_init();
     }
     if (warp == 1) {
-        ptx::tmem_alloc(tmem_slot, p.tmem_cols);
-        ptx::tmem_relinquish();
+        if constexpr (pair) { ptx::tmem_alloc_cg2(tmem_slot, p.tmem_cols); ptx::tmem_relinquish_cg2(); }
+        else { ptx::tmem_alloc(tmem_slot, p.tmem_cols); ptx::tmem_relinquish(); }
     }
     ptx::tc_fence_before();
     __syncthreads();
+    if constexpr (pair) cluster_sync_all();   // the peer's barriers must be initialised before anything is signalled on them
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     ptx::pdl_wait();  // everything above overlapped the previous kernel's tail
@@ -162,7 +250,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tcgen05_kernel(const __gr
     float* s_rb = s_bias + 256;                            // [2][256] row-bias of the (at most two) images of this tile
     int img0 = 0, img1 = 0;
     bool rb_smem = false;
-    if (p.rowbias) {
+    if (p.rowbias && m0 < p.M) {
         img0 = m0 / p.rows_per_image;
         img1 = (min(m0 + p.rows_valid, p.M) - 1) / p.rows_per_image;
         rb_smem = (img1 - img0) <= 1;
@@ -178,63 +266,68 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tcgen05_kernel(const __gr
                 if (p.tile_n > 1) { img = m_tile * p.tile_n; y0 = 0; }
                 else { img = m_tile / p.tiles_y; y0 = (m_tile % p.tiles_y) * p.tile_h; }
             }
-            const int nboxb = p.block_n >> 6;   // 64-column boxes of an MN-major B tile
+            // pair mode: this CTA loads its own A rows and half of the B tile; completion is signalled on the leader's barrier
+            const int nboxb = (p.block_n >> 6) >> (pair ? 1 : 0);   // 64-column boxes of an MN-major B tile held by this CTA
+            const int nb0 = n0 + (pair ? (int)crank * (p.block_n >> 1) : 0);
+            const uint32_t stage_tx = (uint32_t)(p.a_bytes + b_bytes) << (pair ? 1 : 0);
             for (int kb = kb_begin; kb < kb_end; ++kb) {
                 ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-                ptx::mbar_expect_tx(&full_bar[stage], (uint32_t)(p.a_bytes + b_bytes));
+                if (!pair || crank == 0) ptx::mbar_expect_tx(&full_bar[stage], stage_tx);
                 uint8_t* dst_a = smem_a + (size_t)stage * kABytes;
                 uint8_t* dst_b = smem_b + (size_t)stage * b_bytes;
+                uint64_t* fb = &full_bar[stage];
+                const uint32_t fbc = pair ? ptx::mapa_u32(ptx::smem_u32(fb), 0) : 0;
+#define LD2(dst, tm, c0, c1) do { if constexpr (pair) ptx::tma_load_2d_cg2(dst, tm, fbc, c0, c1); else ptx::tma_load_2d(dst, tm, fb, c0, c1); } while (0)
+#define LD3(dst, tm, c0, c1, c2) do { if constexpr (pair) ptx::tma_load_3d_cg2(dst, tm, fbc, c0, c1, c2); else ptx::tma_load_3d(dst, tm, fb, c0, c1, c2); } while (0)
+#define LD4(dst, tm, c0, c1, c2, c3) do { if constexpr (pair) ptx::tma_load_4d_cg2(dst, tm, fbc, c0, c1, c2, c3); else ptx::tma_load_4d(dst, tm, fb, c0, c1, c2, c3); } while (0)
                 // ---- A ----
-                if (p.a_mn) {
-                    ptx::tma_load_2d(dst_a, &p.tmA0, &full_bar[stage], m0, kb * BLOCK_K);
-                    ptx::tma_load_2d(dst_a + kABytes / 2, &p.tmA0, &full_bar[stage], m0 + 64, kb * BLOCK_K);
+                if (a_mn) {
+                    LD2(dst_a, &p.tmA0, m0, kb * BLOCK_K);
+                    LD2(dst_a + kABytes / 2, &p.tmA0, m0 + 64, kb * BLOCK_K);
                 } else if (!p.conv) {
-                    if (kb < p.cblocks0) ptx::tma_load_2d(dst_a, &p.tmA0, &full_bar[stage], kb * BLOCK_K, m0);
-                    else ptx::tma_load_2d(dst_a, &p.tmA1, &full_bar[stage], (kb - p.cblocks0) * BLOCK_K, m0);
+                    if (kb < p.cblocks0) LD2(dst_a, &p.tmA0, kb * BLOCK_K, m0);
+                    else LD2(dst_a, &p.tmA1, (kb - p.cblocks0) * BLOCK_K, m0);
                 } else {
                     const int tap = kb / p.cblocks;
                     const int cb = kb - tap * p.cblocks;
                     const int dy = (tap / 3 - 1) * p.conv_sign, dx = (tap % 3 - 1) * p.conv_sign;
-                    if (cb < p.cblocks0)
-                        ptx::tma_load_4d(dst_a, &p.tmA0, &full_bar[stage], cb * BLOCK_K, dx, y0 + dy, img);
-                    else
-                        ptx::tma_load_4d(dst_a, &p.tmA1, &full_bar[stage], (cb - p.cblocks0) * BLOCK_K, dx, y0 + dy, img);
+                    if (cb < p.cblocks0) LD4(dst_a, &p.tmA0, cb * BLOCK_K, dx, y0 + dy, img);
+                    else LD4(dst_a, &p.tmA1, (cb - p.cblocks0) * BLOCK_K, dx, y0 + dy, img);
                 }
                 // ---- B ----
-                if (p.b_mode == 0) {
-                    ptx::tma_load_2d(dst_b, &p.tmB, &full_bar[stage], kb * BLOCK_K, n0);
-                } else if (p.b_mode == 1) {
+                if (b_mode == 0) {
+                    LD2(dst_b, &p.tmB, kb * BLOCK_K, nb0);
+                } else if (b_mode == 1) {
                     if (!p.conv) {
-                        for (int j = 0; j < nboxb; ++j)
-                            ptx::tma_load_2d(dst_b + j * 8192, &p.tmB, &full_bar[stage], n0 + j * 64, kb * BLOCK_K);
+                        for (int j = 0; j < nboxb; ++j) LD2(dst_b + j * 8192, &p.tmB, nb0 + j * 64, kb * BLOCK_K);
                     } else {
                         const int tap = kb / p.cblocks;
                         const int cb = kb - tap * p.cblocks;
-                        for (int j = 0; j < nboxb; ++j)
-                            ptx::tma_load_3d(dst_b + j * 8192, &p.tmB, &full_bar[stage], n0 + j * 64, tap, cb * BLOCK_K);
+                        for (int j = 0; j < nboxb; ++j) LD3(dst_b + j * 8192, &p.tmB, nb0 + j * 64, tap, cb * BLOCK_K);
                     }
-                } else if (p.b_mode == 2) {
-                    for (int j = 0; j < nboxb; ++j)
-                        ptx::tma_load_2d(dst_b + j * 8192, &p.tmB, &full_bar[stage], n0 + j * 64, kb * BLOCK_K);
+                } else if (b_mode == 2) {
+                    for (int j = 0; j < nboxb; ++j) LD2(dst_b + j * 8192, &p.tmB, nb0 + j * 64, kb * BLOCK_K);
                 } else {
                     // conv wgrad: k-block kb = 64 pixels = box (64 ch, W, tile_h, tile_n) shifted by the tap
                     int bimg, by0;
                     if (p.tile_n > 1) { bimg = kb * p.tile_n; by0 = 0; }
                     else { bimg = kb / p.tiles_y; by0 = (kb - bimg * p.tiles_y) * p.tile_h; }
                     const int dy = w_tap / 3 - 1, dx = w_tap % 3 - 1;
-                    for (int j = 0; j < nboxb; ++j)
-                        ptx::tma_load_4d(dst_b + j * 8192, &p.tmB, &full_bar[stage], n0 + j * 64, dx, by0 + dy, bimg);
+                    for (int j = 0; j < nboxb; ++j) LD4(dst_b + j * 8192, &p.tmB, nb0 + j * 64, dx, by0 + dy, bimg);
                 }
+#undef LD2
+#undef LD3
+#undef LD4
                 if (++stage == p.stages) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
         // ================= MMA issuer (one elected thread) =================
-        if (ptx::elect_one()) {
-            const uint32_t b_mn = p.b_mode != 0;
-            const uint32_t idesc = ptx::umma_idesc_bf16(BLOCK_M, (uint32_t)p.block_n) | ((uint32_t)p.a_mn << 15) | (b_mn << 16);
+        if ((!pair || crank == 0) && ptx::elect_one()) {
+            const uint32_t b_mn = b_mode != 0;
+            const uint32_t idesc = ptx::umma_idesc_bf16(pair ? 2 * BLOCK_M : BLOCK_M, (uint32_t)p.block_n) | ((uint32_t)a_mn << 15) | (b_mn << 16);
             // K-major: +32 B per UMMA_K inside the swizzle atom; MN-major: 16 k-rows = two 1024-byte atoms further
-            const uint32_t a_step = p.a_mn ? (2048 >> 4) : 2, b_step = b_mn ? (2048 >> 4) : 2;
+            const uint32_t a_step = a_mn ? (2048 >> 4) : 2, b_step = b_mn ? (2048 >> 4) : 2;
             int stage = 0;
             uint32_t phase = 0;
             for (int kb = kb_begin; kb < kb_end; ++kb) {
@@ -242,16 +335,19 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tcgen05_kernel(const __gr
                 ptx::tc_fence_after();
                 if (kb == kb_begin) TRACE(2);
                 const uint32_t sa = ptx::smem_u32(smem_a + (size_t)stage * kABytes), sb = ptx::smem_u32(smem_b + (size_t)stage * b_bytes);
-                const uint64_t da = p.a_mn ? ptx::umma_desc_mn_sw128(sa, 8192) : ptx::umma_desc_k_sw128(sa);
+                const uint64_t da = a_mn ? ptx::umma_desc_mn_sw128(sa, 8192) : ptx::umma_desc_k_sw128(sa);
                 const uint64_t db = b_mn ? ptx::umma_desc_mn_sw128(sb, 8192) : ptx::umma_desc_k_sw128(sb);
 #pragma unroll
                 for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-                    ptx::umma_bf16_ss(tmem_base, da + a_step * k, db + b_step * k, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
+                    const uint32_t accum = (kb > kb_begin || k > 0) ? 1u : 0u;
+                    if constexpr (pair) ptx::umma_bf16_ss_cg2(tmem_base, da + a_step * k, db + b_step * k, idesc, accum);
+                    else ptx::umma_bf16_ss(tmem_base, da + a_step * k, db + b_step * k, idesc, accum);
                 }
-                ptx::umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+                // frees the smem slot (of both CTAs in pair mode) when these MMAs retire
+                if constexpr (pair) ptx::umma_commit_cg2(&empty_bar[stage], 3); else ptx::umma_commit(&empty_bar[stage]);
                 if (++stage == p.stages) { stage = 0; phase ^= 1; }
             }
-            ptx::umma_commit(tmem_full_bar);
+            if constexpr (pair) ptx::umma_commit_cg2(tmem_full_bar, 3); else ptx::umma_commit(tmem_full_bar);
             TRACE(3);
         }
     } else {
@@ -297,102 +393,54 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tcgen05_kernel(const __gr
     }
 
     // Split-K: the `split_k` CTAs of a tile form one thread-block cluster; after this barrier every CTA can
-    // read its peers' staging tiles through distributed shared memory.
-    if (p.split_k > 1) cluster_sync_all();
+    // read its peers' staging tiles through distributed shared memory.  Otherwise a CTA barrier: ALL warps
+    // (the producer and MMA warps are done by now) take part in the store phase.
+    if (p.split_k > 1) cluster_sync_all(); else __syncthreads();
 
-    if (warp >= 2) {
+    {
         // ================= epilogue, part 2: reduce (split-K) + fused epilogue + coalesced stores =================
-        // The 128 epilogue threads walk (row, 8-column group) items with consecutive threads on consecutive
-        // 16/32-byte vectors of a row.  With split-K each CTA of the cluster owns 128/split_k rows of the tile and
-        // sums the split partials in a fixed order (deterministic).  Loads of a batch are issued before any
-        // store so that (possibly aliasing, in-place) residual reads are not serialised behind the stores.
+        // Every thread owns ONE 8-column group of the tile and walks down the rows (R rows per pass, U passes in
+        // flight): no index arithmetic in the loop, bias in registers, consecutive threads on consecutive 16/32-byte
+        // vectors of a row.  With split-K each CTA of the cluster owns 128/split_k rows and sums the split partials
+        // in a fixed order (deterministic).  Loads of a batch are issued before any store so that (possibly
+        // aliasing, in-place) residual reads are not serialised behind the stores.
         const int rank = p.split_k > 1 ? (int)cluster_ctarank() : 0;
         const int rows_per_cta = BLOCK_M / p.split_k;
         const int row_begin = rank * rows_per_cta;
         int valid = min(p.rows_valid, p.M - m0) - row_begin;
         valid = max(0, min(valid, rows_per_cta));
-        const uint32_t stage_u32 = ptx::smem_u32(stage);
         const bool geglu = p.epilogue == B200SD_EPI_GEGLU;
         const int half = p.block_n / 2;
         const int groups = (geglu ? half : p.block_n) / 8;
-        const int items = valid * groups;
-        const uint32_t ginv = ((1u << 20) + groups - 1) / groups;  // idx / groups == (idx * ginv) >> 20 for idx < 4160
-        constexpr int U = 4;
-        for (int base = epi_tid; base < items; base += 128 * U) {
-            float v[U][8], r[U][8];
-            int rl[U], c8[U];
-            bool ok[U];
+        const int R = kNumThreads / groups;           // rows per pass
+        const int tid = threadIdx.x;
+        if (tid < R * groups && valid > 0) {
+            const int c8 = tid % groups, r0 = tid / groups;
+            const int cb = c8 * 8;
+            if (geglu || cb < col_valid) {
+                float b[8], bg[8];
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int idx = base + 128 * u;
-                ok[u] = idx < items;
-                const int id = ok[u] ? idx : 0;
-                rl[u] = row_begin + (int)(((uint32_t)id * ginv) >> 20);
-                c8[u] = id - (rl[u] - row_begin) * groups;
-                ok[u] = ok[u] && (c8[u] * 8 < col_valid);
-                const uint32_t off = (uint32_t)(rl[u] * pitch_f + c8[u] * 8) * 4u;
-                if (p.split_k > 1) {
+                for (int i = 0; i < 8; ++i) { b[i] = s_bias[cb + i]; bg[i] = geglu ? s_bias[half + cb + i] : 0.f; }
+                const bool multi_img = p.rowbias != nullptr && img1 != img0;
+                if (p.rowbias != nullptr && !multi_img) {   // one image per tile (the common case): fold the time embedding into the bias
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) v[u][i] = 0.f;
-                    for (int sp = 0; sp < p.split_k; ++sp) {
-                        const float4 a0 = ld_dsmem_v4(stage_u32 + off, sp), a1 = ld_dsmem_v4(stage_u32 + off + 16, sp);
-                        v[u][0] += a0.x; v[u][1] += a0.y; v[u][2] += a0.z; v[u][3] += a0.w;
-                        v[u][4] += a1.x; v[u][5] += a1.y; v[u][6] += a1.z; v[u][7] += a1.w;
-                    }
-                } else {
-                    const float* sp = stage + (size_t)rl[u] * pitch_f + c8[u] * 8;
-                    const float4 a0 = *reinterpret_cast<const float4*>(sp), a1 = *reinterpret_cast<const float4*>(sp + 4);
-                    v[u][0] = a0.x; v[u][1] = a0.y; v[u][2] = a0.z; v[u][3] = a0.w;
-                    v[u][4] = a1.x; v[u][5] = a1.y; v[u][6] = a1.z; v[u][7] = a1.w;
+                    for (int i = 0; i < 8; ++i) b[i] += s_rb[cb + i];
                 }
-                if (geglu) {
-                    const float* sp = stage + (size_t)rl[u] * pitch_f + half + c8[u] * 8;
-                    const float4 g0 = *reinterpret_cast<const float4*>(sp), g1 = *reinterpret_cast<const float4*>(sp + 4);
-                    r[u][0] = g0.x; r[u][1] = g0.y; r[u][2] = g0.z; r[u][3] = g0.w;
-                    r[u][4] = g1.x; r[u][5] = g1.y; r[u][6] = g1.z; r[u][7] = g1.w;
-                } else if (p.residual && ok[u]) {
-                    const size_t ro = (size_t)(m0 + rl[u]) * p.ldr + col_base + c8[u] * 8;
-                    if (p.res_f32) ld8<B200SD_F32>(p.residual, ro, r[u]);
-                    else ld8<B200SD_BF16>(p.residual, ro, r[u]);
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) r[u][i] = 0.f;
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                if (!ok[u]) continue;
-                const int row = m0 + rl[u];
-                const int cb = c8[u] * 8;  // column within the tile
-                float o[8];
-                if (geglu) {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i)
-                        o[i] = (v[u][i] + s_bias[cb + i]) * gelu_erf_f(r[u][i] + s_bias[half + cb + i]);
-                    st8<B200SD_BF16>(p.out, (size_t)row * p.ldc + n_tile * half + cb, o);
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) o[i] = v[u][i] + s_bias[cb + i] + r[u][i];
-                    if (p.rowbias) {
-                        const int img = row / p.rows_per_image;
-                        if (rb_smem) {
-                            const float* rb = s_rb + (img == img0 ? 0 : 256) + cb;
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) o[i] += rb[i];
-                        } else {
-                            float t[8];
-                            ld8<B200SD_F32>(p.rowbias, (size_t)img * p.ldrb + n0 + cb, t);
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) o[i] += t[i];
-                        }
-                    }
-                    if (p.atomic_out) {
-                        float* dst = static_cast<float*>(p.out) + (size_t)row * p.ldc + col_base + cb;
-                        red_add_v4(dst, o[0], o[1], o[2], o[3]);
-                        red_add_v4(dst + 4, o[4], o[5], o[6], o[7]);
-                    } else if (p.out_f32) st8<B200SD_F32>(p.out, (size_t)row * p.ldc + col_base + cb, o);
-                    else st8<B200SD_BF16>(p.out, (size_t)row * p.ldc + col_base + cb, o);
-                }
+                EpiCtx e;
+                e.stage_u32 = ptx::smem_u32(stage);
+                e.pitch_f = pitch_f; e.row_end = row_begin + valid; e.R = R; e.cb = cb; e.half = half; e.m0 = m0;
+                e.col_out = geglu ? n_tile * half + cb : col_base + cb;
+                e.s_rb = s_rb; e.img0 = img0; e.multi_img = multi_img; e.rb_smem = rb_smem; e.n0cb = n0 + cb;
+                const int row0 = row_begin + r0;
+                const int ok = p.atomic_out ? 2 : (p.out_f32 ? 1 : 0);
+                const int rk = p.residual ? (p.res_f32 ? 2 : 1) : 0;
+                if (geglu) epilogue_rows<0, 0, false, true>(p, e, row0, b, bg);
+                else if (p.split_k > 1) {
+                    if (ok == 1) { if (rk == 2) epilogue_rows<1, 2, true, false>(p, e, row0, b, bg); else if (rk == 1) epilogue_rows<1, 1, true, false>(p, e, row0, b, bg); else epilogue_rows<1, 0, true, false>(p, e, row0, b, bg); }
+                    else { if (rk == 2) epilogue_rows<0, 2, true, false>(p, e, row0, b, bg); else if (rk == 1) epilogue_rows<0, 1, true, false>(p, e, row0, b, bg); else epilogue_rows<0, 0, true, false>(p, e, row0, b, bg); }
+                } else if (ok == 2) epilogue_rows<2, 0, false, false>(p, e, row0, b, bg);
+                else if (ok == 1) { if (rk == 2) epilogue_rows<1, 2, false, false>(p, e, row0, b, bg); else if (rk == 1) epilogue_rows<1, 1, false, false>(p, e, row0, b, bg); else epilogue_rows<1, 0, false, false>(p, e, row0, b, bg); }
+                else { if (rk == 2) epilogue_rows<0, 2, false, false>(p, e, row0, b, bg); else if (rk == 1) epilogue_rows<0, 1, false, false>(p, e, row0, b, bg); else epilogue_rows<0, 0, false, false>(p, e, row0, b, bg); }
             }
         }
         if (epi_tid == 0) TRACE(6);
@@ -400,10 +448,12 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tcgen05_kernel(const __gr
     // peers may still be reading this CTA's staging tile
     if (p.split_k > 1) cluster_sync_all();
 
+    ptx::tc_fence_before();
     __syncthreads();
+    if constexpr (pair) cluster_sync_all();   // the leader's MMAs read the peer's smem / write its TMEM: nobody leaves early
     if (warp == 1) {
         ptx::tc_fence_after();
-        ptx::tmem_dealloc(tmem_base, p.tmem_cols);
+        if constexpr (pair) ptx::tmem_dealloc_cg2(tmem_base, p.tmem_cols); else ptx::tmem_dealloc(tmem_base, p.tmem_cols);
     }
     if (threadIdx.x == 0) TRACE(7);
 }
@@ -439,10 +489,25 @@ int pick_block_n(int N, int m_tiles, int epilogue) {
 // Shared tail of every entry point: pipeline depth, smem budget, launch.
 // Grids that fit in one wave keep every k-block of a short K loop in flight (deep ring, 1 CTA/SM);
 // larger grids stay <= ~110 KB so two CTAs share an SM and overlap epilogue with main loop.
+typedef void (*gemm_kernel_t)(const KParams);
+gemm_kernel_t gemm_entry(int pair, int op) {
+    switch ((op << 1) | (pair ? 1 : 0)) {
+        case 0: return gemm_tcgen05_kernel<false, 0>;
+        case 1: return gemm_tcgen05_kernel<true, 0>;
+        case 2: return gemm_tcgen05_kernel<false, 1>;
+        case 3: return gemm_tcgen05_kernel<true, 1>;
+        case 4: return gemm_tcgen05_kernel<false, 2>;
+        case 5: return gemm_tcgen05_kernel<true, 2>;
+        case 6: return gemm_tcgen05_kernel<false, 3>;
+        default: return gemm_tcgen05_kernel<true, 3>;
+    }
+}
+
 int launch_gemm(KParams& p, int m_tiles, int n_tiles, int grid_z, bool cluster, b200sd_stream_t stream) {
     const int sms = b200sd_num_sms();
     const int bn = p.block_n;
-    const int stage_bytes = kABytes + bn * BLOCK_K * 2;
+    if (p.pair) m_tiles = (m_tiles + 1) & ~1;   // an odd tail gets a dummy peer (TMA zero-fills, the epilogue stores nothing)
+    const int stage_bytes = kABytes + ((bn * BLOCK_K * 2) >> (p.pair ? 1 : 0));
     const long total_ctas = (long)m_tiles * n_tiles * grid_z;
     int stages;
     if (total_ctas <= sms || bn > 160) stages = (200 * 1024) / stage_bytes;
@@ -459,7 +524,10 @@ int launch_gemm(KParams& p, int m_tiles, int n_tiles, int grid_z, bool cluster, 
 
     static bool configured = false;
     if (!configured) {
-        B200SD_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
+        for (int i = 0; i < 8; ++i) {
+            B200SD_CUDA(cudaFuncSetAttribute(gemm_entry(i & 1, i >> 1), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
+            B200SD_CUDA(cudaFuncSetAttribute(gemm_entry(i & 1, i >> 1), cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        }
         configured = true;
     }
     p.trace = g_gemm_trace;
@@ -470,11 +538,11 @@ int launch_gemm(KParams& p, int m_tiles, int n_tiles, int grid_z, bool cluster, 
     cfg.stream = static_cast<cudaStream_t>(stream);
     cudaLaunchAttribute attr[2];
     int na = 0;
-    if (cluster && grid_z > 1) {
+    if ((cluster && grid_z > 1) || p.pair) {
         attr[na].id = cudaLaunchAttributeClusterDimension;
-        attr[na].val.clusterDim.x = 1;
+        attr[na].val.clusterDim.x = p.pair ? 2 : 1;
         attr[na].val.clusterDim.y = 1;
-        attr[na].val.clusterDim.z = grid_z;
+        attr[na].val.clusterDim.z = p.pair ? 1 : grid_z;
         ++na;
     }
     if (b200sd_pdl_enabled()) {
@@ -484,10 +552,20 @@ int launch_gemm(KParams& p, int m_tiles, int n_tiles, int grid_z, bool cluster, 
     }
     cfg.attrs = attr;
     cfg.numAttrs = na;
-    B200SD_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel, p));
+    B200SD_CUDA(cudaLaunchKernelEx(&cfg, gemm_entry(p.pair, p.b_mode), p));
     g_b200sd_launches.fetch_add(1, std::memory_order_relaxed);
     B200SD_LAUNCH_CHECK();
     return B200SD_OK;
+}
+
+// CTA pairs (cta_group::2): 0 = auto, 1 = force, -1 = off; env B200SD_PAIR=0 disables the auto choice
+// Measured on B200 (tools/pair_check.py): pairs win 5-13 % on long-K tiles of grids that fill the machine
+// (conv3x3 at batch 8: 1171 -> 1325 TFLOP/s) and lose ~5 % on short-K GEMMs (one more cluster barrier per tile).
+bool want_pair(int request, int split, int m_tiles, int n_tiles, int k_blocks) {
+    static const bool env_off = getenv("B200SD_PAIR") && getenv("B200SD_PAIR")[0] == '0';
+    if (request < 0 || split != 1) return false;
+    if (request > 0) return true;
+    return !env_off && m_tiles >= 2 && k_blocks >= 32 && (long)m_tiles * n_tiles >= b200sd_num_sms();
 }
 
 // tile width for MN-major B operands (64-column TMA boxes): least padded columns, then the widest
@@ -614,6 +692,7 @@ extern "C" int b200sd_gemm(const b200sd_gemm_args* a, b200sd_stream_t stream) {
     p.kb_per_split = ceil_div(p.num_k_blocks, split);
     B200SD_REQUIRE((split - 1) * p.kb_per_split < p.num_k_blocks, "gemm: split_k=%d leaves an empty split for K=%d", split, a->K);
     p.split_k = split;
+    p.pair = want_pair(a->pair, split, m_tiles, n_tiles, p.num_k_blocks) && bn % 32 == 0;
 
     // ---- tensor maps ----
     if (!p.conv) {
@@ -644,7 +723,7 @@ extern "C" int b200sd_gemm(const b200sd_gemm_args* a, b200sd_stream_t stream) {
     {
         const uint64_t dimsB[2] = {(uint64_t)a->K, (uint64_t)a->N};
         const uint64_t strB[2] = {0, (uint64_t)a->K * 2};
-        const uint32_t boxB[2] = {BLOCK_K, (uint32_t)bn};
+        const uint32_t boxB[2] = {BLOCK_K, (uint32_t)(p.pair ? bn / 2 : bn)};
         int rc = b200sd_make_tmap(&p.tmB, a->w, 2, dimsB, strB, boxB, CU_TENSOR_MAP_SWIZZLE_128B);
         if (rc) return rc;
     }
@@ -698,8 +777,14 @@ extern "C" int b200sd_gemm_dgrad(const b200sd_dgrad_args* a, b200sd_stream_t str
         const int rc = conv_m_tiling(p, a->batch, a->H, a->W, a->M, &m_tiles);
         if (rc) return rc;
     }
-    const int bn = a->block_n > 0 ? a->block_n : pick_block_n_mn(a->Cin, m_tiles);
+    int bn = a->block_n > 0 ? a->block_n : pick_block_n_mn(a->Cin, m_tiles);
     B200SD_REQUIRE(bn % 64 == 0 && bn >= 64 && bn <= 256, "dgrad: block_n %d must be 64, 128, 192 or 256", bn);
+    p.pair = want_pair(a->pair, 1, m_tiles, ceil_div(a->Cin, bn), p.num_k_blocks);
+    if (p.pair && bn % 128 != 0) {
+        // a pair splits the 64-column boxes of the B tile evenly: 128 or 256 wide, whichever pads N less
+        if (a->block_n > 0) p.pair = 0;
+        else bn = (ceil_div(a->Cin, 256) * 256 <= ceil_div(a->Cin, 128) * 128) ? 256 : 128;
+    }
     p.block_n = bn;
     const int n_tiles = ceil_div(a->Cin, bn);
     p.tmem_cols = pow2_cols(bn);

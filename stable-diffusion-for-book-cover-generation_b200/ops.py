@@ -171,7 +171,7 @@ def gemm_workspace(device):
 
 
 def gemm(a0, w, out, *, a1=None, bias=None, rowbias=None, residual=None, conv=None, rows_per_image=0,
-         epilogue=EPI_LINEAR, block_n=0, split_k=0, M=None, ldrb=0, launch=True):
+         epilogue=EPI_LINEAR, block_n=0, split_k=0, M=None, ldrb=0, launch=True, pair=0):
     """out[M, N] = [a0 | a1] @ w^T (+bias +rowbias +residual); conv=(batch, H, W) -> 3x3 pad-1 conv (NHWC)."""
     _chk(a0, a1, w, bias, rowbias, residual, out)
     N, K = w.shape
@@ -198,6 +198,7 @@ def gemm(a0, w, out, *, a1=None, bias=None, rowbias=None, residual=None, conv=No
     args.out_dtype = _dt(out)
     args.residual_dtype = _dt(residual) if residual is not None else BF16
     args.block_n, args.split_k = block_n, split_k
+    args.pair = pair
     args.workspace, args.workspace_bytes = _p(ws), ws.numel()
     if not launch:
         return args
@@ -209,7 +210,7 @@ def gemm_run(args):
     check(lib().b200sd_gemm(C.byref(args), _stream()), "gemm")
 
 
-def gemm_dgrad(dy, w, out, *, residual=None, conv=None, Cin=None, block_n=0, launch=True):
+def gemm_dgrad(dy, w, out, *, residual=None, conv=None, Cin=None, block_n=0, launch=True, pair=0):
     """out[M, Cin] = dy[M, Cout] (*) w  (+ residual): data gradient of gemm(); w is the FORWARD weight
     [Cout][taps*Cin]; conv=(batch, H, W) -> gradient of the 3x3 pad-1 conv."""
     _chk(dy, w, residual, out)
@@ -227,6 +228,7 @@ def gemm_dgrad(dy, w, out, *, residual=None, conv=None, Cin=None, block_n=0, lau
     a.out_dtype = _dt(out)
     a.residual_dtype = _dt(residual) if residual is not None else BF16
     a.block_n = block_n
+    a.pair = pair
     if not launch:
         return a
     check(lib().b200sd_gemm_dgrad(C.byref(a), _stream()), "gemm_dgrad")
