@@ -249,10 +249,16 @@ def run_ours(args):
             mm_fl = sum(acc[k][1] for k in ("gemm", "conv3x3") if k in acc)
             mm_n = sum(acc[k][2] for k in ("gemm", "conv3x3") if k in acc)
             achieved = mm_fl / (mm_ms * 1e-3) / 1e12 if mm_ms > 0 else 0.0
+            traffic = None
+            tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
+            if os.path.exists(tp) and B == 1 and not args.portrait:
+                with open(tp) as f:
+                    traffic = json.load(f)["gemm_tcgen05_kernel"]["dram_bytes_per_launch"]   # ncu, per launch, same workload
             roof = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (GEMM + implicit-GEMM conv3x3)",
                     "achieved": achieved, "peak": tf_sus, "unit": "TFLOP/s", "frac": achieved / tf_sus,
                     "peak_kind": f"bf16 sustained, {which}", "launches_per_step": mm_n,
-                    "avg_launch_us": 1e3 * mm_ms / max(mm_n, 1), "flops_per_step": mm_fl, "traffic": None}
+                    "avg_launch_us": 1e3 * mm_ms / max(mm_n, 1), "flops_per_step": mm_fl, "traffic": traffic,
+                    "traffic_unit": "DRAM bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)"}
             tot = sum(v[0] for v in acc.values())
             kernels = {k: {"ms_per_step": round(v[0], 4), "share": round(v[0] / tot, 4), "launches": v[2],
                            "tflops": round(v[1] / (v[0] * 1e-3) / 1e12, 1) if v[1] > 0 and v[0] > 0 else None}
