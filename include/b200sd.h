@@ -205,6 +205,12 @@ int b200sd_groupnorm_silu(const void* x0, const void* x1, int C0, int C1, const 
                           void* out, void* raw_out, float* stats_ws, int batch, int hw, int groups, float eps,
                           int silu, int in_dtype, b200sd_stream_t stream);
 
+/* Same, additionally writing stats_out[batch][groups][2] = (mean, rstd) per (image, group) for the backward pass
+ * (stats_out may be NULL). */
+int b200sd_groupnorm_silu_stats(const void* x0, const void* x1, int C0, int C1, const float* gamma, const float* beta,
+                                void* out, void* raw_out, float* stats_ws, float* stats_out, int batch, int hw, int groups,
+                                float eps, int silu, int in_dtype, b200sd_stream_t stream);
+
 /* LayerNorm over the last dim of [rows, C] (in_dtype: fp32 or bf16) -> bf16 (affine). */
 int b200sd_groupnorm_workspace_floats(int batch);
 int b200sd_layernorm(const void* x, const float* gamma, const float* beta, void* out, int rows, int C, float eps,
@@ -253,12 +259,14 @@ int b200sd_grad_prep(const void* in, int in_dtype, void* out_bf16, float* colsum
  * out0 [rows, C0] / out1 [rows, C1] (out_dtype) receive dx (+ add_src, an optional fp32 [rows, C0+C1]
  * addend: the residual path), overwritten or accumulated per the accumulate flags.  dgamma / dbeta
  * (fp32 [C0+C1]) are ACCUMULATED; pass NULL for both when the parameters are frozen.
- * workspace: float[b200sd_groupnorm_bwd_workspace_floats(batch)]. */
+ * mean_rstd: the forward's stats_out (fast path: one vectorised pass for the per-channel sums), or NULL (the group
+ * statistics are recomputed).  workspace: float[b200sd_groupnorm_bwd_workspace_floats(batch)] of plain scratch.
+ * dx is bit-reproducible (per-slab partial sums folded in a fixed order); dgamma / dbeta are fp32 atomics. */
 int b200sd_groupnorm_bwd_workspace_floats(int batch);
 int b200sd_groupnorm_silu_bwd(const void* x0, const void* x1, int C0, int C1, int in_dtype, const float* gamma,
                               const float* beta, const void* dy, const float* add_src, void* out0, void* out1,
                               int out_dtype, int accumulate0, int accumulate1, float* dgamma, float* dbeta,
-                              float* workspace, int batch, int hw, int groups, float eps, int silu,
+                              const float* mean_rstd, float* workspace, int batch, int hw, int groups, float eps, int silu,
                               b200sd_stream_t stream);
 
 /* Backward of b200sd_layernorm: dres[rows, C] (fp32) += dx;  dgamma / dbeta accumulated (or both NULL). */

@@ -69,6 +69,7 @@ SIGNATURES = {
     "b200sd_conv_in": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "b200sd_conv_out": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "b200sd_groupnorm_silu": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _i, _i, _vp]),
+    "b200sd_groupnorm_silu_stats": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _i, _i, _vp]),
     "b200sd_groupnorm_workspace_floats": (_i, [_i]),
     "b200sd_layernorm": (_i, [_vp, _vp, _vp, _vp, _i, _i, _f, _i, _vp]),
     "b200sd_attention_workspace_bytes": (_sz, [_i, _i, _i, _i]),
@@ -78,8 +79,8 @@ SIGNATURES = {
     "b200sd_attention_bwd": (_i, [_vp] * 9 + [_i] * 13 + [_f, _vp, _sz, _vp]),
     "b200sd_grad_prep": (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "b200sd_groupnorm_bwd_workspace_floats": (_i, [_i]),
-    "b200sd_groupnorm_silu_bwd": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _i, _i,
-                                       _i, _f, _i, _vp]),
+    "b200sd_groupnorm_silu_bwd": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _i,
+                                       _i, _i, _f, _i, _vp]),
     "b200sd_layernorm_bwd": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp]),
     "b200sd_geglu_fwd": (_i, [_vp, _vp, _i64, _i, _vp]),
     "b200sd_geglu_bwd": (_i, [_vp, _vp, _vp, _i64, _i, _vp]),

@@ -166,6 +166,127 @@ __global__ void __launch_bounds__(512) gn_bwd_stats_kernel(const void* __restric
     }
 }
 
+
+// ---- fast path of the GroupNorm backward statistics (forward kept mean / rstd) --------------------------------------
+// Because gamma is constant per channel, the two group means are sums over the group's channels of
+//   gamma_c * sum_p g        and        gamma_c * sum_p g xhat,
+// i.e. exactly the per-channel dbeta_c / dgamma_c.  Pass 1 therefore only needs the per-channel pixel sums: every thread
+// owns ONE 8-channel vector and walks down its pixel slab with 16 / 32-byte loads (grid: slabs x channel chunks x batch),
+// the block folds its rows in smem and adds 2 floats per channel to a small workspace.  Pass 2 (one block per image)
+// turns them into the group means, accumulates dgamma / dbeta and re-zeroes the workspace.
+template <int DT>
+__global__ void __launch_bounds__(256) gn_bwd_partial_kernel(const void* __restrict__ x0, const void* __restrict__ x1, int C0, int C1,
+                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                             const bf16* __restrict__ dy, const float* __restrict__ mean_rstd,
+                                                             float* __restrict__ chan_ws, int hw, int groups, int silu, int VC,
+                                                             int pix_per_slab) {
+    extern __shared__ float s_fold[];   // [2][R][VC * 8]
+    ptx::pdl_trigger();
+    ptx::pdl_wait();
+    const int C = C0 + C1, cpg = C / groups, C8 = C / 8;
+    const int b = blockIdx.z, chunk = blockIdx.y;
+    const int R = blockDim.x / VC;
+    const int vec = threadIdx.x % VC, prow = threadIdx.x / VC;
+    const int v8 = chunk * VC + vec;
+    const int c = v8 * 8;
+    const bool active = prow < R && v8 < C8;
+    float sg[8], sx[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { sg[j] = 0.f; sx[j] = 0.f; }
+    if (active) {
+        float gm[8], bt[8], mu[8], rs[8];
+        ld8<B200SD_F32>(gamma, c, gm);
+        ld8<B200SD_F32>(beta, c, bt);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int g = (c + j) / cpg;
+            mu[j] = __ldg(mean_rstd + ((size_t)b * groups + g) * 2);
+            rs[j] = __ldg(mean_rstd + ((size_t)b * groups + g) * 2 + 1);
+        }
+        const void* src;
+        size_t off;
+        int pitch;
+        if (c < C0) { src = x0; off = (size_t)b * hw * C0 + c; pitch = C0; }
+        else { src = x1; off = (size_t)b * hw * C1 + (c - C0); pitch = C1; }
+        const int p0 = blockIdx.x * pix_per_slab, p1 = min(hw, p0 + pix_per_slab);
+#pragma unroll 2
+        for (int p = p0 + prow; p < p1; p += R) {
+            float f[8], g[8];
+            ld8<DT>(src, off + (size_t)p * pitch, f);
+            ld8<B200SD_BF16>(dy, ((size_t)b * hw + p) * C + c, g);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float xh = (f[j] - mu[j]) * rs[j];
+                float gy = g[j];
+                if (silu) gy *= silu_grad_f(gm[j] * xh + bt[j]);
+                sg[j] += gy;
+                sx[j] += gy * xh;
+            }
+        }
+    }
+    const int W = VC * 8;
+    if (prow < R) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            s_fold[(size_t)prow * W + vec * 8 + j] = sg[j];
+            s_fold[(size_t)(R + prow) * W + vec * 8 + j] = sx[j];
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * W; i += blockDim.x) {
+        const int which = i / W, col = i % W;
+        const int ch = chunk * W + col;
+        if (ch >= C) continue;
+        float a = 0.f;
+        for (int r = 0; r < R; ++r) a += s_fold[(size_t)(which * R + r) * W + col];
+        chan_ws[(((size_t)b * gridDim.x + blockIdx.x) * C + ch) * 2 + which] = a;   // this slab's partial (no atomics: deterministic)
+    }
+}
+
+// grid (groups, batch): one block folds the slab partials of its group's channels in a fixed order
+__global__ void __launch_bounds__(256) gn_bwd_finalize_kernel(const float* __restrict__ gamma, const float* __restrict__ mean_rstd,
+                                                              const float* __restrict__ chan_ws, float4* __restrict__ stats,
+                                                              float* __restrict__ dgamma, float* __restrict__ dbeta, int C, int hw,
+                                                              int groups, int slabs) {
+    extern __shared__ float s_part[];   // [parts][2 * cpg] then [2 * cpg] folded
+    ptx::pdl_trigger();
+    ptx::pdl_wait();
+    const int g = blockIdx.x, b = blockIdx.y, cpg = C / groups;
+    const int nE = 2 * cpg;                               // (sum g, sum g xhat) per channel of the group, interleaved
+    const int parts = max(1, (int)blockDim.x / nE);
+    const float* ws = chan_ws + ((size_t)b * slabs * C + (size_t)g * cpg) * 2;
+    for (int t = threadIdx.x; t < parts * nE; t += blockDim.x) {
+        const int e = t % nE, part = t / nE;
+        float a = 0.f;
+        for (int sl = part; sl < slabs; sl += parts) a += ws[(size_t)sl * C * 2 + e];
+        s_part[part * nE + e] = a;
+    }
+    __syncthreads();
+    float* s_ch = s_part + parts * nE;
+    for (int e = threadIdx.x; e < nE; e += blockDim.x) {
+        float a = 0.f;
+        for (int part = 0; part < parts; ++part) a += s_part[part * nE + e];
+        s_ch[e] = a;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float s1 = 0.f, s2 = 0.f;
+        for (int j = 0; j < cpg; ++j) {
+            const float gm = __ldg(gamma + g * cpg + j);
+            s1 += gm * s_ch[2 * j];
+            s2 += gm * s_ch[2 * j + 1];
+        }
+        const float inv = 1.0f / ((float)hw * (float)cpg);
+        stats[(size_t)b * groups + g] = make_float4(mean_rstd[((size_t)b * groups + g) * 2], mean_rstd[((size_t)b * groups + g) * 2 + 1],
+                                                    s1 * inv, s2 * inv);
+    }
+    if (dgamma != nullptr)
+        for (int j = threadIdx.x; j < cpg; j += blockDim.x) {
+            atomicAdd(dbeta + g * cpg + j, s_ch[2 * j]);
+            atomicAdd(dgamma + g * cpg + j, s_ch[2 * j + 1]);
+        }
+}
+
 template <int DT, int ODT>
 __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const void* __restrict__ x0, const void* __restrict__ x1, int C0,
                                                            int C1, const float* __restrict__ gamma,
@@ -592,19 +713,26 @@ extern "C" int b200sd_grad_prep(const void* in, int in_dtype, void* out_bf16, fl
     return B200SD_OK;
 }
 
-extern "C" int b200sd_groupnorm_bwd_workspace_floats(int batch) { return 4 * batch * 32; }
+// workspace: [kGnBwdMaxBatch * 32] float4 group statistics, then per-(image, pixel slab) per-channel partial sums
+// [batch * slabs][C][2] with batch * slabs <= kGnBwdMaxSlabs + batch.  Plain scratch: no zero-on-entry contract.
+constexpr int kGnBwdMaxC = 4096;
+constexpr int kGnBwdMaxBatch = 1024;
+constexpr int kGnBwdMaxSlabs = 640;
+extern "C" int b200sd_groupnorm_bwd_workspace_floats(int batch) {
+    return 4 * kGnBwdMaxBatch * 32 + 2 * (kGnBwdMaxSlabs + batch) * kGnBwdMaxC;
+}
 
 extern "C" int b200sd_groupnorm_silu_bwd(const void* x0, const void* x1, int C0, int C1, int in_dtype, const float* gamma,
                                          const float* beta, const void* dy, const float* add_src, void* out0, void* out1,
                                          int out_dtype, int accumulate0, int accumulate1, float* dgamma, float* dbeta,
-                                         float* workspace, int batch, int hw, int groups, float eps, int silu,
-                                         b200sd_stream_t stream) {
+                                         const float* mean_rstd, float* workspace, int batch, int hw, int groups, float eps,
+                                         int silu, b200sd_stream_t stream) {
     B200SD_REQUIRE(x0 && gamma && beta && dy && out0 && workspace, "groupnorm_bwd: null pointer");
     if (!x1) C1 = 0;
     B200SD_REQUIRE(C1 == 0 || out1 != nullptr, "groupnorm_bwd: out1 missing for the second source");
     B200SD_REQUIRE((dgamma == nullptr) == (dbeta == nullptr), "groupnorm_bwd: dgamma / dbeta must both be given or both NULL");
     const int C = C0 + C1;
-    B200SD_REQUIRE(batch > 0 && hw > 0 && groups > 0 && groups <= 32 && C % groups == 0, "groupnorm_bwd: bad sizes");
+    B200SD_REQUIRE(batch > 0 && batch <= kGnBwdMaxBatch && hw > 0 && groups > 0 && groups <= 32 && C % groups == 0, "groupnorm_bwd: bad sizes");
     B200SD_REQUIRE(C0 % 8 == 0 && C1 % 8 == 0, "groupnorm_bwd: channel counts must be multiples of 8");
     B200SD_REQUIRE(in_dtype == B200SD_BF16 || in_dtype == B200SD_F32, "groupnorm_bwd: bad input dtype");
     B200SD_REQUIRE(out_dtype == B200SD_BF16 || out_dtype == B200SD_F32, "groupnorm_bwd: bad output dtype");
@@ -612,7 +740,34 @@ extern "C" int b200sd_groupnorm_silu_bwd(const void* x0, const void* x1, int C0,
     B200SD_REQUIRE(cpg <= 512, "groupnorm_bwd: %d channels per group unsupported", cpg);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     float4* stats = reinterpret_cast<float4*>(workspace);
-    {
+    if (mean_rstd != nullptr && C <= kGnBwdMaxC) {
+        float* chan_ws = workspace + 4 * (size_t)kGnBwdMaxBatch * 32;
+        const int C8 = C / 8;
+        const int VC = C8 < 64 ? C8 : 64;                 // 8-channel vectors per block (512 channels)
+        const int chunks = ceil_div(C8, VC);
+        const int R = 256 / VC;
+        const int threads = ceil_div(R * VC, 32) * 32;
+        int slabs = ceil_div(kGnBwdMaxSlabs - 48, batch * chunks);   // ~4 CTAs per SM on 148 SMs, bounded by the scratch size
+        int pps = ceil_div(hw, slabs);
+        if (pps < 2 * R) pps = 2 * R;
+        slabs = ceil_div(hw, pps);
+        const size_t smem = (size_t)2 * R * VC * 8 * sizeof(float);
+        if (in_dtype == B200SD_F32)
+            B200SD_CUDA(b200sd_launch(gn_bwd_partial_kernel<B200SD_F32>, dim3(slabs, chunks, batch), dim3(threads), smem, s, x0, x1, C0, C1, gamma,
+                                      beta, static_cast<const bf16*>(dy), mean_rstd, chan_ws, hw, groups, silu, VC, pps));
+        else
+            B200SD_CUDA(b200sd_launch(gn_bwd_partial_kernel<B200SD_BF16>, dim3(slabs, chunks, batch), dim3(threads), smem, s, x0, x1, C0, C1, gamma,
+                                      beta, static_cast<const bf16*>(dy), mean_rstd, chan_ws, hw, groups, silu, VC, pps));
+        COUNT_LAUNCH();
+        {
+            const int nE = 2 * cpg;
+            const int parts = 256 / nE > 0 ? 256 / nE : 1;
+            B200SD_CUDA(b200sd_launch(gn_bwd_finalize_kernel, dim3(groups, batch), dim3(256), (size_t)(parts + 1) * nE * sizeof(float), s, gamma,
+                                      mean_rstd, chan_ws, stats, dgamma, dbeta, C, hw, groups, slabs));
+        }
+        COUNT_LAUNCH();
+        B200SD_LAUNCH_CHECK();
+    } else {
         int threads = (512 / cpg) * cpg;
         if (threads / cpg > hw) threads = hw * cpg;
         threads = ceil_div(threads, 32) * 32;

@@ -181,7 +181,8 @@ __global__ void __launch_bounds__(512) gn_fused_kernel(const void* __restrict__ 
                                                        int C1, const float* __restrict__ gamma,
                                                        const float* __restrict__ beta, bf16* __restrict__ out,
                                                        bf16* __restrict__ raw_out, int hw, int groups, int G, int CL,
-                                                       int pix_per_cta, int R, float eps, int silu) {
+                                                       int pix_per_cta, int R, float eps, int silu,
+                                                       float* __restrict__ stats_out) {
     extern __shared__ float gsm[];  // [2][R][Cg] per-thread channel sums | [Cg] scale | [Cg] shift
     __shared__ float s_cta[2 * kMaxGroups];   // this CTA's (sum, sumsq) per group of the set
     __shared__ float s_mr[2 * kMaxGroups];    // (mean, rstd) per group of the set
@@ -268,6 +269,10 @@ __global__ void __launch_bounds__(512) gn_fused_kernel(const void* __restrict__ 
         if (var < 0.0) var = 0.0;
         s_mr[2 * threadIdx.x] = (float)mean;
         s_mr[2 * threadIdx.x + 1] = (float)(1.0 / sqrt(var + (double)eps));
+        if (stats_out != nullptr && rank == 0) {   // kept for the backward pass
+            stats_out[((size_t)b * groups + set * G + threadIdx.x) * 2] = s_mr[2 * threadIdx.x];
+            stats_out[((size_t)b * groups + set * G + threadIdx.x) * 2 + 1] = s_mr[2 * threadIdx.x + 1];
+        }
     }
     __syncthreads();
     for (int i = threadIdx.x; i < Cg; i += blockDim.x) {
@@ -337,9 +342,10 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const void* __restrict__
 
 }  // namespace
 
-extern "C" int b200sd_groupnorm_silu(const void* x0, const void* x1, int C0, int C1, const float* gamma,
-                                     const float* beta, void* out, void* raw_out, float* stats_ws, int batch, int hw,
-                                     int groups, float eps, int silu, int in_dtype, b200sd_stream_t stream) {
+extern "C" int b200sd_groupnorm_silu_stats(const void* x0, const void* x1, int C0, int C1, const float* gamma,
+                                           const float* beta, void* out, void* raw_out, float* stats_ws, float* stats_out,
+                                           int batch, int hw, int groups, float eps, int silu, int in_dtype,
+                                           b200sd_stream_t stream) {
     B200SD_REQUIRE(x0 && gamma && beta && out && stats_ws, "groupnorm: null pointer");
     if (!x1) C1 = 0;
     const int C = C0 + C1;
@@ -392,10 +398,10 @@ extern "C" int b200sd_groupnorm_silu(const void* x0, const void* x1, int C0, int
             cfg.numAttrs = na;
             if (in_dtype == B200SD_F32)
                 B200SD_CUDA(cudaLaunchKernelEx(&cfg, gn_fused_kernel<B200SD_F32>, x0, x1, C0, C1, gamma, beta, static_cast<bf16*>(out),
-                                               static_cast<bf16*>(raw_out), hw, groups, G, CL, ppc, R, eps, silu));
+                                               static_cast<bf16*>(raw_out), hw, groups, G, CL, ppc, R, eps, silu, stats_out));
             else
                 B200SD_CUDA(cudaLaunchKernelEx(&cfg, gn_fused_kernel<B200SD_BF16>, x0, x1, C0, C1, gamma, beta, static_cast<bf16*>(out),
-                                               static_cast<bf16*>(raw_out), hw, groups, G, CL, ppc, R, eps, silu));
+                                               static_cast<bf16*>(raw_out), hw, groups, G, CL, ppc, R, eps, silu, stats_out));
             COUNT_LAUNCH();
             B200SD_LAUNCH_CHECK();
             return B200SD_OK;
@@ -425,6 +431,8 @@ extern "C" int b200sd_groupnorm_silu(const void* x0, const void* x1, int C0, int
                                   mean_rstd, counters, hw, groups, pps, rows_per_pass, eps));
     COUNT_LAUNCH();
     B200SD_LAUNCH_CHECK();
+    if (stats_out != nullptr)
+        B200SD_CUDA(cudaMemcpyAsync(stats_out, mean_rstd, (size_t)2 * batch * groups * sizeof(float), cudaMemcpyDeviceToDevice, s));
     int blocks = ceil_div(b200sd_num_sms() * 4, batch);
     int ppb = ceil_div(hw, blocks);
     const int min_ppb = ceil_div(kGnThreads * 4, C / 8);  // >= 4 vectors per thread
@@ -439,6 +447,13 @@ extern "C" int b200sd_groupnorm_silu(const void* x0, const void* x1, int C0, int
     COUNT_LAUNCH();
     B200SD_LAUNCH_CHECK();
     return B200SD_OK;
+}
+
+extern "C" int b200sd_groupnorm_silu(const void* x0, const void* x1, int C0, int C1, const float* gamma,
+                                     const float* beta, void* out, void* raw_out, float* stats_ws, int batch, int hw,
+                                     int groups, float eps, int silu, int in_dtype, b200sd_stream_t stream) {
+    return b200sd_groupnorm_silu_stats(x0, x1, C0, C1, gamma, beta, out, raw_out, stats_ws, nullptr, batch, hw, groups, eps, silu,
+                                       in_dtype, stream);
 }
 
 // workspace floats needed by b200sd_groupnorm_silu for a given batch: 2 * batch * kMaxSlabs * kMaxGroups

@@ -11,6 +11,7 @@ from ._lib import DgradArgs, GemmArgs, WgradArgs, B200SDError, check, lib
 
 F32, BF16 = 0, 1
 EPI_LINEAR, EPI_GEGLU = 0, 1
+_GN_RECOMPUTE = __import__("os").environ.get("B200SD_GN_FAST", "1") == "0"   # debug: GroupNorm backward recomputes its statistics
 
 
 def _dt(t: torch.Tensor) -> int:
@@ -274,15 +275,16 @@ def conv_out(x_nhwc, w_packed, bias, out_nchw):
     return out_nchw
 
 
-def groupnorm_silu(x0, x1, gamma, beta, out, batch, hw, groups=32, eps=1e-5, silu=True, raw_out=None):
-    _chk(x0, x1, gamma, beta, out, raw_out)
+def groupnorm_silu(x0, x1, gamma, beta, out, batch, hw, groups=32, eps=1e-5, silu=True, raw_out=None, stats_out=None):
+    _chk(x0, x1, gamma, beta, out, raw_out, stats_out)
     if x1 is not None and x1.dtype != x0.dtype:
         raise B200SDError("groupnorm: both sources must have the same dtype")
     ws = _workspace("gn", lib().b200sd_groupnorm_workspace_floats(batch) * 4, x0.device)
     C0 = x0.shape[-1]
     C1 = x1.shape[-1] if x1 is not None else 0
-    check(lib().b200sd_groupnorm_silu(_p(x0), _p(x1), C0, C1, _p(gamma), _p(beta), _p(out), _p(raw_out), _p(ws), batch, hw,
-                                      groups, float(eps), int(silu), _dt(x0), _stream()), "groupnorm_silu")
+    check(lib().b200sd_groupnorm_silu_stats(_p(x0), _p(x1), C0, C1, _p(gamma), _p(beta), _p(out), _p(raw_out), _p(ws),
+                                            _p(stats_out), batch, hw, groups, float(eps), int(silu), _dt(x0), _stream()),
+          "groupnorm_silu")
     return out
 
 
@@ -380,14 +382,16 @@ def adamw_step(param, grad, exp_avg, exp_avg_sq, weights_bf16, lr, beta1, beta2,
 
 
 def groupnorm_silu_bwd(x0, x1, gamma, beta, dy, out0, out1, batch, hw, *, add_src=None, acc0=False, acc1=False,
-                       dgamma=None, dbeta=None, groups=32, eps=1e-5, silu=True):
-    _chk(x0, x1, gamma, beta, dy, out0, out1, add_src, dgamma, dbeta)
-    ws = _workspace("gn_bwd", lib().b200sd_groupnorm_bwd_workspace_floats(batch) * 4, x0.device, zero=False)
+                       dgamma=None, dbeta=None, groups=32, eps=1e-5, silu=True, mean_rstd=None):
+    _chk(x0, x1, gamma, beta, dy, out0, out1, add_src, dgamma, dbeta, mean_rstd)
+    if _GN_RECOMPUTE:
+        mean_rstd = None
+    ws = _workspace("gn_bwd", lib().b200sd_groupnorm_bwd_workspace_floats(batch) * 4, x0.device, zero=True)
     C0 = x0.shape[-1]
     C1 = x1.shape[-1] if x1 is not None else 0
     check(lib().b200sd_groupnorm_silu_bwd(_p(x0), _p(x1), C0, C1, _dt(x0), _p(gamma), _p(beta), _p(dy), _p(add_src),
                                           _p(out0), _p(out1), _dt(out0), int(acc0), int(acc1), _p(dgamma), _p(dbeta),
-                                          _p(ws), batch, hw, groups, float(eps), int(silu), _stream()),
+                                          _p(mean_rstd), _p(ws), batch, hw, groups, float(eps), int(silu), _stream()),
           "groupnorm_silu_bwd")
 
 

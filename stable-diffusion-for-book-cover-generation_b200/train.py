@@ -336,12 +336,13 @@ class TrainEngine:
             has_sc = hasattr(r, "conv_shortcut")
             t1 = self._new(M, cin)
             raw = self._new(M, cin) if has_sc else None
-            Fp.append(lambda: ops.groupnorm_silu(x, skip, r.norm1.weight, r.norm1.bias, t1, N, hw, 32, eps, True, raw_out=raw))
+            st1, st2 = torch.empty(N, 32, 2, **f32), torch.empty(N, 32, 2, **f32)   # GroupNorm (mean, rstd), kept for the backward
+            Fp.append(lambda: ops.groupnorm_silu(x, skip, r.norm1.weight, r.norm1.bias, t1, N, hw, 32, eps, True, raw_out=raw, stats_out=st1))
             hbuf = self._new(M, cout, F32)
             rb = (self.tproj.data_ptr() + tp_off[prefix] * 4, n_tp, hw)
             self._gemm(Fp, t1, self.Wb(r.conv1.weight), hbuf, bias=r.conv1.bias, conv=(N, h, w), rowbias_ptr=rb)
             t2 = self._new(M, cout)
-            Fp.append(lambda: ops.groupnorm_silu(hbuf, None, r.norm2.weight, r.norm2.bias, t2, N, hw, 32, eps, True))
+            Fp.append(lambda: ops.groupnorm_silu(hbuf, None, r.norm2.weight, r.norm2.bias, t2, N, hw, 32, eps, True, stats_out=st2))
             if has_sc:
                 sc = self._new(M, cout, F32)
                 self._gemm(Fp, raw, self.Wb(r.conv_shortcut.weight), sc, bias=r.conv_shortcut.bias)
@@ -359,7 +360,8 @@ class TrainEngine:
                 self._dgrad(dy16, self.Wb(r.conv2.weight), dt2, conv=(N, h, w))
                 dh16 = pool.get(M, cout)
                 Bp.append(lambda: ops.groupnorm_silu_bwd(hbuf, None, r.norm2.weight, r.norm2.bias, dt2, dh16, None, N, hw,
-                                                         dgamma=self.G(r.norm2.weight), dbeta=self.G(r.norm2.bias), eps=eps, silu=True))
+                                                         dgamma=self.G(r.norm2.weight), dbeta=self.G(r.norm2.bias), eps=eps, silu=True,
+                                                         mean_rstd=st2))
                 pool.put(dt2)
                 # time-embedding gradient: per-image column sums of dh (conv1.bias gets the same sums, folded at the end)
                 dtp = self.d_tproj.view(-1)[tp_off[prefix]:]
@@ -382,7 +384,7 @@ class TrainEngine:
                 gs, accs = self._grad_of(skip) if skip is not None else (None, False)
                 Bp.append(lambda: ops.groupnorm_silu_bwd(x, skip, r.norm1.weight, r.norm1.bias, dt1, gx, gs, N, hw, add_src=add,
                                                          acc0=accx, acc1=accs, dgamma=self.G(r.norm1.weight),
-                                                         dbeta=self.G(r.norm1.bias), eps=eps, silu=True))
+                                                         dbeta=self.G(r.norm1.bias), eps=eps, silu=True, mean_rstd=st1))
                 pool.put(dt1, dy16 if dy16 is not dy else None, add if add is not dy else None)
 
             blocks.append((backward, r.norm1.weight))
@@ -399,7 +401,8 @@ class TrainEngine:
             w_qkv = flat.span([a1m.to_q.weight, a1m.to_k.weight, a1m.to_v.weight], "wb")
             w_kv2 = flat.span([a2m.to_k.weight, a2m.to_v.weight], "wb")
             t = self._new(M, Cc)
-            Fp.append(lambda: ops.groupnorm_silu(x, None, a.norm.weight, a.norm.bias, t, N, hw, 32, 1e-6, False))
+            st = torch.empty(N, 32, 2, **f32)
+            Fp.append(lambda: ops.groupnorm_silu(x, None, a.norm.weight, a.norm.bias, t, N, hw, 32, 1e-6, False, stats_out=st))
             hs0 = self._new(M, Cc, F32)
             self._gemm(Fp, t, self.Wb(a.proj_in.weight), hs0, bias=a.proj_in.bias)
             # self attention
@@ -505,7 +508,7 @@ class TrainEngine:
                 gx, accx = self._grad_of(x)
                 Bp.append(lambda: ops.groupnorm_silu_bwd(x, None, a.norm.weight, a.norm.bias, dn, gx, None, N, hw, add_src=dy,
                                                          acc0=accx, dgamma=self.G(a.norm.weight), dbeta=self.G(a.norm.bias),
-                                                         eps=1e-6, silu=False))
+                                                         eps=1e-6, silu=False, mean_rstd=st))
                 pool.put(dn)
 
             blocks.append((backward, a.norm.weight))
@@ -591,7 +594,9 @@ class TrainEngine:
         co_w = flat.reg(m.conv_out.weight)
         x_last = x
         t_out = self._new(N * h * w, boc[0])
-        Fp.append(lambda: ops.groupnorm_silu(x_last, None, m.conv_norm_out.weight, m.conv_norm_out.bias, t_out, N, h * w, 32, eps, True))
+        st_out = torch.empty(N, 32, 2, **f32)
+        Fp.append(lambda: ops.groupnorm_silu(x_last, None, m.conv_norm_out.weight, m.conv_norm_out.bias, t_out, N, h * w, 32, eps, True,
+                                             stats_out=st_out))
         Fp.append(lambda: ops.conv_out(t_out, co_w.wf, m.conv_out.bias, self.out))
 
         # ---- backward graph: head, then the blocks in reverse, then the time MLP ----
@@ -602,7 +607,7 @@ class TrainEngine:
         gx, _ = self._grad_of(x_last)
         Bp.append(lambda: ops.groupnorm_silu_bwd(x_last, None, m.conv_norm_out.weight, m.conv_norm_out.bias, dt_out, gx, None, N, hw,
                                                  dgamma=self.G(m.conv_norm_out.weight), dbeta=self.G(m.conv_norm_out.bias),
-                                                 eps=eps, silu=True))
+                                                 eps=eps, silu=True, mean_rstd=st_out))
         self.pool.put(dt_out)
         if tw:
             self.ready_marks.append((len(Bp), flat.reg(m.conv_norm_out.weight).off))

@@ -96,18 +96,28 @@ def test_groupnorm_silu_bwd(B, hw, C0, C1, silu, in_f32, out_f32):
     y.backward(dy.float().reshape(B, hw, C).permute(0, 2, 1))
     want = xr.grad.permute(0, 2, 1).reshape(B * hw, C) + add
     odt = torch.float32 if out_f32 else torch.bfloat16
-    prev0 = torch.randn(B * hw, C0, device=DEV).to(odt)
-    out0 = prev0.clone()
-    out1 = torch.empty(B * hw, C1, device=DEV, dtype=odt) if C1 else None
-    dg, db = torch.zeros(C, device=DEV), torch.zeros(C, device=DEV)
-    ops.groupnorm_silu_bwd(x0, x1, gamma, beta, dy, out0, out1, B, hw, add_src=add, acc0=True, acc1=False, dgamma=dg,
-                           dbeta=db, eps=1e-5, silu=silu)
-    tol = 2e-4 if out_f32 else 1.0 / 100
-    _close(out0, want[:, :C0] + prev0.float(), tol, "dx0 (accumulated)")
-    if C1:
-        _close(out1, want[:, C0:], tol, "dx1")
-    _close(dg, g_.grad, 2e-4, "dgamma")
-    _close(db, b_.grad, 2e-4, "dbeta")
+    # forward kernel (also writes the (mean, rstd) the fast backward path consumes)
+    t_fwd = torch.empty(B * hw, C, device=DEV, dtype=torch.bfloat16)
+    st = torch.empty(B, 32, 2, device=DEV)
+    ops.groupnorm_silu(x0, x1, gamma, beta, t_fwd, B, hw, 32, 1e-5, silu, stats_out=st)
+    _close(t_fwd, y.detach().permute(0, 2, 1).reshape(B * hw, C), 1.0 / 64, "forward")
+    xg = xr.detach().reshape(B, 32, -1)
+    _close(st[..., 0], xg.mean(-1), 1e-4, "saved mean")
+    _close(st[..., 1], (xg.var(-1, unbiased=False) + 1e-5).rsqrt(), 1e-4, "saved rstd")
+    for mean_rstd in (None, st):      # recompute-statistics path and saved-statistics fast path
+        prev0 = torch.randn(B * hw, C0, device=DEV).to(odt)
+        out0 = prev0.clone()
+        out1 = torch.empty(B * hw, C1, device=DEV, dtype=odt) if C1 else None
+        dg, db = torch.zeros(C, device=DEV), torch.zeros(C, device=DEV)
+        ops.groupnorm_silu_bwd(x0, x1, gamma, beta, dy, out0, out1, B, hw, add_src=add, acc0=True, acc1=False, dgamma=dg,
+                               dbeta=db, eps=1e-5, silu=silu, mean_rstd=mean_rstd)
+        tol = 2e-4 if out_f32 else 1.0 / 100
+        tag = "fast" if mean_rstd is not None else "recompute"
+        _close(out0, want[:, :C0] + prev0.float(), tol, f"dx0 (accumulated, {tag})")
+        if C1:
+            _close(out1, want[:, C0:], tol, f"dx1 ({tag})")
+        _close(dg, g_.grad, 2e-4, f"dgamma ({tag})")
+        _close(db, b_.grad, 2e-4, f"dbeta ({tag})")
 
 
 @pytest.mark.parametrize("rows,C,in_f32", [(8192, 320, True), (2048, 640, True), (512, 1280, True), (100, 64, True), (1024, 320, False)])

@@ -200,7 +200,7 @@ def test_trainer_steps_reduce_the_loss():
     tr.train_step(x, noise, t, ctx, sync=False)
     g1 = g0.clone()
     tr.train_step(x, noise, t, ctx, sync=False)
-    assert torch.allclose(g0, 2 * g1, rtol=1e-3, atol=1e-6 * float(g1.abs().max()))
+    assert torch.allclose(g0, 2 * g1, rtol=1e-3, atol=1e-4 * float(g1.abs().max()))   # fp32 atomics: run-to-run noise ~1e-6 of the max
     # the inference engine picks the updated weights up (eval forward == training forward on the same weights)
     unet.eval()
     with torch.no_grad():
