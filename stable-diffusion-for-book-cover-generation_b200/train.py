@@ -564,8 +564,22 @@ class TrainEngine:
             if not tw:
                 return
             g = self._grad_ready(x0)
-            Bp.append(lambda: ops.conv_in_wgrad(g, self.in_sample, ci_w.g))
-            Bp.append(lambda: ops.grad_prep(g, None, self.G(m.conv_in.bias)))
+            if self.W <= 64 and 64 % self.W == 0 and cfg.in_channels <= 8:
+                # weight gradient on the tensor cores: the 4-channel input is padded to 8 channels (16-byte NHWC rows) and
+                # read as the MN-major B operand of the conv wgrad GEMM (TMA zero-fills the rest of the 64-column box)
+                cin = cfg.in_channels
+                x8 = torch.zeros(N * self.H * self.W, 8, dtype=BF16, device=dev)
+                dw8 = torch.zeros(boc[0], 9 * 8, dtype=F32, device=dev)
+                g16 = self.pool.get(g.shape[0], g.shape[1])
+                Bp.append(lambda: ops.grad_prep(g, g16, self.G(m.conv_in.bias)))
+                Bp.append(lambda: x8.view(N, self.H, self.W, 8)[..., :cin].copy_(self.in_sample.permute(0, 2, 3, 1)))
+                Bp.append(lambda: dw8.zero_())
+                self._wgrad(g16, x8, dw8, conv=(N, self.H, self.W))
+                Bp.append(lambda: ci_w.g.view(boc[0], 9, cin).add_(dw8.view(boc[0], 9, 8)[..., :cin]))
+                self.pool.put(g16)
+            else:
+                Bp.append(lambda: ops.conv_in_wgrad(g, self.in_sample, ci_w.g))
+                Bp.append(lambda: ops.grad_prep(g, None, self.G(m.conv_in.bias)))
 
         blocks.append((conv_in_backward, m.conv_in.weight))
         x = x0
@@ -602,8 +616,20 @@ class TrainEngine:
         # ---- backward graph: head, then the blocks in reverse, then the time MLP ----
         hw = h * w
         dt_out = self.pool.get(N * hw, boc[0])
-        Bp.append(lambda: ops.conv_out_bwd(self.d_out, t_out, co_w.wf, dt_out, co_w.g if tw else None,
-                                           self.G(m.conv_out.bias)))
+        cout = cfg.out_channels
+        tc_wgrad = tw and self.W <= 64 and 64 % self.W == 0 and cout <= 8
+        if tc_wgrad:
+            # conv_out weight gradient on the tensor cores: d_out (NCHW, 4 channels) padded to 8-channel NHWC bf16 rows is the
+            # MN-major A operand (rows 4..127 of the 128-row MMA tile are TMA zero fill)
+            dy8 = torch.zeros(N * hw, 8, dtype=BF16, device=dev)
+            dwo = torch.zeros(8, 9 * boc[0], dtype=F32, device=dev)
+            Bp.append(lambda: dy8.view(N, h, w, 8)[..., :cout].copy_(self.d_out.permute(0, 2, 3, 1)))
+            Bp.append(lambda: dwo.zero_())
+            self._wgrad(dy8, t_out, dwo, conv=(N, h, w))
+            Bp.append(lambda: co_w.g.add_(dwo[:cout]))
+            Bp.append(lambda: self.G(m.conv_out.bias).add_(self.d_out.sum(dim=(0, 2, 3))))
+        Bp.append(lambda: ops.conv_out_bwd(self.d_out, t_out, co_w.wf, dt_out, co_w.g if (tw and not tc_wgrad) else None,
+                                           self.G(m.conv_out.bias) if not tc_wgrad else None))
         gx, _ = self._grad_of(x_last)
         Bp.append(lambda: ops.groupnorm_silu_bwd(x_last, None, m.conv_norm_out.weight, m.conv_norm_out.bias, dt_out, gx, None, N, hw,
                                                  dgamma=self.G(m.conv_norm_out.weight), dbeta=self.G(m.conv_norm_out.bias),
