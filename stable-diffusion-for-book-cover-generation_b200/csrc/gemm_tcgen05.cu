@@ -568,15 +568,18 @@ bool want_pair(int request, int split, int m_tiles, int n_tiles, int k_blocks) {
     return !env_off && m_tiles >= 2 && k_blocks >= 32 && (long)m_tiles * n_tiles >= b200sd_num_sms();
 }
 
-// tile width for MN-major B operands (64-column TMA boxes): least padded columns, then the widest
-int pick_block_n_mn(int N, int m_tiles) {
-    int best = 64, best_pad = ceil_div(N, 64) * 64;
-    for (int bn = 128; bn <= 256; bn += 64) {
-        const int pad = ceil_div(N, bn) * bn;
-        if (pad <= best_pad) { best = bn; best_pad = pad; }
-    }
-    // small grids: narrower tiles put more CTAs in flight (64 always has the least padding)
-    if ((long)m_tiles * ceil_div(N, best) * 2 <= b200sd_num_sms()) best = 64;
+// Tile width for MN-major B operands (64-column TMA boxes), from the sweep in tools/bwd_gemm_bench.py (B200, batch 8):
+// 128 wins or ties for dgrad (plain and conv) and conv wgrad; 192 for plain wgrad (long K, small output).  64 is never
+// better than 128 when N > 64 (the main loop is bound by the per-SM operand load rate: wider tiles reuse the A rows).
+// kind: 0 dgrad, 1 wgrad plain, 2 wgrad conv.
+int pick_block_n_mn(int N, int m_tiles, int kind) {
+    int best;
+    if (N <= 64) best = 64;
+    else if (N <= 128) best = 128;
+    else if (kind == 1) best = N <= 192 ? 192 : ((N % 192 == 0 || N % 128 != 0) ? 192 : (N % 256 == 0 ? 256 : 128));
+    else best = (N % 192 == 0 && N % 128 != 0) ? 192 : 128;
+    // small grids: narrower tiles put more CTAs in flight
+    while (best > 64 && (long)m_tiles * ceil_div(N, best) * 2 <= b200sd_num_sms()) best -= 64;
     return best;
 }
 
@@ -777,7 +780,7 @@ extern "C" int b200sd_gemm_dgrad(const b200sd_dgrad_args* a, b200sd_stream_t str
         const int rc = conv_m_tiling(p, a->batch, a->H, a->W, a->M, &m_tiles);
         if (rc) return rc;
     }
-    int bn = a->block_n > 0 ? a->block_n : pick_block_n_mn(a->Cin, m_tiles);
+    int bn = a->block_n > 0 ? a->block_n : pick_block_n_mn(a->Cin, m_tiles, 0);
     B200SD_REQUIRE(bn % 64 == 0 && bn >= 64 && bn <= 256, "dgrad: block_n %d must be 64, 128, 192 or 256", bn);
     p.pair = want_pair(a->pair, 1, m_tiles, ceil_div(a->Cin, bn), p.num_k_blocks);
     if (p.pair && bn % 128 != 0) {
@@ -874,7 +877,7 @@ extern "C" int b200sd_gemm_wgrad(const b200sd_wgrad_args* a, b200sd_stream_t str
         const uint32_t boxA[2] = {64, BLOCK_K};
         if ((rc = b200sd_make_tmap(&p.tmA0, a->dy, 2, dimsA, strA, boxA, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
     }
-    const int bn = a->block_n > 0 ? a->block_n : pick_block_n_mn(a->Cin, m_tiles * a->conv_taps);
+    const int bn = a->block_n > 0 ? a->block_n : pick_block_n_mn(a->Cin, m_tiles * a->conv_taps, a->conv_taps == 9 ? 2 : 1);
     B200SD_REQUIRE(bn % 64 == 0 && bn >= 64 && bn <= 256, "wgrad: block_n %d must be 64, 128, 192 or 256", bn);
     p.block_n = bn;
     p.tiles_per_tap = ceil_div(a->Cin, bn);
