@@ -233,7 +233,8 @@ class UNet2DConditionModel(nn.Module):
         cfg = dict(self.config, _class_name="UNet2DConditionModel", _diffusers_version="0.7.2")
         with open(os.path.join(path, self.config_name), "w") as f:
             json.dump(cfg, f, indent=2)
-        sd = {k: v.detach().cpu() for k, v in self.state_dict().items()}
+        # .contiguous(): after a training call the parameters are (possibly permuted) views of the flat master buffer
+        sd = {k: v.detach().cpu().contiguous() for k, v in self.state_dict().items()}
         if safe_serialization:
             from safetensors.torch import save_file
             save_file(sd, os.path.join(path, "diffusion_pytorch_model.safetensors"))

@@ -209,3 +209,36 @@ def test_trainer_steps_reduce_the_loss():
     b = unet(x, t, ctx).sample.detach()
     rel = float((a - b).abs().max() / b.abs().max())
     assert rel <= 2e-2, rel
+
+
+def test_autograd_mode_accumulates_and_survives_save_load(tmp_path):
+    """Default (autograd) gradient delivery: two backwards without zero_grad accumulate in param.grad like an eager
+    module; the re-homed parameters still round-trip through save_pretrained / from_pretrained (finetune_sd.py:517-537)."""
+    from b200sd import ops
+    from b200sd.unet import UNet2DConditionModel
+    from oracle.unet_ref import TINY_OVERRIDES
+    _setup()
+    torch.manual_seed(0)
+    unet = UNet2DConditionModel(**TINY_OVERRIDES).to(DEV).train()
+    x, noise, ctx, t = _inputs(2, 32, 32, 64, 7)
+    ops.mse_loss(unet(x, t, ctx).sample, noise).backward()
+    g1 = {n: p.grad.clone() for n, p in unet.named_parameters()}
+    assert all(p.grad.is_contiguous() or p.dim() == 4 for p in unet.parameters())
+    ops.mse_loss(unet(x, t, ctx).sample, noise).backward()
+    for n, p in unet.named_parameters():
+        assert torch.allclose(p.grad, 2 * g1[n], rtol=1e-3, atol=1e-4 * float(g1[n].abs().max()) + 1e-12), n
+    # a stock torch optimizer steps the re-homed parameters; the next forward sees the new weights
+    opt = torch.optim.AdamW(unet.parameters(), lr=1e-3)
+    with torch.no_grad():
+        before = unet(x, t, ctx).sample.clone()
+    opt.step()
+    opt.zero_grad()
+    with torch.no_grad():
+        after = unet(x, t, ctx).sample
+    assert float((after - before).abs().max()) > 0
+    for safe in (False, True):
+        d = tmp_path / ("st" if safe else "bin")
+        unet.save_pretrained(str(d), safe_serialization=safe)
+        again = UNet2DConditionModel.from_pretrained(str(d))
+        for (n, p), (_, q) in zip(unet.state_dict().items(), again.state_dict().items()):
+            assert torch.equal(p.detach().cpu(), q), n
