@@ -295,6 +295,27 @@ int b200sd_conv_in_wgrad(const void* dy_nhwc, int dy_dtype, const float* x_nchw,
 int b200sd_cast_act(const float* in, void* out_bf16, int64_t n, int silu, b200sd_stream_t stream);
 int b200sd_silu_bwd_mul(const float* pre, float* grad, int64_t n, b200sd_stream_t stream);
 
+/* ---- fp32-accuracy path (north_star: "the fp32 path within 1e-4") ------------------------------
+ * The tensor cores stay bf16: an fp32 operand x travels as (hi, lo) = (bf16(x), bf16(x - hi)) and a product is
+ * evaluated as A_hi B_hi + A_lo B_hi + A_hi B_lo with fp32 accumulation -- two b200sd_gemm calls:
+ * [A_hi | A_lo] x [B_hi | B_hi]^T (a0 / a1 K-concat), then A_hi x B_lo^T added through the fp32 residual input. */
+int b200sd_split_hi_lo(const float* x, void* hi_bf16, void* lo_bf16, int64_t n, b200sd_stream_t stream);
+/* GroupNorm / LayerNorm that also emit the lo halves (out_lo / raw_lo may be NULL; stats_out as in _stats). */
+int b200sd_groupnorm_silu_split(const void* x0, const void* x1, int C0, int C1, const float* gamma, const float* beta,
+                                void* out, void* out_lo, void* raw_out, void* raw_lo, float* stats_ws, float* stats_out,
+                                int batch, int hw, int groups, float eps, int silu, int in_dtype, b200sd_stream_t stream);
+int b200sd_layernorm_split(const void* x, const float* gamma, const float* beta, void* out, void* out_lo, int rows, int C,
+                           float eps, int in_dtype, b200sd_stream_t stream);
+/* u fp32 [rows, 2*C_half] = [values | gates] -> (hi, lo) of values * gelu_erf(gates), each bf16 [rows, C_half] */
+int b200sd_geglu_f32(const float* u, void* hi_bf16, void* lo_bf16, int64_t rows, int C_half, b200sd_stream_t stream);
+/* fp32 flash attention on the CUDA cores (online softmax with expf, no score matrix in HBM); q is pre-multiplied by
+ * scale inside; same addressing as b200sd_attention but fp32 buffers; d in {8,16,32,40,64,80,128,160}. */
+int b200sd_attention_f32(const float* q, const float* k, const float* v, float* out, int batch, int heads, int Sq, int Skv,
+                         int d, int ldq, int ldk, int ldv, int ldo, float scale, b200sd_stream_t stream);
+/* b200sd_small_linear with fp32 weights (time-embedding MLP and time_emb_proj heads of the fp32 path) */
+int b200sd_small_linear_f32(const float* in, const float* w, const float* bias, float* out, int batch, int N, int K,
+                            int silu_in, int silu_out, b200sd_stream_t stream);
+
 /* ---- optimizer step over the flat kernel-layout buffers (finetune_sd.py:407-420, 569-570) ------ */
 /* out_bf16[i] = in[i] for n (multiple of 8) elements: fp32 master weights -> bf16 tensor-core copy. */
 int b200sd_cast_flat(const float* in, void* out_bf16, int64_t n, b200sd_stream_t stream);

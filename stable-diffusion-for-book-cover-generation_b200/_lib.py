@@ -90,6 +90,12 @@ SIGNATURES = {
     "b200sd_conv_in_wgrad": (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "b200sd_cast_act": (_i, [_vp, _vp, _i64, _i, _vp]),
     "b200sd_silu_bwd_mul": (_i, [_vp, _vp, _i64, _vp]),
+    "b200sd_split_hi_lo": (_i, [_vp, _vp, _vp, _i64, _vp]),
+    "b200sd_groupnorm_silu_split": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _i, _i, _vp]),
+    "b200sd_layernorm_split": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _f, _i, _vp]),
+    "b200sd_geglu_f32": (_i, [_vp, _vp, _vp, _i64, _i, _vp]),
+    "b200sd_attention_f32": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _vp]),
+    "b200sd_small_linear_f32": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "b200sd_cast_flat": (_i, [_vp, _vp, _i64, _vp]),
     "b200sd_adamw_step": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _f, _f, _f, _f, _f, _i, _f, _i, _vp]),
     "b200sd_upsample2x": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),

@@ -9,6 +9,14 @@ extern std::atomic<long long> g_b200sd_launches;
 
 namespace {
 
+// hi / lo split of an fp32 vector for the fp32-accuracy path: hi = bf16(y), lo = bf16(y - hi); y = hi + lo to ~2^-17
+__device__ __forceinline__ void st8_lo(bf16* lo, size_t i, const float (&y)[8]) {
+    float r[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r[j] = y[j] - __bfloat162float(__float2bfloat16(y[j]));
+    st8<B200SD_BF16>(lo, i, r);
+}
+
 constexpr int kGnThreads = 256;
 constexpr int kMaxSlabs = 128;
 constexpr int kCounterFloats = 1024;  // per-image arrival counters (batch <= 1024), must start zeroed
@@ -120,7 +128,8 @@ template <int DT>
 __global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const void* __restrict__ x0, const void* __restrict__ x1,
                                                               int C0, int C1, const float* __restrict__ gamma,
                                                               const float* __restrict__ beta, bf16* __restrict__ out,
-                                                              bf16* __restrict__ raw_out,
+                                                              bf16* __restrict__ raw_out, bf16* __restrict__ out_lo,
+                                                              bf16* __restrict__ raw_lo,
                                                               const float* __restrict__ mean_rstd, int hw,
                                                               int groups, int silu, int pix_per_block) {
     extern __shared__ float2 s_ab[];  // per-channel (scale, shift)
@@ -156,6 +165,8 @@ __global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const void* __rest
         }
         st8<B200SD_BF16>(out, ((size_t)b * hw + p) * C + c, y);
         if (raw_out) st8<B200SD_BF16>(raw_out, ((size_t)b * hw + p) * C + c, f);  // bf16 copy of [x0|x1] (1x1 shortcut operand)
+        if (out_lo) st8_lo(out_lo, ((size_t)b * hw + p) * C + c, y);
+        if (raw_lo) st8_lo(raw_lo, ((size_t)b * hw + p) * C + c, f);
     }
 }
 
@@ -180,7 +191,8 @@ template <int DT>
 __global__ void __launch_bounds__(512) gn_fused_kernel(const void* __restrict__ x0, const void* __restrict__ x1, int C0,
                                                        int C1, const float* __restrict__ gamma,
                                                        const float* __restrict__ beta, bf16* __restrict__ out,
-                                                       bf16* __restrict__ raw_out, int hw, int groups, int G, int CL,
+                                                       bf16* __restrict__ raw_out, bf16* __restrict__ out_lo,
+                                                       bf16* __restrict__ raw_lo, int hw, int groups, int G, int CL,
                                                        int pix_per_cta, int R, float eps, int silu,
                                                        float* __restrict__ stats_out) {
     extern __shared__ float gsm[];  // [2][R][Cg] per-thread channel sums | [Cg] scale | [Cg] shift
@@ -297,6 +309,8 @@ __global__ void __launch_bounds__(512) gn_fused_kernel(const void* __restrict__ 
             const size_t o = ((size_t)b * hw + pp) * C + c;
             st8<B200SD_BF16>(out, o, y);
             if (raw_out) st8<B200SD_BF16>(raw_out, o, f);
+            if (out_lo) st8_lo(out_lo, o, y);
+            if (raw_lo) st8_lo(raw_lo, o, f);
         }
     }
     if (CL > 1) gn_cluster_sync();  // peers may still be reading s_cta
@@ -306,7 +320,7 @@ __global__ void __launch_bounds__(512) gn_fused_kernel(const void* __restrict__ 
 template <int PAIRS_PER_LANE, int DT>
 __global__ void __launch_bounds__(256) layernorm_kernel(const void* __restrict__ x, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, bf16* __restrict__ out,
-                                                        int rows, int C, float eps) {
+                                                        bf16* __restrict__ out_lo, int rows, int C, float eps) {
     ptx::pdl_trigger();
     ptx::pdl_wait();
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -336,16 +350,21 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const void* __restrict__
 #pragma unroll
     for (int i = 0; i < PAIRS_PER_LANE; ++i) {
         const float2 g = __ldg(g2 + lane + 32 * i), bb = __ldg(b2 + lane + 32 * i);
-        dst[lane + 32 * i] = pack_bf16x2((v[i].x - mean) * rstd * g.x + bb.x, (v[i].y - mean) * rstd * g.y + bb.y);
+        const float y0 = (v[i].x - mean) * rstd * g.x + bb.x, y1 = (v[i].y - mean) * rstd * g.y + bb.y;
+        dst[lane + 32 * i] = pack_bf16x2(y0, y1);
+        if (out_lo != nullptr)
+            reinterpret_cast<uint32_t*>(out_lo + (size_t)warp * C)[lane + 32 * i] =
+                pack_bf16x2(y0 - __bfloat162float(__float2bfloat16(y0)), y1 - __bfloat162float(__float2bfloat16(y1)));
     }
 }
 
 }  // namespace
 
-extern "C" int b200sd_groupnorm_silu_stats(const void* x0, const void* x1, int C0, int C1, const float* gamma,
-                                           const float* beta, void* out, void* raw_out, float* stats_ws, float* stats_out,
-                                           int batch, int hw, int groups, float eps, int silu, int in_dtype,
-                                           b200sd_stream_t stream) {
+extern "C" int b200sd_groupnorm_silu_split(const void* x0, const void* x1, int C0, int C1, const float* gamma,
+                                           const float* beta, void* out, void* out_lo, void* raw_out, void* raw_lo,
+                                           float* stats_ws, float* stats_out, int batch, int hw, int groups, float eps,
+                                           int silu, int in_dtype, b200sd_stream_t stream) {
+    B200SD_REQUIRE(raw_lo == nullptr || raw_out != nullptr, "groupnorm: raw_lo needs raw_out");
     B200SD_REQUIRE(x0 && gamma && beta && out && stats_ws, "groupnorm: null pointer");
     if (!x1) C1 = 0;
     const int C = C0 + C1;
@@ -398,10 +417,12 @@ extern "C" int b200sd_groupnorm_silu_stats(const void* x0, const void* x1, int C
             cfg.numAttrs = na;
             if (in_dtype == B200SD_F32)
                 B200SD_CUDA(cudaLaunchKernelEx(&cfg, gn_fused_kernel<B200SD_F32>, x0, x1, C0, C1, gamma, beta, static_cast<bf16*>(out),
-                                               static_cast<bf16*>(raw_out), hw, groups, G, CL, ppc, R, eps, silu, stats_out));
+                                               static_cast<bf16*>(raw_out), static_cast<bf16*>(out_lo), static_cast<bf16*>(raw_lo), hw, groups, G, CL, ppc, R, eps,
+                                               silu, stats_out));
             else
                 B200SD_CUDA(cudaLaunchKernelEx(&cfg, gn_fused_kernel<B200SD_BF16>, x0, x1, C0, C1, gamma, beta, static_cast<bf16*>(out),
-                                               static_cast<bf16*>(raw_out), hw, groups, G, CL, ppc, R, eps, silu, stats_out));
+                                               static_cast<bf16*>(raw_out), static_cast<bf16*>(out_lo), static_cast<bf16*>(raw_lo), hw, groups, G, CL, ppc, R, eps,
+                                               silu, stats_out));
             COUNT_LAUNCH();
             B200SD_LAUNCH_CHECK();
             return B200SD_OK;
@@ -440,10 +461,12 @@ extern "C" int b200sd_groupnorm_silu_stats(const void* x0, const void* x1, int C
     blocks = ceil_div(hw, ppb);
     if (in_dtype == B200SD_F32)
         B200SD_CUDA(b200sd_launch(gn_apply_kernel<B200SD_F32>, dim3(blocks, batch), dim3(kGnThreads), C * sizeof(float2), s, x0, x1, C0, C1,
-                                  gamma, beta, static_cast<bf16*>(out), static_cast<bf16*>(raw_out), mean_rstd, hw, groups, silu, ppb));
+                                  gamma, beta, static_cast<bf16*>(out), static_cast<bf16*>(raw_out), static_cast<bf16*>(out_lo), static_cast<bf16*>(raw_lo),
+                                  mean_rstd, hw, groups, silu, ppb));
     else
         B200SD_CUDA(b200sd_launch(gn_apply_kernel<B200SD_BF16>, dim3(blocks, batch), dim3(kGnThreads), C * sizeof(float2), s, x0, x1, C0, C1,
-                                  gamma, beta, static_cast<bf16*>(out), static_cast<bf16*>(raw_out), mean_rstd, hw, groups, silu, ppb));
+                                  gamma, beta, static_cast<bf16*>(out), static_cast<bf16*>(raw_out), static_cast<bf16*>(out_lo), static_cast<bf16*>(raw_lo),
+                                  mean_rstd, hw, groups, silu, ppb));
     COUNT_LAUNCH();
     B200SD_LAUNCH_CHECK();
     return B200SD_OK;
@@ -452,8 +475,16 @@ extern "C" int b200sd_groupnorm_silu_stats(const void* x0, const void* x1, int C
 extern "C" int b200sd_groupnorm_silu(const void* x0, const void* x1, int C0, int C1, const float* gamma,
                                      const float* beta, void* out, void* raw_out, float* stats_ws, int batch, int hw,
                                      int groups, float eps, int silu, int in_dtype, b200sd_stream_t stream) {
-    return b200sd_groupnorm_silu_stats(x0, x1, C0, C1, gamma, beta, out, raw_out, stats_ws, nullptr, batch, hw, groups, eps, silu,
-                                       in_dtype, stream);
+    return b200sd_groupnorm_silu_split(x0, x1, C0, C1, gamma, beta, out, nullptr, raw_out, nullptr, stats_ws, nullptr, batch, hw,
+                                       groups, eps, silu, in_dtype, stream);
+}
+
+extern "C" int b200sd_groupnorm_silu_stats(const void* x0, const void* x1, int C0, int C1, const float* gamma,
+                                           const float* beta, void* out, void* raw_out, float* stats_ws, float* stats_out,
+                                           int batch, int hw, int groups, float eps, int silu, int in_dtype,
+                                           b200sd_stream_t stream) {
+    return b200sd_groupnorm_silu_split(x0, x1, C0, C1, gamma, beta, out, nullptr, raw_out, nullptr, stats_ws, stats_out, batch, hw,
+                                       groups, eps, silu, in_dtype, stream);
 }
 
 // workspace floats needed by b200sd_groupnorm_silu for a given batch: 2 * batch * kMaxSlabs * kMaxGroups
@@ -461,8 +492,8 @@ extern "C" int b200sd_groupnorm_workspace_floats(int batch) {
     return kCounterFloats + 2 * batch * kMaxGroups + 2 * batch * kMaxSlabs * kMaxGroups;
 }
 
-extern "C" int b200sd_layernorm(const void* x, const float* gamma, const float* beta, void* out, int rows, int C,
-                                float eps, int in_dtype, b200sd_stream_t stream) {
+extern "C" int b200sd_layernorm_split(const void* x, const float* gamma, const float* beta, void* out, void* out_lo, int rows,
+                                      int C, float eps, int in_dtype, b200sd_stream_t stream) {
     B200SD_REQUIRE(x && gamma && beta && out, "layernorm: null pointer");
     B200SD_REQUIRE(rows > 0, "layernorm: rows must be positive");
     B200SD_REQUIRE(C % 64 == 0 && C >= 64 && C <= 1280, "layernorm: C=%d unsupported (multiple of 64, <= 1280)", C);
@@ -471,12 +502,13 @@ extern "C" int b200sd_layernorm(const void* x, const float* gamma, const float* 
     const void* xi = x;
     B200SD_REQUIRE(in_dtype == B200SD_BF16 || in_dtype == B200SD_F32, "layernorm: bad input dtype");
     bf16* xo = static_cast<bf16*>(out);
+    bf16* xl = static_cast<bf16*>(out_lo);
 #define LN_CASE(P)                                                                                     \
     case P:                                                                                            \
         if (in_dtype == B200SD_F32)                                                                         \
-            B200SD_CUDA(b200sd_launch(layernorm_kernel<P, B200SD_F32>, dim3(blocks), dim3(256), 0, s, xi, gamma, beta, xo, rows, C, eps)); \
+            B200SD_CUDA(b200sd_launch(layernorm_kernel<P, B200SD_F32>, dim3(blocks), dim3(256), 0, s, xi, gamma, beta, xo, xl, rows, C, eps)); \
         else                                                                                                \
-            B200SD_CUDA(b200sd_launch(layernorm_kernel<P, B200SD_BF16>, dim3(blocks), dim3(256), 0, s, xi, gamma, beta, xo, rows, C, eps)); \
+            B200SD_CUDA(b200sd_launch(layernorm_kernel<P, B200SD_BF16>, dim3(blocks), dim3(256), 0, s, xi, gamma, beta, xo, xl, rows, C, eps)); \
         break;
     switch (C / 64) {
         LN_CASE(1) LN_CASE(2) LN_CASE(3) LN_CASE(4) LN_CASE(5) LN_CASE(6) LN_CASE(7) LN_CASE(8) LN_CASE(9) LN_CASE(10)
@@ -488,4 +520,9 @@ extern "C" int b200sd_layernorm(const void* x, const float* gamma, const float* 
     COUNT_LAUNCH();
     B200SD_LAUNCH_CHECK();
     return B200SD_OK;
+}
+
+extern "C" int b200sd_layernorm(const void* x, const float* gamma, const float* beta, void* out, int rows, int C,
+                                float eps, int in_dtype, b200sd_stream_t stream) {
+    return b200sd_layernorm_split(x, gamma, beta, out, nullptr, rows, C, eps, in_dtype, stream);
 }

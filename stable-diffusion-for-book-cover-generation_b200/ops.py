@@ -450,3 +450,51 @@ def silu_bwd_mul(pre, grad):
     _chk(pre, grad)
     check(lib().b200sd_silu_bwd_mul(_p(pre), _p(grad), grad.numel(), _stream()), "silu_bwd_mul")
     return grad
+
+
+# ---------------------------------------------------------------------------------------------
+# fp32-accuracy path: operands travel as (hi, lo) bf16 pairs, products are 3-term (see include/b200sd.h)
+# ---------------------------------------------------------------------------------------------
+def split_hi_lo(x, hi, lo):
+    _chk(x, hi, lo)
+    check(lib().b200sd_split_hi_lo(_p(x), _p(hi), _p(lo), x.numel(), _stream()), "split_hi_lo")
+
+
+def groupnorm_silu_split(x0, x1, gamma, beta, out, out_lo, batch, hw, groups=32, eps=1e-5, silu=True, raw_out=None, raw_lo=None):
+    _chk(x0, x1, gamma, beta, out, out_lo, raw_out, raw_lo)
+    ws = _workspace("gn", lib().b200sd_groupnorm_workspace_floats(batch) * 4, x0.device)
+    C0 = x0.shape[-1]
+    C1 = x1.shape[-1] if x1 is not None else 0
+    check(lib().b200sd_groupnorm_silu_split(_p(x0), _p(x1), C0, C1, _p(gamma), _p(beta), _p(out), _p(out_lo), _p(raw_out),
+                                            _p(raw_lo), _p(ws), None, batch, hw, groups, float(eps), int(silu), _dt(x0),
+                                            _stream()), "groupnorm_silu_split")
+
+
+def layernorm_split(x, gamma, beta, out, out_lo, eps=1e-5):
+    _chk(x, gamma, beta, out, out_lo)
+    Cc = x.shape[-1]
+    check(lib().b200sd_layernorm_split(_p(x), _p(gamma), _p(beta), _p(out), _p(out_lo), x.numel() // Cc, Cc, float(eps), _dt(x),
+                                       _stream()), "layernorm_split")
+
+
+def geglu_f32(u, hi, lo):
+    _chk(u, hi, lo)
+    check(lib().b200sd_geglu_f32(_p(u), _p(hi), _p(lo), u.numel() // u.shape[-1], u.shape[-1] // 2, _stream()), "geglu_f32")
+
+
+def attention_f32(q, k, v, out, batch, heads, Sq, Skv, d, scale, ldq=None, ldk=None, ldv=None, ldo=None, q_off=0, k_off=0, v_off=0):
+    _chk(q, k, v, out)
+    check(lib().b200sd_attention_f32(q.data_ptr() + q_off * 4, k.data_ptr() + k_off * 4, v.data_ptr() + v_off * 4, _p(out), batch,
+                                     heads, Sq, Skv, d, ldq or q.shape[-1], ldk or k.shape[-1], ldv or v.shape[-1],
+                                     ldo or out.shape[-1], float(scale), _stream()), "attention_f32")
+
+
+def small_linear_f32(x, w, bias, silu_in=False, silu_out=False, out=None):
+    _chk(x, w, bias, out)
+    B, K = x.shape
+    N = w.shape[0]
+    if out is None:
+        out = torch.empty(B, N, dtype=torch.float32, device=x.device)
+    check(lib().b200sd_small_linear_f32(_p(x), _p(w), _p(bias), _p(out), B, N, K, int(silu_in), int(silu_out), _stream()),
+          "small_linear_f32")
+    return out

@@ -179,6 +179,7 @@ class UNet2DConditionModel(nn.Module):
         self._flat = None            # train.FlatParams (flat bf16 weights + flat fp32 gradients), built on first training call
         self._train_engines = {}
         self._direct_grads = False
+        self._precision = "bf16"       # "bf16" (tensor-core operands rounded to bf16) | "fp32" (split-bf16 3-term products, engine_fp32.py)
         self._grad_ready_hook = None   # direct mode: called with `offset` when flat_gradients()[offset:] is final (trainer.py)
 
     # -- init / (de)serialisation ---------------------------------------------------------------
@@ -253,6 +254,17 @@ class UNet2DConditionModel(nn.Module):
         self._flat = None
         self._train_engines = {}
         return r
+
+    def set_precision(self, precision: str):
+        """"bf16": the fast plan (noise prediction within 1e-2 of the fp32 reference).  "fp32": the accuracy plan
+        (engine_fp32.py: every contraction as a 3-term split-bf16 product with fp32 accumulation, fp32 attention /
+        norms / GEGLU; within 1e-4).  Inference only; training always runs the bf16 plan on fp32 master weights."""
+        if precision not in ("bf16", "fp32"):
+            raise ValueError("precision must be 'bf16' or 'fp32'")
+        if precision != self._precision:
+            self._precision = precision
+            self._engines = {}
+        return self
 
     def enable_direct_gradients(self, enabled: bool = True):
         """param.grad become views of ONE flat fp32 gradient buffer that the backward kernels accumulate into
@@ -399,11 +411,15 @@ class UNet2DConditionModel(nn.Module):
         if self._dirty or self._packed is None or (self.training and self._versions() != self._param_versions):
             self._pack_weights()
             self._engines = {}
-        key = (N, H, Wd, ctx.shape[1], sample.device.index)
+        key = (N, H, Wd, ctx.shape[1], sample.device.index, self._precision)
         eng = self._engines.get(key)
         if eng is None:
-            from .engine import Engine
-            eng = Engine(self, N, H, Wd, ctx.shape[1], sample.device)
+            if self._precision == "fp32":
+                from .engine_fp32 import EngineF32
+                eng = EngineF32(self, N, H, Wd, ctx.shape[1], sample.device)
+            else:
+                from .engine import Engine
+                eng = Engine(self, N, H, Wd, ctx.shape[1], sample.device)
             self._engines[key] = eng
         out = eng.run(sample, timestep, ctx, use_graph=self.use_cuda_graph)
         out = out.to(sample.dtype) if out.dtype != sample.dtype else out

@@ -160,3 +160,27 @@ def test_forward_rejects_bad_inputs(models):
         ours(torch.randn(1, 4, 60, 64, device=DEV), 1, torch.randn(1, 77, 768, device=DEV))
     with pytest.raises(ValueError):
         ours(torch.randn(2, 4, 64, 64, device=DEV), 1, torch.randn(1, 77, 768, device=DEV))
+
+
+def test_fp32_accuracy_path_within_1e_4(models):
+    """BASELINE north_star: "the fp32 path within 1e-4".  unet.set_precision("fp32") evaluates every contraction as a 3-term
+    split-bf16 product with fp32 accumulation on the same tcgen05 kernels (engine_fp32.py)."""
+    oracle, ours = models
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(2, 4, 64, 64, generator=g)
+    ctx = torch.randn(2, 77, 768, generator=g)
+    t = torch.tensor([999, 37])
+    oc = oracle.to(DEV)
+    ours.set_precision("fp32")
+    try:
+        with torch.no_grad():
+            want = oc(x.to(DEV), t.to(DEV), ctx.to(DEV)).sample
+            got = ours(x.to(DEV), t.to(DEV), ctx.to(DEV)).sample
+            again = ours(x.to(DEV), t.to(DEV), ctx.to(DEV)).sample      # graph replay
+    finally:
+        oracle.to("cpu")
+        ours.set_precision("bf16")
+    r = _rel(got, want)
+    print(f"fp32 path max-rel vs fp32 oracle: {r:.3g}")
+    assert r <= 1e-4, f"fp32 path max-rel {r:.4g}"
+    assert torch.equal(got, again)
