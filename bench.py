@@ -162,6 +162,8 @@ def run_ours(args):
     h, w = (96, 64) if args.portrait else (64, 64)
     torch.manual_seed(0)
     unet = UNet2DConditionModel().to(dev).eval()          # random-init weights of the SD v1.5 architecture
+    if args.precision == "fp32":
+        unet.set_precision("fp32")
     sch = DDIMScheduler(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear", clip_sample=False,
                         set_alpha_to_one=False)
     sch.set_timesteps(50)
@@ -242,7 +244,7 @@ def run_ours(args):
         # ---- roofline of the dominant kernel (tcgen05 GEMM / implicit-GEMM conv), timed live ----
         roof = None
         kernels = None
-        if rank == 0:
+        if rank == 0 and args.precision == "bf16":
             acc, per_op = eng.profile(iters=3)
             hbm, tf_burst, tf_sus, which = _peaks()
             mm_ms = sum(acc[k][0] for k in ("gemm", "conv3x3") if k in acc)
@@ -282,7 +284,8 @@ def run_ours(args):
         line = {
             "metric": "unet_denoise_it_per_s", "value": value, "unit": "it/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32 (split-bf16 3-term products on the tensor cores)",
+            "data": "synthetic",
             "config": {"workload": "sd15_unet_ddim50_cfg7.5_" + ("512x768" if args.portrait else "512px"),
                        "images_per_gpu": B, "unet_batch": 2 * B, "latent": f"4x{h}x{w}", "context": "77x768",
                        "weights": "random-init SD v1.5 UNet (859.5M params)", "images_per_s": value / 50.0,
@@ -524,6 +527,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--batch", type=int, default=1, help="images per GPU (UNet batch = 2x with CFG)")
     ap.add_argument("--portrait", action="store_true", help="512x768 book-cover geometry (config 5)")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"], help="fp32 = the accuracy path (engine_fp32.py)")
     ap.add_argument("--impl", default="b200sd", choices=["b200sd", "reference"])
     ap.add_argument("--workload", default="sample", choices=["sample", "train", "train_text"],
                     help="sample = 50-step DDIM + CFG denoising (BASELINE configs[1], the headline); train = fine-tuning step (configs[2])")

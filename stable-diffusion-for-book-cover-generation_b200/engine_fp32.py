@@ -269,9 +269,11 @@ class EngineF32:
                         op()
                     torch.cuda.current_stream().synchronize()
                     g = torch.cuda.CUDAGraph()
+                    before = ops.launch_count()
                     with torch.cuda.graph(g):
                         for op in self.plan:
                             op()
+                    self.kernels_per_graph = ops.launch_count() - before
                     self.graph = g
                 self.graph.replay()
             return self.out.clone()
