@@ -72,6 +72,24 @@ __device__ __forceinline__ float fast_exp2(float x) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+// Blackwell packed fp32x2 math and 3-input max: the softmax warps are instruction-issue bound, these halve the
+// non-MUFU instructions per score element (FFMA2 / FADD2 / FMNMX3 in SASS)
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+    unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a), rb = *reinterpret_cast<unsigned long long*>(&b),
+                       rc = *reinterpret_cast<unsigned long long*>(&c), rd;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+    return *reinterpret_cast<float2*>(&rd);
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+    unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a), rb = *reinterpret_cast<unsigned long long*>(&b), rd;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+    return *reinterpret_cast<float2*>(&rd);
+}
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+    float d;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
 __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -235,14 +253,15 @@ __global__ void __launch_bounds__(kThreads, (D <= 40) ? 2 : 1) attention_tc_kern
                 tmem_ld_32x32b_x32(tmem_S + lane_addr + c + 32, r1);
                 ptx::tmem_ld_wait();
 #pragma unroll
-                for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fmaxf(__uint_as_float(r0[i]), __uint_as_float(r1[i])));
+                for (int i = 0; i < 32; ++i) mx = fmax3(mx, __uint_as_float(r0[i]), __uint_as_float(r1[i]));
             }
             const float mn = fmaxf(m, mx);
             const float corr = fast_exp2((m - mn) * p.scale_log2);
             const float off = mn * p.scale_log2;
             m = mn;
             // pass 2: P = exp2(S * scale - off) -> bf16 -> swizzled smem tile; row sum in fp32
-            float rs = 0.f;
+            float2 rs2 = make_float2(0.f, 0.f);
+            const float2 sc2 = make_float2(p.scale_log2, p.scale_log2), noff2 = make_float2(-off, -off);
 #pragma unroll
             for (int c = 0; c < 128; c += 32) {
                 uint32_t r[32];
@@ -251,10 +270,10 @@ __global__ void __launch_bounds__(kThreads, (D <= 40) ? 2 : 1) attention_tc_kern
                 uint32_t pk[16];
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
-                    const float a = fast_exp2(fmaf(__uint_as_float(r[2 * i]), p.scale_log2, -off));
-                    const float bb = fast_exp2(fmaf(__uint_as_float(r[2 * i + 1]), p.scale_log2, -off));
-                    rs += a + bb;
-                    pk[i] = pack_bf16x2(a, bb);
+                    const float2 t = ffma2(make_float2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])), sc2, noff2);
+                    const float2 e = make_float2(fast_exp2(t.x), fast_exp2(t.y));
+                    rs2 = fadd2(rs2, e);
+                    pk[i] = pack_bf16x2(e.x, e.y);
                 }
                 uint8_t* blk = sP + (c / 64) * kBlk + row * 128;
 #pragma unroll
@@ -263,7 +282,7 @@ __global__ void __launch_bounds__(kThreads, (D <= 40) ? 2 : 1) attention_tc_kern
                     *reinterpret_cast<uint4*>(blk + chunk * 16) = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
                 }
             }
-            l = l * corr + rs;
+            l = l * corr + (rs2.x + rs2.y);
             ptx::tc_fence_before();
             ptx::fence_proxy_async();   // generic-proxy smem writes -> visible to the tensor core (async proxy)
             ptx::mbar_arrive(p_full);

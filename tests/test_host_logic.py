@@ -112,3 +112,29 @@ def test_packing_layouts():
     # tile 8 -> [4 values | 4 gates] per tile: rows 0-3, 8-11, 4-7, 12-15
     assert bg.tolist() == [0, 1, 2, 3, 8, 9, 10, 11, 4, 5, 6, 7, 12, 13, 14, 15]
     assert wg[:, 0].float().tolist() == bg.tolist()
+
+
+def test_fp32_path_weight_split_reconstructs_the_3_term_product():
+    """engine_fp32._pack_lin / _pack_conv: [A_hi | A_lo] x [W_hi | W_hi]^T + A_hi x W_lo^T == A W^T to ~2^-16 (CPU, fp32 math)."""
+    import torch
+    from b200sd.engine_fp32 import _pack_conv, _pack_lin
+    torch.manual_seed(0)
+    A = torch.randn(64, 128)
+    W = torch.randn(96, 128) / 11
+    a_hi = A.bfloat16()
+    a_lo = (A - a_hi.float()).bfloat16()
+    w1, w2 = _pack_lin(W)
+    assert w1.shape == (96, 256) and w2.shape == (96, 128) and w1.dtype == torch.bfloat16
+    got = torch.cat([a_hi, a_lo], 1).float() @ w1.float().t() + a_hi.float() @ w2.float().t()
+    want = A.double() @ W.double().t()
+    rel = float((got.double() - want).abs().max() / want.abs().max())
+    assert rel < 5e-5, rel
+    plain = float(((a_hi.float() @ W.bfloat16().float().t()).double() - want).abs().max() / want.abs().max())
+    assert plain > 20 * rel          # the single-term bf16 product is what the split improves on
+    Wc = torch.randn(32, 64, 3, 3)
+    c1, c2 = _pack_conv(Wc)
+    assert c1.shape == (32, 18 * 64) and c2.shape == (32, 9 * 64)
+    hi = Wc.permute(0, 2, 3, 1).reshape(32, 9, 64).bfloat16()
+    assert torch.equal(c1.view(32, 9, 128)[:, :, :64], hi) and torch.equal(c1.view(32, 9, 128)[:, :, 64:], hi)
+    assert torch.allclose(c1.view(32, 9, 128)[:, :, :64].float() + c2.view(32, 9, 64).float(), Wc.permute(0, 2, 3, 1).reshape(32, 9, 64),
+                          rtol=0, atol=2e-4)
