@@ -10,6 +10,7 @@
 // forward kernel in attention.cu; head dims 40 / 80 / 160 are zero-padded to a multiple of 16 in shared memory.
 // For head dims > 96 the dK/dV accumulators are split in two halves of d across CTAs (register budget).
 #include <atomic>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -342,6 +343,10 @@ int launch_bwd(const BwdParams& p, int batch, cudaStream_t s) {
 
 }  // namespace
 
+int b200sd_attention_bwd_tc(const bf16* q, const bf16* k, const bf16* v, const bf16* dout, const float* lse, const float* delta,
+                            bf16* dq, bf16* dk, bf16* dv, int batch, int heads, int Sq, int Skv, int d, int ldq, int ldk,
+                            int ldv, int lddo, int lddq, int lddk, int lddv, float scale, cudaStream_t s);
+
 extern "C" size_t b200sd_attention_bwd_workspace_bytes(int batch, int heads, int Sq) {
     return (size_t)batch * heads * Sq * sizeof(float);
 }
@@ -370,6 +375,17 @@ extern "C" int b200sd_attention_bwd(const void* q, const void* k, const void* v,
         B200SD_CUDA(b200sd_launch(attn_delta_kernel, dim3(blocks), dim3(256), 0, s, static_cast<const bf16*>(out), static_cast<const bf16*>(dout),
                                   delta, batch, heads, Sq, d, ldo, lddo));
         COUNT_LAUNCH();
+    }
+    {
+        // tensor-core (tcgen05 / TMEM) kernels for the self-attention-sized shapes
+        static const bool no_tc = getenv("B200SD_ATTN_BWD_TC") && getenv("B200SD_ATTN_BWD_TC")[0] == '0';
+        if (!no_tc) {
+            const int rc = b200sd_attention_bwd_tc(static_cast<const bf16*>(q), static_cast<const bf16*>(k), static_cast<const bf16*>(v),
+                                                   static_cast<const bf16*>(dout), lse, delta, static_cast<bf16*>(dq), static_cast<bf16*>(dk),
+                                                   static_cast<bf16*>(dv), batch, heads, Sq, Skv, d, ldq, ldk, ldv, lddo, lddq, lddk, lddv,
+                                                   scale, s);
+            if (rc != B200SD_ERR_UNSUPPORTED) return rc;
+        }
     }
     BwdParams p;
     p.q = static_cast<const bf16*>(q); p.k = static_cast<const bf16*>(k); p.v = static_cast<const bf16*>(v);
