@@ -44,6 +44,23 @@ __device__ __forceinline__ float fast_exp2(float x) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+// packed fp32x2 math (FFMA2 / FADD2 / FMUL2): halves the non-MUFU instructions of the compute warps
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+    unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a), rb = *reinterpret_cast<unsigned long long*>(&b),
+                       rc = *reinterpret_cast<unsigned long long*>(&c), rd;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+    return *reinterpret_cast<float2*>(&rd);
+}
+__device__ __forceinline__ float2 fsub2(float2 a, float2 b) {
+    unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a), rb = *reinterpret_cast<unsigned long long*>(&b), rd;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+    return *reinterpret_cast<float2*>(&rd);
+}
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+    unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a), rb = *reinterpret_cast<unsigned long long*>(&b), rd;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+    return *reinterpret_cast<float2*>(&rd);
+}
 __device__ __forceinline__ void tmem_ld_x32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -80,11 +97,11 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_tc_kernel(const __grid_c
     uint64_t* x_full = bars;
     uint64_t* y_full = bars + 1;              // [STAGES]
     uint64_t* y_empty = bars + 1 + STAGES;    // [STAGES]
-    uint64_t* t_full = bars + 1 + 2 * STAGES;
-    uint64_t* p_full = t_full + 1;
-    uint64_t* p_empty = t_full + 2;
-    uint64_t* acc_full = t_full + 3;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_full + 4);
+    uint64_t* t_full = bars + 1 + 2 * STAGES;   // [2]: one per 64-row half of the streamed tile
+    uint64_t* p_full = t_full + 2;              // [2]
+    uint64_t* p_empty = t_full + 4;             // [2]
+    uint64_t* acc_full = t_full + 6;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_full + 7);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int x0 = blockIdx.x * kT, h = blockIdx.y, b = blockIdx.z;
@@ -102,9 +119,11 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_tc_kernel(const __grid_c
             ptx::mbar_init(&y_full[i], 1);
             ptx::mbar_init(&y_empty[i], 1);
         }
-        ptx::mbar_init(t_full, 1);
-        ptx::mbar_init(p_full, 256);
-        ptx::mbar_init(p_empty, 1);
+        for (int i = 0; i < 2; ++i) {
+            ptx::mbar_init(&t_full[i], 1);
+            ptx::mbar_init(&p_full[i], 256);
+            ptx::mbar_init(&p_empty[i], 1);
+        }
         ptx::mbar_init(acc_full, 1);
         ptx::fence_barrier_init();
     }
@@ -145,49 +164,73 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_tc_kernel(const __grid_c
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
+        // Software-pipelined over the two 64-row halves of every streamed tile: while the compute warps work on one half the
+        // tensor core runs the products of the other, and the next tile's first products are issued as soon as its TMEM
+        // columns have been read.
         if (ptx::elect_one()) {
-            const uint32_t idesc_t = ptx::umma_idesc_bf16(128, 128);
+            const uint32_t idesc_t = ptx::umma_idesc_bf16(128, 64);
             const uint32_t idesc_a = ptx::umma_idesc_bf16(128, DN) | (1u << 16);   // B operand MN-major
-            ptx::mbar_wait(x_full, 0);
-            for (int j = 0; j < num_tiles; ++j) {
-                const int st = j % STAGES;
-                const uint32_t ph = (uint32_t)(j / STAGES) & 1;
-                ptx::mbar_wait(&y_full[st], ph);
-                ptx::tc_fence_after();
-                // ---- T1 = X1 Y1^T, T2 = X2 Y2^T (both operands K-major over d) ----
+            auto issue_T = [&](int st, int half) {   // T1 / T2 columns [half*64, +64): X (128 rows) x 64 streamed rows, K over d
 #pragma unroll
                 for (int ks = 0; ks < KSTEPS; ++ks) {
                     const int kb = ks / 4, kin = ks % 4;
                     const uint64_t da = ptx::umma_desc_k_sw128(ptx::smem_u32(sX1 + kb * kBlk)) + 2 * kin;
-                    const uint64_t db = ptx::umma_desc_k_sw128(ptx::smem_u32(sY1 + (st * DKB + kb) * kBlk)) + 2 * kin;
-                    ptx::umma_bf16_ss(tT1, da, db, idesc_t, ks > 0 ? 1u : 0u);
+                    const uint64_t db = ptx::umma_desc_k_sw128(ptx::smem_u32(sY1 + (st * DKB + kb) * kBlk) + half * 8192) + 2 * kin;
+                    ptx::umma_bf16_ss(tT1 + half * 64, da, db, idesc_t, ks > 0 ? 1u : 0u);
                 }
 #pragma unroll
                 for (int ks = 0; ks < KSTEPS; ++ks) {
                     const int kb = ks / 4, kin = ks % 4;
                     const uint64_t da = ptx::umma_desc_k_sw128(ptx::smem_u32(sX2 + kb * kBlk)) + 2 * kin;
-                    const uint64_t db = ptx::umma_desc_k_sw128(ptx::smem_u32(sY2 + (st * DKB + kb) * kBlk)) + 2 * kin;
-                    ptx::umma_bf16_ss(tT2, da, db, idesc_t, ks > 0 ? 1u : 0u);
+                    const uint64_t db = ptx::umma_desc_k_sw128(ptx::smem_u32(sY2 + (st * DKB + kb) * kBlk) + half * 8192) + 2 * kin;
+                    ptx::umma_bf16_ss(tT2 + half * 64, da, db, idesc_t, ks > 0 ? 1u : 0u);
                 }
-                ptx::umma_commit(t_full);
-                // ---- accumulate: A2 += dS Y1 (and A1 += P Y2 for DKV); A from smem (K-major over the streamed index),
-                //      B = the streamed tile read MN-major: 16 streamed rows per k-step = 2048 B, next 64 d-columns = kBlk ----
-                ptx::mbar_wait(p_full, j & 1);
-                ptx::tc_fence_after();
+                ptx::umma_commit(&t_full[half]);
+            };
+            auto issue_acc = [&](int j, int st, int half) {   // A2 += dS Y1 (A1 += P Y2): 64 streamed rows = 4 k-steps
 #pragma unroll
-                for (int ks = 0; ks < 8; ++ks) {
-                    const int kk = ks / 4, kin = ks % 4;
+                for (int kin = 0; kin < 4; ++kin) {
+                    const int ks = half * 4 + kin;
+                    const uint32_t acc = (j > 0 || ks > 0) ? 1u : 0u;
                     if constexpr (DKV) {
-                        const uint64_t da = ptx::umma_desc_k_sw128(ptx::smem_u32(sP + kk * kBlk)) + 2 * kin;
+                        const uint64_t da = ptx::umma_desc_k_sw128(ptx::smem_u32(sP + half * kBlk)) + 2 * kin;
                         const uint64_t db = ptx::umma_desc_mn_sw128(ptx::smem_u32(sY2 + st * DKB * kBlk) + ks * 2048, kBlk);
-                        ptx::umma_bf16_ss(tA1, da, db, idesc_a, (j > 0 || ks > 0) ? 1u : 0u);
+                        ptx::umma_bf16_ss(tA1, da, db, idesc_a, acc);
                     }
-                    const uint64_t da2 = ptx::umma_desc_k_sw128(ptx::smem_u32(sdS + kk * kBlk)) + 2 * kin;
+                    const uint64_t da2 = ptx::umma_desc_k_sw128(ptx::smem_u32(sdS + half * kBlk)) + 2 * kin;
                     const uint64_t db2 = ptx::umma_desc_mn_sw128(ptx::smem_u32(sY1 + st * DKB * kBlk) + ks * 2048, kBlk);
-                    ptx::umma_bf16_ss(tA2, da2, db2, idesc_a, (j > 0 || ks > 0) ? 1u : 0u);
+                    ptx::umma_bf16_ss(tA2, da2, db2, idesc_a, acc);
                 }
+                ptx::umma_commit(&p_empty[half]);
+            };
+            ptx::mbar_wait(x_full, 0);
+            ptx::mbar_wait(&y_full[0], 0);
+            ptx::tc_fence_after();
+            issue_T(0, 0);
+            issue_T(0, 1);
+            for (int j = 0; j < num_tiles; ++j) {
+                const int st = j % STAGES, stn = (j + 1) % STAGES;
+                const bool more = j + 1 < num_tiles;
+                ptx::mbar_wait(&p_full[0], j & 1);           // half 0 of tile j: T columns read, P / dS written
+                ptx::tc_fence_after();
+                issue_acc(j, st, 0);
+                if (more && STAGES > 1) {
+                    ptx::mbar_wait(&y_full[stn], (uint32_t)((j + 1) / STAGES) & 1);
+                    ptx::tc_fence_after();
+                    issue_T(stn, 0);
+                }
+                ptx::mbar_wait(&p_full[1], j & 1);
+                ptx::tc_fence_after();
+                issue_acc(j, st, 1);
                 ptx::umma_commit(&y_empty[st]);
-                ptx::umma_commit(p_empty);
+                if (more) {
+                    if (STAGES == 1) {   // single-stage ring: the next tile can only land after this one has been consumed
+                        ptx::mbar_wait(&y_full[stn], (uint32_t)((j + 1) / STAGES) & 1);
+                        ptx::tc_fence_after();
+                        issue_T(stn, 0);
+                    }
+                    issue_T(stn, 1);
+                }
             }
             ptx::umma_commit(acc_full);
         }
@@ -204,48 +247,50 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_tc_kernel(const __grid_c
         }
         for (int j = 0; j < num_tiles; ++j) {
             const int st = j % STAGES;
-            ptx::mbar_wait(t_full, j & 1);
-            ptx::tc_fence_after();
-            if (j > 0) ptx::mbar_wait(p_empty, (j - 1) & 1);   // the previous tile's accumulating MMAs have read sP / sdS
             const float* lse_s = sVec + (st * 2) * kT;
             const float* del_s = sVec + (st * 2 + 1) * kT;
 #pragma unroll
-            for (int cc = 0; cc < 64; cc += 32) {
-                const int c = half * 64 + cc;
+            for (int hh = 0; hh < 2; ++hh) {             // the two 64-row halves of the streamed tile
+                ptx::mbar_wait(&t_full[hh], j & 1);
+                ptx::tc_fence_after();
+                if (j > 0) ptx::mbar_wait(&p_empty[hh], (j - 1) & 1);   // the previous tile's accumulating MMAs have read this block
+                const int cc = half * 32;                // this thread's 32 columns inside the 64-column half
+                const int c = hh * 64 + cc;
                 uint32_t r1[32], r2[32];
                 tmem_ld_x32(tT1 + lane_addr + c, r1);
                 tmem_ld_x32(tT2 + lane_addr + c, r2);
                 ptx::tmem_ld_wait();
                 uint32_t pk[16], dk[16];
 #pragma unroll
+                const float2 sl2v = make_float2(p.scale_log2, p.scale_log2);
                 for (int i = 0; i < 16; ++i) {
-                    float l0, l1, e0, e1;
+                    float2 nl, dl;     // -lse and delta of this column pair
                     if constexpr (DKV) {
                         const float2 lv = *reinterpret_cast<const float2*>(lse_s + c + 2 * i);
-                        const float2 dv = *reinterpret_cast<const float2*>(del_s + c + 2 * i);
-                        l0 = lv.x; l1 = lv.y; e0 = dv.x; e1 = dv.y;
+                        nl = make_float2(-lv.x, -lv.y);
+                        dl = *reinterpret_cast<const float2*>(del_s + c + 2 * i);
                     } else {
-                        l0 = l1 = lse_r; e0 = e1 = del_r;
+                        nl = make_float2(-lse_r, -lse_r);
+                        dl = make_float2(del_r, del_r);
                     }
-                    const float p0 = fast_exp2(fmaf(__uint_as_float(r1[2 * i]), p.scale_log2, -l0));
-                    const float p1 = fast_exp2(fmaf(__uint_as_float(r1[2 * i + 1]), p.scale_log2, -l1));
-                    const float d0 = p0 * (__uint_as_float(r2[2 * i]) - e0);
-                    const float d1 = p1 * (__uint_as_float(r2[2 * i + 1]) - e1);
-                    pk[i] = pack_bf16x2(p0, p1);
-                    dk[i] = pack_bf16x2(d0, d1);
+                    const float2 t = ffma2(make_float2(__uint_as_float(r1[2 * i]), __uint_as_float(r1[2 * i + 1])), sl2v, nl);
+                    const float2 pe = make_float2(fast_exp2(t.x), fast_exp2(t.y));
+                    const float2 ds = fmul2(pe, fsub2(make_float2(__uint_as_float(r2[2 * i]), __uint_as_float(r2[2 * i + 1])), dl));
+                    pk[i] = pack_bf16x2(pe.x, pe.y);
+                    dk[i] = pack_bf16x2(ds.x, ds.y);
                 }
-                uint8_t* bp = sP + half * kBlk + row * 128;
-                uint8_t* bd = sdS + half * kBlk + row * 128;
+                uint8_t* bp = sP + hh * kBlk + row * 128;
+                uint8_t* bd = sdS + hh * kBlk + row * 128;
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {   // four 16-byte chunks (8 streamed rows each) of this 32-column piece
                     const int chunk = (cc / 8 + g) ^ (row & 7);
                     if constexpr (DKV) *reinterpret_cast<uint4*>(bp + chunk * 16) = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
                     *reinterpret_cast<uint4*>(bd + chunk * 16) = make_uint4(dk[4 * g], dk[4 * g + 1], dk[4 * g + 2], dk[4 * g + 3]);
                 }
+                ptx::tc_fence_before();
+                ptx::fence_proxy_async();   // generic-proxy smem writes -> visible to the tensor core (async proxy)
+                ptx::mbar_arrive(&p_full[hh]);
             }
-            ptx::tc_fence_before();
-            ptx::fence_proxy_async();   // generic-proxy smem writes -> visible to the tensor core (async proxy)
-            ptx::mbar_arrive(p_full);
         }
         // ---- accumulators -> bf16 global (row per thread; half 0 stores A1 = dV, half 1 stores A2 = dK / dQ (scaled)) ----
         ptx::mbar_wait(acc_full, 0);
