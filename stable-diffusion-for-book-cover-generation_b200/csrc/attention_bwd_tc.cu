@@ -17,6 +17,7 @@
 //               tcgen05.ld, exp2 / FMA in fp32, bf16 P^T / dS^T written into 128B-swizzled smem tiles (the A operands
 //               of the accumulating MMAs); at the end the accumulators are scaled and stored as bf16.
 #include <atomic>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -72,6 +73,13 @@ __device__ __forceinline__ void tmem_ld_x32(uint32_t taddr, uint32_t (&r)[32]) {
         : "r"(taddr)
         : "memory");
 }
+__device__ __forceinline__ void tmem_st_x16(uint32_t taddr, const uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]),
+        "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
 __device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(ptx::smem_u32(dst)),
                  "l"(src), "r"(bytes), "r"(ptx::smem_u32(bar))
@@ -79,7 +87,10 @@ __device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_
 }
 
 // D = head dim (40 / 80); DKB = 64-wide blocks covering it; STAGES = ring depth of the streamed operands
-template <int D, int DKB, int STAGES, bool DKV>
+// ATMEM: P^T / dS^T (the A operands of the accumulating products) are handed to the tensor core through TMEM
+// (tcgen05.st by the compute threads, tcgen05.mma with the A operand in TMEM) instead of 64 KB of swizzled smem tiles:
+// the kernel is shared-memory-bandwidth bound otherwise (~256 KB of smem traffic per 128x128 tile pair).
+template <int D, int DKB, int STAGES, bool DKV, bool ATMEM>
 __global__ void __launch_bounds__(kThreads, 1) attn_bwd_tc_kernel(const __grid_constant__ BwdTcParams p) {
     constexpr int DN = (D + 15) / 16 * 16;     // MMA N of the accumulating products (48 / 80)
     constexpr int KSTEPS = (D + 15) / 16;      // UMMA K steps over the head dim
@@ -135,7 +146,10 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_tc_kernel(const __grid_c
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t tT1 = tmem_base, tT2 = tmem_base + 128, tA1 = tmem_base + 256, tA2 = tmem_base + 384;
+    // TMEM columns: T1 [0,128) T2 [128,256); accumulators A1 [256,..) A2 [320,..) (ATMEM) or [384,..);
+    // ATMEM: P^T operand [384,448), dS^T operand [448,512): 64 bf16 (= 32 columns) per 64-row half of the streamed tile
+    const uint32_t tT1 = tmem_base, tT2 = tmem_base + 128, tA1 = tmem_base + 256, tA2 = tmem_base + (ATMEM ? 320 : 384);
+    const uint32_t tP = tmem_base + 384, tdS = tmem_base + 448;
     ptx::pdl_wait();
 
     if (warp == 0) {
@@ -193,13 +207,13 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_tc_kernel(const __grid_c
                     const int ks = half * 4 + kin;
                     const uint32_t acc = (j > 0 || ks > 0) ? 1u : 0u;
                     if constexpr (DKV) {
-                        const uint64_t da = ptx::umma_desc_k_sw128(ptx::smem_u32(sP + half * kBlk)) + 2 * kin;
                         const uint64_t db = ptx::umma_desc_mn_sw128(ptx::smem_u32(sY2 + st * DKB * kBlk) + ks * 2048, kBlk);
-                        ptx::umma_bf16_ss(tA1, da, db, idesc_a, acc);
+                        if constexpr (ATMEM) ptx::umma_bf16_ts(tA1, tP + half * 32 + kin * 8, db, idesc_a, acc);
+                        else ptx::umma_bf16_ss(tA1, ptx::umma_desc_k_sw128(ptx::smem_u32(sP + half * kBlk)) + 2 * kin, db, idesc_a, acc);
                     }
-                    const uint64_t da2 = ptx::umma_desc_k_sw128(ptx::smem_u32(sdS + half * kBlk)) + 2 * kin;
                     const uint64_t db2 = ptx::umma_desc_mn_sw128(ptx::smem_u32(sY1 + st * DKB * kBlk) + ks * 2048, kBlk);
-                    ptx::umma_bf16_ss(tA2, da2, db2, idesc_a, acc);
+                    if constexpr (ATMEM) ptx::umma_bf16_ts(tA2, tdS + half * 32 + kin * 8, db2, idesc_a, acc);
+                    else ptx::umma_bf16_ss(tA2, ptx::umma_desc_k_sw128(ptx::smem_u32(sdS + half * kBlk)) + 2 * kin, db2, idesc_a, acc);
                 }
                 ptx::umma_commit(&p_empty[half]);
             };
@@ -279,16 +293,24 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_tc_kernel(const __grid_c
                     pk[i] = pack_bf16x2(pe.x, pe.y);
                     dk[i] = pack_bf16x2(ds.x, ds.y);
                 }
-                uint8_t* bp = sP + hh * kBlk + row * 128;
-                uint8_t* bd = sdS + hh * kBlk + row * 128;
+                if constexpr (ATMEM) {
+                    // this thread's 32 streamed rows = 16 packed columns of its lane in the A-operand region of this half
+                    if constexpr (DKV) tmem_st_x16(tP + lane_addr + hh * 32 + half * 16, pk);
+                    tmem_st_x16(tdS + lane_addr + hh * 32 + half * 16, dk);
+                    ptx::tmem_st_wait();
+                    ptx::tc_fence_before();
+                } else {
+                    uint8_t* bp = sP + hh * kBlk + row * 128;
+                    uint8_t* bd = sdS + hh * kBlk + row * 128;
 #pragma unroll
-                for (int g = 0; g < 4; ++g) {   // four 16-byte chunks (8 streamed rows each) of this 32-column piece
-                    const int chunk = (cc / 8 + g) ^ (row & 7);
-                    if constexpr (DKV) *reinterpret_cast<uint4*>(bp + chunk * 16) = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
-                    *reinterpret_cast<uint4*>(bd + chunk * 16) = make_uint4(dk[4 * g], dk[4 * g + 1], dk[4 * g + 2], dk[4 * g + 3]);
+                    for (int g = 0; g < 4; ++g) {   // four 16-byte chunks (8 streamed rows each) of this 32-column piece
+                        const int chunk = (cc / 8 + g) ^ (row & 7);
+                        if constexpr (DKV) *reinterpret_cast<uint4*>(bp + chunk * 16) = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+                        *reinterpret_cast<uint4*>(bd + chunk * 16) = make_uint4(dk[4 * g], dk[4 * g + 1], dk[4 * g + 2], dk[4 * g + 3]);
+                    }
+                    ptx::tc_fence_before();
+                    ptx::fence_proxy_async();   // generic-proxy smem writes -> visible to the tensor core (async proxy)
                 }
-                ptx::tc_fence_before();
-                ptx::fence_proxy_async();   // generic-proxy smem writes -> visible to the tensor core (async proxy)
                 ptx::mbar_arrive(&p_full[hh]);
             }
         }
@@ -336,15 +358,15 @@ int make_map(CUtensorMap* m, const bf16* ptr, int D, int heads, int64_t rows, in
     return b200sd_make_tmap(m, ptr, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
-template <int D, int DKB, int STAGES, bool DKV>
+template <int D, int DKB, int STAGES, bool DKV, bool ATMEM>
 int launch_one(const BwdTcParams& p, int batch, cudaStream_t s) {
     const size_t smem = (size_t)(2 * DKB + 2 * STAGES * DKB + 4) * kBlk + STAGES * 2 * kT * 4 + 256 + 1024;
     static bool configured = false;
     if (!configured) {
-        B200SD_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<D, DKB, STAGES, DKV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        B200SD_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<D, DKB, STAGES, DKV, ATMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
-    B200SD_CUDA(b200sd_launch(attn_bwd_tc_kernel<D, DKB, STAGES, DKV>, dim3(p.Sx / kT, p.heads, batch), dim3(kThreads), smem, s, p));
+    B200SD_CUDA(b200sd_launch(attn_bwd_tc_kernel<D, DKB, STAGES, DKV, ATMEM>, dim3(p.Sx / kT, p.heads, batch), dim3(kThreads), smem, s, p));
     g_b200sd_launches.fetch_add(1, std::memory_order_relaxed);
     B200SD_LAUNCH_CHECK();
     return B200SD_OK;
@@ -380,10 +402,16 @@ int b200sd_attention_bwd_tc(const bf16* q, const bf16* k, const bf16* v, const b
     if ((rc = make_map(&pq.tmY2, v, d, heads, (int64_t)batch * Skv, ldv))) return rc;
     pq.lse = lse; pq.delta = delta; pq.out1 = nullptr; pq.out2 = dq; pq.Sx = Sq; pq.Sy = Skv; pq.heads = heads; pq.ld1 = 0; pq.ld2 = lddq;
     pq.scale = scale; pq.scale_log2 = scale * 1.4426950408889634f;
+    static const bool a_smem = getenv("B200SD_ATTN_BWD_ATMEM") && getenv("B200SD_ATTN_BWD_ATMEM")[0] == '0';
     if (d == 40) {
-        if ((rc = launch_one<40, 1, 2, false>(pq, batch, s))) return rc;
-        return launch_one<40, 1, 2, true>(pk, batch, s);
+        if (a_smem) {
+            if ((rc = launch_one<40, 1, 2, false, false>(pq, batch, s))) return rc;
+            return launch_one<40, 1, 2, true, false>(pk, batch, s);
+        }
+        if ((rc = launch_one<40, 1, 2, false, true>(pq, batch, s))) return rc;
+        return launch_one<40, 1, 2, true, true>(pk, batch, s);
     }
-    if ((rc = launch_one<80, 2, 1, false>(pq, batch, s))) return rc;
-    return launch_one<80, 2, 1, true>(pk, batch, s);
+    // d = 80: 2 x 80 accumulator columns leave no room for the TMEM-resident A operands
+    if ((rc = launch_one<80, 2, 1, false, false>(pq, batch, s))) return rc;
+    return launch_one<80, 2, 1, true, false>(pk, batch, s);
 }
