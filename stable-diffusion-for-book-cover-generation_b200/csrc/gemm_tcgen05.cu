@@ -267,9 +267,13 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tcgen05_kernel(const __gr
                 else { img = m_tile / p.tiles_y; y0 = (m_tile % p.tiles_y) * p.tile_h; }
             }
             // pair mode: this CTA loads its own A rows and half of the B tile; completion is signalled on the leader's barrier
-            const int nboxb = (p.block_n >> 6) >> (pair ? 1 : 0);   // 64-column boxes of an MN-major B tile held by this CTA
+            // MN-major B: only the 64-column boxes that hold existing columns are loaded (the last N tile of a layer may be
+            // narrower than block_n: N = 320 runs as 192 + 128); a pair splits the full tile evenly and keeps it whole
+            const int nbox_live = (b_mode != 0 && !pair) ? (col_valid + 63) >> 6 : (p.block_n >> 6);
+            const int nboxb = nbox_live >> (pair ? 1 : 0);   // 64-column boxes of an MN-major B tile held by this CTA
             const int nb0 = n0 + (pair ? (int)crank * (p.block_n >> 1) : 0);
-            const uint32_t stage_tx = (uint32_t)(p.a_bytes + b_bytes) << (pair ? 1 : 0);
+            const uint32_t stage_tx = (b_mode != 0 && !pair) ? (uint32_t)(p.a_bytes + nbox_live * 8192)
+                                                             : ((uint32_t)(p.a_bytes + b_bytes) << (pair ? 1 : 0));
             for (int kb = kb_begin; kb < kb_end; ++kb) {
                 ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
                 if (!pair || crank == 0) ptx::mbar_expect_tx(&full_bar[stage], stage_tx);
@@ -325,7 +329,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tcgen05_kernel(const __gr
         // ================= MMA issuer (one elected thread) =================
         if ((!pair || crank == 0) && ptx::elect_one()) {
             const uint32_t b_mn = b_mode != 0;
-            const uint32_t idesc = ptx::umma_idesc_bf16(pair ? 2 * BLOCK_M : BLOCK_M, (uint32_t)p.block_n) | ((uint32_t)a_mn << 15) | (b_mn << 16);
+            const uint32_t mma_n = (b_mode != 0 && !pair) ? (uint32_t)(((col_valid + 63) >> 6) << 6) : (uint32_t)p.block_n;   // live boxes only
+            const uint32_t idesc = ptx::umma_idesc_bf16(pair ? 2 * BLOCK_M : BLOCK_M, mma_n) | ((uint32_t)a_mn << 15) | (b_mn << 16);
             // K-major: +32 B per UMMA_K inside the swizzle atom; MN-major: 16 k-rows = two 1024-byte atoms further
             const uint32_t a_step = a_mn ? (2048 >> 4) : 2, b_step = b_mn ? (2048 >> 4) : 2;
             int stage = 0;
@@ -569,8 +574,9 @@ bool want_pair(int request, int split, int m_tiles, int n_tiles, int k_blocks) {
 }
 
 // Tile width for MN-major B operands (64-column TMA boxes), from the sweep in tools/bwd_gemm_bench.py (B200, batch 8):
-// 128 wins or ties for dgrad (plain and conv) and conv wgrad; 192 for plain wgrad (long K, small output).  64 is never
-// better than 128 when N > 64 (the main loop is bound by the per-SM operand load rate: wider tiles reuse the A rows).
+// 128 wins or ties for dgrad (plain and conv) and conv wgrad (two CTAs per SM survive: 3 x 32 KB stages + the staging tile);
+// 192 for plain wgrad (long K, small output).  64 is never better than 128 when N > 64.  Wider tiles were re-measured after the
+// kernel learnt to load only the live boxes of a narrow last tile: still slower (one CTA per SM).
 // kind: 0 dgrad, 1 wgrad plain, 2 wgrad conv.
 int pick_block_n_mn(int N, int m_tiles, int kind) {
     int best;
