@@ -469,7 +469,7 @@ uint32_t pow2_cols(int n) {
     return c;
 }
 
-int pick_block_n(int N, int m_tiles, int epilogue) {
+int pick_block_n(int N, int m_tiles, int epilogue, bool can_split = false) {
     // Legal tile widths: multiple of 16 (32 for GEGLU), <= 256, dividing N.  Prefer 160 (two CTAs per SM,
     // 90 % of the smem read bandwidth the MMA needs); when that leaves the machine more than half empty
     // (small-M layers) fall to a narrower tile so more CTAs stream operands concurrently.
@@ -483,7 +483,9 @@ int pick_block_n(int N, int m_tiles, int epilogue) {
             if (N % bn == 0) { best = bn; break; }
         return best;
     }
-    if (epilogue == B200SD_EPI_LINEAR && (long)m_tiles * (N / best) * 2 <= sms) {
+    // Deep-K layers fill the machine with split-K clusters instead (measured, tools/conv_small_check.py: a 160-wide tile split
+    // 4-8 ways beats an 80-wide tile by 25-40 % on the M = 128 ... 2048 convs); only short-K layers narrow their tiles.
+    if (epilogue == B200SD_EPI_LINEAR && !can_split && (long)m_tiles * (N / best) * 2 <= sms) {
         for (int bn = 80; bn < best; bn += step)  // narrowest tile (>= 80) that still fits one wave
             if (N % bn == 0 && (long)m_tiles * (N / bn) <= sms) { best = bn; break; }
     }
@@ -678,28 +680,43 @@ extern "C" int b200sd_gemm(const b200sd_gemm_args* a, b200sd_stream_t stream) {
     }
 
     // ---- N tiling ----
-    int bn = a->block_n > 0 ? a->block_n : pick_block_n(a->N, m_tiles, a->epilogue);
+    static const bool no_split = getenv("B200SD_SPLITK") && getenv("B200SD_SPLITK")[0] == '0';
+    const bool can_split = !no_split && a->split_k <= 0 && a->epilogue == B200SD_EPI_LINEAR && p.num_k_blocks >= 32;
+    int bn = a->block_n > 0 ? a->block_n : pick_block_n(a->N, m_tiles, a->epilogue, can_split);
     B200SD_REQUIRE(bn >= 16 && bn <= 256 && bn % 16 == 0 && a->N % bn == 0, "gemm: bad block_n %d for N=%d", bn, a->N);
     B200SD_REQUIRE(a->epilogue != B200SD_EPI_GEGLU || bn % 32 == 0, "gemm: GEGLU needs block_n %% 32 == 0");
     p.block_n = bn;
-    const int n_tiles = a->N / bn;
+    int n_tiles = a->N / bn;
     p.tmem_cols = pow2_cols(bn);
 
     // ---- split-K: the splits of a tile form a thread-block cluster (<= 8 CTAs) and reduce over DSMEM ----
     const int sms = b200sd_num_sms();
     int split = a->split_k;
-    static const bool no_split = getenv("B200SD_SPLITK") && getenv("B200SD_SPLITK")[0] == '0';
     if (split <= 0) {
         split = 1;
         const int tiles = m_tiles * n_tiles;
         if (!no_split && a->epilogue == B200SD_EPI_LINEAR && tiles * 2 <= sms && p.num_k_blocks >= 32) {
-            while (split < 8 && tiles * split * 2 <= sms && p.num_k_blocks / (split * 2) >= 16) split *= 2;
+            while (split < 8 && tiles * split * 2 <= sms && p.num_k_blocks / (split * 2) >= 8) split *= 2;
+        }
+    }
+    int n_tiles_f = n_tiles;
+    if (a->split_k <= 0 && a->block_n <= 0 && can_split) {
+        // clusters of 8 only place well up to ~8 of them (measured: 16 clusters of 8 run as two waves); and when the split
+        // grid still leaves half the machine idle, halve the tile width instead of splitting deeper
+        const int tiles = m_tiles * n_tiles;
+        if (split == 8 && tiles > 8) split = 4;
+        if (split <= 4 && tiles * split * 2 <= sms && bn % 32 == 0 && bn / 2 >= 80) {
+            bn /= 2;
+            p.block_n = bn;
+            n_tiles_f = a->N / bn;
+            p.tmem_cols = pow2_cols(bn);
         }
     }
     B200SD_REQUIRE(split == 1 || a->epilogue == B200SD_EPI_LINEAR, "gemm: split-K only with the linear epilogue");
     B200SD_REQUIRE(split == 1 || split == 2 || split == 4 || split == 8, "gemm: split_k must be 1, 2, 4 or 8 (cluster size)");
     p.kb_per_split = ceil_div(p.num_k_blocks, split);
     B200SD_REQUIRE((split - 1) * p.kb_per_split < p.num_k_blocks, "gemm: split_k=%d leaves an empty split for K=%d", split, a->K);
+    n_tiles = n_tiles_f;
     p.split_k = split;
     p.pair = want_pair(a->pair, split, m_tiles, n_tiles, p.num_k_blocks) && bn % 32 == 0;
 

@@ -16,11 +16,17 @@ def timeit(fn, reps=20):
         e0.record(); g.replay(); e1.record(); torch.cuda.synchronize()
         best = min(best, e0.elapsed_time(e1) / reps)
     return best * 1e3
-for (B, H, W, Cin, Cout) in [(2, 8, 8, 1280, 1280), (2, 8, 8, 2560, 1280), (2, 16, 16, 1280, 1280), (2, 32, 32, 640, 640), (2, 32, 32, 1280, 640), (2, 64, 64, 320, 320)]:
+for (B, H, W, Cin, Cout) in [(2, 8, 8, 1280, 1280), (2, 8, 8, 2560, 1280), (2, 16, 16, 1280, 1280), (2, 16, 16, 2560, 1280), (2, 32, 32, 640, 640), (2, 32, 32, 1920, 640)]:
     x = torch.randn(B * H * W, Cin, device=DEV).bfloat16()
     wc = (torch.randn(Cout, 9 * Cin, device=DEV) / (9 * Cin) ** 0.5).bfloat16()
     o = torch.randn(B * H * W, Cout, device=DEV)
     bias = torch.randn(Cout, device=DEV)
-    args = ops.gemm(x, wc, o, conv=(B, H, W), bias=bias, residual=o, launch=False)
-    t = timeit(lambda: ops.gemm_run(args))
-    print(f"conv {B}x{H}x{W} {Cin}->{Cout}: {t:7.1f} us {2 * B * H * W * Cout * 9 * Cin / t / 1e6:6.0f} TF/s", flush=True)
+    row = f"conv {B}x{H}x{W} {Cin}->{Cout}:"
+    for bn, sk in ((0, 0), (160, 8), (160, 4), (80, 8), (80, 4), (80, 2), (160, 2), (64, 4), (128, 4)):
+        try:
+            args = ops.gemm(x, wc, o, conv=(B, H, W), bias=bias, residual=o, block_n=bn, split_k=sk, launch=False)
+            t = timeit(lambda: ops.gemm_run(args))
+            row += f" [bn{bn} sk{sk}] {t:5.1f}"
+        except Exception as e:
+            row += f" [bn{bn} sk{sk}] err"
+    print(row, flush=True)
