@@ -681,7 +681,7 @@ extern "C" int b200sd_gemm(const b200sd_gemm_args* a, b200sd_stream_t stream) {
 
     // ---- N tiling ----
     static const bool no_split = getenv("B200SD_SPLITK") && getenv("B200SD_SPLITK")[0] == '0';
-    const bool can_split = !no_split && a->split_k <= 0 && a->epilogue == B200SD_EPI_LINEAR && p.num_k_blocks >= 32;
+    const bool can_split = !no_split && a->split_k <= 0 && a->epilogue == B200SD_EPI_LINEAR && p.num_k_blocks >= 16;
     int bn = a->block_n > 0 ? a->block_n : pick_block_n(a->N, m_tiles, a->epilogue, can_split);
     B200SD_REQUIRE(bn >= 16 && bn <= 256 && bn % 16 == 0 && a->N % bn == 0, "gemm: bad block_n %d for N=%d", bn, a->N);
     B200SD_REQUIRE(a->epilogue != B200SD_EPI_GEGLU || bn % 32 == 0, "gemm: GEGLU needs block_n %% 32 == 0");
@@ -695,7 +695,7 @@ extern "C" int b200sd_gemm(const b200sd_gemm_args* a, b200sd_stream_t stream) {
     if (split <= 0) {
         split = 1;
         const int tiles = m_tiles * n_tiles;
-        if (!no_split && a->epilogue == B200SD_EPI_LINEAR && tiles * 2 <= sms && p.num_k_blocks >= 32) {
+        if (!no_split && a->epilogue == B200SD_EPI_LINEAR && tiles * 2 <= sms && p.num_k_blocks >= 16) {
             while (split < 8 && tiles * split * 2 <= sms && p.num_k_blocks / (split * 2) >= 8) split *= 2;
         }
     }
@@ -814,8 +814,24 @@ extern "C" int b200sd_gemm_dgrad(const b200sd_dgrad_args* a, b200sd_stream_t str
     p.block_n = bn;
     const int n_tiles = ceil_div(a->Cin, bn);
     p.tmem_cols = pow2_cols(bn);
-    p.split_k = 1;
-    p.kb_per_split = p.num_k_blocks;
+    // split-K clusters for the few-tile / deep-K layers (the 8x8 and 16x16 levels), same policy as the forward GEMM
+    int split = 1;
+    {
+        static const bool no_split = getenv("B200SD_SPLITK") && getenv("B200SD_SPLITK")[0] == '0';
+        const int sms = b200sd_num_sms();
+        const int tiles = m_tiles * n_tiles;
+        if (!no_split && !p.pair && tiles * 2 <= sms && p.num_k_blocks >= 16) {
+            while (split < 8 && tiles * split * 2 <= sms && p.num_k_blocks / (split * 2) >= 8) split *= 2;
+            if (split == 8 && tiles > 8) split = 4;
+        }
+    }
+    p.split_k = split;
+    p.kb_per_split = ceil_div(p.num_k_blocks, split);
+    while (split > 1 && (split - 1) * p.kb_per_split >= p.num_k_blocks) {   // never an empty split
+        split /= 2;
+        p.split_k = split;
+        p.kb_per_split = ceil_div(p.num_k_blocks, split);
+    }
     int rc;
     if (!p.conv) {
         const uint64_t dimsA[2] = {(uint64_t)a->Cout, (uint64_t)a->M};
@@ -836,7 +852,7 @@ extern "C" int b200sd_gemm_dgrad(const b200sd_dgrad_args* a, b200sd_stream_t str
         const uint32_t boxB[3] = {64, 1, BLOCK_K};
         if ((rc = b200sd_make_tmap(&p.tmB, a->w, 3, dimsB, strB, boxB, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
     }
-    return launch_gemm(p, m_tiles, n_tiles, 1, false, stream);
+    return launch_gemm(p, m_tiles, n_tiles, p.split_k, /*cluster=*/true, stream);
 }
 
 extern "C" int b200sd_gemm_wgrad(const b200sd_wgrad_args* a, b200sd_stream_t stream) {
