@@ -159,6 +159,13 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
 
     B = args.batch
+    if args.total_images > 0:
+        # BASELINE config 5: a fixed batch of images sharded over the GPUs (contiguous chunks, remainder to the low ranks;
+        # ranks left without an image idle) -> strong scaling, no collective on the data path
+        B = args.total_images // world + (1 if rank < args.total_images % world else 0)
+    idle = B == 0
+    if idle:
+        B = 1          # keeps the buffers valid; this rank runs no steps and contributes no images
     h, w = (96, 64) if args.portrait else (64, 64)
     torch.manual_seed(0)
     unet = UNet2DConditionModel().to(dev).eval()          # random-init weights of the SD v1.5 architecture
@@ -192,7 +199,7 @@ def run_ours(args):
 
     with torch.no_grad():
         for i in range(max(args.warmup, 3)):
-            step(i)
+            step(i)          # idle ranks warm up too (keeps the code path uniform), but run no timed steps
         eng = next(iter(unet._engines.values()))
         kernels_per_unet = getattr(eng, "kernels_per_graph", 0)
         # ---- device-resident timing ----
@@ -201,7 +208,7 @@ def run_ours(args):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         launches0 = ops.launch_count()
         e0.record()
-        for i in range(args.steps):
+        for i in range(0 if idle else args.steps):
             step(i)
         e1.record()
         barrier()
@@ -231,15 +238,19 @@ def run_ours(args):
             e2e_step(i)
         barrier()
         t0 = time.perf_counter()
-        for i in range(args.steps):
+        for i in range(0 if idle else args.steps):
             e2e_step(i)
         barrier()
         e2e_ms = (time.perf_counter() - t0) * 1e3
 
+        images_total = (0 if idle else B) * 1.0
         if world > 1:
             tt = torch.tensor([ms, e2e_ms], device=dev, dtype=torch.float64)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             ms, e2e_ms = float(tt[0]), float(tt[1])
+            ti = torch.tensor([images_total], device=dev, dtype=torch.float64)
+            dist.all_reduce(ti, op=dist.ReduceOp.SUM)
+            images_total = float(ti[0])
 
         # ---- roofline of the dominant kernel (tcgen05 GEMM / implicit-GEMM conv), timed live ----
         roof = None
@@ -277,17 +288,17 @@ def run_ours(args):
                "sample": f"{done} denoising iterations (CFG batch {2 * B}, fp32 oracle, 1 warm-up) in {t_total:.1f} s"}
 
     if rank == 0:
-        its = B * args.steps * world
+        its = (images_total if args.total_images > 0 else B * world) * args.steps
         value = its / (ms * 1e-3)
         e2e_value = its / (e2e_ms * 1e-3)
         flops_per_it = 2 * (1.2953e12 if args.portrait else FLOPS_PER_SAMPLE_64)
         line = {
             "metric": "unet_denoise_it_per_s", "value": value, "unit": "it/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32 (split-bf16 3-term products on the tensor cores)",
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "strong" if args.total_images > 0 else "weak", "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32 (split-bf16 3-term products on the tensor cores)",
             "data": "synthetic",
             "config": {"workload": "sd15_unet_ddim50_cfg7.5_" + ("512x768" if args.portrait else "512px"),
-                       "images_per_gpu": B, "unet_batch": 2 * B, "latent": f"4x{h}x{w}", "context": "77x768",
+                       "images_per_gpu": B, "total_images": args.total_images if args.total_images > 0 else B * world, "unet_batch": 2 * B, "latent": f"4x{h}x{w}", "context": "77x768",
                        "weights": "random-init SD v1.5 UNet (859.5M params)", "images_per_s": value / 50.0,
                        "e2e_images_per_s": e2e_value / 50.0, "tflops_end_to_end": value * flops_per_it / 1e12,
                        "l2": "no flush: the 1.72 GB of bf16 weights streamed every step exceed the 126 MB L2",
@@ -527,6 +538,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--batch", type=int, default=1, help="images per GPU (UNet batch = 2x with CFG)")
     ap.add_argument("--portrait", action="store_true", help="512x768 book-cover geometry (config 5)")
+    ap.add_argument("--total-images", type=int, default=0,
+                    help="config 5: shard this many images over the GPUs (strong scaling; overrides --batch)")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"], help="fp32 = the accuracy path (engine_fp32.py)")
     ap.add_argument("--impl", default="b200sd", choices=["b200sd", "reference"])
     ap.add_argument("--workload", default="sample", choices=["sample", "train", "train_text"],

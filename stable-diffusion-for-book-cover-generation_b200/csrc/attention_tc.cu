@@ -15,6 +15,7 @@
 // V is consumed K-major (keys contiguous), produced by a small transpose kernel into caller scratch.
 // With 100 KB smem and 256 TMEM columns two CTAs share an SM and fill each other's MMA/softmax bubbles.
 #include <atomic>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -25,7 +26,6 @@ namespace {
 
 constexpr int kQ = 128;     // query rows per CTA
 constexpr int kKV = 128;    // keys per tile
-constexpr int kThreads = 192;
 constexpr int kBlk = kQ * 128;  // bytes of one [128 rows x 64 bf16] swizzled block
 
 struct AttnParams {
@@ -103,13 +103,22 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)
 }
 
 // D = head dim (40 or 80); DKB = number of 64-wide blocks covering it (1 or 2)
-template <int D, int DKB>
-__global__ void __launch_bounds__(kThreads, (D <= 40) ? 2 : 1) attention_tc_kernel(const __grid_constant__ AttnParams p) {
+// HALVES = softmax threads per query row (1: warps 2-5 own whole rows; 2: warps 2-9, each thread owns 64 of the 128
+//          score columns and half of the O columns -- twice the warps to hide TMEM-load / MUFU latency behind)
+// LAZY   = single-pass softmax against a lagging reference max: tile j is exponentiated against the reference of
+//          tile j-1 while its own max is collected in the same pass; only when some row of the warp outgrew the
+//          reference by more than 2^kLazyThr is the tile redone against the true max (S is still in TMEM).
+constexpr float kLazyThr = 6.0f;
+
+template <int D, int DKB, int HALVES, bool LAZY>
+__global__ void __launch_bounds__(64 + 128 * HALVES, (D <= 40) ? 2 : 1) attention_tc_kernel(const __grid_constant__ AttnParams p) {
     constexpr int DN = (D + 15) / 16 * 16;    // MMA N of the PV product (48 / 80)
     constexpr int KSTEPS = (D + 15) / 16;     // UMMA K steps of the QK^T product
     constexpr int VBLK = D * 128;             // bytes of one V^T block [D rows x 64 keys]
     constexpr int VBLK_PAD = ((DN * 128 + 1023) / 1024) * 1024;  // padded so the MMA may read DN rows
     constexpr uint32_t kTmemCols = 256;
+    constexpr int CW = 128 / HALVES;          // score columns per softmax thread
+    constexpr int DNH = DN / HALVES;          // O columns per softmax thread (48 / 24 / 80 / 40)
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sQ = smem;                               // DKB blocks
@@ -127,6 +136,7 @@ __global__ void __launch_bounds__(kThreads, (D <= 40) ? 2 : 1) attention_tc_kern
     uint64_t* o_full = bars + 11;
     uint64_t* o_empty = bars + 12;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+    float* xch = reinterpret_cast<float*>(bars + 32);   // [2 parities][2 halves][128 rows] row exchange between half-threads
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q0 = blockIdx.x * kQ, h = blockIdx.y, b = blockIdx.z;
@@ -145,9 +155,9 @@ __global__ void __launch_bounds__(kThreads, (D <= 40) ? 2 : 1) attention_tc_kern
             ptx::mbar_init(&v_empty[i], 1);
         }
         ptx::mbar_init(s_full, 1);
-        ptx::mbar_init(p_full, 128);
+        ptx::mbar_init(p_full, 4 * HALVES);    // one (warp-aggregated) arrival per softmax warp
         ptx::mbar_init(o_full, 1);
-        ptx::mbar_init(o_empty, 128);
+        ptx::mbar_init(o_empty, 4 * HALVES);
         ptx::fence_barrier_init();
     }
     if (warp == 1) {
@@ -217,55 +227,66 @@ __global__ void __launch_bounds__(kThreads, (D <= 40) ? 2 : 1) attention_tc_kern
             }
         }
     } else {
-        // ================= softmax warps: one thread per query row =================
+        // ================= softmax warps: HALVES threads per query row =================
         // Software-pipelined: the fold of O_{j-1} into the register accumulator happens AFTER P_j has been
         // handed to the tensor core, so the P_{j-1} V_{j-1} product overlaps the softmax of tile j.
-        const int qd = warp & 3;
+        const int qd = warp & 3;                              // TMEM lane quadrant this warp may address
+        const int hf = (HALVES == 2) ? ((warp - 2) >> 2) : 0; // which half of the columns
         const int row = qd * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(qd * 32) << 16;
+        const uint32_t tS = tmem_S + lane_addr + hf * CW;
+        const uint32_t tO = tmem_O + lane_addr + hf * DNH;
         float m = -INFINITY, l = 0.f, corr_prev = 1.f;
-        float o[DN];
+        float o[DNH];
 #pragma unroll
-        for (int i = 0; i < DN; ++i) o[i] = 0.f;
+        for (int i = 0; i < DNH; ++i) o[i] = 0.f;
+
+        // value of the thread owning the other half of this row (double-buffered by exchange parity)
+        auto partner = [&](float v, int n) -> float {
+            if constexpr (HALVES == 1) {
+                return v;
+            } else {
+                float* x = xch + (n & 1) * 256;
+                x[hf * 128 + row] = v;
+                ptx::named_bar_sync(1 + qd, 64);
+                return x[(hf ^ 1) * 128 + row];
+            }
+        };
         auto fold_o = [&](int jj, float corr) {
             ptx::mbar_wait(o_full, jj & 1);
             ptx::tc_fence_after();
+            uint32_t r[DNH];
 #pragma unroll
-            for (int c = 0; c < DN; c += 16) {
-                uint32_t r[16];
-                ptx::tmem_ld_32x32b_x16(tmem_O + lane_addr + c, r);
-                ptx::tmem_ld_wait();
+            for (int c = 0; c + 16 <= DNH; c += 16) ptx::tmem_ld_32x32b_x16(tO + c, *reinterpret_cast<uint32_t(*)[16]>(&r[c]));
+            if constexpr (DNH % 16 == 8) ptx::tmem_ld_32x32b_x8(tO + DNH - 8, *reinterpret_cast<uint32_t(*)[8]>(&r[DNH - 8]));
+            ptx::tmem_ld_wait();
 #pragma unroll
-                for (int i = 0; i < 16; ++i) o[c + i] = o[c + i] * corr + __uint_as_float(r[i]);
-            }
+            for (int i = 0; i < DNH; ++i) o[i] = o[i] * corr + __uint_as_float(r[i]);
             ptx::tc_fence_before();
-            ptx::mbar_arrive(o_empty);
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(o_empty);
         };
-        for (int j = 0; j < num_tiles; ++j) {
-            ptx::mbar_wait(s_full, j & 1);
-            ptx::tc_fence_after();
-            // pass 1: row max of this tile (two TMEM loads in flight per wait)
+        auto max_pass = [&]() -> float {
             float mx = -INFINITY;
 #pragma unroll
-            for (int c = 0; c < 128; c += 64) {
+            for (int c = 0; c < CW; c += 64) {
                 uint32_t r0[32], r1[32];
-                tmem_ld_32x32b_x32(tmem_S + lane_addr + c, r0);
-                tmem_ld_32x32b_x32(tmem_S + lane_addr + c + 32, r1);
+                tmem_ld_32x32b_x32(tS + c, r0);
+                tmem_ld_32x32b_x32(tS + c + 32, r1);
                 ptx::tmem_ld_wait();
 #pragma unroll
                 for (int i = 0; i < 32; ++i) mx = fmax3(mx, __uint_as_float(r0[i]), __uint_as_float(r1[i]));
             }
-            const float mn = fmaxf(m, mx);
-            const float corr = fast_exp2((m - mn) * p.scale_log2);
-            const float off = mn * p.scale_log2;
-            m = mn;
-            // pass 2: P = exp2(S * scale - off) -> bf16 -> swizzled smem tile; row sum in fp32
+            return mx;
+        };
+        // P = exp2(S * scale - off) -> bf16 -> swizzled smem tile; returns the fp32 row sum (of this thread's columns)
+        auto exp_pass = [&](float off, bool track, float& mx) -> float {
             float2 rs2 = make_float2(0.f, 0.f);
             const float2 sc2 = make_float2(p.scale_log2, p.scale_log2), noff2 = make_float2(-off, -off);
 #pragma unroll
-            for (int c = 0; c < 128; c += 32) {
+            for (int c = 0; c < CW; c += 32) {
                 uint32_t r[32];
-                tmem_ld_32x32b_x32(tmem_S + lane_addr + c, r);
+                tmem_ld_32x32b_x32(tS + c, r);
                 ptx::tmem_ld_wait();
                 uint32_t pk[16];
 #pragma unroll
@@ -274,34 +295,63 @@ __global__ void __launch_bounds__(kThreads, (D <= 40) ? 2 : 1) attention_tc_kern
                     const float2 e = make_float2(fast_exp2(t.x), fast_exp2(t.y));
                     rs2 = fadd2(rs2, e);
                     pk[i] = pack_bf16x2(e.x, e.y);
+                    if (track) mx = fmax3(mx, __uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
                 }
-                uint8_t* blk = sP + (c / 64) * kBlk + row * 128;
+                const int col = hf * CW + c;
+                uint8_t* blk = sP + (col / 64) * kBlk + row * 128;
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {   // four 16-byte chunks (8 keys each)
-                    const int chunk = ((c % 64) / 8 + g) ^ (row & 7);
+                    const int chunk = ((col % 64) / 8 + g) ^ (row & 7);
                     *reinterpret_cast<uint4*>(blk + chunk * 16) = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
                 }
             }
-            l = l * corr + (rs2.x + rs2.y);
+            return rs2.x + rs2.y;
+        };
+
+        for (int j = 0; j < num_tiles; ++j) {
+            ptx::mbar_wait(s_full, j & 1);
+            ptx::tc_fence_after();
+            float mx = -INFINITY, rs = 0.f, corr = 1.f;
+            bool redo = true;
+            if (LAZY && j > 0) {
+                rs = exp_pass(m * p.scale_log2, true, mx);
+                mx = fmaxf(mx, partner(mx, j));
+                redo = __any_sync(0xffffffffu, (mx - m) * p.scale_log2 > kLazyThr);
+            } else {
+                mx = max_pass();
+                mx = fmaxf(mx, partner(mx, j));
+            }
+            if (redo) {   // warp-uniform, and identical in the two warps sharing these rows
+                const float mn = fmaxf(m, mx);
+                corr = fast_exp2((m - mn) * p.scale_log2);
+                m = mn;
+                float unused = 0.f;
+                rs = exp_pass(mn * p.scale_log2, false, unused);
+            }
+            l = l * corr + rs;
             ptx::tc_fence_before();
             ptx::fence_proxy_async();   // generic-proxy smem writes -> visible to the tensor core (async proxy)
-            ptx::mbar_arrive(p_full);
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(p_full);
             if (j > 0) fold_o(j - 1, corr_prev);   // P_{j-1} V_{j-1} ran while this tile's softmax was computed
             corr_prev = corr;
         }
         fold_o(num_tiles - 1, corr_prev);
         // ---- normalise and store ----
+        l += (HALVES == 2) ? partner(l, num_tiles) : 0.f;
         const float inv = 1.0f / l;
-        if (p.lse != nullptr) p.lse[((size_t)b * p.heads + h) * p.Sq + q0 + row] = m * p.scale_log2 + log2f(l);
-        bf16* dst = p.out + ((size_t)b * p.Sq + q0 + row) * p.ldo + h * D;
+        if (p.lse != nullptr && hf == 0) p.lse[((size_t)b * p.heads + h) * p.Sq + q0 + row] = m * p.scale_log2 + log2f(l);
+        bf16* dst = p.out + ((size_t)b * p.Sq + q0 + row) * p.ldo + h * D + hf * DNH;
 #pragma unroll
-        for (int c = 0; c < D; c += 8) {
-            uint4 u;
-            u.x = pack_bf16x2(o[c] * inv, o[c + 1] * inv);
-            u.y = pack_bf16x2(o[c + 2] * inv, o[c + 3] * inv);
-            u.z = pack_bf16x2(o[c + 4] * inv, o[c + 5] * inv);
-            u.w = pack_bf16x2(o[c + 6] * inv, o[c + 7] * inv);
-            *reinterpret_cast<uint4*>(dst + c) = u;
+        for (int c = 0; c < DNH; c += 8) {
+            if (hf * DNH + c < D) {
+                uint4 u;
+                u.x = pack_bf16x2(o[c] * inv, o[c + 1] * inv);
+                u.y = pack_bf16x2(o[c + 2] * inv, o[c + 3] * inv);
+                u.z = pack_bf16x2(o[c + 4] * inv, o[c + 5] * inv);
+                u.w = pack_bf16x2(o[c + 6] * inv, o[c + 7] * inv);
+                *reinterpret_cast<uint4*>(dst + c) = u;
+            }
         }
     }
 
@@ -313,7 +363,7 @@ __global__ void __launch_bounds__(kThreads, (D <= 40) ? 2 : 1) attention_tc_kern
     }
 }
 
-template <int D, int DKB>
+template <int D, int DKB, int HALVES, bool LAZY>
 int launch_tc(const bf16* q, const bf16* k, const bf16* vt, bf16* out, float* lse, int batch, int heads, int Sq, int Skv, int ldq,
               int ldk, int ldo, float scale, cudaStream_t s) {
     constexpr int DN = (D + 15) / 16 * 16;
@@ -348,14 +398,14 @@ int launch_tc(const bf16* q, const bf16* k, const bf16* vt, bf16* out, float* ls
     p.heads = heads;
     p.ldo = ldo;
     p.scale_log2 = scale * 1.4426950408889634f;
-    const size_t smem = (size_t)DKB * kBlk + 2 * DKB * kBlk + 4 * VBLK_PAD + 2 * kBlk + 256 + 1024;
+    const size_t smem = (size_t)DKB * kBlk + 2 * DKB * kBlk + 4 * VBLK_PAD + 2 * kBlk + 256 + 2048 + 1024;
     static bool configured = false;
     if (!configured) {
-        B200SD_CUDA(cudaFuncSetAttribute(attention_tc_kernel<D, DKB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        B200SD_CUDA(cudaFuncSetAttribute(attention_tc_kernel<D, DKB>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        B200SD_CUDA(cudaFuncSetAttribute(attention_tc_kernel<D, DKB, HALVES, LAZY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        B200SD_CUDA(cudaFuncSetAttribute(attention_tc_kernel<D, DKB, HALVES, LAZY>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         configured = true;
     }
-    B200SD_CUDA(b200sd_launch(attention_tc_kernel<D, DKB>, dim3(Sq / kQ, heads, batch), dim3(kThreads), smem, s, p));
+    B200SD_CUDA(b200sd_launch(attention_tc_kernel<D, DKB, HALVES, LAZY>, dim3(Sq / kQ, heads, batch), dim3(64 + 128 * HALVES), smem, s, p));
     g_b200sd_launches.fetch_add(1, std::memory_order_relaxed);
     B200SD_LAUNCH_CHECK();
     return B200SD_OK;
@@ -375,9 +425,24 @@ int b200sd_attention_tc(const void* q, const void* k, const void* v, void* out, 
     B200SD_CUDA(b200sd_launch(transpose_v_kernel, dim3(ceil_div(Skv, 64), ceil_div(d, 64), batch * heads), dim3(256), 0, s,
                               static_cast<const bf16*>(v), vt, Skv, heads, d, ldv));
     g_b200sd_launches.fetch_add(1, std::memory_order_relaxed);
-    if (d == 40)
-        return launch_tc<40, 1>(static_cast<const bf16*>(q), static_cast<const bf16*>(k), vt, static_cast<bf16*>(out), lse, batch,
-                                heads, Sq, Skv, ldq, ldk, ldo, scale, s);
-    return launch_tc<80, 2>(static_cast<const bf16*>(q), static_cast<const bf16*>(k), vt, static_cast<bf16*>(out), lse, batch, heads,
-                            Sq, Skv, ldq, ldk, ldo, scale, s);
+    // softmax organisation: B200SD_ATTN_FWD = 0 (4 warps, two passes), 1 (4 warps, lazy), 2 (8 warps, two passes), 3 (8 warps, lazy)
+    static const int variant = [] { const char* e = getenv("B200SD_ATTN_FWD"); return e ? atoi(e) : 3; }();
+#define B200SD_ATTN_GO(DD, KB, HV, LZ)                                                                                          \
+    return launch_tc<DD, KB, HV, LZ>(static_cast<const bf16*>(q), static_cast<const bf16*>(k), vt, static_cast<bf16*>(out), lse, \
+                                     batch, heads, Sq, Skv, ldq, ldk, ldo, scale, s)
+    if (d == 40) {
+        switch (variant) {
+            case 0: B200SD_ATTN_GO(40, 1, 1, false);
+            case 1: B200SD_ATTN_GO(40, 1, 1, true);
+            case 2: B200SD_ATTN_GO(40, 1, 2, false);
+            default: B200SD_ATTN_GO(40, 1, 2, true);
+        }
+    }
+    switch (variant) {
+        case 0: B200SD_ATTN_GO(80, 2, 1, false);
+        case 1: B200SD_ATTN_GO(80, 2, 1, true);
+        case 2: B200SD_ATTN_GO(80, 2, 2, false);
+        default: B200SD_ATTN_GO(80, 2, 2, true);
+    }
+#undef B200SD_ATTN_GO
 }
