@@ -1,19 +1,26 @@
 // b200sd -- flash attention on the sm_100a tensor cores (tcgen05 + TMEM), self-attention sized:
-// head dim 40 / 80, S_q and S_kv multiples of 128 (the 64x64 and 32x32 levels of the UNet: 98 % of the
+// head dim 40 / 80, S_q a multiple of 128 and S_kv of 64 (the 64x64 and 32x32 levels of the UNet: 98 % of the
 // attention FLOPs).  Other shapes keep the register-resident kernel in attention.cu.
 //
-// One CTA = 128 query rows of one (batch, head); it streams 128-key tiles:
-//   warp 0    : TMA producer   Q once; K_j, V^T_j through a 2-stage smem ring (128B-swizzled boxes).  The
-//               q/k/v buffers are addressed as 3-D tensors (d, head, row), so a 64-wide box over a 40-wide
-//               head is zero-filled past the head by TMA -- no padding kernels, no masking.
+// One CTA = 128 query rows of one (batch, head); it streams 64-key tiles and its softmax warps never wait for the
+// tensor core:
+//   warp 0    : TMA producer   Q once; K_j, V^T_j through a 4-stage smem ring (128B-swizzled boxes).  The q/k/v
+//               buffers are addressed as 3-D tensors (d, head, row), so a 64-wide box over a 40-wide head is
+//               zero-filled past the head by TMA -- no padding kernels, no masking.
 //   warp 1    : TMEM allocator + single-thread MMA issuer:
-//                   S_j   = Q K_j^T          (M128 x N128, K = d)      -> TMEM columns [0,128)
-//                   O_j   = P_j V_j          (M128 x N = d, K = 128)   -> TMEM columns [128, 128+d)
-//   warps 2-5 : softmax, one thread per query row (its TMEM lane): tcgen05.ld S, online max / exp2 / sum in
-//               fp32, P_j written as bf16 into a swizzled smem tile (the A operand of the second MMA), then
-//               O_j is read back and folded into register accumulators with the running-max correction.
+//                   S_j   = Q K_j^T     (M128 x N64, K = d)  -> TMEM, double-buffered: QK^T of tile j+1 is issued before
+//                                                              the softmax of tile j has finished
+//                   O    += P_j V_j     (M128 x N = d, K = 64), P_j read from TMEM (A operand), O resident in TMEM
+//   warps 2-5 : softmax, one thread per query row (its TMEM lane): tcgen05.ld S_j, exp2 in fp32 against a LAGGING
+//               reference max (single pass; the tile max is collected on the side), P_j written back as bf16 over the
+//               S columns it came from (tcgen05.st) -- no shared-memory P tile, no proxy fence.  Only when a row
+//               outgrows the reference by 2^kLazyThr is the tile redone (scores are still in registers) and the O
+//               rows rescaled in TMEM.  The softmax is MUFU-bound (16 ex2/clk/SM); every 4th score pair is
+//               exponentiated on the FMA pipe instead (Cody-Waite + cubic).
 // V is consumed K-major (keys contiguous), produced by a small transpose kernel into caller scratch.
-// With 100 KB smem and 256 TMEM columns two CTAs share an SM and fill each other's MMA/softmax bubbles.
+// TMEM columns: S0/P0 [0,64)  S1/P1 [64,128)  O [128,128+DN); two CTAs share an SM at d=40.
+// Measured (B200, d=40, S=4096): batch 2 145 -> 117 us, batch 8 480 -> 372 us against the first version (128-key
+// tiles, S single-buffered, P through shared memory, O folded in registers every tile, two-pass softmax).
 #include <atomic>
 #include <cstdlib>
 #include <cstring>
@@ -25,7 +32,6 @@ extern std::atomic<long long> g_b200sd_launches;
 namespace {
 
 constexpr int kQ = 128;     // query rows per CTA
-constexpr int kKV = 128;    // keys per tile
 constexpr int kBlk = kQ * 128;  // bytes of one [128 rows x 64 bf16] swizzled block
 
 struct AttnParams {
@@ -34,6 +40,7 @@ struct AttnParams {
     float* lse;   // optional [batch][heads][Sq]: log2-domain log-sum-exp of the scaled scores (for the backward)
     int Sq, Skv, heads, ldo;
     float scale_log2;
+    float lazy_thr;   // log2 units a row may outgrow the lagging reference max before its tile is redone
 };
 
 // V [B*Skv, ldv] (head h at columns h*D..) -> Vt [B*H][D][Skv]
@@ -102,41 +109,64 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)
         : "memory");
 }
 
-// D = head dim (40 or 80); DKB = number of 64-wide blocks covering it (1 or 2)
-// HALVES = softmax threads per query row (1: warps 2-5 own whole rows; 2: warps 2-9, each thread owns 64 of the 128
-//          score columns and half of the O columns -- twice the warps to hide TMEM-load / MUFU latency behind)
-// LAZY   = single-pass softmax against a lagging reference max: tile j is exponentiated against the reference of
-//          tile j-1 while its own max is collected in the same pass; only when some row of the warp outgrew the
-//          reference by more than 2^kLazyThr is the tile redone against the true max (S is still in TMEM).
+// log2 units a row may outgrow the lagging reference max before its tile is redone (P <= 2^6 is harmless in bf16/fp32)
 constexpr float kLazyThr = 6.0f;
+constexpr int kKV = 64;
+constexpr int kStages = 4;
+__device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const uint32_t* r) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]),
+        "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
 
-template <int D, int DKB, int HALVES, bool LAZY>
-__global__ void __launch_bounds__(64 + 128 * HALVES, (D <= 40) ? 2 : 1) attention_tc_kernel(const __grid_constant__ AttnParams p) {
+// 2^t for a pair of scores on the FMA pipe (Cody-Waite split + degree-3 minimax polynomial, 7.5e-5 max relative error --
+// P is rounded to bf16, 3.9e-3, right after): the softmax is bound by the 16/clk/SM MUFU unit, so a fraction of the
+// exponentials is moved to the idle FMA lanes.  t is clamped to >= -125 so the exponent arithmetic cannot wrap.
+__device__ __forceinline__ float2 poly_exp2x2(float2 t) {
+    t.x = fmaxf(t.x, -125.f);
+    t.y = fmaxf(t.y, -125.f);
+    const float2 magic = make_float2(12582912.f, 12582912.f), nmagic = make_float2(-12582912.f, -12582912.f);
+    const float2 y = fadd2(t, magic);                      // round-to-nearest integer of t sits in the low mantissa bits
+    const float2 ti = fadd2(y, nmagic);
+    const float2 f = ffma2(ti, make_float2(-1.f, -1.f), t);   // f = t - round(t) in [-0.5, 0.5]
+    float2 q = ffma2(f, make_float2(0.0551716685295105f, 0.0551716685295105f), make_float2(0.2426111251115799f, 0.2426111251115799f));
+    q = ffma2(q, f, make_float2(0.6932609677314758f, 0.6932609677314758f));
+    q = ffma2(q, f, make_float2(0.9999280571937561f, 0.9999280571937561f));
+    float2 e;   // add round(t) to the exponent field: bits(q) + (bits(y) << 23)
+    e.x = __int_as_float(__float_as_int(y.x) * 8388608 + __float_as_int(q.x));
+    e.y = __int_as_float(__float_as_int(y.y) * 8388608 + __float_as_int(q.y));
+    return e;
+}
+
+// POLY: every POLY-th score pair takes the polynomial instead of MUFU.EX2 (0 = none)
+template <int D, int DKB, int POLY>
+__global__ void __launch_bounds__(192, (D <= 40) ? 2 : 1) attention_tc_kernel(const __grid_constant__ AttnParams p) {
     constexpr int DN = (D + 15) / 16 * 16;    // MMA N of the PV product (48 / 80)
     constexpr int KSTEPS = (D + 15) / 16;     // UMMA K steps of the QK^T product
+    constexpr int KBLK = kKV * 128;          // bytes of one K block [64 keys x 64 d]
     constexpr int VBLK = D * 128;             // bytes of one V^T block [D rows x 64 keys]
     constexpr int VBLK_PAD = ((DN * 128 + 1023) / 1024) * 1024;  // padded so the MMA may read DN rows
     constexpr uint32_t kTmemCols = 256;
-    constexpr int CW = 128 / HALVES;          // score columns per softmax thread
-    constexpr int DNH = DN / HALVES;          // O columns per softmax thread (48 / 24 / 80 / 40)
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* sQ = smem;                               // DKB blocks
-    uint8_t* sK = sQ + DKB * kBlk;                    // 2 stages x DKB blocks
-    uint8_t* sV = sK + 2 * DKB * kBlk;                // 2 stages x 2 key-blocks x VBLK_PAD
-    uint8_t* sP = sV + 2 * 2 * VBLK_PAD;              // 2 key-blocks
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * kBlk);
+    uint8_t* sQ = smem;                               // DKB blocks of [128 q x 64 d]
+    uint8_t* sK = sQ + DKB * kBlk;                    // kStages x DKB blocks
+    uint8_t* sV = sK + kStages * DKB * KBLK;         // kStages x VBLK_PAD
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sV + kStages * VBLK_PAD);
     uint64_t* q_full = bars;
-    uint64_t* k_full = bars + 1;   // [2]
-    uint64_t* k_empty = bars + 3;  // [2]
-    uint64_t* v_full = bars + 5;   // [2]
-    uint64_t* v_empty = bars + 7;  // [2]
-    uint64_t* s_full = bars + 9;
-    uint64_t* p_full = bars + 10;
-    uint64_t* o_full = bars + 11;
-    uint64_t* o_empty = bars + 12;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
-    float* xch = reinterpret_cast<float*>(bars + 32);   // [2 parities][2 halves][128 rows] row exchange between half-threads
+    uint64_t* k_full = bars + 1;                  // [kStages]
+    uint64_t* k_empty = k_full + kStages;
+    uint64_t* v_full = k_empty + kStages;
+    uint64_t* v_empty = v_full + kStages;
+    uint64_t* s_full = v_empty + kStages;        // [2]
+    uint64_t* p_full = s_full + 2;                // [2]
+    uint64_t* o_full = p_full + 2;                // [2]: PV_j commits o_full[j & 1].  Two barriers, because a softmax warp may
+                                                  // run one tile ahead of the slowest one: on a single barrier it could find the
+                                                  // phase BEFORE the one it waits for still open, which a parity wait cannot tell
+                                                  // from "already complete"
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q0 = blockIdx.x * kQ, h = blockIdx.y, b = blockIdx.z;
@@ -148,16 +178,17 @@ __global__ void __launch_bounds__(64 + 128 * HALVES, (D <= 40) ? 2 : 1) attentio
         ptx::prefetch_tmap(&p.tmK);
         ptx::prefetch_tmap(&p.tmVt);
         ptx::mbar_init(q_full, 1);
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < kStages; ++i) {
             ptx::mbar_init(&k_full[i], 1);
             ptx::mbar_init(&k_empty[i], 1);
             ptx::mbar_init(&v_full[i], 1);
             ptx::mbar_init(&v_empty[i], 1);
         }
-        ptx::mbar_init(s_full, 1);
-        ptx::mbar_init(p_full, 4 * HALVES);    // one (warp-aggregated) arrival per softmax warp
-        ptx::mbar_init(o_full, 1);
-        ptx::mbar_init(o_empty, 4 * HALVES);
+        for (int i = 0; i < 2; ++i) {
+            ptx::mbar_init(&s_full[i], 1);
+            ptx::mbar_init(&p_full[i], 4);    // one (warp-aggregated) arrival per softmax warp
+            ptx::mbar_init(&o_full[i], 1);
+        }
         ptx::fence_barrier_init();
     }
     if (warp == 1) {
@@ -177,181 +208,141 @@ __global__ void __launch_bounds__(64 + 128 * HALVES, (D <= 40) ? 2 : 1) attentio
             ptx::mbar_expect_tx(q_full, DKB * kBlk);
             for (int kb = 0; kb < DKB; ++kb) tma_load_3d(sQ + kb * kBlk, &p.tmQ, q_full, kb * 64, h, b * p.Sq + q0);
             for (int j = 0; j < num_tiles; ++j) {
-                const int st = j & 1;
-                const uint32_t ph = (j >> 1) & 1;
+                const int st = j % kStages;
+                const uint32_t ph = (j / kStages) & 1;
                 ptx::mbar_wait(&k_empty[st], ph ^ 1);
-                ptx::mbar_expect_tx(&k_full[st], DKB * kBlk);
+                ptx::mbar_expect_tx(&k_full[st], DKB * KBLK);
                 for (int kb = 0; kb < DKB; ++kb)
-                    tma_load_3d(sK + (st * DKB + kb) * kBlk, &p.tmK, &k_full[st], kb * 64, h, b * p.Skv + j * kKV);
+                    tma_load_3d(sK + (st * DKB + kb) * KBLK, &p.tmK, &k_full[st], kb * 64, h, b * p.Skv + j * kKV);
                 ptx::mbar_wait(&v_empty[st], ph ^ 1);
-                ptx::mbar_expect_tx(&v_full[st], 2 * VBLK);
-                for (int kk = 0; kk < 2; ++kk)
-                    tma_load_3d(sV + (st * 2 + kk) * VBLK_PAD, &p.tmVt, &v_full[st], j * kKV + kk * 64, 0, b * p.heads + h);
+                ptx::mbar_expect_tx(&v_full[st], VBLK);
+                tma_load_3d(sV + st * VBLK_PAD, &p.tmVt, &v_full[st], j * kKV, 0, b * p.heads + h);
             }
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
         if (ptx::elect_one()) {
-            const uint32_t idesc_s = ptx::umma_idesc_bf16(128, 128);
+            const uint32_t idesc_s = ptx::umma_idesc_bf16(128, kKV);
             const uint32_t idesc_o = ptx::umma_idesc_bf16(128, DN);
-            ptx::mbar_wait(q_full, 0);
-            for (int j = 0; j < num_tiles; ++j) {
-                const int st = j & 1;
-                const uint32_t ph = (j >> 1) & 1;
-                // ---- S_j = Q K_j^T ----
-                ptx::mbar_wait(&k_full[st], ph);
+            auto issue_qk = [&](int j) {    // S_j = Q K_j^T into S buffer j & 1
+                const int st = j % kStages;
+                ptx::mbar_wait(&k_full[st], (j / kStages) & 1);
                 ptx::tc_fence_after();
 #pragma unroll
                 for (int ks = 0; ks < KSTEPS; ++ks) {
                     const int kb = ks / 4, kin = ks % 4;
                     const uint64_t da = ptx::umma_desc_k_sw128(ptx::smem_u32(sQ + kb * kBlk)) + 2 * kin;
-                    const uint64_t db = ptx::umma_desc_k_sw128(ptx::smem_u32(sK + (st * DKB + kb) * kBlk)) + 2 * kin;
-                    ptx::umma_bf16_ss(tmem_S, da, db, idesc_s, ks > 0 ? 1u : 0u);
+                    const uint64_t db = ptx::umma_desc_k_sw128(ptx::smem_u32(sK + (st * DKB + kb) * KBLK)) + 2 * kin;
+                    ptx::umma_bf16_ss(tmem_S + (j & 1) * kKV, da, db, idesc_s, ks > 0 ? 1u : 0u);
                 }
                 ptx::umma_commit(&k_empty[st]);
-                ptx::umma_commit(s_full);
-                // ---- O_j = P_j V_j ----
-                ptx::mbar_wait(p_full, j & 1);
-                ptx::mbar_wait(&v_full[st], ph);
-                ptx::mbar_wait(o_empty, (j & 1) ^ 1);
+                ptx::umma_commit(&s_full[j & 1]);
+            };
+            ptx::mbar_wait(q_full, 0);
+            issue_qk(0);
+            for (int j = 0; j < num_tiles; ++j) {
+                // S buffer (j+1)&1 is free: its last readers were the softmax of tile j-1 (p_full waited below, one
+                // iteration ago) and the PV product of tile j-1 (issued earlier on this in-order pipe)
+                if (j + 1 < num_tiles) issue_qk(j + 1);
+                const int st = j % kStages;
+                ptx::mbar_wait(&p_full[j & 1], (j >> 1) & 1);
+                ptx::mbar_wait(&v_full[st], (j / kStages) & 1);
                 ptx::tc_fence_after();
 #pragma unroll
-                for (int ks = 0; ks < 8; ++ks) {   // 128 keys = 8 x 16
-                    const int kk = ks / 4, kin = ks % 4;
-                    const uint64_t da = ptx::umma_desc_k_sw128(ptx::smem_u32(sP + kk * kBlk)) + 2 * kin;
-                    const uint64_t db = ptx::umma_desc_k_sw128(ptx::smem_u32(sV + (st * 2 + kk) * VBLK_PAD)) + 2 * kin;
-                    ptx::umma_bf16_ss(tmem_O, da, db, idesc_o, ks > 0 ? 1u : 0u);
+                for (int ks = 0; ks < kKV / 16; ++ks) {   // O += P_j V_j, P read from TMEM (8 columns = 16 keys per step)
+                    const uint64_t db = ptx::umma_desc_k_sw128(ptx::smem_u32(sV + st * VBLK_PAD)) + 2 * ks;
+                    ptx::umma_bf16_ts(tmem_O, tmem_S + (j & 1) * kKV + ks * 8, db, idesc_o, (j > 0 || ks > 0) ? 1u : 0u);
                 }
                 ptx::umma_commit(&v_empty[st]);
-                ptx::umma_commit(o_full);
+                ptx::umma_commit(&o_full[j & 1]);
             }
         }
     } else {
-        // ================= softmax warps: HALVES threads per query row =================
-        // Software-pipelined: the fold of O_{j-1} into the register accumulator happens AFTER P_j has been
-        // handed to the tensor core, so the P_{j-1} V_{j-1} product overlaps the softmax of tile j.
+        // ================= softmax warps: one thread per query row =================
         const int qd = warp & 3;                              // TMEM lane quadrant this warp may address
-        const int hf = (HALVES == 2) ? ((warp - 2) >> 2) : 0; // which half of the columns
         const int row = qd * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(qd * 32) << 16;
-        const uint32_t tS = tmem_S + lane_addr + hf * CW;
-        const uint32_t tO = tmem_O + lane_addr + hf * DNH;
-        float m = -INFINITY, l = 0.f, corr_prev = 1.f;
-        float o[DNH];
-#pragma unroll
-        for (int i = 0; i < DNH; ++i) o[i] = 0.f;
-
-        // value of the thread owning the other half of this row (double-buffered by exchange parity)
-        auto partner = [&](float v, int n) -> float {
-            if constexpr (HALVES == 1) {
-                return v;
-            } else {
-                float* x = xch + (n & 1) * 256;
-                x[hf * 128 + row] = v;
-                ptx::named_bar_sync(1 + qd, 64);
-                return x[(hf ^ 1) * 128 + row];
-            }
-        };
-        auto fold_o = [&](int jj, float corr) {
-            ptx::mbar_wait(o_full, jj & 1);
+        const uint32_t tO = tmem_O + lane_addr;
+        const float2 sc2 = make_float2(p.scale_log2, p.scale_log2);
+        float m = -INFINITY, l = 0.f;
+        for (int j = 0; j < num_tiles; ++j) {
+            const uint32_t tS = tmem_S + lane_addr + (j & 1) * kKV;
+            ptx::mbar_wait(&s_full[j & 1], (j >> 1) & 1);
             ptx::tc_fence_after();
-            uint32_t r[DNH];
-#pragma unroll
-            for (int c = 0; c + 16 <= DNH; c += 16) ptx::tmem_ld_32x32b_x16(tO + c, *reinterpret_cast<uint32_t(*)[16]>(&r[c]));
-            if constexpr (DNH % 16 == 8) ptx::tmem_ld_32x32b_x8(tO + DNH - 8, *reinterpret_cast<uint32_t(*)[8]>(&r[DNH - 8]));
+            uint32_t r[64], pk[32];
+            tmem_ld_32x32b_x32(tS, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
+            tmem_ld_32x32b_x32(tS + 32, *reinterpret_cast<uint32_t(*)[32]>(&r[32]));
             ptx::tmem_ld_wait();
+            // P = exp2(S * scale - off) as packed bf16 pairs; returns the fp32 row sum
+            auto exps = [&](float off, bool track, float& mx) -> float {
+                const float2 noff2 = make_float2(-off, -off);
+                float2 rs2 = make_float2(0.f, 0.f);
 #pragma unroll
-            for (int i = 0; i < DNH; ++i) o[i] = o[i] * corr + __uint_as_float(r[i]);
-            ptx::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(o_empty);
-        };
-        auto max_pass = [&]() -> float {
-            float mx = -INFINITY;
-#pragma unroll
-            for (int c = 0; c < CW; c += 64) {
-                uint32_t r0[32], r1[32];
-                tmem_ld_32x32b_x32(tS + c, r0);
-                tmem_ld_32x32b_x32(tS + c + 32, r1);
-                ptx::tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 32; ++i) mx = fmax3(mx, __uint_as_float(r0[i]), __uint_as_float(r1[i]));
-            }
-            return mx;
-        };
-        // P = exp2(S * scale - off) -> bf16 -> swizzled smem tile; returns the fp32 row sum (of this thread's columns)
-        auto exp_pass = [&](float off, bool track, float& mx) -> float {
-            float2 rs2 = make_float2(0.f, 0.f);
-            const float2 sc2 = make_float2(p.scale_log2, p.scale_log2), noff2 = make_float2(-off, -off);
-#pragma unroll
-            for (int c = 0; c < CW; c += 32) {
-                uint32_t r[32];
-                tmem_ld_32x32b_x32(tS + c, r);
-                ptx::tmem_ld_wait();
-                uint32_t pk[16];
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
+                for (int i = 0; i < 32; ++i) {
                     const float2 t = ffma2(make_float2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])), sc2, noff2);
-                    const float2 e = make_float2(fast_exp2(t.x), fast_exp2(t.y));
+                    const float2 e = (POLY > 0 && i % (POLY > 0 ? POLY : 1) == POLY - 1) ? poly_exp2x2(t)
+                                                                                        : make_float2(fast_exp2(t.x), fast_exp2(t.y));
                     rs2 = fadd2(rs2, e);
                     pk[i] = pack_bf16x2(e.x, e.y);
                     if (track) mx = fmax3(mx, __uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
                 }
-                const int col = hf * CW + c;
-                uint8_t* blk = sP + (col / 64) * kBlk + row * 128;
-#pragma unroll
-                for (int g = 0; g < 4; ++g) {   // four 16-byte chunks (8 keys each)
-                    const int chunk = ((col % 64) / 8 + g) ^ (row & 7);
-                    *reinterpret_cast<uint4*>(blk + chunk * 16) = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
-                }
-            }
-            return rs2.x + rs2.y;
-        };
-
-        for (int j = 0; j < num_tiles; ++j) {
-            ptx::mbar_wait(s_full, j & 1);
-            ptx::tc_fence_after();
-            float mx = -INFINITY, rs = 0.f, corr = 1.f;
+                return rs2.x + rs2.y;
+            };
+            float mx = -INFINITY, rs = 0.f;
             bool redo = true;
-            if (LAZY && j > 0) {
-                rs = exp_pass(m * p.scale_log2, true, mx);
-                mx = fmaxf(mx, partner(mx, j));
-                redo = __any_sync(0xffffffffu, (mx - m) * p.scale_log2 > kLazyThr);
+            if (j > 0) {
+                rs = exps(m * p.scale_log2, true, mx);
+                redo = __any_sync(0xffffffffu, (mx - m) * p.scale_log2 > p.lazy_thr);
             } else {
-                mx = max_pass();
-                mx = fmaxf(mx, partner(mx, j));
+#pragma unroll
+                for (int i = 0; i < 32; ++i) mx = fmax3(mx, __uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
             }
-            if (redo) {   // warp-uniform, and identical in the two warps sharing these rows
+            if (redo) {   // warp-uniform: move every row of the warp to its true running max
                 const float mn = fmaxf(m, mx);
-                corr = fast_exp2((m - mn) * p.scale_log2);
+                const float corr = fast_exp2((m - mn) * p.scale_log2);
                 m = mn;
                 float unused = 0.f;
-                rs = exp_pass(mn * p.scale_log2, false, unused);
-            }
-            l = l * corr + rs;
-            ptx::tc_fence_before();
-            ptx::fence_proxy_async();   // generic-proxy smem writes -> visible to the tensor core (async proxy)
-            __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(p_full);
-            if (j > 0) fold_o(j - 1, corr_prev);   // P_{j-1} V_{j-1} ran while this tile's softmax was computed
-            corr_prev = corr;
-        }
-        fold_o(num_tiles - 1, corr_prev);
-        // ---- normalise and store ----
-        l += (HALVES == 2) ? partner(l, num_tiles) : 0.f;
-        const float inv = 1.0f / l;
-        if (p.lse != nullptr && hf == 0) p.lse[((size_t)b * p.heads + h) * p.Sq + q0 + row] = m * p.scale_log2 + log2f(l);
-        bf16* dst = p.out + ((size_t)b * p.Sq + q0 + row) * p.ldo + h * D + hf * DNH;
+                rs = exps(mn * p.scale_log2, false, unused);
+                l *= corr;
+                if (j > 0) {   // rescale the O rows accumulated so far (PV_{j-1} must have landed; PV_j waits for p_full)
+                    ptx::mbar_wait(&o_full[(j - 1) & 1], ((j - 1) >> 1) & 1);
+                    ptx::tc_fence_after();
+                    uint32_t ob[DN];
 #pragma unroll
-        for (int c = 0; c < DNH; c += 8) {
-            if (hf * DNH + c < D) {
-                uint4 u;
-                u.x = pack_bf16x2(o[c] * inv, o[c + 1] * inv);
-                u.y = pack_bf16x2(o[c + 2] * inv, o[c + 3] * inv);
-                u.z = pack_bf16x2(o[c + 4] * inv, o[c + 5] * inv);
-                u.w = pack_bf16x2(o[c + 6] * inv, o[c + 7] * inv);
-                *reinterpret_cast<uint4*>(dst + c) = u;
+                    for (int c = 0; c < DN; c += 16) ptx::tmem_ld_32x32b_x16(tO + c, *reinterpret_cast<uint32_t(*)[16]>(&ob[c]));
+                    ptx::tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < DN; ++i) ob[i] = __float_as_uint(__uint_as_float(ob[i]) * corr);
+#pragma unroll
+                    for (int c = 0; c < DN; c += 16) tmem_st_32x32b_x16(tO + c, &ob[c]);
+                }
             }
+            l += rs;
+            tmem_st_32x32b_x16(tS, &pk[0]);         // P_j over the first 32 columns of S_j (bf16 pairs)
+            tmem_st_32x32b_x16(tS + 16, &pk[16]);
+            ptx::tmem_st_wait();
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&p_full[j & 1]);
+        }
+        // ---- normalise and store ----
+        ptx::mbar_wait(&o_full[(num_tiles - 1) & 1], ((num_tiles - 1) >> 1) & 1);
+        ptx::tc_fence_after();
+        uint32_t ob[DN];
+#pragma unroll
+        for (int c = 0; c < DN; c += 16) ptx::tmem_ld_32x32b_x16(tO + c, *reinterpret_cast<uint32_t(*)[16]>(&ob[c]));
+        ptx::tmem_ld_wait();
+        const float inv = 1.0f / l;
+        if (p.lse != nullptr) p.lse[((size_t)b * p.heads + h) * p.Sq + q0 + row] = m * p.scale_log2 + log2f(l);
+        bf16* dst = p.out + ((size_t)b * p.Sq + q0 + row) * p.ldo + h * D;
+#pragma unroll
+        for (int c = 0; c < D; c += 8) {
+            uint4 u;
+            u.x = pack_bf16x2(__uint_as_float(ob[c]) * inv, __uint_as_float(ob[c + 1]) * inv);
+            u.y = pack_bf16x2(__uint_as_float(ob[c + 2]) * inv, __uint_as_float(ob[c + 3]) * inv);
+            u.z = pack_bf16x2(__uint_as_float(ob[c + 4]) * inv, __uint_as_float(ob[c + 5]) * inv);
+            u.w = pack_bf16x2(__uint_as_float(ob[c + 6]) * inv, __uint_as_float(ob[c + 7]) * inv);
+            *reinterpret_cast<uint4*>(dst + c) = u;
         }
     }
 
@@ -363,9 +354,9 @@ __global__ void __launch_bounds__(64 + 128 * HALVES, (D <= 40) ? 2 : 1) attentio
     }
 }
 
-template <int D, int DKB, int HALVES, bool LAZY>
+template <int D, int DKB, int POLY>
 int launch_tc(const bf16* q, const bf16* k, const bf16* vt, bf16* out, float* lse, int batch, int heads, int Sq, int Skv, int ldq,
-              int ldk, int ldo, float scale, cudaStream_t s) {
+               int ldk, int ldo, float scale, cudaStream_t s) {
     constexpr int DN = (D + 15) / 16 * 16;
     constexpr int VBLK_PAD = ((DN * 128 + 1023) / 1024) * 1024;
     AttnParams p;
@@ -380,7 +371,7 @@ int launch_tc(const bf16* q, const bf16* k, const bf16* vt, bf16* out, float* ls
     {
         const uint64_t dims[3] = {(uint64_t)D, (uint64_t)heads, (uint64_t)batch * Skv};
         const uint64_t str[3] = {0, (uint64_t)D * 2, (uint64_t)ldk * 2};
-        const uint32_t box[3] = {64, 1, 128};
+        const uint32_t box[3] = {64, 1, (uint32_t)kKV};
         int rc = b200sd_make_tmap(&p.tmK, k, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
         if (rc) return rc;
     }
@@ -398,14 +389,16 @@ int launch_tc(const bf16* q, const bf16* k, const bf16* vt, bf16* out, float* ls
     p.heads = heads;
     p.ldo = ldo;
     p.scale_log2 = scale * 1.4426950408889634f;
-    const size_t smem = (size_t)DKB * kBlk + 2 * DKB * kBlk + 4 * VBLK_PAD + 2 * kBlk + 256 + 2048 + 1024;
+    static const float thr = [] { const char* e = getenv("B200SD_ATTN_THR"); return e ? (float)atof(e) : kLazyThr; }();
+    p.lazy_thr = thr;
+    const size_t smem = (size_t)DKB * kBlk + (size_t)kStages * DKB * kKV * 128 + (size_t)kStages * VBLK_PAD + 256 + 1024;
     static bool configured = false;
     if (!configured) {
-        B200SD_CUDA(cudaFuncSetAttribute(attention_tc_kernel<D, DKB, HALVES, LAZY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        B200SD_CUDA(cudaFuncSetAttribute(attention_tc_kernel<D, DKB, HALVES, LAZY>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        B200SD_CUDA(cudaFuncSetAttribute(attention_tc_kernel<D, DKB, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        B200SD_CUDA(cudaFuncSetAttribute(attention_tc_kernel<D, DKB, POLY>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         configured = true;
     }
-    B200SD_CUDA(b200sd_launch(attention_tc_kernel<D, DKB, HALVES, LAZY>, dim3(Sq / kQ, heads, batch), dim3(64 + 128 * HALVES), smem, s, p));
+    B200SD_CUDA(b200sd_launch(attention_tc_kernel<D, DKB, POLY>, dim3(Sq / kQ, heads, batch), dim3(192), smem, s, p));
     g_b200sd_launches.fetch_add(1, std::memory_order_relaxed);
     B200SD_LAUNCH_CHECK();
     return B200SD_OK;
@@ -425,24 +418,16 @@ int b200sd_attention_tc(const void* q, const void* k, const void* v, void* out, 
     B200SD_CUDA(b200sd_launch(transpose_v_kernel, dim3(ceil_div(Skv, 64), ceil_div(d, 64), batch * heads), dim3(256), 0, s,
                               static_cast<const bf16*>(v), vt, Skv, heads, d, ldv));
     g_b200sd_launches.fetch_add(1, std::memory_order_relaxed);
-    // softmax organisation: B200SD_ATTN_FWD = 0 (4 warps, two passes), 1 (4 warps, lazy), 2 (8 warps, two passes), 3 (8 warps, lazy)
-    static const int variant = [] { const char* e = getenv("B200SD_ATTN_FWD"); return e ? atoi(e) : 3; }();
-#define B200SD_ATTN_GO(DD, KB, HV, LZ)                                                                                          \
-    return launch_tc<DD, KB, HV, LZ>(static_cast<const bf16*>(q), static_cast<const bf16*>(k), vt, static_cast<bf16*>(out), lse, \
-                                     batch, heads, Sq, Skv, ldq, ldk, ldo, scale, s)
+    // B200SD_ATTN_POLY=0 keeps every exponential on MUFU.EX2 (A/B switch; default: every 4th pair on the FMA pipe)
+    static const int poly = [] { const char* e = getenv("B200SD_ATTN_POLY"); return e ? atoi(e) : 4; }();
+#define B200SD_ATTN_GO(DD, KB, PL)                                                                                           \
+    return launch_tc<DD, KB, PL>(static_cast<const bf16*>(q), static_cast<const bf16*>(k), vt, static_cast<bf16*>(out), lse, \
+                                  batch, heads, Sq, Skv, ldq, ldk, ldo, scale, s)
     if (d == 40) {
-        switch (variant) {
-            case 0: B200SD_ATTN_GO(40, 1, 1, false);
-            case 1: B200SD_ATTN_GO(40, 1, 1, true);
-            case 2: B200SD_ATTN_GO(40, 1, 2, false);
-            default: B200SD_ATTN_GO(40, 1, 2, true);
-        }
+        if (poly == 0) B200SD_ATTN_GO(40, 1, 0);
+        B200SD_ATTN_GO(40, 1, 4);
     }
-    switch (variant) {
-        case 0: B200SD_ATTN_GO(80, 2, 1, false);
-        case 1: B200SD_ATTN_GO(80, 2, 1, true);
-        case 2: B200SD_ATTN_GO(80, 2, 2, false);
-        default: B200SD_ATTN_GO(80, 2, 2, true);
-    }
+    if (poly == 0) B200SD_ATTN_GO(80, 2, 0);
+    B200SD_ATTN_GO(80, 2, 4);
 #undef B200SD_ATTN_GO
 }

@@ -99,6 +99,31 @@ def test_attention(B, heads, Sq, Skv, d):
     _close(out, want, 1.0 / 64)
 
 
+@pytest.mark.parametrize("B,S,d,ramp", [(2, 4096, 40, 6.0), (2, 1024, 80, 6.0), (1, 1024, 40, 30.0), (1, 192, 40, 0.0)])
+def test_attention_growing_scores(B, S, d, ramp):
+    """Scores that keep growing along the keys: the tcgen05 kernel exponentiates every tile against a lagging reference
+    max and must redo the tile / rescale its TMEM-resident O rows when a row outgrows it; rows of different warps do
+    so at different tiles.  Also checks the log-sum-exp handed to the backward.  (S=192: a 64-key tail tile.)"""
+    from b200sd import ops
+    torch.manual_seed(9)
+    H = 8
+    C = H * d
+    qkv = torch.randn(B * S, 3 * C, device=DEV)
+    if ramp > 0:
+        qkv[:, C:2 * C] *= (1.0 + ramp * torch.arange(S, device=DEV).repeat(B) / S)[:, None]
+    qkv = qkv.bfloat16()
+    out = torch.empty(B * S, C, device=DEV, dtype=torch.bfloat16)
+    lse = torch.empty(B, H, S, device=DEV)
+    ops.attention_lse(qkv, qkv, qkv, out, lse, B, H, S, S, d, d ** -0.5, ldq=3 * C, ldk=3 * C, ldv=3 * C, ldo=C, k_off=C,
+                      v_off=2 * C)
+    q, k, v = [t.reshape(B, S, H, d).permute(0, 2, 1, 3).float() for t in qkv.split(C, dim=1)]
+    sc = (q @ k.transpose(-1, -2)) * d ** -0.5
+    want = (torch.softmax(sc, -1) @ v).permute(0, 2, 1, 3).reshape(B * S, C)
+    _close(out, want, 1.0 / 64)
+    want_lse = torch.logsumexp(sc, -1) * 1.4426950408889634
+    assert (lse - want_lse).abs().max().item() < 2e-3
+
+
 def test_conv_in_out():
     from b200sd import ops
     from b200sd.packing import pack_conv3x3_f32
