@@ -139,11 +139,17 @@ typedef struct b200sd_gemm_args {
     void* workspace;       /* split-K scratch (may be NULL when split_k == 1) */
     size_t workspace_bytes;
     int pair;              /* CTA pairs (tcgen05 cta_group::2, 256-row MMA tiles): 0 = auto, 1 = on, -1 = off */
+    float* gn_part;        /* optional: per-CTA column statistics [parts][2][N] of the fp32 output (sum | sum of squares over the
+                              rows each CTA stores), consumed by b200sd_groupnorm_silu_parts; layout from b200sd_gemm_gn_layout */
 } b200sd_gemm_args;
 
 size_t b200sd_gemm_workspace_bytes(void);
 int b200sd_geglu_tile(int N); /* tile width used to interleave GEGLU weights for a given N (= 8C) */
 int b200sd_gemm(const b200sd_gemm_args* args, b200sd_stream_t stream);
+/* How a GEMM with these arguments lays out gn_part: image b (hw output rows each) owns the partial rows
+ * [b * parts_per_image, (b + 1) * parts_per_image) of total_parts.  parts_per_image == 0: not available for this shape
+ * (output tiles straddle images, bf16 output, ...) -- leave gn_part NULL and use b200sd_groupnorm_silu. */
+int b200sd_gemm_gn_layout(const b200sd_gemm_args* args, int hw, int* parts_per_image, int* total_parts);
 
 /* ---- backward GEMMs (autograd.backward through the UNet, finetune_sd.py:494) ----
  * Same tcgen05 pipeline as b200sd_gemm; the operands that the forward read K-major are read MN-major
@@ -210,6 +216,15 @@ int b200sd_groupnorm_silu(const void* x0, const void* x1, int C0, int C1, const 
 int b200sd_groupnorm_silu_stats(const void* x0, const void* x1, int C0, int C1, const float* gamma, const float* beta,
                                 void* out, void* raw_out, float* stats_ws, float* stats_out, int batch, int hw, int groups,
                                 float eps, int silu, int in_dtype, b200sd_stream_t stream);
+
+/* GroupNorm (+SiLU, + concat) whose statistics come from the GEMMs that PRODUCED x0 / x1 (b200sd_gemm_args::gn_part,
+ * layout from b200sd_gemm_gn_layout: part [image][ppi][2][ld] floats): no statistics pass over the tensor.  Same
+ * semantics as b200sd_groupnorm_silu_stats otherwise.  Returns B200SD_ERR_UNSUPPORTED for channel layouts it does not
+ * cover -- fall back to b200sd_groupnorm_silu. */
+int b200sd_groupnorm_silu_parts(const void* x0, const void* x1, int C0, int C1, const float* part0, int ppi0, int ld0,
+                                const float* part1, int ppi1, int ld1, const float* gamma, const float* beta, void* out,
+                                void* raw_out, float* stats_out, int batch, int hw, int groups, float eps, int silu,
+                                int in_dtype, b200sd_stream_t stream);
 
 /* LayerNorm over the last dim of [rows, C] (in_dtype: fp32 or bf16) -> bf16 (affine). */
 int b200sd_groupnorm_workspace_floats(int batch);

@@ -23,7 +23,7 @@ class GemmArgs(C.Structure):
         ("lda0", C.c_int), ("lda1", C.c_int), ("ldc", C.c_int), ("ldr", C.c_int), ("ldrb", C.c_int), ("conv_taps", C.c_int),
         ("batch", C.c_int), ("H", C.c_int), ("W", C.c_int), ("rows_per_image", C.c_int), ("epilogue", C.c_int),
         ("out_dtype", C.c_int), ("residual_dtype", C.c_int), ("block_n", C.c_int), ("split_k", C.c_int),
-        ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t), ("pair", C.c_int),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t), ("pair", C.c_int), ("gn_part", C.c_void_p),
     ]
 
 
@@ -64,6 +64,9 @@ SIGNATURES = {
     "b200sd_gemm_workspace_bytes": (_sz, []),
     "b200sd_geglu_tile": (_i, [_i]),
     "b200sd_gemm": (_i, [C.POINTER(GemmArgs), _vp]),
+    "b200sd_gemm_gn_layout": (_i, [C.POINTER(GemmArgs), _i, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "b200sd_groupnorm_silu_parts": (_i, [_vp, _vp, _i, _i, _vp, _i, _i, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _i,
+                                         _i, _vp]),
     "b200sd_gemm_dgrad": (_i, [C.POINTER(DgradArgs), _vp]),
     "b200sd_gemm_wgrad": (_i, [C.POINTER(WgradArgs), _vp]),
     "b200sd_conv_in": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),

@@ -81,6 +81,8 @@ struct KParams {
     int atomic_out;      // fp32 red.add into `out` (wgrad: split-K partials and gradient accumulation)
     int pair;            // CTA pair (cta_group::2): two CTAs adjacent in M form one 256 x block_n MMA tile; each loads its own
                          // 128 A rows and HALF of the B tile, so the L2 -> smem traffic per FLOP drops by ~1/3
+    float* gn_part;      // optional [m_tiles * split_k][2][N]: per-column (sum, sum of squares) of the rows each CTA stores --
+                         // the GroupNorm that consumes this output gets its statistics from here instead of re-reading it
     unsigned long long* trace;  // optional [ctas][8] globaltimer stamps (debug)
 };
 
@@ -117,8 +119,10 @@ __device__ __forceinline__ void lds8(uint32_t addr, float (&v)[8]) {
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "r"(addr + 16));
 }
 // OUT: 0 bf16, 1 fp32, 2 fp32 red.add;  RES: 0 none, 1 bf16, 2 fp32;  SPLIT: sum the cluster's partial tiles over DSMEM
-template <int OUT, int RES, bool SPLIT, bool GEGLU>
-__device__ __forceinline__ void epilogue_rows(const KParams& p, const EpiCtx& e, int row0, const float (&b)[8], const float (&bg)[8]) {
+// STATS: also accumulate this thread's per-column sum / sum of squares of the values it stores (cs / cq)
+template <int OUT, int RES, bool SPLIT, bool GEGLU, bool STATS = false>
+__device__ __forceinline__ void epilogue_rows(const KParams& p, const EpiCtx& e, int row0, const float (&b)[8], const float (&bg)[8],
+                                              float* cs = nullptr, float* cq = nullptr) {
     constexpr int U = 4;
     for (int row = row0; row < e.row_end; row += e.R * U) {
         float v[U][8], r[U][8];
@@ -170,6 +174,10 @@ __device__ __forceinline__ void epilogue_rows(const KParams& p, const EpiCtx& e,
 #pragma unroll
                         for (int i = 0; i < 8; ++i) o[i] += t[i];
                     }
+                }
+                if constexpr (STATS) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) { cs[i] += o[i]; cq[i] = fmaf(o[i], o[i], cq[i]); }
                 }
                 if constexpr (OUT == 2) {
                     float* dst = static_cast<float*>(p.out) + (size_t)grow * p.ldc + e.col_out;
@@ -419,6 +427,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tcgen05_kernel(const __gr
         const int groups = (geglu ? half : p.block_n) / 8;
         const int R = kNumThreads / groups;           // rows per pass
         const int tid = threadIdx.x;
+        float cs[8], cq[8];   // GroupNorm column statistics of the rows this thread stores (p.gn_part)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { cs[i] = 0.f; cq[i] = 0.f; }
         if (tid < R * groups && valid > 0) {
             const int c8 = tid % groups, r0 = tid / groups;
             const int cb = c8 * 8;
@@ -441,17 +452,36 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tcgen05_kernel(const __gr
                 const int rk = p.residual ? (p.res_f32 ? 2 : 1) : 0;
                 if (geglu) epilogue_rows<0, 0, false, true>(p, e, row0, b, bg);
                 else if (p.split_k > 1) {
-                    if (ok == 1) { if (rk == 2) epilogue_rows<1, 2, true, false>(p, e, row0, b, bg); else if (rk == 1) epilogue_rows<1, 1, true, false>(p, e, row0, b, bg); else epilogue_rows<1, 0, true, false>(p, e, row0, b, bg); }
+                    if (ok == 1 && p.gn_part) { if (rk == 2) epilogue_rows<1, 2, true, false, true>(p, e, row0, b, bg, cs, cq); else epilogue_rows<1, 0, true, false, true>(p, e, row0, b, bg, cs, cq); }
+                    else if (ok == 1) { if (rk == 2) epilogue_rows<1, 2, true, false>(p, e, row0, b, bg); else if (rk == 1) epilogue_rows<1, 1, true, false>(p, e, row0, b, bg); else epilogue_rows<1, 0, true, false>(p, e, row0, b, bg); }
                     else { if (rk == 2) epilogue_rows<0, 2, true, false>(p, e, row0, b, bg); else if (rk == 1) epilogue_rows<0, 1, true, false>(p, e, row0, b, bg); else epilogue_rows<0, 0, true, false>(p, e, row0, b, bg); }
                 } else if (ok == 2) epilogue_rows<2, 0, false, false>(p, e, row0, b, bg);
+                else if (ok == 1 && p.gn_part) { if (rk == 2) epilogue_rows<1, 2, false, false, true>(p, e, row0, b, bg, cs, cq); else epilogue_rows<1, 0, false, false, true>(p, e, row0, b, bg, cs, cq); }
                 else if (ok == 1) { if (rk == 2) epilogue_rows<1, 2, false, false>(p, e, row0, b, bg); else if (rk == 1) epilogue_rows<1, 1, false, false>(p, e, row0, b, bg); else epilogue_rows<1, 0, false, false>(p, e, row0, b, bg); }
                 else { if (rk == 2) epilogue_rows<0, 2, false, false>(p, e, row0, b, bg); else if (rk == 1) epilogue_rows<0, 1, false, false>(p, e, row0, b, bg); else epilogue_rows<0, 0, false, false>(p, e, row0, b, bg); }
             }
         }
+        if (p.gn_part != nullptr) {
+            // GroupNorm statistics of the rows this CTA stored.  Once nobody reads the staging tile any more (peers included),
+            // it becomes the scratch for a fixed-order (deterministic) fold of the R row-walkers of every column group;
+            // partial row (m_tile * split_k + rank) = [sum | sum of squares][N].
+            if (p.split_k > 1) cluster_sync_all(); else __syncthreads();
+            float* s_gn = reinterpret_cast<float*>(stage);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { s_gn[tid * 16 + i] = cs[i]; s_gn[tid * 16 + 8 + i] = cq[i]; }
+            __syncthreads();
+            float* dst = p.gn_part + (size_t)(m_tile * p.split_k + rank) * 2 * p.N;
+            for (int idx = tid; idx < groups * 16; idx += kNumThreads) {
+                const int c8 = idx >> 4, k = idx & 15, col = c8 * 8 + (k & 7);
+                float a = 0.f;
+                for (int r = 0; r < R; ++r) a += s_gn[(r * groups + c8) * 16 + k];
+                if (col < col_valid) dst[(size_t)(k >> 3) * p.N + n0 + col] = a;
+            }
+        }
         if (epi_tid == 0) TRACE(6);
     }
-    // peers may still be reading this CTA's staging tile
-    if (p.split_k > 1) cluster_sync_all();
+    // peers may still be reading this CTA's staging tile (with gn_part the cluster has already synchronised above)
+    if (p.split_k > 1 && p.gn_part == nullptr) cluster_sync_all();
 
     ptx::tc_fence_before();
     __syncthreads();
@@ -621,6 +651,68 @@ extern "C" size_t b200sd_gemm_workspace_bytes(void) { return 0; }  // split-K re
 
 extern "C" int b200sd_geglu_tile(int N) { return pick_block_n(N, 1, B200SD_EPI_GEGLU); }
 
+// M / N / split-K tiling of a forward GEMM (shared by the launch and by b200sd_gemm_gn_layout, which tells the consumer of
+// the GroupNorm column statistics how many partial rows each image owns).  Fills the tiling fields of p.
+static int gemm_tiling(const b200sd_gemm_args* a, KParams& p, int* m_tiles_out, int* n_tiles_out) {
+    const int C0 = a->C0, C1 = a->a1 ? a->C1 : 0, C = C0 + C1;
+    (void)C;
+    // ---- M tiling ----
+    if (!p.conv) {
+        p.rows_valid = BLOCK_M;
+        p.a_bytes = kABytes;
+        p.tile_w = p.tile_h = p.tile_n = 1;
+        p.tiles_y = 1;
+        *m_tiles_out = ceil_div(a->M, BLOCK_M);
+    } else {
+        const int rc = conv_m_tiling(p, a->batch, a->H, a->W, a->M, m_tiles_out);
+        if (rc) return rc;
+    }
+
+    const int m_tiles = *m_tiles_out;
+
+    // ---- N tiling ----
+    static const bool no_split = getenv("B200SD_SPLITK") && getenv("B200SD_SPLITK")[0] == '0';
+    const bool can_split = !no_split && a->split_k <= 0 && a->epilogue == B200SD_EPI_LINEAR && p.num_k_blocks >= 16;
+    int bn = a->block_n > 0 ? a->block_n : pick_block_n(a->N, m_tiles, a->epilogue, can_split);
+    B200SD_REQUIRE(bn >= 16 && bn <= 256 && bn % 16 == 0 && a->N % bn == 0, "gemm: bad block_n %d for N=%d", bn, a->N);
+    B200SD_REQUIRE(a->epilogue != B200SD_EPI_GEGLU || bn % 32 == 0, "gemm: GEGLU needs block_n %% 32 == 0");
+    p.block_n = bn;
+    int n_tiles = a->N / bn;
+    p.tmem_cols = pow2_cols(bn);
+
+    // ---- split-K: the splits of a tile form a thread-block cluster (<= 8 CTAs) and reduce over DSMEM ----
+    const int sms = b200sd_num_sms();
+    int split = a->split_k;
+    if (split <= 0) {
+        split = 1;
+        const int tiles = m_tiles * n_tiles;
+        if (!no_split && a->epilogue == B200SD_EPI_LINEAR && tiles * 2 <= sms && p.num_k_blocks >= 16) {
+            while (split < 8 && tiles * split * 2 <= sms && p.num_k_blocks / (split * 2) >= 8) split *= 2;
+        }
+    }
+    int n_tiles_f = n_tiles;
+    if (a->split_k <= 0 && a->block_n <= 0 && can_split) {
+        // clusters of 8 only place well up to ~8 of them (measured: 16 clusters of 8 run as two waves); and when the split
+        // grid still leaves half the machine idle, halve the tile width instead of splitting deeper
+        const int tiles = m_tiles * n_tiles;
+        if (split == 8 && tiles > 8) split = 4;
+        if (split <= 4 && tiles * split * 2 <= sms && bn % 32 == 0 && bn / 2 >= 80) {
+            bn /= 2;
+            p.block_n = bn;
+            n_tiles_f = a->N / bn;
+            p.tmem_cols = pow2_cols(bn);
+        }
+    }
+    B200SD_REQUIRE(split == 1 || a->epilogue == B200SD_EPI_LINEAR, "gemm: split-K only with the linear epilogue");
+    B200SD_REQUIRE(split == 1 || split == 2 || split == 4 || split == 8, "gemm: split_k must be 1, 2, 4 or 8 (cluster size)");
+    p.kb_per_split = ceil_div(p.num_k_blocks, split);
+    B200SD_REQUIRE((split - 1) * p.kb_per_split < p.num_k_blocks, "gemm: split_k=%d leaves an empty split for K=%d", split, a->K);
+    *n_tiles_out = n_tiles_f;
+    p.split_k = split;
+    p.pair = want_pair(a->pair, split, m_tiles, n_tiles_f, p.num_k_blocks) && bn % 32 == 0;
+    return B200SD_OK;
+}
+
 extern "C" int b200sd_gemm(const b200sd_gemm_args* a, b200sd_stream_t stream) {
     B200SD_REQUIRE(a != nullptr, "gemm: null args");
     B200SD_REQUIRE(a->a0 && a->w && a->out, "gemm: null operand pointer");
@@ -666,59 +758,16 @@ extern "C" int b200sd_gemm(const b200sd_gemm_args* a, b200sd_stream_t stream) {
     p.n_valid = a->N;
     p.tiles_per_tap = 1;
 
-    // ---- M tiling ----
-    int m_tiles;
-    if (!p.conv) {
-        p.rows_valid = BLOCK_M;
-        p.a_bytes = kABytes;
-        p.tile_w = p.tile_h = p.tile_n = 1;
-        p.tiles_y = 1;
-        m_tiles = ceil_div(a->M, BLOCK_M);
-    } else {
-        const int rc = conv_m_tiling(p, a->batch, a->H, a->W, a->M, &m_tiles);
+    int m_tiles = 0, n_tiles = 0;
+    {
+        const int rc = gemm_tiling(a, p, &m_tiles, &n_tiles);
         if (rc) return rc;
     }
-
-    // ---- N tiling ----
-    static const bool no_split = getenv("B200SD_SPLITK") && getenv("B200SD_SPLITK")[0] == '0';
-    const bool can_split = !no_split && a->split_k <= 0 && a->epilogue == B200SD_EPI_LINEAR && p.num_k_blocks >= 16;
-    int bn = a->block_n > 0 ? a->block_n : pick_block_n(a->N, m_tiles, a->epilogue, can_split);
-    B200SD_REQUIRE(bn >= 16 && bn <= 256 && bn % 16 == 0 && a->N % bn == 0, "gemm: bad block_n %d for N=%d", bn, a->N);
-    B200SD_REQUIRE(a->epilogue != B200SD_EPI_GEGLU || bn % 32 == 0, "gemm: GEGLU needs block_n %% 32 == 0");
-    p.block_n = bn;
-    int n_tiles = a->N / bn;
-    p.tmem_cols = pow2_cols(bn);
-
-    // ---- split-K: the splits of a tile form a thread-block cluster (<= 8 CTAs) and reduce over DSMEM ----
-    const int sms = b200sd_num_sms();
-    int split = a->split_k;
-    if (split <= 0) {
-        split = 1;
-        const int tiles = m_tiles * n_tiles;
-        if (!no_split && a->epilogue == B200SD_EPI_LINEAR && tiles * 2 <= sms && p.num_k_blocks >= 16) {
-            while (split < 8 && tiles * split * 2 <= sms && p.num_k_blocks / (split * 2) >= 8) split *= 2;
-        }
-    }
-    int n_tiles_f = n_tiles;
-    if (a->split_k <= 0 && a->block_n <= 0 && can_split) {
-        // clusters of 8 only place well up to ~8 of them (measured: 16 clusters of 8 run as two waves); and when the split
-        // grid still leaves half the machine idle, halve the tile width instead of splitting deeper
-        const int tiles = m_tiles * n_tiles;
-        if (split == 8 && tiles > 8) split = 4;
-        if (split <= 4 && tiles * split * 2 <= sms && bn % 32 == 0 && bn / 2 >= 80) {
-            bn /= 2;
-            p.block_n = bn;
-            n_tiles_f = a->N / bn;
-            p.tmem_cols = pow2_cols(bn);
-        }
-    }
-    B200SD_REQUIRE(split == 1 || a->epilogue == B200SD_EPI_LINEAR, "gemm: split-K only with the linear epilogue");
-    B200SD_REQUIRE(split == 1 || split == 2 || split == 4 || split == 8, "gemm: split_k must be 1, 2, 4 or 8 (cluster size)");
-    p.kb_per_split = ceil_div(p.num_k_blocks, split);
-    B200SD_REQUIRE((split - 1) * p.kb_per_split < p.num_k_blocks, "gemm: split_k=%d leaves an empty split for K=%d", split, a->K);
-    n_tiles = n_tiles_f;
-    p.split_k = split;
-    p.pair = want_pair(a->pair, split, m_tiles, n_tiles, p.num_k_blocks) && bn % 32 == 0;
+    const int bn = p.block_n, split = p.split_k;
+    p.gn_part = a->gn_part;
+    B200SD_REQUIRE(!a->gn_part || (a->out_dtype == B200SD_F32 && a->epilogue == B200SD_EPI_LINEAR &&
+                                   (!a->residual || a->residual_dtype == B200SD_F32)),
+                   "gemm: gn_part needs fp32 output, the linear epilogue and no bf16 residual");
 
     // ---- tensor maps ----
     if (!p.conv) {
@@ -755,6 +804,38 @@ extern "C" int b200sd_gemm(const b200sd_gemm_args* a, b200sd_stream_t stream) {
     }
 
     return launch_gemm(p, m_tiles, n_tiles, split, /*cluster=*/true, stream);
+}
+
+// Layout of the GroupNorm column statistics a GEMM with these arguments writes into gn_part: partial row
+// (m_tile * split_k + rank) holds [sum | sum of squares][N] over the output rows that CTA stored; image b owns the rows
+// [b * parts_per_image, (b + 1) * parts_per_image).  parts_per_image == 0: tiles of this shape straddle images (or the
+// shape is otherwise not covered) -- do not pass gn_part.  hw = output rows per image.
+extern "C" int b200sd_gemm_gn_layout(const b200sd_gemm_args* a, int hw, int* parts_per_image, int* total_parts) {
+    B200SD_REQUIRE(a && parts_per_image && total_parts && hw > 0, "gemm_gn_layout: bad arguments");
+    KParams p;
+    memset(&p, 0, sizeof(p));
+    p.M = a->M;
+    p.N = a->N;
+    p.num_k_blocks = a->K / BLOCK_K;
+    p.conv = a->conv_taps == 9;
+    int m_tiles = 0, n_tiles = 0;
+    const int rc = gemm_tiling(a, p, &m_tiles, &n_tiles);
+    if (rc) return rc;
+    *parts_per_image = 0;
+    *total_parts = 0;
+    if (a->out_dtype != B200SD_F32 || a->epilogue != B200SD_EPI_LINEAR || (a->residual && a->residual_dtype != B200SD_F32)) return B200SD_OK;
+    int tiles_per_image;
+    if (p.conv) {
+        if (p.tile_n != 1 || a->H * a->W != hw) return B200SD_OK;
+        tiles_per_image = p.tiles_y;
+    } else {
+        if (hw % BLOCK_M != 0 || a->M % hw != 0) return B200SD_OK;
+        tiles_per_image = hw / BLOCK_M;
+    }
+    if (p.pair) m_tiles = (m_tiles + 1) & ~1;
+    *parts_per_image = tiles_per_image * p.split_k;
+    *total_parts = m_tiles * p.split_k;
+    return B200SD_OK;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -2,6 +2,8 @@
 // Both are bandwidth-bound passes over L2-resident activations (<= 21 MB at CFG batch 2).
 #include <atomic>
 
+#include <algorithm>
+
 #include "common.cuh"
 
 extern std::atomic<long long> g_b200sd_launches;
@@ -316,6 +318,106 @@ __global__ void __launch_bounds__(512) gn_fused_kernel(const void* __restrict__ 
     if (CL > 1) gn_cluster_sync();  // peers may still be reading s_cta
 }
 
+// ---- GroupNorm from producer-side statistics: the GEMM that wrote x0 (/ x1) also wrote, per CTA, the column sums and sums
+// of squares of the rows it stored (gemm_tcgen05.cu, KParams::gn_part).  No statistics pass over the tensor and no cluster:
+// every CTA folds the partial rows of its image for its own channels (fixed order: deterministic), then does the apply
+// pass of gn_fused_kernel over its pixel slab.  part*: [image][ppi][2][ld] floats.
+template <int DT>
+__global__ void __launch_bounds__(512) gn_parts_kernel(const void* __restrict__ x0, const void* __restrict__ x1, int C0, int C1,
+                                                       const float* __restrict__ part0, int ppi0, int ld0,
+                                                       const float* __restrict__ part1, int ppi1, int ld1,
+                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                       bf16* __restrict__ out, bf16* __restrict__ raw_out, int hw, int groups, int G,
+                                                       int pix_per_cta, int R, float eps, int silu, float* __restrict__ stats_out) {
+    extern __shared__ float gsm[];  // [2][Cg] per-channel totals | [Cg] (scale, shift)
+    __shared__ float s_grp[2 * kMaxGroups];
+    __shared__ float s_mr[2 * kMaxGroups];
+    const int C = C0 + C1;
+    const int cpg = C / groups;
+    const int Cg = G * cpg;
+    const int VC = Cg / 8;
+    const int slab = blockIdx.x, set = blockIdx.y, b = blockIdx.z;
+    const int c_base = set * Cg;
+    float* s_tot = gsm;
+    float2* s_ab = reinterpret_cast<float2*>(gsm + 2 * Cg);
+    ptx::pdl_trigger();
+    ptx::pdl_wait();
+    // fold the partial rows: nq thread groups take every nq-th row (8 loads in flight each), then a fixed-order fold
+    float* s_red = gsm + 4 * Cg;    // [nq][2 * Cg]
+    const int nq = max(1, (int)blockDim.x / (2 * Cg));
+    for (int t = threadIdx.x; t < nq * 2 * Cg; t += blockDim.x) {
+        const int q = t / (2 * Cg), v = t % (2 * Cg);
+        const int which = v / Cg, c = c_base + v % Cg;
+        const float* pp;
+        int n, stride;
+        if (c < C0) { pp = part0 + ((size_t)b * ppi0 * 2 + which) * ld0 + c; n = ppi0; stride = 2 * ld0; }
+        else { pp = part1 + ((size_t)b * ppi1 * 2 + which) * ld1 + (c - C0); n = ppi1; stride = 2 * ld1; }
+        float a = 0.f;
+#pragma unroll 8
+        for (int k = q; k < n; k += nq) a += __ldg(pp + (size_t)k * stride);
+        s_red[t] = a;
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < 2 * Cg; t += blockDim.x) {
+        float a = 0.f;
+        for (int q = 0; q < nq; ++q) a += s_red[q * 2 * Cg + t];
+        s_tot[t] = a;
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < 2 * G; t += blockDim.x) {
+        const int which = t / G, g = t % G;
+        float a = 0.f;
+        for (int j = 0; j < cpg; ++j) a += s_tot[which * Cg + g * cpg + j];
+        s_grp[2 * g + which] = a;
+    }
+    __syncthreads();
+    if (threadIdx.x < G) {
+        const double cnt = (double)hw * cpg;
+        const double mean = (double)s_grp[2 * threadIdx.x] / cnt;
+        double var = (double)s_grp[2 * threadIdx.x + 1] / cnt - mean * mean;
+        if (var < 0.0) var = 0.0;
+        s_mr[2 * threadIdx.x] = (float)mean;
+        s_mr[2 * threadIdx.x + 1] = (float)(1.0 / sqrt(var + (double)eps));
+        if (stats_out != nullptr && slab == 0) {
+            stats_out[((size_t)b * groups + set * G + threadIdx.x) * 2] = s_mr[2 * threadIdx.x];
+            stats_out[((size_t)b * groups + set * G + threadIdx.x) * 2 + 1] = s_mr[2 * threadIdx.x + 1];
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < Cg; i += blockDim.x) {
+        const int g = i / cpg;
+        const float a = s_mr[2 * g + 1] * __ldg(gamma + c_base + i);
+        s_ab[i] = make_float2(a, __ldg(beta + c_base + i) - s_mr[2 * g] * a);
+    }
+    __syncthreads();
+    const int vec = threadIdx.x % VC, prow = threadIdx.x / VC;
+    if (prow >= R) return;
+    const int c = c_base + vec * 8;
+    const void* src;
+    size_t off;
+    int pitch;
+    if (c < C0) { src = x0; off = (size_t)b * hw * C0 + c; pitch = C0; }
+    else { src = x1; off = (size_t)b * hw * C1 + (c - C0); pitch = C1; }
+    const int p_begin = slab * pix_per_cta;
+    const int p_end = min(p_begin + pix_per_cta, hw);
+    float2 ab[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) ab[j] = s_ab[vec * 8 + j];
+#pragma unroll 4
+    for (int pp = p_begin + prow; pp < p_end; pp += R) {
+        float f[8], y[8];
+        ld8<DT>(src, off + (size_t)pp * pitch, f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            y[j] = f[j] * ab[j].x + ab[j].y;
+            if (silu) y[j] = silu_f(y[j]);
+        }
+        const size_t o = ((size_t)b * hw + pp) * C + c;
+        st8<B200SD_BF16>(out, o, y);
+        if (raw_out) st8<B200SD_BF16>(raw_out, o, f);
+    }
+}
+
 // ---- LayerNorm: one warp per row, row held in registers (C <= 1280) ------------------------------
 template <int PAIRS_PER_LANE, int DT>
 __global__ void __launch_bounds__(256) layernorm_kernel(const void* __restrict__ x, const float* __restrict__ gamma,
@@ -525,4 +627,50 @@ extern "C" int b200sd_layernorm_split(const void* x, const float* gamma, const f
 extern "C" int b200sd_layernorm(const void* x, const float* gamma, const float* beta, void* out, int rows, int C,
                                 float eps, int in_dtype, b200sd_stream_t stream) {
     return b200sd_layernorm_split(x, gamma, beta, out, nullptr, rows, C, eps, in_dtype, stream);
+}
+
+// GroupNorm (+SiLU, + concat) whose statistics come from the producing GEMMs' gn_part buffers (b200sd_gemm_gn_layout).
+// part1 / ppi1 / ld1 describe the producer of x1 (ignored when x1 == NULL).  Returns B200SD_ERR_UNSUPPORTED for channel
+// layouts it does not cover (the caller then uses b200sd_groupnorm_silu).
+extern "C" int b200sd_groupnorm_silu_parts(const void* x0, const void* x1, int C0, int C1, const float* part0, int ppi0, int ld0,
+                                           const float* part1, int ppi1, int ld1, const float* gamma, const float* beta, void* out,
+                                           void* raw_out, float* stats_out, int batch, int hw, int groups, float eps, int silu,
+                                           int in_dtype, b200sd_stream_t stream) {
+    B200SD_REQUIRE(x0 && part0 && gamma && beta && out && ppi0 > 0, "groupnorm_parts: null pointer");
+    if (!x1) C1 = 0;
+    B200SD_REQUIRE(C1 == 0 || (part1 && ppi1 > 0), "groupnorm_parts: x1 without its statistics");
+    const int C = C0 + C1;
+    B200SD_REQUIRE(batch > 0 && hw > 0 && groups > 0 && groups <= kMaxGroups && C % groups == 0, "groupnorm_parts: bad shape");
+    B200SD_REQUIRE(C0 % 8 == 0 && C1 % 8 == 0, "groupnorm_parts: channel counts must be multiples of 8");
+    B200SD_REQUIRE(in_dtype == B200SD_BF16 || in_dtype == B200SD_F32, "groupnorm_parts: bad input dtype");
+    const int cpg = C / groups;
+    int G = 1;
+    while ((G * cpg) % 8 != 0 && G < groups) G *= 2;
+    while (G * 2 <= groups && groups % (G * 2) == 0 && G * cpg < 32) G *= 2;
+    const int Cg = G * cpg;
+    if ((Cg % 8) != 0 || groups % G != 0 || Cg / 8 > 512) return B200SD_ERR_UNSUPPORTED;
+    const int VC = Cg / 8, sets = groups / G;
+    int slabs = ceil_div(b200sd_num_sms() * 2, batch * sets);
+    if (slabs > hw / 32) slabs = hw / 32;
+    if (slabs < 1) slabs = 1;
+    const int ppc = ceil_div(hw, slabs);
+    slabs = ceil_div(hw, ppc);
+    int R = 256 / VC;
+    if (R < 1) R = 1;
+    if (R > ppc) R = ppc;
+    int threads = ((VC * R + 31) / 32) * 32;
+    if (threads < 64) threads = 64;
+    const size_t smem = ((size_t)4 * Cg + (size_t)std::max(threads, 2 * Cg)) * sizeof(float);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (in_dtype == B200SD_F32)
+        B200SD_CUDA(b200sd_launch(gn_parts_kernel<B200SD_F32>, dim3(slabs, sets, batch), dim3(threads), smem, s, x0, x1, C0, C1, part0, ppi0,
+                                  ld0, part1, ppi1, ld1, gamma, beta, static_cast<bf16*>(out), static_cast<bf16*>(raw_out), hw, groups, G,
+                                  ppc, R, eps, silu, stats_out));
+    else
+        B200SD_CUDA(b200sd_launch(gn_parts_kernel<B200SD_BF16>, dim3(slabs, sets, batch), dim3(threads), smem, s, x0, x1, C0, C1, part0, ppi0,
+                                  ld0, part1, ppi1, ld1, gamma, beta, static_cast<bf16*>(out), static_cast<bf16*>(raw_out), hw, groups, G,
+                                  ppc, R, eps, silu, stats_out));
+    COUNT_LAUNCH();
+    B200SD_LAUNCH_CHECK();
+    return B200SD_OK;
 }

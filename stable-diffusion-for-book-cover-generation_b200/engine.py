@@ -17,6 +17,8 @@ from __future__ import annotations
 
 import ctypes as C
 
+import os
+
 import torch
 
 from . import ops
@@ -70,19 +72,41 @@ class Engine:
         self._keep = []
         self.debug = False      # when True (eager runs only) every tapped activation is cloned
         self.debug_out = {}
+        # GroupNorm statistics from the producing GEMM's epilogue (B200SD_GN_FROM_GEMM=0: always the stand-alone kernel)
+        self.gn_from_gemm = os.environ.get("B200SD_GN_FROM_GEMM", "1") != "0"
+        self._gn_parts = {}     # id(activation buffer) -> ops.GnParts describing its CURRENT contents (plan-build time)
         with torch.cuda.device(device):
             self._build()
 
     # -- plan-building helpers --------------------------------------------------------------------
     def _gemm(self, plan, a0, w, out, **kw):
         rb = kw.pop("rowbias_ptr", None)
+        gn_hw = kw.pop("gn_hw", 0)    # > 0: `out` feeds a GroupNorm -- have the epilogue emit its column statistics
         args = ops.gemm(a0, w, out, launch=False, **kw)
         if rb is not None:
             args.rowbias, args.ldrb, args.rows_per_image = rb[0], rb[1], rb[2]
+        self._gn_parts.pop(id(out), None)      # whatever statistics described this (pooled) buffer are stale now
+        if gn_hw > 0 and self.gn_from_gemm:
+            parts = ops.gemm_attach_gn_parts(args, gn_hw, self.device)
+            if parts is not None:
+                self._gn_parts[id(out)] = parts
         self._keep.append((a0, w, out, kw))
         kind = "conv3x3" if args.conv_taps == 9 else "gemm"
         plan.append(lambda a=args: ops.gemm_run(a), kind, 2.0 * args.M * args.N * args.K,
                     f"{kind} M{args.M} N{args.N} K{args.K}")
+
+    def _groupnorm(self, x, skip, g, b, out, hw, eps, silu, raw_out=None):
+        """Plan one GroupNorm(+SiLU, + concat): from the producers' epilogue statistics when every source has them."""
+        N = self.N
+        p0 = self._gn_parts.get(id(x))
+        p1 = self._gn_parts.get(id(skip)) if skip is not None else None
+        C = x.shape[-1] + (skip.shape[-1] if skip is not None else 0)
+        if p0 is not None and (skip is None or p1 is not None) and ops.gn_parts_supported(C, 32):
+            self._keep.append((p0, p1))
+            self.plan.append(lambda: ops.groupnorm_silu_parts(x, skip, p0, p1, g, b, out, N, hw, 32, eps, silu, raw_out=raw_out),
+                             "groupnorm", 0, "groupnorm (stats from GEMM)")
+        else:
+            self.plan.append(lambda: ops.groupnorm_silu(x, skip, g, b, out, N, hw, 32, eps, silu, raw_out=raw_out), "groupnorm")
 
     def _tap(self, name, t, h, w):
         """Debug probe: snapshot activation `t` ([N*h*w, C] NHWC) as NCHW fp32 under `name`."""
@@ -144,14 +168,13 @@ class Engine:
             cin, cout = r.cin, r.cout
             t1 = pool.get(M, cin)
             raw = pool.get(M, cin) if "wsc" in wr else None   # bf16 copy of [x|skip]: operand of the 1x1 shortcut
-            P.append(lambda: ops.groupnorm_silu(x, skip, wr["g1"], wr["b1"], t1, N, h * w, 32, cfg.norm_eps, True,
-                                                raw_out=raw), "groupnorm")
+            self._groupnorm(x, skip, wr["g1"], wr["b1"], t1, h * w, cfg.norm_eps, True, raw_out=raw)
             hbuf = pool.get(M, cout, F32)
             rb = (self.tproj.data_ptr() + m._tproj_off[prefix] * 4, n_tp, h * w)
-            self._gemm(P, t1, wr["w1"], hbuf, bias=wr["cb1"], conv=(N, h, w), rowbias_ptr=rb)
+            self._gemm(P, t1, wr["w1"], hbuf, bias=wr["cb1"], conv=(N, h, w), rowbias_ptr=rb, gn_hw=h * w)
             pool.put(t1)
             t2 = pool.get(M, cout)
-            P.append(lambda: ops.groupnorm_silu(hbuf, None, wr["g2"], wr["b2"], t2, N, h * w, 32, cfg.norm_eps, True), "groupnorm")
+            self._groupnorm(hbuf, None, wr["g2"], wr["b2"], t2, h * w, cfg.norm_eps, True)
             pool.put(hbuf)
             if "wsc" in wr:
                 sc = pool.get(M, cout, F32)
@@ -160,7 +183,7 @@ class Engine:
             else:
                 sc = x
             y = pool.get(M, cout, F32)
-            self._gemm(P, t2, wr["w2"], y, bias=wr["cb2"], residual=sc, conv=(N, h, w))
+            self._gemm(P, t2, wr["w2"], y, bias=wr["cb2"], residual=sc, conv=(N, h, w), gn_hw=h * w)
             pool.put(t2)
             if sc is not x:
                 pool.put(sc)
@@ -177,7 +200,7 @@ class Engine:
             kv = torch.empty(N * self.S, 2 * Cc, dtype=torch.bfloat16, device=dev)
             self._gemm(self.ctx_plan, self.in_ctx, wa["w_kv2"], kv)
             t = pool.get(M, Cc)
-            P.append(lambda: ops.groupnorm_silu(x, None, wa["gn_g"], wa["gn_b"], t, N, h * w, 32, 1e-6, False), "groupnorm")
+            self._groupnorm(x, None, wa["gn_g"], wa["gn_b"], t, h * w, 1e-6, False)
             hs = pool.get(M, Cc, F32)
             self._gemm(P, t, wa["w_in"], hs, bias=wa["b_in"])
             # self attention
@@ -206,7 +229,7 @@ class Engine:
             self._gemm(P, ff, wa["w_ff2"], t, bias=wa["b_ff2"], residual=hs)
             pool.put(ff)
             y = pool.get(M, Cc, F32)
-            self._gemm(P, t, wa["w_out"], y, bias=wa["b_out"], residual=x)
+            self._gemm(P, t, wa["w_out"], y, bias=wa["b_out"], residual=x, gn_hw=h * w)
             pool.put(t)
             pool.put(hs)
             self._tap(prefix, y, h, w)
@@ -234,7 +257,7 @@ class Engine:
                 P.append(lambda x=x, col=col, h=h, w=w: ops.im2col_s2(x, col, N, h, w), "resample", 0, "im2col_s2")
                 h, w = h // 2, w // 2
                 y = pool.get(N * h * w, Cc, F32)
-                self._gemm(P, col, wd["w"], y, bias=wd["b"])
+                self._gemm(P, col, wd["w"], y, bias=wd["b"], gn_hw=h * w)
                 pool.put(col)
                 release(x)
                 x = y
@@ -273,7 +296,7 @@ class Engine:
                 release(x)
                 h, w = 2 * h, 2 * w
                 y = pool.get(N * h * w, Cc, F32)
-                self._gemm(P, up, wu["w"], y, bias=wu["b"], conv=(N, h, w))
+                self._gemm(P, up, wu["w"], y, bias=wu["b"], conv=(N, h, w), gn_hw=h * w)
                 pool.put(up)
                 x = y
                 self._tap(f"up{i}.us", x, h, w)
@@ -281,7 +304,7 @@ class Engine:
         # ---- out ----
         wo = Wp["conv_out"]
         t = pool.get(N * h * w, boc[0])
-        P.append(lambda x=x, t=t: ops.groupnorm_silu(x, None, wo["g"], wo["beta"], t, N, h * w, 32, cfg.norm_eps, True), "groupnorm")
+        self._groupnorm(x, None, wo["g"], wo["beta"], t, h * w, cfg.norm_eps, True)
         P.append(lambda t=t: ops.conv_out(t, wo["w"], wo["b"], self.out), "conv_io", 0, "conv_out")
         self.activation_bytes = pool.total
 

@@ -211,6 +211,55 @@ def gemm_run(args):
     check(lib().b200sd_gemm(C.byref(args), _stream()), "gemm")
 
 
+class GnParts:
+    """Column statistics a GEMM writes next to its fp32 output (GemmArgs.gn_part) for the GroupNorm that consumes it:
+    buf [total_parts][2][N] floats; image b owns partial rows [b * ppi, (b + 1) * ppi)."""
+    __slots__ = ("buf", "ppi", "ld")
+
+    def __init__(self, buf, ppi, ld):
+        self.buf, self.ppi, self.ld = buf, ppi, ld
+
+
+def gemm_attach_gn_parts(args, hw, device):
+    """Ask the library how a GEMM with `args` would lay out its GroupNorm statistics (hw = output rows per image); when
+    the shape is covered, allocate the buffer, point args.gn_part at it and return a GnParts, else return None."""
+    ppi, total = C.c_int(0), C.c_int(0)
+    check(lib().b200sd_gemm_gn_layout(C.byref(args), int(hw), C.byref(ppi), C.byref(total)), "gemm_gn_layout")
+    if ppi.value <= 0:
+        return None
+    buf = torch.zeros(total.value * 2 * args.N, dtype=torch.float32, device=device)
+    args.gn_part = buf.data_ptr()
+    return GnParts(buf, ppi.value, args.N)
+
+
+def groupnorm_silu_parts(x0, x1, parts0, parts1, gamma, beta, out, batch, hw, groups=32, eps=1e-5, silu=True, raw_out=None,
+                         stats_out=None):
+    """groupnorm_silu() with the statistics taken from the producers' GnParts (check gn_parts_supported(C) first)."""
+    _chk(x0, x1, gamma, beta, out, raw_out, stats_out)
+    C0 = x0.shape[-1]
+    C1 = x1.shape[-1] if x1 is not None else 0
+    rc = lib().b200sd_groupnorm_silu_parts(_p(x0), _p(x1), C0, C1, _p(parts0.buf), parts0.ppi, parts0.ld,
+                                           _p(parts1.buf) if parts1 is not None else None, parts1.ppi if parts1 is not None else 0,
+                                           parts1.ld if parts1 is not None else 0, _p(gamma), _p(beta), _p(out), _p(raw_out),
+                                           _p(stats_out), batch, hw, groups, float(eps), int(silu), _dt(x0), _stream())
+    check(rc, "groupnorm_silu_parts")
+    return out
+
+
+def gn_parts_supported(C, groups=32):
+    """Channel layouts b200sd_groupnorm_silu_parts covers (mirrors its G / Cg choice; anything else returns an error there)."""
+    if C % groups:
+        return False
+    cpg = C // groups
+    G = 1
+    while (G * cpg) % 8 != 0 and G < groups:
+        G *= 2
+    while G * 2 <= groups and groups % (G * 2) == 0 and G * cpg < 32:
+        G *= 2
+    Cg = G * cpg
+    return Cg % 8 == 0 and groups % G == 0 and Cg // 8 <= 512
+
+
 def gemm_dgrad(dy, w, out, *, residual=None, conv=None, Cin=None, block_n=0, launch=True, pair=0):
     """out[M, Cin] = dy[M, Cout] (*) w  (+ residual): data gradient of gemm(); w is the FORWARD weight
     [Cout][taps*Cin]; conv=(batch, H, W) -> gradient of the 3x3 pad-1 conv."""

@@ -159,3 +159,100 @@ def test_gemm_fp32_residual_and_output(M, N, K, split):
     outb = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
     ops.gemm(a, w, outb, bias=bias, residual=res, split_k=split)
     _close(outb, want)
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,conv,res", [
+    (2, 64, 64, 320, 320, True, True),      # 64x64 level conv2 (+fp32 residual), no split
+    (2, 32, 32, 640, 640, True, False),     # split-K cluster: every rank publishes the rows it stores
+    (2, 16, 16, 1280, 1280, True, True),    # deep split
+    (2, 64, 64, 320, 320, False, True),     # plain GEMM (transformer proj_out), hw % 128 == 0
+    (8, 64, 64, 320, 640, True, False),     # CTA pairs at batch 8
+    (2, 32, 48, 640, 640, True, False),     # portrait geometry
+])
+def test_gemm_groupnorm_statistics(B, H, W, Cin, Cout, conv, res):
+    """The fp32-output epilogue also publishes per-CTA column sums / sums of squares (gn_part); GroupNorm from those
+    partials (no statistics pass over the tensor) must match F.group_norm of the GEMM output."""
+    from b200sd import ops
+    from b200sd.packing import pack_conv3x3
+    _setup()
+    torch.manual_seed(B * H + Cin + Cout)
+    hw, M = H * W, B * H * W
+    a = torch.randn(M, Cin, device=DEV).bfloat16()
+    bias = torch.randn(Cout, device=DEV)
+    residual = torch.randn(M, Cout, device=DEV) * 3 + 1 if res else None
+    out = torch.empty(M, Cout, device=DEV)
+    if conv:
+        w = pack_conv3x3((torch.randn(Cout, Cin, 3, 3, device=DEV) / (9 * Cin) ** 0.5).bfloat16())
+        args = ops.gemm(a, w, out, bias=bias, residual=residual, conv=(B, H, W), launch=False)
+    else:
+        w = (torch.randn(Cout, Cin, device=DEV) / Cin ** 0.5).bfloat16()
+        args = ops.gemm(a, w, out, bias=bias, residual=residual, launch=False)
+    parts = ops.gemm_attach_gn_parts(args, hw, DEV)
+    assert parts is not None, "shape should be covered"
+    ops.gemm_run(args)
+    # the partial rows of an image add up to its column sums
+    pb = parts.buf.view(-1, 2, Cout)
+    assert pb.shape[0] >= B * parts.ppi
+    got = pb[:B * parts.ppi].view(B, parts.ppi, 2, Cout).sum(1)
+    o3 = out.view(B, hw, Cout).double()
+    assert (got[:, 0] - o3.sum(1)).abs().max().item() <= 1e-4 * o3.abs().sum(1).max().item() + 1e-3
+    assert (got[:, 1] - (o3 * o3).sum(1)).abs().max().item() <= 1e-4 * (o3 * o3).sum(1).max().item()
+    # GroupNorm from the partials
+    g = torch.randn(Cout, device=DEV)
+    bt = torch.randn(Cout, device=DEV)
+    y = torch.empty(M, Cout, device=DEV, dtype=torch.bfloat16)
+    stats = torch.empty(B, 32, 2, device=DEV)
+    assert ops.gn_parts_supported(Cout)
+    ops.groupnorm_silu_parts(out, None, parts, None, g, bt, y, B, hw, 32, 1e-5, True, stats_out=stats)
+    xn = out.view(B, hw, Cout).permute(0, 2, 1)
+    want = F.silu(F.group_norm(xn, 32, g, bt, 1e-5)).permute(0, 2, 1).reshape(M, Cout)
+    _close(y, want, 1.0 / 128)
+    xg = out.view(B, hw, 32, Cout // 32).double()
+    mean = xg.mean(dim=(1, 3))
+    rstd = 1.0 / torch.sqrt(xg.var(dim=(1, 3), unbiased=False) + 1e-5)
+    assert (stats[:, :, 0] - mean).abs().max().item() < 1e-4 * (1 + mean.abs().max().item())
+    assert ((stats[:, :, 1] - rstd) / rstd).abs().max().item() < 1e-3
+
+
+def test_groupnorm_parts_concat():
+    """[x | skip] GroupNorm with each source's statistics coming from its own producer (up-block resnets)."""
+    from b200sd import ops
+    _setup()
+    torch.manual_seed(5)
+    B, H, W, C0, C1 = 2, 32, 32, 640, 320
+    hw, M = H * W, B * H * W
+    outs, parts = [], []
+    for Cc in (C0, C1):
+        a = torch.randn(M, 320, device=DEV).bfloat16()
+        w = (torch.randn(Cc, 320, device=DEV) / 320 ** 0.5).bfloat16()
+        o = torch.empty(M, Cc, device=DEV)
+        args = ops.gemm(a, w, o, bias=torch.randn(Cc, device=DEV), launch=False)
+        p = ops.gemm_attach_gn_parts(args, hw, DEV)
+        assert p is not None
+        ops.gemm_run(args)
+        outs.append(o)
+        parts.append(p)
+    C = C0 + C1
+    g, bt = torch.randn(C, device=DEV), torch.randn(C, device=DEV)
+    y = torch.empty(M, C, device=DEV, dtype=torch.bfloat16)
+    raw = torch.empty(M, C, device=DEV, dtype=torch.bfloat16)
+    assert ops.gn_parts_supported(C)
+    ops.groupnorm_silu_parts(outs[0], outs[1], parts[0], parts[1], g, bt, y, B, hw, 32, 1e-5, True, raw_out=raw)
+    xc = torch.cat(outs, 1)
+    xn = xc.view(B, hw, C).permute(0, 2, 1)
+    want = F.silu(F.group_norm(xn, 32, g, bt, 1e-5)).permute(0, 2, 1).reshape(M, C)
+    _close(y, want, 1.0 / 128)
+    _close(raw, xc, 1.0 / 128)
+
+
+def test_gemm_gn_layout_rejects_straddling_tiles():
+    """8x8 level: a 128-row tile spans two images -> no statistics layout, the caller keeps the stand-alone GroupNorm."""
+    from b200sd import ops
+    a = torch.randn(2 * 64, 1280, device=DEV).bfloat16()
+    w = torch.randn(1280, 1280, device=DEV).bfloat16()
+    out = torch.empty(2 * 64, 1280, device=DEV)
+    args = ops.gemm(a, w, out, launch=False)
+    assert ops.gemm_attach_gn_parts(args, 64, DEV) is None
+    outb = torch.empty(2 * 256, 1280, device=DEV, dtype=torch.bfloat16)   # bf16 output: not covered either
+    a2 = torch.randn(2 * 256, 1280, device=DEV).bfloat16()
+    assert ops.gemm_attach_gn_parts(ops.gemm(a2, w, outb, launch=False), 256, DEV) is None
