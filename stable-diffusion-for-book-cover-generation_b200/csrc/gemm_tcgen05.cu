@@ -824,16 +824,21 @@ extern "C" int b200sd_gemm_gn_layout(const b200sd_gemm_args* a, int hw, int* par
     *parts_per_image = 0;
     *total_parts = 0;
     if (a->out_dtype != B200SD_F32 || a->epilogue != B200SD_EPI_LINEAR || (a->residual && a->residual_dtype != B200SD_F32)) return B200SD_OK;
-    int tiles_per_image;
+    // Partial row (m_tile * split + rank) covers the BLOCK_M / split output rows that rank stores; it is usable when those
+    // rows never straddle two images and the partial rows of an image are contiguous.
+    const int rpp = BLOCK_M / p.split_k;     // rows per partial
+    int ppi;
     if (p.conv) {
-        if (p.tile_n != 1 || a->H * a->W != hw) return B200SD_OK;
-        tiles_per_image = p.tiles_y;
+        if (a->H * a->W != hw) return B200SD_OK;
+        if (p.tile_n == 1) ppi = p.tiles_y * p.split_k;              // tiles inside one image (empty ranks publish zeros)
+        else if (p.rows_valid == BLOCK_M && hw % rpp == 0) ppi = hw / rpp;   // whole images per tile, split finer than an image
+        else return B200SD_OK;
     } else {
-        if (hw % BLOCK_M != 0 || a->M % hw != 0) return B200SD_OK;
-        tiles_per_image = hw / BLOCK_M;
+        if (a->M % hw != 0 || hw % rpp != 0) return B200SD_OK;
+        ppi = hw / rpp;
     }
     if (p.pair) m_tiles = (m_tiles + 1) & ~1;
-    *parts_per_image = tiles_per_image * p.split_k;
+    *parts_per_image = ppi;
     *total_parts = m_tiles * p.split_k;
     return B200SD_OK;
 }

@@ -168,6 +168,9 @@ def test_gemm_fp32_residual_and_output(M, N, K, split):
     (2, 64, 64, 320, 320, False, True),     # plain GEMM (transformer proj_out), hw % 128 == 0
     (8, 64, 64, 320, 640, True, False),     # CTA pairs at batch 8
     (2, 32, 48, 640, 640, True, False),     # portrait geometry
+    (2, 8, 8, 1280, 1280, True, True),      # 8x8 level: one tile holds both images, the split-K ranks separate them
+    (2, 8, 8, 1280, 1280, False, True),     # same for the plain GEMM (proj_out), split 2
+    (2, 8, 12, 1280, 1280, True, False),    # portrait 8x12: 96-row tiles, trailing ranks publish zeros
 ])
 def test_gemm_groupnorm_statistics(B, H, W, Cin, Cout, conv, res):
     """The fp32-output epilogue also publishes per-CTA column sums / sums of squares (gn_part); GroupNorm from those
@@ -246,10 +249,11 @@ def test_groupnorm_parts_concat():
 
 
 def test_gemm_gn_layout_rejects_straddling_tiles():
-    """8x8 level: a 128-row tile spans two images -> no statistics layout, the caller keeps the stand-alone GroupNorm."""
+    """A 128-row tile spanning two images with no K split to separate them -> no statistics layout, the caller keeps the
+    stand-alone GroupNorm."""
     from b200sd import ops
-    a = torch.randn(2 * 64, 1280, device=DEV).bfloat16()
-    w = torch.randn(1280, 1280, device=DEV).bfloat16()
+    a = torch.randn(2 * 64, 320, device=DEV).bfloat16()
+    w = torch.randn(1280, 320, device=DEV).bfloat16()
     out = torch.empty(2 * 64, 1280, device=DEV)
     args = ops.gemm(a, w, out, launch=False)
     assert ops.gemm_attach_gn_parts(args, 64, DEV) is None
