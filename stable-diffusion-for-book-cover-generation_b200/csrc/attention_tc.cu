@@ -135,8 +135,8 @@ __device__ __forceinline__ float2 poly_exp2x2(float2 t) {
     q = ffma2(q, f, make_float2(0.6932609677314758f, 0.6932609677314758f));
     q = ffma2(q, f, make_float2(0.9999280571937561f, 0.9999280571937561f));
     float2 e;   // add round(t) to the exponent field: bits(q) + (bits(y) << 23)
-    e.x = __int_as_float(__float_as_int(y.x) * 8388608 + __float_as_int(q.x));
-    e.y = __int_as_float(__float_as_int(y.y) * 8388608 + __float_as_int(q.y));
+    e.x = __uint_as_float((__float_as_uint(y.x) << 23) + __float_as_uint(q.x));   // unsigned: wrap-around is intended
+    e.y = __uint_as_float((__float_as_uint(y.y) << 23) + __float_as_uint(q.y));
     return e;
 }
 

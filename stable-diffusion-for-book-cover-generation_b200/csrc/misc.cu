@@ -25,7 +25,8 @@ __global__ void temb_kernel(const float* __restrict__ t, float* __restrict__ out
 }
 
 // ---- small-M linear: one warp per output feature, up to 8 batch rows at a time --------------------
-constexpr int kSlRows = 8;
+// kSlRows = batch rows handled per CTA (template: CFG batch 2 must not pay for 8 rows of accumulators and staging)
+template <int kSlRows>
 __global__ void __launch_bounds__(256) small_linear_kernel(const float* __restrict__ in, const bf16* __restrict__ w,
                                                            const float* __restrict__ bias, float* __restrict__ out,
                                                            int batch, int N, int K, int silu_in, int silu_out) {
@@ -53,7 +54,8 @@ __global__ void __launch_bounds__(256) small_linear_kernel(const float* __restri
         for (int f = 0; f < NF; ++f)
 #pragma unroll
             for (int r = 0; r < kSlRows; ++r) acc[f][r] = 0.f;
-        for (int v8 = lane; v8 < K / 8; v8 += 32) {
+#pragma unroll 5
+        for (int v8 = lane; v8 < K / 8; v8 += 32) {   // K = 1280: 5 x NF 16-byte weight loads in flight per lane
             uint4 u[NF];
 #pragma unroll
             for (int f = 0; f < NF; ++f) {
@@ -153,12 +155,14 @@ __global__ void conv_in_kernel(const float* __restrict__ x, const float* __restr
 
 // ---- conv_out: NHWC bf16 (Cin = 320) -> NCHW fp32 (Cout = 4); warp per pixel, lanes over channels -
 constexpr int kCoutMax = 4;
+constexpr int kCoCP = 5;   // channel pairs per lane of the unrolled path: Cin = 64 * kCoCP = 320
 __global__ void __launch_bounds__(256) conv_out_kernel(const bf16* __restrict__ x, const float* __restrict__ w,
                                                        const float* __restrict__ bias, float* __restrict__ out,
                                                        int batch, int Cin, int Cout, int H, int W, int pix_per_warp) {
     extern __shared__ float s_w[];  // packed [Cout][tap][Cin]
     ptx::pdl_trigger();
-    for (int i = threadIdx.x; i < Cout * 9 * Cin; i += blockDim.x) s_w[i] = __ldg(w + i);  // static weights: before the wait
+    for (int i = threadIdx.x; i < Cout * 9 * Cin / 4; i += blockDim.x)   // static weights: before the wait (Cin % 4 == 0)
+        reinterpret_cast<float4*>(s_w)[i] = __ldg(reinterpret_cast<const float4*>(w) + i);
     __syncthreads();
     ptx::pdl_wait();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -167,17 +171,45 @@ __global__ void __launch_bounds__(256) conv_out_kernel(const bf16* __restrict__ 
     for (int pix = first; pix < min(first + pix_per_warp, total); ++pix) {
         const int b = pix / hw, rem = pix % hw, y = rem / W, xx = rem % W;
         float acc[kCoutMax] = {0.f, 0.f, 0.f, 0.f};
-        for (int tap = 0; tap < 9; ++tap) {
-            const int yy = y + tap / 3 - 1, xs = xx + tap % 3 - 1;
-            if (yy < 0 || yy >= H || xs < 0 || xs >= W) continue;
-            const uint32_t* src = reinterpret_cast<const uint32_t*>(x + ((size_t)(b * H + yy) * W + xs) * Cin);
-            for (int c2 = lane; c2 < Cin / 2; c2 += 32) {
-                const float2 f = unpack_bf16x2(__ldg(src + c2));
+        if (Cin == 64 * kCoCP) {
+            // SD's conv_out (Cin = 320): issue the loads of all 9 taps before any arithmetic -- one memory latency per pixel
+            // instead of one per tap (the kernel was latency-bound: 45 us for 94 MFLOP)
+            uint32_t v[9][kCoCP];
 #pragma unroll
-                for (int co = 0; co < kCoutMax; ++co) {
-                    if (co < Cout) {
-                        const float* wp = s_w + (size_t)(co * 9 + tap) * Cin + 2 * c2;
-                        acc[co] += f.x * wp[0] + f.y * wp[1];
+            for (int tap = 0; tap < 9; ++tap) {
+                const int yy = y + tap / 3 - 1, xs = xx + tap % 3 - 1;
+                const bool ok = yy >= 0 && yy < H && xs >= 0 && xs < W;
+                const uint32_t* src = reinterpret_cast<const uint32_t*>(x + ((size_t)(b * H + (ok ? yy : y)) * W + (ok ? xs : xx)) * Cin);
+#pragma unroll
+                for (int i = 0; i < kCoCP; ++i) v[tap][i] = ok ? __ldg(src + lane + 32 * i) : 0u;
+            }
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) {
+#pragma unroll
+                for (int i = 0; i < kCoCP; ++i) {
+                    const float2 f = unpack_bf16x2(v[tap][i]);
+#pragma unroll
+                    for (int co = 0; co < kCoutMax; ++co) {
+                        if (co < Cout) {
+                            const float2 wv = *reinterpret_cast<const float2*>(s_w + (size_t)(co * 9 + tap) * Cin + 2 * (lane + 32 * i));
+                            acc[co] += f.x * wv.x + f.y * wv.y;
+                        }
+                    }
+                }
+            }
+        } else {
+            for (int tap = 0; tap < 9; ++tap) {
+                const int yy = y + tap / 3 - 1, xs = xx + tap % 3 - 1;
+                if (yy < 0 || yy >= H || xs < 0 || xs >= W) continue;
+                const uint32_t* src = reinterpret_cast<const uint32_t*>(x + ((size_t)(b * H + yy) * W + xs) * Cin);
+                for (int c2 = lane; c2 < Cin / 2; c2 += 32) {
+                    const float2 f = unpack_bf16x2(__ldg(src + c2));
+#pragma unroll
+                    for (int co = 0; co < kCoutMax; ++co) {
+                        if (co < Cout) {
+                            const float* wp = s_w + (size_t)(co * 9 + tap) * Cin + 2 * c2;
+                            acc[co] += f.x * wp[0] + f.y * wp[1];
+                        }
                     }
                 }
             }
@@ -257,19 +289,23 @@ extern "C" int b200sd_small_linear(const float* in, const void* w_bf16, const fl
                                    int K, int silu_in, int silu_out, b200sd_stream_t stream) {
     B200SD_REQUIRE(in && w_bf16 && out, "small_linear: null pointer");
     B200SD_REQUIRE(batch > 0 && N > 0 && K > 0 && K % 8 == 0, "small_linear: bad sizes (K must be a multiple of 8)");
-    const size_t smem = (size_t)kSlRows * K * sizeof(float);
+    const int rows = batch <= 2 ? 2 : (batch <= 4 ? 4 : 8);
+    const size_t smem = (size_t)rows * K * sizeof(float);
     B200SD_REQUIRE(smem <= 96 * 1024, "small_linear: K=%d too large", K);
     static bool configured = false;
     if (!configured) {
-        B200SD_CUDA(cudaFuncSetAttribute(small_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        B200SD_CUDA(cudaFuncSetAttribute(small_linear_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        B200SD_CUDA(cudaFuncSetAttribute(small_linear_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        B200SD_CUDA(cudaFuncSetAttribute(small_linear_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
         configured = true;
     }
     int gx = ceil_div(N, 8 * 4);
     const int cap = b200sd_num_sms() * 4;
     if (gx > cap) gx = cap;
-    dim3 grid(gx, ceil_div(batch, kSlRows));
-    B200SD_CUDA(b200sd_launch(small_linear_kernel, dim3(grid), dim3(256), smem, static_cast<cudaStream_t>(stream), in, static_cast<const bf16*>(w_bf16), bias,
-                                                                               out, batch, N, K, silu_in, silu_out));
+    dim3 grid(gx, ceil_div(batch, rows));
+    auto kern = rows == 2 ? small_linear_kernel<2> : (rows == 4 ? small_linear_kernel<4> : small_linear_kernel<8>);
+    B200SD_CUDA(b200sd_launch(kern, dim3(grid), dim3(256), smem, static_cast<cudaStream_t>(stream), in, static_cast<const bf16*>(w_bf16), bias,
+                              out, batch, N, K, silu_in, silu_out));
     COUNT_LAUNCH();
     B200SD_LAUNCH_CHECK();
     return B200SD_OK;
@@ -298,7 +334,7 @@ extern "C" int b200sd_conv_in(const float* x_nchw, const float* w, const float* 
 extern "C" int b200sd_conv_out(const void* x_nhwc, const float* w, const float* bias, float* out_nchw, int batch, int Cin,
                                int Cout, int H, int W, b200sd_stream_t stream) {
     B200SD_REQUIRE(x_nhwc && w && bias && out_nchw, "conv_out: null pointer");
-    B200SD_REQUIRE(Cout >= 1 && Cout <= kCoutMax && Cin % 2 == 0, "conv_out: Cout must be <= 4 and Cin even");
+    B200SD_REQUIRE(Cout >= 1 && Cout <= kCoutMax && Cin % 4 == 0, "conv_out: Cout must be <= 4 and Cin a multiple of 4");
     const size_t smem = (size_t)Cout * 9 * Cin * sizeof(float);
     B200SD_REQUIRE(smem <= 96 * 1024, "conv_out: Cin=%d too large", Cin);
     static bool configured = false;

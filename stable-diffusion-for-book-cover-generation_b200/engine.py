@@ -90,6 +90,8 @@ class Engine:
             parts = ops.gemm_attach_gn_parts(args, gn_hw, self.device)
             if parts is not None:
                 self._gn_parts[id(out)] = parts
+                self._keep.append(parts)       # the captured launch writes into parts.buf on every replay: it must outlive
+                #                                its entry in _gn_parts (popped when the pooled buffer is produced again)
         self._keep.append((a0, w, out, kw))
         kind = "conv3x3" if args.conv_taps == 9 else "gemm"
         plan.append(lambda a=args: ops.gemm_run(a), kind, 2.0 * args.M * args.N * args.K,
