@@ -564,5 +564,8 @@ def main():
         run_ours(args)
 
 
+# NCCL writes its banner ("NCCL version ...") to stdout; the contract is ONE JSON line there, so its log goes to stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+
 if __name__ == "__main__":
     main()
