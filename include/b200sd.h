@@ -234,9 +234,9 @@ int b200sd_layernorm(const void* x, const float* gamma, const float* beta, void*
 /* Fused (flash-style) attention: out = softmax(scale * Q K^T) V per (batch, head).
  * q: [batch*Sq, ldq] with head h at columns [h*d, (h+1)*d); k, v likewise with ldk / ldv;
  * out: [batch*Sq, ldo].  All bf16, fp32 softmax/accumulate.  d in {40, 80, 160} (+ 32, 64, 128).
- * workspace (optional, b200sd_attention_workspace_bytes, 128-byte aligned): with it, head dims 40 / 80 and
- * S_q, S_kv multiples of 128 run on the tcgen05/TMEM kernel (V is transposed into the workspace first);
- * every other shape, or workspace == NULL, runs the register-resident mma.sync kernel.
+ * Head dims 40 / 80 with S_q a multiple of 128 and S_kv a multiple of 64 run on the tcgen05/TMEM kernel (q, k, v read
+ * in place through TMA); every other shape runs the register-resident mma.sync kernel.  workspace / workspace_bytes are
+ * kept for ABI stability and ignored (b200sd_attention_workspace_bytes returns 0): no scratch is needed any more.
  * Replaces CrossAttention._attention (baddbmm + softmax + bmm). */
 size_t b200sd_attention_workspace_bytes(int batch, int heads, int Skv, int d);
 int b200sd_attention(const void* q, const void* k, const void* v, void* out, int batch, int heads, int Sq, int Skv,

@@ -246,8 +246,11 @@ int b200sd_attention_tc(const void* q, const void* k, const void* v, void* out, 
                         int d, int ldq, int ldk, int ldv, int ldo, float scale, void* workspace, size_t ws_bytes,
                         cudaStream_t s);
 
+// The tcgen05 kernel used to need a V^T scratch copy; it now reads V in place, so no workspace is required any more.
+// The entry point stays in the ABI (callers size their buffer with it) and returns 0.
 extern "C" size_t b200sd_attention_workspace_bytes(int batch, int heads, int Skv, int d) {
-    return (size_t)batch * heads * d * Skv * sizeof(bf16);
+    (void)batch; (void)heads; (void)Skv; (void)d;
+    return 0;
 }
 
 extern "C" int b200sd_attention_lse(const void* q, const void* k, const void* v, void* out, float* lse, int batch, int heads,

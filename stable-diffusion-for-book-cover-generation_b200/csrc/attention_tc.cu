@@ -4,7 +4,7 @@
 //
 // One CTA = 128 query rows of one (batch, head); it streams 64-key tiles and its softmax warps never wait for the
 // tensor core:
-//   warp 0    : TMA producer   Q once; K_j, V^T_j through a 4-stage smem ring (128B-swizzled boxes).  The q/k/v
+//   warp 0    : TMA producer   Q once; K_j, V_j through a 4-stage smem ring (128B-swizzled boxes).  The q/k/v
 //               buffers are addressed as 3-D tensors (d, head, row), so a 64-wide box over a 40-wide head is
 //               zero-filled past the head by TMA -- no padding kernels, no masking.
 //   warp 1    : TMEM allocator + single-thread MMA issuer:
@@ -12,13 +12,13 @@
 //                                                              the softmax of tile j has finished
 //                   O    += P_j V_j     (M128 x N = d, K = 64), P_j read from TMEM (A operand), O resident in TMEM
 //   warps 2-5 : softmax, one thread per query row (its TMEM lane): tcgen05.ld S_j, exp2 in fp32 against a LAGGING
-//               reference max (single pass; the tile max is collected on the side), P_j written back as bf16 over the
-//               S columns it came from (tcgen05.st) -- no shared-memory P tile, no proxy fence.  Only when a row
+//               reference max (single pass; the tile max is collected on the side), P_j written back to TMEM as bf16
+//               (tcgen05.st) -- no shared-memory P tile, no proxy fence.  Only when a row
 //               outgrows the reference by 2^kLazyThr is the tile redone (scores are still in registers) and the O
 //               rows rescaled in TMEM.  The softmax is MUFU-bound (16 ex2/clk/SM); every 4th score pair is
 //               exponentiated on the FMA pipe instead (Cody-Waite + cubic).
-// V is consumed K-major (keys contiguous), produced by a small transpose kernel into caller scratch.
-// TMEM columns: S0/P0 [0,64)  S1/P1 [64,128)  O [128,128+DN); two CTAs share an SM at d=40.
+// V is consumed in place: its [64 keys x 64 d] TMA boxes are the MN-major B operand of P V (no transpose kernel, no scratch).
+// TMEM columns: S0 [0,64)  S1 [64,128)  O [128,128+DN)  P0 P1 [.., +64) (bf16 pairs); two CTAs share an SM at d=40.
 // Measured (B200, d=40, S=4096): batch 2 145 -> 117 us, batch 8 480 -> 372 us against the first version (128-key
 // tiles, S single-buffered, P through shared memory, O folded in registers every tile, two-pass softmax).
 #include <atomic>
@@ -35,38 +35,13 @@ constexpr int kQ = 128;     // query rows per CTA
 constexpr int kBlk = kQ * 128;  // bytes of one [128 rows x 64 bf16] swizzled block
 
 struct AttnParams {
-    CUtensorMap tmQ, tmK, tmVt;
+    CUtensorMap tmQ, tmK, tmV;
     bf16* out;
     float* lse;   // optional [batch][heads][Sq]: log2-domain log-sum-exp of the scaled scores (for the backward)
     int Sq, Skv, heads, ldo;
     float scale_log2;
     float lazy_thr;   // log2 units a row may outgrow the lagging reference max before its tile is redone
 };
-
-// V [B*Skv, ldv] (head h at columns h*D..) -> Vt [B*H][D][Skv]
-__global__ void transpose_v_kernel(const bf16* __restrict__ v, bf16* __restrict__ vt, int Skv, int heads, int D, int ldv) {
-    __shared__ bf16 tile[64][72];  // [key][d] (+pad)
-    ptx::pdl_trigger();
-    ptx::pdl_wait();
-    const int bh = blockIdx.z, b = bh / heads, h = bh % heads;
-    const int s0 = blockIdx.x * 64, d0 = blockIdx.y * 64;
-    const int dcount = min(64, D - d0);
-    for (int i = threadIdx.x; i < 64 * 8; i += blockDim.x) {   // 64 keys x 8 16-byte chunks
-        const int r = i >> 3, c = (i & 7) * 8;
-        uint4 u = make_uint4(0, 0, 0, 0);
-        if (c < dcount && s0 + r < Skv) u = __ldg(reinterpret_cast<const uint4*>(v + (size_t)(b * Skv + s0 + r) * ldv + h * D + d0 + c));
-        *reinterpret_cast<uint4*>(&tile[r][c]) = u;
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < dcount * 8; i += blockDim.x) {  // dcount rows x 8 chunks of 8 keys
-        const int dd = i >> 3, sc = (i & 7) * 8;
-        bf16 tmp[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) tmp[j] = tile[sc + j][dd];
-        if (s0 + sc < Skv)
-            *reinterpret_cast<uint4*>(vt + ((size_t)bh * D + d0 + dd) * Skv + s0 + sc) = *reinterpret_cast<uint4*>(tmp);
-    }
-}
 
 __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
     asm volatile(
@@ -146,15 +121,13 @@ __global__ void __launch_bounds__(192, (D <= 40) ? 2 : 1) attention_tc_kernel(co
     constexpr int DN = (D + 15) / 16 * 16;    // MMA N of the PV product (48 / 80)
     constexpr int KSTEPS = (D + 15) / 16;     // UMMA K steps of the QK^T product
     constexpr int KBLK = kKV * 128;          // bytes of one K block [64 keys x 64 d]
-    constexpr int VBLK = D * 128;             // bytes of one V^T block [D rows x 64 keys]
-    constexpr int VBLK_PAD = ((DN * 128 + 1023) / 1024) * 1024;  // padded so the MMA may read DN rows
-    constexpr uint32_t kTmemCols = 256;
+    constexpr uint32_t kTmemCols = (128 + DN + 64 <= 256) ? 256 : 512;   // S0 S1 | O | P0 P1
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sQ = smem;                               // DKB blocks of [128 q x 64 d]
     uint8_t* sK = sQ + DKB * kBlk;                    // kStages x DKB blocks
-    uint8_t* sV = sK + kStages * DKB * KBLK;         // kStages x VBLK_PAD
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sV + kStages * VBLK_PAD);
+    uint8_t* sV = sK + kStages * DKB * KBLK;         // kStages x DKB blocks [64 keys x 64 d]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sV + kStages * DKB * KBLK);
     uint64_t* q_full = bars;
     uint64_t* k_full = bars + 1;                  // [kStages]
     uint64_t* k_empty = k_full + kStages;
@@ -176,7 +149,7 @@ __global__ void __launch_bounds__(192, (D <= 40) ? 2 : 1) attention_tc_kernel(co
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tmap(&p.tmQ);
         ptx::prefetch_tmap(&p.tmK);
-        ptx::prefetch_tmap(&p.tmVt);
+        ptx::prefetch_tmap(&p.tmV);
         ptx::mbar_init(q_full, 1);
         for (int i = 0; i < kStages; ++i) {
             ptx::mbar_init(&k_full[i], 1);
@@ -199,7 +172,9 @@ __global__ void __launch_bounds__(192, (D <= 40) ? 2 : 1) attention_tc_kernel(co
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 128;
+    // P has its own columns: were it written over S (as a first version did), the QK^T of tile j+2 would overwrite columns the
+    // PV product of tile j is still reading, ordered by nothing but the tensor pipe's issue order
+    const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 128, tmem_P = tmem_base + 128 + DN;
     ptx::pdl_wait();
 
     if (warp == 0) {
@@ -215,15 +190,16 @@ __global__ void __launch_bounds__(192, (D <= 40) ? 2 : 1) attention_tc_kernel(co
                 for (int kb = 0; kb < DKB; ++kb)
                     tma_load_3d(sK + (st * DKB + kb) * KBLK, &p.tmK, &k_full[st], kb * 64, h, b * p.Skv + j * kKV);
                 ptx::mbar_wait(&v_empty[st], ph ^ 1);
-                ptx::mbar_expect_tx(&v_full[st], VBLK);
-                tma_load_3d(sV + st * VBLK_PAD, &p.tmVt, &v_full[st], j * kKV, 0, b * p.heads + h);
+                ptx::mbar_expect_tx(&v_full[st], DKB * KBLK);
+                for (int kb = 0; kb < DKB; ++kb)
+                    tma_load_3d(sV + (st * DKB + kb) * KBLK, &p.tmV, &v_full[st], kb * 64, h, b * p.Skv + j * kKV);
             }
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
         if (ptx::elect_one()) {
             const uint32_t idesc_s = ptx::umma_idesc_bf16(128, kKV);
-            const uint32_t idesc_o = ptx::umma_idesc_bf16(128, DN);
+            const uint32_t idesc_o = ptx::umma_idesc_bf16(128, DN) | (1u << 16);   // B (= V, d contiguous) is MN-major
             auto issue_qk = [&](int j) {    // S_j = Q K_j^T into S buffer j & 1
                 const int st = j % kStages;
                 ptx::mbar_wait(&k_full[st], (j / kStages) & 1);
@@ -250,8 +226,9 @@ __global__ void __launch_bounds__(192, (D <= 40) ? 2 : 1) attention_tc_kernel(co
                 ptx::tc_fence_after();
 #pragma unroll
                 for (int ks = 0; ks < kKV / 16; ++ks) {   // O += P_j V_j, P read from TMEM (8 columns = 16 keys per step)
-                    const uint64_t db = ptx::umma_desc_k_sw128(ptx::smem_u32(sV + st * VBLK_PAD)) + 2 * ks;
-                    ptx::umma_bf16_ts(tmem_O, tmem_S + (j & 1) * kKV + ks * 8, db, idesc_o, (j > 0 || ks > 0) ? 1u : 0u);
+                    // 16 keys = two 1024-byte swizzle atoms per k-step; the second 64-wide d block is KBLK further
+                    const uint64_t db = ptx::umma_desc_mn_sw128(ptx::smem_u32(sV + st * DKB * KBLK) + ks * 2048, KBLK);
+                    ptx::umma_bf16_ts(tmem_O, tmem_P + (j & 1) * 32 + ks * 8, db, idesc_o, (j > 0 || ks > 0) ? 1u : 0u);
                 }
                 ptx::umma_commit(&v_empty[st]);
                 ptx::umma_commit(&o_full[j & 1]);
@@ -318,8 +295,10 @@ __global__ void __launch_bounds__(192, (D <= 40) ? 2 : 1) attention_tc_kernel(co
                 }
             }
             l += rs;
-            tmem_st_32x32b_x16(tS, &pk[0]);         // P_j over the first 32 columns of S_j (bf16 pairs)
-            tmem_st_32x32b_x16(tS + 16, &pk[16]);
+            // P_j as bf16 pairs into P buffer j & 1: its previous reader, PV_{j-2}, completed before QK_j did (s_full above)
+            const uint32_t tP = tmem_P + lane_addr + (j & 1) * 32;
+            tmem_st_32x32b_x16(tP, &pk[0]);
+            tmem_st_32x32b_x16(tP + 16, &pk[16]);
             ptx::tmem_st_wait();
             ptx::tc_fence_before();
             __syncwarp();
@@ -355,10 +334,8 @@ __global__ void __launch_bounds__(192, (D <= 40) ? 2 : 1) attention_tc_kernel(co
 }
 
 template <int D, int DKB, int POLY>
-int launch_tc(const bf16* q, const bf16* k, const bf16* vt, bf16* out, float* lse, int batch, int heads, int Sq, int Skv, int ldq,
-               int ldk, int ldo, float scale, cudaStream_t s) {
-    constexpr int DN = (D + 15) / 16 * 16;
-    constexpr int VBLK_PAD = ((DN * 128 + 1023) / 1024) * 1024;
+int launch_tc(const bf16* q, const bf16* k, const bf16* v, bf16* out, float* lse, int batch, int heads, int Sq, int Skv, int ldq,
+               int ldk, int ldv, int ldo, float scale, cudaStream_t s) {
     AttnParams p;
     memset(&p, 0, sizeof(p));
     {
@@ -376,10 +353,10 @@ int launch_tc(const bf16* q, const bf16* k, const bf16* vt, bf16* out, float* ls
         if (rc) return rc;
     }
     {
-        const uint64_t dims[3] = {(uint64_t)Skv, (uint64_t)D, (uint64_t)batch * heads};
-        const uint64_t str[3] = {0, (uint64_t)Skv * 2, (uint64_t)D * Skv * 2};
-        const uint32_t box[3] = {64, (uint32_t)D, 1};
-        int rc = b200sd_make_tmap(&p.tmVt, vt, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+        const uint64_t dims[3] = {(uint64_t)D, (uint64_t)heads, (uint64_t)batch * Skv};
+        const uint64_t str[3] = {0, (uint64_t)D * 2, (uint64_t)ldv * 2};
+        const uint32_t box[3] = {64, 1, (uint32_t)kKV};
+        int rc = b200sd_make_tmap(&p.tmV, v, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
         if (rc) return rc;
     }
     p.out = out;
@@ -391,7 +368,7 @@ int launch_tc(const bf16* q, const bf16* k, const bf16* vt, bf16* out, float* ls
     p.scale_log2 = scale * 1.4426950408889634f;
     static const float thr = [] { const char* e = getenv("B200SD_ATTN_THR"); return e ? (float)atof(e) : kLazyThr; }();
     p.lazy_thr = thr;
-    const size_t smem = (size_t)DKB * kBlk + (size_t)kStages * DKB * kKV * 128 + (size_t)kStages * VBLK_PAD + 256 + 1024;
+    const size_t smem = (size_t)DKB * kBlk + (size_t)2 * kStages * DKB * kKV * 128 + 256 + 1024;
     static bool configured = false;
     if (!configured) {
         B200SD_CUDA(cudaFuncSetAttribute(attention_tc_kernel<D, DKB, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -411,18 +388,14 @@ int b200sd_attention_tc(const void* q, const void* k, const void* v, void* out, 
                         int d, int ldq, int ldk, int ldv, int ldo, float scale, void* workspace, size_t ws_bytes,
                         cudaStream_t s) {
     if (!(d == 40 || d == 80) || Sq % kQ != 0 || Skv % kKV != 0) return B200SD_ERR_UNSUPPORTED;
-    const size_t need = (size_t)batch * heads * d * Skv * sizeof(bf16);
-    if (workspace == nullptr || ws_bytes < need) return B200SD_ERR_UNSUPPORTED;
-    if ((ldq * 2) % 16 != 0 || (ldk * 2) % 16 != 0 || (reinterpret_cast<uintptr_t>(workspace) & 127) != 0) return B200SD_ERR_UNSUPPORTED;
-    bf16* vt = static_cast<bf16*>(workspace);
-    B200SD_CUDA(b200sd_launch(transpose_v_kernel, dim3(ceil_div(Skv, 64), ceil_div(d, 64), batch * heads), dim3(256), 0, s,
-                              static_cast<const bf16*>(v), vt, Skv, heads, d, ldv));
-    g_b200sd_launches.fetch_add(1, std::memory_order_relaxed);
+    (void)workspace;   // no scratch any more: V is consumed in place (MN-major B operand), the V^T transpose kernel is gone
+    (void)ws_bytes;
+    if ((ldq * 2) % 16 != 0 || (ldk * 2) % 16 != 0 || (ldv * 2) % 16 != 0) return B200SD_ERR_UNSUPPORTED;
     // B200SD_ATTN_POLY=0 keeps every exponential on MUFU.EX2 (A/B switch; default: every 4th pair on the FMA pipe)
     static const int poly = [] { const char* e = getenv("B200SD_ATTN_POLY"); return e ? atoi(e) : 4; }();
 #define B200SD_ATTN_GO(DD, KB, PL)                                                                                           \
-    return launch_tc<DD, KB, PL>(static_cast<const bf16*>(q), static_cast<const bf16*>(k), vt, static_cast<bf16*>(out), lse, \
-                                  batch, heads, Sq, Skv, ldq, ldk, ldo, scale, s)
+    return launch_tc<DD, KB, PL>(static_cast<const bf16*>(q), static_cast<const bf16*>(k), static_cast<const bf16*>(v),      \
+                                  static_cast<bf16*>(out), lse, batch, heads, Sq, Skv, ldq, ldk, ldv, ldo, scale, s)
     if (d == 40) {
         if (poly == 0) B200SD_ATTN_GO(40, 1, 0);
         B200SD_ATTN_GO(40, 1, 4);

@@ -19,6 +19,8 @@ import ctypes as C
 
 import os
 
+import weakref
+
 import torch
 
 from . import ops
@@ -313,13 +315,16 @@ class Engine:
     # -- execution --------------------------------------------------------------------------------
     def set_context(self, ctx):
         """Project the (constant-over-steps) text context to every cross-attention's K/V once."""
-        key = (ctx.data_ptr(), ctx._version, tuple(ctx.shape), ctx.dtype)
-        if key == self._ctx_key:
+        # Cache hit only for the SAME live tensor object at the same version.  (The key used to be (data_ptr, version, shape):
+        # a new context tensor that the caching allocator placed at the freed address of the previous one -- same shape,
+        # version 0 -- was then taken for the old one and sampled with stale K/V.)
+        ref = self._ctx_key[0]() if self._ctx_key is not None else None
+        if ref is ctx and self._ctx_key[1] == ctx._version:
             return
         self.in_ctx.copy_(ctx.reshape(self.N * self.S, self.ctx_dim))
         for op in self.ctx_plan:
             op()
-        self._ctx_key = key
+        self._ctx_key = (weakref.ref(ctx), ctx._version)
 
     def _run_plan(self):
         for op in self.plan:

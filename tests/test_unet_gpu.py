@@ -184,3 +184,22 @@ def test_fp32_accuracy_path_within_1e_4(models):
     print(f"fp32 path max-rel vs fp32 oracle: {r:.3g}")
     assert r <= 1e-4, f"fp32 path max-rel {r:.4g}"
     assert torch.equal(got, again)
+
+
+def test_context_cache_is_not_fooled_by_address_reuse(models):
+    """The engine projects the context to K/V once per context tensor.  A NEW context that the caching allocator places at
+    the freed address of the previous one (same shape, version 0) must not be taken for the old one."""
+    _, ours = models
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(2, 4, 64, 64, generator=g).to(DEV)
+    ctx_a = torch.randn(2, 77, 768, generator=g).to(DEV)
+    ctx_b_host = torch.randn(2, 77, 768, generator=g)
+    with torch.no_grad():
+        ours(x, 500, ctx_a)
+        ptr_a = ctx_a.data_ptr()
+        del ctx_a
+        ctx_b = ctx_b_host.to(DEV)                    # usually lands on ctx_a's block
+        got = ours(x, 500, ctx_b).sample.clone()
+        same_address = ctx_b.data_ptr() == ptr_a
+        want = ours(x, 500, ctx_b.clone()).sample     # a different object: always re-projected
+    assert torch.equal(got, want), f"stale context K/V (address reused: {same_address})"
