@@ -41,12 +41,15 @@ def _stream():
 
 
 _ws_cache: dict = {}
+_ws_retired: list = []
 
 
 def _workspace(key, nbytes, device, zero=True):
     k = (key, device.index if device.index is not None else torch.cuda.current_device())
     t = _ws_cache.get(k)
     if t is None or t.numel() < nbytes:
+        if t is not None:
+            _ws_retired.append(t)   # a captured CUDA graph may still hold its address: outgrown scratch is kept, never freed
         t = (torch.zeros if zero else torch.empty)(nbytes, dtype=torch.uint8, device=device)
         _ws_cache[k] = t
     return t
