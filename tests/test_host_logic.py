@@ -138,3 +138,37 @@ def test_fp32_path_weight_split_reconstructs_the_3_term_product():
     assert torch.equal(c1.view(32, 9, 128)[:, :, :64], hi) and torch.equal(c1.view(32, 9, 128)[:, :, 64:], hi)
     assert torch.allclose(c1.view(32, 9, 128)[:, :, :64].float() + c2.view(32, 9, 64).float(), Wc.permute(0, 2, 3, 1).reshape(32, 9, 64),
                           rtol=0, atol=2e-4)
+
+
+def test_fma_pipe_exp2_polynomial_model():
+    """Numpy model of the attention kernel's FMA-pipe exponential (attention_tc.cu::poly_exp2x2): round-to-nearest split
+    through the 1.5 * 2^23 magic constant, cubic on [-0.5, 0.5], exponent add on the bit pattern.  Pins the coefficients:
+    relative error <= 1e-4 (P is rounded to bf16, 3.9e-3, right after) over the whole admissible range."""
+    import numpy as np
+    t = np.concatenate([np.linspace(-125.0, 6.0, 200001), np.array([-300.0, -125.0, -0.5, 0.0, 0.5, 6.0])]).astype(np.float32)
+    tc = np.maximum(t, np.float32(-125.0))
+    magic = np.float32(12582912.0)
+    y = (tc + magic).astype(np.float32)
+    ti = (y - magic).astype(np.float32)
+    f = (tc - ti).astype(np.float32)
+    assert np.all(np.abs(f) <= 0.5)
+    c = [np.float32(v) for v in (0.9999280571937561, 0.6932609677314758, 0.2426111251115799, 0.0551716685295105)]
+    q = (c[3] * f + c[2]).astype(np.float32)
+    q = (q * f + c[1]).astype(np.float32)
+    q = (q * f + c[0]).astype(np.float32)
+    bits = ((y.view(np.uint32).astype(np.uint64) << np.uint64(23)) + q.view(np.uint32).astype(np.uint64)) & np.uint64(0xFFFFFFFF)
+    e = bits.astype(np.uint32).view(np.float32)
+    want = np.exp2(tc.astype(np.float64))
+    rel = np.abs(e.astype(np.float64) - want) / want
+    assert rel.max() <= 1e-4, rel.max()
+
+
+def test_gn_parts_layouts_cover_every_sd_groupnorm():
+    """ops.gn_parts_supported mirrors the G / Cg choice of b200sd_groupnorm_silu_parts: every GroupNorm width of the SD v1.5
+    UNet (incl. the up-block concats) must be covered; a width the group count does not divide is refused."""
+    import importlib
+    ops = importlib.import_module("b200sd.ops")
+    for C in (320, 640, 960, 1280, 1920, 2560):
+        assert ops.gn_parts_supported(C, 32), C
+    assert not ops.gn_parts_supported(330, 32)     # not divisible by the group count
+    assert ops.gn_parts_supported(96, 32)          # 3 channels per group: 16 groups per CTA make 8-channel vectors
