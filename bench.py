@@ -139,6 +139,66 @@ def run_reference(args):
 
 
 # ---------------------------------------------------------------------------------------------------
+# library bar (SURVEY.md 8(d) "extra comparator"): the oracle module itself on the GPU in bf16 under eager torch
+# (cuDNN / cuBLASLt kernels), attention as the reference's diffusers materialises it and again through torch SDPA.
+# Not the reference arm and not part of the driver contract -- a reported yardstick for the same workload.
+# ---------------------------------------------------------------------------------------------------
+def run_library(args):
+    if int(os.environ.get("RANK", 0)) != 0:
+        return
+    import torch
+    import torch.nn.functional as F
+    from oracle import unet_ref
+    dev = torch.device("cuda", 0)
+    B = args.batch
+    h, w = (96, 64) if args.portrait else (64, 64)
+    m = unet_ref.make_oracle_unet(seed=0).to(dev).bfloat16().eval()
+    g = torch.Generator().manual_seed(42)
+    x = torch.randn(2 * B, 4, h, w, generator=g).to(dev).bfloat16()
+    ctx = torch.randn(2 * B, 77, 768, generator=g).to(dev).bfloat16()
+
+    def timed():
+        with torch.no_grad():
+            for _ in range(max(args.warmup, 3)):
+                m(x, 500, ctx)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            for i in range(args.steps):
+                m(x, 980 - 20 * (i % 50), ctx)
+            e1.record()
+            torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / args.steps
+
+    ms_mat = timed()
+
+    def sdpa_forward(self, xx, context=None):
+        context = xx if context is None else context
+        b, s, c = xx.shape
+        hh = self.heads
+        q = self.to_q(xx).view(b, s, hh, c // hh).transpose(1, 2)
+        k = self.to_k(context).view(b, -1, hh, c // hh).transpose(1, 2)
+        v = self.to_v(context).view(b, -1, hh, c // hh).transpose(1, 2)
+        o = F.scaled_dot_product_attention(q, k, v, scale=self.scale).transpose(1, 2).reshape(b, s, c)
+        return self.to_out[0](o)
+
+    orig = unet_ref.CrossAttention.forward
+    unet_ref.CrossAttention.forward = sdpa_forward
+    try:
+        ms_sdpa = timed()
+    finally:
+        unet_ref.CrossAttention.forward = orig
+    best = min(ms_mat, ms_sdpa)
+    print(json.dumps({
+        "impl": "library", "metric": "unet_denoise_it_per_s", "value": B * 1e3 / best, "unit": "it/s", "n_gpus": 1,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": best, "higher_is_better": True, "dtype": "bf16",
+        "data": "synthetic",
+        "config": {"workload": "sd15_unet_cfg_batch%d_%s" % (2 * B, "512x768" if args.portrait else "512px"),
+                   "what": "fp32-oracle module .cuda().bfloat16() under eager torch %s (cuDNN/cuBLASLt), UNet call only" % torch.__version__,
+                   "ms_per_step_materialised_attention": ms_mat, "ms_per_step_sdpa_attention": ms_sdpa}}), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------------
 def run_ours(args):
@@ -541,7 +601,8 @@ def main():
     ap.add_argument("--total-images", type=int, default=0,
                     help="config 5: shard this many images over the GPUs (strong scaling; overrides --batch)")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"], help="fp32 = the accuracy path (engine_fp32.py)")
-    ap.add_argument("--impl", default="b200sd", choices=["b200sd", "reference"])
+    ap.add_argument("--impl", default="b200sd", choices=["b200sd", "reference", "library"],
+                    help="library = the oracle module in bf16 under eager torch on the GPU (yardstick, sampling workload only)")
     ap.add_argument("--workload", default="sample", choices=["sample", "train", "train_text"],
                     help="sample = 50-step DDIM + CFG denoising (BASELINE configs[1], the headline); train = fine-tuning step (configs[2])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -555,6 +616,8 @@ def main():
         run_train_text(args) if args.workload == "train_text" and args.impl != "reference" else run_train(args)
     elif args.impl == "reference":
         run_reference(args)
+    elif args.impl == "library":
+        run_library(args)
     else:
         if args.gpus > 1 and "RANK" not in os.environ:
             # convenience: self-launch under torchrun
