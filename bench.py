@@ -627,8 +627,9 @@ def main():
         run_ours(args)
 
 
-# NCCL writes its banner ("NCCL version ...") to stdout; the contract is ONE JSON line there, so its log goes to stderr
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+# NCCL writes its banner ("NCCL version ...") to stdout; the contract is ONE JSON line there, so its log goes to a file
+# (not /dev/stderr: fopen(..., "w") would truncate a redirected log).  Set NCCL_DEBUG_FILE yourself to put it elsewhere.
+os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/b200sd_nccl.%h.%p.log")
 
 if __name__ == "__main__":
     main()
