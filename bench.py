@@ -198,6 +198,12 @@ def run_library(args):
                    "ms_per_step_materialised_attention": ms_mat, "ms_per_step_sdpa_attention": ms_sdpa}}), flush=True)
 
 
+def shard_images(total: int, world: int, rank: int) -> int:
+    """images of one batch are independent units -- contiguous chunks, remainder to the low ranks; a rank
+    may get none (B < #GPUs)."""
+    return total // world + (1 if rank < total % world else 0)
+
+
 # ---------------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------------
@@ -222,7 +228,7 @@ def run_ours(args):
     if args.total_images > 0:
         # BASELINE config 5: a fixed batch of images sharded over the GPUs (contiguous chunks, remainder to the low ranks;
         # ranks left without an image idle) -> strong scaling, no collective on the data path
-        B = args.total_images // world + (1 if rank < args.total_images % world else 0)
+        B = shard_images(args.total_images, world, rank)
     idle = B == 0
     if idle:
         B = 1          # keeps the buffers valid; this rank runs no steps and contributes no images

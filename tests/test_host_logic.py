@@ -172,3 +172,16 @@ def test_gn_parts_layouts_cover_every_sd_groupnorm():
         assert ops.gn_parts_supported(C, 32), C
     assert not ops.gn_parts_supported(330, 32)     # not divisible by the group count
     assert ops.gn_parts_supported(96, 32)          # 3 channels per group: 16 groups per CTA make 8-channel vectors
+
+
+def test_bench_image_sharding():
+    """bench.py --total-images: every image lands on exactly one rank, chunks differ by at most one, low ranks first."""
+    import importlib.util, os
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(os.path.dirname(os.path.dirname(__file__)), "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    for total in (1, 2, 3, 7, 8, 64):
+        for world in (1, 2, 4, 8):
+            parts = [bench.shard_images(total, world, r) for r in range(world)]
+            assert sum(parts) == total and max(parts) - min(parts) <= 1
+            assert parts == sorted(parts, reverse=True)
