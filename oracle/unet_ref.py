@@ -16,7 +16,8 @@ Self-checks standing in for the missing pins (tests/test_oracle_unet.py): 859 52
 686 state-dict tensors with the diffusers key names, timestep-embedding
 known answers (App. B.5), explicit-softmax attention vs torch SDPA, conv vs unfold+matmul.
 
-Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import
+Only tests/, __graft_entry__.smoke() and bench.py's baseline legs (cpu_baseline, --impl reference, --impl library: the checker / yardstick,
+never the thing shipped) may import
 this file.  The product path (package `b200sd`) never does.
 """
 from __future__ import annotations
