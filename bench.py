@@ -47,7 +47,7 @@ class ClockSampler:
         self.p = None
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={self.Q}",
-                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                       "--format=csv,noheader,nounits", "-lms", "20"], stdout=self.f,
                                       stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
@@ -87,10 +87,20 @@ def ddim_coefs(sch, t):
     return sch._coefs(t)
 
 
+def sample_config(batch, world, total_images, portrait):
+    """`config` of the sampling workload -- ONE builder for our arm and the reference arm, so that the two lines name the
+    workload identically (the driver compares the dicts)."""
+    h, w = (96, 64) if portrait else (64, 64)
+    return {"workload": "sd15_unet_ddim50_cfg7.5_" + ("512x768" if portrait else "512px"),
+            "images_per_gpu": batch, "total_images": total_images if total_images > 0 else batch * world,
+            "unet_batch": 2 * batch, "latent": f"4x{h}x{w}", "context": "77x768",
+            "weights": "random-init SD v1.5 UNet (859.5M params)", "guidance_scale": 7.5, "scheduler": "DDIM, 50 steps"}
+
+
 # ---------------------------------------------------------------------------------------------------
 # reference arm / cpu_baseline: the fp32 oracle (restated diffusers 0.7.2 math) on the host cores
 # ---------------------------------------------------------------------------------------------------
-def cpu_oracle_it_per_s(batch_images, budget_s, max_iters, warmup=1):
+def cpu_oracle_it_per_s(batch_images, budget_s, max_iters, warmup=1, hw=(64, 64)):
     import torch
     from oracle.unet_ref import make_oracle_unet
     from oracle import schedulers_ref as R
@@ -99,7 +109,7 @@ def cpu_oracle_it_per_s(batch_images, budget_s, max_iters, warmup=1):
     sch = R.DDIMSchedulerRef(clip_sample=False, set_alpha_to_one=False)
     sch.set_timesteps(50)
     g = torch.Generator().manual_seed(42)
-    lat = torch.randn(batch_images, 4, 64, 64, generator=g)
+    lat = torch.randn(batch_images, 4, hw[0], hw[1], generator=g)
     ctx2 = torch.randn(2 * batch_images, 77, 768, generator=g)
     ts = sch.timesteps.tolist()
     done, t_total = 0, 0.0
@@ -123,14 +133,14 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
-    v, done, t_total, cores = cpu_oracle_it_per_s(args.batch, budget_s=150.0, max_iters=args.steps, warmup=min(args.warmup, 1))
+    v, done, t_total, cores = cpu_oracle_it_per_s(args.batch, budget_s=150.0, max_iters=args.steps, warmup=min(args.warmup, 1),
+                                                  hw=(96, 64) if args.portrait else (64, 64))
     sample = f"{done} of {args.steps} denoising iterations (time-bounded), fp32 oracle on host CPU, CFG batch {2 * args.batch}"
     line = {
         "impl": "reference", "metric": "unet_denoise_it_per_s", "value": v, "unit": "it/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / max(done, 1),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "sd15_unet_ddim50_cfg7.5_512px", "images_per_gpu": args.batch, "latent": "4x64x64",
-                   "context": "77x768", "images_per_s": v / 50.0},
+        "config": sample_config(args.batch, args.gpus, args.total_images, args.portrait), "images_per_s": v / 50.0,
         "cpu_baseline": {"value": v, "unit": "it/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "it/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -202,6 +212,63 @@ def shard_images(total: int, world: int, rank: int) -> int:
     """images of one batch are independent units -- contiguous chunks, remainder to the low ranks; a rank
     may get none (B < #GPUs)."""
     return total // world + (1 if rank < total % world else 0)
+
+
+# ---------------------------------------------------------------------------------------------------
+# elementwise kernels (north_star subsystem 3): achieved HBM GB/s, SURVEY.md 8(d) algorithmic bytes
+# ---------------------------------------------------------------------------------------------------
+def elementwise_gbs(dev):
+    """cfg_ddim_step / cfg_plms_step / add_noise / mse at the REAL size of the workload (one 4x64x64 latent: 16 384 elements --
+    launch-latency-bound, a few hundred KB moved) and at a saturating 64 Mi elements (every operand larger than the 126 MB L2,
+    so each launch streams from HBM).  fp32 operands.  Each kernel: 3 warm-up launches, then `reps` launches captured into one
+    CUDA graph, CUDA-event timed.  bytes = operands the kernel must read + results it must write (stated per kernel)."""
+    import torch
+    from b200sd import ops
+    hbm, _, _, which = _peaks()
+    out = {"peak_gbs": hbm, "peak_kind": f"HBM copy bandwidth, {which}", "dtype": "f32", "sizes": {}}
+    sa = torch.linspace(0.99, 0.07, 1000, device=dev)
+    sb = (1 - sa * sa).sqrt()
+
+    def timed(fn, reps):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream()
+        with torch.cuda.graph(g, stream=side):
+            for _ in range(reps):
+                fn()
+        g.replay()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) * 1e-3 / reps
+
+    for label, B, E1, reps in (("real_1x4x64x64", 1, 4 * 64 * 64, 50), ("saturating_64Mi", 64, 1 << 20, 5)):
+        E = B * E1
+        mk = lambda: torch.randn(B, E1, device=dev)
+        eu, ec, x, o, eo, h1, h2, h3 = (mk() for _ in range(8))
+        t = torch.randint(0, 1000, (B,), device=dev)
+        rec = {}
+        cases = {
+            # name: (callable, bytes moved, formula)
+            "cfg_ddim_step": (lambda: ops.cfg_ddim_step(eu, ec, x, 7.5, 0.9, 0.43, 0.92, 0.39, out=o), 4 * E * 4,
+                              "4*E*b: read eps_u, eps_c, x; write x'"),
+            "cfg_plms_step": (lambda: ops.cfg_plms_step(eu, ec, x, [h1, h2, h3], [55 / 24, -59 / 24, 37 / 24, -9 / 24], 7.5, 1.01, 0.02,
+                                                        out=o, eps_out=eo), 8 * E * 4,
+                              "(k+5)*E*b, k=3: read eps_u, eps_c, x, 3 history eps; write x', combined eps (history)"),
+            "add_noise": (lambda: ops.add_noise(x, eu, t, sa, sb, out=o), 3 * E * 4, "3*E*b: read x0, noise; write x_t (+8 B/sample)"),
+            "mse_loss_fwd": (lambda: ops.mse_loss_fwd(eu, ec), 2 * E * 4, "2*E*b: read pred, target"),
+        }
+        for name, (fn, nbytes, formula) in cases.items():
+            sec = timed(fn, reps)
+            rec[name] = {"us": round(sec * 1e6, 2), "bytes": nbytes, "gbs": round(nbytes / sec / 1e9, 1),
+                         "frac_of_hbm_peak": round(nbytes / sec / 1e9 / hbm, 4), "bytes_formula": formula}
+        out["sizes"][label] = {"elements": E, "kernels": rec}
+    return out
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -279,7 +346,6 @@ def run_ours(args):
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
-        clocks = sampler.stop() if sampler else None
         eager_launches = ops.launch_count() - launches0
         gpu_launches = eager_launches + kernels_per_unet * args.steps
 
@@ -308,6 +374,7 @@ def run_ours(args):
             e2e_step(i)
         barrier()
         e2e_ms = (time.perf_counter() - t0) * 1e3
+        clocks = sampler.stop() if sampler else None      # sampled over both timed regions (device-resident + end to end)
 
         images_total = (0 if idle else B) * 1.0
         if world > 1:
@@ -318,34 +385,48 @@ def run_ours(args):
             dist.all_reduce(ti, op=dist.ReduceOp.SUM)
             images_total = float(ti[0])
 
-        # ---- roofline of the dominant kernel (tcgen05 GEMM / implicit-GEMM conv), timed live ----
+        # ---- roofline of the dominant kernel (tcgen05 GEMM / implicit-GEMM conv), timed live INSIDE the captured step ----
         roof = None
         kernels = None
-        if rank == 0 and args.precision == "bf16":
-            acc, per_op = eng.profile(iters=3)
+        if rank == 0 and args.precision == "bf16" and not idle:
+            acc, per_op, instrumented_ms = eng.profile(iters=5)
             hbm, tf_burst, tf_sus, which = _peaks()
             mm_ms = sum(acc[k][0] for k in ("gemm", "conv3x3") if k in acc)
             mm_fl = sum(acc[k][1] for k in ("gemm", "conv3x3") if k in acc)
             mm_n = sum(acc[k][2] for k in ("gemm", "conv3x3") if k in acc)
             achieved = mm_fl / (mm_ms * 1e-3) / 1e12 if mm_ms > 0 else 0.0
             traffic = None
-            tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
-            if os.path.exists(tp) and B == 1 and not args.portrait:
-                with open(tp) as f:
-                    traffic = json.load(f)["gemm_tcgen05_kernel"]["dram_bytes_per_launch"]   # ncu, per launch, same workload
+            for tp in ("r02_traffic.json", "r01_traffic.json"):
+                tp = os.path.join(ROOT, "profiles", tp)
+                if os.path.exists(tp) and B == 1 and not args.portrait:
+                    with open(tp) as f:
+                        traffic = json.load(f)["gemm_tcgen05_kernel"]["dram_bytes_per_launch"]   # ncu, per launch, same workload
+                    break
+            # the kernel is timed inside a long step -> the SUSTAINED bf16 peak is the denominator; the burst fraction is
+            # printed next to it
             roof = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (GEMM + implicit-GEMM conv3x3)",
                     "achieved": achieved, "peak": tf_sus, "unit": "TFLOP/s", "frac": achieved / tf_sus,
-                    "peak_kind": f"bf16 sustained, {which}", "launches_per_step": mm_n,
-                    "avg_launch_us": 1e3 * mm_ms / max(mm_n, 1), "flops_per_step": mm_fl, "traffic": traffic,
+                    "peak_kind": f"bf16 sustained, {which}", "frac_of_burst_peak": achieved / tf_burst, "burst_peak": tf_burst,
+                    "launches_per_step": mm_n, "avg_launch_us": 1e3 * mm_ms / max(mm_n, 1), "flops_per_step": mm_fl,
+                    "how": "CUDA-graph replay of the step with an event-record node between consecutive kernels "
+                           "(cold weights from HBM, true predecessor in L2); share of the step = "
+                           f"{mm_ms / max(instrumented_ms, 1e-9):.3f}",
+                    "traffic": traffic,
                     "traffic_unit": "DRAM bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)"}
             tot = sum(v[0] for v in acc.values())
             kernels = {k: {"ms_per_step": round(v[0], 4), "share": round(v[0] / tot, 4), "launches": v[2],
                            "tflops": round(v[1] / (v[0] * 1e-3) / 1e12, 1) if v[1] > 0 and v[0] > 0 else None}
                        for k, v in sorted(acc.items(), key=lambda kv: -kv[1][0])}
+            kernels["_instrumented_step_ms"] = round(instrumented_ms, 4)
             if args.dump_ops:
                 with open(args.dump_ops, "w") as f:
+                    f.write(f"# {len(per_op)} launches, in-step (instrumented graph replay {instrumented_ms:.3f} ms)\n")
                     for name, t_ms, fl in sorted(per_op, key=lambda r: -r[1]):
                         f.write(f"{t_ms * 1e3:9.1f} us  {fl / (t_ms * 1e-3) / 1e12 if fl else 0:8.1f} TF/s  {name}\n")
+
+    elementwise = None
+    if rank == 0 and args.precision == "bf16" and not args.no_elementwise:
+        elementwise = elementwise_gbs(dev)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -363,18 +444,26 @@ def run_ours(args):
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "strong" if args.total_images > 0 else "weak", "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32 (split-bf16 3-term products on the tensor cores)",
             "data": "synthetic",
-            "config": {"workload": "sd15_unet_ddim50_cfg7.5_" + ("512x768" if args.portrait else "512px"),
-                       "images_per_gpu": B, "total_images": args.total_images if args.total_images > 0 else B * world, "unet_batch": 2 * B, "latent": f"4x{h}x{w}", "context": "77x768",
-                       "weights": "random-init SD v1.5 UNet (859.5M params)", "images_per_s": value / 50.0,
-                       "e2e_images_per_s": e2e_value / 50.0, "tflops_end_to_end": value * flops_per_it / 1e12,
-                       "l2": "no flush: the 1.72 GB of bf16 weights streamed every step exceed the 126 MB L2",
-                       "cuda_graph": True},
+            "config": sample_config(args.batch if args.total_images <= 0 else B, world, args.total_images, args.portrait),
+            "images_per_s": value / 50.0, "e2e_images_per_s": e2e_value / 50.0, "tflops_end_to_end": value * flops_per_it / 1e12,
+            "l2": "no flush: the 1.72 GB of bf16 weights streamed every step exceed the 126 MB L2", "cuda_graph": True,
             "e2e": {"value": e2e_value, "unit": "it/s",
                     "h2d_bytes_per_step": int(lat_host.numel() * 4 + ctx_host.numel() * 4),
                     "d2h_bytes_per_step": int(out_host.numel() * 4)},
             "gpu_launches": int(gpu_launches), "clocks": clocks, "roofline": roof, "kernels": kernels,
-            "cpu_baseline": cpu,
+            "elementwise": elementwise, "cpu_baseline": cpu,
         }
+    # ---- fine-tuning legs (BASELINE configs[2] / [3]) inside the same line: the gradient-allreduce path is the only
+    # collective of the hot path, and the driver's scaling run only ever launches `bench.py --gpus N` ----
+    train = train_text = None
+    if args.precision == "bf16" and args.total_images <= 0 and not args.portrait and not args.no_train_legs:
+        torch.cuda.empty_cache()
+        train = train_leg(dev, world, rank, steps=5, warmup=3)
+        torch.cuda.empty_cache()
+        train_text = train_text_leg(dev, world, rank, local, steps=5, warmup=3)
+    if rank == 0:
+        line["train"] = train
+        line["train_text"] = train_text
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -408,6 +497,113 @@ def cpu_oracle_train_samples_per_s(batch, steps):
         t_total += time.perf_counter() - t0
         done += 1
     return done * batch / t_total, done, t_total, torch.get_num_threads()
+
+
+def _timed_steps(step_fn, steps, warmup, world, dev):
+    """W untimed + K timed calls of step_fn, barrier + synchronize on both sides, CUDA events, MAX over ranks -> ms/step."""
+    import torch
+    import torch.distributed as dist
+    for _ in range(warmup):
+        step_fn()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step_fn()
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    if world > 1:
+        tt = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = float(tt[0])
+    return ms
+
+
+def train_leg(dev, world, rank, steps=5, warmup=3, B=8):
+    """BASELINE configs[2] inside the default bench line: `steps` UNet fine-tuning steps at batch 8/GPU (add_noise + UNet fwd +
+    MSE + bwd + bucketed NCCL allreduce of the 859.5 M fp32 gradients + fused AdamW), then the SAME steps with the collective
+    switched off (every rank steps on its local gradient) -- the difference is the exposed (non-overlapped) communication."""
+    import torch
+    from b200sd.schedulers import DDPMScheduler
+    from b200sd.trainer import Trainer
+    from b200sd.unet import UNet2DConditionModel
+    torch.manual_seed(0)
+    unet = UNet2DConditionModel().to(dev)
+    sched = DDPMScheduler(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear", num_train_timesteps=1000)
+    tr = Trainer(unet, sched, lr=1e-5, weight_decay=1e-2)
+    g = torch.Generator().manual_seed(1000 + rank)
+    x0, noise = torch.randn(B, 4, 64, 64, generator=g).to(dev), torch.randn(B, 4, 64, 64, generator=g).to(dev)
+    t, ctx = torch.randint(0, 1000, (B,), generator=g).to(dev), torch.randn(B, 77, 768, generator=g).to(dev)
+    step = lambda: tr.train_step(x0, noise, t, ctx)
+    ms = _timed_steps(step, steps, warmup, world, dev)
+    tr.allreduce_enabled = False
+    ms_local = _timed_steps(step, steps, 1, world, dev)
+    tr.allreduce_enabled = True
+    loss = float(step())
+    n_param = sum(p.numel() for p in unet.parameters())
+    _, _, tf_sus, _ = _peaks()
+    flops_step = 3 * B * FLOPS_PER_SAMPLE_64
+    rec = {"workload": "sd15_unet_finetune_512px", "batch_per_gpu": B, "steps": steps, "warmup": warmup, "n_gpus": world,
+           "ms_per_step": ms, "samples_per_s": B * world / (ms * 1e-3), "ms_per_step_without_allreduce": ms_local,
+           "exposed_comm_ms": ms - ms_local, "allreduce_bytes_on_wire_per_gpu": int(2 * (world - 1) / world * n_param * 4),
+           "tflops_per_gpu": flops_step / (ms * 1e-3) / 1e12, "frac_of_sustained_bf16_peak": flops_step / (ms * 1e-3) / 1e12 / tf_sus,
+           "last_loss": loss, "collective": "NCCL all_reduce(SUM) of the flat fp32 gradient buffer in 64 MB buckets, overlapped with the backward"}
+    del tr, unet
+    return rec
+
+
+def train_text_leg(dev, world, rank, local, steps=5, warmup=3, B=8):
+    """BASELINE configs[3]: text-encoder fine-tuning (UNet frozen: our forward + data-gradient-only backward down to the context;
+    CLIP text model = stock transformers under DistributedDataParallel) at batch 8/GPU."""
+    import torch
+    from transformers import CLIPTextConfig, CLIPTextModel
+    from b200sd import ops
+    from b200sd.schedulers import DDPMScheduler
+    from b200sd.unet import UNet2DConditionModel
+    torch.manual_seed(0)
+    unet = UNet2DConditionModel().to(dev).eval().requires_grad_(False)            # finetune_sd.py:391-395
+    clip = CLIPTextModel(CLIPTextConfig(hidden_size=768, intermediate_size=3072, num_hidden_layers=12, num_attention_heads=12,
+                                        vocab_size=49408, max_position_embeddings=77, hidden_act="quick_gelu")).to(dev).train()
+    model = torch.nn.parallel.DistributedDataParallel(clip, device_ids=[local]) if world > 1 else clip
+    opt = torch.optim.AdamW(clip.parameters(), lr=1e-5, weight_decay=1e-2, fused=True)
+    sched = DDPMScheduler(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear", num_train_timesteps=1000)
+    g = torch.Generator().manual_seed(1000 + rank)
+    x0, noise = torch.randn(B, 4, 64, 64, generator=g).to(dev), torch.randn(B, 4, 64, 64, generator=g).to(dev)
+    t, ids = torch.randint(0, 1000, (B,), generator=g).to(dev), torch.randint(0, 49408, (B, 77), generator=g).to(dev)
+    last = []
+
+    def step(m=model):
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            ctx = m(ids)[0]                                                        # finetune_sd.py:477
+        noisy = sched.add_noise(x0, noise, t)
+        loss = ops.mse_loss(unet(noisy, t, ctx.float()).sample, noise)
+        loss.backward()
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+        last[:] = [loss.detach()]
+
+    ms = _timed_steps(step, steps, warmup, world, dev)
+    ms_local = ms
+    if world > 1:
+        def local_step():
+            with model.no_sync():          # same step, DDP's allreduce suppressed
+                step()
+        ms_local = _timed_steps(local_step, steps, 1, world, dev)
+    n_param = sum(p.numel() for p in clip.parameters())
+    _, _, tf_sus, _ = _peaks()
+    flops_step = 2 * B * FLOPS_PER_SAMPLE_64
+    rec = {"workload": "sd15_text_encoder_finetune_512px", "batch_per_gpu": B, "steps": steps, "warmup": warmup, "n_gpus": world,
+           "ms_per_step": ms, "samples_per_s": B * world / (ms * 1e-3), "ms_per_step_without_allreduce": ms_local,
+           "exposed_comm_ms": ms - ms_local, "allreduce_bytes_on_wire_per_gpu": int(2 * (world - 1) / world * n_param * 4),
+           "tflops_per_gpu": flops_step / (ms * 1e-3) / 1e12, "frac_of_sustained_bf16_peak": flops_step / (ms * 1e-3) / 1e12 / tf_sus,
+           "last_loss": float(last[0]), "collective": "torch DistributedDataParallel (NCCL) over the 123.1 M CLIP parameters"}
+    del model, clip, unet, opt
+    return rec
 
 
 def run_train(args):
@@ -612,6 +808,8 @@ def main():
     ap.add_argument("--workload", default="sample", choices=["sample", "train", "train_text"],
                     help="sample = 50-step DDIM + CFG denoising (BASELINE configs[1], the headline); train = fine-tuning step (configs[2])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train-legs", action="store_true", help="skip the fine-tuning sub-records (configs 3 / 4) of the default line")
+    ap.add_argument("--no-elementwise", action="store_true", help="skip the elementwise GB/s sub-record")
     ap.add_argument("--dump-ops", default=None, help="write the per-launch timing table to this file")
     args = ap.parse_args()
     if args.workload in ("train", "train_text"):

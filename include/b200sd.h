@@ -41,6 +41,13 @@ int b200sd_version(void);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 int64_t b200sd_launch_count(void);
 
+/* In-graph timers (measurement plumbing): process-wide CUDA events.  b200sd_timer_record(i) records event i on
+ * `stream`; while the stream is being captured the record becomes an external event-record node, so a replay of the captured
+ * plan timestamps the gaps between its kernels and b200sd_timer_elapsed_ms(i, j) gives per-kernel times inside the real step. */
+int b200sd_timer_reserve(int n);
+int b200sd_timer_record(int i, b200sd_stream_t stream);
+int b200sd_timer_elapsed_ms(int i, int j, float* ms);
+
 /* ---- scheduler / loss elementwise kernels (HBM-bound) ------------------------------------- */
 
 /* Classifier-free-guidance combine fused with the DDIM update (eta = 0):
@@ -114,6 +121,8 @@ int b200sd_small_linear(const float* in, const void* w_bf16, const float* bias, 
  */
 #define B200SD_EPI_LINEAR 0
 #define B200SD_EPI_GEGLU 1
+#define B200SD_W_ROW_MAJOR 0
+#define B200SD_W_KBLOCK_MAJOR 1
 
 typedef struct b200sd_gemm_args {
     const void* a0;        /* bf16 */
@@ -141,6 +150,9 @@ typedef struct b200sd_gemm_args {
     int pair;              /* CTA pairs (tcgen05 cta_group::2, 256-row MMA tiles): 0 = auto, 1 = on, -1 = off */
     float* gn_part;        /* optional: per-CTA column statistics [parts][2][N] of the fp32 output (sum | sum of squares over the
                               rows each CTA stores), consumed by b200sd_groupnorm_silu_parts; layout from b200sd_gemm_gn_layout */
+    int w_layout;          /* B200SD_W_ROW_MAJOR: w is [N][K]; B200SD_W_KBLOCK_MAJOR: w is [K/64][N][64] (the 64-wide k-blocks of
+                              all N rows stored together), so the weight tile of one k-block is one contiguous run of DRAM --
+                              the layout for weights that are streamed from HBM once per step (small-M / deep-K layers) */
 } b200sd_gemm_args;
 
 size_t b200sd_gemm_workspace_bytes(void);

@@ -27,12 +27,22 @@ class _UNetFn(torch.autograd.Function):
         ctx.n_params = len(params)
         ctx.param_ids = [id(p) for p in params]
         ctx.need_ctx = ehs.requires_grad
-        return engine.run_forward(sample.detach(), timestep, ehs.detach())
+        ctx.ehs_dtype = ehs.dtype
+        out = engine.run_forward(sample.detach(), timestep, ehs.detach())
+        # the engine keeps the activations the backward needs in per-geometry static buffers: a second forward of the
+        # same geometry overwrites them, so each node remembers which forward it belongs to
+        engine.forward_generation = getattr(engine, "forward_generation", 0) + 1
+        ctx.generation = engine.forward_generation
+        return out
 
     @staticmethod
     @once_differentiable
     def backward(ctx, d_out):
         eng = ctx.engine
+        if ctx.generation != eng.forward_generation:
+            raise RuntimeError("b200sd: backward() of a UNet forward whose saved activations were overwritten by a later forward "
+                               "of the same geometry (the training engine keeps ONE set of static buffers per geometry): "
+                               "call backward() before the next training forward")
         model, flat = eng.model, eng.flat
         direct = model._direct_grads
         if eng.train_weights:
@@ -47,7 +57,8 @@ class _UNetFn(torch.autograd.Function):
             grads = tuple(flat.regs[i].gview if flat.regs[i].param.requires_grad else None for i in ctx.param_ids)
         else:
             grads = (None,) * ctx.n_params
-        return (None, None, None, d_ctx if ctx.need_ctx else None) + grads
+        # d_ctx is a view of an engine buffer that the next backward overwrites: hand autograd its own copy
+        return (None, None, None, d_ctx.to(ctx.ehs_dtype, copy=True) if ctx.need_ctx and d_ctx is not None else None) + grads
 
 
 def ensure_flat(model, dev):

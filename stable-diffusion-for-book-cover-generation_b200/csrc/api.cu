@@ -21,6 +21,34 @@ extern "C" const char* b200sd_last_error(void) { return g_err; }
 extern "C" int b200sd_version(void) { return 100; }
 extern "C" int64_t b200sd_launch_count(void) { return g_b200sd_launches.load(); }
 
+// ---- in-graph timers: events recorded with cudaEventRecordExternal, so that a captured plan can carry a timestamp between
+// any two of its kernels and a replay yields per-kernel times under the REAL conditions of the step (cold weights streaming
+// from HBM, the true predecessor in L2) -- what bench.py's roofline uses.
+#include <vector>
+static std::vector<cudaEvent_t> g_timers;
+extern "C" int b200sd_timer_reserve(int n) {
+    B200SD_REQUIRE(n >= 0 && n <= (1 << 20), "timer_reserve: bad count %d", n);
+    while ((int)g_timers.size() < n) {
+        cudaEvent_t e;
+        B200SD_CUDA(cudaEventCreate(&e));
+        g_timers.push_back(e);
+    }
+    return B200SD_OK;
+}
+extern "C" int b200sd_timer_record(int i, b200sd_stream_t stream) {
+    B200SD_REQUIRE(i >= 0 && i < (int)g_timers.size(), "timer_record: index %d not reserved", i);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    B200SD_CUDA(cudaStreamIsCapturing(s, &st));
+    B200SD_CUDA(cudaEventRecordWithFlags(g_timers[i], s, st == cudaStreamCaptureStatusActive ? cudaEventRecordExternal : cudaEventRecordDefault));
+    return B200SD_OK;
+}
+extern "C" int b200sd_timer_elapsed_ms(int i, int j, float* ms) {
+    B200SD_REQUIRE(ms && i >= 0 && j >= 0 && i < (int)g_timers.size() && j < (int)g_timers.size(), "timer_elapsed: bad index");
+    B200SD_CUDA(cudaEventElapsedTime(ms, g_timers[i], g_timers[j]));
+    return B200SD_OK;
+}
+
 bool b200sd_pdl_enabled() {
     static int v = -1;
     if (v < 0) {

@@ -81,6 +81,8 @@ struct KParams {
     int atomic_out;      // fp32 red.add into `out` (wgrad: split-K partials and gradient accumulation)
     int pair;            // CTA pair (cta_group::2): two CTAs adjacent in M form one 256 x block_n MMA tile; each loads its own
                          // 128 A rows and HALF of the B tile, so the L2 -> smem traffic per FLOP drops by ~1/3
+    int w_kmajor;        // forward B operand stored k-block-major [K/64][N][64]: one tile k-block = ONE contiguous bn x 128 B run of
+                         // DRAM instead of bn 128-byte pieces a whole weight row (K * 2 B) apart
     float* gn_part;      // optional [m_tiles * split_k][2][N]: per-column (sum, sum of squares) of the rows each CTA stores --
                          // the GroupNorm that consumes this output gets its statistics from here instead of re-reading it
     unsigned long long* trace;  // optional [ctas][8] globaltimer stamps (debug)
@@ -308,7 +310,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tcgen05_kernel(const __gr
                 }
                 // ---- B ----
                 if (b_mode == 0) {
-                    LD2(dst_b, &p.tmB, kb * BLOCK_K, nb0);
+                    if (p.w_kmajor) LD3(dst_b, &p.tmB, 0, nb0, kb);
+                    else LD2(dst_b, &p.tmB, kb * BLOCK_K, nb0);
                 } else if (b_mode == 1) {
                     if (!p.conv) {
                         for (int j = 0; j < nboxb; ++j) LD2(dst_b + j * 8192, &p.tmB, nb0 + j * 64, kb * BLOCK_K);
@@ -795,7 +798,15 @@ extern "C" int b200sd_gemm(const b200sd_gemm_args* a, b200sd_stream_t stream) {
             if (rc) return rc;
         }
     }
-    {
+    p.w_kmajor = a->w_layout == B200SD_W_KBLOCK_MAJOR;
+    B200SD_REQUIRE(a->w_layout == B200SD_W_ROW_MAJOR || a->w_layout == B200SD_W_KBLOCK_MAJOR, "gemm: bad w_layout %d", a->w_layout);
+    if (p.w_kmajor) {
+        const uint64_t dimsB[3] = {(uint64_t)BLOCK_K, (uint64_t)a->N, (uint64_t)(a->K / BLOCK_K)};
+        const uint64_t strB[3] = {0, (uint64_t)BLOCK_K * 2, (uint64_t)a->N * BLOCK_K * 2};
+        const uint32_t boxB[3] = {BLOCK_K, (uint32_t)(p.pair ? bn / 2 : bn), 1};
+        int rc = b200sd_make_tmap(&p.tmB, a->w, 3, dimsB, strB, boxB, CU_TENSOR_MAP_SWIZZLE_128B);
+        if (rc) return rc;
+    } else {
         const uint64_t dimsB[2] = {(uint64_t)a->K, (uint64_t)a->N};
         const uint64_t strB[2] = {0, (uint64_t)a->K * 2};
         const uint32_t boxB[2] = {BLOCK_K, (uint32_t)(p.pair ? bn / 2 : bn)};

@@ -353,40 +353,43 @@ class Engine:
                 self.graph.replay()
             return self.out.clone()
 
-    def profile(self, iters=3, reps=4):
-        """Per-launch device time of every plan entry, measured warm and without host launch gaps:
-        each entry is captured into its own CUDA graph holding `reps` back-to-back launches and
-        the replay is timed with CUDA events.  Returns ({kind: [ms, flops, launches]} per step,
-        [(name, ms, flops)] per entry)."""
+    def profile(self, iters=5):
+        """Per-launch device time of every plan entry measured INSIDE the step: the whole plan is captured once more into a CUDA
+        graph with an external event-record node (b200sd_timer_record) between consecutive entries, and the replays are read
+        back per entry.  Every kernel therefore runs under the conditions of the real step -- its weights streaming cold from
+        HBM, its input left in L2 by its true predecessor, no host launch gaps.  (The first version replayed each entry four
+        times back to back in a graph of its own: warm weights, optimistic.)  Returns ({kind: [ms, flops, launches]} per step,
+        [(name, ms, flops)] per entry, ms of the whole instrumented replay)."""
         with torch.cuda.device(self.device):
+            entries = [(op, meta) for op, meta in zip(self.plan, self.plan.meta) if meta[0] != "tap"]
+            n = len(entries)
+            check(lib().b200sd_timer_reserve(n + 1), "timer_reserve")
             self._run_plan()
             torch.cuda.synchronize()
-            graphs = []
             side = torch.cuda.Stream()
-            for op, (kind, flops, name) in zip(self.plan, self.plan.meta):
-                if kind == "tap":
-                    continue
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g, stream=side):
-                    for _ in range(reps):
-                        op()
-                graphs.append((g, kind, flops, name))
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=side):
+                sh = torch.cuda.current_stream().cuda_stream
+                for i, (op, _meta) in enumerate(entries):
+                    check(lib().b200sd_timer_record(i, sh), "timer_record")
+                    op()
+                check(lib().b200sd_timer_record(n, sh), "timer_record")
             torch.cuda.synchronize()
-            times = [0.0] * len(graphs)
+            times = [0.0] * n
+            total = 0.0
+            ms = C.c_float(0.0)
+            g.replay()          # warm-up replay of the instrumented graph
+            torch.cuda.synchronize()
             for _ in range(iters):
-                self._run_plan()   # restore a coherent activation state, warm L2 with the real data flow
-                evs = []
-                for g, kind, flops, name in graphs:
-                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                    e0.record()
-                    g.replay()
-                    e1.record()
-                    evs.append((e0, e1))
+                g.replay()
                 torch.cuda.synchronize()
-                for i, (e0, e1) in enumerate(evs):
-                    times[i] += e0.elapsed_time(e1) / reps / iters
+                for i in range(n):
+                    check(lib().b200sd_timer_elapsed_ms(i, i + 1, C.byref(ms)), "timer_elapsed")
+                    times[i] += ms.value / iters
+                check(lib().b200sd_timer_elapsed_ms(0, n, C.byref(ms)), "timer_elapsed")
+                total += ms.value / iters
             acc, per_op = {}, []
-            for t, (g, kind, flops, name) in zip(times, graphs):
+            for t, (op, (kind, flops, name)) in zip(times, entries):
                 a = acc.setdefault(kind, [0.0, 0.0, 0])
                 a[0] += t
                 a[1] += flops
@@ -394,4 +397,4 @@ class Engine:
                 per_op.append((name or kind, t, flops))
             self._run_plan()
             torch.cuda.synchronize()
-        return acc, per_op
+        return acc, per_op, total

@@ -14,6 +14,14 @@ EPI_LINEAR, EPI_GEGLU = 0, 1
 _GN_RECOMPUTE = __import__("os").environ.get("B200SD_GN_FAST", "1") == "0"   # debug: GroupNorm backward recomputes its statistics
 
 
+def _up16(*ts):
+    """fp16 tensors (the reference builds every pipeline with torch_dtype=torch.float16: inference.py:406, 425; utils.py:189,
+    249) are upcast to fp32 at the Python boundary -- the kernels compute in fp32 either way -- and the caller casts the
+    result back.  Returns (tensors..., had_fp16)."""
+    had = any(t is not None and t.dtype == torch.float16 for t in ts)
+    return tuple(t.float() if (t is not None and t.dtype == torch.float16) else t for t in ts) + (had,)
+
+
 def _dt(t: torch.Tensor) -> int:
     if t.dtype == torch.float32:
         return F32
@@ -67,6 +75,13 @@ def launch_count() -> int:
 # scheduler / loss elementwise
 # ---------------------------------------------------------------------------------------------
 def cfg_ddim_step(eps_u, eps_c, x, guidance, sa_t, sb_t, sa_p, sb_p, out=None, eps_out=None):
+    eps_u, eps_c, x, half = _up16(eps_u, eps_c, x)
+    if half:
+        if eps_out is not None:
+            raise B200SDError("cfg_ddim_step: eps_out is not supported with float16 inputs")
+        r = cfg_ddim_step(eps_u.contiguous(), None if eps_c is None else eps_c.contiguous(), x.contiguous(), guidance, sa_t, sb_t,
+                          sa_p, sb_p).half()
+        return r if out is None else out.copy_(r)
     _chk(eps_u, eps_c, x, out, eps_out)
     if out is None:
         out = torch.empty_like(x)
@@ -81,6 +96,12 @@ def cfg_ddim_step(eps_u, eps_c, x, guidance, sa_t, sb_t, sa_p, sb_p, out=None, e
 
 
 def cfg_plms_step(eps_u, eps_c, x, hist, weights, guidance, cx, ce, out=None, eps_out=None):
+    eps_u, eps_c, x, half = _up16(eps_u, eps_c, x)
+    if half:
+        # the eps history (eps_out / hist) stays fp32: it never leaves the scheduler
+        r = cfg_plms_step(eps_u.contiguous(), None if eps_c is None else eps_c.contiguous(), x.contiguous(), hist, weights, guidance,
+                          cx, ce, eps_out=eps_out).half()
+        return r if out is None else out.copy_(r)
     _chk(eps_u, eps_c, x, out, eps_out, *hist)
     if out is None:
         out = torch.empty_like(x)
@@ -95,6 +116,10 @@ def cfg_plms_step(eps_u, eps_c, x, hist, weights, guidance, cx, ce, out=None, ep
 
 
 def add_noise(x0, noise, timesteps, sa_table, sb_table, out=None):
+    x0, noise, half = _up16(x0, noise)
+    if half:
+        r = add_noise(x0.contiguous(), noise.contiguous(), timesteps, sa_table, sb_table).half()
+        return r if out is None else out.copy_(r)
     _chk(x0, noise, timesteps, sa_table, sb_table, out)
     if x0.shape != noise.shape:
         raise ValueError("original_samples / noise shape mismatch")
@@ -133,13 +158,15 @@ def mse_loss_bwd(pred, target, grad_loss):
 class _MSELoss(torch.autograd.Function):
     @staticmethod
     def forward(ctx, pred, target):
+        ctx.pred_dtype = pred.dtype
+        pred, target, _ = _up16(pred, target)          # fp16 (autocast / fp16 pipelines): the loss is computed in fp32 as F.mse_loss under autocast
         ctx.save_for_backward(pred, target)
         return mse_loss_fwd(pred.contiguous(), target.contiguous()).reshape(())
 
     @staticmethod
     def backward(ctx, grad):
         pred, target = ctx.saved_tensors
-        return mse_loss_bwd(pred.contiguous(), target.contiguous(), grad.contiguous()), None
+        return mse_loss_bwd(pred.contiguous(), target.contiguous(), grad.contiguous().float()).to(ctx.pred_dtype), None
 
 
 def mse_loss(pred, target):
@@ -178,7 +205,10 @@ def gemm(a0, w, out, *, a1=None, bias=None, rowbias=None, residual=None, conv=No
          epilogue=EPI_LINEAR, block_n=0, split_k=0, M=None, ldrb=0, launch=True, pair=0):
     """out[M, N] = [a0 | a1] @ w^T (+bias +rowbias +residual); conv=(batch, H, W) -> 3x3 pad-1 conv (NHWC)."""
     _chk(a0, a1, w, bias, rowbias, residual, out)
-    N, K = w.shape
+    if w.dim() == 3:            # k-block-major weights [K/64][N][64] (packing.kblock_major)
+        N, K = w.shape[1], w.shape[0] * w.shape[2]
+    else:
+        N, K = w.shape
     C0 = a0.shape[-1]
     C1 = a1.shape[-1] if a1 is not None else 0
     if M is None:
@@ -203,6 +233,7 @@ def gemm(a0, w, out, *, a1=None, bias=None, rowbias=None, residual=None, conv=No
     args.residual_dtype = _dt(residual) if residual is not None else BF16
     args.block_n, args.split_k = block_n, split_k
     args.pair = pair
+    args.w_layout = 1 if w.dim() == 3 else 0
     args.workspace, args.workspace_bytes = _p(ws), ws.numel()
     if not launch:
         return args

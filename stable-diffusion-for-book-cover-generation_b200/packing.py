@@ -33,3 +33,12 @@ def pack_geglu(w: torch.Tensor, b: torch.Tensor, tile: int):
     wp = torch.cat([wv, wg], dim=1).reshape(n2, -1).contiguous().to(torch.bfloat16)
     bp = torch.cat([bv, bg], dim=1).reshape(n2).contiguous().float()
     return wp, bp
+
+
+def kblock_major(w: torch.Tensor) -> torch.Tensor:
+    """[N][K] -> [K/64][N][64] (B200SD_W_KBLOCK_MAJOR): the 64-wide k-blocks of all N rows stored together, so the weight
+    tile a GEMM CTA fetches per k-block (block_n rows x 128 B) is one contiguous run of DRAM instead of block_n pieces a whole
+    weight row apart.  ops.gemm recognises the layout by the 3-D shape."""
+    n, k = w.shape
+    assert k % 64 == 0
+    return w.reshape(n, k // 64, 64).permute(1, 0, 2).contiguous()

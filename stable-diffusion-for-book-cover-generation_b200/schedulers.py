@@ -180,7 +180,7 @@ class PNDMScheduler(_SchedulerBase):
         self.timesteps = torch.from_numpy(plms.astype(np.int64))
         self.ets, self.counter, self.cur_sample = [], 0, None
 
-    def _plms(self, eps_u, eps_c, timestep, sample, guidance):
+    def _plms(self, eps_u, eps_c, timestep, sample, guidance, out=None):
         self._check_step_args(eps_u, sample)
         t = int(timestep)
         ratio = self.num_train_timesteps // self.num_inference_steps
@@ -194,7 +194,7 @@ class PNDMScheduler(_SchedulerBase):
             n_after = len(self.ets)
         if n_after == 1 and self.counter == 0:
             w, hist, x = [1.0], [], sample
-            self.cur_sample = sample
+            self.cur_sample = sample.clone()    # the caller may recycle its latent buffers (step_cfg(out=...))
         elif n_after == 1 and self.counter == 1:
             w, hist, x = [0.5, 0.5], [self.ets[-1]], self.cur_sample
             self.cur_sample = None
@@ -209,7 +209,14 @@ class PNDMScheduler(_SchedulerBase):
         cx = (a_p / a_t) ** 0.5
         ce = (a_p - a_t) / (a_t * b_p ** 0.5 + (a_t * b_t * a_p) ** 0.5)
         eps_out = torch.empty_like(eps_u) if keep_eps else None
-        prev = ops.cfg_plms_step(eps_u, eps_c, x.contiguous(), hist, w, guidance, cx, ce, eps_out=eps_out)
+        if eps_u.dtype == torch.float16:      # fp16 pipelines: the eps history is kept in fp32
+            eps_u, eps_c = eps_u.float(), (None if eps_c is None else eps_c.float())
+            eps_out = torch.empty_like(eps_u) if keep_eps else None
+            prev = ops.cfg_plms_step(eps_u, eps_c, x.float().contiguous(), hist, w, guidance, cx, ce, eps_out=eps_out).to(x.dtype)
+            if out is not None:
+                prev = out.copy_(prev)
+        else:
+            prev = ops.cfg_plms_step(eps_u, eps_c, x.contiguous(), hist, w, guidance, cx, ce, out=out, eps_out=eps_out)
         if keep_eps:
             self.ets.append(eps_out)
         self.counter += 1
@@ -220,4 +227,4 @@ class PNDMScheduler(_SchedulerBase):
 
     def step_cfg(self, model_output_2b, timestep, sample, guidance_scale, out=None):
         B = sample.shape[0]
-        return self._plms(model_output_2b[:B], model_output_2b[B:], timestep, sample, guidance_scale)
+        return self._plms(model_output_2b[:B], model_output_2b[B:], timestep, sample, guidance_scale, out=out)

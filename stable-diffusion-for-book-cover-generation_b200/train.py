@@ -32,7 +32,7 @@ _ALIGN = 64  # elements: every region starts 128-byte aligned in the bf16 buffer
 
 class _Reg:
     """One parameter inside the flat buffers."""
-    __slots__ = ("param", "kind", "off", "numel", "shape2d", "g", "gview", "wb", "wf", "pview")
+    __slots__ = ("param", "kind", "off", "numel", "shape2d", "g", "gview", "wb", "wf", "pview", "rehomed", "src")
 
 
 class FlatParams:
@@ -53,9 +53,12 @@ class FlatParams:
 
         def add(p, kind):
             nonlocal off
-            if p.dtype != F32:
+            if p.dtype != F32 and p.requires_grad:
                 raise B200SDError("training needs fp32 master parameters (the kernels compute in bf16 on their own copy)")
             r = _Reg()
+            # a FROZEN fp16 / bf16 parameter (finetune_sd.py:393: unet.to(device, dtype=torch.float16) while the text encoder
+            # trains) keeps its own storage; the flat fp32 master holds an upcast copy for the kernels
+            r.rehomed = p.dtype == F32
             r.param, r.kind, r.numel = p, kind, p.numel()
             r.off = off
             off += (p.numel() + _ALIGN - 1) // _ALIGN * _ALIGN
@@ -153,7 +156,9 @@ class FlatParams:
         with torch.no_grad():
             for r in self.order:
                 r.pview.copy_(r.param.data)
-                r.param.data = r.pview
+                if r.rehomed:
+                    r.param.data = r.pview
+                r.src = (r.param.data.data_ptr(), r.param.dtype)
         self._versions = None
 
     def reg(self, p) -> _Reg:
@@ -172,6 +177,9 @@ class FlatParams:
         ver = sum(r.param._version for r in self.order)
         if not force and ver == self._versions:
             return False
+        for r in self.order:
+            if not r.rehomed:           # frozen fp16 / bf16 parameter: the master holds an upcast COPY
+                r.pview.copy_(r.param.data)
         ops.cast_flat(self.master, self.wb)
         self._versions = ver
         return True
@@ -188,7 +196,8 @@ class FlatParams:
     def owns(self, model) -> bool:
         """True while every parameter still lives in the flat master buffer (a .to() / load of new tensors breaks it)."""
         base = self.master.untyped_storage().data_ptr()
-        return all(r.param.data.untyped_storage().data_ptr() == base for r in self.order[:4] + self.order[-4:])
+        return all((r.param.data.untyped_storage().data_ptr() == base) if r.rehomed
+                   else (r.param.data.data_ptr(), r.param.dtype) == r.src for r in self.order[:4] + self.order[-4:])
 
 
 class _Pool:

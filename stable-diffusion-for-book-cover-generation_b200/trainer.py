@@ -61,18 +61,42 @@ class BucketReducer:
 class FlatAdamW:
     """torch.optim.AdamW semantics over train.FlatParams (one fused kernel per step)."""
 
-    def __init__(self, flat, lr=1e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2):
+    def __init__(self, flat, lr=1e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, state=None):
         self.flat, self.lr, self.betas, self.eps, self.weight_decay = flat, lr, betas, eps, weight_decay
-        self.exp_avg = torch.zeros_like(flat.master)
-        self.exp_avg_sq = torch.zeros_like(flat.master)
-        self.steps = 0
+        if state is not None and state.exp_avg.numel() == flat.master.numel():
+            # the flat buffers were rebuilt (unet.to() / _apply un-homes the parameters): same model, same layout ->
+            # the moments and the step count carry over instead of silently restarting from zero
+            self.exp_avg = state.exp_avg.to(flat.master.device)
+            self.exp_avg_sq = state.exp_avg_sq.to(flat.master.device)
+            self.steps = state.steps
+        else:
+            self.exp_avg = torch.zeros_like(flat.master)
+            self.exp_avg_sq = torch.zeros_like(flat.master)
+            self.steps = 0
+        # contiguous runs of TRAINABLE regions: frozen parameters (requires_grad=False) get neither an update nor
+        # decoupled weight decay, as with torch.optim.AdamW over `filter(requires_grad, parameters)`
+        self.spans = []
+        for r in flat.order:
+            if not r.param.requires_grad:
+                continue
+            a, b = r.off, r.off + (r.numel + 63) // 64 * 64
+            if self.spans and self.spans[-1][1] == a:
+                self.spans[-1][1] = b
+            else:
+                self.spans.append([a, b])
+        if self.spans:
+            self.spans[-1][1] = min(self.spans[-1][1], flat.master.numel())
 
     def step(self, grad_scale=1.0, zero_grad=True):
         self.steps += 1
         f = self.flat
-        ops.adamw_step(f.master, f.grad, self.exp_avg, self.exp_avg_sq, f.wb, self.lr, self.betas[0], self.betas[1], self.eps,
-                       self.weight_decay, self.steps, grad_scale=grad_scale, zero_grad=zero_grad)
-        # the kernel wrote the bf16 copy itself: the version bookkeeping of refresh_weights() stays valid
+        for a, b in self.spans:
+            ops.adamw_step(f.master[a:b], f.grad[a:b], self.exp_avg[a:b], self.exp_avg_sq[a:b], f.wb[a:b], self.lr, self.betas[0],
+                           self.betas[1], self.eps, self.weight_decay, self.steps, grad_scale=grad_scale, zero_grad=zero_grad)
+        # the kernel wrote the bf16 copy itself: the version bookkeeping of refresh_weights() stays valid.  The raw kernel
+        # bumps no tensor version, so tell the facade: its inference engines hold their own packed copy of the weights and
+        # must repack before the next eval-mode forward (finetune_sd.py:264-271 samples between training steps).
+        f.model.mark_weights_changed()
         return self
 
 
@@ -86,21 +110,26 @@ class Trainer:
         unet.enable_direct_gradients()
         self.reducer = None
         self.opt = None
+        self.micro_steps = 0
+        self.allreduce_enabled = True    # False: every rank steps on its local gradient (bench.py times the exposed communication)
 
     def _prepare(self, device):
         from .autograd import ensure_flat
         flat = ensure_flat(self.unet, device)
         if self.reducer is None or self.reducer.flat is not flat.grad:
             self.reducer = BucketReducer(flat.grad, self.group, self.bucket_bytes)
-            self.opt = FlatAdamW(flat, **self.opt_args)
+            self.opt = FlatAdamW(flat, state=self.opt, **self.opt_args)
             flat.zero_grad()
             flat.attach_grads()
+            self.micro_steps = 0
 
     def train_step(self, latents, noise, timesteps, encoder_hidden_states, sync=True):
-        """one micro-step; with sync=True (the default) also allreduce + optimizer step.  Returns the loss (0-d tensor)."""
+        """one micro-step; with sync=True (the default) also allreduce + optimizer step.  Returns the loss (0-d tensor).
+        Gradient accumulation follows accelerate (finetune_sd.py:454-458, 494): the k micro-steps since the last optimizer
+        step are AVERAGED (accelerator.backward divides the loss by gradient_accumulation_steps), and so are the ranks."""
         unet = self.unet
         self._prepare(latents.device)
-        reduce_now = sync and self.world > 1
+        reduce_now = sync and self.world > 1 and self.allreduce_enabled
         if reduce_now:
             self.reducer.begin()
         unet._grad_ready_hook = self.reducer.on_ready if reduce_now else None
@@ -109,8 +138,10 @@ class Trainer:
         loss = ops.mse_loss(pred, noise)
         loss.backward()
         unet._grad_ready_hook = None
+        self.micro_steps += 1
         if sync:
             if reduce_now:
                 self.reducer.finish()
-            self.opt.step(grad_scale=1.0 / self.world, zero_grad=True)
+            self.opt.step(grad_scale=1.0 / (self.world * self.micro_steps), zero_grad=True)
+            self.micro_steps = 0
         return loss.detach()

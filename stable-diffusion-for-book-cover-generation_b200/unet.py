@@ -284,7 +284,8 @@ class UNet2DConditionModel(nn.Module):
         super().zero_grad(set_to_none=set_to_none)
 
     def mark_weights_changed(self):
-        """Call after an optimizer step in eval-mode use; in train() mode it is checked automatically."""
+        """The inference engines hold their own packed bf16 copy of the weights: call this after changing parameters through
+        anything that bumps no tensor version (raw kernels; b200sd.trainer.FlatAdamW does it itself)."""
         self._dirty = True
 
     @property
@@ -304,7 +305,7 @@ class UNet2DConditionModel(nn.Module):
     def _pack_weights(self):
         """diffusers layouts -> kernel layouts (bf16 K-major GEMM operands, fp32 biases / norms)."""
         W = {}
-        f32 = lambda t: t.detach().float().contiguous()
+        f32 = lambda t: t.detach().float().clone()     # a COPY: FlatParams later re-homes the parameter storage
 
         def res(prefix, r):
             W[prefix] = dict(
@@ -360,6 +361,16 @@ class UNet2DConditionModel(nn.Module):
             if hasattr(b, "upsamplers"):
                 W[f"up{i}.us"] = dict(w=packing.pack_conv3x3(b.upsamplers[0].conv.weight.detach()),
                                       b=f32(b.upsamplers[0].conv.bias))
+        # weights are streamed from HBM once per step: store every tensor-core GEMM operand k-block-major so that a CTA's
+        # weight tile is one contiguous run of DRAM (B200SD_W_KMAJOR=0 keeps the row-major [N][K] layout for A/B runs)
+        if os.environ.get("B200SD_W_KMAJOR", "1") != "0":
+            gemm_keys = ("w1", "w2", "wsc", "w_in", "w_out", "w_qkv", "w_o1", "w_q2", "w_kv2", "w_o2", "w_ff1", "w_ff2")
+            for prefix, d in W.items():
+                if prefix in ("conv_in", "conv_out", "temb", "tproj"):
+                    continue
+                for k in list(d.keys()):
+                    if k in gemm_keys or (k == "w" and (prefix.endswith(".ds") or prefix.endswith(".us"))):
+                        d[k] = packing.kblock_major(d[k])
         self._packed = W
         self._dirty = False
         self._param_versions = self._versions()
@@ -408,7 +419,9 @@ class UNet2DConditionModel(nn.Module):
             out = unet_forward_train(self, sample, timestep, ctx)
             return UNet2DConditionOutput(sample=out) if return_dict else (out,)
 
-        if self._dirty or self._packed is None or (self.training and self._versions() != self._param_versions):
+        # version sum of the 686 parameters: catches in-place optimizer steps in eval mode too (the fused flat AdamW bumps no
+        # version and calls mark_weights_changed() instead)
+        if self._dirty or self._packed is None or self._versions() != self._param_versions:
             self._pack_weights()
             self._engines = {}
         key = (N, H, Wd, ctx.shape[1], sample.device.index, self._precision)

@@ -37,6 +37,26 @@ def test_gemm_plain(M, N, K):
     _close(out, want)
 
 
+@pytest.mark.parametrize("M,N,K,conv", [(128, 1280, 5120, None), (512, 1280, 1280, None), (8192, 320, 320, None),
+                                        (2048, 640, 9 * 640, (2, 32, 32)), (128, 1280, 9 * 1280, (2, 8, 8))])
+def test_gemm_kblock_major_weights(M, N, K, conv):
+    """B200SD_W_KBLOCK_MAJOR ([K/64][N][64], the DRAM-contiguous layout for streamed weights) == row-major, bit for bit."""
+    from b200sd import ops, packing
+    _setup()
+    torch.manual_seed(M + N + K)
+    C = K // 9 if conv else K
+    a = torch.randn(M, C, device=DEV).bfloat16()
+    w = (torch.randn(N, K, device=DEV) / K ** 0.5).bfloat16()
+    bias = torch.randn(N, device=DEV)
+    out0 = torch.empty(M, N, device=DEV, dtype=torch.float32)
+    out1 = torch.empty_like(out0)
+    ops.gemm(a, w, out0, bias=bias, conv=conv)
+    ops.gemm(a, packing.kblock_major(w), out1, bias=bias, conv=conv)
+    assert torch.equal(out0, out1)
+    if conv is None:
+        _close(out1, a.float() @ w.float().t() + bias, rel=1e-3)
+
+
 def test_gemm_f32_out_no_bias():
     from b200sd import ops
     _setup()
