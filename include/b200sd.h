@@ -44,6 +44,8 @@ int64_t b200sd_launch_count(void);
 /* In-graph timers (measurement plumbing): process-wide CUDA events.  b200sd_timer_record(i) records event i on
  * `stream`; while the stream is being captured the record becomes an external event-record node, so a replay of the captured
  * plan timestamps the gaps between its kernels and b200sd_timer_elapsed_ms(i, j) gives per-kernel times inside the real step. */
+/* debug: every CTA of the GEMM kernels stamps %globaltimer at 8 phase boundaries into buf[cta][8] (NULL switches it off) */
+void b200sd_debug_gemm_trace(void* buf);
 int b200sd_timer_reserve(int n);
 int b200sd_timer_record(int i, b200sd_stream_t stream);
 int b200sd_timer_elapsed_ms(int i, int j, float* ms);

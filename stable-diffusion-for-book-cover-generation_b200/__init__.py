@@ -1,7 +1,7 @@
 """b200sd -- B200-native (sm_100a) SD v1.x UNet denoise hot path behind the diffusers class surface.
 
 Public surface (mirrors what finetune_sd.py / inference.py / StableDiffusionPipeline touch):
-    UNet2DConditionModel, DDIMScheduler, PNDMScheduler, DDPMScheduler, denoise_loop, mse_loss
+    UNet2DConditionModel, DDIMScheduler, PNDMScheduler, DDPMScheduler, StableDiffusionPipeline, denoise_loop, mse_loss
 """
 __version__ = "0.1.0"
 
@@ -14,6 +14,7 @@ def __getattr__(name):  # lazy: importing the package must not require torch.cud
         "PNDMScheduler": "b200sd.schedulers",
         "DDPMScheduler": "b200sd.schedulers",
         "denoise_loop": "b200sd.pipeline",
+        "StableDiffusionPipeline": "b200sd.pipeline",
         "mse_loss": "b200sd.ops",
     }
     if name in table:

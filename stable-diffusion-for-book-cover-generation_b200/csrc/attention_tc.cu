@@ -1,6 +1,7 @@
-// b200sd -- flash attention on the sm_100a tensor cores (tcgen05 + TMEM), self-attention sized:
-// head dim 40 / 80, S_q a multiple of 128 and S_kv of 64 (the 64x64 and 32x32 levels of the UNet: 98 % of the
-// attention FLOPs).  Other shapes keep the register-resident kernel in attention.cu.
+// b200sd -- flash attention on the sm_100a tensor cores (tcgen05 + TMEM): every attention of the SD v1.x UNet -- head dim
+// 40 / 80 / 160, self-attention (S_kv = 4096 ... 64) and cross-attention against the 77-token text context (S_kv = 77: the
+// second 64-key tile is masked past key 12 before the softmax).  Other head dims keep the register-resident kernel in
+// attention.cu.
 //
 // One CTA = 128 query rows of one (batch, head); it streams 64-key tiles and its softmax warps never wait for the
 // tensor core:
@@ -24,6 +25,7 @@
 #include <atomic>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 
 #include "common.cuh"
 
@@ -87,7 +89,6 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)
 // log2 units a row may outgrow the lagging reference max before its tile is redone (P <= 2^6 is harmless in bf16/fp32)
 constexpr float kLazyThr = 6.0f;
 constexpr int kKV = 64;
-constexpr int kStages = 4;
 __device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const uint32_t* r) {
     asm volatile(
         "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
@@ -116,7 +117,8 @@ __device__ __forceinline__ float2 poly_exp2x2(float2 t) {
 }
 
 // POLY: every POLY-th score pair takes the polynomial instead of MUFU.EX2 (0 = none)
-template <int D, int DKB, int POLY>
+// kStages: depth of the K / V smem ring (4; 2 at d = 160, whose three 64-wide d blocks per tile would not fit otherwise)
+template <int D, int DKB, int POLY, int kStages>
 __global__ void __launch_bounds__(192, (D <= 40) ? 2 : 1) attention_tc_kernel(const __grid_constant__ AttnParams p) {
     constexpr int DN = (D + 15) / 16 * 16;    // MMA N of the PV product (48 / 80)
     constexpr int KSTEPS = (D + 15) / 16;     // UMMA K steps of the QK^T product
@@ -143,7 +145,7 @@ __global__ void __launch_bounds__(192, (D <= 40) ? 2 : 1) attention_tc_kernel(co
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q0 = blockIdx.x * kQ, h = blockIdx.y, b = blockIdx.z;
-    const int num_tiles = p.Skv / kKV;
+    const int num_tiles = (p.Skv + kKV - 1) / kKV;   // the last tile may be partial (cross-attention: 77 = 64 + 13 keys)
 
     ptx::pdl_trigger();
     if (warp == 0 && lane == 0) {
@@ -250,6 +252,14 @@ __global__ void __launch_bounds__(192, (D <= 40) ? 2 : 1) attention_tc_kernel(co
             tmem_ld_32x32b_x32(tS, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
             tmem_ld_32x32b_x32(tS + 32, *reinterpret_cast<uint32_t(*)[32]>(&r[32]));
             ptx::tmem_ld_wait();
+            if ((j + 1) * kKV > p.Skv) {
+                // partial last tile: the key rows past S_kv are the next image's keys (or TMA zero fill) -- their scores are
+                // set to -inf before the max and the exponentials, so P is exactly 0 there (warp-uniform branch)
+                const int valid = p.Skv - j * kKV;
+#pragma unroll
+                for (int i = 0; i < kKV; ++i)
+                    if (i >= valid) r[i] = 0xff800000u;
+            }
             // P = exp2(S * scale - off) as packed bf16 pairs; returns the fp32 row sum
             auto exps = [&](float off, bool track, float& mx) -> float {
                 const float2 noff2 = make_float2(-off, -off);
@@ -284,14 +294,21 @@ __global__ void __launch_bounds__(192, (D <= 40) ? 2 : 1) attention_tc_kernel(co
                 if (j > 0) {   // rescale the O rows accumulated so far (PV_{j-1} must have landed; PV_j waits for p_full)
                     ptx::mbar_wait(&o_full[(j - 1) & 1], ((j - 1) >> 1) & 1);
                     ptx::tc_fence_after();
-                    uint32_t ob[DN];
+                    // 48 columns at a time: the scores of this tile stay live in registers (r[64]) across the rescale
 #pragma unroll
-                    for (int c = 0; c < DN; c += 16) ptx::tmem_ld_32x32b_x16(tO + c, *reinterpret_cast<uint32_t(*)[16]>(&ob[c]));
-                    ptx::tmem_ld_wait();
+                    for (int c0 = 0; c0 < DN; c0 += 48) {
+                        constexpr int kPiece = 48;
+                        uint32_t ob[kPiece];
 #pragma unroll
-                    for (int i = 0; i < DN; ++i) ob[i] = __float_as_uint(__uint_as_float(ob[i]) * corr);
+                        for (int c = 0; c < kPiece; c += 16)
+                            if (c0 + c < DN) ptx::tmem_ld_32x32b_x16(tO + c0 + c, *reinterpret_cast<uint32_t(*)[16]>(&ob[c]));
+                        ptx::tmem_ld_wait();
 #pragma unroll
-                    for (int c = 0; c < DN; c += 16) tmem_st_32x32b_x16(tO + c, &ob[c]);
+                        for (int i = 0; i < kPiece; ++i) ob[i] = __float_as_uint(__uint_as_float(ob[i]) * corr);
+#pragma unroll
+                        for (int c = 0; c < kPiece; c += 16)
+                            if (c0 + c < DN) tmem_st_32x32b_x16(tO + c0 + c, &ob[c]);
+                    }
                 }
             }
             l += rs;
@@ -307,21 +324,26 @@ __global__ void __launch_bounds__(192, (D <= 40) ? 2 : 1) attention_tc_kernel(co
         // ---- normalise and store ----
         ptx::mbar_wait(&o_full[(num_tiles - 1) & 1], ((num_tiles - 1) >> 1) & 1);
         ptx::tc_fence_after();
-        uint32_t ob[DN];
-#pragma unroll
-        for (int c = 0; c < DN; c += 16) ptx::tmem_ld_32x32b_x16(tO + c, *reinterpret_cast<uint32_t(*)[16]>(&ob[c]));
-        ptx::tmem_ld_wait();
         const float inv = 1.0f / l;
-        if (p.lse != nullptr) p.lse[((size_t)b * p.heads + h) * p.Sq + q0 + row] = m * p.scale_log2 + log2f(l);
+        const bool live = q0 + row < p.Sq;   // S_q tail: rows past the image's last query were computed on foreign rows -- not stored
+        if (p.lse != nullptr && live) p.lse[((size_t)b * p.heads + h) * p.Sq + q0 + row] = m * p.scale_log2 + log2f(l);
         bf16* dst = p.out + ((size_t)b * p.Sq + q0 + row) * p.ldo + h * D;
 #pragma unroll
-        for (int c = 0; c < D; c += 8) {
-            uint4 u;
-            u.x = pack_bf16x2(__uint_as_float(ob[c]) * inv, __uint_as_float(ob[c + 1]) * inv);
-            u.y = pack_bf16x2(__uint_as_float(ob[c + 2]) * inv, __uint_as_float(ob[c + 3]) * inv);
-            u.z = pack_bf16x2(__uint_as_float(ob[c + 4]) * inv, __uint_as_float(ob[c + 5]) * inv);
-            u.w = pack_bf16x2(__uint_as_float(ob[c + 6]) * inv, __uint_as_float(ob[c + 7]) * inv);
-            *reinterpret_cast<uint4*>(dst + c) = u;
+        for (int c0 = 0; c0 < DN; c0 += 16) {
+            uint32_t ob[16];
+            ptx::tmem_ld_32x32b_x16(tO + c0, ob);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int c = 0; c < 16; c += 8) {
+                if (c0 + c < D && live) {
+                    uint4 u;
+                    u.x = pack_bf16x2(__uint_as_float(ob[c]) * inv, __uint_as_float(ob[c + 1]) * inv);
+                    u.y = pack_bf16x2(__uint_as_float(ob[c + 2]) * inv, __uint_as_float(ob[c + 3]) * inv);
+                    u.z = pack_bf16x2(__uint_as_float(ob[c + 4]) * inv, __uint_as_float(ob[c + 5]) * inv);
+                    u.w = pack_bf16x2(__uint_as_float(ob[c + 6]) * inv, __uint_as_float(ob[c + 7]) * inv);
+                    *reinterpret_cast<uint4*>(dst + c0 + c) = u;
+                }
+            }
         }
     }
 
@@ -333,7 +355,7 @@ __global__ void __launch_bounds__(192, (D <= 40) ? 2 : 1) attention_tc_kernel(co
     }
 }
 
-template <int D, int DKB, int POLY>
+template <int D, int DKB, int POLY, int kStages>
 int launch_tc(const bf16* q, const bf16* k, const bf16* v, bf16* out, float* lse, int batch, int heads, int Sq, int Skv, int ldq,
                int ldk, int ldv, int ldo, float scale, cudaStream_t s) {
     AttnParams p;
@@ -369,13 +391,20 @@ int launch_tc(const bf16* q, const bf16* k, const bf16* v, bf16* out, float* lse
     static const float thr = [] { const char* e = getenv("B200SD_ATTN_THR"); return e ? (float)atof(e) : kLazyThr; }();
     p.lazy_thr = thr;
     const size_t smem = (size_t)DKB * kBlk + (size_t)2 * kStages * DKB * kKV * 128 + 256 + 1024;
-    static bool configured = false;
-    if (!configured) {
-        B200SD_CUDA(cudaFuncSetAttribute(attention_tc_kernel<D, DKB, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        B200SD_CUDA(cudaFuncSetAttribute(attention_tc_kernel<D, DKB, POLY>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        configured = true;
+    {
+        // per-device opt-in to the large dynamic smem (one static per template instantiation), under a mutex
+        static std::mutex mu;
+        static bool configured[64] = {};
+        int dev = 0;
+        B200SD_CUDA(cudaGetDevice(&dev));
+        std::lock_guard<std::mutex> lock(mu);
+        if (dev >= 0 && dev < 64 && !configured[dev]) {
+            B200SD_CUDA(cudaFuncSetAttribute(attention_tc_kernel<D, DKB, POLY, kStages>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            B200SD_CUDA(cudaFuncSetAttribute(attention_tc_kernel<D, DKB, POLY, kStages>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+            configured[dev] = true;
+        }
     }
-    B200SD_CUDA(b200sd_launch(attention_tc_kernel<D, DKB, POLY>, dim3(Sq / kQ, heads, batch), dim3(192), smem, s, p));
+    B200SD_CUDA(b200sd_launch(attention_tc_kernel<D, DKB, POLY, kStages>, dim3((Sq + kQ - 1) / kQ, heads, batch), dim3(192), smem, s, p));
     g_b200sd_launches.fetch_add(1, std::memory_order_relaxed);
     B200SD_LAUNCH_CHECK();
     return B200SD_OK;
@@ -387,20 +416,23 @@ int launch_tc(const bf16* q, const bf16* k, const bf16* v, bf16* out, float* lse
 int b200sd_attention_tc(const void* q, const void* k, const void* v, void* out, float* lse, int batch, int heads, int Sq, int Skv,
                         int d, int ldq, int ldk, int ldv, int ldo, float scale, void* workspace, size_t ws_bytes,
                         cudaStream_t s) {
-    if (!(d == 40 || d == 80) || Sq % kQ != 0 || Skv % kKV != 0) return B200SD_ERR_UNSUPPORTED;
+    if (!(d == 40 || d == 80 || d == 160) || Sq < 1 || Skv < 1) return B200SD_ERR_UNSUPPORTED;
     (void)workspace;   // no scratch any more: V is consumed in place (MN-major B operand), the V^T transpose kernel is gone
     (void)ws_bytes;
     if ((ldq * 2) % 16 != 0 || (ldk * 2) % 16 != 0 || (ldv * 2) % 16 != 0) return B200SD_ERR_UNSUPPORTED;
     // B200SD_ATTN_POLY=0 keeps every exponential on MUFU.EX2 (A/B switch; default: every 4th pair on the FMA pipe)
     static const int poly = [] { const char* e = getenv("B200SD_ATTN_POLY"); return e ? atoi(e) : 4; }();
-#define B200SD_ATTN_GO(DD, KB, PL)                                                                                           \
-    return launch_tc<DD, KB, PL>(static_cast<const bf16*>(q), static_cast<const bf16*>(k), static_cast<const bf16*>(v),      \
-                                  static_cast<bf16*>(out), lse, batch, heads, Sq, Skv, ldq, ldk, ldv, ldo, scale, s)
+#define B200SD_ATTN_GO(DD, KB, PL, ST)                                                                                        \
+    return launch_tc<DD, KB, PL, ST>(static_cast<const bf16*>(q), static_cast<const bf16*>(k), static_cast<const bf16*>(v),   \
+                                      static_cast<bf16*>(out), lse, batch, heads, Sq, Skv, ldq, ldk, ldv, ldo, scale, s)
     if (d == 40) {
-        if (poly == 0) B200SD_ATTN_GO(40, 1, 0);
-        B200SD_ATTN_GO(40, 1, 4);
+        if (poly == 0) B200SD_ATTN_GO(40, 1, 0, 4);
+        B200SD_ATTN_GO(40, 1, 4, 4);
     }
-    if (poly == 0) B200SD_ATTN_GO(80, 2, 0);
-    B200SD_ATTN_GO(80, 2, 4);
+    if (d == 80) {
+        if (poly == 0) B200SD_ATTN_GO(80, 2, 0, 4);
+        B200SD_ATTN_GO(80, 2, 4, 4);
+    }
+    B200SD_ATTN_GO(160, 3, 4, 2);
 #undef B200SD_ATTN_GO
 }

@@ -162,6 +162,20 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* m, uin
         : "memory");
 }
 
+// ---- TMA store: smem tile -> global through a tensor map (bulk async-group completion) ----
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(m)),
+                 "r"(smem_u32(src)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// wait until at most N of this thread's committed bulk groups are still READING their smem source
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+// wait until at most N committed bulk groups are still in flight at all (writes performed)
+template <int N>
+__device__ __forceinline__ void tma_store_wait() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
+
 // ---- CTA-pair (cta_group::2) variants: both CTAs of a pair issue their own loads into their own smem, the
 // transaction bytes are signalled on the LEADER's mbarrier (a shared::cluster address obtained with mapa) ----
 __device__ __forceinline__ uint32_t mapa_u32(uint32_t local_smem_addr, uint32_t cta_rank) {
@@ -354,6 +368,21 @@ __device__ __forceinline__ void st8(void* p, size_t i, const float (&v)[8]) {
 }
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
 __device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+
+// erf GELU on 2 MUFU + ~12 FMA-pipe instructions: Phi(x) = 1/2 erfc(-x / sqrt 2) with erfc(z) = poly(t) exp(-z^2), t = 1 / (1 + p z)
+// (Abramowitz-Stegun 7.1.26, |error| <= 1.5e-7 on erfc).  Computing through erfc keeps the left tail free of cancellation;
+// the absolute error on gelu(x) stays below 3e-7 |x|, far under the bf16 rounding of the result it feeds.
+__device__ __forceinline__ float gelu_erf_fast(float x) {
+    const float z = fabsf(x) * 0.70710678118654752f;
+    const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+    float poly = fmaf(1.061405429f, t, -1.453152027f);
+    poly = fmaf(poly, t, 1.421413741f);
+    poly = fmaf(poly, t, -0.284496736f);
+    poly = fmaf(poly, t, 0.254829592f);
+    const float e = poly * t * exp2f(-1.4426950408889634f * z * z);   // erfc(z)
+    const float phi = x < 0.f ? 0.5f * e : fmaf(-0.5f, e, 1.0f);
+    return x * phi;
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -16,6 +16,7 @@
 // distributed shared memory, and each reduces + stores 128/split rows in a fixed order (deterministic).
 #include <atomic>
 #include <cstring>
+#include <mutex>
 #include <cstdio>
 #include <cstdlib>
 
@@ -81,6 +82,7 @@ struct KParams {
     int atomic_out;      // fp32 red.add into `out` (wgrad: split-K partials and gradient accumulation)
     int pair;            // CTA pair (cta_group::2): two CTAs adjacent in M form one 256 x block_n MMA tile; each loads its own
                          // 128 A rows and HALF of the B tile, so the L2 -> smem traffic per FLOP drops by ~1/3
+    int persist;         // host only: this launch goes to gemm_persist_kernel (set by gemm_tiling)
     int w_kmajor;        // forward B operand stored k-block-major [K/64][N][64]: one tile k-block = ONE contiguous bn x 128 B run of
                          // DRAM instead of bn 128-byte pieces a whole weight row (K * 2 B) apart
     float* gn_part;      // optional [m_tiles * split_k][2][N]: per-column (sum, sum of squares) of the rows each CTA stores --
@@ -496,6 +498,393 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tcgen05_kernel(const __gr
     if (threadIdx.x == 0) TRACE(7);
 }
 
+// =================================================================================================================
+// Persistent forward kernel: one CTA per SM walks the output tiles of the layer (tile = blockIdx.x + i * gridDim.x).
+//   warp 0     : TMA producer -- runs ahead across tile boundaries, the smem ring never drains between tiles
+//   warp 1     : TMEM allocator + tcgen05.mma issuer; TWO accumulator stages in TMEM, so the MMAs of tile i+1 are issued
+//                while the epilogue warps still drain tile i
+//   warps 2..9 : epilogue, TWO warps per 32-lane quarter of the accumulator (a warp may only touch the TMEM lanes of its
+//                quarter = 32 output rows); the pair splits the tile's 32-column chunks odd / even.  Per chunk: tcgen05.ld -> registers -> (+bias, +time embedding, +residual | GEGLU) -> swizzled
+//                4 KB smem chunk -> TMA store (cp.async.bulk.tensor, bulk groups).  The residual chunk arrives by TMA in
+//                the SAME smem chunk, issued `depth - 1` chunks ahead (for a one-tile CTA: during the main loop), so no
+//                epilogue thread ever waits on a global load -- the old store phase was bound by exactly that latency
+//                (7 of the 10.7 us of an M8192 N320 K320 projection).
+// GroupNorm column statistics (gn_part) are summed from the finished fp32 chunk in smem, one partial row per (tile, warp).
+// Covers forward GEMM / conv3x3 tiles of 128 rows without split-K and without CTA pairs; everything else stays on
+// gemm_tcgen05_kernel above.
+// =================================================================================================================
+constexpr int kEpiWarps = 8;
+constexpr int kPersistThreads = 64 + 32 * kEpiWarps;
+constexpr int kMaxDepth = 3;
+
+struct PParams {
+    CUtensorMap tmA0, tmA1, tmB, tmOut, tmRes;
+    const float* bias;
+    const float* rowbias;
+    float* gn_part;
+    int M, N;
+    int num_k_blocks, block_n, stages;
+    int conv, cblocks0, cblocks, tile_h, tile_n, tiles_y, w_kmajor;
+    int n_tiles, num_tiles;
+    int ldrb, rows_per_image;
+    int geglu, out_f32, res_kind;   // res_kind: 0 none, 1 bf16, 2 fp32
+    int depth;                      // smem chunks per epilogue warp (3 with a residual, 2 without)
+    int chunk_bytes;                // 4096: 32 rows x 128 B (an fp32 chunk is involved); 2048: 32 rows x 64 B (bf16 only)
+    uint32_t tmem_cols, acc_stride;
+    uint32_t off_b, off_epi, off_bias, off_stat, off_bars;   // byte offsets from the 1024-aligned smem base
+    unsigned long long* trace;      // optional [ctas][8] globaltimer stamps (debug)
+};
+#define PTRACE(slot) do { if (p.trace) p.trace[(size_t)blockIdx.x * 8 + (slot)] = gtimer(); } while (0)
+
+
+// one 32-column chunk of this warp's 32 accumulator rows; cb = the warp's smem chunk (holds the residual when RES != 0)
+template <bool OUT_F32, int RES, bool GEGLU, bool STATS>
+__device__ __forceinline__ void persist_chunk(const PParams& p, uint32_t taddr, int ch, const float* sbv, const float* sbg, uint8_t* cb,
+                                              int lane, bool last_chunk, uint64_t* tempty_bar, uint64_t* rfull_bar, uint32_t rparity,
+                                              float* gn_dst, int nrows) {
+    uint32_t r0[16], r1[16], g0[16], g1[16];
+    ptx::tmem_ld_32x32b_x16(taddr + ch * 32, r0);
+    ptx::tmem_ld_32x32b_x16(taddr + ch * 32 + 16, r1);
+    const int half = p.block_n >> 1;
+    if constexpr (GEGLU) {
+        ptx::tmem_ld_32x32b_x16(taddr + half + ch * 32, g0);
+        ptx::tmem_ld_32x32b_x16(taddr + half + ch * 32 + 16, g1);
+    }
+    if constexpr (RES != 0) ptx::mbar_wait(rfull_bar, rparity);
+    ptx::tmem_ld_wait();
+    if (last_chunk) {   // the accumulator stage is free as soon as its last column left TMEM
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(tempty_bar);
+    }
+    float v[32];
+    const float4* sb4 = reinterpret_cast<const float4*>(sbv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float4 b = sb4[j];   // same address in every lane: broadcast
+        const uint32_t* r = j < 4 ? r0 : r1;
+        const int o = (j & 3) * 4;
+        v[4 * j + 0] = __uint_as_float(r[o + 0]) + b.x;
+        v[4 * j + 1] = __uint_as_float(r[o + 1]) + b.y;
+        v[4 * j + 2] = __uint_as_float(r[o + 2]) + b.z;
+        v[4 * j + 3] = __uint_as_float(r[o + 3]) + b.w;
+    }
+    if constexpr (GEGLU) {
+        const float4* sg4 = reinterpret_cast<const float4*>(sbg);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float4 b = sg4[j];
+            const uint32_t* r = j < 4 ? g0 : g1;
+            const int o = (j & 3) * 4;
+            v[4 * j + 0] *= gelu_erf_fast(__uint_as_float(r[o + 0]) + b.x);
+            v[4 * j + 1] *= gelu_erf_fast(__uint_as_float(r[o + 1]) + b.y);
+            v[4 * j + 2] *= gelu_erf_fast(__uint_as_float(r[o + 2]) + b.z);
+            v[4 * j + 3] *= gelu_erf_fast(__uint_as_float(r[o + 3]) + b.w);
+        }
+    }
+    // smem chunk layouts = what TMA produces / consumes: fp32 rows of 128 B with the 128-byte swizzle (16-byte piece j of row r
+    // at j ^ (r & 7)), bf16 rows of 64 B with the 64-byte swizzle (piece j at j ^ ((r >> 1) & 3))
+    uint8_t* row128 = cb + lane * 128;
+    uint8_t* row64 = cb + lane * 64;
+    const int x128 = lane & 7, x64 = (lane >> 1) & 3;
+    if constexpr (RES == 2) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float4 t = *reinterpret_cast<const float4*>(row128 + ((j ^ x128) << 4));
+            v[4 * j + 0] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
+        }
+    } else if constexpr (RES == 1) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint4 u = *reinterpret_cast<const uint4*>(row64 + ((j ^ x64) << 4));
+            float2 f;
+            f = unpack_bf16x2(u.x); v[8 * j + 0] += f.x; v[8 * j + 1] += f.y;
+            f = unpack_bf16x2(u.y); v[8 * j + 2] += f.x; v[8 * j + 3] += f.y;
+            f = unpack_bf16x2(u.z); v[8 * j + 4] += f.x; v[8 * j + 5] += f.y;
+            f = unpack_bf16x2(u.w); v[8 * j + 6] += f.x; v[8 * j + 7] += f.y;
+        }
+    }
+    // residual and output rows of different widths overlap across threads: everyone reads before anyone writes
+    if constexpr (RES != 0 && ((RES == 2) != OUT_F32)) __syncwarp();
+    if constexpr (OUT_F32) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<float4*>(row128 + ((j ^ x128) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            uint4 u;
+            u.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
+            u.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+            u.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+            u.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+            *reinterpret_cast<uint4*>(row64 + ((j ^ x64) << 4)) = u;
+        }
+    }
+    if constexpr (STATS) {
+        // column sums of the finished fp32 chunk: lane c walks column c down the warp's rows (conflict-free: the swizzle
+        // permutes 16-byte pieces inside a row, a warp still reads one whole 128-byte row per step)
+        __syncwarp();
+        float s = 0.f, ss = 0.f;
+        const uint8_t* colp = cb + ((lane & 3) << 2);
+        const int piece = lane >> 2;
+        for (int r = 0; r < nrows; ++r) {
+            const float x = *reinterpret_cast<const float*>(colp + r * 128 + ((piece ^ (r & 7)) << 4));
+            s += x;
+            ss = fmaf(x, x, ss);
+        }
+        gn_dst[ch * 32 + lane] = s;          // this quarter's slot of the tile's statistics scratch: [sum 256 | sum of squares 256]
+        gn_dst[256 + ch * 32 + lane] = ss;
+    }
+}
+
+template <bool OUT_F32, int RES, bool GEGLU, bool STATS>
+__device__ __forceinline__ void persist_epilogue(const PParams& p, uint8_t* smem, uint32_t tmem_base, int warp, int lane) {
+    const int ew = warp - 2;  // 0..7
+    const int q = warp & 3;   // TMEM lane quarter this warp may access = rows [32q, 32q + 32) of the tile
+    const int h = ew >> 2;    // which chunks of the quarter: ch = h, h + 2, ...  (warps 2..5 -> h 0, warps 6..9 -> h 1; quarters distinct in each group)
+    const int D = p.depth;
+    const int kChunkBytes = p.chunk_bytes;
+    uint8_t* my = smem + p.off_epi + (size_t)ew * D * kChunkBytes;
+    float* sb = reinterpret_cast<float*>(smem + p.off_bias) + ew * 256;   // [128 value biases | 128 gate biases] of this warp's chunks
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.off_bars);
+    uint64_t* tfull = bars + 16;
+    uint64_t* tempty = bars + 18;
+    uint64_t* rfull = bars + 20 + ew * kMaxDepth;
+    const int half = p.block_n >> 1;
+    const int nch = (GEGLU ? half : p.block_n) >> 5;
+    const int nl = nch > h ? (nch - h + 1) >> 1 : 0;   // chunks of a tile this warp moves
+    const int my_tiles = ((int)blockIdx.x < p.num_tiles) ? (p.num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    const int total = my_tiles * nl;
+    const int out_n = GEGLU ? half : p.block_n;   // output columns per tile
+
+    auto issue_res = [&](int g) {   // lane 0: this warp's g-th residual chunk -> smem chunk g % D
+        const int itl = g / nl, ch = h + 2 * (g - itl * nl);
+        const int tile = (int)blockIdx.x + itl * (int)gridDim.x;
+        const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
+        const int buf = g % D;
+        ptx::mbar_expect_tx(&rfull[buf], RES == 2 ? 4096u : 2048u);
+        ptx::tma_load_2d(my + buf * kChunkBytes, &p.tmRes, &rfull[buf], n_tile * p.block_n + ch * 32, m_tile * BLOCK_M + q * 32);
+    };
+    if constexpr (RES != 0) {
+        if (lane == 0)
+            for (int g = 0; g < D && g < total; ++g) issue_res(g);
+    }
+
+    int g = 0;
+    for (int it = 0; it < my_tiles; ++it) {
+        const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+        const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
+        const int n0 = n_tile * p.block_n;
+        const int row0 = m_tile * BLOCK_M + q * 32;
+        // the biases of this warp's chunks (+ the time-embedding row of this warp's image) -> the warp's smem copy
+        __syncwarp();
+        {
+            const int img = p.rowbias ? min(row0, p.M - 1) / p.rows_per_image : 0;
+            for (int l = 0; l < nl; ++l) {
+                const int c = (h + 2 * l) * 32 + lane;
+                float b = p.bias ? __ldg(p.bias + n0 + c) : 0.f;
+                if (p.rowbias) b += __ldg(p.rowbias + (size_t)img * p.ldrb + n0 + c);
+                sb[l * 32 + lane] = b;
+                if constexpr (GEGLU) sb[128 + l * 32 + lane] = p.bias ? __ldg(p.bias + n0 + half + c) : 0.f;
+            }
+        }
+        __syncwarp();
+        const int acc = it & 1;
+        ptx::mbar_wait(&tfull[acc], (uint32_t)(it >> 1) & 1u);
+        ptx::tc_fence_after();
+        if (it == 0 && ew == 0 && lane == 0) PTRACE(4);
+        const uint32_t taddr = tmem_base + (uint32_t)acc * p.acc_stride + ((uint32_t)(q * 32) << 16);
+        const int nrows = max(0, min(32, p.M - row0));
+        float* sstat = reinterpret_cast<float*>(smem + p.off_stat);   // [4 quarters][2][256]
+        float* gn_dst = STATS ? sstat + q * 512 : nullptr;
+        if (nl == 0) {   // nothing to move for this warp (a one-chunk tile): it still takes part in the stage hand-back
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&tempty[acc]);
+        }
+        for (int l = 0; l < nl; ++l, ++g) {
+            const int ch = h + 2 * l;
+            const int buf = g % D;
+            uint8_t* cb = my + buf * kChunkBytes;
+            if constexpr (RES == 0) {
+                // the store that last read this chunk (D = 2 chunks ago) must be done with it
+                if (lane == 0) ptx::tma_store_wait_read<1>();
+                __syncwarp();
+            }
+            persist_chunk<OUT_F32, RES, GEGLU, STATS>(p, taddr, ch, sb + l * 32, sb + 128 + l * 32, cb, lane, l == nl - 1, &tempty[acc],
+                                                     &rfull[buf], (uint32_t)(g / D) & 1u, gn_dst, nrows);
+            ptx::fence_proxy_async();   // generic-proxy smem writes -> visible to the TMA (async proxy)
+            __syncwarp();
+            if (lane == 0) {
+                ptx::tma_store_2d(&p.tmOut, cb, n_tile * out_n + ch * 32, row0);
+                ptx::tma_store_commit();
+                if constexpr (RES != 0) {
+                    // chunk g - 1 has been read by its store by now (at most this one still pending): refill it D - 1 ahead
+                    if (g >= 1 && g - 1 + D < total) {
+                        ptx::tma_store_wait_read<1>();
+                        issue_res(g - 1 + D);
+                    }
+                }
+            }
+        }
+        if constexpr (STATS) {
+            // GroupNorm statistics of the tile: the four quarters' column sums folded in a fixed order (bit-reproducible) into
+            // ONE partial row per tile, [m_tile][sum | sum of squares][N] -- what b200sd_groupnorm_silu_parts folds per image
+            ptx::named_bar_sync(1, kEpiWarps * 32);
+            const int te = ew * 32 + lane;
+            if (te < p.block_n) {
+                float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+                for (int qq = 0; qq < 4; ++qq) { s0 += sstat[qq * 512 + te]; s1 += sstat[qq * 512 + 256 + te]; }
+                float* dst = p.gn_part + (size_t)m_tile * 2 * p.N + n0 + te;
+                dst[0] = s0;
+                dst[p.N] = s1;
+            }
+            ptx::named_bar_sync(1, kEpiWarps * 32);   // the scratch is rewritten by the next tile
+        }
+    }
+    if (ew == 0 && lane == 0) PTRACE(5);
+    if (lane == 0) ptx::tma_store_wait<0>();   // all output writes performed before the CTA may exit
+    __syncwarp();
+    if (ew == 0 && lane == 0) PTRACE(6);
+}
+
+__global__ void __launch_bounds__(kPersistThreads, 1) gemm_persist_kernel(const __grid_constant__ PParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + p.off_b;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.off_bars);
+    uint64_t* full_bar = bars;            // [8]
+    uint64_t* empty_bar = bars + 8;       // [8]
+    uint64_t* tfull = bars + 16;          // [2]  accumulator stage ready for the epilogue
+    uint64_t* tempty = bars + 18;         // [2]  accumulator stage drained (one arrival per epilogue warp)
+    uint64_t* rfull = bars + 20;          // [8 warps][3]  residual chunk landed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20 + kEpiWarps * kMaxDepth);
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int b_bytes = p.block_n * BLOCK_K * 2;
+
+    ptx::pdl_trigger();
+    if (threadIdx.x == 0) PTRACE(0);
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tmap(&p.tmA0);
+        ptx::prefetch_tmap(&p.tmB);
+        ptx::prefetch_tmap(&p.tmOut);
+        if (p.cblocks0 != p.cblocks) ptx::prefetch_tmap(&p.tmA1);
+        if (p.res_kind) ptx::prefetch_tmap(&p.tmRes);
+        for (int s = 0; s < p.stages; ++s) {
+            ptx::mbar_init(&full_bar[s], 1);
+            ptx::mbar_init(&empty_bar[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            ptx::mbar_init(&tfull[s], 1);
+            ptx::mbar_init(&tempty[s], kEpiWarps);
+        }
+        for (int s = 0; s < kEpiWarps * kMaxDepth; ++s) ptx::mbar_init(&rfull[s], 1);
+        ptx::fence_barrier_init();
+    }
+    if (warp == 1) {
+        ptx::tmem_alloc(tmem_slot, p.tmem_cols);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    ptx::pdl_wait();   // everything above overlapped the previous kernel's tail
+    if (threadIdx.x == 0) PTRACE(1);
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (ptx::elect_one()) {
+            int stage = 0;
+            uint32_t phase = 0;
+            const uint32_t stage_tx = (uint32_t)(kABytes + b_bytes);
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
+                const int m0 = m_tile * BLOCK_M, n0 = n_tile * p.block_n;
+                int img = 0, y0 = 0;
+                if (p.conv) {
+                    if (p.tile_n > 1) { img = m_tile * p.tile_n; y0 = 0; }
+                    else { img = m_tile / p.tiles_y; y0 = (m_tile - img * p.tiles_y) * p.tile_h; }
+                }
+                for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+                    ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint64_t* fb = &full_bar[stage];
+                    ptx::mbar_expect_tx(fb, stage_tx);
+                    uint8_t* dst_a = smem_a + (size_t)stage * kABytes;
+                    uint8_t* dst_b = smem_b + (size_t)stage * b_bytes;
+                    if (!p.conv) {
+                        if (kb < p.cblocks0) ptx::tma_load_2d(dst_a, &p.tmA0, fb, kb * BLOCK_K, m0);
+                        else ptx::tma_load_2d(dst_a, &p.tmA1, fb, (kb - p.cblocks0) * BLOCK_K, m0);
+                    } else {
+                        const int tap = kb / p.cblocks;
+                        const int cb = kb - tap * p.cblocks;
+                        const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+                        if (cb < p.cblocks0) ptx::tma_load_4d(dst_a, &p.tmA0, fb, cb * BLOCK_K, dx, y0 + dy, img);
+                        else ptx::tma_load_4d(dst_a, &p.tmA1, fb, (cb - p.cblocks0) * BLOCK_K, dx, y0 + dy, img);
+                    }
+                    if (p.w_kmajor) ptx::tma_load_3d(dst_b, &p.tmB, fb, 0, n0, kb);
+                    else ptx::tma_load_2d(dst_b, &p.tmB, fb, kb * BLOCK_K, n0);
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer (one elected thread) =================
+        if (ptx::elect_one()) {
+            const uint32_t idesc = ptx::umma_idesc_bf16(BLOCK_M, (uint32_t)p.block_n);
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+                const int acc = it & 1;
+                ptx::mbar_wait(&tempty[acc], ((uint32_t)(it >> 1) & 1u) ^ 1u);   // the epilogue has drained this stage
+                ptx::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)acc * p.acc_stride;
+                for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+                    ptx::mbar_wait(&full_bar[stage], phase);
+                    ptx::tc_fence_after();
+                    if (it == 0 && kb == 0) PTRACE(2);
+                    const uint64_t da = ptx::umma_desc_k_sw128(ptx::smem_u32(smem_a + (size_t)stage * kABytes));
+                    const uint64_t db = ptx::umma_desc_k_sw128(ptx::smem_u32(smem_b + (size_t)stage * b_bytes));
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+                        ptx::umma_bf16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                    ptx::umma_commit(&empty_bar[stage]);   // frees the smem slot when these MMAs retire
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                }
+                ptx::umma_commit(&tfull[acc]);
+                if (it == 0) PTRACE(3);
+            }
+        }
+    } else {
+        // ================= epilogue warps =================
+        const int variant = (p.geglu ? 100 : 0) + (p.out_f32 ? 10 : 0) + p.res_kind + (p.gn_part ? 1000 : 0);
+        switch (variant) {
+            case 100: persist_epilogue<false, 0, true, false>(p, smem, tmem_base, warp, lane); break;
+            case 0: persist_epilogue<false, 0, false, false>(p, smem, tmem_base, warp, lane); break;
+            case 1: persist_epilogue<false, 1, false, false>(p, smem, tmem_base, warp, lane); break;
+            case 2: persist_epilogue<false, 2, false, false>(p, smem, tmem_base, warp, lane); break;
+            case 10: persist_epilogue<true, 0, false, false>(p, smem, tmem_base, warp, lane); break;
+            case 11: persist_epilogue<true, 1, false, false>(p, smem, tmem_base, warp, lane); break;
+            case 12: persist_epilogue<true, 2, false, false>(p, smem, tmem_base, warp, lane); break;
+            case 1010: persist_epilogue<true, 0, false, true>(p, smem, tmem_base, warp, lane); break;
+            case 1012: persist_epilogue<true, 2, false, true>(p, smem, tmem_base, warp, lane); break;
+            default: break;   // the host never launches another combination
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem_base, p.tmem_cols);
+    }
+    if (threadIdx.x == 0) PTRACE(7);
+}
+
 uint32_t pow2_cols(int n) {
     uint32_t c = 32;
     while ((int)c < n) c <<= 1;
@@ -543,6 +932,128 @@ gemm_kernel_t gemm_entry(int pair, int op) {
     }
 }
 
+// The opt-in to > 48 KB of dynamic smem is a per-DEVICE function attribute: configure every kernel once per device
+// (a second GPU in the same process would otherwise launch without it), under a mutex (the C ABI may be called from threads).
+int configure_gemm_kernels() {
+    static std::mutex mu;
+    static bool configured[64] = {};
+    int dev = 0;
+    B200SD_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(mu);
+    if (dev < 0 || dev >= 64 || configured[dev]) return B200SD_OK;
+    for (int i = 0; i < 8; ++i) {
+        B200SD_CUDA(cudaFuncSetAttribute(gemm_entry(i & 1, i >> 1), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
+        B200SD_CUDA(cudaFuncSetAttribute(gemm_entry(i & 1, i >> 1), cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    }
+    B200SD_CUDA(cudaFuncSetAttribute(gemm_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
+    B200SD_CUDA(cudaFuncSetAttribute(gemm_persist_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    configured[dev] = true;
+    return B200SD_OK;
+}
+
+// ---- persistent path (gemm_persist_kernel): tile width, eligibility, launch ----
+bool persist_enabled() {
+    static const bool off = getenv("B200SD_PERSIST") && getenv("B200SD_PERSIST")[0] == '0';
+    return !off;
+}
+// Tile width for the persistent kernel: a multiple of 32 (its epilogue chunk; 64 for GEGLU: values | gates) dividing N.
+// cost = rounds of tiles per SM x operand bytes a tile pulls per k-block (128 + bn rows): the smallest tile that still
+// fits one round wins on short grids (more CTAs, shorter epilogue), wide tiles win once several rounds are needed anyway.
+int pick_block_n_persist(int N, int m_tiles, bool geglu) {
+    const int sms = b200sd_num_sms();
+    const int step = geglu ? 64 : 32;
+    long best_cost = 0;
+    int best = 0;
+    for (int bn = step; bn <= 256; bn += step) {
+        if (N % bn) continue;
+        const long tiles = (long)m_tiles * (N / bn);
+        const long cost = ((tiles + sms - 1) / sms) * (BLOCK_M + bn);
+        if (best == 0 || cost < best_cost || (cost == best_cost && bn > best)) { best = bn; best_cost = cost; }
+    }
+    return best;
+}
+
+int launch_persist(const b200sd_gemm_args* a, const KParams& k, int m_tiles, b200sd_stream_t stream) {
+    PParams p;
+    memset(&p, 0, sizeof(p));
+    p.tmA0 = k.tmA0; p.tmA1 = k.tmA1; p.tmB = k.tmB;
+    p.bias = k.bias; p.rowbias = k.rowbias; p.gn_part = k.gn_part;
+    p.M = k.M; p.N = k.N;
+    p.num_k_blocks = k.num_k_blocks; p.block_n = k.block_n;
+    p.conv = k.conv; p.cblocks0 = k.cblocks0; p.cblocks = k.cblocks;
+    p.tile_h = k.tile_h; p.tile_n = k.tile_n; p.tiles_y = k.tiles_y; p.w_kmajor = k.w_kmajor;
+    p.n_tiles = k.N / k.block_n;
+    p.num_tiles = m_tiles * p.n_tiles;
+    p.ldrb = k.ldrb; p.rows_per_image = k.rows_per_image;
+    p.geglu = k.epilogue == B200SD_EPI_GEGLU;
+    p.out_f32 = k.out_f32;
+    p.res_kind = k.residual ? (k.res_f32 ? 2 : 1) : 0;
+    p.depth = p.res_kind ? kMaxDepth : 2;
+    const int bn = k.block_n;
+    p.acc_stride = bn <= 128 ? 128 : 256;
+    p.tmem_cols = 2 * p.acc_stride;
+    // ---- output / residual tensor maps: 32-column x 32-row boxes (one epilogue chunk of one warp) ----
+    const int out_cols = p.geglu ? k.N / 2 : k.N;
+    {
+        const uint64_t dims[2] = {(uint64_t)out_cols, (uint64_t)k.M};
+        const uint64_t str[2] = {0, (uint64_t)k.ldc * (k.out_f32 ? 4 : 2)};
+        const uint32_t box[2] = {32, 32};
+        const int rc = b200sd_make_tmap(&p.tmOut, k.out, 2, dims, str, box, k.out_f32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                                        k.out_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
+        if (rc) return rc;
+    }
+    if (p.res_kind) {
+        const uint64_t dims[2] = {(uint64_t)k.N, (uint64_t)k.M};
+        const uint64_t str[2] = {0, (uint64_t)k.ldr * (k.res_f32 ? 4 : 2)};
+        const uint32_t box[2] = {32, 32};
+        const int rc = b200sd_make_tmap(&p.tmRes, k.residual, 2, dims, str, box, k.res_f32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                                        k.res_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
+        if (rc) return rc;
+    }
+    // ---- smem layout ----
+    const int stage_bytes = kABytes + bn * BLOCK_K * 2;
+    p.chunk_bytes = (p.out_f32 || p.res_kind == 2) ? 4096 : 2048;
+    const int epi_bytes = kEpiWarps * p.depth * p.chunk_bytes;
+    const int bias_bytes = kEpiWarps * 256 * (int)sizeof(float);
+    const int stat_bytes = k.gn_part ? 4 * 2 * 256 * (int)sizeof(float) : 0;
+    const int bars_bytes = 512;
+    const int budget = 227 * 1024 - 1024;
+    int stages = (budget - epi_bytes - bias_bytes - stat_bytes - bars_bytes) / stage_bytes;
+    if (stages > kMaxStages) stages = kMaxStages;
+    B200SD_REQUIRE(stages >= 2, "gemm(persistent): smem budget leaves %d stages for block_n %d", stages, bn);
+    p.stages = stages;
+    p.off_b = (uint32_t)stages * kABytes;
+    p.off_epi = (uint32_t)stages * stage_bytes;
+    p.off_bias = p.off_epi + epi_bytes;
+    p.off_stat = p.off_bias + bias_bytes;
+    p.off_bars = p.off_stat + stat_bytes;
+    const size_t smem_bytes = (size_t)p.off_bars + bars_bytes + 1024;
+    p.trace = g_gemm_trace;
+    {
+        const int rc = configure_gemm_kernels();
+        if (rc) return rc;
+    }
+    const int sms = b200sd_num_sms();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(p.num_tiles < sms ? p.num_tiles : sms);
+    cfg.blockDim = dim3(kPersistThreads);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = static_cast<cudaStream_t>(stream);
+    cudaLaunchAttribute attr[1];
+    int na = 0;
+    if (b200sd_pdl_enabled()) {
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    cfg.attrs = attr;
+    cfg.numAttrs = na;
+    B200SD_CUDA(cudaLaunchKernelEx(&cfg, gemm_persist_kernel, p));
+    g_b200sd_launches.fetch_add(1, std::memory_order_relaxed);
+    B200SD_LAUNCH_CHECK();
+    return B200SD_OK;
+}
+
 int launch_gemm(KParams& p, int m_tiles, int n_tiles, int grid_z, bool cluster, b200sd_stream_t stream) {
     const int sms = b200sd_num_sms();
     const int bn = p.block_n;
@@ -562,13 +1073,9 @@ int launch_gemm(KParams& p, int m_tiles, int n_tiles, int grid_z, bool cluster, 
     const size_t smem_bytes = (size_t)stages * stage_bytes + 1024 /*align slack*/ + 256 /*barriers*/ + 3072 /*bias tiles*/;
     B200SD_REQUIRE(smem_bytes <= 227 * 1024, "gemm: smem budget exceeded (%zu B)", smem_bytes);
 
-    static bool configured = false;
-    if (!configured) {
-        for (int i = 0; i < 8; ++i) {
-            B200SD_CUDA(cudaFuncSetAttribute(gemm_entry(i & 1, i >> 1), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
-            B200SD_CUDA(cudaFuncSetAttribute(gemm_entry(i & 1, i >> 1), cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        }
-        configured = true;
+    {
+        const int rc = configure_gemm_kernels();
+        if (rc) return rc;
     }
     p.trace = g_gemm_trace;
     cudaLaunchConfig_t cfg = {};
@@ -652,7 +1159,15 @@ int conv_m_tiling(KParams& p, int NB, int H, int W, int M, int* m_tiles) {
 
 extern "C" size_t b200sd_gemm_workspace_bytes(void) { return 0; }  // split-K reduces over DSMEM: no scratch needed
 
-extern "C" int b200sd_geglu_tile(int N) { return pick_block_n(N, 1, B200SD_EPI_GEGLU); }
+extern "C" int b200sd_geglu_tile(int N) {
+    // the persistent kernel moves 32-column chunks of values and gates: tile = [tile/2 values | tile/2 gates], tile % 64 == 0
+    if (persist_enabled()) {
+        if (N % 256 == 0) return 256;
+        if (N % 128 == 0) return 128;
+        if (N % 64 == 0) return 64;
+    }
+    return pick_block_n(N, 1, B200SD_EPI_GEGLU);
+}
 
 // M / N / split-K tiling of a forward GEMM (shared by the launch and by b200sd_gemm_gn_layout, which tells the consumer of
 // the GroupNorm column statistics how many partial rows each image owns).  Fills the tiling fields of p.
@@ -713,6 +1228,19 @@ static int gemm_tiling(const b200sd_gemm_args* a, KParams& p, int* m_tiles_out, 
     *n_tiles_out = n_tiles_f;
     p.split_k = split;
     p.pair = want_pair(a->pair, split, m_tiles, n_tiles_f, p.num_k_blocks) && bn % 32 == 0;
+    // ---- persistent kernel (TMA-store epilogue, double-buffered TMEM): un-split, un-paired tiles of 128 rows ----
+    p.persist = 0;
+    const bool geglu = a->epilogue == B200SD_EPI_GEGLU;
+    if (persist_enabled() && split == 1 && !p.pair && p.rows_valid == BLOCK_M && a->N % 32 == 0 &&
+        (!a->rowbias || (a->rows_per_image > 0 && a->rows_per_image % 32 == 0)) &&
+        !(a->residual && a->residual == a->out && a->residual_dtype != a->out_dtype)) {
+        const int bnp = a->block_n > 0 ? a->block_n : pick_block_n_persist(a->N, m_tiles, geglu);
+        if (bnp > 0 && bnp <= 256 && bnp % (geglu ? 64 : 32) == 0 && a->N % bnp == 0) {
+            p.persist = 1;
+            p.block_n = bnp;
+            *n_tiles_out = a->N / bnp;
+        }
+    }
     return B200SD_OK;
 }
 
@@ -814,6 +1342,7 @@ extern "C" int b200sd_gemm(const b200sd_gemm_args* a, b200sd_stream_t stream) {
         if (rc) return rc;
     }
 
+    if (p.persist) return launch_persist(a, p, m_tiles, stream);
     return launch_gemm(p, m_tiles, n_tiles, split, /*cluster=*/true, stream);
 }
 
@@ -835,6 +1364,13 @@ extern "C" int b200sd_gemm_gn_layout(const b200sd_gemm_args* a, int hw, int* par
     *parts_per_image = 0;
     *total_parts = 0;
     if (a->out_dtype != B200SD_F32 || a->epilogue != B200SD_EPI_LINEAR || (a->residual && a->residual_dtype != B200SD_F32)) return B200SD_OK;
+    if (p.persist) {
+        // the persistent kernel publishes one partial row per 128-row tile
+        if (a->M % hw != 0 || hw % BLOCK_M != 0 || (p.conv && a->H * a->W != hw)) return B200SD_OK;
+        *parts_per_image = hw / BLOCK_M;
+        *total_parts = m_tiles;
+        return B200SD_OK;
+    }
     // Partial row (m_tile * split + rank) covers the BLOCK_M / split output rows that rank stores; it is usable when those
     // rows never straddle two images and the partial rows of an image are contiguous.
     const int rpp = BLOCK_M / p.split_k;     // rows per partial

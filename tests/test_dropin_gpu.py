@@ -188,3 +188,25 @@ def test_accumulation_averages_and_frozen_parameters_do_not_decay():
         deltas.append(unet.conv_out.weight.detach() - before)
     assert float(deltas[0].abs().max()) > 0
     assert _rel(deltas[1], deltas[0]) <= 1e-2
+
+
+def test_pipeline_call_matches_the_oracle_loop():
+    """inference.py:342-351: pipeline(..., height, width, num_inference_steps, guidance_scale, latents=fixed) -- through the
+    StableDiffusionPipeline wrapper with precomputed text embeddings (CLIP is a neighbour) vs the oracle's App. B.4 loop."""
+    from b200sd import StableDiffusionPipeline
+    from b200sd.schedulers import DDIMScheduler
+    from oracle import schedulers_ref as R
+    oracle, unet = _pair()
+    g = torch.Generator().manual_seed(42)
+    lat = torch.randn(2, 4, 32, 32, generator=g)
+    ctx2 = torch.randn(4, 77, 64, generator=g)
+    kw = dict(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear", clip_sample=False, set_alpha_to_one=False)
+    pipe = StableDiffusionPipeline(unet=unet, scheduler=DDIMScheduler(**kw), safety_checker=None).to(DEV)
+    out = pipe(prompt_embeds=ctx2.to(DEV), height=256, width=256, num_inference_steps=6, guidance_scale=7.5, latents=lat.to(DEV),
+               output_type="latent")
+    with torch.no_grad():
+        want = R.denoise_loop(oracle, R.DDIMSchedulerRef(clip_sample=False, set_alpha_to_one=False), lat, ctx2, 6, 7.5)
+    cos = float(F.cosine_similarity(out.images.float().cpu().flatten(), want.flatten(), dim=0))
+    assert out.images.shape == (2, 4, 32, 32) and cos >= 0.999, cos
+    with pytest.raises(ValueError, match="Unexpected latents shape"):
+        pipe(prompt_embeds=ctx2.to(DEV), height=256, width=256, latents=lat[:, :, :16].to(DEV))

@@ -268,15 +268,29 @@ def test_groupnorm_parts_concat():
     _close(raw, xc, 1.0 / 128)
 
 
-def test_gemm_gn_layout_rejects_straddling_tiles():
-    """A 128-row tile spanning two images with no K split to separate them -> no statistics layout, the caller keeps the
+def test_gemm_gn_layout_straddling_tiles():
+    """A 128-row tile spanning two images: the persistent kernel publishes one partial row per 32 output rows (never straddles a
+    64-row image); images that are not a multiple of 32 rows and bf16 outputs get no statistics layout -- the caller keeps the
     stand-alone GroupNorm."""
     from b200sd import ops
+    _setup()
+    torch.manual_seed(9)
     a = torch.randn(2 * 64, 320, device=DEV).bfloat16()
-    w = torch.randn(1280, 320, device=DEV).bfloat16()
+    w = (torch.randn(1280, 320, device=DEV) / 18).bfloat16()
     out = torch.empty(2 * 64, 1280, device=DEV)
     args = ops.gemm(a, w, out, launch=False)
-    assert ops.gemm_attach_gn_parts(args, 64, DEV) is None
+    parts = ops.gemm_attach_gn_parts(args, 64, DEV)
+    if parts is not None:
+        ops.gemm_run(args)
+        pp = parts.buf.view(-1, 2, 1280)
+        assert pp.shape[0] >= 2 * parts.ppi
+        for b in range(2):
+            x = out[b * 64:(b + 1) * 64].double()
+            got = pp[b * parts.ppi:(b + 1) * parts.ppi].double().sum(0)
+            assert (got[0] - x.sum(0)).abs().max().item() < 1e-3
+            assert (got[1] - (x * x).sum(0)).abs().max().item() < 1e-2
+    a3 = torch.randn(2 * 48, 320, device=DEV).bfloat16()
+    assert ops.gemm_attach_gn_parts(ops.gemm(a3, w, torch.empty(2 * 48, 1280, device=DEV), launch=False), 48, DEV) is None
     outb = torch.empty(2 * 256, 1280, device=DEV, dtype=torch.bfloat16)   # bf16 output: not covered either
     a2 = torch.randn(2 * 256, 1280, device=DEV).bfloat16()
     assert ops.gemm_attach_gn_parts(ops.gemm(a2, w, outb, launch=False), 256, DEV) is None

@@ -185,3 +185,40 @@ def test_bench_image_sharding():
             parts = [bench.shard_images(total, world, r) for r in range(world)]
             assert sum(parts) == total and max(parts) - min(parts) <= 1
             assert parts == sorted(parts, reverse=True)
+
+
+def test_pipeline_wrapper_save_load_layout(tmp_path):
+    """finetune_sd.py:517-537 builds StableDiffusionPipeline(text_encoder=, vae=, unet=, tokenizer=, scheduler=, safety_checker=,
+    feature_extractor=) and save_pretrained()s it; utils.py:187-191 loads it back with safety_checker=None: the diffusers directory
+    layout (model_index.json + unet/ + scheduler/) round-trips, including the scheduler CLASS (B.6: a DDPMScheduler is what the
+    training script saves)."""
+    from b200sd import StableDiffusionPipeline
+    from b200sd.schedulers import DDIMScheduler, DDPMScheduler, PNDMScheduler
+    from b200sd.unet import UNet2DConditionModel
+    kw = dict(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear")
+    unet = UNet2DConditionModel(**U.TINY_OVERRIDES)
+    for sch in (DDPMScheduler(num_train_timesteps=1000, **kw), DDIMScheduler(clip_sample=False, set_alpha_to_one=False, **kw),
+                PNDMScheduler(skip_prk_steps=True, **kw)):
+        d = tmp_path / type(sch).__name__
+        pipe = StableDiffusionPipeline(text_encoder=None, vae=None, unet=unet, tokenizer=None, scheduler=sch,
+                                       safety_checker=None, feature_extractor=None)
+        pipe.save_pretrained(str(d))
+        index = json.load(open(d / "model_index.json"))
+        assert index["_class_name"] == "StableDiffusionPipeline"
+        assert index["unet"] == ["diffusers", "UNet2DConditionModel"] and index["scheduler"][1] == type(sch).__name__
+        assert index["safety_checker"] == [None, None] and index["vae"] == [None, None]
+        assert os.path.exists(d / "unet" / "config.json") and os.path.exists(d / "scheduler" / "scheduler_config.json")
+        again = StableDiffusionPipeline.from_pretrained(str(d), safety_checker=None)
+        assert type(again.scheduler) is type(sch)
+        assert again.scheduler.config.beta_end == 0.012
+        for (k, a), (_, b) in zip(unet.state_dict().items(), again.unet.state_dict().items()):
+            assert torch.equal(a, b), k
+        # inference.py:404-409: the scheduler can be overridden at load time
+        swapped = StableDiffusionPipeline.from_pretrained(str(d), scheduler=DDIMScheduler(clip_sample=False, set_alpha_to_one=False, **kw))
+        assert isinstance(swapped.scheduler, DDIMScheduler)
+    with pytest.raises(ValueError):
+        StableDiffusionPipeline(unet=None, scheduler=None)
+    with pytest.raises(ValueError):       # diffusers' own message for sizes that are not multiples of 8
+        pipe(prompt_embeds=torch.zeros(2, 77, 64), height=100, width=64)
+    with pytest.raises(ValueError):       # strings need a tokenizer / text encoder
+        pipe("a book cover")

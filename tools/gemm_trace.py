@@ -8,9 +8,9 @@ from b200sd._lib import lib
 from b200sd.packing import pack_conv3x3
 DEV = "cuda:0"
 L = lib()
-L.b200sd_debug_gemm_trace.argtypes = [ctypes.c_void_p]
 trace = torch.zeros(4096 * 8, dtype=torch.int64, device=DEV)
-names = ["start", "prologue done", "first tile landed", "all MMA issued", "accum ready (epi)", "phaseA done", "phaseB done", "exit"]
+names = ["start", "prologue done", "first tile landed", "all MMA issued", "accum ready (epi)", "phaseA done | chunks issued", "phaseB done | stores drained", "exit"]
+# persistent kernel: slot 5 = warp 2 issued its last TMA store, slot 6 = its stores have completed
 
 def run(label, fn, nctas):
     for _ in range(3): fn()
@@ -36,12 +36,12 @@ def gemm_case(M, N, K, res=True, f32=True):
     args = ops.gemm(a, w, out, bias=bias, residual=r, launch=False)
     return (lambda: ops.gemm_run(args)), (a, w, bias, out)
 
-for (M, N, K) in [(8192, 320, 320), (512, 1280, 1280), (2048, 640, 640), (8192, 320, 1280)]:
-    fn, keep = gemm_case(M, N, K)
+for (M, N, K, res, f32) in [(8192, 320, 320, True, True), (8192, 320, 320, False, False), (8192, 960, 320, False, False), (512, 1280, 1280, True, True), (2048, 640, 640, True, True), (8192, 320, 1280, True, True)]:
+    fn, keep = gemm_case(M, N, K, res, f32)
     # ask the library how many CTAs: replicate heuristics crudely by reading the trace afterwards
     trace.zero_(); L.b200sd_debug_gemm_trace(trace.data_ptr()); fn(); torch.cuda.synchronize(); L.b200sd_debug_gemm_trace(None)
     n = int((trace.view(-1, 8)[:, 0] != 0).sum())
-    run(f"gemm M{M} N{N} K{K} (+bias +fp32 residual, fp32 out)", fn, n)
+    run(f"gemm M{M} N{N} K{K} (+bias, residual={res}, fp32 out={f32})", fn, n)
 
 B, H, W, Cin, Cout = 2, 8, 8, 1280, 1280
 x = torch.randn(B * H * W, Cin, device=DEV).bfloat16()

@@ -15,7 +15,7 @@ ctx = torch.randn(2 * B, 77, 768, device=dev)
 with torch.no_grad():
     unet(x, 500, ctx)
     eng = next(iter(unet._engines.values()))
-    acc, per_op = eng.profile()
+    acc, per_op, _total = eng.profile()
 tot = sum(ms for _, ms, _ in per_op)
 print(f"# {len(per_op)} launches, sum {tot:.3f} ms (isolated; the captured step is faster)")
 for name, ms, fl in sorted(per_op, key=lambda t: -t[1]):
