@@ -464,10 +464,11 @@ def run_ours(args):
     # collective of the hot path, and the driver's scaling run only ever launches `bench.py --gpus N` ----
     train = train_text = None
     if args.precision == "bf16" and args.total_images <= 0 and not args.portrait and not args.no_train_legs:
+        unet._engines = {}                       # the sampling plan's buffers are not needed any more
         torch.cuda.empty_cache()
-        train = train_leg(dev, world, rank, steps=5, warmup=3)
+        train = train_leg(dev, world, rank, steps=5, warmup=3, unet=unet)          # same model object: one 860 M-parameter init per rank
         torch.cuda.empty_cache()
-        train_text = train_text_leg(dev, world, rank, local, steps=5, warmup=3)
+        train_text = train_text_leg(dev, world, rank, local, steps=5, warmup=3, unet=unet)
     if rank == 0:
         line["train"] = train
         line["train_text"] = train_text
@@ -531,7 +532,7 @@ def _timed_steps(step_fn, steps, warmup, world, dev):
     return ms
 
 
-def train_leg(dev, world, rank, steps=5, warmup=3, B=8):
+def train_leg(dev, world, rank, steps=5, warmup=3, B=8, unet=None):
     """BASELINE configs[2] inside the default bench line: `steps` UNet fine-tuning steps at batch 8/GPU (add_noise + UNet fwd +
     MSE + bwd + bucketed NCCL allreduce of the 859.5 M fp32 gradients + fused AdamW), then the SAME steps with the collective
     switched off (every rank steps on its local gradient) -- the difference is the exposed (non-overlapped) communication."""
@@ -539,8 +540,10 @@ def train_leg(dev, world, rank, steps=5, warmup=3, B=8):
     from b200sd.schedulers import DDPMScheduler
     from b200sd.trainer import Trainer
     from b200sd.unet import UNet2DConditionModel
-    torch.manual_seed(0)
-    unet = UNet2DConditionModel().to(dev)
+    if unet is None:
+        torch.manual_seed(0)
+        unet = UNet2DConditionModel().to(dev)          # identical initial weights on every rank
+    unet.requires_grad_(True)
     sched = DDPMScheduler(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear", num_train_timesteps=1000)
     tr = Trainer(unet, sched, lr=1e-5, weight_decay=1e-2)
     g = torch.Generator().manual_seed(1000 + rank)
@@ -560,11 +563,11 @@ def train_leg(dev, world, rank, steps=5, warmup=3, B=8):
            "exposed_comm_ms": ms - ms_local, "allreduce_bytes_on_wire_per_gpu": int(2 * (world - 1) / world * n_param * 4),
            "tflops_per_gpu": flops_step / (ms * 1e-3) / 1e12, "frac_of_sustained_bf16_peak": flops_step / (ms * 1e-3) / 1e12 / tf_sus,
            "last_loss": loss, "collective": "NCCL all_reduce(SUM) of the flat fp32 gradient buffer in 64 MB buckets, overlapped with the backward"}
-    del tr, unet
+    del tr
     return rec
 
 
-def train_text_leg(dev, world, rank, local, steps=5, warmup=3, B=8):
+def train_text_leg(dev, world, rank, local, steps=5, warmup=3, B=8, unet=None):
     """BASELINE configs[3]: text-encoder fine-tuning (UNet frozen: our forward + data-gradient-only backward down to the context;
     CLIP text model = stock transformers under DistributedDataParallel) at batch 8/GPU."""
     import torch
@@ -573,7 +576,9 @@ def train_text_leg(dev, world, rank, local, steps=5, warmup=3, B=8):
     from b200sd.schedulers import DDPMScheduler
     from b200sd.unet import UNet2DConditionModel
     torch.manual_seed(0)
-    unet = UNet2DConditionModel().to(dev).eval().requires_grad_(False)            # finetune_sd.py:391-395
+    if unet is None:
+        unet = UNet2DConditionModel().to(dev)
+    unet = unet.eval().requires_grad_(False)                                      # finetune_sd.py:391-395
     clip = CLIPTextModel(CLIPTextConfig(hidden_size=768, intermediate_size=3072, num_hidden_layers=12, num_attention_heads=12,
                                         vocab_size=49408, max_position_embeddings=77, hidden_act="quick_gelu")).to(dev).train()
     model = torch.nn.parallel.DistributedDataParallel(clip, device_ids=[local]) if world > 1 else clip
@@ -609,7 +614,7 @@ def train_text_leg(dev, world, rank, local, steps=5, warmup=3, B=8):
            "exposed_comm_ms": ms - ms_local, "allreduce_bytes_on_wire_per_gpu": int(2 * (world - 1) / world * n_param * 4),
            "tflops_per_gpu": flops_step / (ms * 1e-3) / 1e12, "frac_of_sustained_bf16_peak": flops_step / (ms * 1e-3) / 1e12 / tf_sus,
            "last_loss": float(last[0]), "collective": "torch DistributedDataParallel (NCCL) over the 123.1 M CLIP parameters"}
-    del model, clip, unet, opt
+    del model, clip, opt
     return rec
 
 

@@ -46,6 +46,9 @@ int64_t b200sd_launch_count(void);
  * plan timestamps the gaps between its kernels and b200sd_timer_elapsed_ms(i, j) gives per-kernel times inside the real step. */
 /* debug: every CTA of the GEMM kernels stamps %globaltimer at 8 phase boundaries into buf[cta][8] (NULL switches it off) */
 void b200sd_debug_gemm_trace(void* buf);
+/* debug / tuning overrides of the GEMM launch policy: key 0 = persistent kernel (-1 default, 0 off, 1 on), 1 = smem ring depth cap
+ * (0 = auto), 2 = cap on the persistent grid (0 = one CTA per SM) */
+void b200sd_debug_set(int key, int value);
 int b200sd_timer_reserve(int n);
 int b200sd_timer_record(int i, b200sd_stream_t stream);
 int b200sd_timer_elapsed_ms(int i, int j, float* ms);

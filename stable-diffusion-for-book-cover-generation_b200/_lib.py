@@ -53,6 +53,7 @@ SIGNATURES = {
     "b200sd_version": (_i, []),
     "b200sd_launch_count": (_i64, []),
     "b200sd_debug_gemm_trace": (None, [_vp]),
+    "b200sd_debug_set": (None, [_i, _i]),
     "b200sd_timer_reserve": (_i, [_i]),
     "b200sd_timer_record": (_i, [_i, _vp]),
     "b200sd_timer_elapsed_ms": (_i, [_i, _i, C.POINTER(C.c_float)]),

@@ -67,7 +67,7 @@ def ensure_flat(model, dev):
     if getattr(model, "_flat", None) is None or model._flat.device != dev or not model._flat.owns(model):
         model._flat = FlatParams(model, dev)
         model._train_engines = {}
-    return model._flat
+    return model._flat.materialize()
 
 
 def unet_forward_train(model, sample, timestep, ctx):

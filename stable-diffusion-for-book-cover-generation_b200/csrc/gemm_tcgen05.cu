@@ -25,6 +25,15 @@
 extern std::atomic<long long> g_b200sd_launches;
 
 static unsigned long long* g_gemm_trace = nullptr;
+// debug / tuning overrides (tools/conv_probe.py): key 0 = persistent kernel (-1 default, 0 off, 1 on), key 1 = smem ring depth
+// (0 = auto), key 2 = cap on the persistent grid (0 = one CTA per SM)
+static int g_dbg[4] = {-1, 0, 0, 0};   // [3] = residual prefetch depth (2 / 3)
+static const int g_dbg_env = [] {
+    const char* e = getenv("B200SD_EPI_DEPTH");
+    if (e) g_dbg[3] = atoi(e);
+    return 0;
+}();
+extern "C" void b200sd_debug_set(int key, int value) { if (key >= 0 && key < 4) g_dbg[key] = value; }
 extern "C" void b200sd_debug_gemm_trace(void* buf) { g_gemm_trace = static_cast<unsigned long long*>(buf); }
 
 namespace {
@@ -36,7 +45,7 @@ __device__ __forceinline__ unsigned long long gtimer() {
 }
 #define TRACE(slot)                                                                                   \
     do {                                                                                              \
-        if (p.trace) p.trace[((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 8 + (slot)] = gtimer(); \
+        if (p.trace) p.trace[((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 16 + (slot)] = gtimer(); \
     } while (0)
 
 constexpr int BLOCK_M = 128;
@@ -514,7 +523,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tcgen05_kernel(const __gr
 // gemm_tcgen05_kernel above.
 // =================================================================================================================
 constexpr int kEpiWarps = 8;
-constexpr int kPersistThreads = 64 + 32 * kEpiWarps;
+constexpr int kPersistThreads = 64 + 32 * kEpiWarps + 32;   // A producer | MMA | 8 epilogue | B producer
 constexpr int kMaxDepth = 3;
 
 struct PParams {
@@ -528,13 +537,20 @@ struct PParams {
     int n_tiles, num_tiles;
     int ldrb, rows_per_image;
     int geglu, out_f32, res_kind;   // res_kind: 0 none, 1 bf16, 2 fp32
+    int pf_share;                   // CTAs that stream the same weight tile concurrently: they split its L2 prefetch k-block by k-block
     int depth;                      // smem chunks per epilogue warp (3 with a residual, 2 without)
     int chunk_bytes;                // 4096: 32 rows x 128 B (an fp32 chunk is involved); 2048: 32 rows x 64 B (bf16 only)
     uint32_t tmem_cols, acc_stride;
     uint32_t off_b, off_epi, off_bias, off_stat, off_bars;   // byte offsets from the 1024-aligned smem base
     unsigned long long* trace;      // optional [ctas][8] globaltimer stamps (debug)
 };
-#define PTRACE(slot) do { if (p.trace) p.trace[(size_t)blockIdx.x * 8 + (slot)] = gtimer(); } while (0)
+#define PTRACE(slot) do { if (p.trace) p.trace[(size_t)blockIdx.x * 16 + (slot)] = gtimer(); } while (0)
+// epilogue phase accounting of warp 2, lane 0 (clock64 ticks summed over its chunks) -> trace slots 8..13
+#ifdef B200SD_TRACE_EPILOGUE
+#define PACC(i) do { if (p.trace && ew == 0) { const long long t__ = clock64(); pacc[i] += t__ - pt0; pt0 = t__; } } while (0)
+#else
+#define PACC(i) do { } while (0)
+#endif
 
 
 // one 32-column chunk of this warp's 32 accumulator rows; cb = the warp's smem chunk (holds the residual when RES != 0)
@@ -667,16 +683,22 @@ __device__ __forceinline__ void persist_epilogue(const PParams& p, uint8_t* smem
         ptx::tma_load_2d(my + buf * kChunkBytes, &p.tmRes, &rfull[buf], n_tile * p.block_n + ch * 32, m_tile * BLOCK_M + q * 32);
     };
     if constexpr (RES != 0) {
+        // (holding this prefetch back until the producer's first ring of operand loads is out was measured: the residual then
+        // lands too late for a short-K tile -- M8192 N320 K320 7.9 -> 9.0 us -- so it goes out at once)
         if (lane == 0)
             for (int g = 0; g < D && g < total; ++g) issue_res(g);
     }
 
     int g = 0;
+#ifdef B200SD_TRACE_EPILOGUE
+    long long pacc[6] = {0, 0, 0, 0, 0, 0}, pt0 = clock64();
+#endif
     for (int it = 0; it < my_tiles; ++it) {
         const int tile = (int)blockIdx.x + it * (int)gridDim.x;
         const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
         const int n0 = n_tile * p.block_n;
         const int row0 = m_tile * BLOCK_M + q * 32;
+        PACC(5);
         // the biases of this warp's chunks (+ the time-embedding row of this warp's image) -> the warp's smem copy
         __syncwarp();
         {
@@ -690,9 +712,11 @@ __device__ __forceinline__ void persist_epilogue(const PParams& p, uint8_t* smem
             }
         }
         __syncwarp();
+        PACC(0);   // bias staging
         const int acc = it & 1;
         ptx::mbar_wait(&tfull[acc], (uint32_t)(it >> 1) & 1u);
         ptx::tc_fence_after();
+        PACC(1);   // waiting for the accumulator
         if (it == 0 && ew == 0 && lane == 0) PTRACE(4);
         const uint32_t taddr = tmem_base + (uint32_t)acc * p.acc_stride + ((uint32_t)(q * 32) << 16);
         const int nrows = max(0, min(32, p.M - row0));
@@ -712,8 +736,10 @@ __device__ __forceinline__ void persist_epilogue(const PParams& p, uint8_t* smem
                 if (lane == 0) ptx::tma_store_wait_read<1>();
                 __syncwarp();
             }
+            PACC(2);   // waiting for the smem chunk to be free
             persist_chunk<OUT_F32, RES, GEGLU, STATS>(p, taddr, ch, sb + l * 32, sb + 128 + l * 32, cb, lane, l == nl - 1, &tempty[acc],
                                                      &rfull[buf], (uint32_t)(g / D) & 1u, gn_dst, nrows);
+            PACC(3);   // TMEM -> registers -> epilogue math -> smem
             ptx::fence_proxy_async();   // generic-proxy smem writes -> visible to the TMA (async proxy)
             __syncwarp();
             if (lane == 0) {
@@ -727,6 +753,7 @@ __device__ __forceinline__ void persist_epilogue(const PParams& p, uint8_t* smem
                     }
                 }
             }
+            PACC(4);   // proxy fence + TMA store issue (+ residual refill)
         }
         if constexpr (STATS) {
             // GroupNorm statistics of the tile: the four quarters' column sums folded in a fixed order (bit-reproducible) into
@@ -745,6 +772,10 @@ __device__ __forceinline__ void persist_epilogue(const PParams& p, uint8_t* smem
         }
     }
     if (ew == 0 && lane == 0) PTRACE(5);
+#ifdef B200SD_TRACE_EPILOGUE
+    if (p.trace && ew == 0 && lane == 0)
+        for (int i = 0; i < 6; ++i) p.trace[(size_t)blockIdx.x * 16 + 8 + i] = (unsigned long long)pacc[i];
+#endif
     if (lane == 0) ptx::tma_store_wait<0>();   // all output writes performed before the CTA may exit
     __syncwarp();
     if (ew == 0 && lane == 0) PTRACE(6);
@@ -766,6 +797,76 @@ __global__ void __launch_bounds__(kPersistThreads, 1) gemm_persist_kernel(const 
     const int lane = threadIdx.x & 31;
     const int b_bytes = p.block_n * BLOCK_K * 2;
 
+    // ---- TMA producers, resumable.  TWO threads feed the ring: thread 0 loads the A tiles, lane 0 of the last warp the B
+    // (weight) tiles -- issuing a cp.async.bulk.tensor costs the issuing thread a few hundred cycles, and with both loads of a
+    // k-block on one thread that thread, not the memory system, paced the main loop of a one-CTA-per-SM grid (measured: adding
+    // ~300 cycles of index arithmetic per k-block to the single producer slowed an M8192 K2880 conv from 22.6 to 33.1 us).
+    // All per-tile index arithmetic is hoisted out of the k loop; the first ring of loads is issued BEFORE the CTA-wide prologue
+    // sync, so the load latency of the first tile overlaps the TMEM allocation and the barrier hand-shake. ----
+    int pr_stage = 0, pr_tile = blockIdx.x, pr_kb = 0, pr_m0 = 0, pr_n0 = 0, pr_img = 0, pr_y0 = 0, pr_tap = 0, pr_cb = 0, pr_me = 0;
+    uint32_t pr_phase = 0;
+    // The weights are cold in HBM at every kernel of the step (1.7 GB stream through a 126 MB L2), and the smem ring is only 3-4
+    // k-blocks deep: the weight tiles beyond the ring are pulled into L2 by prefetch boxes, kPrefetch k-blocks ahead of the loads.
+    // CTAs that work on the same n-tile at the same time (different m-tiles) share that duty: k-block k is prefetched by the
+    // CTA with m_tile % pf_share == k % pf_share.
+    // Measured inside the step: 5.126 ms without, 5.203 ms with the prefetch boxes -- every cp.async.bulk.* instruction costs the
+    // issuing producer thread a few hundred cycles, which is what paces the main loop; kept behind kPrefetch for a third thread.
+    constexpr int kPrefetch = 0;
+    auto prefetch_b = [&](int k) {
+        if (k < p.num_k_blocks && k % p.pf_share == pr_me) {
+            if (p.w_kmajor) ptx::tma_prefetch_3d(&p.tmB, 0, pr_n0, k);
+            else ptx::tma_prefetch_2d(&p.tmB, k * BLOCK_K, pr_n0);
+        }
+    };
+    // what: bit 0 = issue the A load, bit 1 = issue the B load, 0 = only advance the cursor (the B producer skips the first ring,
+    // which thread 0 issued in full before the prologue sync)
+    auto produce = [&](int limit, const int what) {
+        const bool load_a = what & 1, load_b = what & 2;
+        while (limit > 0 && pr_tile < p.num_tiles) {
+            if (pr_kb == 0) {   // new tile
+                const int m_tile = pr_tile / p.n_tiles, n_tile = pr_tile - m_tile * p.n_tiles;
+                pr_m0 = m_tile * BLOCK_M;
+                pr_n0 = n_tile * p.block_n;
+                if (p.conv) {
+                    if (p.tile_n > 1) { pr_img = m_tile * p.tile_n; pr_y0 = 0; }
+                    else { pr_img = m_tile / p.tiles_y; pr_y0 = (m_tile - pr_img * p.tiles_y) * p.tile_h; }
+                }
+                pr_tap = 0;
+                pr_cb = 0;
+                pr_me = m_tile % p.pf_share;
+                if (load_b)
+                    for (int k = p.stages; k < kPrefetch; ++k) prefetch_b(k);   // k-blocks [0, stages) are loaded right away, [kPrefetch, ..) follow the loads
+            }
+            uint64_t* fb = &full_bar[pr_stage];
+            if (what) ptx::mbar_wait(&empty_bar[pr_stage], pr_phase ^ 1);
+            if (load_a) {
+                ptx::mbar_expect_tx(fb, (uint32_t)kABytes);      // full barriers count two arrivals: one per operand
+
+                uint8_t* dst_a = smem_a + (size_t)pr_stage * kABytes;
+                if (!p.conv) {
+                    if (pr_kb < p.cblocks0) ptx::tma_load_2d(dst_a, &p.tmA0, fb, pr_kb * BLOCK_K, pr_m0);
+                    else ptx::tma_load_2d(dst_a, &p.tmA1, fb, (pr_kb - p.cblocks0) * BLOCK_K, pr_m0);
+                } else {
+                    const int dy = pr_tap / 3 - 1, dx = pr_tap - (pr_tap / 3) * 3 - 1;
+                    if (pr_cb < p.cblocks0) ptx::tma_load_4d(dst_a, &p.tmA0, fb, pr_cb * BLOCK_K, dx, pr_y0 + dy, pr_img);
+                    else ptx::tma_load_4d(dst_a, &p.tmA1, fb, (pr_cb - p.cblocks0) * BLOCK_K, dx, pr_y0 + dy, pr_img);
+                }
+            }
+            if (load_b) {
+                ptx::mbar_expect_tx(fb, (uint32_t)b_bytes);
+                uint8_t* dst_b = smem_b + (size_t)pr_stage * b_bytes;
+                if (p.w_kmajor) ptx::tma_load_3d(dst_b, &p.tmB, fb, 0, pr_n0, pr_kb);
+                else ptx::tma_load_2d(dst_b, &p.tmB, fb, pr_kb * BLOCK_K, pr_n0);
+                if (kPrefetch > 0) prefetch_b(pr_kb + kPrefetch);
+            }
+            if (++pr_stage == p.stages) { pr_stage = 0; pr_phase ^= 1; }
+            if (++pr_cb == p.cblocks) { pr_cb = 0; ++pr_tap; }
+            if (++pr_kb == p.num_k_blocks) { pr_kb = 0; pr_tile += gridDim.x; }
+            --limit;
+        }
+    };
+    const bool is_prod_a = threadIdx.x == 0, is_prod_b = threadIdx.x == kPersistThreads - 32;
+
     ptx::pdl_trigger();
     if (threadIdx.x == 0) PTRACE(0);
     if (warp == 0 && lane == 0) {
@@ -775,7 +876,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) gemm_persist_kernel(const 
         if (p.cblocks0 != p.cblocks) ptx::prefetch_tmap(&p.tmA1);
         if (p.res_kind) ptx::prefetch_tmap(&p.tmRes);
         for (int s = 0; s < p.stages; ++s) {
-            ptx::mbar_init(&full_bar[s], 1);
+            ptx::mbar_init(&full_bar[s], 2);     // A producer + B producer
             ptx::mbar_init(&empty_bar[s], 1);
         }
         for (int s = 0; s < 2; ++s) {
@@ -784,6 +885,8 @@ __global__ void __launch_bounds__(kPersistThreads, 1) gemm_persist_kernel(const 
         }
         for (int s = 0; s < kEpiWarps * kMaxDepth; ++s) ptx::mbar_init(&rfull[s], 1);
         ptx::fence_barrier_init();
+        ptx::pdl_wait();          // the operands may be the previous kernel's output
+        produce(p.stages, 3);     // first ring, both operands; every ring slot is free: none of these waits blocks
     }
     if (warp == 1) {
         ptx::tmem_alloc(tmem_slot, p.tmem_cols);
@@ -797,40 +900,13 @@ __global__ void __launch_bounds__(kPersistThreads, 1) gemm_persist_kernel(const 
     if (threadIdx.x == 0) PTRACE(1);
 
     if (warp == 0) {
-        // ================= TMA producer =================
-        if (ptx::elect_one()) {
-            int stage = 0;
-            uint32_t phase = 0;
-            const uint32_t stage_tx = (uint32_t)(kABytes + b_bytes);
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-                const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
-                const int m0 = m_tile * BLOCK_M, n0 = n_tile * p.block_n;
-                int img = 0, y0 = 0;
-                if (p.conv) {
-                    if (p.tile_n > 1) { img = m_tile * p.tile_n; y0 = 0; }
-                    else { img = m_tile / p.tiles_y; y0 = (m_tile - img * p.tiles_y) * p.tile_h; }
-                }
-                for (int kb = 0; kb < p.num_k_blocks; ++kb) {
-                    ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-                    uint64_t* fb = &full_bar[stage];
-                    ptx::mbar_expect_tx(fb, stage_tx);
-                    uint8_t* dst_a = smem_a + (size_t)stage * kABytes;
-                    uint8_t* dst_b = smem_b + (size_t)stage * b_bytes;
-                    if (!p.conv) {
-                        if (kb < p.cblocks0) ptx::tma_load_2d(dst_a, &p.tmA0, fb, kb * BLOCK_K, m0);
-                        else ptx::tma_load_2d(dst_a, &p.tmA1, fb, (kb - p.cblocks0) * BLOCK_K, m0);
-                    } else {
-                        const int tap = kb / p.cblocks;
-                        const int cb = kb - tap * p.cblocks;
-                        const int dy = tap / 3 - 1, dx = tap % 3 - 1;
-                        if (cb < p.cblocks0) ptx::tma_load_4d(dst_a, &p.tmA0, fb, cb * BLOCK_K, dx, y0 + dy, img);
-                        else ptx::tma_load_4d(dst_a, &p.tmA1, fb, (cb - p.cblocks0) * BLOCK_K, dx, y0 + dy, img);
-                    }
-                    if (p.w_kmajor) ptx::tma_load_3d(dst_b, &p.tmB, fb, 0, n0, kb);
-                    else ptx::tma_load_2d(dst_b, &p.tmB, fb, kb * BLOCK_K, n0);
-                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
-                }
-            }
+        // ================= TMA producer of the A tiles (its first ring of loads went out before the CTA-wide sync above) =================
+        if (is_prod_a) produce(0x7fffffff, 1);
+    } else if (warp == kPersistThreads / 32 - 1) {
+        // ================= TMA producer of the B (weight) tiles =================
+        if (is_prod_b) {
+            produce(p.stages, 0);      // thread 0 issued the first ring
+            produce(0x7fffffff, 2);
         }
     } else if (warp == 1) {
         // ================= MMA issuer (one elected thread) =================
@@ -954,6 +1030,7 @@ int configure_gemm_kernels() {
 // ---- persistent path (gemm_persist_kernel): tile width, eligibility, launch ----
 bool persist_enabled() {
     static const bool off = getenv("B200SD_PERSIST") && getenv("B200SD_PERSIST")[0] == '0';
+    if (g_dbg[0] >= 0) return g_dbg[0] != 0;
     return !off;
 }
 // Tile width for the persistent kernel: a multiple of 32 (its epilogue chunk; 64 for GEGLU: values | gates) dividing N.
@@ -988,7 +1065,15 @@ int launch_persist(const b200sd_gemm_args* a, const KParams& k, int m_tiles, b20
     p.geglu = k.epilogue == B200SD_EPI_GEGLU;
     p.out_f32 = k.out_f32;
     p.res_kind = k.residual ? (k.res_f32 ? 2 : 1) : 0;
+    {
+        const int sms_ = b200sd_num_sms();
+        const int grid_ = p.num_tiles < sms_ ? p.num_tiles : sms_;
+        int share = grid_ / p.n_tiles;
+        if (share > m_tiles) share = m_tiles;
+        p.pf_share = share < 1 ? 1 : share;
+    }
     p.depth = p.res_kind ? kMaxDepth : 2;
+    if (p.res_kind && g_dbg[3] >= 2 && g_dbg[3] <= kMaxDepth) p.depth = g_dbg[3];
     const int bn = k.block_n;
     p.acc_stride = bn <= 128 ? 128 : 256;
     p.tmem_cols = 2 * p.acc_stride;
@@ -1020,6 +1105,7 @@ int launch_persist(const b200sd_gemm_args* a, const KParams& k, int m_tiles, b20
     const int budget = 227 * 1024 - 1024;
     int stages = (budget - epi_bytes - bias_bytes - stat_bytes - bars_bytes) / stage_bytes;
     if (stages > kMaxStages) stages = kMaxStages;
+    if (g_dbg[1] > 0 && g_dbg[1] < stages) stages = g_dbg[1];
     B200SD_REQUIRE(stages >= 2, "gemm(persistent): smem budget leaves %d stages for block_n %d", stages, bn);
     p.stages = stages;
     p.off_b = (uint32_t)stages * kABytes;
@@ -1035,7 +1121,9 @@ int launch_persist(const b200sd_gemm_args* a, const KParams& k, int m_tiles, b20
     }
     const int sms = b200sd_num_sms();
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(p.num_tiles < sms ? p.num_tiles : sms);
+    int grid = p.num_tiles < sms ? p.num_tiles : sms;
+    if (g_dbg[2] > 0 && g_dbg[2] < grid) grid = g_dbg[2];
+    cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(kPersistThreads);
     cfg.dynamicSmemBytes = smem_bytes;
     cfg.stream = static_cast<cudaStream_t>(stream);
@@ -1066,6 +1154,7 @@ int launch_gemm(KParams& p, int m_tiles, int n_tiles, int grid_z, bool cluster, 
     if (stages > kMaxStages) stages = kMaxStages;
     if (stages > p.kb_per_split && total_ctas <= sms) stages = p.kb_per_split;
     const int min_stages = ceil_div(BLOCK_M * (bn + 4) * (int)sizeof(float), stage_bytes);  // epilogue staging tile
+    if (g_dbg[1] > 0 && g_dbg[1] < stages) stages = g_dbg[1];
     if (stages < min_stages) stages = min_stages;
     if (stages < 2) stages = 2;
     p.stages = stages;
@@ -1161,7 +1250,10 @@ extern "C" size_t b200sd_gemm_workspace_bytes(void) { return 0; }  // split-K re
 
 extern "C" int b200sd_geglu_tile(int N) {
     // the persistent kernel moves 32-column chunks of values and gates: tile = [tile/2 values | tile/2 gates], tile % 64 == 0
-    if (persist_enabled()) {
+    // ... except for the widest feed-forward (N = 8C = 10240, only ever run at M <= 512 rows at 64x64 latents): 160 tiles of 256
+    // columns on 148 SMs would leave a second, nearly empty round; it keeps the 160-wide tiles of gemm_tcgen05_kernel (measured
+    // with cold weights: 19.2 us vs 24.9 persistent)
+    if (persist_enabled() && N < 10240) {
         if (N % 256 == 0) return 256;
         if (N % 128 == 0) return 128;
         if (N % 64 == 0) return 64;
@@ -1235,7 +1327,21 @@ static int gemm_tiling(const b200sd_gemm_args* a, KParams& p, int* m_tiles_out, 
         (!a->rowbias || (a->rows_per_image > 0 && a->rows_per_image % 32 == 0)) &&
         !(a->residual && a->residual == a->out && a->residual_dtype != a->out_dtype)) {
         const int bnp = a->block_n > 0 ? a->block_n : pick_block_n_persist(a->N, m_tiles, geglu);
-        if (bnp > 0 && bnp <= 256 && bnp % (geglu ? 64 : 32) == 0 && a->N % bnp == 0) {
+        // WHERE the persistent kernel is used.  Measured on B200 inside the real step and with a cold-weight probe
+        // (tools/cold_probe.py: every launch reads a different copy of the weights, as in the step where 1.7 GB of weights
+        // stream through the 126 MB L2): it wins where a CTA walks >= 2 tiles -- GEGLU feed-forward M8192 N2560 K320 35.0 ->
+        // 23.4 us, M2048 N5120 K640 24.4 -> 21.8, fused QKV M8192 N960 K320 14.8 -> 12.2 -- because the epilogue of tile i
+        // overlaps the main loop of tile i+1 and no CTA is launched / set up per tile.  On one-tile-per-CTA grids (<= 148
+        // tiles) the critical path is load latency -> MMAs -> epilogue either way, the deeper ring of gemm_tcgen05_kernel
+        // (5-6 stages: nothing of its smem is set aside for epilogue chunks) hides the HBM latency of the cold weights better,
+        // and the persistent kernel measured level or slower (M8192 N320 K1280 12.4 -> 14.1 us): those grids stay there.
+        // B200SD_PERSIST_MASK (A/B switch): 1 = GEGLU, 2 = multi-round plain GEMMs / convs, 4 = one-round grids
+        const long ptiles = bnp > 0 ? (long)m_tiles * (a->N / bnp) : 0;
+        const int sms_p = b200sd_num_sms();
+        static const int mask = [] { const char* e = getenv("B200SD_PERSIST_MASK"); return e ? atoi(e) : 3; }();
+        const bool multi = ptiles >= 2L * sms_p;
+        const int cls = !multi ? 4 : (geglu ? 1 : 2);
+        if (bnp > 0 && bnp <= 256 && bnp % (geglu ? 64 : 32) == 0 && a->N % bnp == 0 && ((mask & cls) || g_dbg[0] > 0)) {
             p.persist = 1;
             p.block_n = bnp;
             *n_tiles_out = a->N / bnp;

@@ -45,7 +45,7 @@ class FlatParams:
        grad   fp32  every parameter's gradient (accumulated by the backward kernels)
     state_dict() / load_state_dict() / torch optimizers keep working on the re-homed parameters."""
 
-    def __init__(self, model, device):
+    def __init__(self, model, device, lazy=False):
         self.model, self.device = model, device
         self.regs = {}        # id(param) -> _Reg
         self.order = []
@@ -129,29 +129,23 @@ class FlatParams:
             raise B200SDError(f"FlatParams: parameters not laid out: {missing[:4]}...")
         self.total = off
         self.master = torch.zeros(off, dtype=F32, device=device)
-        self.grad = torch.zeros(off, dtype=F32, device=device)
-        self.wb = torch.zeros(off, dtype=BF16, device=device)
+        self.grad = self.wb = None           # allocated by materialize() at the first training forward
         for r in self.order:
             p = r.param
-            sl = slice(r.off, r.off + r.numel)
-            g, w, mst = self.grad[sl], self.wb[sl], self.master[sl]
-            r.wb = r.wf = None
+            mst = self.master[r.off:r.off + r.numel]
+            r.wb = r.wf = r.g = r.gview = None
             if r.kind in ("conv3", "conv_f32"):
                 co, ci, kh, kw = p.shape
                 r.shape2d = (co, kh * kw * ci)
-                r.g = g.view(r.shape2d)
-                r.gview = g.view(co, kh, kw, ci).permute(0, 3, 1, 2)
                 r.pview = mst.view(co, kh, kw, ci).permute(0, 3, 1, 2)
-                if r.kind == "conv3":
-                    r.wb = w.view(r.shape2d)
-                else:
+                if r.kind == "conv_f32":
                     r.wf = mst.view(r.shape2d)       # the CUDA-core end convs read the fp32 master directly
             elif r.kind == "lin":
                 r.shape2d = (p.shape[0], p.numel() // p.shape[0])
-                r.g, r.gview, r.pview, r.wb = g.view(r.shape2d), g.view(p.shape), mst.view(p.shape), w.view(r.shape2d)
+                r.pview = mst.view(p.shape)
             else:
                 r.shape2d = (p.numel(),)
-                r.g, r.gview, r.pview = g, g.view(p.shape), mst.view(p.shape)
+                r.pview = mst.view(p.shape)
         # re-home the parameters into the flat master buffer (Parameter identity is preserved)
         with torch.no_grad():
             for r in self.order:
@@ -160,6 +154,35 @@ class FlatParams:
                     r.param.data = r.pview
                 r.src = (r.param.data.data_ptr(), r.param.dtype)
         self._versions = None
+        if not lazy:
+            self.materialize()
+
+    def materialize(self):
+        """Allocate the training-only state: the flat fp32 gradient buffer and the bf16 tensor-core copy of the weights.  (The
+        master buffer alone is set up as soon as the model lands on the GPU -- unet.to(device) -- so that whoever wraps the model
+        afterwards, e.g. DistributedDataParallel via accelerator.prepare (finetune_sd.py:363, 386), sees the parameters' FINAL
+        strides: the 3x3 conv weights are permuted views of their kernel-layout storage.)"""
+        if self.grad is not None:
+            return self
+        dev = self.master.device
+        self.grad = torch.zeros(self.total, dtype=F32, device=dev)
+        self.wb = torch.zeros(self.total, dtype=BF16, device=dev)
+        for r in self.order:
+            p = r.param
+            sl = slice(r.off, r.off + r.numel)
+            g, w = self.grad[sl], self.wb[sl]
+            if r.kind in ("conv3", "conv_f32"):
+                co, ci, kh, kw = p.shape
+                r.g = g.view(r.shape2d)
+                r.gview = g.view(co, kh, kw, ci).permute(0, 3, 1, 2)
+                if r.kind == "conv3":
+                    r.wb = w.view(r.shape2d)
+            elif r.kind == "lin":
+                r.g, r.gview, r.wb = g.view(r.shape2d), g.view(p.shape), w.view(r.shape2d)
+            else:
+                r.g, r.gview = g, g.view(p.shape)
+        self._versions = None
+        return self
 
     def reg(self, p) -> _Reg:
         return self.regs[id(p)]
@@ -283,6 +306,12 @@ class TrainEngine:
     def Wb(self, p):
         return self.flat.reg(p).wb
 
+    def P(self, p):
+        """fp32 view of parameter p in the flat master buffer -- what the kernels read for biases / norm affines.  (For a re-homed
+        fp32 parameter this IS p.data; a frozen fp16 / bf16 parameter keeps its own storage and the master holds the upcast copy.)"""
+        r = self.flat.reg(p)
+        return r.pview if r.pview.is_contiguous() else r.param.data
+
     def _prep(self, g, want_bf16=True, bias_param=None, **kw):
         """bwd: bf16 copy of fp32 gradient g (+ bias gradient)"""
         out = self.pool.get(g.shape[0], g.shape[1]) if want_bf16 and g.dtype == F32 else None
@@ -327,8 +356,8 @@ class TrainEngine:
         self.tproj = torch.empty(N, n_tp, **f32)
         self.d_tproj = torch.zeros(N, n_tp, **f32)
         Fp.append(lambda: ops.timestep_embedding(self.in_t, boc[0], out=t_sin))
-        Fp.append(lambda: ops.small_linear(t_sin, self.Wb(te.linear_1.weight), te.linear_1.bias, out=t_h1))
-        Fp.append(lambda: ops.small_linear(t_h1, self.Wb(te.linear_2.weight), te.linear_2.bias, silu_in=True, out=t_emb))
+        Fp.append(lambda: ops.small_linear(t_sin, self.Wb(te.linear_1.weight), self.P(te.linear_1.bias), out=t_h1))
+        Fp.append(lambda: ops.small_linear(t_h1, self.Wb(te.linear_2.weight), self.P(te.linear_2.bias), silu_in=True, out=t_emb))
         Fp.append(lambda: ops.small_linear(t_emb, tp_w, tp_b, silu_in=True, out=self.tproj))
 
         self.attn_ws = torch.empty(ops.attention_workspace_bytes(N, heads, self.H * self.W, max(boc[0] // heads, 8)) + 256,
@@ -346,19 +375,19 @@ class TrainEngine:
             t1 = self._new(M, cin)
             raw = self._new(M, cin) if has_sc else None
             st1, st2 = torch.empty(N, 32, 2, **f32), torch.empty(N, 32, 2, **f32)   # GroupNorm (mean, rstd), kept for the backward
-            Fp.append(lambda: ops.groupnorm_silu(x, skip, r.norm1.weight, r.norm1.bias, t1, N, hw, 32, eps, True, raw_out=raw, stats_out=st1))
+            Fp.append(lambda: ops.groupnorm_silu(x, skip, self.P(r.norm1.weight), self.P(r.norm1.bias), t1, N, hw, 32, eps, True, raw_out=raw, stats_out=st1))
             hbuf = self._new(M, cout, F32)
             rb = (self.tproj.data_ptr() + tp_off[prefix] * 4, n_tp, hw)
-            self._gemm(Fp, t1, self.Wb(r.conv1.weight), hbuf, bias=r.conv1.bias, conv=(N, h, w), rowbias_ptr=rb)
+            self._gemm(Fp, t1, self.Wb(r.conv1.weight), hbuf, bias=self.P(r.conv1.bias), conv=(N, h, w), rowbias_ptr=rb)
             t2 = self._new(M, cout)
-            Fp.append(lambda: ops.groupnorm_silu(hbuf, None, r.norm2.weight, r.norm2.bias, t2, N, hw, 32, eps, True, stats_out=st2))
+            Fp.append(lambda: ops.groupnorm_silu(hbuf, None, self.P(r.norm2.weight), self.P(r.norm2.bias), t2, N, hw, 32, eps, True, stats_out=st2))
             if has_sc:
                 sc = self._new(M, cout, F32)
-                self._gemm(Fp, raw, self.Wb(r.conv_shortcut.weight), sc, bias=r.conv_shortcut.bias)
+                self._gemm(Fp, raw, self.Wb(r.conv_shortcut.weight), sc, bias=self.P(r.conv_shortcut.bias))
             else:
                 sc = x
             y = self._new(M, cout, F32)
-            self._gemm(Fp, t2, self.Wb(r.conv2.weight), y, bias=r.conv2.bias, residual=sc, conv=(N, h, w))
+            self._gemm(Fp, t2, self.Wb(r.conv2.weight), y, bias=self.P(r.conv2.bias), residual=sc, conv=(N, h, w))
 
             def backward():
                 pool = self.pool
@@ -368,7 +397,7 @@ class TrainEngine:
                 dt2 = pool.get(M, cout)
                 self._dgrad(dy16, self.Wb(r.conv2.weight), dt2, conv=(N, h, w))
                 dh16 = pool.get(M, cout)
-                Bp.append(lambda: ops.groupnorm_silu_bwd(hbuf, None, r.norm2.weight, r.norm2.bias, dt2, dh16, None, N, hw,
+                Bp.append(lambda: ops.groupnorm_silu_bwd(hbuf, None, self.P(r.norm2.weight), self.P(r.norm2.bias), dt2, dh16, None, N, hw,
                                                          dgamma=self.G(r.norm2.weight), dbeta=self.G(r.norm2.bias), eps=eps, silu=True,
                                                          mean_rstd=st2))
                 pool.put(dt2)
@@ -391,7 +420,7 @@ class TrainEngine:
                     add = dy
                 gx, accx = self._grad_of(x)
                 gs, accs = self._grad_of(skip) if skip is not None else (None, False)
-                Bp.append(lambda: ops.groupnorm_silu_bwd(x, skip, r.norm1.weight, r.norm1.bias, dt1, gx, gs, N, hw, add_src=add,
+                Bp.append(lambda: ops.groupnorm_silu_bwd(x, skip, self.P(r.norm1.weight), self.P(r.norm1.bias), dt1, gx, gs, N, hw, add_src=add,
                                                          acc0=accx, acc1=accs, dgamma=self.G(r.norm1.weight),
                                                          dbeta=self.G(r.norm1.bias), eps=eps, silu=True, mean_rstd=st1))
                 pool.put(dt1, dy16 if dy16 is not dy else None, add if add is not dy else None)
@@ -411,12 +440,12 @@ class TrainEngine:
             w_kv2 = flat.span([a2m.to_k.weight, a2m.to_v.weight], "wb")
             t = self._new(M, Cc)
             st = torch.empty(N, 32, 2, **f32)
-            Fp.append(lambda: ops.groupnorm_silu(x, None, a.norm.weight, a.norm.bias, t, N, hw, 32, 1e-6, False, stats_out=st))
+            Fp.append(lambda: ops.groupnorm_silu(x, None, self.P(a.norm.weight), self.P(a.norm.bias), t, N, hw, 32, 1e-6, False, stats_out=st))
             hs0 = self._new(M, Cc, F32)
-            self._gemm(Fp, t, self.Wb(a.proj_in.weight), hs0, bias=a.proj_in.bias)
+            self._gemm(Fp, t, self.Wb(a.proj_in.weight), hs0, bias=self.P(a.proj_in.bias))
             # self attention
             n1 = self._new(M, Cc)
-            Fp.append(lambda: ops.layernorm(hs0, blk.norm1.weight, blk.norm1.bias, n1))
+            Fp.append(lambda: ops.layernorm(hs0, self.P(blk.norm1.weight), self.P(blk.norm1.bias), n1))
             qkv = self._new(M, 3 * Cc)
             self._gemm(Fp, n1, w_qkv, qkv)
             at1 = self._new(M, Cc)
@@ -424,10 +453,10 @@ class TrainEngine:
             Fp.append(lambda: ops.attention_lse(qkv, qkv, qkv, at1, lse1, N, heads, hw, hw, d, scale, ldq=3 * Cc, ldk=3 * Cc,
                                                 ldv=3 * Cc, ldo=Cc, k_off=Cc, v_off=2 * Cc, ws=self.attn_ws))
             hs1 = self._new(M, Cc, F32)
-            self._gemm(Fp, at1, self.Wb(a1m.to_out[0].weight), hs1, bias=a1m.to_out[0].bias, residual=hs0)
+            self._gemm(Fp, at1, self.Wb(a1m.to_out[0].weight), hs1, bias=self.P(a1m.to_out[0].bias), residual=hs0)
             # cross attention
             n2 = self._new(M, Cc)
-            Fp.append(lambda: ops.layernorm(hs1, blk.norm2.weight, blk.norm2.bias, n2))
+            Fp.append(lambda: ops.layernorm(hs1, self.P(blk.norm2.weight), self.P(blk.norm2.bias), n2))
             q2 = self._new(M, Cc)
             self._gemm(Fp, n2, self.Wb(a2m.to_q.weight), q2)
             kv = self._new(N * S, 2 * Cc)
@@ -437,18 +466,18 @@ class TrainEngine:
             Fp.append(lambda: ops.attention_lse(q2, kv, kv, at2, lse2, N, heads, hw, S, d, scale, ldq=Cc, ldk=2 * Cc, ldv=2 * Cc,
                                                 ldo=Cc, v_off=Cc, ws=self.attn_ws))
             hs2 = self._new(M, Cc, F32)
-            self._gemm(Fp, at2, self.Wb(a2m.to_out[0].weight), hs2, bias=a2m.to_out[0].bias, residual=hs1)
+            self._gemm(Fp, at2, self.Wb(a2m.to_out[0].weight), hs2, bias=self.P(a2m.to_out[0].bias), residual=hs1)
             # GEGLU feed-forward (pre-activation kept)
             n3 = self._new(M, Cc)
-            Fp.append(lambda: ops.layernorm(hs2, blk.norm3.weight, blk.norm3.bias, n3))
+            Fp.append(lambda: ops.layernorm(hs2, self.P(blk.norm3.weight), self.P(blk.norm3.bias), n3))
             u = self._new(M, 8 * Cc)
-            self._gemm(Fp, n3, self.Wb(ff.net[0].proj.weight), u, bias=ff.net[0].proj.bias)
+            self._gemm(Fp, n3, self.Wb(ff.net[0].proj.weight), u, bias=self.P(ff.net[0].proj.bias))
             f = self._new(M, 4 * Cc)
             Fp.append(lambda: ops.geglu_fwd(u, f))
             hs3 = self._new(M, Cc)
-            self._gemm(Fp, f, self.Wb(ff.net[2].weight), hs3, bias=ff.net[2].bias, residual=hs2)
+            self._gemm(Fp, f, self.Wb(ff.net[2].weight), hs3, bias=self.P(ff.net[2].bias), residual=hs2)
             y = self._new(M, Cc, F32)
-            self._gemm(Fp, hs3, self.Wb(a.proj_out.weight), y, bias=a.proj_out.bias, residual=x)
+            self._gemm(Fp, hs3, self.Wb(a.proj_out.weight), y, bias=self.P(a.proj_out.bias), residual=x)
 
             def backward():
                 pool = self.pool
@@ -473,7 +502,7 @@ class TrainEngine:
                 dn = pool.get(M, Cc)
                 self._dgrad(du, self.Wb(ff.net[0].proj.weight), dn)
                 pool.put(du)
-                Bp.append(lambda: ops.layernorm_bwd(hs2, blk.norm3.weight, dn, dhs, self.G(blk.norm3.weight), self.G(blk.norm3.bias)))
+                Bp.append(lambda: ops.layernorm_bwd(hs2, self.P(blk.norm3.weight), dn, dhs, self.G(blk.norm3.weight), self.G(blk.norm3.bias)))
                 # cross attention
                 g16 = self._prep(dhs, bias_param=a2m.to_out[0].bias if tw else None)
                 self._wgrad(g16, at2, self.G(a2m.to_out[0].weight))
@@ -493,7 +522,7 @@ class TrainEngine:
                     self._dgrad(dkv, w_kv2, self.d_ctx, residual=self.d_ctx if ctx_state["init"] else None)
                     ctx_state["init"] = True
                 pool.put(dq2, dkv)
-                Bp.append(lambda: ops.layernorm_bwd(hs1, blk.norm2.weight, dn, dhs, self.G(blk.norm2.weight), self.G(blk.norm2.bias)))
+                Bp.append(lambda: ops.layernorm_bwd(hs1, self.P(blk.norm2.weight), dn, dhs, self.G(blk.norm2.weight), self.G(blk.norm2.bias)))
                 # self attention
                 g16 = self._prep(dhs, bias_param=a1m.to_out[0].bias if tw else None)
                 self._wgrad(g16, at1, self.G(a1m.to_out[0].weight))
@@ -508,14 +537,14 @@ class TrainEngine:
                     self._wgrad(dqkv, n1, flat.span([a1m.to_q.weight, a1m.to_k.weight, a1m.to_v.weight], "grad"))
                 self._dgrad(dqkv, w_qkv, dn)
                 pool.put(dqkv)
-                Bp.append(lambda: ops.layernorm_bwd(hs0, blk.norm1.weight, dn, dhs, self.G(blk.norm1.weight), self.G(blk.norm1.bias)))
+                Bp.append(lambda: ops.layernorm_bwd(hs0, self.P(blk.norm1.weight), dn, dhs, self.G(blk.norm1.weight), self.G(blk.norm1.bias)))
                 # proj_in + GroupNorm
                 g16 = self._prep(dhs, bias_param=a.proj_in.bias if tw else None)
                 self._wgrad(g16, t, self.G(a.proj_in.weight))
                 self._dgrad(g16, self.Wb(a.proj_in.weight), dn)
                 pool.put(g16, dhs)
                 gx, accx = self._grad_of(x)
-                Bp.append(lambda: ops.groupnorm_silu_bwd(x, None, a.norm.weight, a.norm.bias, dn, gx, None, N, hw, add_src=dy,
+                Bp.append(lambda: ops.groupnorm_silu_bwd(x, None, self.P(a.norm.weight), self.P(a.norm.bias), dn, gx, None, N, hw, add_src=dy,
                                                          acc0=accx, dgamma=self.G(a.norm.weight), dbeta=self.G(a.norm.bias),
                                                          eps=1e-6, silu=False, mean_rstd=st))
                 pool.put(dn)
@@ -528,7 +557,7 @@ class TrainEngine:
             col = self._new(N * (h // 2) * (w // 2), 9 * Cc)
             Fp.append(lambda: ops.im2col_s2(x, col, N, h, w))
             y = self._new(N * (h // 2) * (w // 2), Cc, F32)
-            self._gemm(Fp, col, self.Wb(ds.conv.weight), y, bias=ds.conv.bias)
+            self._gemm(Fp, col, self.Wb(ds.conv.weight), y, bias=self.P(ds.conv.bias))
 
             def backward():
                 dy = self._grad_ready(y)
@@ -548,7 +577,7 @@ class TrainEngine:
             up = self._new(N * 4 * h * w, Cc)
             Fp.append(lambda: ops.upsample2x(x, up, N, h, w))
             y = self._new(N * 4 * h * w, Cc, F32)
-            self._gemm(Fp, up, self.Wb(us.conv.weight), y, bias=us.conv.bias, conv=(N, 2 * h, 2 * w))
+            self._gemm(Fp, up, self.Wb(us.conv.weight), y, bias=self.P(us.conv.bias), conv=(N, 2 * h, 2 * w))
 
             def backward():
                 dy = self._grad_ready(y)
@@ -567,7 +596,7 @@ class TrainEngine:
         h, w = self.H, self.W
         ci_w = flat.reg(m.conv_in.weight)
         x0 = self._new(N * h * w, boc[0], F32)
-        Fp.append(lambda: ops.conv_in(self.in_sample, ci_w.wf, m.conv_in.bias, x0))
+        Fp.append(lambda: ops.conv_in(self.in_sample, ci_w.wf, self.P(m.conv_in.bias), x0))
 
         def conv_in_backward():
             if not tw:
@@ -618,9 +647,9 @@ class TrainEngine:
         x_last = x
         t_out = self._new(N * h * w, boc[0])
         st_out = torch.empty(N, 32, 2, **f32)
-        Fp.append(lambda: ops.groupnorm_silu(x_last, None, m.conv_norm_out.weight, m.conv_norm_out.bias, t_out, N, h * w, 32, eps, True,
+        Fp.append(lambda: ops.groupnorm_silu(x_last, None, self.P(m.conv_norm_out.weight), self.P(m.conv_norm_out.bias), t_out, N, h * w, 32, eps, True,
                                              stats_out=st_out))
-        Fp.append(lambda: ops.conv_out(t_out, co_w.wf, m.conv_out.bias, self.out))
+        Fp.append(lambda: ops.conv_out(t_out, co_w.wf, self.P(m.conv_out.bias), self.out))
 
         # ---- backward graph: head, then the blocks in reverse, then the time MLP ----
         hw = h * w
@@ -640,7 +669,7 @@ class TrainEngine:
         Bp.append(lambda: ops.conv_out_bwd(self.d_out, t_out, co_w.wf, dt_out, co_w.g if (tw and not tc_wgrad) else None,
                                            self.G(m.conv_out.bias) if not tc_wgrad else None))
         gx, _ = self._grad_of(x_last)
-        Bp.append(lambda: ops.groupnorm_silu_bwd(x_last, None, m.conv_norm_out.weight, m.conv_norm_out.bias, dt_out, gx, None, N, hw,
+        Bp.append(lambda: ops.groupnorm_silu_bwd(x_last, None, self.P(m.conv_norm_out.weight), self.P(m.conv_norm_out.bias), dt_out, gx, None, N, hw,
                                                  dgamma=self.G(m.conv_norm_out.weight), dbeta=self.G(m.conv_norm_out.bias),
                                                  eps=eps, silu=True, mean_rstd=st_out))
         self.pool.put(dt_out)

@@ -253,7 +253,21 @@ class UNet2DConditionModel(nn.Module):
         self._engines = {}
         self._flat = None
         self._train_engines = {}
+        self._rehome()
         return r
+
+    def _rehome(self):
+        """As soon as the fp32 parameters sit on a GPU, move them into the flat kernel-layout master buffer (train.FlatParams:
+        every Parameter becomes a view of it; 3x3 conv weights permuted views).  Doing this at .to(device) time -- not lazily at
+        the first training forward -- matters for wrappers that record the parameters' strides when they are constructed:
+        DistributedDataParallel (accelerator.prepare, finetune_sd.py:363, 386) builds its gradient buckets from them, and
+        gradients whose strides differ from what it saw come back corrupted (found by tests/test_dropin_gpu.py)."""
+        ps = list(self.parameters())
+        if not ps or any((not p.is_cuda) or p.dtype != torch.float32 or p.device != ps[0].device for p in ps):
+            return
+        from .train import FlatParams
+        with torch.cuda.device(ps[0].device):
+            self._flat = FlatParams(self, ps[0].device, lazy=True)
 
     def set_precision(self, precision: str):
         """"bf16": the fast plan (noise prediction within 1e-2 of the fp32 reference).  "fp32": the accuracy plan
@@ -277,7 +291,7 @@ class UNet2DConditionModel(nn.Module):
         return None if self._flat is None else self._flat.grad
 
     def zero_grad(self, set_to_none: bool = True):
-        if self._direct_grads and self._flat is not None:
+        if self._direct_grads and self._flat is not None and self._flat.grad is not None:
             self._flat.zero_grad()
             self._flat.attach_grads()
             return
