@@ -49,6 +49,8 @@ __device__ __forceinline__ unsigned long long gtimer() {
     } while (0)
 
 constexpr int BLOCK_M = 128;
+constexpr size_t kWsPartialBytes = (size_t)160 * 128 * 256 * sizeof(float);   // split-K partial tiles (<= one per SM), see b200sd_gemm_workspace_bytes
+constexpr size_t kWsCounterBytes = 4096;
 constexpr int BLOCK_K = 64;  // 64 bf16 = 128 B = one swizzle row
 constexpr int UMMA_K = 16;
 constexpr int kNumThreads = 192;
@@ -92,6 +94,7 @@ struct KParams {
     int pair;            // CTA pair (cta_group::2): two CTAs adjacent in M form one 256 x block_n MMA tile; each loads its own
                          // 128 A rows and HALF of the B tile, so the L2 -> smem traffic per FLOP drops by ~1/3
     int persist;         // host only: this launch goes to gemm_persist_kernel (set by gemm_tiling)
+    int psplit;          // host only: ... in its split-K mode with this many K slices per tile (0 = no)
     int w_kmajor;        // forward B operand stored k-block-major [K/64][N][64]: one tile k-block = ONE contiguous bn x 128 B run of
                          // DRAM instead of bn 128-byte pieces a whole weight row (K * 2 B) apart
     float* gn_part;      // optional [m_tiles * split_k][2][N]: per-column (sum, sum of squares) of the rows each CTA stores --
@@ -542,6 +545,14 @@ struct PParams {
     int chunk_bytes;                // 4096: 32 rows x 128 B (an fp32 chunk is involved); 2048: 32 rows x 64 B (bf16 only)
     uint32_t tmem_cols, acc_stride;
     uint32_t off_b, off_epi, off_bias, off_stat, off_bars;   // byte offsets from the 1024-aligned smem base
+    // ---- split-K mode (small-M / deep-K layers): CTA u computes K slice u % split of tile u / split ----
+    int split, kb_per_split;
+    CUtensorMap tmWs;               // fp32 partial tiles in the workspace: [units * 128][block_n]
+    float* ws;                      // the same buffer, for the reduction's plain loads
+    int* cnt;                       // [2][num_tiles] arrival / departure counters (zero between launches: self-resetting)
+    const void* residual;           // raw pointers for the reduction phase
+    void* out;
+    int ldc, ldr;
     unsigned long long* trace;      // optional [ctas][8] globaltimer stamps (debug)
 };
 #define PTRACE(slot) do { if (p.trace) p.trace[(size_t)blockIdx.x * 16 + (slot)] = gtimer(); } while (0)
@@ -781,6 +792,153 @@ __device__ __forceinline__ void persist_epilogue(const PParams& p, uint8_t* smem
     if (ew == 0 && lane == 0) PTRACE(6);
 }
 
+// ---- split-K epilogue: K slice s of a tile.  Phase 1: the fp32 partial accumulator goes to the workspace (TMA stores, same
+// chunk machinery).  Then the `split` CTAs of the tile meet on an arrival counter in global memory (all CTAs of the grid are
+// co-resident: the launch is cooperative and has at most one CTA per SM).  Phase 2: CTA s owns rows [s * 128 / split, ...) of
+// the tile: it sums the `split` partials of those rows IN SLICE ORDER (deterministic), adds bias / time embedding / residual,
+// stores, and publishes the GroupNorm column statistics of its rows.  The partials never leave L2.
+// (The first design exchanged partials over distributed shared memory inside a thread-block cluster: at most 8 slices, clusters
+// of 8 placed badly -- 16 of them ran as two waves -- and the pull-style DSMEM reduction took longer than the main loop:
+// 10.5 of 22 us on the 8x8 convs.)
+template <bool OUT_F32, int RES, bool STATS>
+__device__ __forceinline__ void persist_epilogue_split(const PParams& p, uint8_t* smem, uint32_t tmem_base, int warp, int lane) {
+    const int ew = warp - 2, q = warp & 3, h = ew >> 2;
+    const int kChunkBytes = 4096;
+    uint8_t* my = smem + p.off_epi + (size_t)ew * 2 * kChunkBytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.off_bars);
+    uint64_t* tfull = bars + 16;
+    uint64_t* tempty = bars + 18;
+    const int unit = blockIdx.x, tile = unit / p.split, s = unit - tile * p.split;
+    const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
+    const int n0 = n_tile * p.block_n, m0 = m_tile * BLOCK_M;
+    const int nch = p.block_n >> 5;
+    const int nl = nch > h ? (nch - h + 1) >> 1 : 0;
+    // ---- phase 1: partial accumulator -> workspace ----
+    ptx::mbar_wait(&tfull[0], 0);
+    ptx::tc_fence_after();
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+    for (int l = 0; l < nl; ++l) {
+        const int ch = h + 2 * l;
+        uint8_t* cb = my + (l & 1) * kChunkBytes;
+        if (lane == 0) ptx::tma_store_wait_read<1>();
+        __syncwarp();
+        uint32_t r0[16], r1[16];
+        ptx::tmem_ld_32x32b_x16(taddr + ch * 32, r0);
+        ptx::tmem_ld_32x32b_x16(taddr + ch * 32 + 16, r1);
+        ptx::tmem_ld_wait();
+        uint8_t* row128 = cb + lane * 128;
+        const int x128 = lane & 7;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const uint32_t* r = j < 4 ? r0 : r1;
+            const int o = (j & 3) * 4;
+            *reinterpret_cast<uint4*>(row128 + ((j ^ x128) << 4)) = make_uint4(r[o], r[o + 1], r[o + 2], r[o + 3]);
+        }
+        ptx::fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+            ptx::tma_store_2d(&p.tmWs, cb, ch * 32, unit * BLOCK_M + q * 32);
+            ptx::tma_store_commit();
+        }
+    }
+    ptx::tc_fence_before();
+    __syncwarp();
+    if (lane == 0) {
+        ptx::mbar_arrive(&tempty[0]);
+        ptx::tma_store_wait<0>();        // this warp's partial rows are written
+        ptx::fence_proxy_async_global(); // async-proxy writes -> ordered before the generic-proxy release below
+        __threadfence();
+    }
+    ptx::named_bar_sync(1, kEpiWarps * 32);
+    const int te = ew * 32 + lane;
+    int* cnt_in = p.cnt + tile;
+    int* cnt_out = p.cnt + p.num_tiles + tile;
+    if (te == 0) {
+        atomicAdd(cnt_in, 1);
+        int seen;
+        long long t0 = clock64();
+        do {
+            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(cnt_in) : "memory");
+            if (clock64() - t0 > 4000000000LL) { printf("b200sd: split-K arrival wait timed out (unit %d)\n", unit); __trap(); }
+        } while (seen < p.split);
+        __threadfence();
+    }
+    ptx::named_bar_sync(1, kEpiWarps * 32);
+    // ---- phase 2: rows [s * rpc, (s + 1) * rpc) of the tile, all block_n columns ----
+    const int rpc = BLOCK_M / p.split;
+    const int groups = p.block_n >> 2;                 // float4 column groups
+    const int rslots = (kEpiWarps * 32) / groups < 4 ? (kEpiWarps * 32) / groups : 4;
+    const int c4 = te % groups, rslot = te / groups;
+    float* sstat = reinterpret_cast<float*>(smem + p.off_stat);   // [4][2][256]
+    float cs[4] = {0.f, 0.f, 0.f, 0.f}, cq[4] = {0.f, 0.f, 0.f, 0.f};
+    if (rslot < rslots) {
+        const int col = n0 + c4 * 4;
+        float4 b4 = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int r = rslot; r < rpc; r += rslots) {
+            const int trow = s * rpc + r;                // row inside the tile
+            const int grow = m0 + trow;
+            if (grow >= p.M) break;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            const float* src = p.ws + ((size_t)(tile * p.split) * BLOCK_M + trow) * p.block_n + c4 * 4;
+            for (int j = 0; j < p.split; ++j) {
+                const float4 t = __ldcg(reinterpret_cast<const float4*>(src + (size_t)j * BLOCK_M * p.block_n));
+                v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+            }
+            v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
+            if (p.rowbias) {
+                const float4 t = __ldg(reinterpret_cast<const float4*>(p.rowbias + (size_t)(grow / p.rows_per_image) * p.ldrb + col));
+                v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+            }
+            if constexpr (RES == 2) {
+                const float4 t = __ldcg(reinterpret_cast<const float4*>(static_cast<const float*>(p.residual) + (size_t)grow * p.ldr + col));
+                v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+            } else if constexpr (RES == 1) {
+                const uint2 u = __ldcg(reinterpret_cast<const uint2*>(static_cast<const bf16*>(p.residual) + (size_t)grow * p.ldr + col));
+                const float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y);
+                v.x += f0.x; v.y += f0.y; v.z += f1.x; v.w += f1.y;
+            }
+            if constexpr (STATS) {
+                cs[0] += v.x; cs[1] += v.y; cs[2] += v.z; cs[3] += v.w;
+                cq[0] = fmaf(v.x, v.x, cq[0]); cq[1] = fmaf(v.y, v.y, cq[1]); cq[2] = fmaf(v.z, v.z, cq[2]); cq[3] = fmaf(v.w, v.w, cq[3]);
+            }
+            if constexpr (OUT_F32) {
+                *reinterpret_cast<float4*>(static_cast<float*>(p.out) + (size_t)grow * p.ldc + col) = v;
+            } else {
+                uint2 u;
+                u.x = pack_bf16x2(v.x, v.y);
+                u.y = pack_bf16x2(v.z, v.w);
+                *reinterpret_cast<uint2*>(static_cast<bf16*>(p.out) + (size_t)grow * p.ldc + col) = u;
+            }
+        }
+    }
+    if constexpr (STATS) {
+        // column statistics of this CTA's rows: the row slots folded in a fixed order; partial row = m_tile * split + s (the
+        // n-tiles of a row band write disjoint column ranges of the same partial row)
+        if (rslot < 4) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { sstat[rslot * 512 + c4 * 4 + i] = cs[i]; sstat[rslot * 512 + 256 + c4 * 4 + i] = cq[i]; }
+        }
+        ptx::named_bar_sync(1, kEpiWarps * 32);
+        if (te < p.block_n) {
+            float s0 = 0.f, s1 = 0.f;
+            for (int rs = 0; rs < rslots; ++rs) { s0 += sstat[rs * 512 + te]; s1 += sstat[rs * 512 + 256 + te]; }
+            float* dst = p.gn_part + (size_t)(m_tile * p.split + s) * 2 * p.N + n0 + te;
+            dst[0] = s0;
+            dst[p.N] = s1;
+        }
+    }
+    // ---- departure: the last CTA of the tile to finish reading re-arms both counters for the next launch ----
+    ptx::named_bar_sync(1, kEpiWarps * 32);
+    if (te == 0) {
+        __threadfence();
+        if (atomicAdd(cnt_out, 1) == p.split - 1) {
+            *cnt_out = 0;
+            *cnt_in = 0;
+            __threadfence();
+        }
+    }
+}
+
 __global__ void __launch_bounds__(kPersistThreads, 1) gemm_persist_kernel(const __grid_constant__ PParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -803,7 +961,15 @@ __global__ void __launch_bounds__(kPersistThreads, 1) gemm_persist_kernel(const 
     // ~300 cycles of index arithmetic per k-block to the single producer slowed an M8192 K2880 conv from 22.6 to 33.1 us).
     // All per-tile index arithmetic is hoisted out of the k loop; the first ring of loads is issued BEFORE the CTA-wide prologue
     // sync, so the load latency of the first tile overlaps the TMEM allocation and the barrier hand-shake. ----
-    int pr_stage = 0, pr_tile = blockIdx.x, pr_kb = 0, pr_m0 = 0, pr_n0 = 0, pr_img = 0, pr_y0 = 0, pr_tap = 0, pr_cb = 0, pr_me = 0;
+    const bool splitk = p.split > 1;
+    // work items: whole tiles blockIdx.x, blockIdx.x + gridDim.x, ... -- or, in split-K mode, ONE K slice of one tile
+    const int sk_tile = splitk ? (int)blockIdx.x / p.split : 0, sk_s = splitk ? (int)blockIdx.x - sk_tile * p.split : 0;
+    // slice s = k-blocks [s * nkb / split, (s + 1) * nkb / split): never empty while nkb >= split
+    const int sk_kb0 = splitk ? (sk_s * p.num_k_blocks) / p.split : 0;
+    const int sk_kb1 = splitk ? ((sk_s + 1) * p.num_k_blocks) / p.split : p.num_k_blocks;
+    int pr_stage = 0, pr_tile = splitk ? sk_tile : (int)blockIdx.x, pr_kb = sk_kb0, pr_m0 = 0, pr_n0 = 0, pr_img = 0, pr_y0 = 0, pr_tap = 0,
+        pr_cb = 0, pr_me = 0;
+    bool pr_new = true;
     uint32_t pr_phase = 0;
     // The weights are cold in HBM at every kernel of the step (1.7 GB stream through a 126 MB L2), and the smem ring is only 3-4
     // k-blocks deep: the weight tiles beyond the ring are pulled into L2 by prefetch boxes, kPrefetch k-blocks ahead of the loads.
@@ -823,7 +989,8 @@ __global__ void __launch_bounds__(kPersistThreads, 1) gemm_persist_kernel(const 
     auto produce = [&](int limit, const int what) {
         const bool load_a = what & 1, load_b = what & 2;
         while (limit > 0 && pr_tile < p.num_tiles) {
-            if (pr_kb == 0) {   // new tile
+            if (pr_new) {   // new work item
+                pr_new = false;
                 const int m_tile = pr_tile / p.n_tiles, n_tile = pr_tile - m_tile * p.n_tiles;
                 pr_m0 = m_tile * BLOCK_M;
                 pr_n0 = n_tile * p.block_n;
@@ -831,8 +998,8 @@ __global__ void __launch_bounds__(kPersistThreads, 1) gemm_persist_kernel(const 
                     if (p.tile_n > 1) { pr_img = m_tile * p.tile_n; pr_y0 = 0; }
                     else { pr_img = m_tile / p.tiles_y; pr_y0 = (m_tile - pr_img * p.tiles_y) * p.tile_h; }
                 }
-                pr_tap = 0;
-                pr_cb = 0;
+                pr_tap = pr_kb / p.cblocks;           // 0 unless this is a K slice
+                pr_cb = pr_kb - pr_tap * p.cblocks;
                 pr_me = m_tile % p.pf_share;
                 if (load_b)
                     for (int k = p.stages; k < kPrefetch; ++k) prefetch_b(k);   // k-blocks [0, stages) are loaded right away, [kPrefetch, ..) follow the loads
@@ -861,7 +1028,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) gemm_persist_kernel(const 
             }
             if (++pr_stage == p.stages) { pr_stage = 0; pr_phase ^= 1; }
             if (++pr_cb == p.cblocks) { pr_cb = 0; ++pr_tap; }
-            if (++pr_kb == p.num_k_blocks) { pr_kb = 0; pr_tile += gridDim.x; }
+            if (++pr_kb == sk_kb1) { pr_kb = 0; pr_new = true; pr_tile = splitk ? p.num_tiles : pr_tile + (int)gridDim.x; }
             --limit;
         }
     };
@@ -915,12 +1082,13 @@ __global__ void __launch_bounds__(kPersistThreads, 1) gemm_persist_kernel(const 
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+            const int nkb = sk_kb1 - sk_kb0;      // k-blocks per work item
+            for (int tile = splitk ? sk_tile : (int)blockIdx.x; tile < p.num_tiles; tile = splitk ? p.num_tiles : tile + (int)gridDim.x, ++it) {
                 const int acc = it & 1;
                 ptx::mbar_wait(&tempty[acc], ((uint32_t)(it >> 1) & 1u) ^ 1u);   // the epilogue has drained this stage
                 ptx::tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)acc * p.acc_stride;
-                for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+                for (int kb = 0; kb < nkb; ++kb) {
                     ptx::mbar_wait(&full_bar[stage], phase);
                     ptx::tc_fence_after();
                     if (it == 0 && kb == 0) PTRACE(2);
@@ -939,6 +1107,19 @@ __global__ void __launch_bounds__(kPersistThreads, 1) gemm_persist_kernel(const 
     } else {
         // ================= epilogue warps =================
         const int variant = (p.geglu ? 100 : 0) + (p.out_f32 ? 10 : 0) + p.res_kind + (p.gn_part ? 1000 : 0);
+        if (splitk) {
+            switch (variant) {
+                case 0: persist_epilogue_split<false, 0, false>(p, smem, tmem_base, warp, lane); break;
+                case 1: persist_epilogue_split<false, 1, false>(p, smem, tmem_base, warp, lane); break;
+                case 2: persist_epilogue_split<false, 2, false>(p, smem, tmem_base, warp, lane); break;
+                case 10: persist_epilogue_split<true, 0, false>(p, smem, tmem_base, warp, lane); break;
+                case 11: persist_epilogue_split<true, 1, false>(p, smem, tmem_base, warp, lane); break;
+                case 12: persist_epilogue_split<true, 2, false>(p, smem, tmem_base, warp, lane); break;
+                case 1010: persist_epilogue_split<true, 0, true>(p, smem, tmem_base, warp, lane); break;
+                case 1012: persist_epilogue_split<true, 2, true>(p, smem, tmem_base, warp, lane); break;
+                default: break;
+            }
+        } else
         switch (variant) {
             case 100: persist_epilogue<false, 0, true, false>(p, smem, tmem_base, warp, lane); break;
             case 0: persist_epilogue<false, 0, false, false>(p, smem, tmem_base, warp, lane); break;
@@ -1074,6 +1255,24 @@ int launch_persist(const b200sd_gemm_args* a, const KParams& k, int m_tiles, b20
     }
     p.depth = p.res_kind ? kMaxDepth : 2;
     if (p.res_kind && g_dbg[3] >= 2 && g_dbg[3] <= kMaxDepth) p.depth = g_dbg[3];
+    p.split = k.psplit > 1 ? k.psplit : 1;
+    p.kb_per_split = ceil_div(k.num_k_blocks, p.split);
+    p.residual = k.residual; p.out = k.out; p.ldc = k.ldc; p.ldr = k.ldr;
+    const int units = p.num_tiles * p.split;
+    if (p.split > 1) {
+        B200SD_REQUIRE(k.num_k_blocks >= p.split, "gemm(split-K): fewer K blocks (%d) than slices (%d)", k.num_k_blocks, p.split);
+        B200SD_REQUIRE(units <= b200sd_num_sms() && (size_t)units * BLOCK_M * k.block_n * sizeof(float) <= kWsPartialBytes &&
+                           (size_t)2 * p.num_tiles * sizeof(int) <= kWsCounterBytes,
+                       "gemm(split-K): %d units do not fit the workspace / the machine", units);
+        p.depth = 2;     // no residual prefetch: the residual is read in the reduction phase
+        p.ws = static_cast<float*>(a->workspace);
+        p.cnt = reinterpret_cast<int*>(static_cast<char*>(a->workspace) + kWsPartialBytes);
+        const uint64_t dims[2] = {(uint64_t)k.block_n, (uint64_t)units * BLOCK_M};
+        const uint64_t str[2] = {0, (uint64_t)k.block_n * 4};
+        const uint32_t box[2] = {32, 32};
+        const int rc = b200sd_make_tmap(&p.tmWs, a->workspace, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_DATA_TYPE_FLOAT32);
+        if (rc) return rc;
+    }
     const int bn = k.block_n;
     p.acc_stride = bn <= 128 ? 128 : 256;
     p.tmem_cols = 2 * p.acc_stride;
@@ -1097,7 +1296,7 @@ int launch_persist(const b200sd_gemm_args* a, const KParams& k, int m_tiles, b20
     }
     // ---- smem layout ----
     const int stage_bytes = kABytes + bn * BLOCK_K * 2;
-    p.chunk_bytes = (p.out_f32 || p.res_kind == 2) ? 4096 : 2048;
+    p.chunk_bytes = (p.out_f32 || p.res_kind == 2 || k.psplit > 1) ? 4096 : 2048;
     const int epi_bytes = kEpiWarps * p.depth * p.chunk_bytes;
     const int bias_bytes = kEpiWarps * 256 * (int)sizeof(float);
     const int stat_bytes = k.gn_part ? 4 * 2 * 256 * (int)sizeof(float) : 0;
@@ -1123,12 +1322,18 @@ int launch_persist(const b200sd_gemm_args* a, const KParams& k, int m_tiles, b20
     cudaLaunchConfig_t cfg = {};
     int grid = p.num_tiles < sms ? p.num_tiles : sms;
     if (g_dbg[2] > 0 && g_dbg[2] < grid) grid = g_dbg[2];
+    if (p.split > 1) grid = units;
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(kPersistThreads);
     cfg.dynamicSmemBytes = smem_bytes;
     cfg.stream = static_cast<cudaStream_t>(stream);
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     int na = 0;
+    if (p.split > 1) {   // the K slices of a tile wait for one another: every CTA of the grid must be resident
+        attr[na].id = cudaLaunchAttributeCooperative;
+        attr[na].val.cooperative = 1;
+        ++na;
+    }
     if (b200sd_pdl_enabled()) {
         attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr[na].val.programmaticStreamSerializationAllowed = 1;
@@ -1246,7 +1451,9 @@ int conv_m_tiling(KParams& p, int NB, int H, int W, int M, int* m_tiles) {
 
 }  // namespace
 
-extern "C" size_t b200sd_gemm_workspace_bytes(void) { return 0; }  // split-K reduces over DSMEM: no scratch needed
+// Split-K scratch of the persistent kernel: fp32 partial tiles (at most one 128 x 256 tile per SM) + the per-tile counters.
+// The counters must be ZERO before the first launch that uses the buffer (the kernel leaves them zeroed).
+extern "C" size_t b200sd_gemm_workspace_bytes(void) { return kWsPartialBytes + kWsCounterBytes; }
 
 extern "C" int b200sd_geglu_tile(int N) {
     // the persistent kernel moves 32-column chunks of values and gates: tile = [tile/2 values | tile/2 gates], tile % 64 == 0
@@ -1322,7 +1529,35 @@ static int gemm_tiling(const b200sd_gemm_args* a, KParams& p, int* m_tiles_out, 
     p.pair = want_pair(a->pair, split, m_tiles, n_tiles_f, p.num_k_blocks) && bn % 32 == 0;
     // ---- persistent kernel (TMA-store epilogue, double-buffered TMEM): un-split, un-paired tiles of 128 rows ----
     p.persist = 0;
+    p.psplit = 0;
     const bool geglu = a->epilogue == B200SD_EPI_GEGLU;
+    // ---- ... and its split-K mode for the few-tile / deep-K layers the policy above would hand to a split cluster: up to 16
+    // K slices per tile, one CTA per slice, partials through an L2-resident workspace (persist_epilogue_split) ----
+    static const bool no_psplit = getenv("B200SD_PSPLIT") && getenv("B200SD_PSPLIT")[0] == '0';
+    if (persist_enabled() && !no_psplit && a->split_k <= 0 && a->block_n <= 0 && split > 1 && !geglu && p.rows_valid == BLOCK_M &&
+        a->N % 32 == 0 && a->workspace != nullptr && a->workspace_bytes >= kWsPartialBytes + kWsCounterBytes &&
+        (reinterpret_cast<uintptr_t>(a->workspace) & 127) == 0 && a->ldc % 4 == 0 && (!a->residual || a->ldr % 4 == 0)) {
+        int bnp = 0;
+        for (int cand : {160, 128, 256, 192, 96, 64, 32})
+            if (a->N % cand == 0) { bnp = cand; break; }
+        const int sms_s = b200sd_num_sms();
+        const long tiles = bnp ? (long)m_tiles * (a->N / bnp) : sms_s + 1;
+        int S = 1;
+        while (S < 16 && tiles * (S * 2) <= sms_s && p.num_k_blocks / (S * 2) >= 4) S *= 2;
+        // Measured with cold weights (tools/cold_probe.py): the trip through the workspace and the counter costs ~6 us, more
+        // than the DSMEM exchange of a split cluster (~4 us) -- it only pays where 16 slices put twice as many SMs on the weight
+        // stream as a cluster of 8 can: the 8x8 level (M = 128: 8 tiles; K 23040: 31.2 -> 22.5 us).  Elsewhere (M 512 K 1280:
+        // 10.1 -> 15.9 us) the cluster path stays.
+        if (S == 16 && p.num_k_blocks >= 128) {
+            p.persist = 1;
+            p.psplit = S;
+            p.block_n = bnp;
+            p.split_k = 1;
+            p.pair = 0;
+            *n_tiles_out = a->N / bnp;
+            return B200SD_OK;
+        }
+    }
     if (persist_enabled() && split == 1 && !p.pair && p.rows_valid == BLOCK_M && a->N % 32 == 0 &&
         (!a->rowbias || (a->rows_per_image > 0 && a->rows_per_image % 32 == 0)) &&
         !(a->residual && a->residual == a->out && a->residual_dtype != a->out_dtype)) {
@@ -1470,6 +1705,14 @@ extern "C" int b200sd_gemm_gn_layout(const b200sd_gemm_args* a, int hw, int* par
     *parts_per_image = 0;
     *total_parts = 0;
     if (a->out_dtype != B200SD_F32 || a->epilogue != B200SD_EPI_LINEAR || (a->residual && a->residual_dtype != B200SD_F32)) return B200SD_OK;
+    if (p.persist && p.psplit > 1) {
+        // split-K mode: one partial row per (tile, K slice) = 128 / split output rows
+        const int rpc = BLOCK_M / p.psplit;
+        if (a->M % hw != 0 || hw % rpc != 0 || (p.conv && a->H * a->W != hw)) return B200SD_OK;
+        *parts_per_image = hw / rpc;
+        *total_parts = m_tiles * p.psplit;
+        return B200SD_OK;
+    }
     if (p.persist) {
         // the persistent kernel publishes one partial row per 128-row tile
         if (a->M % hw != 0 || hw % BLOCK_M != 0 || (p.conv && a->H * a->W != hw)) return B200SD_OK;

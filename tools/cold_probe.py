@@ -51,6 +51,16 @@ def case(kind, M, N, K, conv=None, res=True, f32=True, geglu=False, variants=((0
     L.b200sd_debug_set(0, -1)
     print(row, flush=True)
 
+case("conv", 128, 1280, 11520, conv=(2, 8, 8))
+case("conv", 128, 1280, 23040, conv=(2, 8, 8))
+case("conv", 512, 1280, 11520, conv=(2, 16, 16))
+case("conv", 512, 1280, 23040, conv=(2, 16, 16))
+case("gemm", 512, 1280, 1280)
+case("gemm", 512, 1280, 5120)
+case("gemm", 2048, 640, 2560)
+case("gemm", 128, 1280, 1280)
+case("conv", 2048, 640, 5760, conv=(2, 32, 32))
+if os.environ.get("SMALL_ONLY"): sys.exit(0)
 case("gemm", 8192, 320, 320)
 case("gemm", 2048, 640, 640)
 case("gemm", 8192, 320, 1280)
