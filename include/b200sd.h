@@ -155,6 +155,9 @@ typedef struct b200sd_gemm_args {
     int pair;              /* CTA pairs (tcgen05 cta_group::2, 256-row MMA tiles): 0 = auto, 1 = on, -1 = off */
     float* gn_part;        /* optional: per-CTA column statistics [parts][2][N] of the fp32 output (sum | sum of squares over the
                               rows each CTA stores), consumed by b200sd_groupnorm_silu_parts; layout from b200sd_gemm_gn_layout */
+    const void* prefetch;  /* optional: memory the NEXT kernels of the stream will stream from HBM (the next layer's weights): this
+                              launch pulls prefetch_bytes of it into L2 while it runs (cp.async.bulk.prefetch.L2, spread over its CTAs) */
+    size_t prefetch_bytes;
     int w_layout;          /* B200SD_W_ROW_MAJOR: w is [N][K]; B200SD_W_KBLOCK_MAJOR: w is [K/64][N][64] (the 64-wide k-blocks of
                               all N rows stored together), so the weight tile of one k-block is one contiguous run of DRAM --
                               the layout for weights that are streamed from HBM once per step (small-M / deep-K layers) */

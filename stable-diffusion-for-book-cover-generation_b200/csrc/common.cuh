@@ -177,6 +177,24 @@ __device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* m, int c0, in
                  : "memory");
 }
 
+// pull `bytes` (multiple of 16, 16-byte aligned) of global memory into L2; fire and forget
+__device__ __forceinline__ void bulk_prefetch_l2(const void* p, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+// this CTA's share of a [ptr, ptr + bytes) prefetch spread over `nctas` CTAs (called by ONE thread)
+__device__ __forceinline__ void prefetch_share_l2(const void* ptr, size_t bytes, int cta, int nctas) {
+    if (ptr == nullptr || bytes == 0) return;
+    const size_t per = ((bytes + nctas - 1) / nctas + 4095) & ~size_t(4095);
+    size_t off = (size_t)cta * per;
+    const size_t end = off + per < bytes ? off + per : (bytes & ~size_t(15));
+    const char* base = static_cast<const char*>(ptr);
+    while (off < end) {
+        const size_t n = end - off < 65536 ? end - off : 65536;
+        bulk_prefetch_l2(base + off, (uint32_t)n);
+        off += n;
+    }
+}
+
 // ---- TMA store: smem tile -> global through a tensor map (bulk async-group completion) ----
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* src, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(m)),

@@ -97,6 +97,8 @@ struct KParams {
     int psplit;          // host only: ... in its split-K mode with this many K slices per tile (0 = no)
     int w_kmajor;        // forward B operand stored k-block-major [K/64][N][64]: one tile k-block = ONE contiguous bn x 128 B run of
                          // DRAM instead of bn 128-byte pieces a whole weight row (K * 2 B) apart
+    const void* prefetch;       // next layer's weights: pulled into L2 while this kernel runs (see b200sd_gemm_args::prefetch)
+    size_t prefetch_bytes;
     float* gn_part;      // optional [m_tiles * split_k][2][N]: per-column (sum, sum of squares) of the rows each CTA stores --
                          // the GroupNorm that consumes this output gets its statistics from here instead of re-reading it
     unsigned long long* trace;  // optional [ctas][8] globaltimer stamps (debug)
@@ -394,6 +396,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tcgen05_kernel(const __gr
                 s_rb[256 + c] = __ldg(p.rowbias + (size_t)img1 * p.ldrb + n0 + c);
             }
         }
+        if (epi_tid == 0 && p.prefetch_bytes)   // idle until the accumulator is ready: stage the NEXT layer's weights in L2
+            ptx::prefetch_share_l2(p.prefetch, p.prefetch_bytes, (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x,
+                              gridDim.x * gridDim.y * gridDim.z);
         ptx::mbar_wait(tmem_full_bar, 0);
         ptx::tc_fence_after();
         if (epi_tid == 0) TRACE(4);
@@ -550,6 +555,8 @@ struct PParams {
     CUtensorMap tmWs;               // fp32 partial tiles in the workspace: [units * 128][block_n]
     float* ws;                      // the same buffer, for the reduction's plain loads
     int* cnt;                       // [2][num_tiles] arrival / departure counters (zero between launches: self-resetting)
+    const void* prefetch;           // next layer's weights -> L2 (b200sd_gemm_args::prefetch)
+    size_t prefetch_bytes;
     const void* residual;           // raw pointers for the reduction phase
     void* out;
     int ldc, ldr;
@@ -1106,6 +1113,8 @@ __global__ void __launch_bounds__(kPersistThreads, 1) gemm_persist_kernel(const 
         }
     } else {
         // ================= epilogue warps =================
+        if (warp == 2 && lane == 0 && p.prefetch_bytes)   // idle until the first accumulator: stage the NEXT layer's weights in L2
+            ptx::prefetch_share_l2(p.prefetch, p.prefetch_bytes, blockIdx.x, gridDim.x);
         const int variant = (p.geglu ? 100 : 0) + (p.out_f32 ? 10 : 0) + p.res_kind + (p.gn_part ? 1000 : 0);
         if (splitk) {
             switch (variant) {
@@ -1258,6 +1267,7 @@ int launch_persist(const b200sd_gemm_args* a, const KParams& k, int m_tiles, b20
     p.split = k.psplit > 1 ? k.psplit : 1;
     p.kb_per_split = ceil_div(k.num_k_blocks, p.split);
     p.residual = k.residual; p.out = k.out; p.ldc = k.ldc; p.ldr = k.ldr;
+    p.prefetch = k.prefetch; p.prefetch_bytes = k.prefetch_bytes;
     const int units = p.num_tiles * p.split;
     if (p.split > 1) {
         B200SD_REQUIRE(k.num_k_blocks >= p.split, "gemm(split-K): fewer K blocks (%d) than slices (%d)", k.num_k_blocks, p.split);
@@ -1637,6 +1647,9 @@ extern "C" int b200sd_gemm(const b200sd_gemm_args* a, b200sd_stream_t stream) {
     }
     const int bn = p.block_n, split = p.split_k;
     p.gn_part = a->gn_part;
+    p.prefetch = a->prefetch;
+    p.prefetch_bytes = a->prefetch ? a->prefetch_bytes : 0;
+    B200SD_REQUIRE(!a->prefetch || (reinterpret_cast<uintptr_t>(a->prefetch) & 15) == 0, "gemm: prefetch pointer must be 16-byte aligned");
     B200SD_REQUIRE(!a->gn_part || (a->out_dtype == B200SD_F32 && a->epilogue == B200SD_EPI_LINEAR &&
                                    (!a->residual || a->residual_dtype == B200SD_F32)),
                    "gemm: gn_part needs fp32 output, the linear epilogue and no bf16 residual");

@@ -77,6 +77,9 @@ class Engine:
         # GroupNorm statistics from the producing GEMM's epilogue (B200SD_GN_FROM_GEMM=0: always the stand-alone kernel)
         self.gn_from_gemm = os.environ.get("B200SD_GN_FROM_GEMM", "1") != "0"
         self._gn_parts = {}     # id(activation buffer) -> ops.GnParts describing its CURRENT contents (plan-build time)
+        self.prefetch_kblocks = int(os.environ.get("B200SD_PREFETCH", "0"))     # k-blocks of the next layer staged in L2 (0 = off)
+        self.prefetch_weights = self.prefetch_kblocks > 0
+        self._prev_gemm, self._first_w = None, None
         with torch.cuda.device(device):
             self._build()
 
@@ -95,9 +98,26 @@ class Engine:
                 self._keep.append(parts)       # the captured launch writes into parts.buf on every replay: it must outlive
                 #                                its entry in _gn_parts (popped when the pooled buffer is produced again)
         self._keep.append((a0, w, out, kw))
+        if plan is self.plan and self.prefetch_weights:
+            # the weights of THIS layer are what the PREVIOUS tensor-core launch pulls into L2 while it runs: every layer's weights
+            # are cold in HBM when its kernel starts (1.7 GB stream through a 126 MB L2 once per step)
+            if self._prev_gemm is not None:
+                self._prev_gemm.prefetch, self._prev_gemm.prefetch_bytes = w.data_ptr(), self._prefetch_bytes(w)
+            else:
+                self._first_w = w
+            self._prev_gemm = args
         kind = "conv3x3" if args.conv_taps == 9 else "gemm"
         plan.append(lambda a=args: ops.gemm_run(a), kind, 2.0 * args.M * args.N * args.K,
                     f"{kind} M{args.M} N{args.N} K{args.K}")
+
+    def _prefetch_bytes(self, w):
+        """How much of the next layer's weights the previous launch stages in L2.  Staging ALL of it was measured slower (the
+        prefetch stream competes with the running kernel's own, latency-critical loads: 5.01 vs 4.95 ms per step); what the next
+        kernel needs at once is its first k-blocks -- a contiguous prefix in the k-block-major layout ([K/64][N][64])."""
+        total = w.numel() * w.element_size()
+        if w.dim() == 3:
+            return min(total, self.prefetch_kblocks * w.shape[1] * w.shape[2] * w.element_size())
+        return total if self.prefetch_kblocks >= 1000 else 0
 
     def _groupnorm(self, x, skip, g, b, out, hw, eps, silu, raw_out=None):
         """Plan one GroupNorm(+SiLU, + concat): from the producers' epilogue statistics when every source has them."""
@@ -310,6 +330,8 @@ class Engine:
         t = pool.get(N * h * w, boc[0])
         self._groupnorm(x, None, wo["g"], wo["beta"], t, h * w, cfg.norm_eps, True)
         P.append(lambda t=t: ops.conv_out(t, wo["w"], wo["b"], self.out), "conv_io", 0, "conv_out")
+        if self._prev_gemm is not None and self._first_w is not None:   # the last layer stages the first layer of the next step
+            self._prev_gemm.prefetch, self._prev_gemm.prefetch_bytes = self._first_w.data_ptr(), self._prefetch_bytes(self._first_w)
         self.activation_bytes = pool.total
 
     # -- execution --------------------------------------------------------------------------------
