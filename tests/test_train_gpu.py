@@ -242,3 +242,32 @@ def test_autograd_mode_accumulates_and_survives_save_load(tmp_path):
         again = UNet2DConditionModel.from_pretrained(str(d))
         for (n, p), (_, q) in zip(unet.state_dict().items(), again.state_dict().items()):
             assert torch.equal(p.detach().cpu(), q), n
+
+
+def test_sd15_unet_gradients_batch8_and_frozen_context_gradient():
+    """The benchmarked training shapes (BASELINE configs 3 and 4): full SD v1.5 UNet at batch 8 -- all 686 parameter gradients
+    with the weights trainable, then the data-gradient-only plan (UNet frozen, finetune_sd.py:391-395) down to the context."""
+    from b200sd import ops
+    oracle, ours = _pair({})
+    x, noise, ctx, t = _inputs(8, 64, 64, 768, 11)
+    ref_loss, ref, ref_dctx = _ref_grads(oracle, x, noise, ctx, t, ctx_grad=True)
+    oracle.zero_grad(set_to_none=True)
+    loss = ops.mse_loss(ours(x, t, ctx).sample, noise)
+    loss.backward()
+    assert abs(float(loss) - ref_loss) <= 2e-2 * ref_loss
+    worst, cos_all, bad = _compare(ref, {n: p.grad for n, p in ours.named_parameters()})
+    print(f"sd15 batch-8 grads: worst per-tensor max-rel {worst:.4g}, global cosine {cos_all:.6f}, out-of-tolerance {len(bad)}")
+    assert not bad, f"{len(bad)} tensors out of tolerance, e.g. {bad[:5]}"
+    assert cos_all >= 0.9995, cos_all
+    del ref
+    torch.cuda.empty_cache()
+    # config 4: frozen UNet, gradient into the (CLIP) context only
+    ours.zero_grad(set_to_none=True)
+    ours.requires_grad_(False).eval()
+    c = ctx.clone().requires_grad_(True)
+    ops.mse_loss(ours(x, t, c).sample, noise).backward()
+    assert all(p.grad is None for p in ours.parameters())
+    rel = float((c.grad - ref_dctx).abs().max() / ref_dctx.abs().max())
+    cos = float(F.cosine_similarity(c.grad.flatten(), ref_dctx.flatten(), dim=0))
+    print(f"sd15 batch-8 frozen-UNet context gradient: max-rel {rel:.4g}, cosine {cos:.6f}")
+    assert rel <= 4e-2 and cos >= 0.999, (rel, cos)
