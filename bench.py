@@ -478,6 +478,84 @@ def run_ours(args):
 
 
 # ---------------------------------------------------------------------------------------------------
+# BASELINE configs[4]: book-cover portrait (512 x 768) batched generation, batch 1-64 sharded over the GPUs
+# ---------------------------------------------------------------------------------------------------
+def run_sweep(args):
+    """`--workload sweep [--portrait]`: for every total batch B in --sweep-batches, shard the B images over the ranks (contiguous
+    chunks, remainder to the low ranks, ranks without an image idle), run `steps` denoising iterations of the 50-step CFG DDIM
+    sampler and print ONE JSON line per B: whole-job images/s = B / (50 * max-over-ranks ms per iteration).  One model per rank,
+    no collective on the data path."""
+    import torch
+    import torch.distributed as dist
+    from b200sd.schedulers import DDIMScheduler
+    from b200sd.unet import UNet2DConditionModel
+    rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    h, w = (96, 64) if args.portrait else (64, 64)
+    torch.manual_seed(0)
+    unet = UNet2DConditionModel().to(dev).eval()
+    sch = DDIMScheduler(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear", clip_sample=False, set_alpha_to_one=False)
+    sch.set_timesteps(50)
+    ts = sch.timesteps.tolist()
+    flops_per_img_it = 2 * (1.2953e12 if args.portrait else FLOPS_PER_SAMPLE_64)
+    for total in [int(x) for x in args.sweep_batches.split(",")]:
+        B = shard_images(total, world, rank)
+        idle = B == 0
+        ms = 0.0
+        if not idle:
+            g = torch.Generator().manual_seed(42 + rank)
+            lat = torch.randn(B, 4, h, w, generator=g).to(dev)
+            ctx = torch.randn(2 * B, 77, 768, generator=g).to(dev)
+            x2 = torch.empty(2 * B, 4, h, w, device=dev)
+            nxt = torch.empty_like(lat)
+            with torch.no_grad():
+                def step(i):
+                    nonlocal lat, nxt
+                    x2[:B].copy_(lat); x2[B:].copy_(lat)
+                    sch.step_cfg(unet(x2, ts[i % 50], ctx).sample, ts[i % 50], lat, 7.5, out=nxt)
+                    lat, nxt = nxt, lat
+                for i in range(max(args.warmup, 3)):
+                    step(i)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        if not idle:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            with torch.no_grad():
+                e0.record()
+                for i in range(args.steps):
+                    step(i)
+                e1.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        if not idle:
+            ms = e0.elapsed_time(e1) / args.steps
+        active = torch.tensor([ms, 0.0 if idle else 1.0], device=dev, dtype=torch.float64)
+        if world > 1:
+            mx = active.clone()
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+            dist.all_reduce(active, op=dist.ReduceOp.SUM)
+            ms_max, n_active = float(mx[0]), int(active[1])
+        else:
+            ms_max, n_active = ms, 0 if idle else 1
+        if rank == 0:
+            ips = total / (50.0 * ms_max * 1e-3)
+            print(json.dumps({"metric": "images_per_s", "value": ips, "unit": "images/s", "n_gpus": world, "gpus_active": n_active,
+                              "gpus_idle": world - n_active, "total_images": total, "images_on_rank0": B if not idle else 0,
+                              "ms_per_iteration_max_over_ranks": ms_max, "steps": args.steps, "scaling": "strong", "dtype": "bf16",
+                              "tflops_per_active_gpu": (total / max(n_active, 1)) * flops_per_img_it / (ms_max * 1e-3) / 1e12 if ms_max else 0,
+                              "config": sample_config(B, world, total, args.portrait)}), flush=True)
+        unet._engines = {}
+        torch.cuda.empty_cache()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ---------------------------------------------------------------------------------------------------
 # fine-tuning step (BASELINE config 3): add_noise + UNet fwd/bwd + MSE + gradient allreduce + AdamW
 # ---------------------------------------------------------------------------------------------------
 def cpu_oracle_train_samples_per_s(batch, steps):
@@ -817,13 +895,20 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"], help="fp32 = the accuracy path (engine_fp32.py)")
     ap.add_argument("--impl", default="b200sd", choices=["b200sd", "reference", "library"],
                     help="library = the oracle module in bf16 under eager torch on the GPU (yardstick, sampling workload only)")
-    ap.add_argument("--workload", default="sample", choices=["sample", "train", "train_text"],
+    ap.add_argument("--sweep-batches", default="1,2,4,8,16,32,64", help="--workload sweep: total image batches to run")
+    ap.add_argument("--workload", default="sample", choices=["sample", "train", "train_text", "sweep"],
                     help="sample = 50-step DDIM + CFG denoising (BASELINE configs[1], the headline); train = fine-tuning step (configs[2])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train-legs", action="store_true", help="skip the fine-tuning sub-records (configs 3 / 4) of the default line")
     ap.add_argument("--no-elementwise", action="store_true", help="skip the elementwise GB/s sub-record")
     ap.add_argument("--dump-ops", default=None, help="write the per-launch timing table to this file")
     args = ap.parse_args()
+    if args.workload == "sweep":
+        if args.gpus > 1 and "RANK" not in os.environ:
+            cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+                   "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.abspath(__file__)] + sys.argv[1:]
+            raise SystemExit(subprocess.call(cmd))
+        return run_sweep(args)
     if args.workload in ("train", "train_text"):
         if args.impl != "reference" and args.gpus > 1 and "RANK" not in os.environ:
             cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",

@@ -220,6 +220,11 @@ int b200sd_conv_in(const float* x_nchw, const float* w, const float* bias, void*
                    int Cout, int H, int W, int out_dtype, b200sd_stream_t stream);
 int b200sd_conv_out(const void* x_nhwc, const float* w, const float* bias, float* out_nchw, int batch, int Cin,
                     int Cout, int H, int W, b200sd_stream_t stream);
+/* Tail of conv_out when it runs as an implicit GEMM on the tensor cores (large batches: b200sd_gemm with the 4 output channels
+ * padded to a 32-wide tile and the fp32 weights split into bf16 hi | lo halves along K): x fp32 [batch*hw][ld] NHWC, the first C
+ * (<= 4) columns are the channels; out_nchw[b][c][p] = x[b*hw + p][c] + bias[c]. */
+int b200sd_nhwc_bias_to_nchw(const float* x, const float* bias, float* out_nchw, int batch, int C, int hw, int ld,
+                             b200sd_stream_t stream);
 
 /* GroupNorm over NHWC input, optionally over the channel concat [x0 | x1] (torch.cat fused),
  * optional SiLU, bf16 output [rows, C0+C1].  stats_ws: float[b200sd_groupnorm_workspace_floats(batch)]

@@ -76,6 +76,7 @@ SIGNATURES = {
     "b200sd_gemm_wgrad": (_i, [C.POINTER(WgradArgs), _vp]),
     "b200sd_conv_in": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "b200sd_conv_out": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "b200sd_nhwc_bias_to_nchw": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "b200sd_groupnorm_silu": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _i, _i, _vp]),
     "b200sd_groupnorm_silu_stats": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _i, _i, _vp]),
     "b200sd_groupnorm_workspace_floats": (_i, [_i]),

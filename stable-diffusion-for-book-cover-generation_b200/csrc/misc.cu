@@ -353,6 +353,31 @@ extern "C" int b200sd_conv_out(const void* x_nhwc, const float* w, const float* 
     return B200SD_OK;
 }
 
+// [M][ld] fp32 (NHWC, the first C of ld columns) + bias -> NCHW fp32: the tail of the tensor-core conv_out
+__global__ void __launch_bounds__(256) nhwc_bias_to_nchw_kernel(const float* __restrict__ x, const float* __restrict__ bias,
+                                                                float* __restrict__ out, int total, int hw, int C, int ld) {
+    ptx::pdl_trigger();
+    ptx::pdl_wait();
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= total) return;
+    const int b = m / hw, pix = m - b * hw;
+    const float4 v = __ldg(reinterpret_cast<const float4*>(x + (size_t)m * ld));
+    const float vv[4] = {v.x, v.y, v.z, v.w};
+    for (int c = 0; c < C; ++c) out[((size_t)b * C + c) * hw + pix] = vv[c] + __ldg(bias + c);
+}
+
+extern "C" int b200sd_nhwc_bias_to_nchw(const float* x, const float* bias, float* out_nchw, int batch, int C, int hw, int ld,
+                                        b200sd_stream_t stream) {
+    B200SD_REQUIRE(x && bias && out_nchw, "nhwc_bias_to_nchw: null pointer");
+    B200SD_REQUIRE(C >= 1 && C <= 4 && ld % 4 == 0 && ld >= 4 && batch > 0 && hw > 0, "nhwc_bias_to_nchw: C in 1..4, ld %% 4 == 0");
+    const int total = batch * hw;
+    B200SD_CUDA(b200sd_launch(nhwc_bias_to_nchw_kernel, dim3(ceil_div(total, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), x, bias,
+                              out_nchw, total, hw, C, ld));
+    COUNT_LAUNCH();
+    B200SD_LAUNCH_CHECK();
+    return B200SD_OK;
+}
+
 extern "C" int b200sd_upsample2x(const void* x, void* out, int batch, int H, int W, int C, int in_dtype,
                                  b200sd_stream_t stream) {
     B200SD_REQUIRE(x && out, "upsample2x: null pointer");

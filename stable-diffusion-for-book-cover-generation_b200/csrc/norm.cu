@@ -4,6 +4,8 @@
 
 #include <algorithm>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 extern std::atomic<long long> g_b200sd_launches;
@@ -650,7 +652,8 @@ extern "C" int b200sd_groupnorm_silu_parts(const void* x0, const void* x1, int C
     const int Cg = G * cpg;
     if ((Cg % 8) != 0 || groups % G != 0 || Cg / 8 > 512) return B200SD_ERR_UNSUPPORTED;
     const int VC = Cg / 8, sets = groups / G;
-    int slabs = ceil_div(b200sd_num_sms() * 2, batch * sets);
+    static const int ctas_per_sm = [] { const char* e = getenv("B200SD_GN_CTAS_PER_SM"); return e ? atoi(e) : 2; }();
+    int slabs = ceil_div(b200sd_num_sms() * ctas_per_sm, batch * sets);
     if (slabs > hw / 32) slabs = hw / 32;
     if (slabs < 1) slabs = 1;
     const int ppc = ceil_div(hw, slabs);

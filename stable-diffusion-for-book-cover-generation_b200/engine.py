@@ -163,7 +163,17 @@ class Engine:
         P.append(lambda: ops.timestep_embedding(self.in_t, boc[0], out=t_sin), "time_embed")
         P.append(lambda: ops.small_linear(t_sin, te["w1"], te["b1"], silu_out=True, out=t_h), "time_embed")
         P.append(lambda: ops.small_linear(t_h, te["w2"], te["b2"], out=t_emb), "time_embed")
-        P.append(lambda: ops.small_linear(t_emb, Wp["tproj"]["w"], Wp["tproj"]["b"], silu_in=True, out=self.tproj), "time_embed", 0, "time_emb_proj x22")
+        # all 22 time_emb_proj heads at once: (N, 1280) x (19200, 1280)^T.  The CUDA-core small_linear re-reads the 49 MB of weights
+        # per group of 8 batch rows (16 us at CFG batch 2, 154 us at batch 16); from 8 rows on it is one tensor-core GEMM
+        # (rows beyond N are TMA zero fill) behind a SiLU + bf16 cast of the 1280-vector
+        self.large_batch = N >= int(os.environ.get("B200SD_LARGE_BATCH", "8"))
+        if self.large_batch:
+            a16 = torch.empty(N, temb_dim, dtype=torch.bfloat16, device=dev)
+            P.append(lambda: ops.cast_act(t_emb, a16, silu=True), "time_embed")
+            self._gemm(P, a16, Wp["tproj"]["w"], self.tproj, bias=Wp["tproj"]["b"])
+            self.plan.meta[-1] = ("time_embed", self.plan.meta[-1][1], "time_emb_proj x22 (tensor cores)")
+        else:
+            P.append(lambda: ops.small_linear(t_emb, Wp["tproj"]["w"], Wp["tproj"]["b"], silu_in=True, out=self.tproj), "time_embed", 0, "time_emb_proj x22")
 
         # scratch for the tensor-core attention (V^T of the largest self-attention), owned by this engine
         self.attn_ws = torch.empty(ops.attention_workspace_bytes(N, self.heads, self.H * self.W, boc[0] // self.heads) + 256,
@@ -329,7 +339,16 @@ class Engine:
         wo = Wp["conv_out"]
         t = pool.get(N * h * w, boc[0])
         self._groupnorm(x, None, wo["g"], wo["beta"], t, h * w, cfg.norm_eps, True)
-        P.append(lambda t=t: ops.conv_out(t, wo["w"], wo["b"], self.out), "conv_io", 0, "conv_out")
+        if self.large_batch and boc[0] % 64 == 0 and cfg.out_channels <= 4:
+            # conv_out (320 -> 4) as an implicit GEMM on the tensor cores: [x | x] . [w_hi | w_lo] per tap (fp32-accurate weights),
+            # the 4 channels padded to a 32-wide tile, then bias + NHWC -> NCHW.  The CUDA-core kernel is latency-bound at CFG batch 2
+            # (32 us) and stops scaling beyond (267 us at batch 16).
+            tmp = pool.get(N * h * w, 32, F32)
+            self._gemm(P, t, wo["w_tc"], tmp, a1=t, conv=(N, h, w))
+            self.plan.meta[-1] = ("conv_io", self.plan.meta[-1][1], "conv_out (tensor cores)")
+            P.append(lambda tmp=tmp: ops.nhwc_bias_to_nchw(tmp, wo["b"], self.out), "conv_io", 0, "conv_out: bias + NCHW")
+        else:
+            P.append(lambda t=t: ops.conv_out(t, wo["w"], wo["b"], self.out), "conv_io", 0, "conv_out")
         if self._prev_gemm is not None and self._first_w is not None:   # the last layer stages the first layer of the next step
             self._prev_gemm.prefetch, self._prev_gemm.prefetch_bytes = self._first_w.data_ptr(), self._prefetch_bytes(self._first_w)
         self.activation_bytes = pool.total

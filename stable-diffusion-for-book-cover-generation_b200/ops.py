@@ -358,6 +358,14 @@ def conv_out(x_nhwc, w_packed, bias, out_nchw):
     return out_nchw
 
 
+def nhwc_bias_to_nchw(x_f32, bias, out_nchw):
+    """out_nchw[b][c][p] = x[b*hw + p][c] + bias[c] (x: fp32 [batch*hw][ld], c < out channels <= 4)."""
+    _chk(x_f32, bias, out_nchw)
+    B, C, H, W = out_nchw.shape
+    check(lib().b200sd_nhwc_bias_to_nchw(_p(x_f32), _p(bias), _p(out_nchw), B, C, H * W, x_f32.shape[-1], _stream()), "nhwc_bias_to_nchw")
+    return out_nchw
+
+
 def groupnorm_silu(x0, x1, gamma, beta, out, batch, hw, groups=32, eps=1e-5, silu=True, raw_out=None, stats_out=None):
     _chk(x0, x1, gamma, beta, out, raw_out, stats_out)
     if x1 is not None and x1.dtype != x0.dtype:

@@ -42,3 +42,17 @@ def kblock_major(w: torch.Tensor) -> torch.Tensor:
     n, k = w.shape
     assert k % 64 == 0
     return w.reshape(n, k // 64, 64).permute(1, 0, 2).contiguous()
+
+
+def pack_conv_out_tc(w: torch.Tensor, pad_to: int = 32) -> torch.Tensor:
+    """conv_out (Cout <= 4, Cin, 3, 3) fp32 -> bf16 [pad_to][9][2*Cin] for the tensor-core path: per tap [hi | lo] with
+    hi = bf16(w), lo = bf16(w - hi), so that [x | x] . [hi | lo] restores the fp32 weights to ~2^-17 (the last layer of the network
+    feeds the noise prediction directly: plain bf16 weights would cost ~1e-3 of the 1e-2 parity budget).  Rows >= Cout are zero."""
+    co, ci, kh, kw = w.shape
+    wt = w.permute(0, 2, 3, 1).reshape(co, kh * kw, ci).float()
+    hi = wt.to(torch.bfloat16)
+    lo = (wt - hi.float()).to(torch.bfloat16)
+    out = torch.zeros(pad_to, kh * kw, 2 * ci, dtype=torch.bfloat16, device=w.device)
+    out[:co, :, :ci] = hi
+    out[:co, :, ci:] = lo
+    return out.reshape(pad_to, kh * kw * 2 * ci).contiguous()

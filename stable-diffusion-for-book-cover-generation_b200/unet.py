@@ -352,7 +352,8 @@ class UNet2DConditionModel(nn.Module):
 
         W["conv_in"] = dict(w=packing.pack_conv3x3_f32(self.conv_in.weight.detach()), b=f32(self.conv_in.bias))
         W["conv_out"] = dict(w=packing.pack_conv3x3_f32(self.conv_out.weight.detach()), b=f32(self.conv_out.bias),
-                             g=f32(self.conv_norm_out.weight), beta=f32(self.conv_norm_out.bias))
+                             g=f32(self.conv_norm_out.weight), beta=f32(self.conv_norm_out.bias),
+                             w_tc=packing.pack_conv_out_tc(self.conv_out.weight.detach()))
         te = self.time_embedding
         W["temb"] = dict(w1=packing.pack_linear(te.linear_1.weight.detach()), b1=f32(te.linear_1.bias),
                          w2=packing.pack_linear(te.linear_2.weight.detach()), b2=f32(te.linear_2.bias))

@@ -157,6 +157,26 @@ def test_config1_margin_over_five_input_seeds(models):
     assert max(rels) <= 1e-2, rels
 
 
+def test_large_batch_plan_batch8(models):
+    """UNet batch >= 8 switches two ends of the plan to the tensor cores (all 22 time_emb_proj heads as one GEMM; conv_out as an
+    implicit GEMM with hi | lo split weights) and every GEMM grid becomes multi-round (persistent kernel): same 1e-2 bar."""
+    oracle, ours = models
+    g = torch.Generator().manual_seed(21)
+    x = torch.randn(8, 4, 64, 64, generator=g).to(DEV)
+    ctx = torch.randn(8, 77, 768, generator=g).to(DEV)
+    t = torch.randint(0, 1000, (8,), generator=g).to(DEV)
+    oc = oracle.to(DEV)
+    try:
+        with torch.no_grad():
+            want = oc(x, t, ctx).sample
+            got = ours(x, t, ctx).sample
+    finally:
+        oracle.to("cpu")
+    r = _rel(got, want)
+    print(f"batch-8 plan max-rel {r:.4g}")
+    assert r <= 1e-2, r
+
+
 def test_50_step_cfg_plms_sampling_cosine(models):
     from b200sd.pipeline import denoise_loop
     from b200sd.schedulers import PNDMScheduler
