@@ -659,7 +659,7 @@ def train_text_leg(dev, world, rank, local, steps=5, warmup=3, B=8, unet=None):
     unet = unet.eval().requires_grad_(False)                                      # finetune_sd.py:391-395
     clip = CLIPTextModel(CLIPTextConfig(hidden_size=768, intermediate_size=3072, num_hidden_layers=12, num_attention_heads=12,
                                         vocab_size=49408, max_position_embeddings=77, hidden_act="quick_gelu")).to(dev).train()
-    model = torch.nn.parallel.DistributedDataParallel(clip, device_ids=[local]) if world > 1 else clip
+    model = torch.nn.parallel.DistributedDataParallel(clip, device_ids=[local], gradient_as_bucket_view=True, bucket_cap_mb=int(os.environ.get('B200SD_DDP_BUCKET_MB', '128'))) if world > 1 else clip
     opt = torch.optim.AdamW(clip.parameters(), lr=1e-5, weight_decay=1e-2, fused=True)
     sched = DDPMScheduler(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear", num_train_timesteps=1000)
     g = torch.Generator().manual_seed(1000 + rank)
@@ -814,7 +814,7 @@ def run_train_text(args):
     unet = UNet2DConditionModel().to(dev).eval().requires_grad_(False)            # finetune_sd.py:391-395
     clip = CLIPTextModel(CLIPTextConfig(hidden_size=768, intermediate_size=3072, num_hidden_layers=12, num_attention_heads=12,
                                         vocab_size=49408, max_position_embeddings=77, hidden_act="quick_gelu")).to(dev).train()
-    model = torch.nn.parallel.DistributedDataParallel(clip, device_ids=[local]) if world > 1 else clip
+    model = torch.nn.parallel.DistributedDataParallel(clip, device_ids=[local], gradient_as_bucket_view=True, bucket_cap_mb=int(os.environ.get('B200SD_DDP_BUCKET_MB', '128'))) if world > 1 else clip
     opt = torch.optim.AdamW(clip.parameters(), lr=1e-5, weight_decay=1e-2, fused=True)
     sched = DDPMScheduler(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear", num_train_timesteps=1000)
     g = torch.Generator().manual_seed(1000 + rank)

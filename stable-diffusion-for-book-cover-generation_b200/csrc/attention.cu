@@ -227,11 +227,7 @@ int launch_attention(const bf16* q, const bf16* k, const bf16* v, bf16* out, flo
                      int D, int ldq, int ldk, int ldv, int ldo, float scale, cudaStream_t s) {
     constexpr int PITCH = DP * 2 + 16;
     const size_t smem = (size_t)(kBM + 4 * kBN) * PITCH;
-    static bool configured = false;
-    if (!configured) {
-        B200SD_CUDA(cudaFuncSetAttribute(attention_kernel<DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    B200SD_CUDA(b200sd_opt_in_smem(attention_kernel<DP>, (int)smem));
     dim3 grid(ceil_div(Sq, kBM), heads, batch);
     B200SD_CUDA(b200sd_launch(attention_kernel<DP>, dim3(grid), dim3(kThreads), smem, s, q, k, v, out, lse, Sq, Skv, D, ldq, ldk, ldv, ldo,
                                                       scale * 1.4426950408889634f));

@@ -327,12 +327,8 @@ int launch_bwd(const BwdParams& p, int batch, cudaStream_t s) {
     constexpr int DSPLIT = (DP > 96 && (DP / 16) % 2 == 0) ? 2 : 1;
     const size_t smem_dq = (size_t)6 * kT * PITCH;
     const size_t smem_dkv = (size_t)6 * kT * PITCH + 4 * kT * sizeof(float);
-    static bool configured = false;
-    if (!configured) {
-        B200SD_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel<DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_dq));
-        B200SD_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_kernel<DP, DSPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_dkv));
-        configured = true;
-    }
+    B200SD_CUDA(b200sd_opt_in_smem(attn_bwd_dq_kernel<DP>, (int)smem_dq));
+    B200SD_CUDA(b200sd_opt_in_smem(attn_bwd_dkv_kernel<DP, DSPLIT>, (int)smem_dkv));
     B200SD_CUDA(b200sd_launch(attn_bwd_dq_kernel<DP>, dim3(ceil_div(p.Sq, kT), p.heads, batch), dim3(kThreads), smem_dq, s, p));
     COUNT_LAUNCH();
     B200SD_CUDA(b200sd_launch(attn_bwd_dkv_kernel<DP, DSPLIT>, dim3(ceil_div(p.Skv, kT) * DSPLIT, p.heads, batch), dim3(kThreads), smem_dkv, s, p));

@@ -361,11 +361,7 @@ int make_map(CUtensorMap* m, const bf16* ptr, int D, int heads, int64_t rows, in
 template <int D, int DKB, int STAGES, bool DKV, bool ATMEM>
 int launch_one(const BwdTcParams& p, int batch, cudaStream_t s) {
     const size_t smem = (size_t)(2 * DKB + 2 * STAGES * DKB + 4) * kBlk + STAGES * 2 * kT * 4 + 256 + 1024;
-    static bool configured = false;
-    if (!configured) {
-        B200SD_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<D, DKB, STAGES, DKV, ATMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    B200SD_CUDA(b200sd_opt_in_smem(attn_bwd_tc_kernel<D, DKB, STAGES, DKV, ATMEM>, (int)smem));
     B200SD_CUDA(b200sd_launch(attn_bwd_tc_kernel<D, DKB, STAGES, DKV, ATMEM>, dim3(p.Sx / kT, p.heads, batch), dim3(kThreads), smem, s, p));
     g_b200sd_launches.fetch_add(1, std::memory_order_relaxed);
     B200SD_LAUNCH_CHECK();

@@ -391,19 +391,7 @@ int launch_tc(const bf16* q, const bf16* k, const bf16* v, bf16* out, float* lse
     static const float thr = [] { const char* e = getenv("B200SD_ATTN_THR"); return e ? (float)atof(e) : kLazyThr; }();
     p.lazy_thr = thr;
     const size_t smem = (size_t)DKB * kBlk + (size_t)2 * kStages * DKB * kKV * 128 + 256 + 1024;
-    {
-        // per-device opt-in to the large dynamic smem (one static per template instantiation), under a mutex
-        static std::mutex mu;
-        static bool configured[64] = {};
-        int dev = 0;
-        B200SD_CUDA(cudaGetDevice(&dev));
-        std::lock_guard<std::mutex> lock(mu);
-        if (dev >= 0 && dev < 64 && !configured[dev]) {
-            B200SD_CUDA(cudaFuncSetAttribute(attention_tc_kernel<D, DKB, POLY, kStages>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            B200SD_CUDA(cudaFuncSetAttribute(attention_tc_kernel<D, DKB, POLY, kStages>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-            configured[dev] = true;
-        }
-    }
+    B200SD_CUDA(b200sd_opt_in_smem(attention_tc_kernel<D, DKB, POLY, kStages>, (int)smem, /*max_carveout=*/true));
     B200SD_CUDA(b200sd_launch(attention_tc_kernel<D, DKB, POLY, kStages>, dim3((Sq + kQ - 1) / kQ, heads, batch), dim3(192), smem, s, p));
     g_b200sd_launches.fetch_add(1, std::memory_order_relaxed);
     B200SD_LAUNCH_CHECK();

@@ -155,11 +155,7 @@ int launch_attn_f32(const float* q, const float* k, const float* v, float* out, 
                     int ldv, int ldo, float scale, cudaStream_t s) {
     constexpr int D = DQ * 4;
     const size_t smem = ((size_t)3 * 64 * (D + 1) + 64 * 65) * sizeof(float);
-    static bool configured = false;
-    if (!configured) {
-        B200SD_CUDA(cudaFuncSetAttribute(attention_f32_kernel<DQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    B200SD_CUDA(b200sd_opt_in_smem(attention_f32_kernel<DQ>, (int)smem));
     B200SD_CUDA(b200sd_launch(attention_f32_kernel<DQ>, dim3(ceil_div(Sq, kFQ), heads, batch), dim3(kFThreads), smem, s, q, k, v, out, Sq, Skv,
                               ldq, ldk, ldv, ldo, scale));
     COUNT_LAUNCH();

@@ -292,13 +292,9 @@ extern "C" int b200sd_small_linear(const float* in, const void* w_bf16, const fl
     const int rows = batch <= 2 ? 2 : (batch <= 4 ? 4 : 8);
     const size_t smem = (size_t)rows * K * sizeof(float);
     B200SD_REQUIRE(smem <= 96 * 1024, "small_linear: K=%d too large", K);
-    static bool configured = false;
-    if (!configured) {
-        B200SD_CUDA(cudaFuncSetAttribute(small_linear_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-        B200SD_CUDA(cudaFuncSetAttribute(small_linear_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-        B200SD_CUDA(cudaFuncSetAttribute(small_linear_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-        configured = true;
-    }
+    B200SD_CUDA(b200sd_opt_in_smem(small_linear_kernel<2>, 96 * 1024));
+    B200SD_CUDA(b200sd_opt_in_smem(small_linear_kernel<4>, 96 * 1024));
+    B200SD_CUDA(b200sd_opt_in_smem(small_linear_kernel<8>, 96 * 1024));
     int gx = ceil_div(N, 8 * 4);
     const int cap = b200sd_num_sms() * 4;
     if (gx > cap) gx = cap;
@@ -337,11 +333,7 @@ extern "C" int b200sd_conv_out(const void* x_nhwc, const float* w, const float* 
     B200SD_REQUIRE(Cout >= 1 && Cout <= kCoutMax && Cin % 4 == 0, "conv_out: Cout must be <= 4 and Cin a multiple of 4");
     const size_t smem = (size_t)Cout * 9 * Cin * sizeof(float);
     B200SD_REQUIRE(smem <= 96 * 1024, "conv_out: Cin=%d too large", Cin);
-    static bool configured = false;
-    if (!configured) {
-        B200SD_CUDA(cudaFuncSetAttribute(conv_out_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-        configured = true;
-    }
+    B200SD_CUDA(b200sd_opt_in_smem(conv_out_kernel, 96 * 1024));
     const int total = batch * H * W;
     int ppw = ceil_div(total, b200sd_num_sms() * 2 * 8);
     if (ppw < 4) ppw = 4;

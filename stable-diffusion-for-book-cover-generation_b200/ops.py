@@ -198,7 +198,9 @@ def small_linear(x, w_bf16, bias, silu_in=False, silu_out=False, out=None):
 
 
 def gemm_workspace(device):
-    return _workspace("gemm", max(16, lib().b200sd_gemm_workspace_bytes()), device)
+    """Split-K scratch of the GEMM kernels (partial tiles + self-resetting counters, zeroed once).  One buffer per (device, stream):
+    launches that share it must be stream-ordered."""
+    return _workspace(("gemm", _stream()), max(16, lib().b200sd_gemm_workspace_bytes()), device)
 
 
 def gemm(a0, w, out, *, a1=None, bias=None, rowbias=None, residual=None, conv=None, rows_per_image=0,

@@ -187,6 +187,22 @@ def test_bench_image_sharding():
             assert parts == sorted(parts, reverse=True)
 
 
+def test_bench_config_dicts_of_both_arms_are_one_function():
+    """The driver compares the `config` of `bench.py` and `bench.py --impl reference` (same_config): both arms must build it from
+    the same arguments with the same function, and it must name the workload without model-training keys."""
+    import importlib.util, inspect, os
+    spec = importlib.util.spec_from_file_location("bench_mod2", os.path.join(os.path.dirname(os.path.dirname(__file__)), "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    a = bench.sample_config(1, 1, 0, False)
+    assert a["workload"] == "sd15_unet_ddim50_cfg7.5_512px" and a["unet_batch"] == 2 and a["total_images"] == 1
+    assert bench.sample_config(1, 8, 0, False)["total_images"] == 8
+    assert bench.sample_config(2, 4, 7, True)["workload"].endswith("512x768") and bench.sample_config(2, 4, 7, True)["total_images"] == 7
+    src_ref, src_ours = inspect.getsource(bench.run_reference), inspect.getsource(bench.run_ours)
+    assert '"config": sample_config(args.batch, args.gpus, args.total_images, args.portrait)' in src_ref
+    assert '"config": sample_config(' in src_ours
+
+
 def test_pipeline_wrapper_save_load_layout(tmp_path):
     """finetune_sd.py:517-537 builds StableDiffusionPipeline(text_encoder=, vae=, unet=, tokenizer=, scheduler=, safety_checker=,
     feature_extractor=) and save_pretrained()s it; utils.py:187-191 loads it back with safety_checker=None: the diffusers directory
