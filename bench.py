@@ -274,6 +274,59 @@ def elementwise_gbs(dev):
 # ---------------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------------
+class _PerCallSampler:
+    """The per-call loop of pipeline.denoise_loop behind CapturedSampler's surface (fp32-accuracy plan; PLMS)."""
+
+    def __init__(self, unet, sch, B, h, w, dev):
+        import torch
+        self.unet, self.sch, self.B = unet, sch, B
+        self.ts = sch.timesteps.tolist()
+        self.i = 0
+        self.x2 = torch.empty(2 * B, 4, h, w, device=dev)
+        self.latents = torch.empty(B, 4, h, w, device=dev)
+        self.nxt = torch.empty_like(self.latents)
+        self.ctx = None
+        self.kernels_per_step = 0
+        self.lanes = 1
+
+    def set_context(self, ctx):
+        self.ctx = ctx
+
+    def set_latents(self, lat):
+        self.latents.copy_(lat)
+
+    def reset(self, step=0):
+        self.i = step
+
+    def step(self):
+        t = self.ts[self.i % len(self.ts)]
+        self.i += 1
+        B = self.B
+        self.x2[:B].copy_(self.latents)
+        self.x2[B:].copy_(self.latents)
+        eps2 = self.unet(self.x2, t, self.ctx).sample
+        self.sch.step_cfg(eps2, t, self.latents, 7.5, out=self.nxt)
+        self.latents, self.nxt = self.nxt, self.latents
+        eng = next(iter(self.unet._engines.values()))
+        self.kernels_per_step = getattr(eng, "kernels_per_graph", 0)
+        self.engines = [eng]
+
+    def bind_host(self, lat_host, ctx_host, out_host):
+        import torch
+        self._host = (lat_host, ctx_host, out_host)
+        self._ctx_d = torch.empty_like(ctx_host, device=self.latents.device)
+
+    def host_step(self):
+        import torch
+        lat_host, ctx_host, out_host = self._host
+        self.latents.copy_(lat_host, non_blocking=True)
+        self._ctx_d.copy_(ctx_host, non_blocking=True)
+        self.ctx = self._ctx_d
+        self.step()
+        out_host.copy_(self.latents, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -313,17 +366,14 @@ def run_ours(args):
     ctx_host = torch.randn(2 * B, 77, 768, generator=g).pin_memory()
     lat = lat_host.to(dev)
     ctx = ctx_host.to(dev)
-    x2 = torch.empty(2 * B, 4, h, w, device=dev)
-    lat_next = torch.empty_like(lat)
+    # The step a user runs: b200sd.sampler.CapturedSampler -- timestep, UNet plan (one launch chain per CFG half = "lane"), CFG
+    # combine + DDIM update as ONE CUDA graph; pipeline.denoise_loop uses the same object.  --lanes 0 = the library's default.
+    # (--precision fp32, the accuracy path, keeps the per-call loop: UNet graph + one eager CFG/DDIM kernel per step.)
+    from b200sd.sampler import CapturedSampler
+    smp = CapturedSampler(unet, sch, B, h, w, 77, 7.5, lanes=(args.lanes or None)) if args.precision == "bf16" else _PerCallSampler(unet, sch, B, h, w, dev)
 
     def step(i):
-        nonlocal lat, lat_next
-        t = ts[i % len(ts)]
-        x2[:B].copy_(lat)
-        x2[B:].copy_(lat)
-        eps2 = unet(x2, t, ctx).sample
-        sch.step_cfg(eps2, t, lat, 7.5, out=lat_next)
-        lat, lat_next = lat_next, lat
+        smp.step()
 
     def barrier():
         if world > 1:
@@ -331,10 +381,12 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     with torch.no_grad():
+        smp.set_context(ctx)
+        smp.set_latents(lat)
+        smp.reset(0)
         for i in range(max(args.warmup, 3)):
             step(i)          # idle ranks warm up too (keeps the code path uniform), but run no timed steps
-        eng = next(iter(unet._engines.values()))
-        kernels_per_unet = getattr(eng, "kernels_per_graph", 0)
+        eng = smp.engines[0]
         # ---- device-resident timing ----
         barrier()
         sampler = ClockSampler(local) if rank == 0 else None
@@ -347,23 +399,16 @@ def run_ours(args):
         barrier()
         ms = e0.elapsed_time(e1)
         eager_launches = ops.launch_count() - launches0
-        gpu_launches = eager_launches + kernels_per_unet * args.steps
+        gpu_launches = eager_launches + smp.kernels_per_step * (0 if idle else args.steps)
 
-        # ---- end to end through the public API with host buffers (H2D + D2H inside the timed region) ----
+        # ---- end to end through the public API with host buffers (H2D + D2H inside the timed region): every step copies the
+        # latents and the text context out of pinned host memory, projects the context, runs the step and copies the new
+        # latents back; the host waits for them and feeds them to the next step ----
         out_host = torch.empty(B, 4, h, w).pin_memory()
-        lat_d = torch.empty(B, 4, h, w, device=dev)
-        ctx_d = torch.empty(2 * B, 77, 768, device=dev)
+        smp.bind_host(lat_host, ctx_host, out_host)
 
         def e2e_step(i):
-            t = ts[i % len(ts)]
-            lat_d.copy_(lat_host, non_blocking=True)
-            ctx_d.copy_(ctx_host, non_blocking=True)
-            x2[:B].copy_(lat_d)
-            x2[B:].copy_(lat_d)
-            eps2 = unet(x2, t, ctx_d).sample
-            new = sch.step_cfg(eps2, t, lat_d, 7.5).prev_sample
-            out_host.copy_(new, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
+            smp.host_step()
             lat_host.copy_(out_host)
 
         for i in range(3):
@@ -394,6 +439,11 @@ def run_ours(args):
             mm_ms = sum(acc[k][0] for k in ("gemm", "conv3x3") if k in acc)
             mm_fl = sum(acc[k][1] for k in ("gemm", "conv3x3") if k in acc)
             mm_n = sum(acc[k][2] for k in ("gemm", "conv3x3") if k in acc)
+            # `eng` is the plan of ONE lane (its share of the CFG batch); the step runs smp.lanes such chains side by side, so
+            # the step's FLOPs and launches are lanes x the lane's, and the kernel's share of a lane's chain is its share of
+            # the step
+            mm_fl *= smp.lanes
+            mm_n *= smp.lanes
             # The event-record nodes serialise the graph (no tail / launch overlap between kernels) and stretch every interval
             # by a few us: the kernel's SHARE of the instrumented step is what carries over, so its time inside the real step
             # is share x the un-instrumented step time measured above.
@@ -417,7 +467,8 @@ def run_ours(args):
                     "share_of_step": share, "avg_launch_us_instrumented": 1e3 * mm_ms / max(mm_n, 1),
                     "how": "CUDA-graph replay of the step with an event-record node between consecutive kernels (cold weights "
                            "from HBM, true predecessor in L2) gives the kernel's share of the step; achieved = FLOPs / "
-                           "(share x un-instrumented ms_per_step)",
+                           "(share x un-instrumented ms_per_step)" + (f"; the step runs {smp.lanes} independent launch chains "
+                           "(one per CFG half) concurrently: share is measured on one chain, FLOPs and launches count all of them" if smp.lanes > 1 else ""),
                     "traffic": traffic,
                     "traffic_unit": "DRAM bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)"}
             tot = sum(v[0] for v in acc.values())
@@ -453,6 +504,7 @@ def run_ours(args):
             "data": "synthetic",
             "config": sample_config(args.batch if args.total_images <= 0 else B, world, args.total_images, args.portrait),
             "images_per_s": value / 50.0, "e2e_images_per_s": e2e_value / 50.0, "tflops_end_to_end": value * flops_per_it / 1e12,
+            "lanes": smp.lanes,
             "l2": "no flush: the 1.72 GB of bf16 weights streamed every step exceed the 126 MB L2", "cuda_graph": True,
             "e2e": {"value": e2e_value, "unit": "it/s",
                     "h2d_bytes_per_step": int(lat_host.numel() * 4 + ctx_host.numel() * 4),
@@ -465,6 +517,7 @@ def run_ours(args):
     train = train_text = None
     if args.precision == "bf16" and args.total_images <= 0 and not args.portrait and not args.no_train_legs:
         unet._engines = {}                       # the sampling plan's buffers are not needed any more
+        del smp, eng, step, e2e_step
         torch.cuda.empty_cache()
         train = train_leg(dev, world, rank, steps=5, warmup=3, unet=unet)          # same model object: one 860 M-parameter init per rank
         torch.cuda.empty_cache()
@@ -889,6 +942,7 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--batch", type=int, default=1, help="images per GPU (UNet batch = 2x with CFG)")
+    ap.add_argument("--lanes", type=int, default=0, help="concurrent launch chains of the captured step (0 = library default)")
     ap.add_argument("--portrait", action="store_true", help="512x768 book-cover geometry (config 5)")
     ap.add_argument("--total-images", type=int, default=0,
                     help="config 5: shard this many images over the GPUs (strong scaling; overrides --batch)")

@@ -66,6 +66,18 @@ int b200sd_cfg_ddim_step(const void* eps_u, const void* eps_c, const void* x, vo
                          int64_t n, float guidance, float sa_t, float sb_t, float sa_p, float sb_p,
                          int eps_dtype, int x_dtype, b200sd_stream_t stream);
 
+/* Captured sampler: the whole denoising step (timestep -> UNet plan -> CFG + DDIM update) is ONE CUDA graph that is replayed
+ * with no host-side arguments, so the step index lives on the device.  `cursor` is int[2]: [0] = next step, [1] = the step
+ * being executed.  b200sd_sampler_advance opens a step: in_t[0..n_t) = timesteps[cursor[0]] (the UNet plan's timestep input),
+ * cursor[1] = cursor[0], cursor[0] = (cursor[0] + 1) % n_steps.  b200sd_cfg_ddim_step_table closes it: the same kernel as
+ * b200sd_cfg_ddim_step with (sa_t, sb_t, sa_p, sb_p) = coef_table[cursor[1]] ([n_steps][4] floats, 16-byte aligned).
+ * out may alias x (elementwise).  Replaces the per-step Python of StableDiffusionPipeline.__call__'s loop
+ * (reference call sites inference.py:175-176, 342-351). */
+int b200sd_sampler_advance(const float* timesteps, int n_steps, int* cursor, float* in_t, int n_t, b200sd_stream_t stream);
+int b200sd_cfg_ddim_step_table(const void* eps_u, const void* eps_c, const void* x, void* out, void* eps_out,
+                               int64_t n, float guidance, const float* coef_table, const int* cursor,
+                               int eps_dtype, int x_dtype, b200sd_stream_t stream);
+
 /* CFG combine fused with the PLMS (PNDM skip_prk_steps=True) linear-multistep update:
  *   eps = eps_u + g (eps_c - eps_u);  e = w[0] eps + sum_{i<nhist} w[1+i] hist[i];
  *   out = cx * x - ce * e

@@ -18,6 +18,30 @@ void b200sd_set_error(const char* fmt, ...) {
 }
 
 extern "C" const char* b200sd_last_error(void) { return g_err; }
+
+// The opt-in to > 48 KB of dynamic shared memory is a per-DEVICE attribute of a kernel function: set once per (kernel address,
+// device) under a mutex (the C ABI may be called from several threads, and a process may drive several GPUs).
+#include <map>
+#include <utility>
+cudaError_t b200sd_opt_in_smem_impl(const void* kernel, int bytes, bool max_carveout) {
+    static std::mutex mu;
+    static std::map<std::pair<const void*, int>, int> configured;      // (kernel, device) -> bytes opted in
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> lock(mu);
+    auto key = std::make_pair(kernel, dev);
+    auto it = configured.find(key);
+    if (it != configured.end() && it->second >= bytes) return cudaSuccess;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess) return e;
+    if (max_carveout) {
+        e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        if (e != cudaSuccess) return e;
+    }
+    configured[key] = bytes;
+    return cudaSuccess;
+}
 extern "C" int b200sd_version(void) { return 100; }
 extern "C" int64_t b200sd_launch_count(void) { return g_b200sd_launches.load(); }
 

@@ -52,26 +52,13 @@ int b200sd_make_tmap(CUtensorMap* out, const void* base, int rank, const uint64_
                      CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
 
 #ifdef __CUDACC__
-#include <mutex>
 // The opt-in to > 48 KB of dynamic shared memory is a per-DEVICE attribute of a kernel function: set it once per (kernel
 // instantiation, device), under a mutex (the C ABI may be called from several threads, and a process may drive several GPUs).
+// (Keyed on the kernel's ADDRESS, not on its type: instantiations of one kernel template share a function-pointer type.)
+cudaError_t b200sd_opt_in_smem_impl(const void* kernel, int bytes, bool max_carveout);
 template <typename K>
 static inline cudaError_t b200sd_opt_in_smem(K kernel, int bytes, bool max_carveout = false) {
-    static std::mutex mu;
-    static bool configured[64] = {};
-    int dev = 0;
-    cudaError_t e = cudaGetDevice(&dev);
-    if (e != cudaSuccess) return e;
-    std::lock_guard<std::mutex> lock(mu);
-    if (dev >= 0 && dev < 64 && configured[dev]) return cudaSuccess;
-    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    if (e != cudaSuccess) return e;
-    if (max_carveout) {
-        e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-        if (e != cudaSuccess) return e;
-    }
-    if (dev >= 0 && dev < 64) configured[dev] = true;
-    return cudaSuccess;
+    return b200sd_opt_in_smem_impl(reinterpret_cast<const void*>(kernel), bytes, max_carveout);
 }
 
 // Launch with the programmatic-stream-serialization attribute: the next kernel's CTAs may become

@@ -90,9 +90,14 @@ template <int EDT, int XDT>
 __global__ void __launch_bounds__(kThreads) cfg_ddim_kernel(const void* __restrict__ eps_u,
                                                             const void* __restrict__ eps_c,
                                                             const void* __restrict__ x, void* __restrict__ out,
-                                                            void* __restrict__ eps_out, int64_t n, int64_t nvec, DdimCoef c) {
+                                                            void* __restrict__ eps_out, int64_t n, int64_t nvec, DdimCoef c,
+                                                            const float4* __restrict__ coef_table, const int* __restrict__ cursor) {
     ptx::pdl_trigger();
     ptx::pdl_wait();
+    if (coef_table != nullptr) {     // captured sampler: this step's coefficients come from a device table (b200sd_sampler_advance)
+        const float4 v = coef_table[cursor[1]];
+        c.sa_t = v.x, c.sb_t = v.y, c.sa_p = v.z, c.sb_p = v.w;
+    }
     const bool cfg = eps_c != nullptr;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
@@ -328,7 +333,54 @@ extern "C" int b200sd_cfg_ddim_step(const void* eps_u, const void* eps_c, const 
     if (n == 0) return B200SD_OK;
     DdimCoef c{guidance, sa_t, sb_t, sa_p, sb_p};
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    DISPATCH2(eps_dtype, x_dtype, cfg_ddim_kernel, grid_for(vec ? n / 8 : n), s, eps_u, eps_c, x, out, eps_out, n, nvec, c);
+    DISPATCH2(eps_dtype, x_dtype, cfg_ddim_kernel, grid_for(vec ? n / 8 : n), s, eps_u, eps_c, x, out, eps_out, n, nvec, c,
+              (const float4*)nullptr, (const int*)nullptr);
+    COUNT_LAUNCH();
+    B200SD_LAUNCH_CHECK();
+    return B200SD_OK;
+}
+
+// Captured sampler (one CUDA graph per denoising step, replayed with no host-side arguments): the step index lives on the
+// device.  cursor[0] = next step, cursor[1] = the step being executed.
+namespace {
+__global__ void sampler_advance_kernel(const float* __restrict__ timesteps, int n_steps, int* __restrict__ cursor,
+                                       float* __restrict__ in_t, int n_t) {
+    const int c = cursor[0];
+    const float t = timesteps[c];
+    for (int i = threadIdx.x; i < n_t; i += blockDim.x) in_t[i] = t;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        cursor[1] = c;
+        cursor[0] = (c + 1 == n_steps) ? 0 : c + 1;
+    }
+}
+}  // namespace
+
+extern "C" int b200sd_sampler_advance(const float* timesteps, int n_steps, int* cursor, float* in_t, int n_t,
+                                      b200sd_stream_t stream) {
+    B200SD_REQUIRE(timesteps && cursor && in_t, "sampler_advance: null pointer");
+    B200SD_REQUIRE(n_steps > 0 && n_t > 0, "sampler_advance: empty table");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    B200SD_CUDA(b200sd_launch(sampler_advance_kernel, dim3(1), dim3(64), 0, s, timesteps, n_steps, cursor, in_t, n_t));
+    COUNT_LAUNCH();
+    B200SD_LAUNCH_CHECK();
+    return B200SD_OK;
+}
+
+extern "C" int b200sd_cfg_ddim_step_table(const void* eps_u, const void* eps_c, const void* x, void* out, void* eps_out,
+                                          int64_t n, float guidance, const float* coef_table, const int* cursor,
+                                          int eps_dtype, int x_dtype, b200sd_stream_t stream) {
+    B200SD_REQUIRE(eps_u && x && out && coef_table && cursor, "cfg_ddim_step_table: null pointer");
+    B200SD_REQUIRE(n >= 0, "cfg_ddim_step_table: negative n");
+    B200SD_REQUIRE(dtype_ok(eps_dtype) && dtype_ok(x_dtype), "cfg_ddim_step_table: bad dtype");
+    B200SD_REQUIRE(aligned16(coef_table), "cfg_ddim_step_table: coef_table must be 16-byte aligned");
+    const bool vec = aligned16(eps_u) && aligned16(eps_c) && aligned16(x) && aligned16(out) && aligned16(eps_out);
+    const int64_t nvec = vec ? n / 8 : 0;
+    if (n == 0) return B200SD_OK;
+    DdimCoef c{guidance, 1.f, 0.f, 1.f, 0.f};
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    DISPATCH2(eps_dtype, x_dtype, cfg_ddim_kernel, grid_for(vec ? n / 8 : n), s, eps_u, eps_c, x, out, eps_out, n, nvec, c,
+              reinterpret_cast<const float4*>(coef_table), cursor);
     COUNT_LAUNCH();
     B200SD_LAUNCH_CHECK();
     return B200SD_OK;

@@ -60,9 +60,10 @@ class _Plan(list):
 
 
 class Engine:
-    def __init__(self, model, N, H, W, S_ctx, device):
+    def __init__(self, model, N, H, W, S_ctx, device, io=None):
         self.model, self.N, self.H, self.W, self.S = model, N, H, W, S_ctx
         self.device = device
+        self._io = io           # LanedEngine: (in_sample, in_t, out) views of the parent's static buffers
         cfg = model.config
         self.heads = cfg.attention_head_dim
         self.ctx_dim = cfg.cross_attention_dim
@@ -147,10 +148,13 @@ class Engine:
         f32 = dict(dtype=torch.float32, device=dev)
 
         # static inputs
-        self.in_sample = torch.zeros(N, cfg.in_channels, self.H, self.W, **f32)
-        self.in_t = torch.zeros(N, **f32)
+        if self._io is not None:
+            self.in_sample, self.in_t, self.out = self._io
+        else:
+            self.in_sample = torch.zeros(N, cfg.in_channels, self.H, self.W, **f32)
+            self.in_t = torch.zeros(N, **f32)
+            self.out = torch.zeros(N, cfg.out_channels, self.H, self.W, **f32)
         self.in_ctx = torch.zeros(N * self.S, self.ctx_dim, dtype=torch.bfloat16, device=dev)
-        self.out = torch.zeros(N, cfg.out_channels, self.H, self.W, **f32)
 
         # ---- time embedding: sinusoid -> MLP -> all 22 time_emb_proj heads in one launch ----
         temb_dim = boc[0] * 4

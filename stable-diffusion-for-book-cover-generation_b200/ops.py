@@ -372,7 +372,7 @@ def groupnorm_silu(x0, x1, gamma, beta, out, batch, hw, groups=32, eps=1e-5, sil
     _chk(x0, x1, gamma, beta, out, raw_out, stats_out)
     if x1 is not None and x1.dtype != x0.dtype:
         raise B200SDError("groupnorm: both sources must have the same dtype")
-    ws = _workspace("gn", lib().b200sd_groupnorm_workspace_floats(batch) * 4, x0.device)
+    ws = _workspace(("gn", _stream()), lib().b200sd_groupnorm_workspace_floats(batch) * 4, x0.device)   # per stream: lanes run concurrently
     C0 = x0.shape[-1]
     C1 = x1.shape[-1] if x1 is not None else 0
     check(lib().b200sd_groupnorm_silu_stats(_p(x0), _p(x1), C0, C1, _p(gamma), _p(beta), _p(out), _p(raw_out), _p(ws),

@@ -16,6 +16,9 @@ def denoise_loop(unet, scheduler, latents, encoder_hidden_states_2b, num_inferen
     if encoder_hidden_states_2b.shape[0] != 2 * latents.shape[0]:
         raise ValueError("encoder_hidden_states must be cat([uncond, cond]) with batch 2B")
     scheduler.set_timesteps(num_inference_steps)
+    sampler = _captured_sampler(unet, scheduler, latents, encoder_hidden_states_2b, guidance_scale) if record is None else None
+    if sampler is not None:
+        return sampler.run(latents, encoder_hidden_states_2b).to(latents.dtype)
     latents = (latents * scheduler.init_noise_sigma).float().contiguous()
     x2 = torch.empty((2 * latents.shape[0],) + tuple(latents.shape[1:]), dtype=latents.dtype, device=latents.device)
     B = latents.shape[0]
@@ -28,6 +31,30 @@ def denoise_loop(unet, scheduler, latents, encoder_hidden_states_2b, num_inferen
         latents = scheduler.step_cfg(eps2.float() if eps2.dtype not in (torch.float32, torch.bfloat16) else eps2, t,
                                      latents, guidance_scale).prev_sample
     return latents
+
+
+def _captured_sampler(unet, scheduler, latents, ctx2, guidance_scale):
+    """The whole-step CUDA graph (sampler.CapturedSampler) when the combination is covered: b200sd UNet on its bf16 plan with
+    CUDA graphs on, DDIM, CUDA tensors.  Cached on the UNet per (geometry, schedule, guidance); None -> the per-call loop."""
+    from .schedulers import DDIMScheduler
+    from .unet import UNet2DConditionModel
+    if not (isinstance(unet, UNet2DConditionModel) and isinstance(scheduler, DDIMScheduler) and latents.is_cuda
+            and unet._precision == "bf16" and unet.use_cuda_graph and not unet.training):
+        return None
+    from .sampler import CapturedSampler, default_lanes
+    B, _, h, w = latents.shape
+    key = (B, h, w, ctx2.shape[1], latents.device.index, float(guidance_scale), default_lanes(B),
+           tuple(scheduler.timesteps.tolist()), tuple(sorted((k, str(v)) for k, v in vars(scheduler.config).items())))
+    cache = unet.__dict__.setdefault("_samplers", {})
+    smp = cache.get(key)
+    if smp is not None and unet._stale(smp._pack_gen):
+        cache.clear()
+        smp = None
+    if smp is None:
+        if len(cache) >= 4:
+            cache.clear()          # each sampler owns a full set of activation buffers
+        smp = cache[key] = CapturedSampler(unet, scheduler, B, h, w, ctx2.shape[1], guidance_scale)
+    return smp
 
 
 # ---------------------------------------------------------------------------------------------------

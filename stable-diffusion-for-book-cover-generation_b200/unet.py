@@ -390,6 +390,18 @@ class UNet2DConditionModel(nn.Module):
         self._dirty = False
         self._param_versions = self._versions()
 
+    def _ensure_packed(self):
+        """(Re)pack the kernel-layout weights when the parameters changed; engines built on the old packing are dropped."""
+        if self._dirty or self._packed is None or self._versions() != self._param_versions:
+            self._pack_weights()
+            self._engines = {}
+            self.__dict__["_pack_gen"] = self.__dict__.get("_pack_gen", 0) + 1
+        return self.__dict__.setdefault("_pack_gen", 0)
+
+    def _stale(self, pack_gen):
+        """True when plans built at packing generation `pack_gen` (CapturedSampler) no longer match the parameters."""
+        return self._ensure_packed() != pack_gen
+
     def _versions(self):
         # called on EVERY forward: the parameter list is cached (walking the module tree costs ~1 ms for 686 parameters, which is
         # 20 % of a 5 ms denoising step on the host side); nn.Parameter objects are never replaced by .to() / load_state_dict()
@@ -441,9 +453,7 @@ class UNet2DConditionModel(nn.Module):
 
         # version sum of the 686 parameters: catches in-place optimizer steps in eval mode too (the fused flat AdamW bumps no
         # version and calls mark_weights_changed() instead)
-        if self._dirty or self._packed is None or self._versions() != self._param_versions:
-            self._pack_weights()
-            self._engines = {}
+        self._ensure_packed()
         key = (N, H, Wd, ctx.shape[1], sample.device.index, self._precision)
         eng = self._engines.get(key)
         if eng is None:

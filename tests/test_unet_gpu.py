@@ -271,3 +271,130 @@ def test_context_cache_is_not_fooled_by_address_reuse(models):
         same_address = ctx_b.data_ptr() == ptr_a
         want = ours(x, 500, ctx_b.clone()).sample     # a different object: always re-projected
     assert torch.equal(got, want), f"stale context K/V (address reused: {same_address})"
+
+
+# ---------------------------------------------------------------------------------------------------
+# CapturedSampler: the whole denoising step as one CUDA graph, CFG halves on concurrent lanes
+# ---------------------------------------------------------------------------------------------------
+_DDIM_KW = dict(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear", clip_sample=False, set_alpha_to_one=False)
+
+
+@pytest.fixture(scope="module")
+def oracle_50_step(models):
+    from oracle import schedulers_ref as R
+    oracle, _ours = models
+    g = torch.Generator().manual_seed(42)
+    lat = torch.randn(1, 4, 64, 64, generator=g)
+    ctx2 = torch.randn(2, 77, 768, generator=g)
+    oc = oracle.to(DEV)
+    try:
+        with torch.no_grad():
+            want = R.denoise_loop(oc, R.DDIMSchedulerRef(clip_sample=False, set_alpha_to_one=False), lat.to(DEV), ctx2.to(DEV), 50, 7.5)
+    finally:
+        oracle.to("cpu")
+    return lat, ctx2, want.cpu()
+
+
+@pytest.mark.parametrize("lanes", [1, 2])
+def test_captured_sampler_50_steps_vs_oracle(models, oracle_50_step, lanes):
+    """BASELINE config 2 through the one-graph-per-step sampler (what bench.py times): 50-step latents cosine >= 0.999 vs the
+    fp32 oracle loop, with the two CFG halves on one lane and on two concurrent lanes."""
+    from b200sd.sampler import CapturedSampler
+    from b200sd.schedulers import DDIMScheduler
+    _oracle, ours = models
+    lat, ctx2, want = oracle_50_step
+    sch = DDIMScheduler(**_DDIM_KW)
+    sch.set_timesteps(50)
+    smp = CapturedSampler(ours, sch, 1, 64, 64, 77, 7.5, lanes=lanes)
+    got = smp.run(lat.to(DEV), ctx2.to(DEV)).cpu()
+    cos = float(torch.nn.functional.cosine_similarity(got.flatten(), want.flatten(), dim=0))
+    assert cos >= 0.999, f"lanes={lanes}: 50-step latents cosine {cos:.6f}"
+    # the same sampler object again, other latents first: no state leaks between runs (cursor, context K/V, latents)
+    smp.run(torch.randn(1, 4, 64, 64).to(DEV), ctx2.flip(0).to(DEV))
+    again = smp.run(lat.to(DEV), ctx2.to(DEV)).cpu()
+    assert torch.equal(again, got), "a second run of the captured sampler on the same inputs must be bit-identical"
+
+
+def test_denoise_loop_takes_the_captured_sampler_and_matches_the_per_call_loop(models, oracle_50_step):
+    from b200sd.pipeline import denoise_loop
+    from b200sd.schedulers import DDIMScheduler
+    _oracle, ours = models
+    lat, ctx2, want = oracle_50_step
+    rec = []
+    per_call = denoise_loop(ours, DDIMScheduler(**_DDIM_KW), lat.to(DEV), ctx2.to(DEV), 50, 7.5, record=rec).cpu()   # record -> per-call loop
+    captured = denoise_loop(ours, DDIMScheduler(**_DDIM_KW), lat.to(DEV), ctx2.to(DEV), 50, 7.5).cpu()
+    assert getattr(ours, "_samplers", None), "denoise_loop did not build a CapturedSampler"
+    cos = float(torch.nn.functional.cosine_similarity(captured.flatten(), per_call.flatten(), dim=0))
+    assert cos >= 0.9995, f"captured vs per-call loop cosine {cos:.6f}"
+    cos_o = float(torch.nn.functional.cosine_similarity(captured.flatten(), want.flatten(), dim=0))
+    assert cos_o >= 0.999
+
+
+def test_captured_sampler_host_step_equals_device_steps(models):
+    """host_step(): H2D latents + context out of pinned buffers, context K/V, step, D2H -- the same numbers as step()."""
+    from b200sd.sampler import CapturedSampler
+    from b200sd.schedulers import DDIMScheduler
+    _oracle, ours = models
+    g = torch.Generator().manual_seed(7)
+    lat = torch.randn(1, 4, 64, 64, generator=g)
+    ctx2 = torch.randn(2, 77, 768, generator=g)
+    sch = DDIMScheduler(**_DDIM_KW)
+    sch.set_timesteps(50)
+    smp = CapturedSampler(ours, sch, 1, 64, 64, 77, 7.5)
+    smp.set_context(ctx2.to(DEV))
+    smp.set_latents(lat.to(DEV))
+    smp.reset(0)
+    for _ in range(3):
+        smp.step()
+    want = smp.latents.cpu()
+    lat_h, ctx_h, out_h = lat.clone().pin_memory(), ctx2.clone().pin_memory(), torch.empty(1, 4, 64, 64).pin_memory()
+    smp.bind_host(lat_h, ctx_h, out_h)
+    smp.reset(0)
+    for _ in range(3):
+        smp.host_step()
+        lat_h.copy_(out_h)
+    assert torch.equal(out_h, want)
+
+
+def test_captured_sampler_refuses_stale_weights(models):
+    from b200sd.sampler import CapturedSampler
+    from b200sd.schedulers import DDIMScheduler
+    from b200sd._lib import B200SDError
+    _oracle, ours = models
+    sch = DDIMScheduler(**_DDIM_KW)
+    sch.set_timesteps(4)
+    smp = CapturedSampler(ours, sch, 1, 64, 64, 77, 7.5)
+    w = ours.conv_out.bias
+    with torch.no_grad():
+        w.add_(1.0)
+    try:
+        with pytest.raises(B200SDError):
+            smp.run(torch.randn(1, 4, 64, 64).to(DEV), torch.randn(2, 77, 768).to(DEV))
+    finally:
+        with torch.no_grad():
+            w.sub_(1.0)
+
+
+@pytest.mark.parametrize("lanes", [1, 2, 4])
+def test_captured_sampler_batched_portrait_tiny_net(lanes):
+    """2 images (UNet batch 4) at a portrait geometry on the reduced-width network: lanes 1 / 2 / 4 (sub-batches of one CFG
+    half) all reproduce the oracle loop."""
+    from b200sd.sampler import CapturedSampler
+    from b200sd.schedulers import DDIMScheduler
+    from b200sd.unet import UNet2DConditionModel
+    from oracle import schedulers_ref as R
+    from oracle.unet_ref import TINY_OVERRIDES, make_oracle_unet
+    oracle = make_oracle_unet(seed=0, **TINY_OVERRIDES)
+    ours = UNet2DConditionModel(**TINY_OVERRIDES)
+    ours.load_state_dict(oracle.state_dict(), strict=True)
+    ours = ours.to(DEV).eval()
+    g = torch.Generator().manual_seed(3)
+    lat = torch.randn(2, 4, 48, 32, generator=g)
+    ctx2 = torch.randn(4, 77, 64, generator=g)
+    with torch.no_grad():
+        want = R.denoise_loop(oracle, R.DDIMSchedulerRef(clip_sample=False, set_alpha_to_one=False), lat, ctx2, 6, 7.5)
+    sch = DDIMScheduler(**_DDIM_KW)
+    sch.set_timesteps(6)
+    got = CapturedSampler(ours, sch, 2, 48, 32, 77, 7.5, lanes=lanes).run(lat.to(DEV), ctx2.to(DEV)).cpu()
+    cos = float(torch.nn.functional.cosine_similarity(got.flatten(), want.flatten(), dim=0))
+    assert cos >= 0.999, f"lanes={lanes}: cosine {cos:.6f}"
