@@ -700,43 +700,34 @@ def train_leg(dev, world, rank, steps=5, warmup=3, B=8, unet=None):
 
 def train_text_leg(dev, world, rank, local, steps=5, warmup=3, B=8, unet=None):
     """BASELINE configs[3]: text-encoder fine-tuning (UNet frozen: our forward + data-gradient-only backward down to the context;
-    CLIP text model = stock transformers under DistributedDataParallel) at batch 8/GPU."""
+    CLIP text model = b200sd.clip.CLIPTextModel, forward and backward on our kernels; flat-gradient allreduce + fused AdamW in
+    trainer.TextEncoderTrainer) at batch 8/GPU."""
     import torch
-    from transformers import CLIPTextConfig, CLIPTextModel
-    from b200sd import ops
+    from b200sd.clip import CLIPTextModel
     from b200sd.schedulers import DDPMScheduler
+    from b200sd.trainer import TextEncoderTrainer
     from b200sd.unet import UNet2DConditionModel
     torch.manual_seed(0)
     if unet is None:
         unet = UNet2DConditionModel().to(dev)
     unet = unet.eval().requires_grad_(False)                                      # finetune_sd.py:391-395
-    clip = CLIPTextModel(CLIPTextConfig(hidden_size=768, intermediate_size=3072, num_hidden_layers=12, num_attention_heads=12,
-                                        vocab_size=49408, max_position_embeddings=77, hidden_act="quick_gelu")).to(dev).train()
-    model = torch.nn.parallel.DistributedDataParallel(clip, device_ids=[local], gradient_as_bucket_view=True, bucket_cap_mb=int(os.environ.get('B200SD_DDP_BUCKET_MB', '128'))) if world > 1 else clip
-    opt = torch.optim.AdamW(clip.parameters(), lr=1e-5, weight_decay=1e-2, fused=True)
+    clip = CLIPTextModel().to(dev).train()                                        # SD v1.x text tower, random init (123.1 M)
     sched = DDPMScheduler(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear", num_train_timesteps=1000)
+    tr = TextEncoderTrainer(clip, unet, sched, lr=1e-5, weight_decay=1e-2)
     g = torch.Generator().manual_seed(1000 + rank)
     x0, noise = torch.randn(B, 4, 64, 64, generator=g).to(dev), torch.randn(B, 4, 64, 64, generator=g).to(dev)
     t, ids = torch.randint(0, 1000, (B,), generator=g).to(dev), torch.randint(0, 49408, (B, 77), generator=g).to(dev)
     last = []
 
-    def step(m=model):
-        with torch.autocast("cuda", dtype=torch.bfloat16):
-            ctx = m(ids)[0]                                                        # finetune_sd.py:477
-        noisy = sched.add_noise(x0, noise, t)
-        loss = ops.mse_loss(unet(noisy, t, ctx.float()).sample, noise)
-        loss.backward()
-        opt.step()
-        opt.zero_grad(set_to_none=True)
-        last[:] = [loss.detach()]
+    def step():
+        last[:] = [tr.train_step(x0, noise, t, ids)]                               # finetune_sd.py:477-494, 569-570
 
     ms = _timed_steps(step, steps, warmup, world, dev)
     ms_local = ms
     if world > 1:
-        def local_step():
-            with model.no_sync():          # same step, DDP's allreduce suppressed
-                step()
-        ms_local = _timed_steps(local_step, steps, 1, world, dev)
+        tr.allreduce_enabled = False       # same step, every rank on its local gradient
+        ms_local = _timed_steps(step, steps, 1, world, dev)
+        tr.allreduce_enabled = True
     n_param = sum(p.numel() for p in clip.parameters())
     _, _, tf_sus, _ = _peaks()
     flops_step = 2 * B * FLOPS_PER_SAMPLE_64
@@ -744,8 +735,9 @@ def train_text_leg(dev, world, rank, local, steps=5, warmup=3, B=8, unet=None):
            "ms_per_step": ms, "samples_per_s": B * world / (ms * 1e-3), "ms_per_step_without_allreduce": ms_local,
            "exposed_comm_ms": ms - ms_local, "allreduce_bytes_on_wire_per_gpu": int(2 * (world - 1) / world * n_param * 4),
            "tflops_per_gpu": flops_step / (ms * 1e-3) / 1e12, "frac_of_sustained_bf16_peak": flops_step / (ms * 1e-3) / 1e12 / tf_sus,
-           "last_loss": float(last[0]), "collective": "torch DistributedDataParallel (NCCL) over the 123.1 M CLIP parameters"}
-    del model, clip, opt
+           "last_loss": float(last[0]), "text_encoder": "b200sd.clip.CLIPTextModel (own kernels, forward + backward)",
+           "collective": "NCCL all_reduce(SUM) of the flat fp32 gradient buffer of the 123.1 M CLIP parameters (4 chunks) + fused AdamW"}
+    del tr, clip
     return rec
 
 
@@ -845,14 +837,15 @@ def run_train(args):
 
 # ---------------------------------------------------------------------------------------------------
 # text-encoder fine-tuning (BASELINE config 4): UNet frozen (our forward + dgrad-only backward down to the context),
-# CLIP text encoder = stock transformers / torch (a neighbour of the hot path), DDP over NCCL
+# CLIP text encoder = b200sd.clip.CLIPTextModel (forward + backward on our kernels), flat-gradient allreduce
 # ---------------------------------------------------------------------------------------------------
 def run_train_text(args):
     import torch
     import torch.distributed as dist
-    from transformers import CLIPTextConfig, CLIPTextModel
     from b200sd import ops
+    from b200sd.clip import CLIPTextModel
     from b200sd.schedulers import DDPMScheduler
+    from b200sd.trainer import TextEncoderTrainer
     from b200sd.unet import UNet2DConditionModel
 
     rank = int(os.environ.get("RANK", 0))
@@ -865,25 +858,17 @@ def run_train_text(args):
     B = args.batch if args.batch > 1 else 8
     torch.manual_seed(0)
     unet = UNet2DConditionModel().to(dev).eval().requires_grad_(False)            # finetune_sd.py:391-395
-    clip = CLIPTextModel(CLIPTextConfig(hidden_size=768, intermediate_size=3072, num_hidden_layers=12, num_attention_heads=12,
-                                        vocab_size=49408, max_position_embeddings=77, hidden_act="quick_gelu")).to(dev).train()
-    model = torch.nn.parallel.DistributedDataParallel(clip, device_ids=[local], gradient_as_bucket_view=True, bucket_cap_mb=int(os.environ.get('B200SD_DDP_BUCKET_MB', '128'))) if world > 1 else clip
-    opt = torch.optim.AdamW(clip.parameters(), lr=1e-5, weight_decay=1e-2, fused=True)
+    clip = CLIPTextModel().to(dev).train()
     sched = DDPMScheduler(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear", num_train_timesteps=1000)
     g = torch.Generator().manual_seed(1000 + rank)
     host = dict(x0=torch.randn(B, 4, 64, 64, generator=g).pin_memory(), noise=torch.randn(B, 4, 64, 64, generator=g).pin_memory(),
                 t=torch.randint(0, 1000, (B,), generator=g).pin_memory(), ids=torch.randint(0, 49408, (B, 77), generator=g).pin_memory())
     d = {k: v.to(dev) for k, v in host.items()}
 
+    tr = TextEncoderTrainer(clip, unet, sched, lr=1e-5, weight_decay=1e-2)
+
     def step(b):
-        with torch.autocast("cuda", dtype=torch.bfloat16):
-            ctx = model(b["ids"])[0]                                                # finetune_sd.py:477
-        noisy = sched.add_noise(b["x0"], b["noise"], b["t"])
-        loss = ops.mse_loss(unet(noisy, b["t"], ctx.float()).sample, b["noise"])
-        loss.backward()
-        opt.step()
-        opt.zero_grad(set_to_none=True)
-        return loss.detach()
+        return tr.train_step(b["x0"], b["noise"], b["t"], b["ids"])                # finetune_sd.py:477-494, 569-570
 
     def barrier():
         if world > 1:
@@ -924,7 +909,7 @@ def run_train_text(args):
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": "sd15_text_encoder_finetune_512px", "batch_per_gpu": B, "latent": "4x64x64", "tokens": 77,
-                       "step": "CLIP fwd (torch) + add_noise + frozen UNet fwd + MSE + UNet dgrad-only bwd -> d ctx + CLIP bwd (torch) + DDP allreduce + AdamW",
+                       "step": "CLIP fwd + add_noise + frozen UNet fwd + MSE + UNet dgrad-only bwd -> d ctx + CLIP bwd + flat-gradient allreduce + fused AdamW (all b200sd kernels)",
                        "last_loss": loss_val},
             "e2e": {"value": samples / (e2e_ms * 1e-3), "unit": "samples/s",
                     "h2d_bytes_per_step": int(sum(v.numel() * v.element_size() for v in host.values())), "d2h_bytes_per_step": 4},

@@ -299,6 +299,32 @@ int b200sd_attention_bwd(const void* q, const void* k, const void* v, const void
                          int ldq, int ldk, int ldv, int ldo, int lddo, int lddq, int lddk, int lddv, float scale,
                          void* workspace, size_t workspace_bytes, b200sd_stream_t stream);
 
+/* ---- CLIP text encoder: the non-GEMM kernels of transformers' CLIPTextModel forward / backward ----------
+ * Reference call sites: finetune_sd.py:322-324 (load), 375-379 (train), 477 (`text_encoder(batch["input_ids"])[0]`).
+ * The linears of the 12 layers run on b200sd_gemm / _dgrad / _wgrad, LayerNorm 1/2 on b200sd_layernorm(_bwd). */
+
+/* x[b*S + s][:] = tok[ids[b][s]][:] + pos[s][:]   (ids int64 [batch][S]; tok fp32 [vocab][C]; pos fp32 [S][C]; x fp32). */
+int b200sd_clip_embed(const int64_t* ids, const float* tok, const float* pos, float* out, int batch, int S, int C, int vocab,
+                      b200sd_stream_t stream);
+/* dtok[ids[b][s]] += dx[b][s] (fp32 atomics: a token may repeat), dpos[s] += sum_b dx[b][s] (fixed order). */
+int b200sd_clip_embed_bwd(const int64_t* ids, const float* dx, float* dtok, float* dpos, int batch, int S, int C, int vocab,
+                          b200sd_stream_t stream);
+/* quick-GELU (CLIP's hidden_act): out = u * sigmoid(1.702 u);  du = dg * d/du of that.  bf16, n % 8 == 0. */
+int b200sd_quick_gelu_fwd(const void* u, void* out, int64_t n, b200sd_stream_t stream);
+int b200sd_quick_gelu_bwd(const void* u, const void* dg, void* du, int64_t n, b200sd_stream_t stream);
+/* LayerNorm fp32 [rows, C] -> fp32 (CLIP's final_layer_norm: the text context keeps fp32). */
+int b200sd_layernorm_f32out(const float* x, const float* gamma, const float* beta, float* out, int rows, int C, float eps,
+                            b200sd_stream_t stream);
+/* Causal multi-head attention over S <= 96 tokens, head dim d <= 64 (d % 8 == 0): one CTA per (prompt, head), Q/K/V/P of
+ * the head in shared memory.  qkv bf16 [batch*S][ld] with q / k / v of head h at columns {q,k,v}_off + h*d;
+ * out bf16 [batch*S][ldo] at column h*d.  out = softmax_causal(scale * q k^T) v. */
+int b200sd_causal_attention(const void* qkv, void* out, int batch, int heads, int S, int d, int ld, int ldo, int q_off,
+                            int k_off, int v_off, float scale, b200sd_stream_t stream);
+/* Backward of b200sd_causal_attention (probabilities recomputed; deterministic): dqkv bf16 [batch*S][ldd], same column
+ * layout as qkv; dout bf16 [batch*S][lddo]. */
+int b200sd_causal_attention_bwd(const void* qkv, const void* dout, void* dqkv, int batch, int heads, int S, int d, int ld,
+                                int lddo, int ldd, int q_off, int k_off, int v_off, float scale, b200sd_stream_t stream);
+
 /* ---- non-GEMM kernels of the backward pass ----------------------------------- */
 
 /* Gradient prep: optional bf16 copy of a [rows, N] (pitch ld) gradient (the tensor-core operand of

@@ -58,6 +58,13 @@ SIGNATURES = {
     "b200sd_timer_record": (_i, [_i, _vp]),
     "b200sd_timer_elapsed_ms": (_i, [_i, _i, C.POINTER(C.c_float)]),
     "b200sd_cfg_ddim_step": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _f, _f, _f, _f, _f, _i, _i, _vp]),
+    "b200sd_clip_embed": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "b200sd_clip_embed_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "b200sd_quick_gelu_fwd": (_i, [_vp, _vp, _i64, _vp]),
+    "b200sd_quick_gelu_bwd": (_i, [_vp, _vp, _vp, _i64, _vp]),
+    "b200sd_layernorm_f32out": (_i, [_vp, _vp, _vp, _vp, _i, _i, _f, _vp]),
+    "b200sd_causal_attention": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _vp]),
+    "b200sd_causal_attention_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _vp]),
     "b200sd_sampler_advance": (_i, [_vp, _i, _vp, _vp, _i, _vp]),
     "b200sd_cfg_ddim_step_table": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _f, _vp, _vp, _i, _i, _vp]),
     "b200sd_cfg_plms_step": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, C.POINTER(C.c_float), _i64, _f, _f,

@@ -591,3 +591,59 @@ def small_linear_f32(x, w, bias, silu_in=False, silu_out=False, out=None):
     check(lib().b200sd_small_linear_f32(_p(x), _p(w), _p(bias), _p(out), B, N, K, int(silu_in), int(silu_out), _stream()),
           "small_linear_f32")
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# CLIP text encoder
+# ---------------------------------------------------------------------------------------------
+def clip_embed(ids, tok, pos, out):
+    _chk(ids, tok, pos, out)
+    B, S = ids.shape
+    check(lib().b200sd_clip_embed(_p(ids), _p(tok), _p(pos), _p(out), B, S, tok.shape[1], tok.shape[0], _stream()), "clip_embed")
+    return out
+
+
+def clip_embed_bwd(ids, dx, dtok, dpos):
+    _chk(ids, dx, dtok, dpos)
+    B, S = ids.shape
+    check(lib().b200sd_clip_embed_bwd(_p(ids), _p(dx), _p(dtok), _p(dpos), B, S, dtok.shape[1], dtok.shape[0], _stream()),
+          "clip_embed_bwd")
+
+
+def quick_gelu_fwd(u, out):
+    _chk(u, out)
+    check(lib().b200sd_quick_gelu_fwd(_p(u), _p(out), u.numel(), _stream()), "quick_gelu_fwd")
+    return out
+
+
+def quick_gelu_bwd(u, dg, du):
+    _chk(u, dg, du)
+    check(lib().b200sd_quick_gelu_bwd(_p(u), _p(dg), _p(du), u.numel(), _stream()), "quick_gelu_bwd")
+    return du
+
+
+def layernorm_f32out(x, gamma, beta, out, eps=1e-5):
+    _chk(x, gamma, beta, out)
+    if x.dtype != torch.float32 or out.dtype != torch.float32:
+        raise B200SDError("layernorm_f32out: fp32 in, fp32 out")
+    Cc = x.shape[-1]
+    check(lib().b200sd_layernorm_f32out(_p(x), _p(gamma), _p(beta), _p(out), x.numel() // Cc, Cc, float(eps), _stream()),
+          "layernorm_f32out")
+    return out
+
+
+def causal_attention(qkv, out, batch, heads, S, d, scale):
+    """qkv bf16 [batch*S, 3*heads*d] = [q | k | v]; out bf16 [batch*S, heads*d]"""
+    _chk(qkv, out)
+    Cc = heads * d
+    check(lib().b200sd_causal_attention(_p(qkv), _p(out), batch, heads, S, d, qkv.shape[-1], out.shape[-1], 0, Cc, 2 * Cc,
+                                        float(scale), _stream()), "causal_attention")
+    return out
+
+
+def causal_attention_bwd(qkv, dout, dqkv, batch, heads, S, d, scale):
+    _chk(qkv, dout, dqkv)
+    Cc = heads * d
+    check(lib().b200sd_causal_attention_bwd(_p(qkv), _p(dout), _p(dqkv), batch, heads, S, d, qkv.shape[-1], dout.shape[-1],
+                                            dqkv.shape[-1], 0, Cc, 2 * Cc, float(scale), _stream()), "causal_attention_bwd")
+    return dqkv

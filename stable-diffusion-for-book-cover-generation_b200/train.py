@@ -73,57 +73,8 @@ class FlatParams:
                     raise B200SDError("fused weight regions must be multiples of 64 elements")
                 add(p, kind)
 
-        def add_resnet(r):
-            add(r.norm1.weight, "vec"); add(r.norm1.bias, "vec")
-            add(r.conv1.weight, "conv3"); add(r.conv1.bias, "vec")
-            add(r.norm2.weight, "vec"); add(r.norm2.bias, "vec")
-            add(r.conv2.weight, "conv3"); add(r.conv2.bias, "vec")
-            if hasattr(r, "conv_shortcut"):
-                add(r.conv_shortcut.weight, "lin"); add(r.conv_shortcut.bias, "vec")
-
-        def add_xformer(a):
-            blk = a.transformer_blocks[0]
-            add(a.norm.weight, "vec"); add(a.norm.bias, "vec")
-            add(a.proj_in.weight, "lin"); add(a.proj_in.bias, "vec")
-            for n in (blk.norm1, blk.norm2, blk.norm3):
-                add(n.weight, "vec"); add(n.bias, "vec")
-            add_adjacent([blk.attn1.to_q.weight, blk.attn1.to_k.weight, blk.attn1.to_v.weight], "lin")
-            add(blk.attn1.to_out[0].weight, "lin"); add(blk.attn1.to_out[0].bias, "vec")
-            add(blk.attn2.to_q.weight, "lin")
-            add_adjacent([blk.attn2.to_k.weight, blk.attn2.to_v.weight], "lin")
-            add(blk.attn2.to_out[0].weight, "lin"); add(blk.attn2.to_out[0].bias, "vec")
-            add(blk.ff.net[0].proj.weight, "lin"); add(blk.ff.net[0].proj.bias, "vec")
-            add(blk.ff.net[2].weight, "lin"); add(blk.ff.net[2].bias, "vec")
-            add(a.proj_out.weight, "lin"); add(a.proj_out.bias, "vec")
-
-        def add_sampler(s):
-            add(s.conv.weight, "conv3"); add(s.conv.bias, "vec")
-
         m = model
-        te = m.time_embedding
-        add(te.linear_1.weight, "lin"); add(te.linear_1.bias, "vec")
-        add(te.linear_2.weight, "lin"); add(te.linear_2.bias, "vec")
-        resnets = list(m._iter_resnets())
-        add_adjacent([r.time_emb_proj.weight for _, r in resnets], "lin")
-        add_adjacent([r.time_emb_proj.bias for _, r in resnets], "vec")
-        add(m.conv_in.weight, "conv_f32"); add(m.conv_in.bias, "vec")
-        for b in m.down_blocks:
-            for j, r in enumerate(b.resnets):
-                add_resnet(r)
-                if hasattr(b, "attentions"):
-                    add_xformer(b.attentions[j])
-            if hasattr(b, "downsamplers"):
-                add_sampler(b.downsamplers[0])
-        add_resnet(m.mid_block.resnets[0]); add_xformer(m.mid_block.attentions[0]); add_resnet(m.mid_block.resnets[1])
-        for b in m.up_blocks:
-            for j, r in enumerate(b.resnets):
-                add_resnet(r)
-                if hasattr(b, "attentions"):
-                    add_xformer(b.attentions[j])
-            if hasattr(b, "upsamplers"):
-                add_sampler(b.upsamplers[0])
-        add(m.conv_norm_out.weight, "vec"); add(m.conv_norm_out.bias, "vec")
-        add(m.conv_out.weight, "conv_f32"); add(m.conv_out.bias, "vec")
+        self._layout(model, add, add_adjacent)
         missing = [n for n, p in m.named_parameters() if id(p) not in self.regs]
         if missing:
             raise B200SDError(f"FlatParams: parameters not laid out: {missing[:4]}...")
@@ -156,6 +107,60 @@ class FlatParams:
         self._versions = None
         if not lazy:
             self.materialize()
+
+    def _layout(self, m, add, add_adjacent):
+        """Register every parameter of the model, in the order the forward uses them (subclasses: other model families)."""
+        def add_resnet(r):
+            add(r.norm1.weight, "vec"); add(r.norm1.bias, "vec")
+            add(r.conv1.weight, "conv3"); add(r.conv1.bias, "vec")
+            add(r.norm2.weight, "vec"); add(r.norm2.bias, "vec")
+            add(r.conv2.weight, "conv3"); add(r.conv2.bias, "vec")
+            if hasattr(r, "conv_shortcut"):
+                add(r.conv_shortcut.weight, "lin"); add(r.conv_shortcut.bias, "vec")
+
+        def add_xformer(a):
+            blk = a.transformer_blocks[0]
+            add(a.norm.weight, "vec"); add(a.norm.bias, "vec")
+            add(a.proj_in.weight, "lin"); add(a.proj_in.bias, "vec")
+            for n in (blk.norm1, blk.norm2, blk.norm3):
+                add(n.weight, "vec"); add(n.bias, "vec")
+            add_adjacent([blk.attn1.to_q.weight, blk.attn1.to_k.weight, blk.attn1.to_v.weight], "lin")
+            add(blk.attn1.to_out[0].weight, "lin"); add(blk.attn1.to_out[0].bias, "vec")
+            add(blk.attn2.to_q.weight, "lin")
+            add_adjacent([blk.attn2.to_k.weight, blk.attn2.to_v.weight], "lin")
+            add(blk.attn2.to_out[0].weight, "lin"); add(blk.attn2.to_out[0].bias, "vec")
+            add(blk.ff.net[0].proj.weight, "lin"); add(blk.ff.net[0].proj.bias, "vec")
+            add(blk.ff.net[2].weight, "lin"); add(blk.ff.net[2].bias, "vec")
+            add(a.proj_out.weight, "lin"); add(a.proj_out.bias, "vec")
+
+        def add_sampler(s):
+            add(s.conv.weight, "conv3"); add(s.conv.bias, "vec")
+
+        te = m.time_embedding
+        add(te.linear_1.weight, "lin"); add(te.linear_1.bias, "vec")
+        add(te.linear_2.weight, "lin"); add(te.linear_2.bias, "vec")
+        resnets = list(m._iter_resnets())
+        add_adjacent([r.time_emb_proj.weight for _, r in resnets], "lin")
+        add_adjacent([r.time_emb_proj.bias for _, r in resnets], "vec")
+        add(m.conv_in.weight, "conv_f32"); add(m.conv_in.bias, "vec")
+        for b in m.down_blocks:
+            for j, r in enumerate(b.resnets):
+                add_resnet(r)
+                if hasattr(b, "attentions"):
+                    add_xformer(b.attentions[j])
+            if hasattr(b, "downsamplers"):
+                add_sampler(b.downsamplers[0])
+        add_resnet(m.mid_block.resnets[0]); add_xformer(m.mid_block.attentions[0]); add_resnet(m.mid_block.resnets[1])
+        for b in m.up_blocks:
+            for j, r in enumerate(b.resnets):
+                add_resnet(r)
+                if hasattr(b, "attentions"):
+                    add_xformer(b.attentions[j])
+            if hasattr(b, "upsamplers"):
+                add_sampler(b.upsamplers[0])
+        add(m.conv_norm_out.weight, "vec"); add(m.conv_norm_out.bias, "vec")
+        add(m.conv_out.weight, "conv_f32"); add(m.conv_out.bias, "vec")
+
 
     def materialize(self):
         """Allocate the training-only state: the flat fp32 gradient buffer and the bf16 tensor-core copy of the weights.  (The

@@ -145,3 +145,60 @@ class Trainer:
             self.opt.step(grad_scale=1.0 / (self.world * self.micro_steps), zero_grad=True)
             self.micro_steps = 0
         return loss.detach()
+
+
+class TextEncoderTrainer:
+    """Data-parallel fine-tuning step of the TEXT ENCODER with the UNet frozen (BASELINE config 4; the reference's default mode,
+    finetune_sd.py:29, 375-383, 391-395, 477-494):
+
+        ctx   = text_encoder(input_ids)[0]                                     finetune_sd.py:477   (b200sd.clip.CLIPTextModel)
+        noisy = noise_scheduler.add_noise(latents, noise, timesteps)           finetune_sd.py:473-474
+        pred  = unet(noisy, timesteps, ctx).sample                             finetune_sd.py:480-481 (frozen: forward + data
+        loss  = mse(pred, noise); accelerator.backward(loss); optimizer.step()                         gradient down to ctx)
+
+    The UNet's backward hands d(loss)/d(ctx) to the text encoder's backward plan, whose kernels accumulate all 123 M parameter
+    gradients into ONE flat fp32 buffer; that buffer is allreduced over NCCL in `chunks` pieces (the first starts while the host
+    is still queueing the others) and `FlatAdamW` updates master weights, the bf16 tensor-core copy and zeroes the gradients in
+    one pass."""
+
+    def __init__(self, text_encoder, unet, noise_scheduler, lr=1e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, group=None,
+                 chunks: int = 4):
+        self.te, self.unet, self.sched, self.group = text_encoder.train(), unet.eval().requires_grad_(False), noise_scheduler, group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.opt_args = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
+        self.chunks = max(1, int(chunks))
+        text_encoder.enable_direct_gradients()
+        self.opt = None
+        self._flat_id = None
+        self.micro_steps = 0
+        self.allreduce_enabled = True
+
+    def _prepare(self, device):
+        flat = self.te._ensure_flat(device)
+        if self._flat_id is not flat.grad:
+            self.opt = FlatAdamW(flat, state=self.opt, **self.opt_args)
+            flat.zero_grad()
+            flat.attach_grads()
+            self._flat_id = flat.grad
+            self.micro_steps = 0
+        return flat
+
+    def train_step(self, latents, noise, timesteps, input_ids, sync=True):
+        flat = self._prepare(latents.device)
+        ctx = self.te(input_ids)[0]
+        noisy = self.sched.add_noise(latents, noise, timesteps)
+        pred = self.unet(noisy, timesteps, ctx).sample
+        loss = ops.mse_loss(pred, noise)
+        loss.backward()
+        self.micro_steps += 1
+        if sync:
+            if self.world > 1 and self.allreduce_enabled:
+                n = flat.grad.numel()
+                step = (n + self.chunks - 1) // self.chunks
+                works = [dist.all_reduce(flat.grad[a:min(a + step, n)], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+                         for a in range(0, n, step)]
+                for w in works:
+                    w.wait()
+            self.opt.step(grad_scale=1.0 / (self.world * self.micro_steps), zero_grad=True)
+            self.micro_steps = 0
+        return loss.detach()
