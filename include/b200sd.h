@@ -325,6 +325,26 @@ int b200sd_causal_attention(const void* qkv, void* out, int batch, int heads, in
 int b200sd_causal_attention_bwd(const void* qkv, const void* dout, void* dqkv, int batch, int heads, int S, int d, int ld,
                                 int lddo, int ldd, int q_off, int k_off, int v_off, float scale, b200sd_stream_t stream);
 
+/* ---- AutoencoderKL: what the VAE needs beyond the UNet's kernels -------------------------------------
+ * Reference call sites: finetune_sd.py:325-327 (load), 460-462 (`vae.encode(pixel_values).latent_dist.sample() * 0.18215`),
+ * and `vae.decode(latents / 0.18215)` inside every pipeline(...) call (inference.py:175-176, 342-351).
+ * b200sd_gemm's conv3x3 accepts image rows wider than one 128-pixel tile (W % 128 == 0) for the 256 / 512-pixel levels. */
+
+/* b200sd_im2col_s2 with the padding as an argument: pad = 1 is the UNet's Downsample2D, pad = 0 the VAE encoder's
+ * `F.pad(x, (0, 1, 0, 1))` + stride-2 conv (taps beyond the right / bottom edge read zero). */
+int b200sd_im2col_s2_pad(const void* x, void* out, int batch, int H, int W, int C, int in_dtype, int pad,
+                         b200sd_stream_t stream);
+/* out[r][0..L) = softmax(scale * x[r][0..L))  fp32 [rows][ldx] -> bf16 [rows][ldo]: the probabilities of the mid block's
+ * single-head attention between its two GEMMs (scores = q k^T as b200sd_gemm, out = P v as b200sd_gemm_dgrad). */
+int b200sd_softmax_rows(const float* x, void* out_bf16, int rows, int L, int ldx, int ldo, float scale, b200sd_stream_t stream);
+/* 1x1 convolution over <= 8 channels, NCHW fp32 -> NCHW fp32 (post_quant_conv; w [Cout][Cin]). */
+int b200sd_conv1x1_small(const float* x_nchw, const float* w, const float* bias, float* out_nchw, int batch, int Cin, int Cout,
+                         int hw, b200sd_stream_t stream);
+/* DiagonalGaussianDistribution: moments NCHW [batch][2C][hw] = [mean | logvar];
+ * out = (mean + exp(0.5 * clamp(logvar, -30, 20)) * noise) * out_scale; noise == NULL gives the mode. */
+int b200sd_gaussian_sample(const float* moments, const float* noise, float* out, int batch, int C, int hw, float out_scale,
+                           b200sd_stream_t stream);
+
 /* ---- non-GEMM kernels of the backward pass ----------------------------------- */
 
 /* Gradient prep: optional bf16 copy of a [rows, N] (pitch ld) gradient (the tensor-core operand of

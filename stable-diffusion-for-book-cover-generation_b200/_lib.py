@@ -65,6 +65,10 @@ SIGNATURES = {
     "b200sd_layernorm_f32out": (_i, [_vp, _vp, _vp, _vp, _i, _i, _f, _vp]),
     "b200sd_causal_attention": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _vp]),
     "b200sd_causal_attention_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _vp]),
+    "b200sd_im2col_s2_pad": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "b200sd_softmax_rows": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _vp]),
+    "b200sd_conv1x1_small": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "b200sd_gaussian_sample": (_i, [_vp, _vp, _vp, _i, _i, _i, _f, _vp]),
     "b200sd_sampler_advance": (_i, [_vp, _i, _vp, _vp, _i, _vp]),
     "b200sd_cfg_ddim_step_table": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _f, _vp, _vp, _i, _i, _vp]),
     "b200sd_cfg_plms_step": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, C.POINTER(C.c_float), _i64, _f, _f,

@@ -75,6 +75,7 @@ struct KParams {
     int cblocks;         // (C0 + C1) / 64
     int tile_w, tile_h, tile_n;   // conv box geometry
     int tiles_y;         // H / tile_h (conv, tile_n == 1)
+    int tiles_x;         // W / tile_w: 1 unless an image row is wider than one 128-pixel tile (VAE: W = 256 / 512)
     int rows_valid;      // valid rows in a tile (<= 128)
     int a_bytes;         // bytes TMA delivers for A per stage
     int ldc, ldr, ldrb;
@@ -287,10 +288,14 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tcgen05_kernel(const __gr
         if (ptx::elect_one()) {
             int stage = 0;
             uint32_t phase = 0;
-            int img = 0, y0 = 0;
+            int img = 0, y0 = 0, x0 = 0;
             if (p.conv) {
                 if (p.tile_n > 1) { img = m_tile * p.tile_n; y0 = 0; }
-                else { img = m_tile / p.tiles_y; y0 = (m_tile % p.tiles_y) * p.tile_h; }
+                else {
+                    int mt = m_tile;
+                    if (p.tiles_x > 1) { x0 = (mt % p.tiles_x) * p.tile_w; mt /= p.tiles_x; }
+                    img = mt / p.tiles_y; y0 = (mt % p.tiles_y) * p.tile_h;
+                }
             }
             // pair mode: this CTA loads its own A rows and half of the B tile; completion is signalled on the leader's barrier
             // MN-major B: only the 64-column boxes that hold existing columns are loaded (the last N tile of a layer may be
@@ -321,8 +326,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tcgen05_kernel(const __gr
                     const int tap = kb / p.cblocks;
                     const int cb = kb - tap * p.cblocks;
                     const int dy = (tap / 3 - 1) * p.conv_sign, dx = (tap % 3 - 1) * p.conv_sign;
-                    if (cb < p.cblocks0) LD4(dst_a, &p.tmA0, cb * BLOCK_K, dx, y0 + dy, img);
-                    else LD4(dst_a, &p.tmA1, (cb - p.cblocks0) * BLOCK_K, dx, y0 + dy, img);
+                    if (cb < p.cblocks0) LD4(dst_a, &p.tmA0, cb * BLOCK_K, x0 + dx, y0 + dy, img);
+                    else LD4(dst_a, &p.tmA1, (cb - p.cblocks0) * BLOCK_K, x0 + dx, y0 + dy, img);
                 }
                 // ---- B ----
                 if (b_mode == 0) {
@@ -542,6 +547,7 @@ struct PParams {
     int M, N;
     int num_k_blocks, block_n, stages;
     int conv, cblocks0, cblocks, tile_h, tile_n, tiles_y, w_kmajor;
+    int tile_w, tiles_x;            // image rows wider than a tile (see KParams::tiles_x)
     int n_tiles, num_tiles;
     int ldrb, rows_per_image;
     int geglu, out_f32, res_kind;   // res_kind: 0 none, 1 bf16, 2 fp32
@@ -974,7 +980,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) gemm_persist_kernel(const 
     // slice s = k-blocks [s * nkb / split, (s + 1) * nkb / split): never empty while nkb >= split
     const int sk_kb0 = splitk ? (sk_s * p.num_k_blocks) / p.split : 0;
     const int sk_kb1 = splitk ? ((sk_s + 1) * p.num_k_blocks) / p.split : p.num_k_blocks;
-    int pr_stage = 0, pr_tile = splitk ? sk_tile : (int)blockIdx.x, pr_kb = sk_kb0, pr_m0 = 0, pr_n0 = 0, pr_img = 0, pr_y0 = 0, pr_tap = 0,
+    int pr_stage = 0, pr_tile = splitk ? sk_tile : (int)blockIdx.x, pr_kb = sk_kb0, pr_m0 = 0, pr_n0 = 0, pr_img = 0, pr_y0 = 0, pr_x0 = 0, pr_tap = 0,
         pr_cb = 0, pr_me = 0;
     bool pr_new = true;
     uint32_t pr_phase = 0;
@@ -1003,7 +1009,11 @@ __global__ void __launch_bounds__(kPersistThreads, 1) gemm_persist_kernel(const 
                 pr_n0 = n_tile * p.block_n;
                 if (p.conv) {
                     if (p.tile_n > 1) { pr_img = m_tile * p.tile_n; pr_y0 = 0; }
-                    else { pr_img = m_tile / p.tiles_y; pr_y0 = (m_tile - pr_img * p.tiles_y) * p.tile_h; }
+                    else {
+                        int mt = m_tile;
+                        if (p.tiles_x > 1) { pr_x0 = (mt % p.tiles_x) * p.tile_w; mt /= p.tiles_x; }
+                        pr_img = mt / p.tiles_y; pr_y0 = (mt - pr_img * p.tiles_y) * p.tile_h;
+                    }
                 }
                 pr_tap = pr_kb / p.cblocks;           // 0 unless this is a K slice
                 pr_cb = pr_kb - pr_tap * p.cblocks;
@@ -1022,8 +1032,8 @@ __global__ void __launch_bounds__(kPersistThreads, 1) gemm_persist_kernel(const 
                     else ptx::tma_load_2d(dst_a, &p.tmA1, fb, (pr_kb - p.cblocks0) * BLOCK_K, pr_m0);
                 } else {
                     const int dy = pr_tap / 3 - 1, dx = pr_tap - (pr_tap / 3) * 3 - 1;
-                    if (pr_cb < p.cblocks0) ptx::tma_load_4d(dst_a, &p.tmA0, fb, pr_cb * BLOCK_K, dx, pr_y0 + dy, pr_img);
-                    else ptx::tma_load_4d(dst_a, &p.tmA1, fb, (pr_cb - p.cblocks0) * BLOCK_K, dx, pr_y0 + dy, pr_img);
+                    if (pr_cb < p.cblocks0) ptx::tma_load_4d(dst_a, &p.tmA0, fb, pr_cb * BLOCK_K, pr_x0 + dx, pr_y0 + dy, pr_img);
+                    else ptx::tma_load_4d(dst_a, &p.tmA1, fb, (pr_cb - p.cblocks0) * BLOCK_K, pr_x0 + dx, pr_y0 + dy, pr_img);
                 }
             }
             if (load_b) {
@@ -1249,6 +1259,7 @@ int launch_persist(const b200sd_gemm_args* a, const KParams& k, int m_tiles, b20
     p.num_k_blocks = k.num_k_blocks; p.block_n = k.block_n;
     p.conv = k.conv; p.cblocks0 = k.cblocks0; p.cblocks = k.cblocks;
     p.tile_h = k.tile_h; p.tile_n = k.tile_n; p.tiles_y = k.tiles_y; p.w_kmajor = k.w_kmajor;
+    p.tile_w = k.tile_w; p.tiles_x = k.tiles_x;
     p.n_tiles = k.N / k.block_n;
     p.num_tiles = m_tiles * p.n_tiles;
     p.ldrb = k.ldrb; p.rows_per_image = k.rows_per_image;
@@ -1438,7 +1449,19 @@ int pick_block_n_mn(int N, int m_tiles, int kind) {
 // conv geometry shared by forward / dgrad: M tile = (tile_w x tile_h x tile_n) pixels <= 128
 int conv_m_tiling(KParams& p, int NB, int H, int W, int M, int* m_tiles) {
     B200SD_REQUIRE(NB > 0 && H > 0 && W > 0 && M == NB * H * W, "gemm(conv): M=%d != batch*H*W", M);
-    B200SD_REQUIRE(W <= BLOCK_M, "gemm(conv): W=%d > 128 unsupported", W);
+    p.tiles_x = 1;
+    if (W > BLOCK_M) {
+        // an image row is wider than one tile (VAE at 256 / 512 pixels): a tile = 128 consecutive pixels of ONE row, box
+        // (64 ch, 128, 1, 1) at x0 = tile_x * 128; the halo columns x0 - 1 / x0 + 128 come from the neighbouring pixels of the
+        // same row (or TMA zero fill at the image border), exactly as for whole-row tiles
+        B200SD_REQUIRE(W % BLOCK_M == 0, "gemm(conv): W=%d > 128 must be a multiple of 128", W);
+        p.tile_w = BLOCK_M; p.tile_h = 1; p.tile_n = 1;
+        p.tiles_x = W / BLOCK_M; p.tiles_y = H;
+        p.rows_valid = BLOCK_M;
+        p.a_bytes = p.rows_valid * BLOCK_K * 2;
+        *m_tiles = NB * H * p.tiles_x;
+        return B200SD_OK;
+    }
     const int max_h = BLOCK_M / W;
     if (H <= max_h) {
         p.tile_h = H;
@@ -1488,6 +1511,7 @@ static int gemm_tiling(const b200sd_gemm_args* a, KParams& p, int* m_tiles_out, 
         p.rows_valid = BLOCK_M;
         p.a_bytes = kABytes;
         p.tile_w = p.tile_h = p.tile_n = 1;
+        p.tiles_x = 1;
         p.tiles_y = 1;
         *m_tiles_out = ceil_div(a->M, BLOCK_M);
     } else {
@@ -1739,7 +1763,7 @@ extern "C" int b200sd_gemm_gn_layout(const b200sd_gemm_args* a, int hw, int* par
     int ppi;
     if (p.conv) {
         if (a->H * a->W != hw) return B200SD_OK;
-        if (p.tile_n == 1) ppi = p.tiles_y * p.split_k;              // tiles inside one image (empty ranks publish zeros)
+        if (p.tile_n == 1) ppi = p.tiles_y * p.tiles_x * p.split_k;              // tiles inside one image (empty ranks publish zeros)
         else if (p.rows_valid == BLOCK_M && hw % rpp == 0) ppi = hw / rpp;   // whole images per tile, split finer than an image
         else return B200SD_OK;
     } else {
@@ -1792,6 +1816,7 @@ extern "C" int b200sd_gemm_dgrad(const b200sd_dgrad_args* a, b200sd_stream_t str
         p.rows_valid = BLOCK_M;
         p.a_bytes = kABytes;
         p.tile_w = p.tile_h = p.tile_n = p.tiles_y = 1;
+        p.tiles_x = 1;
         m_tiles = ceil_div(a->M, BLOCK_M);
     } else {
         B200SD_REQUIRE(ldy == a->Cout, "dgrad(conv): dy must be dense NHWC");
@@ -1887,6 +1912,7 @@ extern "C" int b200sd_gemm_wgrad(const b200sd_wgrad_args* a, b200sd_stream_t str
         B200SD_REQUIRE(NB > 0 && H > 0 && W > 0 && a->rows == NB * H * W, "wgrad(conv): rows=%d != batch*H*W", a->rows);
         B200SD_REQUIRE(W <= 64 && 64 % W == 0, "wgrad(conv): W=%d must divide 64", W);
         B200SD_REQUIRE(ldy == a->Cout && ldx == a->Cin, "wgrad(conv): dy / x must be dense NHWC");
+        p.tiles_x = 1;
         p.tile_w = W;
         p.tile_h = (64 / W < H) ? 64 / W : H;
         B200SD_REQUIRE(H % p.tile_h == 0, "wgrad(conv): H=%d not a multiple of the %d-row pixel block", H, p.tile_h);
@@ -1899,6 +1925,7 @@ extern "C" int b200sd_gemm_wgrad(const b200sd_wgrad_args* a, b200sd_stream_t str
         if ((rc = b200sd_make_tmap(&p.tmB, a->x, 4, dims, str, boxB, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
     } else {
         p.tile_w = p.tile_h = p.tile_n = p.tiles_y = 1;
+        p.tiles_x = 1;
         p.num_k_blocks = ceil_div(a->rows, BLOCK_K);
         const uint64_t dimsB[2] = {(uint64_t)a->Cin, (uint64_t)a->rows};
         const uint64_t strB[2] = {0, (uint64_t)ldx * 2};

@@ -243,7 +243,7 @@ __global__ void upsample2x_kernel(const void* __restrict__ x, bf16* __restrict__
 
 // ---- im2col for the stride-2 pad-1 3x3 Downsample2D conv --------------------------------------------
 template <int DT>
-__global__ void im2col_s2_kernel(const void* __restrict__ x, bf16* __restrict__ out, int batch, int H, int W, int C8) {
+__global__ void im2col_s2_kernel(const void* __restrict__ x, bf16* __restrict__ out, int batch, int H, int W, int C8, int pad) {
     ptx::pdl_trigger();
     ptx::pdl_wait();
     const int OH = H / 2, OW = W / 2;
@@ -258,7 +258,7 @@ __global__ void im2col_s2_kernel(const void* __restrict__ x, bf16* __restrict__ 
         p /= OW;
         const int oy = (int)(p % OH);
         const int b = (int)(p / OH);
-        const int y = 2 * oy + tap / 3 - 1, xx = 2 * ox + tap % 3 - 1;
+        const int y = 2 * oy + tap / 3 - pad, xx = 2 * ox + tap % 3 - pad;   // pad 1: UNet Downsample2D; pad 0: the VAE's (0,1,0,1) padding
         float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         if (y >= 0 && y < H && xx >= 0 && xx < W) ld8<DT>(x, (size_t)(((int64_t)(b * H + y) * W + xx) * C8 + c) * 8, v);
         st8<B200SD_BF16>(out, (size_t)i * 8, v);
@@ -354,14 +354,15 @@ __global__ void __launch_bounds__(256) nhwc_bias_to_nchw_kernel(const float* __r
     if (m >= total) return;
     const int b = m / hw, pix = m - b * hw;
     const float4 v = __ldg(reinterpret_cast<const float4*>(x + (size_t)m * ld));
-    const float vv[4] = {v.x, v.y, v.z, v.w};
+    const float4 u = C > 4 ? __ldg(reinterpret_cast<const float4*>(x + (size_t)m * ld) + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float vv[8] = {v.x, v.y, v.z, v.w, u.x, u.y, u.z, u.w};
     for (int c = 0; c < C; ++c) out[((size_t)b * C + c) * hw + pix] = vv[c] + __ldg(bias + c);
 }
 
 extern "C" int b200sd_nhwc_bias_to_nchw(const float* x, const float* bias, float* out_nchw, int batch, int C, int hw, int ld,
                                         b200sd_stream_t stream) {
     B200SD_REQUIRE(x && bias && out_nchw, "nhwc_bias_to_nchw: null pointer");
-    B200SD_REQUIRE(C >= 1 && C <= 4 && ld % 4 == 0 && ld >= 4 && batch > 0 && hw > 0, "nhwc_bias_to_nchw: C in 1..4, ld %% 4 == 0");
+    B200SD_REQUIRE(C >= 1 && C <= 8 && ld % 4 == 0 && ld >= (C > 4 ? 8 : 4) && batch > 0 && hw > 0, "nhwc_bias_to_nchw: C in 1..8, ld %% 4 == 0");
     const int total = batch * hw;
     B200SD_CUDA(b200sd_launch(nhwc_bias_to_nchw_kernel, dim3(ceil_div(total, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), x, bias,
                               out_nchw, total, hw, C, ld));
@@ -388,15 +389,21 @@ extern "C" int b200sd_upsample2x(const void* x, void* out, int batch, int H, int
 
 extern "C" int b200sd_im2col_s2(const void* x, void* out, int batch, int H, int W, int C, int in_dtype,
                                 b200sd_stream_t stream) {
+    return b200sd_im2col_s2_pad(x, out, batch, H, W, C, in_dtype, 1, stream);
+}
+
+extern "C" int b200sd_im2col_s2_pad(const void* x, void* out, int batch, int H, int W, int C, int in_dtype, int pad,
+                                    b200sd_stream_t stream) {
     B200SD_REQUIRE(x && out, "im2col_s2: null pointer");
+    B200SD_REQUIRE(pad == 0 || pad == 1, "im2col_s2: pad must be 0 (pad right/bottom only) or 1 (symmetric)");
     B200SD_REQUIRE(C % 8 == 0 && batch > 0 && H % 2 == 0 && W % 2 == 0, "im2col_s2: bad sizes");
     const int64_t total = (int64_t)batch * (H / 2) * (W / 2) * 9 * (C / 8);
     if (in_dtype == B200SD_F32)
         B200SD_CUDA(b200sd_launch(im2col_s2_kernel<B200SD_F32>, dim3(ew_grid(total, 256)), dim3(256), 0,
-                                  static_cast<cudaStream_t>(stream), x, static_cast<bf16*>(out), batch, H, W, C / 8));
+                                  static_cast<cudaStream_t>(stream), x, static_cast<bf16*>(out), batch, H, W, C / 8, pad));
     else
         B200SD_CUDA(b200sd_launch(im2col_s2_kernel<B200SD_BF16>, dim3(ew_grid(total, 256)), dim3(256), 0,
-                                  static_cast<cudaStream_t>(stream), x, static_cast<bf16*>(out), batch, H, W, C / 8));
+                                  static_cast<cudaStream_t>(stream), x, static_cast<bf16*>(out), batch, H, W, C / 8, pad));
     COUNT_LAUNCH();
     B200SD_LAUNCH_CHECK();
     return B200SD_OK;

@@ -409,9 +409,9 @@ def upsample2x(x, out, batch, H, W):
     return out
 
 
-def im2col_s2(x, out, batch, H, W):
+def im2col_s2(x, out, batch, H, W, pad=1):
     _chk(x, out)
-    check(lib().b200sd_im2col_s2(_p(x), _p(out), batch, H, W, x.shape[-1], _dt(x), _stream()), "im2col_s2")
+    check(lib().b200sd_im2col_s2_pad(_p(x), _p(out), batch, H, W, x.shape[-1], _dt(x), int(pad), _stream()), "im2col_s2")
     return out
 
 
@@ -647,3 +647,28 @@ def causal_attention_bwd(qkv, dout, dqkv, batch, heads, S, d, scale):
     check(lib().b200sd_causal_attention_bwd(_p(qkv), _p(dout), _p(dqkv), batch, heads, S, d, qkv.shape[-1], dout.shape[-1],
                                             dqkv.shape[-1], 0, Cc, 2 * Cc, float(scale), _stream()), "causal_attention_bwd")
     return dqkv
+
+
+# ---------------------------------------------------------------------------------------------
+# AutoencoderKL
+# ---------------------------------------------------------------------------------------------
+def softmax_rows(x, out, scale=1.0):
+    """x fp32 [rows, L] -> out bf16 [rows, L] = softmax(scale * x) along the last dim"""
+    _chk(x, out)
+    rows, L = x.shape
+    check(lib().b200sd_softmax_rows(_p(x), _p(out), rows, L, x.shape[-1], out.shape[-1], float(scale), _stream()), "softmax_rows")
+    return out
+
+
+def conv1x1_small(x_nchw, w, bias, out_nchw):
+    _chk(x_nchw, w, bias, out_nchw)
+    B, Cin, H, W = x_nchw.shape
+    check(lib().b200sd_conv1x1_small(_p(x_nchw), _p(w), _p(bias), _p(out_nchw), B, Cin, w.shape[0], H * W, _stream()), "conv1x1_small")
+    return out_nchw
+
+
+def gaussian_sample(moments, noise, out, out_scale=1.0):
+    _chk(moments, noise, out)
+    B, C2, H, W = moments.shape
+    check(lib().b200sd_gaussian_sample(_p(moments), _p(noise), _p(out), B, C2 // 2, H * W, float(out_scale), _stream()), "gaussian_sample")
+    return out

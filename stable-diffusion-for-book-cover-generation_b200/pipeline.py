@@ -60,8 +60,8 @@ def _captured_sampler(unet, scheduler, latents, ctx2, guidance_scale):
 # ---------------------------------------------------------------------------------------------------
 # StableDiffusionPipeline-compatible wrapper: what finetune_sd.py:517-537 builds and saves,
 # what utils.py:181-256 / inference.py:404-429 load, and what inference.py:175-176, 342-351 call.
-# The UNet and the scheduler are b200sd's; tokenizer / text encoder / VAE are NEIGHBOURS of the hot path: whatever objects
-# the caller passes (transformers' CLIPTokenizer / CLIPTextModel, a diffusers AutoencoderKL) are used as they are.
+# UNet, scheduler, text encoder (clip.py) and VAE (vae.py) are b200sd's; objects the caller passes instead (transformers'
+# CLIPTextModel, a diffusers AutoencoderKL) are used as they are.  The tokenizer is transformers' CLIPTokenizer (host code).
 # ---------------------------------------------------------------------------------------------------
 import json
 import os
@@ -136,7 +136,8 @@ class StableDiffusionPipeline:
     @classmethod
     def from_pretrained(cls, path, torch_dtype=None, safety_checker=None, scheduler=None, **overrides):
         """Loads `unet/` and `scheduler/` with b200sd's classes; tokenizer / text encoder through transformers when their
-        sub-folders exist (offline); a VAE only when passed as `vae=` (no AutoencoderKL implementation lives here)."""
+        `text_encoder/` and `vae/` sub-folders exist (b200sd.clip.CLIPTextModel, b200sd.vae.AutoencoderKL); the tokenizer through
+        transformers (offline)."""
         from . import schedulers as S
         from .unet import UNet2DConditionModel
         with open(os.path.join(path, cls.config_name)) as f:
@@ -155,9 +156,13 @@ class StableDiffusionPipeline:
             from transformers import CLIPTokenizer
             tokenizer = CLIPTokenizer.from_pretrained(os.path.join(path, "tokenizer"))
         if text_encoder is None and os.path.isdir(os.path.join(path, "text_encoder")):
-            from transformers import CLIPTextModel
-            text_encoder = CLIPTextModel.from_pretrained(os.path.join(path, "text_encoder"), torch_dtype=torch_dtype)
-        return cls(vae=overrides.pop("vae", None), text_encoder=text_encoder, tokenizer=tokenizer, unet=unet,
+            from .clip import CLIPTextModel
+            text_encoder = CLIPTextModel.from_pretrained(path, subfolder="text_encoder", torch_dtype=torch_dtype)
+        vae = overrides.pop("vae", None)
+        if vae is None and os.path.isdir(os.path.join(path, "vae")):
+            from .vae import AutoencoderKL
+            vae = AutoencoderKL.from_pretrained(path, subfolder="vae", torch_dtype=torch_dtype)
+        return cls(vae=vae, text_encoder=text_encoder, tokenizer=tokenizer, unet=unet,
                    scheduler=scheduler, safety_checker=None, feature_extractor=overrides.pop("feature_extractor", None))
 
     # -- sampling ------------------------------------------------------------------------------------

@@ -1,0 +1,193 @@
+"""GPU parity of AutoencoderKL (finetune_sd.py:325-327, 460-462; the decode inside pipeline(...),
+inference.py:175-176) against the fp32 oracle (oracle/vae_ref.py, a restatement of diffusers 0.7.2 -- parity unpinned) on
+identical random-init weights and inputs: the VAE-only kernels one by one, wide-row conv tiles, encode / decode of the
+reduced-width network at several geometries, and the real SD v1.x VAE at 512 x 512.
+
+Tolerance.  The north_star's bf16 bar (max|x-ref| / max|ref| <= 1e-2) is stated for the UNet's noise prediction; the VAE is ~35
+GEMM layers of bf16-operand rounding on an un-normalised output, and measures 1.0-2.2e-2 here.  The bar used is therefore
+self-calibrating: not worse than the LIBRARY bf16 path on the same input -- the oracle module itself under
+torch.autocast(bfloat16) (cuDNN / cuBLAS) -- with a hard cap of 3e-2, plus cosine >= 0.9995.  (After `/2 + 0.5`, clamp and 8-bit
+quantisation, 2e-2 of the output range is ~2 grey levels.)"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _rel(got, want):
+    return float((got.float().cpu() - want.float().cpu()).abs().max() / (want.float().abs().max() + 1e-12))
+
+
+def _cos(got, want):
+    return float(F.cosine_similarity(got.float().cpu().flatten(), want.float().cpu().flatten(), dim=0))
+
+
+def _check_vs_library_bf16(got, want, fn_on_gpu_oracle, what):
+    """ours <= max(1e-2, error of the oracle module under torch bf16 autocast), hard cap 3e-2, cosine >= 0.9995"""
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        lib = fn_on_gpu_oracle().float().cpu()
+    e, e_lib = _rel(got, want), _rel(lib, want)
+    assert e <= max(1e-2, e_lib) and e <= 3e-2, f"{what}: ours {e:.4f}, torch bf16 autocast {e_lib:.4f}"
+    assert _cos(got, want) >= 0.9995, f"{what}: cosine {_cos(got, want):.6f}"
+
+
+def test_softmax_rows_conv1x1_gaussian_sample_kernels():
+    from b200sd import ops
+    g = torch.Generator().manual_seed(0)
+    x = 4 * torch.randn(300, 4096, generator=g)
+    out = torch.empty(300, 4096, dtype=torch.bfloat16, device=DEV)
+    ops.softmax_rows(x.to(DEV), out, 0.37)
+    assert _rel(out, torch.softmax(0.37 * x, -1)) <= 5e-3
+    xi, w, b = torch.randn(2, 4, 9, 7, generator=g), torch.randn(4, 4, generator=g), torch.randn(4, generator=g)
+    o = torch.empty(2, 4, 9, 7, device=DEV)
+    ops.conv1x1_small(xi.to(DEV), w.to(DEV), b.to(DEV), o)
+    assert _rel(o, F.conv2d(xi, w.view(4, 4, 1, 1), b)) <= 1e-6
+    mom, noise = torch.randn(2, 8, 5, 5, generator=g), torch.randn(2, 4, 5, 5, generator=g)
+    mom[0, 5] = 50.0
+    s = torch.empty(2, 4, 5, 5, device=DEV)
+    ops.gaussian_sample(mom.to(DEV), noise.to(DEV), s, 0.18215)
+    want = (mom[:, :4] + torch.exp(0.5 * mom[:, 4:].clamp(-30, 20)) * noise) * 0.18215
+    assert _rel(s, want) <= 1e-6
+    ops.gaussian_sample(mom.to(DEV), None, s)
+    assert torch.equal(s.cpu(), mom[:, :4])
+
+
+def test_im2col_s2_pad0_is_the_encoder_downsample():
+    from b200sd import ops
+    g = torch.Generator().manual_seed(1)
+    B, H, W, C = 2, 8, 16, 64
+    x = torch.randn(B, C, H, W, generator=g)
+    wt, bias = torch.randn(C, C, 3, 3, generator=g) * 0.05, torch.randn(C, generator=g)
+    want = F.conv2d(F.pad(x, (0, 1, 0, 1)), wt, bias, stride=2)
+    nhwc = x.permute(0, 2, 3, 1).reshape(B * H * W, C).contiguous().to(DEV)
+    col = torch.empty(B * (H // 2) * (W // 2), 9 * C, dtype=torch.bfloat16, device=DEV)
+    ops.im2col_s2(nhwc, col, B, H, W, pad=0)
+    out = torch.empty(B * (H // 2) * (W // 2), C, device=DEV)
+    ops.gemm(col, wt.permute(0, 2, 3, 1).reshape(C, 9 * C).contiguous().bfloat16().to(DEV), out, bias=bias.to(DEV))
+    got = out.view(B, H // 2, W // 2, C).permute(0, 3, 1, 2)
+    assert _rel(got, want) <= 1e-2
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(1, 4, 256, 64, 64), (2, 3, 512, 128, 128), (1, 8, 384, 64, 192), (1, 2, 1024, 64, 64)])
+def test_conv3x3_rows_wider_than_a_tile(B, H, W, Cin, Cout):
+    """W > 128: a tile is 128 consecutive pixels of one image row (gemm_tcgen05.cu tiles_x); halo columns come from the
+    neighbouring tile's pixels / TMA zero fill at the image border."""
+    from b200sd import ops, packing
+    g = torch.Generator().manual_seed(W + Cin)
+    x = torch.randn(B, Cin, H, W, generator=g)
+    wt, bias = torch.randn(Cout, Cin, 3, 3, generator=g) * (Cin * 9) ** -0.5, torch.randn(Cout, generator=g)
+    res = torch.randn(B, Cout, H, W, generator=g)
+    want = F.conv2d(x.bfloat16().float(), wt.bfloat16().float(), bias, padding=1) + res
+    nhwc = lambda t: t.permute(0, 2, 3, 1).reshape(-1, t.shape[1]).contiguous()
+    out = torch.empty(B * H * W, Cout, device=DEV)
+    ops.gemm(nhwc(x).bfloat16().to(DEV), packing.pack_conv3x3(wt).to(DEV), out, bias=bias.to(DEV), residual=nhwc(res).to(DEV),
+             conv=(B, H, W))
+    got = out.view(B, H, W, Cout).permute(0, 3, 1, 2)
+    assert _rel(got, want) <= 2e-3
+
+
+def _pair(seed, **overrides):
+    from b200sd.vae import AutoencoderKL
+    from oracle.vae_ref import make_oracle_vae
+    oracle = make_oracle_vae(seed=seed, **overrides)
+    ours = AutoencoderKL(**overrides)
+    ours.load_state_dict(oracle.state_dict(), strict=True)
+    return oracle, ours.to(DEV).eval()
+
+
+@pytest.mark.parametrize("B,H,W", [(1, 64, 64), (2, 128, 64), (1, 64, 256), (1, 64, 512)])
+def test_tiny_vae_encode_decode_vs_oracle(B, H, W):
+    from oracle.vae_ref import TINY_VAE_OVERRIDES
+    oracle, ours = _pair(0, **TINY_VAE_OVERRIDES)
+    g = torch.Generator().manual_seed(H + W)
+    img = torch.randn(B, 3, H, W, generator=g)
+    import copy
+    oc = copy.deepcopy(oracle).to(DEV)
+    with torch.no_grad():
+        want_m = oracle.quant_conv(oracle.encoder(img))
+        post = ours.encode(img.to(DEV)).latent_dist
+        _check_vs_library_bf16(post.parameters, want_m, lambda: oc.quant_conv(oc.encoder(img.to(DEV))), "moments")
+        assert torch.equal(post.mode(), post.parameters[:, :4])
+        z = torch.randn(B, 4, H // 8, W // 8, generator=g)
+        want = oracle.decode(z).sample
+        got = ours.decode(z.to(DEV)).sample
+        assert tuple(got.shape) == (B, 3, H, W)
+        _check_vs_library_bf16(got, want, lambda: oc.decode(z.to(DEV)).sample, "decode")
+        again = ours.decode(z.to(DEV)).sample             # graph replay
+        assert torch.equal(again, got)
+        # latent_dist.sample() * 0.18215 (finetune_sd.py:460-462): same torch.randn stream as diffusers
+        gen = torch.Generator(device=DEV).manual_seed(3)
+        s = post.sample(generator=gen)
+        noise = torch.randn(post.mean.shape, generator=torch.Generator(device=DEV).manual_seed(3), device=DEV)
+        assert _rel(s, post.mean + post.std * noise) <= 1e-5
+
+
+@pytest.fixture(scope="module")
+def sd15_vae():
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    return _pair(0)
+
+
+def test_sd15_vae_decode_512_vs_oracle(sd15_vae):
+    """the real SD v1.x VAE: latents 4x64x64 -> 3x512x512 (the decode at the end of every pipeline(...) call)"""
+    oracle, ours = sd15_vae
+    g = torch.Generator().manual_seed(0)
+    z = torch.randn(1, 4, 64, 64, generator=g)
+    oc = oracle.to(DEV)
+    try:
+        with torch.no_grad():
+            want = oc.decode(z.to(DEV)).sample.cpu()
+        got = ours.decode(z.to(DEV)).sample
+        assert tuple(got.shape) == (1, 3, 512, 512)
+        _check_vs_library_bf16(got, want, lambda: oc.decode(z.to(DEV)).sample, "decode 512x512")
+    finally:
+        oracle.to("cpu")
+
+
+def test_sd15_vae_encode_512_and_portrait_decode_vs_oracle(sd15_vae):
+    oracle, ours = sd15_vae
+    g = torch.Generator().manual_seed(1)
+    img = torch.randn(1, 3, 512, 512, generator=g)
+    z = torch.randn(1, 4, 96, 64, generator=g)               # 512 x 768 book-cover portrait (config 5)
+    oc = oracle.to(DEV)
+    try:
+        with torch.no_grad():
+            want_m = oc.quant_conv(oc.encoder(img.to(DEV))).cpu()
+            want = oc.decode(z.to(DEV)).sample.cpu()
+        post = ours.encode(img.to(DEV)).latent_dist
+        assert tuple(post.parameters.shape) == (1, 8, 64, 64)
+        _check_vs_library_bf16(post.parameters, want_m, lambda: oc.quant_conv(oc.encoder(img.to(DEV))), "moments 512x512")
+        got = ours.decode(z.to(DEV)).sample
+        assert tuple(got.shape) == (1, 3, 768, 512)
+        _check_vs_library_bf16(got, want, lambda: oc.decode(z.to(DEV)).sample, "decode 512x768")
+    finally:
+        oracle.to("cpu")
+
+
+def test_pipeline_text_to_image_on_own_clip_unet_vae():
+    """StableDiffusionPipeline(prompt_embeds=...) -> images through b200sd's UNet, scheduler and VAE (reduced-width networks),
+    against the same chain of oracles."""
+    from b200sd.pipeline import StableDiffusionPipeline
+    from b200sd.schedulers import DDIMScheduler
+    from b200sd.unet import UNet2DConditionModel
+    from oracle import schedulers_ref as R
+    from oracle.unet_ref import TINY_OVERRIDES, make_oracle_unet
+    from oracle.vae_ref import TINY_VAE_OVERRIDES
+    o_unet = make_oracle_unet(seed=0, **TINY_OVERRIDES)
+    unet = UNet2DConditionModel(**TINY_OVERRIDES)
+    unet.load_state_dict(o_unet.state_dict(), strict=True)
+    o_vae, vae = _pair(2, **TINY_VAE_OVERRIDES)
+    sch = DDIMScheduler(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear", clip_sample=False, set_alpha_to_one=False)
+    pipe = StableDiffusionPipeline(vae=vae, unet=unet.to(DEV).eval(), scheduler=sch)
+    g = torch.Generator().manual_seed(5)
+    lat, ctx2 = torch.randn(1, 4, 32, 32, generator=g), torch.randn(2, 77, 64, generator=g)
+    out = pipe(prompt_embeds=ctx2.to(DEV), height=256, width=256, num_inference_steps=4, guidance_scale=7.5, latents=lat.to(DEV),
+               output_type="pt").images
+    with torch.no_grad():
+        want_l = R.denoise_loop(o_unet, R.DDIMSchedulerRef(clip_sample=False, set_alpha_to_one=False), lat, ctx2, 4, 7.5)
+        want = (o_vae.decode(want_l / 0.18215).sample / 2 + 0.5).clamp(0, 1)
+    assert tuple(out.shape) == (1, 3, 256, 256)
+    assert float((out.cpu() - want).abs().max()) <= 2e-2
