@@ -514,15 +514,19 @@ def run_ours(args):
         }
     # ---- fine-tuning legs (BASELINE configs[2] / [3]) inside the same line: the gradient-allreduce path is the only
     # collective of the hot path, and the driver's scaling run only ever launches `bench.py --gpus N` ----
-    train = train_text = None
+    train = train_text = t2i = None
     if args.precision == "bf16" and args.total_images <= 0 and not args.portrait and not args.no_train_legs:
         unet._engines = {}                       # the sampling plan's buffers are not needed any more
         del smp, eng, step, e2e_step
         torch.cuda.empty_cache()
+        if rank == 0:
+            t2i = text_to_image_leg(dev, unet)
+            torch.cuda.empty_cache()
         train = train_leg(dev, world, rank, steps=5, warmup=3, unet=unet)          # same model object: one 860 M-parameter init per rank
         torch.cuda.empty_cache()
         train_text = train_text_leg(dev, world, rank, local, steps=5, warmup=3, unet=unet)
     if rank == 0:
+        line["text_to_image"] = t2i
         line["train"] = train
         line["train_text"] = train_text
         print(json.dumps(line), flush=True)
@@ -696,6 +700,60 @@ def train_leg(dev, world, rank, steps=5, warmup=3, B=8, unet=None):
            "last_loss": loss, "collective": "NCCL all_reduce(SUM) of the flat fp32 gradient buffer in 64 MB buckets, overlapped with the backward"}
     del tr
     return rec
+
+
+def text_to_image_leg(dev, unet, images=(1, 4), reps=3):
+    """The whole `pipeline(prompt_ids, 512, 512, 50 steps, CFG 7.5)` call of inference.py:175-176, 342-351 on b200sd's own
+    models: CLIP text encoder over the [uncond | cond] token ids -> 50 captured DDIM steps -> VAE decode -> uint8 image on the
+    host.  Random-init SD v1.x architectures, synthetic token ids; H2D of the ids and D2H of the images inside the timed region."""
+    import torch
+    from b200sd.clip import CLIPTextModel
+    from b200sd.sampler import CapturedSampler
+    from b200sd.schedulers import DDIMScheduler
+    from b200sd.vae import AutoencoderKL
+    torch.manual_seed(0)
+    clip = CLIPTextModel().to(dev).eval().requires_grad_(False)
+    vae = AutoencoderKL().to(dev).eval()
+    sch = DDIMScheduler(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear", clip_sample=False, set_alpha_to_one=False)
+    sch.set_timesteps(50)
+    out = {}
+    for B in images:
+        smp = CapturedSampler(unet, sch, B, 64, 64, 77, 7.5)
+        g = torch.Generator().manual_seed(7)
+        ids_host = torch.randint(0, 49408, (2 * B, 77), generator=g).pin_memory()
+        lat_host = torch.randn(B, 4, 64, 64, generator=g).pin_memory()
+        img_host = torch.empty(B, 512, 512, 3, dtype=torch.uint8).pin_memory()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+
+        def once():
+            with torch.no_grad():
+                ev[0].record()
+                ctx2 = clip(ids_host.to(dev, non_blocking=True))[0]
+                ev[1].record()
+                lat = smp.run(lat_host.to(dev, non_blocking=True), ctx2)
+                ev[2].record()
+                img = vae.decode(lat / 0.18215).sample
+                img = ((img / 2 + 0.5).clamp(0, 1) * 255).round().to(torch.uint8).permute(0, 2, 3, 1).contiguous()
+                img_host.copy_(img, non_blocking=True)
+                ev[3].record()
+                torch.cuda.current_stream().synchronize()
+
+        once()
+        once()
+        t0 = time.perf_counter()
+        parts = [0.0, 0.0, 0.0]
+        for _ in range(reps):
+            once()
+            for i in range(3):
+                parts[i] += ev[i].elapsed_time(ev[i + 1]) / reps
+        wall_ms = (time.perf_counter() - t0) * 1e3 / reps
+        out[f"{B}_images"] = {"images_per_s": B / (wall_ms * 1e-3), "ms_per_call": wall_ms, "clip_ms": parts[0], "denoise_50_steps_ms": parts[1],
+                              "vae_decode_ms": parts[2]}
+        del smp
+    out["what"] = ("text ids -> CLIP -> 50 DDIM steps (CFG 7.5) -> VAE decode -> uint8 512x512 on the host, all b200sd kernels; wall "
+                   "clock per call incl. H2D / D2H")
+    del clip, vae
+    return out
 
 
 def train_text_leg(dev, world, rank, local, steps=5, warmup=3, B=8, unet=None):

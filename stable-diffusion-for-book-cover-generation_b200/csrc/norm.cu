@@ -486,7 +486,11 @@ extern "C" int b200sd_groupnorm_silu_split(const void* x0, const void* x1, int C
         while ((G * cpg) % 8 != 0 && G < groups) G *= 2;
         while (G * 2 <= groups && groups % (G * 2) == 0 && G * cpg < 32) G *= 2;   // >= 32 channels per pixel segment
         const int Cg = G * cpg;
-        if ((Cg % 8) == 0 && groups % G == 0 && Cg / 8 <= 512) {
+        // The single-kernel path keeps an image's pixels on at most 8 CTAs per channel set: right for the UNet (<= 2.6 M elements
+        // per image, launch latency dominates), hopeless for the VAE's 256^2 / 512^2 levels (33 M elements on 32 CTAs measured
+        // 832 us = 0.4 TB/s).  Large images take the two-kernel path below: 128 statistics slabs + 4 apply CTAs per SM.
+        static const long fused_max = [] { const char* e = getenv("B200SD_GN_FUSED_MAX"); return e ? atol(e) : 3000000L; }();
+        if ((Cg % 8) == 0 && groups % G == 0 && Cg / 8 <= 512 && (long)hw * C <= fused_max) {
             const int VC = Cg / 8;
             const int sets = groups / G;
             int CL = 1;

@@ -399,47 +399,56 @@ class Engine:
             return self.out.clone()
 
     def profile(self, iters=5):
-        """Per-launch device time of every plan entry measured INSIDE the step: the whole plan is captured once more into a CUDA
-        graph with an external event-record node (b200sd_timer_record) between consecutive entries, and the replays are read
-        back per entry.  Every kernel therefore runs under the conditions of the real step -- its weights streaming cold from
-        HBM, its input left in L2 by its true predecessor, no host launch gaps.  (The first version replayed each entry four
-        times back to back in a graph of its own: warm weights, optimistic.)  Returns ({kind: [ms, flops, launches]} per step,
-        [(name, ms, flops)] per entry, ms of the whole instrumented replay)."""
-        with torch.cuda.device(self.device):
-            entries = [(op, meta) for op, meta in zip(self.plan, self.plan.meta) if meta[0] != "tap"]
-            n = len(entries)
-            check(lib().b200sd_timer_reserve(n + 1), "timer_reserve")
-            self._run_plan()
+        """Per-launch device time of every plan entry measured INSIDE the step (see profile_plan)."""
+        return profile_plan(self.plan, self.device, iters)
+
+
+def profile_plan(plan, device, iters=5):
+    """Per-launch device time of every entry of a launch plan measured INSIDE the step: the whole plan is captured once more
+    into a CUDA graph with an external event-record node (b200sd_timer_record) between consecutive entries, and the replays are
+    read back per entry.  Every kernel therefore runs under the conditions of the real step -- its weights streaming cold from
+    HBM, its input left in L2 by its true predecessor, no host launch gaps.  (The first version replayed each entry four
+    times back to back in a graph of its own: warm weights, optimistic.)  Returns ({kind: [ms, flops, launches]} per step,
+    [(name, ms, flops)] per entry, ms of the whole instrumented replay)."""
+    with torch.cuda.device(device):
+        entries = [(op, meta) for op, meta in zip(plan, plan.meta) if meta[0] != "tap"]
+        n = len(entries)
+        check(lib().b200sd_timer_reserve(n + 1), "timer_reserve")
+
+        def run_all():
+            for op, _m in entries:
+                op()
+        run_all()
+        torch.cuda.synchronize()
+        side = torch.cuda.Stream()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=side):
+            sh = torch.cuda.current_stream().cuda_stream
+            for i, (op, _meta) in enumerate(entries):
+                check(lib().b200sd_timer_record(i, sh), "timer_record")
+                op()
+            check(lib().b200sd_timer_record(n, sh), "timer_record")
+        torch.cuda.synchronize()
+        times = [0.0] * n
+        total = 0.0
+        ms = C.c_float(0.0)
+        g.replay()          # warm-up replay of the instrumented graph
+        torch.cuda.synchronize()
+        for _ in range(iters):
+            g.replay()
             torch.cuda.synchronize()
-            side = torch.cuda.Stream()
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, stream=side):
-                sh = torch.cuda.current_stream().cuda_stream
-                for i, (op, _meta) in enumerate(entries):
-                    check(lib().b200sd_timer_record(i, sh), "timer_record")
-                    op()
-                check(lib().b200sd_timer_record(n, sh), "timer_record")
-            torch.cuda.synchronize()
-            times = [0.0] * n
-            total = 0.0
-            ms = C.c_float(0.0)
-            g.replay()          # warm-up replay of the instrumented graph
-            torch.cuda.synchronize()
-            for _ in range(iters):
-                g.replay()
-                torch.cuda.synchronize()
-                for i in range(n):
-                    check(lib().b200sd_timer_elapsed_ms(i, i + 1, C.byref(ms)), "timer_elapsed")
-                    times[i] += ms.value / iters
-                check(lib().b200sd_timer_elapsed_ms(0, n, C.byref(ms)), "timer_elapsed")
-                total += ms.value / iters
-            acc, per_op = {}, []
-            for t, (op, (kind, flops, name)) in zip(times, entries):
-                a = acc.setdefault(kind, [0.0, 0.0, 0])
-                a[0] += t
-                a[1] += flops
-                a[2] += 1
-                per_op.append((name or kind, t, flops))
-            self._run_plan()
-            torch.cuda.synchronize()
-        return acc, per_op, total
+            for i in range(n):
+                check(lib().b200sd_timer_elapsed_ms(i, i + 1, C.byref(ms)), "timer_elapsed")
+                times[i] += ms.value / iters
+            check(lib().b200sd_timer_elapsed_ms(0, n, C.byref(ms)), "timer_elapsed")
+            total += ms.value / iters
+        acc, per_op = {}, []
+        for t, (op, (kind, flops, name)) in zip(times, entries):
+            a = acc.setdefault(kind, [0.0, 0.0, 0])
+            a[0] += t
+            a[1] += flops
+            a[2] += 1
+            per_op.append((name or kind, t, flops))
+        run_all()
+        torch.cuda.synchronize()
+    return acc, per_op, total

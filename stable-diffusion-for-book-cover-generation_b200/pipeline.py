@@ -135,7 +135,7 @@ class StableDiffusionPipeline:
 
     @classmethod
     def from_pretrained(cls, path, torch_dtype=None, safety_checker=None, scheduler=None, **overrides):
-        """Loads `unet/` and `scheduler/` with b200sd's classes; tokenizer / text encoder through transformers when their
+        """Loads `unet/` and `scheduler/` with b200sd's classes, and the text encoder / VAE with b200sd's when their
         `text_encoder/` and `vae/` sub-folders exist (b200sd.clip.CLIPTextModel, b200sd.vae.AutoencoderKL); the tokenizer through
         transformers (offline)."""
         from . import schedulers as S

@@ -191,3 +191,35 @@ def test_pipeline_text_to_image_on_own_clip_unet_vae():
         want = (o_vae.decode(want_l / 0.18215).sample / 2 + 0.5).clamp(0, 1)
     assert tuple(out.shape) == (1, 3, 256, 256)
     assert float((out.cpu() - want).abs().max()) <= 2e-2
+
+
+def test_pipeline_save_and_reload_with_all_four_models(tmp_path):
+    """finetune_sd.py:517-537 builds StableDiffusionPipeline(text_encoder, vae, unet, tokenizer, scheduler) and saves it;
+    utils.py:181-256 / inference.py:404-429 load it back: model_index.json + unet/ scheduler/ text_encoder/ vae/ round-trip
+    into b200sd's own classes and sample the same image; text_encoder(ids)[0] feeds the UNet directly."""
+    from b200sd.clip import CLIPTextModel
+    from b200sd.pipeline import StableDiffusionPipeline
+    from b200sd.schedulers import DDIMScheduler
+    from b200sd.unet import UNet2DConditionModel
+    from b200sd.vae import AutoencoderKL
+    from oracle.unet_ref import TINY_OVERRIDES
+    from oracle.vae_ref import TINY_VAE_OVERRIDES
+    torch.manual_seed(0)
+    unet = UNet2DConditionModel(**TINY_OVERRIDES).to(DEV).eval()
+    vae = AutoencoderKL(**TINY_VAE_OVERRIDES).to(DEV).eval()
+    te = CLIPTextModel(vocab_size=1000, hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=1).to(DEV).eval()
+    sch = DDIMScheduler(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear", clip_sample=False, set_alpha_to_one=False)
+    pipe = StableDiffusionPipeline(vae=vae, text_encoder=te, unet=unet, scheduler=sch)
+    d = str(tmp_path / "pipe")
+    pipe.save_pretrained(d)
+    import json, os
+    index = json.load(open(os.path.join(d, "model_index.json")))
+    assert index["vae"] == ["diffusers", "AutoencoderKL"] and index["text_encoder"] == ["transformers", "CLIPTextModel"]
+    pipe2 = StableDiffusionPipeline.from_pretrained(d).to(DEV)
+    assert type(pipe2.vae) is AutoencoderKL and type(pipe2.text_encoder) is CLIPTextModel and type(pipe2.unet) is UNet2DConditionModel
+    ids = torch.randint(2, 900, (2, 77), generator=torch.Generator().manual_seed(1)).to(DEV)
+    lat = torch.randn(1, 4, 32, 32, generator=torch.Generator().manual_seed(2)).to(DEV)
+    with torch.no_grad():
+        a = pipe(prompt_embeds=pipe.text_encoder(ids)[0], height=256, width=256, num_inference_steps=3, latents=lat, output_type="pt").images
+        b = pipe2(prompt_embeds=pipe2.text_encoder(ids)[0], height=256, width=256, num_inference_steps=3, latents=lat, output_type="pt").images
+    assert torch.equal(a, b) and tuple(a.shape) == (1, 3, 256, 256) and float(a.min()) >= 0.0 and float(a.max()) <= 1.0
