@@ -566,14 +566,14 @@ def run_sweep(args):
             g = torch.Generator().manual_seed(42 + rank)
             lat = torch.randn(B, 4, h, w, generator=g).to(dev)
             ctx = torch.randn(2 * B, 77, 768, generator=g).to(dev)
-            x2 = torch.empty(2 * B, 4, h, w, device=dev)
-            nxt = torch.empty_like(lat)
+            from b200sd.sampler import CapturedSampler
+            smp = CapturedSampler(unet, sch, B, h, w, 77, 7.5)       # the whole step as one CUDA graph (what denoise_loop runs)
+            smp.set_context(ctx)
+            smp.set_latents(lat)
+            smp.reset(0)
             with torch.no_grad():
                 def step(i):
-                    nonlocal lat, nxt
-                    x2[:B].copy_(lat); x2[B:].copy_(lat)
-                    sch.step_cfg(unet(x2, ts[i % 50], ctx).sample, ts[i % 50], lat, 7.5, out=nxt)
-                    lat, nxt = nxt, lat
+                    smp.step()
                 for i in range(max(args.warmup, 3)):
                     step(i)
         if world > 1:
@@ -607,6 +607,7 @@ def run_sweep(args):
                               "tflops_per_active_gpu": (total / max(n_active, 1)) * flops_per_img_it / (ms_max * 1e-3) / 1e12 if ms_max else 0,
                               "config": sample_config(B, world, total, args.portrait)}), flush=True)
         unet._engines = {}
+        smp = step = None
         torch.cuda.empty_cache()
     if world > 1:
         dist.destroy_process_group()

@@ -229,3 +229,67 @@ def test_text_encoder_finetune_step_through_the_frozen_unet():
             moved += 1
     assert moved > 20
     assert all(float(p.grad.abs().max()) == 0.0 for p in clip.parameters())                   # zeroed by the fused step
+
+
+def test_reference_shaped_text_encoder_training_loop_under_ddp():
+    """The reference's default mode wired as finetune_sd.py does it: `text_encoder = accelerator.prepare(text_encoder)` ->
+    DistributedDataParallel (:375-377), `unet.to(device, dtype=torch.float16)` frozen (:391-395), forward under autocast (:453),
+    `F.mse_loss(...).mean([1,2,3]).mean()` (:483-484), `accelerator.backward` + a torch optimizer (:494, 569-570): the CLIP
+    gradients arrive in param.grad through DDP's hooks and match torch autograd through the two oracles."""
+    import os
+    import torch.distributed as dist
+    import torch.nn.functional as F
+    from b200sd.clip import CLIPTextModel
+    from b200sd.schedulers import DDPMScheduler
+    from b200sd.unet import UNet2DConditionModel
+    from oracle import schedulers_ref as R
+    from oracle.clip_ref import make_oracle_clip
+    from oracle.unet_ref import TINY_OVERRIDES, make_oracle_unet
+    clip_kw = dict(vocab_size=1000, hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=1)
+    o_unet, o_clip = make_oracle_unet(seed=0, **TINY_OVERRIDES), make_oracle_clip(seed=0, **clip_kw)
+    clip = CLIPTextModel(**clip_kw)
+    clip.load_state_dict(o_clip.state_dict(), strict=True)
+    clip = clip.to(DEV).train()
+    unet = UNet2DConditionModel(**TINY_OVERRIDES)
+    unet.load_state_dict(o_unet.state_dict(), strict=True)
+    unet = unet.to(DEV, dtype=torch.float16).requires_grad_(False).eval()
+    B = 2
+    ids, g = _ids(B, 1000, 21)
+    x0, noise = torch.randn(B, 4, 32, 32, generator=g), torch.randn(B, 4, 32, 32, generator=g)
+    t = torch.tensor([77, 640])
+    for p in o_clip.parameters():
+        p.requires_grad_(True)
+    F.mse_loss(o_unet(R.DDPMSchedulerRef().add_noise(x0, noise, t), t, o_clip(ids)[0]).sample, noise).backward()
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29578")
+    created = not dist.is_initialized()
+    if created:
+        dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device(DEV))
+    try:
+        ddp = torch.nn.parallel.DistributedDataParallel(clip, device_ids=[0])
+        opt = torch.optim.AdamW(ddp.parameters(), lr=1e-4)
+        sched = DDPMScheduler(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear", num_train_timesteps=1000)
+        with torch.autocast("cuda", dtype=torch.float16):
+            ctx = ddp(ids.to(DEV))[0]
+            noisy = sched.add_noise(x0.to(DEV), noise.to(DEV), t.to(DEV))
+            pred = unet(noisy.half(), t.to(DEV), ctx.half()).sample
+            loss = F.mse_loss(pred.float(), noise.to(DEV), reduction="none").mean([1, 2, 3]).mean()
+        loss.backward()
+        ref = dict(o_clip.named_parameters())
+        dot = n1 = n2 = 0.0
+        for n, p in clip.named_parameters():
+            assert p.grad is not None, n
+            a, b = p.grad.float().cpu().double(), ref[n].grad.double()
+            dot += float((a * b).sum()); n1 += float((a * a).sum()); n2 += float((b * b).sum())
+        cos = dot / (n1 ** 0.5 * n2 ** 0.5)
+        assert cos >= 0.99, cos
+        w0 = clip.text_model.encoder.layers[0].mlp.fc1.weight.detach().clone()
+        opt.step()
+        opt.zero_grad()
+        assert float((clip.text_model.encoder.layers[0].mlp.fc1.weight - w0).abs().max()) > 0
+        with torch.no_grad():                      # the next forward sees the updated weights (version-tracked bf16 re-cast)
+            again = ddp(ids.to(DEV))[0]
+        assert float((again - ctx.float()).abs().max()) > 0
+    finally:
+        if created:
+            dist.destroy_process_group()

@@ -210,3 +210,58 @@ def test_pipeline_call_matches_the_oracle_loop():
     assert out.images.shape == (2, 4, 32, 32) and cos >= 0.999, cos
     with pytest.raises(ValueError, match="Unexpected latents shape"):
         pipe(prompt_embeds=ctx2.to(DEV), height=256, width=256, latents=lat[:, :, :16].to(DEV))
+
+
+def test_reference_train_unet_loop_body_with_all_four_models():
+    """The loop body of finetune_sd.py:453-494 in train_unet mode, every model b200sd's own (reduced widths):
+        latents = vae.encode(batch["pixel_values"]).latent_dist.sample() * 0.18215        :460-462  (frozen fp16 VAE)
+        noise, timesteps; noisy_latents = noise_scheduler.add_noise(...)                  :465-474
+        encoder_hidden_states = text_encoder(batch["input_ids"])[0]                       :477      (frozen fp16 CLIP)
+        noise_pred = unet(noisy_latents, timesteps, encoder_hidden_states).sample         :480-481
+        loss = F.mse_loss(...).mean([1,2,3]).mean(); backward; optimizer.step()           :483-494, 569-570
+    The loss must equal the chain of oracles on the same posterior noise, and a few steps must reduce it."""
+    from b200sd.clip import CLIPTextModel
+    from b200sd.schedulers import DDPMScheduler
+    from b200sd.vae import AutoencoderKL
+    from oracle import schedulers_ref as R
+    from oracle.clip_ref import make_oracle_clip
+    from oracle.vae_ref import TINY_VAE_OVERRIDES, make_oracle_vae
+    o_unet, unet = _pair(train=True)
+    clip_kw = dict(vocab_size=1000, hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=1)
+    o_clip, o_vae = make_oracle_clip(seed=0, **clip_kw), make_oracle_vae(seed=0, **TINY_VAE_OVERRIDES)
+    clip = CLIPTextModel(**clip_kw)
+    clip.load_state_dict(o_clip.state_dict(), strict=True)
+    clip = clip.to(DEV, dtype=torch.float16).requires_grad_(False).eval()
+    vae = AutoencoderKL(**TINY_VAE_OVERRIDES)
+    vae.load_state_dict(o_vae.state_dict(), strict=True)
+    vae = vae.to(DEV, dtype=torch.float16).requires_grad_(False).eval()
+    g = torch.Generator().manual_seed(9)
+    B = 2
+    pixels = torch.randn(B, 3, 256, 256, generator=g).clamp(-1, 1)
+    ids = torch.randint(2, 990, (B, 77), generator=g)
+    t = torch.tensor([150, 720])
+    sched = DDPMScheduler(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear", num_train_timesteps=1000)
+    opt = torch.optim.AdamW(unet.parameters(), lr=2e-4)
+    losses = []
+    for it in range(4):
+        with torch.autocast("cuda", dtype=torch.float16):
+            post = vae.encode(pixels.to(DEV).half()).latent_dist
+            gen = torch.Generator(device=DEV).manual_seed(100)
+            latents = post.sample(generator=gen) * 0.18215
+            noise = torch.randn(latents.shape, generator=torch.Generator(device=DEV).manual_seed(200), device=DEV).to(latents.dtype)
+            noisy = sched.add_noise(latents, noise, t.to(DEV))
+            ehs = clip(ids.to(DEV))[0]
+            pred = unet(noisy, t.to(DEV), ehs).sample
+            loss = F.mse_loss(pred.float(), noise.float(), reduction="none").mean([1, 2, 3]).mean()
+        if it == 0:
+            with torch.no_grad():
+                eps = torch.randn(latents.shape, generator=torch.Generator(device=DEV).manual_seed(100), device=DEV).cpu()
+                lat_ref = o_vae.encode(pixels).latent_dist.sample(noise=eps) * 0.18215
+                noisy_ref = R.DDPMSchedulerRef().add_noise(lat_ref, noise.float().cpu(), t)
+                want = F.mse_loss(o_unet(noisy_ref, t, o_clip(ids)[0]).sample, noise.float().cpu())
+            assert abs(float(loss) - float(want)) <= 3e-2 * float(want), (float(loss), float(want))
+        loss.backward()
+        opt.step()
+        opt.zero_grad()
+        losses.append(float(loss))
+    assert losses[-1] < losses[0], losses
