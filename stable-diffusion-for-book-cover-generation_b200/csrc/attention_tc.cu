@@ -415,10 +415,14 @@ int b200sd_attention_tc(const void* q, const void* k, const void* v, void* out, 
                                       static_cast<bf16*>(out), lse, batch, heads, Sq, Skv, ldq, ldk, ldv, ldo, scale, s)
     if (d == 40) {
         if (poly == 0) B200SD_ATTN_GO(40, 1, 0, 4);
+        if (poly == 2) B200SD_ATTN_GO(40, 1, 2, 4);
+        if (poly == 3) B200SD_ATTN_GO(40, 1, 3, 4);
         B200SD_ATTN_GO(40, 1, 4, 4);
     }
     if (d == 80) {
         if (poly == 0) B200SD_ATTN_GO(80, 2, 0, 4);
+        if (poly == 2) B200SD_ATTN_GO(80, 2, 2, 4);
+        if (poly == 3) B200SD_ATTN_GO(80, 2, 3, 4);
         B200SD_ATTN_GO(80, 2, 4, 4);
     }
     B200SD_ATTN_GO(160, 3, 4, 2);

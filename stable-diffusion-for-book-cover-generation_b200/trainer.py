@@ -147,6 +147,19 @@ class Trainer:
         return loss.detach()
 
 
+def allreduce_in_chunks(flat: torch.Tensor, chunks: int, group=None):
+    """SUM-allreduce a flat buffer as `chunks` asynchronous pieces (the first is on the wire while the host queues the rest);
+    returns the (begin, end) ranges it used.  A world of 1 reduces nothing."""
+    n = flat.numel()
+    step = (n + max(1, int(chunks)) - 1) // max(1, int(chunks))
+    ranges = [(a, min(a + step, n)) for a in range(0, n, step)]
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        works = [dist.all_reduce(flat[a:b], op=dist.ReduceOp.SUM, group=group, async_op=True) for a, b in ranges]
+        for w in works:
+            w.wait()
+    return ranges
+
+
 class TextEncoderTrainer:
     """Data-parallel fine-tuning step of the TEXT ENCODER with the UNet frozen (BASELINE config 4; the reference's default mode,
     finetune_sd.py:29, 375-383, 391-395, 477-494):
@@ -193,12 +206,7 @@ class TextEncoderTrainer:
         self.micro_steps += 1
         if sync:
             if self.world > 1 and self.allreduce_enabled:
-                n = flat.grad.numel()
-                step = (n + self.chunks - 1) // self.chunks
-                works = [dist.all_reduce(flat.grad[a:min(a + step, n)], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
-                         for a in range(0, n, step)]
-                for w in works:
-                    w.wait()
+                allreduce_in_chunks(flat.grad, self.chunks, self.group)
             self.opt.step(grad_scale=1.0 / (self.world * self.micro_steps), zero_grad=True)
             self.micro_steps = 0
         return loss.detach()

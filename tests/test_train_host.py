@@ -75,6 +75,67 @@ def test_bucket_reducer_single_process_ranges():
     assert r.ranges == [(0, 1000)]
 
 
+def test_clip_flat_rehoming_keeps_the_transformers_surface():
+    """ClipFlat: every CLIP parameter is a view of one master buffer, q|k|v weights and biases adjacent (one fused QKV GEMM),
+    state_dict unchanged."""
+    from b200sd.clip import CLIPTextModel, ClipFlat
+    torch.manual_seed(0)
+    m = CLIPTextModel(vocab_size=300, hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=1)
+    before = {k: v.clone() for k, v in m.state_dict().items()}
+    flat = ClipFlat(m, torch.device("cpu"))
+    assert flat.owns(m) and flat.total % 64 == 0
+    after = m.state_dict()
+    assert list(after) == list(before) and all(torch.equal(after[k], before[k]) for k in before)
+    a = m.text_model.encoder.layers[1].self_attn
+    assert torch.equal(flat.span([a.q_proj.weight, a.k_proj.weight, a.v_proj.weight], "master"),
+                       torch.cat([a.q_proj.weight, a.k_proj.weight, a.v_proj.weight]).detach())
+    assert torch.equal(flat.span([a.q_proj.bias, a.k_proj.bias, a.v_proj.bias], "master"),
+                       torch.cat([a.q_proj.bias, a.k_proj.bias, a.v_proj.bias]).detach())
+    tm = m.text_model
+    offs = [flat.reg(p).off for p in (tm.embeddings.token_embedding.weight, tm.encoder.layers[0].layer_norm1.weight,
+                                      tm.encoder.layers[1].mlp.fc2.bias, tm.final_layer_norm.bias)]
+    assert offs == sorted(offs) and offs[0] == 0
+    flat.attach_grads()
+    assert a.q_proj.weight.grad.shape == a.q_proj.weight.shape
+
+
+def test_allreduce_in_chunks_ranges_single_process():
+    from b200sd.trainer import allreduce_in_chunks
+    assert allreduce_in_chunks(torch.ones(10), 4) == [(0, 3), (3, 6), (6, 9), (9, 10)]
+    assert allreduce_in_chunks(torch.ones(8), 1) == [(0, 8)]
+    assert allreduce_in_chunks(torch.ones(3), 8) == [(0, 1), (1, 2), (2, 3)]
+
+
+def _chunk_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from b200sd.trainer import allreduce_in_chunks
+        flat = torch.arange(1001, dtype=torch.float32) * (rank + 1)
+        ranges = allreduce_in_chunks(flat, 4)
+        want = torch.arange(1001, dtype=torch.float32) * sum(range(1, world + 1))
+        q.put((rank, bool(torch.equal(flat, want)), ranges))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_allreduce_in_chunks_two_ranks_gloo():
+    """the text-encoder trainer's collective (BASELINE config 4 at N > 1), gloo here / NCCL on the GPU box"""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_chunk_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, ok, ranges in res:
+        assert ok, f"rank {rank}: chunked allreduce result wrong"
+        assert ranges == [(0, 251), (251, 502), (502, 753), (753, 1001)]
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))

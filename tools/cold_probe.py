@@ -51,23 +51,23 @@ def case(kind, M, N, K, conv=None, res=True, f32=True, geglu=False, variants=((0
     L.b200sd_debug_set(0, -1)
     print(row, flush=True)
 
-case("conv", 128, 1280, 11520, conv=(2, 8, 8))
-case("conv", 128, 1280, 23040, conv=(2, 8, 8))
-case("conv", 512, 1280, 11520, conv=(2, 16, 16))
-case("conv", 512, 1280, 23040, conv=(2, 16, 16))
-case("gemm", 512, 1280, 1280)
-case("gemm", 512, 1280, 5120)
-case("gemm", 2048, 640, 2560)
-case("gemm", 128, 1280, 1280)
-case("conv", 2048, 640, 5760, conv=(2, 32, 32))
-if os.environ.get("SMALL_ONLY"): sys.exit(0)
-case("gemm", 8192, 320, 320)
-case("gemm", 2048, 640, 640)
-case("gemm", 8192, 320, 1280)
-case("gemm", 8192, 960, 320, res=False, f32=False)
-case("gemm", 2048, 1920, 640, res=False, f32=False)
-case("conv", 8192, 320, 2880, conv=(2, 64, 64))
-case("conv", 2048, 640, 5760, conv=(2, 32, 32))
-case("geglu", 8192, 2560, 320, geglu=True, variants=((0, 160), (1, 256), (1, 128)))
-case("geglu", 2048, 5120, 640, geglu=True, variants=((0, 160), (1, 256), (1, 128)))
-case("geglu", 512, 10240, 1280, geglu=True, variants=((0, 160), (1, 256), (1, 128)))
+if __name__ == "__main__": case("conv", 128, 1280, 11520, conv=(2, 8, 8))
+if __name__ == "__main__": case("conv", 128, 1280, 23040, conv=(2, 8, 8))
+if __name__ == "__main__": case("conv", 512, 1280, 11520, conv=(2, 16, 16))
+if __name__ == "__main__": case("conv", 512, 1280, 23040, conv=(2, 16, 16))
+if __name__ == "__main__": case("gemm", 512, 1280, 1280)
+if __name__ == "__main__": case("gemm", 512, 1280, 5120)
+if __name__ == "__main__": case("gemm", 2048, 640, 2560)
+if __name__ == "__main__": case("gemm", 128, 1280, 1280)
+if __name__ == "__main__": case("conv", 2048, 640, 5760, conv=(2, 32, 32))
+if __name__ == "__main__" and os.environ.get("SMALL_ONLY"): sys.exit(0)
+if __name__ == "__main__": case("gemm", 8192, 320, 320)
+if __name__ == "__main__": case("gemm", 2048, 640, 640)
+if __name__ == "__main__": case("gemm", 8192, 320, 1280)
+if __name__ == "__main__": case("gemm", 8192, 960, 320, res=False, f32=False)
+if __name__ == "__main__": case("gemm", 2048, 1920, 640, res=False, f32=False)
+if __name__ == "__main__": case("conv", 8192, 320, 2880, conv=(2, 64, 64))
+if __name__ == "__main__": case("conv", 2048, 640, 5760, conv=(2, 32, 32))
+if __name__ == "__main__": case("geglu", 8192, 2560, 320, geglu=True, variants=((0, 160), (1, 256), (1, 128)))
+if __name__ == "__main__": case("geglu", 2048, 5120, 640, geglu=True, variants=((0, 160), (1, 256), (1, 128)))
+if __name__ == "__main__": case("geglu", 512, 10240, 1280, geglu=True, variants=((0, 160), (1, 256), (1, 128)))
