@@ -78,6 +78,14 @@ int b200sd_cfg_ddim_step_table(const void* eps_u, const void* eps_c, const void*
                                int64_t n, float guidance, const float* coef_table, const int* cursor,
                                int eps_dtype, int x_dtype, b200sd_stream_t stream);
 
+/* The PLMS counterpart of b200sd_cfg_ddim_step_table (fp32): x (the latents) is updated in place; `saved` (n floats) holds the
+ * sample of the first call for PNDM's repeated first timestep; `ring` is the 4-deep eps history (4 * n floats).  Per call one
+ * row of 12 floats of `table`, indexed by cursor[1]: w0 w1 w2 w3 | cx ce | h1 h2 h3 (ring slot of ets[-1], ets[-2], ets[-3];
+ * -1 = unused) | out_slot (-1 = this call's eps is not kept) | x_from_saved | save_x.  The host fills the table by running
+ * PNDMScheduler's counter logic once (sampler.py); reference call site utils.py:222-224. */
+int b200sd_cfg_plms_step_table(const float* eps_u, const float* eps_c, float* x, float* saved, float* ring, int64_t n,
+                               float guidance, const float* table, const int* cursor, b200sd_stream_t stream);
+
 /* CFG combine fused with the PLMS (PNDM skip_prk_steps=True) linear-multistep update:
  *   eps = eps_u + g (eps_c - eps_u);  e = w[0] eps + sum_{i<nhist} w[1+i] hist[i];
  *   out = cx * x - ce * e

@@ -367,6 +367,54 @@ extern "C" int b200sd_sampler_advance(const float* timesteps, int n_steps, int* 
     return B200SD_OK;
 }
 
+// Captured PLMS step: everything that changes from call to call -- the linear-multistep weights, which slots of the 4-deep eps
+// ring hold the history, where this call's eps goes, whether x is the running sample or the one saved by the first call
+// (PNDM's second call re-does the first timestep), the two scalars of _get_prev_sample -- is one row of a device table indexed
+// by the cursor.  Row layout (12 floats): w0 w1 w2 w3 | cx ce | h1 h2 h3 (ring slots, -1 = unused) | out_slot (-1 = not
+// kept) | x_from_saved | save_x.
+namespace {
+constexpr int kPlmsRow = 12;
+__global__ void __launch_bounds__(kThreads) cfg_plms_table_kernel(const float* __restrict__ eps_u, const float* __restrict__ eps_c,
+                                                                  float* __restrict__ x, float* __restrict__ saved,
+                                                                  float* __restrict__ ring, int64_t n, float g,
+                                                                  const float* __restrict__ table, const int* __restrict__ cursor) {
+    ptx::pdl_trigger();
+    ptx::pdl_wait();
+    const float* row = table + (size_t)cursor[1] * kPlmsRow;
+    const float w0 = row[0], w1 = row[1], w2 = row[2], w3 = row[3], cx = row[4], ce = row[5];
+    const int h1 = (int)row[6], h2 = (int)row[7], h3 = (int)row[8], slot = (int)row[9];
+    const bool from_saved = row[10] != 0.f, save_x = row[11] != 0.f;
+    const bool cfg = eps_c != nullptr;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const float eu = eps_u[i];
+        const float e = cfg ? (eu + g * (eps_c[i] - eu)) : eu;
+        float acc = w0 * e;
+        if (h1 >= 0) acc = fmaf(w1, ring[(size_t)h1 * n + i], acc);
+        if (h2 >= 0) acc = fmaf(w2, ring[(size_t)h2 * n + i], acc);
+        if (h3 >= 0) acc = fmaf(w3, ring[(size_t)h3 * n + i], acc);
+        const float cur = x[i];
+        const float xv = from_saved ? saved[i] : cur;
+        if (save_x) saved[i] = cur;
+        x[i] = cx * xv - ce * acc;
+        if (slot >= 0) ring[(size_t)slot * n + i] = e;
+    }
+}
+}  // namespace
+
+extern "C" int b200sd_cfg_plms_step_table(const float* eps_u, const float* eps_c, float* x, float* saved, float* ring, int64_t n,
+                                          float guidance, const float* table, const int* cursor, b200sd_stream_t stream) {
+    B200SD_REQUIRE(eps_u && x && saved && ring && table && cursor, "cfg_plms_step_table: null pointer");
+    B200SD_REQUIRE(n >= 0, "cfg_plms_step_table: negative n");
+    if (n == 0) return B200SD_OK;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    B200SD_CUDA(b200sd_launch(cfg_plms_table_kernel, dim3(grid_for(n)), dim3(kThreads), 0, s, eps_u, eps_c, x, saved, ring, n, guidance,
+                              table, cursor));
+    COUNT_LAUNCH();
+    B200SD_LAUNCH_CHECK();
+    return B200SD_OK;
+}
+
 extern "C" int b200sd_cfg_ddim_step_table(const void* eps_u, const void* eps_c, const void* x, void* out, void* eps_out,
                                           int64_t n, float guidance, const float* coef_table, const int* cursor,
                                           int eps_dtype, int x_dtype, b200sd_stream_t stream) {

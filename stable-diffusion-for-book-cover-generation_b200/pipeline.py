@@ -35,15 +35,15 @@ def denoise_loop(unet, scheduler, latents, encoder_hidden_states_2b, num_inferen
 
 def _captured_sampler(unet, scheduler, latents, ctx2, guidance_scale):
     """The whole-step CUDA graph (sampler.CapturedSampler) when the combination is covered: b200sd UNet on its bf16 plan with
-    CUDA graphs on, DDIM, CUDA tensors.  Cached on the UNet per (geometry, schedule, guidance); None -> the per-call loop."""
-    from .schedulers import DDIMScheduler
+    CUDA graphs on, DDIM or PLMS, CUDA tensors.  Cached on the UNet per (geometry, schedule, guidance); None -> the per-call loop."""
+    from .schedulers import DDIMScheduler, PNDMScheduler
     from .unet import UNet2DConditionModel
-    if not (isinstance(unet, UNet2DConditionModel) and isinstance(scheduler, DDIMScheduler) and latents.is_cuda
+    if not (isinstance(unet, UNet2DConditionModel) and isinstance(scheduler, (DDIMScheduler, PNDMScheduler)) and latents.is_cuda
             and unet._precision == "bf16" and unet.use_cuda_graph and not unet.training):
         return None
     from .sampler import CapturedSampler, default_lanes
     B, _, h, w = latents.shape
-    key = (B, h, w, ctx2.shape[1], latents.device.index, float(guidance_scale), default_lanes(B),
+    key = (type(scheduler).__name__, B, h, w, ctx2.shape[1], latents.device.index, float(guidance_scale), default_lanes(B),
            tuple(scheduler.timesteps.tolist()), tuple(sorted((k, str(v)) for k, v in vars(scheduler.config).items())))
     cache = unet.__dict__.setdefault("_samplers", {})
     smp = cache.get(key)

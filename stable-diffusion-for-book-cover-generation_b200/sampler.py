@@ -1,4 +1,4 @@
-"""The whole denoising step of StableDiffusionPipeline.__call__ as ONE CUDA graph (DDIM + classifier-free guidance).
+"""The whole denoising step of StableDiffusionPipeline.__call__ as ONE CUDA graph (DDIM or PLMS + classifier-free guidance).
 
 Reference call sites: the loop inside `pipeline(...)` -- inference.py:175-176, 342-351; finetune_sd.py:264-271 -- i.e. per
 step `latent_model_input = cat([latents] * 2)`, `unet(...)`, `noise_pred_uncond + guidance_scale * (...)`, `scheduler.step`.
@@ -10,6 +10,8 @@ What the graph holds (nothing is launched eagerly between two steps, the host on
            └─> lane 1: UNet plan over the CONDITIONAL half                 ──┤  (lanes: independent launch chains on
       join <──────────────────────────────────────────────────────────────────┘   forked streams of the same graph)
     cfg_ddim_step_table        latents <- DDIM(eps_u + g (eps_c - eps_u)), coefficients = table[cursor], in place
+    (PNDMScheduler / PLMS: cfg_plms_step_table -- weights, eps-ring slots and the saved-sample flags of this call = table[cursor];
+     the 4-deep eps history is a device ring, PNDM's repeated first timestep reads the sample saved by the first call)
 
 Lanes (`lanes` = 1, 2, or any even number that divides 2B into whole sub-batches of one half; default 1).  The two halves of
 the CFG batch never meet before the combine, so they can run as two independent launch chains reading the SAME latent buffer
@@ -42,9 +44,10 @@ def default_lanes(batch_images: int) -> int:
 
 class CapturedSampler:
     def __init__(self, unet, scheduler, batch_images, h, w, S_ctx=77, guidance_scale=7.5, lanes=None):
-        from .schedulers import DDIMScheduler
-        if not isinstance(scheduler, DDIMScheduler):
-            raise B200SDError("CapturedSampler covers DDIMScheduler (PLMS keeps its history on the host: use denoise_loop)")
+        from .schedulers import DDIMScheduler, PNDMScheduler
+        if not isinstance(scheduler, (DDIMScheduler, PNDMScheduler)):
+            raise B200SDError("CapturedSampler covers DDIMScheduler and PNDMScheduler (PLMS)")
+        self.plms = isinstance(scheduler, PNDMScheduler)
         if scheduler.num_inference_steps is None:
             raise ValueError("call scheduler.set_timesteps(n) first")
         if unet._precision != "bf16":
@@ -68,7 +71,12 @@ class CapturedSampler:
             ts = [float(t) for t in scheduler.timesteps.tolist()]
             self.n_steps = len(ts)
             self.t_table = torch.tensor(ts, **f32)
-            self.coef_table = torch.tensor([scheduler._coefs(int(t)) for t in ts], **f32).contiguous()
+            if self.plms:
+                self.coef_table = torch.tensor(scheduler.plms_plan(), **f32).contiguous()       # [calls][12]
+                self.saved = torch.zeros_like(self.latents)                                        # the first call's sample
+                self.ring = torch.zeros(4, self.latents.numel(), **f32)                            # eps history
+            else:
+                self.coef_table = torch.tensor([scheduler._coefs(int(t)) for t in ts], **f32).contiguous()
             self.cursor = torch.zeros(2, dtype=torch.int32, device=dev)
             self.streams = [torch.cuda.Stream(device=dev) for _ in range(L)]
             # lane l of L > 1: half = l // (L/2) (0 = unconditional), images [j*c, (j+1)*c) of that half
@@ -133,6 +141,12 @@ class CapturedSampler:
             self.x2[self.B:].copy_(self.latents)
         self._fork_join(lambda l: self.engines[l]._run_plan())
         B = self.B
+        if self.plms:
+            check(lib().b200sd_cfg_plms_step_table(self.eps[:B].data_ptr(), self.eps[B:].data_ptr(), self.latents.data_ptr(),
+                                                   self.saved.data_ptr(), self.ring.data_ptr(), self.latents.numel(), self.guidance,
+                                                   self.coef_table.data_ptr(), self.cursor.data_ptr(), ops._stream()),
+                  "cfg_plms_step_table")
+            return
         check(lib().b200sd_cfg_ddim_step_table(self.eps[:B].data_ptr(), self.eps[B:].data_ptr(), self.latents.data_ptr(),
                                                self.latents.data_ptr(), None, self.latents.numel(), self.guidance,
                                                self.coef_table.data_ptr(), self.cursor.data_ptr(), ops.F32, ops.F32,

@@ -222,6 +222,48 @@ class PNDMScheduler(_SchedulerBase):
         self.counter += 1
         return SchedulerOutput(prev_sample=prev)
 
+    def plms_plan(self):
+        """The whole call sequence of one sampling run as data: one row per UNet call for b200sd_cfg_plms_step_table
+        (w0 w1 w2 w3 | cx ce | ring slots of ets[-1], ets[-2], ets[-3] | slot this call's eps goes to | x_from_saved | save_x).
+        It is `_plms`'s counter logic run once on the host with a 4-slot eps ring instead of tensors, so that
+        sampler.CapturedSampler can replay every call as the same CUDA graph (the step index lives on the device)."""
+        if self.num_inference_steps is None:
+            raise ValueError("call set_timesteps first")
+        ratio = self.num_train_timesteps // self.num_inference_steps
+        rows, ets = [], []
+        for counter, timestep in enumerate(self.timesteps.tolist()):
+            t = int(timestep)
+            prev_t = t - ratio
+            keep_eps = counter != 1
+            if keep_eps:
+                ets = ets[-3:]
+                n_after = len(ets) + 1
+            else:
+                prev_t, t = t, t + ratio
+                n_after = len(ets)
+            from_saved = save_x = 0.0
+            if n_after == 1 and counter == 0:
+                w, hist, save_x = [1.0], [], 1.0
+            elif n_after == 1 and counter == 1:
+                w, hist, from_saved = [0.5, 0.5], [ets[-1]], 1.0
+            elif n_after == 2:
+                w, hist = [1.5, -0.5], [ets[-1]]
+            elif n_after == 3:
+                w, hist = [23 / 12, -16 / 12, 5 / 12], [ets[-1], ets[-2]]
+            else:
+                w, hist = [55 / 24, -59 / 24, 37 / 24, -9 / 24], [ets[-1], ets[-2], ets[-3]]
+            a_t, a_p = self._ac[t], self._alpha_prev(prev_t)
+            b_t, b_p = 1 - a_t, 1 - a_p
+            cx = (a_p / a_t) ** 0.5
+            ce = (a_p - a_t) / (a_t * b_p ** 0.5 + (a_t * b_t * a_p) ** 0.5)
+            slot = -1
+            if keep_eps:
+                slot = next(k for k in range(4) if k not in ets)       # ets holds <= 3 live slots here
+                ets.append(slot)
+            rows.append(w + [0.0] * (4 - len(w)) + [cx, ce] + [float(h) for h in hist] + [-1.0] * (3 - len(hist))
+                        + [float(slot), from_saved, save_x])
+        return rows
+
     def step(self, model_output, timestep, sample, **kw):
         return self._plms(model_output.contiguous(), None, timestep, sample, 0.0)
 

@@ -238,3 +238,37 @@ def test_pipeline_wrapper_save_load_layout(tmp_path):
         pipe(prompt_embeds=torch.zeros(2, 77, 64), height=100, width=64)
     with pytest.raises(ValueError):       # strings need a tokenizer / text encoder
         pipe("a book cover")
+
+
+def test_plms_plan_table_reproduces_the_oracle_pndm_scheduler():
+    """PNDMScheduler.plms_plan(): the per-call rows that drive the captured PLMS kernel (weights, eps-ring slots, saved-sample
+    flags, cx / ce), executed here in plain torch on a random eps sequence, must walk the same trajectory as the oracle's
+    PNDMScheduler (skip_prk_steps=True) -- including the repeated first timestep and the 4-deep history."""
+    import torch
+    from b200sd.schedulers import PNDMScheduler
+    from oracle import schedulers_ref as R
+    for steps, offset in ((50, 1), (50, 0), (7, 1), (4, 0)):
+        ours = PNDMScheduler(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear", skip_prk_steps=True, steps_offset=offset)
+        ours.set_timesteps(steps)
+        ref = R.PNDMSchedulerRef(skip_prk_steps=True, steps_offset=offset)
+        ref.set_timesteps(steps)
+        assert ours.timesteps.tolist() == ref.timesteps.tolist() and len(ours.timesteps) == steps + 1
+        rows = ours.plms_plan()
+        assert len(rows) == steps + 1 and all(len(r) == 12 for r in rows)
+        g = torch.Generator().manual_seed(steps)
+        x = torch.randn(2, 4, 4, 4, generator=g, dtype=torch.float64)
+        want = x.clone()
+        ring, saved = [None] * 4, None
+        for k, t in enumerate(ref.timesteps):
+            eps = torch.randn(2, 4, 4, 4, generator=g, dtype=torch.float64)
+            want = ref.step(eps, t, want).prev_sample
+            w, (cx, ce), h, (slot, from_saved, save_x) = rows[k][:4], rows[k][4:6], [int(v) for v in rows[k][6:9]], rows[k][9:]
+            acc = w[0] * eps + sum(w[1 + i] * ring[h[i]] for i in range(3) if h[i] >= 0)
+            xv = saved if from_saved else x
+            if save_x:
+                saved = x.clone()
+            x = cx * xv - ce * acc
+            if slot >= 0:
+                assert int(slot) not in [v for v in h if v >= 0]      # this call's eps never overwrites a slot it reads
+                ring[int(slot)] = eps
+            assert float((x - want).abs().max()) <= 2e-6 * max(1.0, float(want.abs().max())), (steps, offset, k)   # the oracle keeps its alpha table in fp32

@@ -398,3 +398,38 @@ def test_captured_sampler_batched_portrait_tiny_net(lanes):
     got = CapturedSampler(ours, sch, 2, 48, 32, 77, 7.5, lanes=lanes).run(lat.to(DEV), ctx2.to(DEV)).cpu()
     cos = float(torch.nn.functional.cosine_similarity(got.flatten(), want.flatten(), dim=0))
     assert cos >= 0.999, f"lanes={lanes}: cosine {cos:.6f}"
+
+
+def test_captured_sampler_plms_51_calls_vs_oracle_and_per_call_loop(models):
+    """utils.py:222-224: PNDM skip_prk_steps=True (PLMS).  The captured sampler replays all 51 UNet calls (the first timestep
+    twice) as the same CUDA graph with the eps history in a device ring: latents cosine >= 0.999 vs the fp32 oracle loop and
+    ~equal to our per-call loop."""
+    from b200sd.pipeline import denoise_loop
+    from b200sd.sampler import CapturedSampler
+    from b200sd.schedulers import PNDMScheduler
+    from oracle import schedulers_ref as R
+    oracle, ours = models
+    g = torch.Generator().manual_seed(11)
+    lat = torch.randn(1, 4, 64, 64, generator=g)
+    ctx2 = torch.randn(2, 77, 768, generator=g)
+    kw = dict(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear", skip_prk_steps=True, steps_offset=1)
+    oc = oracle.to(DEV)
+    try:
+        with torch.no_grad():
+            want = R.denoise_loop(oc, R.PNDMSchedulerRef(skip_prk_steps=True, steps_offset=1), lat.to(DEV), ctx2.to(DEV), 50, 7.5).cpu()
+    finally:
+        oracle.to("cpu")
+    sch = PNDMScheduler(**kw)
+    sch.set_timesteps(50)
+    smp = CapturedSampler(ours, sch, 1, 64, 64, 77, 7.5)
+    assert smp.n_steps == 51
+    got = smp.run(lat.to(DEV), ctx2.to(DEV)).cpu()
+    cos = float(torch.nn.functional.cosine_similarity(got.flatten(), want.flatten(), dim=0))
+    assert cos >= 0.999, f"captured PLMS latents cosine {cos:.6f}"
+    assert torch.equal(smp.run(lat.to(DEV), ctx2.to(DEV)).cpu(), got)          # ring / saved sample / cursor fully re-armed
+    rec = []
+    per_call = denoise_loop(ours, PNDMScheduler(**kw), lat.to(DEV), ctx2.to(DEV), 50, 7.5, record=rec).cpu()
+    cos2 = float(torch.nn.functional.cosine_similarity(got.flatten(), per_call.flatten(), dim=0))
+    assert cos2 >= 0.9999, f"captured vs per-call PLMS cosine {cos2:.6f}"
+    via_loop = denoise_loop(ours, PNDMScheduler(**kw), lat.to(DEV), ctx2.to(DEV), 50, 7.5).cpu()     # takes the captured sampler
+    assert torch.equal(via_loop, got)
