@@ -369,7 +369,10 @@ class CLIPTextModel(nn.Module):
 
     def _ensure_flat(self, dev):
         if self._flat is None or self._flat.device != dev or not self._flat.owns(self):
-            self._flat = ClipFlat(self, dev)
+            # fp16 / bf16 parameters (StableDiffusionPipeline.from_pretrained(torch_dtype=torch.float16), inference.py:406; the
+            # frozen copy of finetune_sd.py:381) keep their own storage, the kernels read an fp32 upcast: inference only --
+            # forward() refuses to TRAIN such a model
+            self._flat = ClipFlat(self, dev, allow_half_trainable=True)
             self._engines = {}
         return self._flat.materialize()
 
@@ -389,6 +392,9 @@ class CLIPTextModel(nn.Module):
         dev = ids.device
         flat = self._ensure_flat(dev)
         train = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+        if train and self.dtype != torch.float32:
+            raise B200SDError("training the text encoder needs fp32 master parameters (the kernels compute in bf16 on their own "
+                              "copy); run a half-precision model under torch.no_grad() or freeze it (requires_grad_(False))")
         key = (B, S, dev.index, train)
         eng = self._engines.get(key)
         if eng is None:

@@ -45,7 +45,7 @@ class FlatParams:
        grad   fp32  every parameter's gradient (accumulated by the backward kernels)
     state_dict() / load_state_dict() / torch optimizers keep working on the re-homed parameters."""
 
-    def __init__(self, model, device, lazy=False):
+    def __init__(self, model, device, lazy=False, allow_half_trainable=False):
         self.model, self.device = model, device
         self.regs = {}        # id(param) -> _Reg
         self.order = []
@@ -53,7 +53,7 @@ class FlatParams:
 
         def add(p, kind):
             nonlocal off
-            if p.dtype != F32 and p.requires_grad:
+            if p.dtype != F32 and p.requires_grad and not allow_half_trainable:
                 raise B200SDError("training needs fp32 master parameters (the kernels compute in bf16 on their own copy)")
             r = _Reg()
             # a FROZEN fp16 / bf16 parameter (finetune_sd.py:393: unet.to(device, dtype=torch.float16) while the text encoder

@@ -163,6 +163,15 @@ def test_frozen_fp16_text_encoder_and_direct_gradient_mode():
     frozen = ours.to(DEV, dtype=torch.float16).requires_grad_(False).eval()          # finetune_sd.py:381-383
     got = frozen(ids.to(DEV))[0]
     assert got.dtype == torch.float16 and _rel(got, want) <= 2e-2
+    # an fp16 pipeline (from_pretrained(torch_dtype=torch.float16), inference.py:406): parameters still require grad, the call
+    # runs under no_grad -> inference works; asking for gradients of a half-precision model is refused loudly
+    from b200sd._lib import B200SDError
+    _o, half = _pair(5, **TINY_CLIP_OVERRIDES)
+    half = half.to(DEV, dtype=torch.float16).eval()
+    with torch.no_grad():
+        assert _rel(half(ids.to(DEV))[0], want) <= 2e-2
+    with pytest.raises(B200SDError):
+        half(ids.to(DEV))
     oracle2, ours2 = _pair(5, **TINY_CLIP_OVERRIDES)
     ours2.train().enable_direct_gradients()
     w = torch.randn(2, 77, 128, generator=g)
