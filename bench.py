@@ -83,6 +83,31 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+# ---------------------------------------------------------------------------------------------------
+# stdout carries the JSON line(s) of this script and NOTHING else: the process that does the work moves file descriptor 1 onto
+# stderr (C-level writers included -- NCCL prints its "NCCL version ..." banner to stdout from inside init_process_group) and
+# writes its result lines to a private duplicate of the original stdout.
+# ---------------------------------------------------------------------------------------------------
+_RESULT_OUT = None
+
+
+def _claim_stdout():
+    global _RESULT_OUT
+    if _RESULT_OUT is None:
+        sys.stdout.flush()
+        _RESULT_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(text):
+    if _RESULT_OUT is None:
+        print(text, flush=True)
+    else:
+        _RESULT_OUT.write(text + "\n")
+        _RESULT_OUT.flush()
+
+
+
 def ddim_coefs(sch, t):
     return sch._coefs(t)
 
@@ -130,6 +155,7 @@ def cpu_oracle_it_per_s(batch_images, budget_s, max_iters, warmup=1, hw=(64, 64)
 
 
 def run_reference(args):
+    _claim_stdout()
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
@@ -145,7 +171,7 @@ def run_reference(args):
         "e2e": {"value": v, "unit": "it/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(json.dumps(line))
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -154,6 +180,7 @@ def run_reference(args):
 # Not the reference arm and not part of the driver contract -- a reported yardstick for the same workload.
 # ---------------------------------------------------------------------------------------------------
 def run_library(args):
+    _claim_stdout()
     if int(os.environ.get("RANK", 0)) != 0:
         return
     import torch
@@ -199,13 +226,13 @@ def run_library(args):
     finally:
         unet_ref.CrossAttention.forward = orig
     best = min(ms_mat, ms_sdpa)
-    print(json.dumps({
+    emit(json.dumps({
         "impl": "library", "metric": "unet_denoise_it_per_s", "value": B * 1e3 / best, "unit": "it/s", "n_gpus": 1,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": best, "higher_is_better": True, "dtype": "bf16",
         "data": "synthetic",
         "config": {"workload": "sd15_unet_cfg_batch%d_%s" % (2 * B, "512x768" if args.portrait else "512px"),
                    "what": "fp32-oracle module .cuda().bfloat16() under eager torch %s (cuDNN/cuBLASLt), UNet call only" % torch.__version__,
-                   "ms_per_step_materialised_attention": ms_mat, "ms_per_step_sdpa_attention": ms_sdpa}}), flush=True)
+                   "ms_per_step_materialised_attention": ms_mat, "ms_per_step_sdpa_attention": ms_sdpa}}))
 
 
 def shard_images(total: int, world: int, rank: int) -> int:
@@ -328,6 +355,7 @@ class _PerCallSampler:
 
 
 def run_ours(args):
+    _claim_stdout()
     import torch
     import torch.distributed as dist
     from b200sd import ops
@@ -529,7 +557,7 @@ def run_ours(args):
         line["text_to_image"] = t2i
         line["train"] = train
         line["train_text"] = train_text
-        print(json.dumps(line), flush=True)
+        emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
@@ -542,6 +570,7 @@ def run_sweep(args):
     chunks, remainder to the low ranks, ranks without an image idle), run `steps` denoising iterations of the 50-step CFG DDIM
     sampler and print ONE JSON line per B: whole-job images/s = B / (50 * max-over-ranks ms per iteration).  One model per rank,
     no collective on the data path."""
+    _claim_stdout()
     import torch
     import torch.distributed as dist
     from b200sd.schedulers import DDIMScheduler
@@ -601,11 +630,11 @@ def run_sweep(args):
             ms_max, n_active = ms, 0 if idle else 1
         if rank == 0:
             ips = total / (50.0 * ms_max * 1e-3)
-            print(json.dumps({"metric": "images_per_s", "value": ips, "unit": "images/s", "n_gpus": world, "gpus_active": n_active,
+            emit(json.dumps({"metric": "images_per_s", "value": ips, "unit": "images/s", "n_gpus": world, "gpus_active": n_active,
                               "gpus_idle": world - n_active, "total_images": total, "images_on_rank0": B if not idle else 0,
                               "ms_per_iteration_max_over_ranks": ms_max, "steps": args.steps, "scaling": "strong", "dtype": "bf16",
                               "tflops_per_active_gpu": (total / max(n_active, 1)) * flops_per_img_it / (ms_max * 1e-3) / 1e12 if ms_max else 0,
-                              "config": sample_config(B, world, total, args.portrait)}), flush=True)
+                              "config": sample_config(B, world, total, args.portrait)}))
         unet._engines = {}
         smp = step = None
         torch.cuda.empty_cache()
@@ -801,6 +830,7 @@ def train_text_leg(dev, world, rank, local, steps=5, warmup=3, B=8, unet=None):
 
 
 def run_train(args):
+    _claim_stdout()
     import torch
     import torch.distributed as dist
     from b200sd import ops
@@ -814,14 +844,14 @@ def run_train(args):
     if args.impl == "reference":
         if rank == 0:
             v, done, t_total, cores = cpu_oracle_train_samples_per_s(1, max(1, min(args.steps, 2)))
-            print(json.dumps({"impl": "reference", "metric": "unet_finetune_samples_per_s", "value": v, "unit": "samples/s",
+            emit(json.dumps({"impl": "reference", "metric": "unet_finetune_samples_per_s", "value": v, "unit": "samples/s",
                               "n_gpus": args.gpus, "steps": done, "warmup": 0, "ms_per_step": 1e3 * t_total / done,
                               "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                               "config": {"workload": "sd15_unet_finetune_512px", "batch_per_gpu": 1},
                               "cpu_baseline": {"value": v, "unit": "samples/s", "cores": cores, "kind": "port",
                                                "sample": f"{done} optimizer steps at batch 1 (fp32 oracle + torch autograd + AdamW)"},
                               "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                              "gpu_launches": 0}), flush=True)
+                              "gpu_launches": 0}))
         return
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -889,7 +919,7 @@ def run_train(args):
                 "roofline": {"bound": "tensor", "kernel": "whole step (forward + backward GEMM / conv / attention)", "achieved": achieved,
                              "peak": tf_sus, "unit": "TFLOP/s", "frac": achieved / tf_sus, "peak_kind": f"bf16 sustained, {which}",
                              "flops_per_step": flops_step, "traffic": None}}
-        print(json.dumps(line), flush=True)
+        emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
@@ -899,6 +929,7 @@ def run_train(args):
 # CLIP text encoder = b200sd.clip.CLIPTextModel (forward + backward on our kernels), flat-gradient allreduce
 # ---------------------------------------------------------------------------------------------------
 def run_train_text(args):
+    _claim_stdout()
     import torch
     import torch.distributed as dist
     from b200sd import ops
@@ -963,7 +994,7 @@ def run_train_text(args):
         step_ms = ms / args.steps
         flops_step = 2 * B * FLOPS_PER_SAMPLE_64          # UNet fwd + dgrad (CLIP ~0.3 % on top)
         achieved = flops_step / (step_ms * 1e-3) / 1e12
-        print(json.dumps({
+        emit(json.dumps({
             "metric": "text_encoder_finetune_samples_per_s", "value": samples / (ms * 1e-3), "unit": "samples/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
@@ -975,7 +1006,7 @@ def run_train_text(args):
             "gpu_launches": int(launches), "clocks": clocks,
             "roofline": {"bound": "tensor", "kernel": "whole step (UNet forward + data-gradient backward)", "achieved": achieved,
                          "peak": tf_sus, "unit": "TFLOP/s", "frac": achieved / tf_sus, "peak_kind": f"bf16 sustained, {which}",
-                         "flops_per_step": flops_step, "traffic": None}}), flush=True)
+                         "flops_per_step": flops_step, "traffic": None}}))
     if world > 1:
         dist.destroy_process_group()
 
