@@ -259,6 +259,8 @@ class TrainEngine:
         self.saved_bytes = 0
         self._keep = []
         self._gi = {}      # id(activation) -> [grad buffer, initialised?]
+        self._gn_parts = {}   # id(fp32 activation) -> ops.GnParts written by the GEMM that produced it
+        self.gn_from_gemm = __import__("os").environ.get("B200SD_TRAIN_GN_FROM_GEMM", "1") != "0"
         self.pool = _Pool(device)
         with torch.cuda.device(device):
             self._build()
@@ -270,11 +272,30 @@ class TrainEngine:
 
     def _gemm(self, plan, a0, w, out, **kw):
         rb = kw.pop("rowbias_ptr", None)
+        gn_hw = kw.pop("gn_hw", 0)     # > 0: `out` feeds a GroupNorm -- the epilogue also publishes its column statistics (engine.py)
         args = ops.gemm(a0, w, out, launch=False, **kw)
         if rb is not None:
             args.rowbias, args.ldrb, args.rows_per_image = rb
+        if gn_hw > 0 and self.gn_from_gemm:
+            parts = ops.gemm_attach_gn_parts(args, gn_hw, self.device)
+            if parts is not None:
+                self._gn_parts[id(out)] = parts      # forward buffers are never recycled here: the entry stays valid
+                self._keep.append(parts)
         self._keep.append((a0, w, out, kw))
         plan.append(lambda a=args: ops.gemm_run(a))
+
+    def _groupnorm(self, x, skip, g, b, out, hw, eps, silu, raw_out=None, stats_out=None):
+        """forward GroupNorm(+SiLU, +concat): apply-only from the producers' epilogue statistics when every source has them
+        (the forward keeps (mean, rstd) in stats_out for the backward either way)"""
+        N = self.N
+        p0 = self._gn_parts.get(id(x))
+        p1 = self._gn_parts.get(id(skip)) if skip is not None else None
+        C = x.shape[-1] + (skip.shape[-1] if skip is not None else 0)
+        if p0 is not None and (skip is None or p1 is not None) and ops.gn_parts_supported(C, 32):
+            self.fwd.append(lambda: ops.groupnorm_silu_parts(x, skip, p0, p1, g, b, out, N, hw, 32, eps, silu, raw_out=raw_out,
+                                                             stats_out=stats_out))
+        else:
+            self.fwd.append(lambda: ops.groupnorm_silu(x, skip, g, b, out, N, hw, 32, eps, silu, raw_out=raw_out, stats_out=stats_out))
 
     def _dgrad(self, dy, w, out, **kw):
         args = ops.gemm_dgrad(dy, w, out, launch=False, **kw)
@@ -380,19 +401,19 @@ class TrainEngine:
             t1 = self._new(M, cin)
             raw = self._new(M, cin) if has_sc else None
             st1, st2 = torch.empty(N, 32, 2, **f32), torch.empty(N, 32, 2, **f32)   # GroupNorm (mean, rstd), kept for the backward
-            Fp.append(lambda: ops.groupnorm_silu(x, skip, self.P(r.norm1.weight), self.P(r.norm1.bias), t1, N, hw, 32, eps, True, raw_out=raw, stats_out=st1))
+            self._groupnorm(x, skip, self.P(r.norm1.weight), self.P(r.norm1.bias), t1, hw, eps, True, raw_out=raw, stats_out=st1)
             hbuf = self._new(M, cout, F32)
             rb = (self.tproj.data_ptr() + tp_off[prefix] * 4, n_tp, hw)
-            self._gemm(Fp, t1, self.Wb(r.conv1.weight), hbuf, bias=self.P(r.conv1.bias), conv=(N, h, w), rowbias_ptr=rb)
+            self._gemm(Fp, t1, self.Wb(r.conv1.weight), hbuf, bias=self.P(r.conv1.bias), conv=(N, h, w), rowbias_ptr=rb, gn_hw=hw)
             t2 = self._new(M, cout)
-            Fp.append(lambda: ops.groupnorm_silu(hbuf, None, self.P(r.norm2.weight), self.P(r.norm2.bias), t2, N, hw, 32, eps, True, stats_out=st2))
+            self._groupnorm(hbuf, None, self.P(r.norm2.weight), self.P(r.norm2.bias), t2, hw, eps, True, stats_out=st2)
             if has_sc:
                 sc = self._new(M, cout, F32)
                 self._gemm(Fp, raw, self.Wb(r.conv_shortcut.weight), sc, bias=self.P(r.conv_shortcut.bias))
             else:
                 sc = x
             y = self._new(M, cout, F32)
-            self._gemm(Fp, t2, self.Wb(r.conv2.weight), y, bias=self.P(r.conv2.bias), residual=sc, conv=(N, h, w))
+            self._gemm(Fp, t2, self.Wb(r.conv2.weight), y, bias=self.P(r.conv2.bias), residual=sc, conv=(N, h, w), gn_hw=hw)
 
             def backward():
                 pool = self.pool
@@ -445,7 +466,7 @@ class TrainEngine:
             w_kv2 = flat.span([a2m.to_k.weight, a2m.to_v.weight], "wb")
             t = self._new(M, Cc)
             st = torch.empty(N, 32, 2, **f32)
-            Fp.append(lambda: ops.groupnorm_silu(x, None, self.P(a.norm.weight), self.P(a.norm.bias), t, N, hw, 32, 1e-6, False, stats_out=st))
+            self._groupnorm(x, None, self.P(a.norm.weight), self.P(a.norm.bias), t, hw, 1e-6, False, stats_out=st)
             hs0 = self._new(M, Cc, F32)
             self._gemm(Fp, t, self.Wb(a.proj_in.weight), hs0, bias=self.P(a.proj_in.bias))
             # self attention
@@ -482,7 +503,7 @@ class TrainEngine:
             hs3 = self._new(M, Cc)
             self._gemm(Fp, f, self.Wb(ff.net[2].weight), hs3, bias=self.P(ff.net[2].bias), residual=hs2)
             y = self._new(M, Cc, F32)
-            self._gemm(Fp, hs3, self.Wb(a.proj_out.weight), y, bias=self.P(a.proj_out.bias), residual=x)
+            self._gemm(Fp, hs3, self.Wb(a.proj_out.weight), y, bias=self.P(a.proj_out.bias), residual=x, gn_hw=hw)
 
             def backward():
                 pool = self.pool
@@ -562,7 +583,7 @@ class TrainEngine:
             col = self._new(N * (h // 2) * (w // 2), 9 * Cc)
             Fp.append(lambda: ops.im2col_s2(x, col, N, h, w))
             y = self._new(N * (h // 2) * (w // 2), Cc, F32)
-            self._gemm(Fp, col, self.Wb(ds.conv.weight), y, bias=self.P(ds.conv.bias))
+            self._gemm(Fp, col, self.Wb(ds.conv.weight), y, bias=self.P(ds.conv.bias), gn_hw=(h // 2) * (w // 2))
 
             def backward():
                 dy = self._grad_ready(y)
@@ -582,7 +603,7 @@ class TrainEngine:
             up = self._new(N * 4 * h * w, Cc)
             Fp.append(lambda: ops.upsample2x(x, up, N, h, w))
             y = self._new(N * 4 * h * w, Cc, F32)
-            self._gemm(Fp, up, self.Wb(us.conv.weight), y, bias=self.P(us.conv.bias), conv=(N, 2 * h, 2 * w))
+            self._gemm(Fp, up, self.Wb(us.conv.weight), y, bias=self.P(us.conv.bias), conv=(N, 2 * h, 2 * w), gn_hw=4 * h * w)
 
             def backward():
                 dy = self._grad_ready(y)
@@ -652,8 +673,7 @@ class TrainEngine:
         x_last = x
         t_out = self._new(N * h * w, boc[0])
         st_out = torch.empty(N, 32, 2, **f32)
-        Fp.append(lambda: ops.groupnorm_silu(x_last, None, self.P(m.conv_norm_out.weight), self.P(m.conv_norm_out.bias), t_out, N, h * w, 32, eps, True,
-                                             stats_out=st_out))
+        self._groupnorm(x_last, None, self.P(m.conv_norm_out.weight), self.P(m.conv_norm_out.bias), t_out, h * w, eps, True, stats_out=st_out)
         Fp.append(lambda: ops.conv_out(t_out, co_w.wf, self.P(m.conv_out.bias), self.out))
 
         # ---- backward graph: head, then the blocks in reverse, then the time MLP ----
