@@ -49,13 +49,22 @@ class BucketReducer:
         if self.world > 1:
             self.works.append(dist.all_reduce(self.flat[a:b], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
 
-    def finish(self):
+    def finish(self, wait=True):
+        """Launch the allreduce of whatever is still pending; wait=False leaves the waiting to the caller (Trainer interleaves it
+        with the optimizer: `pending()` yields (range, work) in launch order)."""
         if self.hi > 0:
             self._launch(0, self.hi)
             self.hi = 0
-        for w in self.works:
-            w.wait()
+        if wait:
+            for w in self.works:
+                w.wait()
+            self.works = []
+
+    def pending(self):
+        """(a, b, work) of every launched range, in launch order (= completion order on the NCCL stream); clears the list"""
+        out = [(a, b, w) for (a, b), w in zip(self.ranges, self.works)] if self.works else [(a, b, None) for a, b in self.ranges]
         self.works = []
+        return out
 
 
 class FlatAdamW:
@@ -87,16 +96,34 @@ class FlatAdamW:
         if self.spans:
             self.spans[-1][1] = min(self.spans[-1][1], flat.master.numel())
 
+    def _update(self, a, b, grad_scale, zero_grad):
+        f = self.flat
+        ops.adamw_step(f.master[a:b], f.grad[a:b], self.exp_avg[a:b], self.exp_avg_sq[a:b], f.wb[a:b], self.lr, self.betas[0],
+                       self.betas[1], self.eps, self.weight_decay, self.steps, grad_scale=grad_scale, zero_grad=zero_grad)
+
+    def begin_step(self):
+        """open an optimizer step that is applied range by range (step_range), e.g. as gradient buckets finish their allreduce"""
+        self.steps += 1
+
+    def step_range(self, lo, hi, grad_scale=1.0, zero_grad=True):
+        """the part of the current step (begin_step) that falls into flat[lo:hi): trainable spans clipped to the range"""
+        for a, b in self.spans:
+            a2, b2 = max(a, lo), min(b, hi)
+            if a2 < b2:
+                self._update(a2, b2, grad_scale, zero_grad)
+
+    def end_step(self):
+        self.flat.model.mark_weights_changed()
+        return self
+
     def step(self, grad_scale=1.0, zero_grad=True):
         self.steps += 1
-        f = self.flat
         for a, b in self.spans:
-            ops.adamw_step(f.master[a:b], f.grad[a:b], self.exp_avg[a:b], self.exp_avg_sq[a:b], f.wb[a:b], self.lr, self.betas[0],
-                           self.betas[1], self.eps, self.weight_decay, self.steps, grad_scale=grad_scale, zero_grad=zero_grad)
+            self._update(a, b, grad_scale, zero_grad)
         # the kernel wrote the bf16 copy itself: the version bookkeeping of refresh_weights() stays valid.  The raw kernel
         # bumps no tensor version, so tell the facade: its inference engines hold their own packed copy of the weights and
         # must repack before the next eval-mode forward (finetune_sd.py:264-271 samples between training steps).
-        f.model.mark_weights_changed()
+        self.flat.model.mark_weights_changed()
         return self
 
 
@@ -112,6 +139,7 @@ class Trainer:
         self.opt = None
         self.micro_steps = 0
         self.allreduce_enabled = True    # False: every rank steps on its local gradient (bench.py times the exposed communication)
+        self.pipelined_optimizer = __import__("os").environ.get("B200SD_PIPELINED_ADAMW", "1") != "0"
 
     def _prepare(self, device):
         from .autograd import ensure_flat
@@ -140,9 +168,22 @@ class Trainer:
         unet._grad_ready_hook = None
         self.micro_steps += 1
         if sync:
-            if reduce_now:
-                self.reducer.finish()
-            self.opt.step(grad_scale=1.0 / (self.world * self.micro_steps), zero_grad=True)
+            scale = 1.0 / (self.world * self.micro_steps)
+            if reduce_now and self.pipelined_optimizer:
+                # AdamW bucket by bucket, in the order the buckets were put on the wire: the update of the early buckets (the
+                # tail of the flat buffer, reduced while the backward was still running) overlaps the allreduce of the last
+                # ones, which used to be fully exposed; work.wait() makes the compute STREAM wait, not the host
+                self.reducer.finish(wait=False)
+                self.opt.begin_step()
+                for a, b, work in self.reducer.pending():
+                    if work is not None:
+                        work.wait()
+                    self.opt.step_range(a, b, grad_scale=scale, zero_grad=True)
+                self.opt.end_step()
+            else:
+                if reduce_now:
+                    self.reducer.finish()
+                self.opt.step(grad_scale=scale, zero_grad=True)
             self.micro_steps = 0
         return loss.detach()
 

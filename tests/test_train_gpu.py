@@ -178,6 +178,41 @@ def test_flat_adamw_matches_torch_adamw():
     assert torch.equal(flat.wb, flat.master.bfloat16())
 
 
+def test_flat_adamw_range_by_range_equals_one_pass():
+    """The data-parallel trainer applies AdamW bucket by bucket as the gradient allreduces complete (begin_step / step_range /
+    end_step): any cover of the flat buffer by ranges -- cut at arbitrary 64-element boundaries, also inside a parameter and
+    across frozen ones -- must give bit-identical state to the one-pass step()."""
+    from b200sd.train import FlatParams
+    from b200sd.trainer import FlatAdamW
+    from b200sd.unet import UNet2DConditionModel
+    from oracle.unet_ref import TINY_OVERRIDES
+    _setup()
+    res = []
+    for mode in ("one_pass", "ranges"):
+        torch.manual_seed(0)
+        m = UNet2DConditionModel(**TINY_OVERRIDES).to(DEV)
+        m.mid_block.resnets[0].conv1.weight.requires_grad_(False)      # a frozen region in the middle
+        flat = FlatParams(m, torch.device(DEV))
+        flat.attach_grads()
+        opt = FlatAdamW(flat, lr=1e-3, weight_decay=0.1)
+        g = torch.Generator(device=DEV).manual_seed(3)
+        for step in range(2):
+            flat.grad.copy_(torch.randn(flat.grad.shape, generator=g, device=DEV))
+            if mode == "one_pass":
+                opt.step(grad_scale=0.25, zero_grad=True)
+            else:
+                n = flat.grad.numel()
+                cuts = sorted({0, n} | {int(c) // 64 * 64 for c in torch.linspace(0, n, 9)[1:-1].tolist()} | {64 * 1001, 64 * 1002})
+                opt.begin_step()
+                for a, b in reversed(list(zip(cuts[:-1], cuts[1:]))):      # back to front, as the backward completes them
+                    opt.step_range(a, b, grad_scale=0.25, zero_grad=True)
+                opt.end_step()
+        res.append((flat.master.clone(), flat.wb.clone(), opt.exp_avg.clone(), opt.exp_avg_sq.clone(), flat.grad.clone(), opt.steps))
+    for a, b in zip(res[0][:5], res[1][:5]):
+        assert torch.equal(a, b)
+    assert res[0][5] == res[1][5] == 2
+
+
 def test_trainer_steps_reduce_the_loss():
     """finetune_sd.py:453-494 loop body through b200sd.trainer.Trainer on one GPU: a fixed batch is (over)fitted."""
     from b200sd.schedulers import DDPMScheduler

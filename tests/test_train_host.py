@@ -155,7 +155,18 @@ def _worker(rank, world, port, q):
             red.on_ready(off)
         red.finish()
         want = torch.arange(1000, dtype=torch.float32) * sum(range(1, world + 1))
-        q.put((rank, bool(torch.equal(flat, want)), red.ranges))
+        ok = bool(torch.equal(flat, want))
+        # finish(wait=False) + pending(): what Trainer uses to interleave the optimizer with the collectives
+        flat2 = torch.arange(1000, dtype=torch.float32) * (rank + 1)
+        red2 = BucketReducer(flat2, bucket_bytes=1200)
+        red2.on_ready(600)
+        red2.finish(wait=False)
+        pend = red2.pending()
+        for a, b, work in pend:
+            work.wait()
+            ok = ok and bool(torch.equal(flat2[a:b], want[a:b]))
+        ok = ok and [(a, b) for a, b, _ in pend] == [(600, 1000), (0, 600)] and red2.works == []
+        q.put((rank, ok, red.ranges))
     finally:
         dist.destroy_process_group()
 
