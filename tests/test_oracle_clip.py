@@ -115,3 +115,20 @@ def test_product_module_has_the_transformers_state_dict_and_config_surface(tmp_p
         assert float((hf(ids)[0] - o(ids)[0]).abs().max()) <= 1e-4
     with pytest.raises(Exception):
         m(ids)           # CPU tensors: no fallback
+
+
+def test_loads_a_directory_written_by_transformers_itself(tmp_path):
+    """`CLIPTextModel.from_pretrained(path, subfolder="text_encoder")` (finetune_sd.py:322-324) on a checkpoint saved by the
+    library class: config.json keys and model.safetensors tensor names are read as they are."""
+    transformers = pytest.importorskip("transformers")
+    from b200sd.clip import CLIPTextModel
+    cfg = transformers.CLIPTextConfig(hidden_act="quick_gelu", max_position_embeddings=77, eos_token_id=999, bos_token_id=0,
+                                      pad_token_id=1, **TINY_CLIP_OVERRIDES)
+    torch.manual_seed(4)
+    hf = transformers.CLIPTextModel(cfg).eval()
+    hf.save_pretrained(str(tmp_path / "text_encoder"))
+    ours = CLIPTextModel.from_pretrained(str(tmp_path), subfolder="text_encoder")
+    assert ours.config.hidden_size == 128 and ours.config.num_hidden_layers == 2 and ours.config.vocab_size == 1000
+    sd_hf = {k: v for k, v in hf.state_dict().items() if not k.endswith("position_ids")}
+    assert set(sd_hf) == set(ours.state_dict())
+    assert all(torch.equal(v, ours.state_dict()[k]) for k, v in sd_hf.items())

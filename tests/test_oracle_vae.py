@@ -81,3 +81,33 @@ def test_product_module_has_the_diffusers_state_dict_surface(tmp_path):
     assert all(torch.equal(v, m2.state_dict()[k]) for k, v in m.state_dict().items())
     with pytest.raises(Exception):
         m.decode(torch.randn(1, 4, 8, 8))            # CPU tensors: no fallback
+
+
+def test_quant_conv_is_folded_into_the_encoder_conv_out_exactly():
+    """vae.py packs `quant_conv(conv_out(x))` as ONE conv (W' = Wq . Wc per tap, b' = Wq bc + bq) with hi/lo-split bf16 weights
+    padded to a 32-wide tensor-core tile: the packed weights, put back together, must reproduce the two-layer result."""
+    from b200sd.vae import AutoencoderKL
+    o = make_oracle_vae(3, **TINY_VAE_OVERRIDES)
+    m = AutoencoderKL(**TINY_VAE_OVERRIDES)
+    m.load_state_dict(o.state_dict(), strict=True)
+    m._pack_weights()                                    # pure tensor reshuffles: runs on CPU
+    pk = m._packed["enc.conv_out"]
+    cin = o.encoder.conv_out.weight.shape[1]
+    w = pk["w_tc"].float().view(32, 9, 2 * cin)
+    assert float(w[8:].abs().max()) == 0.0               # rows beyond the 8 moment channels are padding
+    w_fold = (w[:8, :, :cin] + w[:8, :, cin:]).view(8, 3, 3, cin).permute(0, 3, 1, 2)      # hi + lo, back to OIHW
+    x = torch.randn(2, cin, 6, 5)
+    with torch.no_grad():
+        want = o.quant_conv(o.encoder.conv_out(x))
+        got = F.conv2d(x, w_fold, pk["b"], padding=1)
+    assert float((got - want).abs().max()) <= 2e-5 * float(want.abs().max())
+    # decoder conv_out: same hi/lo packing of the 3 image channels; post_quant_conv kept as a [4][4] matrix
+    wd = m._packed["dec.conv_out"]["w_tc"].float()
+    c0 = o.decoder.conv_out.weight.shape[1]
+    wd = wd.view(32, 9, 2 * c0)
+    back = (wd[:3, :, :c0] + wd[:3, :, c0:]).view(3, 3, 3, c0).permute(0, 3, 1, 2)
+    assert float((back - o.decoder.conv_out.weight.detach()).abs().max()) <= 1e-5 * float(o.decoder.conv_out.weight.abs().max())
+    assert torch.equal(m._packed["post_quant"]["w"], o.post_quant_conv.weight.detach().view(4, 4))
+    # the 3-channel encoder conv_in is packed with a zero fourth input channel
+    wi = m._packed["enc.conv_in"]["w"].view(-1, 9, 4)
+    assert float(wi[:, :, 3].abs().max()) == 0.0
