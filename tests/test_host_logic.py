@@ -272,3 +272,25 @@ def test_plms_plan_table_reproduces_the_oracle_pndm_scheduler():
                 assert int(slot) not in [v for v in h if v >= 0]      # this call's eps never overwrites a slot it reads
                 ring[int(slot)] = eps
             assert float((x - want).abs().max()) <= 2e-6 * max(1.0, float(want.abs().max())), (steps, offset, k)   # the oracle keeps its alpha table in fp32
+
+
+def test_bench_reference_arm_prints_exactly_one_json_line_on_stdout():
+    """The driver contract: stdout carries ONE JSON line.  The reference arm (the fp32 oracle on the host cores) runs here without
+    a GPU; anything else the process writes to file descriptor 1 (C-level writers such as NCCL's banner at N > 1) is moved onto
+    stderr by bench._claim_stdout()."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import os, sys; sys.argv = ['bench.py', '--impl', 'reference', '--steps', '1', '--warmup', '0']; "
+            "import bench; bench._claim_stdout(); os.write(1, b'NCCL version 0.0 (noise written to fd 1 by a C library)\\n'); bench.main()")
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, r.stdout[:500]
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "unet_denoise_it_per_s" and d["unit"] == "it/s" and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0 and d["gpu_launches"] == 0
+    assert d["config"]["workload"] == "sd15_unet_ddim50_cfg7.5_512px" and d["config"]["unet_batch"] == 2
+    assert "NCCL version 0.0" in r.stderr
