@@ -1,8 +1,12 @@
 """ORACLE (test infrastructure, not product code) -- diffusers 0.7.2 scheduler / pipeline-loop math
 restated in plain PyTorch + Python floats.
 
-PARITY UNPINNED (see oracle/unet_ref.py header): `diffusers==0.7.2` (env.yaml:112) is un-vendored
-and the reference holds no scheduler tests.  Anchors are the reference call sites:
+PARITY PINNED against the known answers diffusers 0.7.2 holds in its own test suite
+(tests/test_scheduler.py: the DDIM and PNDM `test_full_loop_*` sums / means, transcribed into
+tests/golden/diffusers_0_7_2_kat.json; checked by tests/test_oracle_diffusers_kat.py).  `diffusers==0.7.2`
+(env.yaml:112) itself is un-vendored and not installable here and the reference holds no scheduler tests;
+`add_noise` has no diffusers known answer and stays pinned by its closed form only.  Anchors are the
+reference call sites:
 
   * DDIMScheduler(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear",
     clip_sample=False, set_alpha_to_one=False)                     -- inference.py:386-387
@@ -148,6 +152,38 @@ class PNDMSchedulerRef(_Base):
         sample_coeff = (a_p / a_t) ** 0.5
         denom = a_t * b_p ** 0.5 + (a_t * b_t * a_p) ** 0.5
         return sample_coeff * sample - (a_p - a_t) * e / denom
+
+
+def pndm_prk_warmup(sch: "PNDMSchedulerRef", model, sample):
+    """diffusers 0.7.2 scheduling_pndm.py `set_timesteps` (skip_prk_steps=False branch) + `step_prk`: the 12
+    Runge-Kutta calls that precede PLMS when PRK is not skipped.  NOT on the reference path (utils.py:222-224 sets
+    skip_prk_steps=True); restated only because diffusers' own known-answer test of `step_plms` /
+    `_get_prev_sample` (tests/test_scheduler.py PNDMSchedulerTest.full_loop) enters PLMS through it.
+    Leaves `sch` as diffusers would (3 saved eps, counter 12) and returns (sample, plms_timesteps)."""
+    n = sch.num_inference_steps
+    ratio = sch.num_train_timesteps // n
+    _t = (np.arange(0, n) * ratio).round() + sch.config.steps_offset
+    prk = np.array(_t[-sch.pndm_order:]).repeat(2) + np.tile(np.array([0, ratio // 2]), sch.pndm_order)
+    prk = (prk[:-1].repeat(2)[1:-1])[::-1].copy().astype(np.int64)
+    plms = _t[:-3][::-1].copy().astype(np.int64)
+    cur_out, cur_sample, ets = 0, None, []
+    for c, t in enumerate(prk):
+        t = int(t)
+        out = model(sample, t)
+        prev_t = t - (0 if c % 2 else ratio // 2)
+        t0 = int(prk[c // 4 * 4])
+        if c % 4 == 0:
+            cur_out = cur_out + out / 6
+            ets.append(out)
+            cur_sample = sample
+        elif c % 4 in (1, 2):
+            cur_out = cur_out + out / 3
+        else:
+            out = cur_out + out / 6
+            cur_out = 0
+        sample = sch._get_prev_sample(cur_sample, t0, prev_t, out)
+    sch.ets, sch.counter = ets, len(prk)
+    return sample, plms
 
 
 def cfg_combine(eps2, guidance_scale: float):

@@ -135,3 +135,39 @@ def test_bad_inputs_raise():
     xd = x.to(_dev())
     with pytest.raises(ValueError):
         ops.cfg_ddim_step(xd, None, torch.randn(5, 4, device=_dev()), 7.5, 1.0, 0.0, 1.0, 0.0)
+
+
+# ---- the CUDA scheduler kernels against diffusers 0.7.2's OWN known answers (tests/golden/diffusers_0_7_2_kat.json;
+# ---- recipes in tests/test_oracle_diffusers_kat.py): not oracle-vs-kernel but published-vector-vs-kernel
+
+
+@pytest.mark.parametrize("variant", ["no_noise", "set_alpha_to_one", "no_set_alpha_to_one"])
+def test_ddim_kernel_reproduces_diffusers_full_loop_known_answer(variant):
+    from b200sd.schedulers import DDIMScheduler
+    from test_oracle_diffusers_kat import SCHED_CFG, VARIANTS, _check_sched, dummy_model, dummy_sample_deter
+    # clip_sample=False (the reference's setting, inference.py:386-387): the clamp of diffusers' test config never binds here
+    sch = DDIMScheduler(**{**SCHED_CFG, "clip_sample": False, **VARIANTS[variant]})
+    sch.set_timesteps(10)
+    sample = dummy_sample_deter().contiguous().to(_dev())
+    for t in sch.timesteps:
+        sample = sch.step(dummy_model(sample, t).contiguous(), t, sample).prev_sample
+    _check_sched("ddim", variant, sample.cpu())
+
+
+@pytest.mark.parametrize("variant", ["no_noise", "set_alpha_to_one", "no_set_alpha_to_one"])
+def test_plms_kernel_reproduces_diffusers_full_loop_known_answer(variant):
+    """diffusers' test enters PLMS through 12 Runge-Kutta calls, which the reference skips (utils.py:222-224) and the product
+    refuses; they run on the oracle, the 7 `step_plms` calls (4th-order branch, `_get_prev_sample`) run on the CUDA kernel."""
+    from b200sd.schedulers import PNDMScheduler
+    from test_oracle_diffusers_kat import SCHED_CFG, VARIANTS, _check_sched, dummy_model, dummy_sample_deter
+    cfg = {**SCHED_CFG, "skip_prk_steps": True, **VARIANTS[variant]}
+    warm = R.PNDMSchedulerRef(**cfg)
+    warm.set_timesteps(10)
+    sample, plms_timesteps = R.pndm_prk_warmup(warm, dummy_model, dummy_sample_deter())
+    sch = PNDMScheduler(**cfg)
+    sch.set_timesteps(10)
+    sch.ets, sch.counter = [e.contiguous().to(_dev()) for e in warm.ets], warm.counter
+    sample = sample.contiguous().to(_dev())
+    for t in plms_timesteps:
+        sample = sch.step(dummy_model(sample, int(t)).contiguous(), int(t), sample).prev_sample
+    _check_sched("pndm", variant, sample.cpu())

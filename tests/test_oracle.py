@@ -1,6 +1,6 @@
 """CPU tests of the oracle (the checker): structural invariants of the public SD v1.x checkpoint, the
 closed-form known answers of SURVEY.md App. B.5, committed golden vectors, and cross-implementation
-checks.  (Parity against diffusers itself is unpinned: see oracle/unet_ref.py.)"""
+checks.  (The pins against diffusers 0.7.2's own known-answer vectors are in tests/test_oracle_diffusers_kat.py.)"""
 import json
 import os
 

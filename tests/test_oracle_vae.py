@@ -1,4 +1,4 @@
-"""CPU self-checks of the AutoencoderKL oracle (oracle/vae_ref.py; parity unpinned -- diffusers is not installable here): the
+"""CPU self-checks of the AutoencoderKL oracle (oracle/vae_ref.py; its layers are pinned to diffusers' own known answers in tests/test_oracle_diffusers_kat.py, its wiring is checked here): the
 public SD v1.x VAE's parameter / tensor counts and key names, explicit-softmax attention vs torch SDPA, the asymmetric
 downsample padding vs an explicit unfold, posterior arithmetic, and the product module's state-dict surface."""
 import pytest

@@ -1,5 +1,5 @@
 """GPU parity of AutoencoderKL (finetune_sd.py:325-327, 460-462; the decode inside pipeline(...),
-inference.py:175-176) against the fp32 oracle (oracle/vae_ref.py, a restatement of diffusers 0.7.2 -- parity unpinned) on
+inference.py:175-176) against the fp32 oracle (oracle/vae_ref.py, a restatement of diffusers 0.7.2 -- layers pinned, wiring unpinned: DESIGN.md section 3) on
 identical random-init weights and inputs: the VAE-only kernels one by one, wide-row conv tiles, encode / decode of the
 reduced-width network at several geometries, and the real SD v1.x VAE at 512 x 512.
 
