@@ -13,8 +13,11 @@ nor installable here, and the reference repository itself holds no tests, golden
     with provenance into tests/golden/diffusers_0_7_2_kat.json and checked to diffusers' own 1e-3 by
     tests/test_oracle_diffusers_kat.py -- the recipes seed the CPU generator and use default-initialised
     modules, so they also pin the construction (= state-dict) order of every submodule;
-  * NOT pinned above the block level (diffusers has no checkpoint-free known answer for a whole
-    UNet2DConditionModel): skip-connection order and the channel plan are anchored on the public checkpoint's
+  * pinned one level up where diffusers publishes a seeded vector (tests/test_unet_blocks.py of a later release):
+    DownBlock2D and UpBlock2D, i.e. what goes on the skip stack and the cat([hidden, skip]) order;
+  * NOT pinned above that (diffusers has no checkpoint-free known answer for a whole UNet2DConditionModel,
+    and its cross-attention block tests draw the context from an unseeded generator): which block feeds which
+    and the channel plan are anchored on the public checkpoint's
     859 520 964 parameters, 686 tensor names and shapes (SURVEY.md App. A.4, tests/test_oracle.py);
   * anchored on the reference's call sites:
 

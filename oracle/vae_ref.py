@@ -5,7 +5,8 @@ PARITY: LAYERS PINNED, BLOCK WIRING UNPINNED.  The arithmetic lives in the un-ve
 nor installable here, and the reference holds no fixtures.  This module restates the published 0.7.2 algorithm.  Its layers are
 pinned against the known answers diffusers 0.7.2 holds in its own test suite (tests/golden/diffusers_0_7_2_kat.json, checked by
 tests/test_oracle_diffusers_kat.py): `AttentionBlock` at the SD shape (512 channels, one head) and the decoder upsampler directly,
-`ResnetBlock2D` through the UNet oracle's pinned block (same weights, time-embedding projection zeroed).  The encoder/decoder
+`ResnetBlock2D` through the UNet oracle's pinned block (same weights, time-embedding projection zeroed), the encoder / decoder
+blocks against DownEncoderBlock2D / UpDecoderBlock2D vectors (diffusers tests/test_unet_blocks.py).  The encoder/decoder stack
 wiring, the asymmetric stride-2 padding and the latent distribution have no checkpoint-free known answer in diffusers and stay
 anchored on the reference's call sites:
 

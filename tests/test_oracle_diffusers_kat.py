@@ -125,6 +125,64 @@ def test_vae_attention_block_sd_shape():
     _check("attention_block_sd", out)
 
 
+# ---------------------------------------------------------------- blocks (wiring one level up)
+
+
+def _check_block(name, out, shape):
+    assert out.shape == shape
+    want = torch.tensor(KAT["blocks"][name])
+    torch.testing.assert_close(_slice(out), want, rtol=0, atol=KAT["tolerances"]["block_slice_atol"])   # diffusers: 5e-3
+
+
+def test_unet_down_block():
+    """resnet -> stride-2 conv, both outputs pushed on the skip stack."""
+    torch.manual_seed(0)
+    hidden, temb = torch.randn(4, 32, 32, 32), torch.randn(4, 128)
+    block = U.DownBlock(32, 32, 128, 1, False, None, None, True)
+    with torch.no_grad():
+        out, skips = block(hidden, temb, None)
+    assert len(skips) == 2 and skips[1] is out
+    _check_block("DownBlock2D", out, (4, 32, 16, 16))
+
+
+def test_unet_up_block_skip_concatenation_order():
+    """cat([hidden, skip], dim=1) -> resnet (64 -> 32, 1x1 shortcut) -> nearest-2x + conv: the order of the concatenation is
+    what a mis-wired skip path would get wrong without changing any tensor shape."""
+    torch.manual_seed(0)
+    hidden, temb = torch.randn(4, 32, 32, 32), torch.randn(4, 128)
+    torch.manual_seed(1)
+    skip = torch.randn(4, 32, 32, 32)
+    block = U.UpBlock(32, 32, 32, 128, 1, False, None, None, True)
+    with torch.no_grad():
+        out = block(hidden, [skip], temb, None)
+    _check_block("UpBlock2D", out, (4, 32, 64, 64))
+
+
+def test_vae_decoder_up_block():
+    torch.manual_seed(0)
+    hidden = torch.randn(4, 32, 32, 32)
+    block = V._DecBlock(32, 32, 1, 32, True)
+    with torch.no_grad():
+        out = block(hidden)
+    _check_block("UpDecoderBlock2D", out, (4, 32, 64, 64))
+
+
+def test_vae_encoder_down_block():
+    """diffusers' block test uses the block's default downsample_padding=1; the VAE encoder passes 0 (pad right / bottom only),
+    which no diffusers vector covers -- so the oracle block's stride-2 conv is applied with padding 1 here and the asymmetric
+    padding itself stays checked against an explicit unfold (tests/test_oracle_vae.py)."""
+    torch.manual_seed(0)
+    hidden = torch.randn(4, 32, 32, 32)
+    block = V._EncBlock(32, 32, 1, 32, True)
+    conv = block.downsamplers[0].conv
+    with torch.no_grad():
+        x = hidden
+        for r in block.resnets:
+            x = r(x)
+        out = F.conv2d(x, conv.weight, conv.bias, stride=2, padding=1)
+    _check_block("DownEncoderBlock2D", out, (4, 32, 16, 16))
+
+
 @pytest.mark.parametrize("cin,cout", [(32, 32), (64, 128)])
 def test_vae_resnet_block_is_the_pinned_unet_block_without_time_embedding(cin, cout):
     """diffusers' VAE uses the same ResnetBlock2D class with temb_channels=None; the UNet oracle's block is pinned above."""
