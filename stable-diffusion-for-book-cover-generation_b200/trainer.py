@@ -67,21 +67,37 @@ class BucketReducer:
         return out
 
 
-class FlatAdamW:
-    """torch.optim.AdamW semantics over train.FlatParams (one fused kernel per step)."""
+class FlatAdamW(torch.optim.Optimizer):
+    """torch.optim.AdamW semantics over train.FlatParams (one fused kernel per step).
+
+    It IS a `torch.optim.Optimizer` (one param group over the flat fp32 master buffer), so the reference's
+    `torch.optim.lr_scheduler.CosineAnnealingLR(optimizer, T_max=..., eta_min=1e-6)` + `scheduler.step()` after every
+    `optimizer.step()` (finetune_sd.py:421-422, 577) drives it unchanged: the kernel reads `param_groups[0]["lr"]` at every step;
+    `state_dict()` / `load_state_dict()` carry the moments and the step count.  When the model's flat buffers are rebuilt
+    (`unet.to()` un-homes the parameters) the trainers `rebind()` this object instead of replacing it, so a scheduler that holds
+    a reference to it stays attached."""
 
     def __init__(self, flat, lr=1e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, state=None):
-        self.flat, self.lr, self.betas, self.eps, self.weight_decay = flat, lr, betas, eps, weight_decay
-        if state is not None and state.exp_avg.numel() == flat.master.numel():
-            # the flat buffers were rebuilt (unet.to() / _apply un-homes the parameters): same model, same layout ->
-            # the moments and the step count carry over instead of silently restarting from zero
-            self.exp_avg = state.exp_avg.to(flat.master.device)
-            self.exp_avg_sq = state.exp_avg_sq.to(flat.master.device)
-            self.steps = state.steps
+        if lr < 0 or eps < 0 or weight_decay < 0 or not (0 <= betas[0] < 1 and 0 <= betas[1] < 1):
+            raise ValueError(f"invalid AdamW hyper-parameters lr={lr} betas={betas} eps={eps} weight_decay={weight_decay}")
+        super().__init__([flat.master], dict(lr=lr, betas=tuple(betas), eps=eps, weight_decay=weight_decay))
+        self.flat = None
+        self.rebind(flat, state)
+
+    def rebind(self, flat, state=None):
+        """(re)attach to a FlatParams: same model and layout -> the moments and the step count carry over (from `state`, another
+        FlatAdamW, or from this object's own state) instead of silently restarting from zero"""
+        old = state.state.get(state.flat.master) if state is not None else (
+            self.state.pop(self.flat.master, None) if self.flat is not None else None)
+        self.flat = flat
+        self.param_groups[0]["params"] = [flat.master]
+        self.state.clear()
+        dev = flat.master.device
+        if old is not None and old["exp_avg"].numel() == flat.master.numel():
+            st = dict(step=int(old["step"]), exp_avg=old["exp_avg"].to(dev), exp_avg_sq=old["exp_avg_sq"].to(dev))
         else:
-            self.exp_avg = torch.zeros_like(flat.master)
-            self.exp_avg_sq = torch.zeros_like(flat.master)
-            self.steps = 0
+            st = dict(step=0, exp_avg=torch.zeros_like(flat.master), exp_avg_sq=torch.zeros_like(flat.master))
+        self.state[flat.master] = st
         # contiguous runs of TRAINABLE regions: frozen parameters (requires_grad=False) get neither an update nor
         # decoupled weight decay, as with torch.optim.AdamW over `filter(requires_grad, parameters)`
         self.spans = []
@@ -95,6 +111,33 @@ class FlatAdamW:
                 self.spans.append([a, b])
         if self.spans:
             self.spans[-1][1] = min(self.spans[-1][1], flat.master.numel())
+        return self
+
+    # the hyper-parameters live in param_groups[0] (what torch's lr schedulers write); attribute access for the callers
+    lr = property(lambda self: self.param_groups[0]["lr"], lambda self, v: self.param_groups[0].__setitem__("lr", v))
+    betas = property(lambda self: self.param_groups[0]["betas"], lambda self, v: self.param_groups[0].__setitem__("betas", tuple(v)))
+    eps = property(lambda self: self.param_groups[0]["eps"], lambda self, v: self.param_groups[0].__setitem__("eps", v))
+    weight_decay = property(lambda self: self.param_groups[0]["weight_decay"],
+                            lambda self, v: self.param_groups[0].__setitem__("weight_decay", v))
+    exp_avg = property(lambda self: self.state[self.flat.master]["exp_avg"])
+    exp_avg_sq = property(lambda self: self.state[self.flat.master]["exp_avg_sq"])
+    steps = property(lambda self: self.state[self.flat.master]["step"],
+                     lambda self, v: self.state[self.flat.master].__setitem__("step", int(v)))
+
+    def load_state_dict(self, state_dict):
+        super().load_state_dict(state_dict)
+        st = self.state[self.flat.master]
+        st["step"] = int(st["step"])
+        for k in ("exp_avg", "exp_avg_sq"):
+            if st[k].shape != self.flat.master.shape:
+                raise ValueError(f"optimizer state {k} has {st[k].numel()} elements, the flat parameter buffer {self.flat.master.numel()}")
+            st[k] = st[k].to(device=self.flat.master.device, dtype=torch.float32).contiguous()
+
+    def zero_grad(self, set_to_none: bool = True):
+        """`optimizer.zero_grad()` of the reference loop (finetune_sd.py:570).  step() already zeroes the flat gradient buffer in the
+        same pass that consumes it; this is for callers that discard gradients without stepping."""
+        if self.flat.grad is not None:
+            self.flat.zero_grad()
 
     def _update(self, a, b, grad_scale, zero_grad):
         f = self.flat
@@ -114,9 +157,12 @@ class FlatAdamW:
 
     def end_step(self):
         self.flat.model.mark_weights_changed()
+        self._opt_called = True      # what torch's lr schedulers look at to tell "optimizer stepped before scheduler.step()"
         return self
 
-    def step(self, grad_scale=1.0, zero_grad=True):
+    def step(self, closure=None, grad_scale=1.0, zero_grad=True):
+        if closure is not None:
+            raise NotImplementedError("FlatAdamW.step takes no closure (the reference never passes one)")
         self.steps += 1
         for a, b in self.spans:
             self._update(a, b, grad_scale, zero_grad)
@@ -146,10 +192,17 @@ class Trainer:
         flat = ensure_flat(self.unet, device)
         if self.reducer is None or self.reducer.flat is not flat.grad:
             self.reducer = BucketReducer(flat.grad, self.group, self.bucket_bytes)
-            self.opt = FlatAdamW(flat, state=self.opt, **self.opt_args)
+            self.opt = FlatAdamW(flat, **self.opt_args) if self.opt is None else self.opt.rebind(flat)
             flat.zero_grad()
             flat.attach_grads()
             self.micro_steps = 0
+
+    def optimizer(self, device=None):
+        """the FlatAdamW of this trainer (a torch.optim.Optimizer), e.g. to hang the reference's lr scheduler on it:
+        `sched = torch.optim.lr_scheduler.CosineAnnealingLR(trainer.optimizer(), T_max=n, eta_min=1e-6)`; call `sched.step()` after
+        every `train_step(sync=True)` (finetune_sd.py:421-422, 577)."""
+        self._prepare(device if device is not None else self.unet.device)
+        return self.opt
 
     def train_step(self, latents, noise, timesteps, encoder_hidden_states, sync=True):
         """one micro-step; with sync=True (the default) also allreduce + optimizer step.  Returns the loss (0-d tensor).
@@ -230,12 +283,17 @@ class TextEncoderTrainer:
     def _prepare(self, device):
         flat = self.te._ensure_flat(device)
         if self._flat_id is not flat.grad:
-            self.opt = FlatAdamW(flat, state=self.opt, **self.opt_args)
+            self.opt = FlatAdamW(flat, **self.opt_args) if self.opt is None else self.opt.rebind(flat)
             flat.zero_grad()
             flat.attach_grads()
             self._flat_id = flat.grad
             self.micro_steps = 0
         return flat
+
+    def optimizer(self, device=None):
+        """the FlatAdamW of this trainer (see Trainer.optimizer)"""
+        self._prepare(device if device is not None else self.te.device)
+        return self.opt
 
     def train_step(self, latents, noise, timesteps, input_ids, sync=True):
         flat = self._prepare(latents.device)

@@ -178,6 +178,46 @@ def test_flat_adamw_matches_torch_adamw():
     assert torch.equal(flat.wb, flat.master.bfloat16())
 
 
+def test_flat_adamw_under_the_reference_cosine_lr_schedule():
+    """finetune_sd.py:421-422, 577: torch's CosineAnnealingLR(optimizer, T_max, eta_min=1e-6) hangs on FlatAdamW (a
+    torch.optim.Optimizer) and the fused kernel follows torch.optim.AdamW under the same schedule; optimizer.zero_grad() and the
+    state_dict round trip of the reference's surface work on it."""
+    from b200sd.train import FlatParams
+    from b200sd.trainer import FlatAdamW
+    from b200sd.unet import UNet2DConditionModel
+    from oracle.unet_ref import TINY_OVERRIDES
+    _setup()
+    torch.manual_seed(0)
+    ours = UNet2DConditionModel(**TINY_OVERRIDES).to(DEV)
+    ref_params = [p.detach().clone().requires_grad_(True) for p in ours.parameters()]
+    flat = FlatParams(ours, torch.device(DEV))
+    flat.attach_grads()
+    opt = FlatAdamW(flat, lr=1e-3, weight_decay=1e-2)
+    ref = torch.optim.AdamW(ref_params, lr=1e-3, weight_decay=1e-2)
+    sched = torch.optim.lr_scheduler.CosineAnnealingLR(opt, T_max=5, eta_min=1e-6)
+    rsched = torch.optim.lr_scheduler.CosineAnnealingLR(ref, T_max=5, eta_min=1e-6)
+    for step in range(4):
+        for p, q in zip(ours.parameters(), ref_params):
+            g = torch.randn_like(q)
+            q.grad = g
+            p.grad.copy_(g)
+        opt.step()
+        opt.zero_grad()
+        ref.step()
+        sched.step()
+        rsched.step()
+        assert opt.lr == ref.param_groups[0]["lr"]
+    assert opt.steps == 4 and opt.lr < 2e-4
+    for (n, p), q in zip(ours.named_parameters(), ref_params):
+        err = float((p.detach() - q.detach()).abs().max())
+        assert err <= 2e-6 * (1 + float(q.abs().max())), (n, err)
+    sd = opt.state_dict()
+    opt2 = FlatAdamW(flat, lr=1.0)
+    opt2.load_state_dict(sd)
+    assert opt2.lr == opt.lr and opt2.steps == 4 and torch.equal(opt2.exp_avg_sq, opt.exp_avg_sq)
+    assert opt2.exp_avg.device == flat.master.device
+
+
 def test_flat_adamw_range_by_range_equals_one_pass():
     """The data-parallel trainer applies AdamW bucket by bucket as the gradient allreduces complete (begin_step / step_range /
     end_step): any cover of the flat buffer by ranges -- cut at arbitrary 64-element boundaries, also inside a parameter and
@@ -244,6 +284,37 @@ def test_trainer_steps_reduce_the_loss():
     b = unet(x, t, ctx).sample.detach()
     rel = float((a - b).abs().max() / b.abs().max())
     assert rel <= 2e-2, rel
+
+
+def test_trainer_optimizer_takes_the_reference_lr_scheduler_and_survives_a_rebuild_of_the_flat_buffers():
+    """finetune_sd.py:421-422, 569-577: `scheduler.step()` after every optimizer step.  Trainer.optimizer() is the FlatAdamW (a
+    torch.optim.Optimizer); unet.to() un-homes the parameters, the trainer rebuilds the flat buffers and re-binds the SAME optimizer
+    object: moments, step count and the attached scheduler carry over."""
+    from b200sd.schedulers import DDPMScheduler
+    from b200sd.trainer import Trainer
+    from b200sd.unet import UNet2DConditionModel
+    from oracle.unet_ref import TINY_OVERRIDES
+    _setup()
+    torch.manual_seed(0)
+    unet = UNet2DConditionModel(**TINY_OVERRIDES).to(DEV)
+    sched = DDPMScheduler(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear", num_train_timesteps=1000)
+    tr = Trainer(unet, sched, lr=2e-4, weight_decay=0.0)
+    opt = tr.optimizer()
+    assert isinstance(opt, torch.optim.Optimizer)
+    lr_sched = torch.optim.lr_scheduler.CosineAnnealingLR(opt, T_max=8, eta_min=1e-6)
+    x, noise, ctx, t = _inputs(2, 32, 32, 64, 5)
+    losses, lrs = [], []
+    for it in range(6):
+        if it == 3:
+            unet.to(DEV)                       # _apply: the parameters leave the flat master buffer
+        losses.append(float(tr.train_step(x, noise, t, ctx)))
+        lr_sched.step()
+        lrs.append(opt.lr)
+        assert tr.opt is opt and opt.steps == it + 1
+    assert lrs == sorted(lrs, reverse=True) and lrs[-1] == lr_sched.get_last_lr()[0] < 1e-4
+    assert float(opt.exp_avg.abs().max()) > 0 and losses[-1] < losses[0], losses
+    sd = opt.state_dict()
+    assert sd["state"][0]["step"] == 6 and sd["state"][0]["exp_avg"].numel() == opt.flat.master.numel()
 
 
 def test_autograd_mode_accumulates_and_survives_save_load(tmp_path):

@@ -185,3 +185,81 @@ def test_bucket_reducer_two_ranks_gloo():
     for rank, ok, ranges in res:
         assert ok, f"rank {rank}: allreduce result wrong"
         assert ranges == [(700, 1000), (200, 700), (0, 200)]
+
+
+def _torch_adamw_stand_in(monkeypatch):
+    """ops.adamw_step is a CUDA kernel; on the CPU the same update (torch.optim.AdamW's formulas, decoupled decay, grads zeroed)
+    stands in so that the optimizer-surface plumbing of FlatAdamW can be exercised without a GPU."""
+    from b200sd import ops
+
+    def adamw_step(param, grad, exp_avg, exp_avg_sq, weights_bf16, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0,
+                   zero_grad=True):
+        g = grad * grad_scale
+        param.mul_(1 - lr * weight_decay)
+        exp_avg.mul_(beta1).add_(g, alpha=1 - beta1)
+        exp_avg_sq.mul_(beta2).addcmul_(g, g, value=1 - beta2)
+        denom = (exp_avg_sq / (1 - beta2 ** step)).sqrt_().add_(eps)
+        param.addcdiv_(exp_avg, denom, value=-lr / (1 - beta1 ** step))
+        if weights_bf16 is not None:
+            weights_bf16.copy_(param)
+        if zero_grad:
+            grad.zero_()
+    monkeypatch.setattr(ops, "adamw_step", adamw_step)
+
+
+def test_flat_adamw_is_a_torch_optimizer_driven_by_the_reference_lr_schedule(monkeypatch):
+    """finetune_sd.py:421-422, 577: CosineAnnealingLR(optimizer, T_max, eta_min=1e-6) + scheduler.step() after optimizer.step().
+    FlatAdamW takes the lr from param_groups[0] at every step, so torch's own scheduler drives it; the parameters follow
+    torch.optim.AdamW under the same schedule; state_dict round-trips; rebind() keeps moments, step count AND the scheduler."""
+    from b200sd.train import FlatParams
+    from b200sd.trainer import FlatAdamW
+    _torch_adamw_stand_in(monkeypatch)
+    m = _tiny()
+    m.mark_weights_changed = lambda: None
+    ref = [p.detach().clone().requires_grad_(True) for p in m.parameters()]
+    flat = FlatParams(m, torch.device("cpu"))
+    flat.attach_grads()
+    opt = FlatAdamW(flat, lr=1e-3, betas=(0.9, 0.99), weight_decay=0.1)
+    assert isinstance(opt, torch.optim.Optimizer) and opt.param_groups[0]["params"][0] is flat.master
+    ropt = torch.optim.AdamW(ref, lr=1e-3, betas=(0.9, 0.99), weight_decay=0.1)
+    sched = torch.optim.lr_scheduler.CosineAnnealingLR(opt, T_max=4, eta_min=1e-6)
+    rsched = torch.optim.lr_scheduler.CosineAnnealingLR(ropt, T_max=4, eta_min=1e-6)
+    gen = torch.Generator().manual_seed(0)
+    lrs = []
+    for it in range(3):
+        for p, q in zip(m.parameters(), ref):
+            g = torch.randn(p.shape, generator=gen)
+            p.grad.copy_(g)
+            q.grad = g.clone()
+        if it == 1:      # the trainers' bucket-by-bucket form of the same step
+            opt.begin_step()
+            half = flat.total // 2 // 64 * 64
+            opt.step_range(half, flat.total)
+            opt.step_range(0, half)
+            opt.end_step()
+        else:
+            opt.step()
+        ropt.step()
+        sched.step()
+        rsched.step()
+        lrs.append(opt.lr)
+        assert opt.lr == ropt.param_groups[0]["lr"] and opt.lr < 1e-3
+        assert float(flat.grad.abs().max()) == 0.0
+    assert lrs == sorted(lrs, reverse=True) and opt.steps == 3
+    for p, q in zip(m.parameters(), ref):
+        torch.testing.assert_close(p.detach(), q.detach(), rtol=1e-5, atol=1e-7)
+    # state_dict round trip into a fresh optimizer over the same buffers
+    sd = opt.state_dict()
+    assert sd["state"][0]["step"] == 3 and sd["param_groups"][0]["lr"] == opt.lr
+    opt2 = FlatAdamW(flat, lr=5.0)
+    opt2.load_state_dict(sd)
+    assert opt2.lr == opt.lr and opt2.steps == 3 and torch.equal(opt2.exp_avg, opt.exp_avg) and opt2.betas == (0.9, 0.99)
+    # the flat buffers are rebuilt (unet.to() un-homes the parameters): same object, same state, scheduler still attached
+    exp_avg = opt.exp_avg.clone()
+    flat_b = FlatParams(m, torch.device("cpu"))
+    assert opt.rebind(flat_b) is opt and opt.param_groups[0]["params"][0] is flat_b.master
+    assert opt.steps == 3 and torch.equal(opt.exp_avg, exp_avg) and len(opt.state) == 1
+    sched.step()
+    assert opt.lr == sched.get_last_lr()[0] < lrs[-1]
+    with pytest.raises(ValueError):
+        FlatAdamW(flat_b, lr=-1.0)
