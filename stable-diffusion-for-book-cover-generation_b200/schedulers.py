@@ -144,12 +144,12 @@ class DDIMScheduler(_SchedulerBase):
         a_t, a_p = self._ac[t], self._alpha_prev(prev_t)
         return a_t ** 0.5, (1 - a_t) ** 0.5, a_p ** 0.5, (1 - a_p) ** 0.5
 
-    def step(self, model_output, timestep, sample, eta: float = 0.0, **kw):
+    def step(self, model_output, timestep, sample, eta: float = 0.0, return_dict: bool = True, **kw):
         if eta != 0.0:
             raise NotImplementedError("eta != 0 is not on the reference path")
         self._check_step_args(model_output, sample)
         prev = ops.cfg_ddim_step(model_output.contiguous(), None, sample.contiguous(), 0.0, *self._coefs(timestep))
-        return SchedulerOutput(prev_sample=prev)
+        return SchedulerOutput(prev_sample=prev) if return_dict else (prev,)
 
     def step_cfg(self, model_output_2b, timestep, sample, guidance_scale, out=None):
         """Fused `eps_u + s (eps_c - eps_u)` + DDIM update; model_output_2b is the (2B, ...) UNet output."""
@@ -264,8 +264,9 @@ class PNDMScheduler(_SchedulerBase):
                         + [float(slot), from_saved, save_x])
         return rows
 
-    def step(self, model_output, timestep, sample, **kw):
-        return self._plms(model_output.contiguous(), None, timestep, sample, 0.0)
+    def step(self, model_output, timestep, sample, return_dict: bool = True, **kw):
+        out = self._plms(model_output.contiguous(), None, timestep, sample, 0.0)
+        return out if return_dict else (out.prev_sample,)
 
     def step_cfg(self, model_output_2b, timestep, sample, guidance_scale, out=None):
         B = sample.shape[0]

@@ -150,7 +150,8 @@ def test_ddim_kernel_reproduces_diffusers_full_loop_known_answer(variant):
     sch.set_timesteps(10)
     sample = dummy_sample_deter().contiguous().to(_dev())
     for t in sch.timesteps:
-        sample = sch.step(dummy_model(sample, t).contiguous(), t, sample).prev_sample
+        sample = sch.step(dummy_model(sample, t).contiguous(), t, sample, eta=0.0).prev_sample
+    assert isinstance(sch.step(sample, 0, sample, return_dict=False), tuple)
     _check_sched("ddim", variant, sample.cpu())
 
 
@@ -169,5 +170,5 @@ def test_plms_kernel_reproduces_diffusers_full_loop_known_answer(variant):
     sch.ets, sch.counter = [e.contiguous().to(_dev()) for e in warm.ets], warm.counter
     sample = sample.contiguous().to(_dev())
     for t in plms_timesteps:
-        sample = sch.step(dummy_model(sample, int(t)).contiguous(), int(t), sample).prev_sample
+        sample = sch.step(dummy_model(sample, int(t)).contiguous(), int(t), sample, return_dict=False)[0]   # diffusers' tuple form
     _check_sched("pndm", variant, sample.cpu())
