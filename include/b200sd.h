@@ -433,6 +433,21 @@ int b200sd_adamw_step(float* param, float* grad, float* exp_avg, float* exp_avg_
                       float lr, float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
                       int zero_grad, b200sd_stream_t stream);
 
+/* bnb.optim.AdamW8bit semantics -- the reference's default optimizer (finetune_sd.py:300 use_8bit_adam=True, :407-420
+ * `bnb.optim.AdamW8bit(params, lr, weight_decay, min_8bit_size=16384)`; bitsandbytes 0.35.4, un-vendored) -- over the n (multiple
+ * of 64) parameters of a flat buffer: both Adam moments are stored as 1-byte codes of a 256-entry code book (`qmap1` signed,
+ * `qmap2` unsigned: bitsandbytes' "dynamic" maps, sorted ascending) times one fp32 absmax per block of 2048 values
+ * (`absmax1/2`: ceil(n / 2048) floats).  `chunk_mode` (n / 64 ints, or NULL = every value 8-bit) says, per 64-value chunk of the
+ * flat buffer: -1 = 8-bit moments, -2 = frozen / padding (nothing read or written), k >= 0 = fp32 moments at
+ * small_exp_avg[k ..] / small_exp_avg_sq[k ..] (tensors below min_8bit_size).  Update (bitsandbytes' order):
+ * m = b1 m + (1-b1) g; v = b2 v + (1-b2) g g; p += -lr sqrt(1-b2^t)/(1-b1^t) * m / (sqrt(v) + sqrt(1-b2^t) eps); p *= 1 - lr wd;
+ * re-quantise m / max|m|, v / max|v| to the nearest code.  Fused like b200sd_adamw_step: grad_scale, bf16 re-cast of the weights,
+ * optional zeroing of grad.  HBM-bound: 10 B read + 8 B (12 B with zero_grad) written per parameter. */
+int b200sd_adamw8bit_step(float* param, float* grad, uint8_t* state1, uint8_t* state2, float* absmax1, float* absmax2,
+                          const float* qmap1, const float* qmap2, const int32_t* chunk_mode, float* small_exp_avg,
+                          float* small_exp_avg_sq, void* weights_bf16, int64_t n, float lr, float beta1, float beta2, float eps,
+                          float weight_decay, int step, float grad_scale, int zero_grad, b200sd_stream_t stream);
+
 /* nearest x2 upsample NHWC bf16: (batch,H,W,C) -> (batch,2H,2W,C)  (Upsample2D's F.interpolate) */
 int b200sd_upsample2x(const void* x, void* out, int batch, int H, int W, int C, int in_dtype, b200sd_stream_t stream);
 /* im2col for the three stride-2 Downsample2D convs: NHWC (batch,H,W,C) -> [batch*(H/2)*(W/2)][9*C] */

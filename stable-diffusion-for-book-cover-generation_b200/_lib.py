@@ -121,6 +121,7 @@ SIGNATURES = {
     "b200sd_small_linear_f32": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "b200sd_cast_flat": (_i, [_vp, _vp, _i64, _vp]),
     "b200sd_adamw_step": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _f, _f, _f, _f, _f, _i, _f, _i, _vp]),
+    "b200sd_adamw8bit_step": (_i, [_vp] * 12 + [_i64, _f, _f, _f, _f, _f, _i, _f, _i, _vp]),
     "b200sd_upsample2x": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "b200sd_im2col_s2": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
 }

@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libb200sd.so")
-SOURCES = ["api.cu", "elementwise.cu", "gemm_tcgen05.cu", "norm.cu", "misc.cu", "attention.cu", "attention_tc.cu", "backward.cu", "attention_bwd.cu", "attention_bwd_tc.cu", "fp32path.cu", "clip.cu", "vae.cu"]
+SOURCES = ["api.cu", "elementwise.cu", "gemm_tcgen05.cu", "norm.cu", "misc.cu", "attention.cu", "attention_tc.cu", "backward.cu", "attention_bwd.cu", "attention_bwd_tc.cu", "fp32path.cu", "clip.cu", "vae.cu", "optim8bit.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC"]

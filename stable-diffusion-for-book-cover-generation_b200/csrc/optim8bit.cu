@@ -1,0 +1,203 @@
+// b200sd -- block-wise 8-bit AdamW over the flat kernel-layout buffers: the optimizer the reference uses by default
+// (finetune_sd.py:300 use_8bit_adam=True, :407-420 bnb.optim.AdamW8bit(..., min_8bit_size=16384)).
+//
+// HBM-bound byte work: per parameter 10 B read (p, g fp32 + two 1-byte moment codes) and 8 B written (p fp32, bf16 tensor-core
+// copy, two codes; +4 B when the gradient is zeroed in the same pass) against 16 B + 14 (18) B of the fp32-state kernel
+// (adamw_flat_kernel in backward.cu).  One persistent CTA per SM slot walks 2048-value blocks (bitsandbytes' block size):
+// de-quantise both moments with the block's absmax, Adam update, block max-reduce of the new moments, parameter update, re-quantise
+// to the nearest entry of the 256-value dynamic code book.  The code books live in shared memory once per CTA; the nearest-code
+// search runs over their midpoints stored in breadth-first (Eytzinger) order, so the first six of its eight levels touch at most
+// one shared-memory bank per lane.  Every product / sum is a separately rounded fp32 operation (__f*_rn) in the order of
+// oracle/adam8bit_ref.py, which makes the codes, the absmax tables and the parameters bit-identical to the CPU restatement.
+#include <atomic>
+#include <cmath>
+
+#include "common.cuh"
+
+extern std::atomic<long long> g_b200sd_launches;
+#define COUNT_LAUNCH() g_b200sd_launches.fetch_add(1, std::memory_order_relaxed)
+
+namespace {
+
+constexpr int kBlock = 2048;      // values per quantisation block
+constexpr int kThreads = 256;     // x 8 values per thread
+constexpr int kModeSkip = -2;     // chunk_mode: frozen parameter / padding -- untouched
+constexpr int kMode8bit = -1;     // chunk_mode: moments stored as codes; >= 0: offset into the compact fp32 moments
+
+struct Adam8Consts {
+    float beta1, beta2, omb1, omb2, eps_c2, step_size, decay, grad_scale;
+    int apply_decay, zero_grad;
+};
+
+// number of midpoints strictly below x == index of the nearest code (ties to the lower code); e[] is the BFS layout of the
+// 255 sorted midpoints: node k (1-based) has children 2k, 2k + 1
+__device__ __forceinline__ int nearest_code(const float* __restrict__ e, float x) {
+    int k = 1;
+#pragma unroll
+    for (int l = 0; l < 8; ++l) k = 2 * k + (x > e[k] ? 1 : 0);
+    return k - 256;
+}
+
+__global__ void __launch_bounds__(kThreads) adamw8bit_kernel(float* __restrict__ p, float* __restrict__ g, uint8_t* __restrict__ st1,
+                                                             uint8_t* __restrict__ st2, float* __restrict__ absmax1,
+                                                             float* __restrict__ absmax2, const float* __restrict__ qmap1,
+                                                             const float* __restrict__ qmap2, const int32_t* __restrict__ chunk_mode,
+                                                             float* __restrict__ small_m, float* __restrict__ small_v,
+                                                             bf16* __restrict__ wb, int64_t n, int64_t nblocks, Adam8Consts c) {
+    __shared__ float q1[256], q2[256], e1[256], e2[256];
+    __shared__ float red1[kThreads / 32], red2[kThreads / 32];
+    const int tid = threadIdx.x;
+    ptx::pdl_trigger();
+    ptx::pdl_wait();
+    q1[tid] = __ldg(qmap1 + tid);
+    q2[tid] = __ldg(qmap2 + tid);
+    __syncthreads();
+    if (tid >= 1) {
+        // BFS node tid at level L (2^L <= tid < 2^(L+1)), j-th of its level, holds the sorted midpoint of rank (2j + 1) 2^(7-L) - 1
+        const int L = 31 - __clz(tid), j = tid - (1 << L);
+        const int r = (2 * j + 1) * (1 << (7 - L)) - 1;
+        e1[tid] = __fmul_rn(__fadd_rn(q1[r], q1[r + 1]), 0.5f);
+        e2[tid] = __fmul_rn(__fadd_rn(q2[r], q2[r + 1]), 0.5f);
+    } else {
+        e1[0] = e2[0] = 0.f;
+    }
+    __syncthreads();
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int64_t blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
+        const int64_t i0 = blk * kBlock + (int64_t)tid * 8;
+        int mode = kModeSkip;
+        if (i0 < n) mode = chunk_mode ? __ldg(chunk_mode + (i0 >> 6)) : kMode8bit;
+        float P[8], S1[8], S2[8];
+        float lmax1 = 0.f, lmax2 = 0.f;
+        if (mode != kModeSkip) {
+            float G[8];
+            {
+                const float4 a = reinterpret_cast<const float4*>(p + i0)[0], b = reinterpret_cast<const float4*>(p + i0)[1];
+                P[0] = a.x; P[1] = a.y; P[2] = a.z; P[3] = a.w; P[4] = b.x; P[5] = b.y; P[6] = b.z; P[7] = b.w;
+                const float4 ga = reinterpret_cast<const float4*>(g + i0)[0], gb = reinterpret_cast<const float4*>(g + i0)[1];
+                G[0] = ga.x; G[1] = ga.y; G[2] = ga.z; G[3] = ga.w; G[4] = gb.x; G[5] = gb.y; G[6] = gb.z; G[7] = gb.w;
+            }
+            int64_t so = 0;
+            if (mode == kMode8bit) {
+                const float a1 = absmax1[blk], a2 = absmax2[blk];
+                const uint2 u1 = *reinterpret_cast<const uint2*>(st1 + i0), u2 = *reinterpret_cast<const uint2*>(st2 + i0);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const uint32_t w1 = j < 4 ? u1.x : u1.y, w2 = j < 4 ? u2.x : u2.y;
+                    S1[j] = __fmul_rn(q1[(w1 >> (8 * (j & 3))) & 255u], a1);
+                    S2[j] = __fmul_rn(q2[(w2 >> (8 * (j & 3))) & 255u], a2);
+                }
+            } else {
+                so = (int64_t)mode + (i0 & 63);
+                const float4 a = reinterpret_cast<const float4*>(small_m + so)[0], b = reinterpret_cast<const float4*>(small_m + so)[1];
+                S1[0] = a.x; S1[1] = a.y; S1[2] = a.z; S1[3] = a.w; S1[4] = b.x; S1[5] = b.y; S1[6] = b.z; S1[7] = b.w;
+                const float4 va = reinterpret_cast<const float4*>(small_v + so)[0], vb = reinterpret_cast<const float4*>(small_v + so)[1];
+                S2[0] = va.x; S2[1] = va.y; S2[2] = va.z; S2[3] = va.w; S2[4] = vb.x; S2[5] = vb.y; S2[6] = vb.z; S2[7] = vb.w;
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float gv = __fmul_rn(G[j], c.grad_scale);
+                S2[j] = __fadd_rn(__fmul_rn(S2[j], c.beta2), __fmul_rn(__fmul_rn(c.omb2, gv), gv));
+                S1[j] = __fadd_rn(__fmul_rn(S1[j], c.beta1), __fmul_rn(c.omb1, gv));
+                const float upd = __fdiv_rn(S1[j], __fadd_rn(__fsqrt_rn(S2[j]), c.eps_c2));
+                P[j] = __fadd_rn(P[j], __fmul_rn(c.step_size, upd));
+                if (c.apply_decay) P[j] = __fmul_rn(P[j], c.decay);
+            }
+            reinterpret_cast<float4*>(p + i0)[0] = make_float4(P[0], P[1], P[2], P[3]);
+            reinterpret_cast<float4*>(p + i0)[1] = make_float4(P[4], P[5], P[6], P[7]);
+            uint4 w;
+            w.x = pack_bf16x2(P[0], P[1]);
+            w.y = pack_bf16x2(P[2], P[3]);
+            w.z = pack_bf16x2(P[4], P[5]);
+            w.w = pack_bf16x2(P[6], P[7]);
+            *reinterpret_cast<uint4*>(wb + i0) = w;
+            if (c.zero_grad) {
+                reinterpret_cast<float4*>(g + i0)[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+                reinterpret_cast<float4*>(g + i0)[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            if (mode == kMode8bit) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    lmax1 = fmaxf(lmax1, fabsf(S1[j]));
+                    lmax2 = fmaxf(lmax2, fabsf(S2[j]));
+                }
+            } else {
+                reinterpret_cast<float4*>(small_m + so)[0] = make_float4(S1[0], S1[1], S1[2], S1[3]);
+                reinterpret_cast<float4*>(small_m + so)[1] = make_float4(S1[4], S1[5], S1[6], S1[7]);
+                reinterpret_cast<float4*>(small_v + so)[0] = make_float4(S2[0], S2[1], S2[2], S2[3]);
+                reinterpret_cast<float4*>(small_v + so)[1] = make_float4(S2[4], S2[5], S2[6], S2[7]);
+            }
+        }
+        // new absmax of the block: max over the threads that hold 8-bit moments (every thread takes part in the reduction)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lmax1 = fmaxf(lmax1, __shfl_xor_sync(0xffffffffu, lmax1, o));
+            lmax2 = fmaxf(lmax2, __shfl_xor_sync(0xffffffffu, lmax2, o));
+        }
+        if (lane == 0) { red1[warp] = lmax1; red2[warp] = lmax2; }
+        __syncthreads();
+        float n1 = red1[0], n2 = red2[0];
+#pragma unroll
+        for (int w = 1; w < kThreads / 32; ++w) { n1 = fmaxf(n1, red1[w]); n2 = fmaxf(n2, red2[w]); }
+        if (mode == kMode8bit) {
+            uint32_t o1[2] = {0u, 0u}, o2[2] = {0u, 0u};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float x1 = n1 > 0.f ? __fdiv_rn(S1[j], n1) : 0.f;
+                const float x2 = n2 > 0.f ? __fdiv_rn(S2[j], n2) : 0.f;
+                int c1 = nearest_code(e1, x1);
+                // bitsandbytes: "make sure state1 term has still the same sign after quantization"
+                if ((__float_as_uint(q1[c1]) >> 31) != (__float_as_uint(S1[j]) >> 31)) c1 += S1[j] > 0.f ? 1 : -1;
+                const int c2 = nearest_code(e2, x2);
+                o1[j >> 2] |= (uint32_t)(c1 & 255) << (8 * (j & 3));
+                o2[j >> 2] |= (uint32_t)(c2 & 255) << (8 * (j & 3));
+            }
+            *reinterpret_cast<uint2*>(st1 + i0) = make_uint2(o1[0], o1[1]);
+            *reinterpret_cast<uint2*>(st2 + i0) = make_uint2(o2[0], o2[1]);
+        }
+        if (tid == 0) { absmax1[blk] = n1; absmax2[blk] = n2; }
+        __syncthreads();      // red1 / red2 are rewritten by the next block
+    }
+}
+
+}  // namespace
+
+// bnb.optim.AdamW8bit semantics (block-wise dynamic 8-bit moments, fp32 moments for the tensors below min_8bit_size) over the
+// n (multiple of 64) parameters of a flat buffer; see include/b200sd.h.
+extern "C" int b200sd_adamw8bit_step(float* param, float* grad, uint8_t* state1, uint8_t* state2, float* absmax1, float* absmax2,
+                                     const float* qmap1, const float* qmap2, const int32_t* chunk_mode, float* small_exp_avg,
+                                     float* small_exp_avg_sq, void* weights_bf16, int64_t n, float lr, float beta1, float beta2,
+                                     float eps, float weight_decay, int step, float grad_scale, int zero_grad,
+                                     b200sd_stream_t stream) {
+    B200SD_REQUIRE(param && grad && state1 && state2 && absmax1 && absmax2 && qmap1 && qmap2 && weights_bf16,
+                   "adamw8bit_step: null pointer");
+    B200SD_REQUIRE(n > 0 && n % 64 == 0 && step >= 1, "adamw8bit_step: n must be a positive multiple of 64 and step >= 1");
+    B200SD_REQUIRE(((reinterpret_cast<uintptr_t>(param) | reinterpret_cast<uintptr_t>(grad) | reinterpret_cast<uintptr_t>(weights_bf16) |
+                     reinterpret_cast<uintptr_t>(small_exp_avg) | reinterpret_cast<uintptr_t>(small_exp_avg_sq)) & 15) == 0 &&
+                       ((reinterpret_cast<uintptr_t>(state1) | reinterpret_cast<uintptr_t>(state2)) & 7) == 0,
+                   "adamw8bit_step: pointers must be 16-byte (codes: 8-byte) aligned");
+    B200SD_REQUIRE(chunk_mode == nullptr || (small_exp_avg && small_exp_avg_sq),
+                   "adamw8bit_step: a chunk table needs the compact fp32 moment buffers of the small tensors");
+    const double c1 = 1.0 - pow((double)beta1, (double)step);
+    const double c2 = sqrt(1.0 - pow((double)beta2, (double)step));
+    Adam8Consts c;
+    c.beta1 = beta1;
+    c.beta2 = beta2;
+    c.omb1 = (float)(1.0 - (double)beta1);
+    c.omb2 = (float)(1.0 - (double)beta2);
+    c.eps_c2 = (float)((double)eps * c2);
+    c.step_size = (float)(-(double)lr * c2 / c1);
+    c.decay = (float)(1.0 - (double)lr * (double)weight_decay);
+    c.apply_decay = weight_decay > 0.f ? 1 : 0;
+    c.grad_scale = grad_scale;
+    c.zero_grad = zero_grad;
+    const int64_t nblocks = (n + kBlock - 1) / kBlock;
+    int64_t grid = (int64_t)b200sd_num_sms() * 6;
+    if (grid > nblocks) grid = nblocks;
+    B200SD_CUDA(b200sd_launch(adamw8bit_kernel, dim3((unsigned)grid), dim3(kThreads), 0, static_cast<cudaStream_t>(stream), param, grad,
+                              state1, state2, absmax1, absmax2, qmap1, qmap2, chunk_mode, small_exp_avg, small_exp_avg_sq,
+                              static_cast<bf16*>(weights_bf16), n, nblocks, c));
+    COUNT_LAUNCH();
+    B200SD_LAUNCH_CHECK();
+    return B200SD_OK;
+}

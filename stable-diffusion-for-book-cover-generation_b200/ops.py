@@ -474,6 +474,16 @@ def adamw_step(param, grad, exp_avg, exp_avg_sq, weights_bf16, lr, beta1, beta2,
                                   float(grad_scale), int(zero_grad), _stream()), "adamw_step")
 
 
+def adamw8bit_step(param, grad, state1, state2, absmax1, absmax2, qmap1, qmap2, chunk_mode, small_exp_avg, small_exp_avg_sq,
+                   weights_bf16, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0, zero_grad=False):
+    """bnb.optim.AdamW8bit semantics over a flat buffer (include/b200sd.h: b200sd_adamw8bit_step)"""
+    _chk(param, grad, state1, state2, absmax1, absmax2, qmap1, qmap2, chunk_mode, small_exp_avg, small_exp_avg_sq, weights_bf16)
+    check(lib().b200sd_adamw8bit_step(_p(param), _p(grad), _p(state1), _p(state2), _p(absmax1), _p(absmax2), _p(qmap1), _p(qmap2),
+                                      _p(chunk_mode), _p(small_exp_avg), _p(small_exp_avg_sq), _p(weights_bf16), param.numel(),
+                                      float(lr), float(beta1), float(beta2), float(eps), float(weight_decay), int(step),
+                                      float(grad_scale), int(zero_grad), _stream()), "adamw8bit_step")
+
+
 def groupnorm_silu_bwd(x0, x1, gamma, beta, dy, out0, out1, batch, hw, *, add_src=None, acc0=False, acc1=False,
                        dgamma=None, dbeta=None, groups=32, eps=1e-5, silu=True, mean_rstd=None):
     _chk(x0, x1, gamma, beta, dy, out0, out1, add_src, dgamma, dbeta, mean_rstd)

@@ -92,12 +92,7 @@ class FlatAdamW(torch.optim.Optimizer):
         self.flat = flat
         self.param_groups[0]["params"] = [flat.master]
         self.state.clear()
-        dev = flat.master.device
-        if old is not None and old["exp_avg"].numel() == flat.master.numel():
-            st = dict(step=int(old["step"]), exp_avg=old["exp_avg"].to(dev), exp_avg_sq=old["exp_avg_sq"].to(dev))
-        else:
-            st = dict(step=0, exp_avg=torch.zeros_like(flat.master), exp_avg_sq=torch.zeros_like(flat.master))
-        self.state[flat.master] = st
+        self.state[flat.master] = self._make_state(flat, old)
         # contiguous runs of TRAINABLE regions: frozen parameters (requires_grad=False) get neither an update nor
         # decoupled weight decay, as with torch.optim.AdamW over `filter(requires_grad, parameters)`
         self.spans = []
@@ -113,6 +108,12 @@ class FlatAdamW(torch.optim.Optimizer):
             self.spans[-1][1] = min(self.spans[-1][1], flat.master.numel())
         return self
 
+    def _make_state(self, flat, old):
+        dev = flat.master.device
+        if old is not None and "exp_avg" in old and old["exp_avg"].numel() == flat.master.numel():
+            return dict(step=int(old["step"]), exp_avg=old["exp_avg"].to(dev), exp_avg_sq=old["exp_avg_sq"].to(dev))
+        return dict(step=0, exp_avg=torch.zeros_like(flat.master), exp_avg_sq=torch.zeros_like(flat.master))
+
     # the hyper-parameters live in param_groups[0] (what torch's lr schedulers write); attribute access for the callers
     lr = property(lambda self: self.param_groups[0]["lr"], lambda self, v: self.param_groups[0].__setitem__("lr", v))
     betas = property(lambda self: self.param_groups[0]["betas"], lambda self, v: self.param_groups[0].__setitem__("betas", tuple(v)))
@@ -124,14 +125,20 @@ class FlatAdamW(torch.optim.Optimizer):
     steps = property(lambda self: self.state[self.flat.master]["step"],
                      lambda self, v: self.state[self.flat.master].__setitem__("step", int(v)))
 
+    _state_dtypes = {"exp_avg": torch.float32, "exp_avg_sq": torch.float32}
+
     def load_state_dict(self, state_dict):
-        super().load_state_dict(state_dict)
+        want = {k: v.shape for k, v in self.state[self.flat.master].items() if torch.is_tensor(v)}
+        saved = {k: (v.dtype if torch.is_tensor(v) else None) for k, v in state_dict["state"].get(0, {}).items()}
+        super().load_state_dict(state_dict)       # torch casts every floating state tensor to the parameter's dtype / device
         st = self.state[self.flat.master]
         st["step"] = int(st["step"])
-        for k in ("exp_avg", "exp_avg_sq"):
-            if st[k].shape != self.flat.master.shape:
-                raise ValueError(f"optimizer state {k} has {st[k].numel()} elements, the flat parameter buffer {self.flat.master.numel()}")
-            st[k] = st[k].to(device=self.flat.master.device, dtype=torch.float32).contiguous()
+        for k, shape in want.items():
+            if k not in st or st[k].shape != shape:
+                raise ValueError(f"optimizer state '{k}' does not fit this model's flat parameter buffer ({tuple(shape)})")
+            if saved.get(k) != self._state_dtypes[k]:
+                raise ValueError(f"optimizer state '{k}' was saved as {saved.get(k)}, expected {self._state_dtypes[k]}")
+            st[k] = st[k].to(device=self.flat.master.device, dtype=self._state_dtypes[k]).contiguous()
 
     def zero_grad(self, set_to_none: bool = True):
         """`optimizer.zero_grad()` of the reference loop (finetune_sd.py:570).  step() already zeroes the flat gradient buffer in the
@@ -173,9 +180,125 @@ class FlatAdamW(torch.optim.Optimizer):
         return self
 
 
+def create_dynamic_map(signed: bool = True, n: int = 7) -> torch.Tensor:
+    """bitsandbytes' "dynamic" 8-bit code book (functional.create_dynamic_map, 0.35.x): 256 sorted fp32 values; decade i of the
+    7 decades 1e-6 .. 1 holds 2^i (signed: of each sign) / 2^(i+1) (unsigned) linearly spaced fractions, plus 0 and 1."""
+    data = []
+    extra = (2 ** (7 - n) - 1) * (1 if signed else 2)
+    for i in range(n):
+        items = 2 ** (i + 7 - n) + 1 if signed else 2 ** (i + 7 - n + 1) + 1
+        edges = torch.linspace(0.1, 1, items)
+        means = (edges[:-1] + edges[1:]) / 2.0
+        data += ((10 ** (-(n - 1) + i)) * means).tolist()
+        if signed:
+            data += (-(10 ** (-(n - 1) + i)) * means).tolist()
+    if extra > 0:
+        edges = torch.linspace(0.1, 1, extra + 1)
+        means = (edges[:-1] + edges[1:]) / 2.0
+        data += ((10 ** (-(n - 1) + i)) * means).tolist()
+        if signed:
+            data += (-(10 ** (-(n - 1) + i)) * means).tolist()
+    data += [0.0, 1.0]
+    if len(data) != 256:
+        raise ValueError("the 8-bit code book must have 256 entries")
+    return torch.tensor(sorted(data), dtype=torch.float32)
+
+
+class FlatAdamW8bit(FlatAdamW):
+    """`bnb.optim.AdamW8bit(params, lr, weight_decay, min_8bit_size=16384)` -- the reference's DEFAULT optimizer
+    (finetune_sd.py:300 use_8bit_adam=True, :407-420) -- over train.FlatParams, one fused kernel per step
+    (csrc/optim8bit.cu: b200sd_adamw8bit_step).
+
+    Both Adam moments are 1-byte codes of bitsandbytes' dynamic code books with one fp32 absmax per block of 2048 values;
+    tensors with fewer than `min_8bit_size` elements (biases, norms) keep fp32 moments in a compact side buffer, frozen
+    parameters are skipped.  2 B of optimizer state per parameter instead of 8 B, and 18 B (22 B with the gradient zeroing)
+    of HBM traffic per parameter and step instead of 30 B (34 B).  Blocks run over the flat buffer, not per tensor (a block may
+    hold the tail of one tensor and the head of the next); the update order is bitsandbytes' (decay after the Adam update).
+    It is a torch.optim.Optimizer like FlatAdamW: lr schedulers, state_dict(), rebind() work the same way."""
+
+    BLOCK, CHUNK, MODE_8BIT, MODE_SKIP = 2048, 64, -1, -2
+    _state_dtypes = {"state1": torch.uint8, "state2": torch.uint8, "absmax1": torch.float32, "absmax2": torch.float32,
+                     "exp_avg": torch.float32, "exp_avg_sq": torch.float32}
+
+    def __init__(self, flat, lr=1e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, min_8bit_size=16384, state=None):
+        self.min_8bit_size = int(min_8bit_size)
+        self._pending = False
+        super().__init__(flat, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, state=state)
+
+    def _make_state(self, flat, old):
+        dev, n = flat.master.device, flat.master.numel()
+        if n % self.CHUNK:
+            raise ValueError("the flat parameter buffer must be a multiple of 64 elements")
+        mode = torch.full((n // self.CHUNK,), self.MODE_SKIP, dtype=torch.int32)
+        n_small = 0
+        for r in flat.order:
+            c0, c1 = r.off // self.CHUNK, (r.off + r.numel + self.CHUNK - 1) // self.CHUNK
+            if not r.param.requires_grad:
+                continue
+            if r.numel < self.min_8bit_size:
+                mode[c0:c1] = torch.arange(n_small, n_small + (c1 - c0) * self.CHUNK, self.CHUNK, dtype=torch.int32)
+                n_small += (c1 - c0) * self.CHUNK
+            else:
+                mode[c0:c1] = self.MODE_8BIT
+        self.chunk_mode = mode.to(dev)
+        self.qmap1, self.qmap2 = create_dynamic_map(True).to(dev), create_dynamic_map(False).to(dev)
+        nblocks = (n + self.BLOCK - 1) // self.BLOCK
+        n_small = max(n_small, self.CHUNK)            # never an empty (null-pointer) buffer
+        if (old is not None and "state1" in old and old["state1"].numel() == n and old["exp_avg"].numel() == n_small):
+            return {k: (int(v) if k == "step" else v.to(dev)) for k, v in old.items()}
+        return dict(step=0, state1=torch.zeros(n, dtype=torch.uint8, device=dev), state2=torch.zeros(n, dtype=torch.uint8, device=dev),
+                    absmax1=torch.zeros(nblocks, device=dev), absmax2=torch.zeros(nblocks, device=dev),
+                    exp_avg=torch.zeros(n_small, device=dev), exp_avg_sq=torch.zeros(n_small, device=dev))
+
+    def state_bytes(self):
+        return sum(v.numel() * v.element_size() for v in self.state[self.flat.master].values() if torch.is_tensor(v))
+
+    def _launch(self, grad_scale, zero_grad):
+        f, st = self.flat, self.state[self.flat.master]
+        ops.adamw8bit_step(f.master, f.grad, st["state1"], st["state2"], st["absmax1"], st["absmax2"], self.qmap1, self.qmap2,
+                           self.chunk_mode, st["exp_avg"], st["exp_avg_sq"], f.wb, self.lr, self.betas[0], self.betas[1], self.eps,
+                           self.weight_decay, self.steps, grad_scale=grad_scale, zero_grad=zero_grad)
+
+    # a quantisation block of 2048 values does not respect gradient-bucket boundaries: the range-by-range form of the step
+    # (Trainer's pipelined AdamW) is accepted and applied as ONE launch when the step is closed
+    def begin_step(self):
+        self.steps += 1
+        self._pending = None
+
+    def step_range(self, lo, hi, grad_scale=1.0, zero_grad=True):
+        if self._pending not in (None, (grad_scale, zero_grad)):
+            raise ValueError("FlatAdamW8bit: the ranges of one step must share grad_scale / zero_grad")
+        self._pending = (grad_scale, zero_grad)
+
+    def end_step(self):
+        if self._pending:
+            self._launch(*self._pending)
+        self._pending = False
+        return super().end_step()
+
+    def step(self, closure=None, grad_scale=1.0, zero_grad=True):
+        if closure is not None:
+            raise NotImplementedError("FlatAdamW8bit.step takes no closure (the reference never passes one)")
+        self.steps += 1
+        self._launch(grad_scale, zero_grad)
+        self.flat.model.mark_weights_changed()
+        return self
+
+
+def _make_optimizer(flat, optim_bits, opt_args, min_8bit_size):
+    if optim_bits == 32:
+        return FlatAdamW(flat, **opt_args)
+    if optim_bits == 8:
+        return FlatAdamW8bit(flat, min_8bit_size=min_8bit_size, **opt_args)
+    raise ValueError("optim_bits must be 32 (torch.optim.AdamW semantics) or 8 (bnb.optim.AdamW8bit semantics)")
+
+
 class Trainer:
     def __init__(self, unet, noise_scheduler, lr=1e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, group=None,
-                 bucket_bytes: int = 64 << 20):
+                 bucket_bytes: int = 64 << 20, optim_bits: int = 32, min_8bit_size: int = 16384):
+        """optim_bits=8: the reference's default `bnb.optim.AdamW8bit(..., min_8bit_size=16384)` (finetune_sd.py:300, 407-410) as
+        FlatAdamW8bit; 32 (default here): torch.optim.AdamW semantics, the reference's use_8bit_adam=False branch."""
+        self.optim_bits, self.min_8bit_size = optim_bits, min_8bit_size
         self.unet, self.sched, self.group = unet.train(), noise_scheduler, group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.bucket_bytes = bucket_bytes
@@ -192,7 +315,8 @@ class Trainer:
         flat = ensure_flat(self.unet, device)
         if self.reducer is None or self.reducer.flat is not flat.grad:
             self.reducer = BucketReducer(flat.grad, self.group, self.bucket_bytes)
-            self.opt = FlatAdamW(flat, **self.opt_args) if self.opt is None else self.opt.rebind(flat)
+            self.opt = (_make_optimizer(flat, self.optim_bits, self.opt_args, self.min_8bit_size) if self.opt is None
+                        else self.opt.rebind(flat))
             flat.zero_grad()
             flat.attach_grads()
             self.micro_steps = 0
@@ -269,7 +393,8 @@ class TextEncoderTrainer:
     one pass."""
 
     def __init__(self, text_encoder, unet, noise_scheduler, lr=1e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, group=None,
-                 chunks: int = 4):
+                 chunks: int = 4, optim_bits: int = 32, min_8bit_size: int = 16384):
+        self.optim_bits, self.min_8bit_size = optim_bits, min_8bit_size
         self.te, self.unet, self.sched, self.group = text_encoder.train(), unet.eval().requires_grad_(False), noise_scheduler, group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.opt_args = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
@@ -283,7 +408,8 @@ class TextEncoderTrainer:
     def _prepare(self, device):
         flat = self.te._ensure_flat(device)
         if self._flat_id is not flat.grad:
-            self.opt = FlatAdamW(flat, **self.opt_args) if self.opt is None else self.opt.rebind(flat)
+            self.opt = (_make_optimizer(flat, self.optim_bits, self.opt_args, self.min_8bit_size) if self.opt is None
+                        else self.opt.rebind(flat))
             flat.zero_grad()
             flat.attach_grads()
             self._flat_id = flat.grad
