@@ -290,6 +290,23 @@ def elementwise_gbs(dev):
             "add_noise": (lambda: ops.add_noise(x, eu, t, sa, sb, out=o), 3 * E * 4, "3*E*b: read x0, noise; write x_t (+8 B/sample)"),
             "mse_loss_fwd": (lambda: ops.mse_loss_fwd(eu, ec), 2 * E * 4, "2*E*b: read pred, target"),
         }
+        if label.startswith("saturating"):
+            # the optimizer step of the fine-tuning path (finetune_sd.py:407-420, 569): fp32-moment AdamW and the
+            # reference's default, block-wise 8-bit AdamW, over E parameters of a flat buffer (fused: gradient scaling, bf16
+            # re-cast of the weights, gradient zeroing)
+            from b200sd.trainer import create_dynamic_map
+            pf, gf = eu.view(-1), ec.view(-1).mul_(0.01)
+            mf, vf = torch.zeros(E, device=dev), torch.zeros(E, device=dev)
+            wbf = torch.empty(E, device=dev, dtype=torch.bfloat16)
+            c1, c2 = torch.zeros(E, device=dev, dtype=torch.uint8), torch.zeros(E, device=dev, dtype=torch.uint8)
+            am1, am2 = torch.zeros(E // 2048, device=dev), torch.zeros(E // 2048, device=dev)
+            q1, q2 = create_dynamic_map(True).to(dev), create_dynamic_map(False).to(dev)
+            cases["adamw_step"] = (lambda: ops.adamw_step(pf, gf, mf, vf, wbf, 1e-5, 0.9, 0.999, 1e-8, 1e-2, 1, grad_scale=1.0,
+                                                          zero_grad=True), 34 * E,
+                                   "34 B/param: read p, g, m, v (fp32); write p, m, v, zeroed g (fp32) + bf16 weights")
+            cases["adamw8bit_step"] = (lambda: ops.adamw8bit_step(pf, gf, c1, c2, am1, am2, q1, q2, None, None, None, wbf, 1e-5, 0.9,
+                                                                  0.999, 1e-8, 1e-2, 1, grad_scale=1.0, zero_grad=True), 22 * E,
+                                       "22 B/param: read p, g (fp32) + 2 moment codes (u8); write p, zeroed g (fp32), bf16 weights, 2 codes")
         for name, (fn, nbytes, formula) in cases.items():
             sec = timed(fn, reps)
             rec[name] = {"us": round(sec * 1e6, 2), "bytes": nbytes, "gbs": round(nbytes / sec / 1e9, 1),
@@ -861,7 +878,7 @@ def run_train(args):
     torch.manual_seed(0)                                   # identical initial weights on every rank
     unet = UNet2DConditionModel().to(dev)
     sched = DDPMScheduler(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear", num_train_timesteps=1000)
-    tr = Trainer(unet, sched, lr=1e-5, weight_decay=1e-2)
+    tr = Trainer(unet, sched, lr=1e-5, weight_decay=1e-2, optim_bits=args.optim_bits)
     g = torch.Generator().manual_seed(1000 + rank)
     host = dict(x0=torch.randn(B, 4, 64, 64, generator=g).pin_memory(), noise=torch.randn(B, 4, 64, 64, generator=g).pin_memory(),
                 t=torch.randint(0, 1000, (B,), generator=g).pin_memory(), ctx=torch.randn(B, 77, 768, generator=g).pin_memory())
@@ -910,6 +927,8 @@ def run_train(args):
                 "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
                 "config": {"workload": "sd15_unet_finetune_512px", "batch_per_gpu": B, "latent": "4x64x64", "context": "77x768",
                            "step": "add_noise + UNet fwd + MSE + bwd (dgrad + wgrad) + bucketed NCCL allreduce + fused AdamW",
+                           "optimizer": ("block-wise 8-bit AdamW (bnb.optim.AdamW8bit semantics, the reference's default)"
+                                         if args.optim_bits == 8 else "AdamW, fp32 moments (torch.optim.AdamW semantics)"),
                            "weights": "random-init SD v1.5 UNet (859.5M params), fp32 master + bf16 tensor-core copy",
                            "allreduce_bytes_per_gpu": int(2 * (world - 1) / world * n_param * 4), "last_loss": loss_val,
                            "l2": "no flush: 7.4 GB of saved activations + 8.6 GB of parameter state stream through the 126 MB L2 every step"},
@@ -1027,6 +1046,8 @@ def main():
     ap.add_argument("--sweep-batches", default="1,2,4,8,16,32,64", help="--workload sweep: total image batches to run")
     ap.add_argument("--workload", default="sample", choices=["sample", "train", "train_text", "sweep"],
                     help="sample = 50-step DDIM + CFG denoising (BASELINE configs[1], the headline); train = fine-tuning step (configs[2])")
+    ap.add_argument("--optim-bits", type=int, default=32, choices=[32, 8],
+                    help="--workload train: 8 = the reference's default block-wise 8-bit AdamW state (finetune_sd.py:300, 407-410)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train-legs", action="store_true", help="skip the fine-tuning sub-records (configs 3 / 4) of the default line")
     ap.add_argument("--no-elementwise", action="store_true", help="skip the elementwise GB/s sub-record")

@@ -160,8 +160,11 @@ class AdamW8bitRef:
         pad = self.nblocks * BLOCK - self.n
         a1 = torch.cat([torch.where(is8, s1.abs(), torch.zeros(())), torch.zeros(pad)]).view(self.nblocks, BLOCK).amax(dim=1)
         a2 = torch.cat([torch.where(is8, s2.abs(), torch.zeros(())), torch.zeros(pad)]).view(self.nblocks, BLOCK).amax(dim=1)
-        x1 = torch.where(a1[blk] > 0, s1 / a1[blk], torch.zeros(()))
-        x2 = torch.where(a2[blk] > 0, s2 / a2[blk], torch.zeros(()))
+        # scaled by the block's reciprocal absmax (one correctly rounded 1 / absmax per block, then a product per value;
+        # bitsandbytes divides every value with the approximate __fdividef)
+        inv1 = torch.where(a1 > 0, torch.ones_like(a1) / a1, torch.zeros(()))
+        inv2 = torch.where(a2 > 0, torch.ones_like(a2) / a2, torch.zeros(()))
+        x1, x2 = s1 * inv1[blk], s2 * inv2[blk]
         c1 = quantize_nearest(x1, self.qmap1).long()
         flip = torch.signbit(self.qmap1[c1]) != torch.signbit(s1)
         c1 = torch.where(flip, torch.where(s1 > 0, c1 + 1, c1 - 1), c1)

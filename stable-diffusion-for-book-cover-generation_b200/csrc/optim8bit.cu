@@ -5,10 +5,15 @@
 // copy, two codes; +4 B when the gradient is zeroed in the same pass) against 16 B + 14 (18) B of the fp32-state kernel
 // (adamw_flat_kernel in backward.cu).  One persistent CTA per SM slot walks 2048-value blocks (bitsandbytes' block size):
 // de-quantise both moments with the block's absmax, Adam update, block max-reduce of the new moments, parameter update, re-quantise
-// to the nearest entry of the 256-value dynamic code book.  The code books live in shared memory once per CTA; the nearest-code
-// search runs over their midpoints stored in breadth-first (Eytzinger) order, so the first six of its eight levels touch at most
-// one shared-memory bank per lane.  Every product / sum is a separately rounded fp32 operation (__f*_rn) in the order of
+// to the nearest entry of the 256-value dynamic code book.  The code books live in shared memory once per CTA.  Nearest code =
+// number of code-book midpoints below x: a per-CTA lookup table indexed by the top 16 bits of x's order-preserving integer key
+// (sign, exponent, 7 mantissa bits: 128 bins per octave over 25 octaves) gives the count at the low edge of x's bin, two
+// compares against the sorted midpoints finish it (the dynamic code books put at most one midpoint into a bin; a code book
+// denser than two per bin switches the CTA to the generic eight-level search over the midpoints in breadth-first order, which
+// also builds the table).  Every product / sum is a separately rounded fp32 operation (__f*_rn) in the order of
 // oracle/adam8bit_ref.py, which makes the codes, the absmax tables and the parameters bit-identical to the CPU restatement.
+// v1 of this kernel (eight-level search per value, one IEEE division per value for the scaling, 6 CTAs per SM requested where
+// 4 fit) ran at 2.66 TB/s = 41 % of the measured copy bandwidth (profiles/r02c_elementwise_with_optimizers_v1.json).
 #include <atomic>
 #include <cmath>
 
@@ -23,6 +28,10 @@ constexpr int kBlock = 2048;      // values per quantisation block
 constexpr int kThreads = 256;     // x 8 values per thread
 constexpr int kModeSkip = -2;     // chunk_mode: frozen parameter / padding -- untouched
 constexpr int kMode8bit = -1;     // chunk_mode: moments stored as codes; >= 0: offset into the compact fp32 moments
+// lookup-table bins: q = (order-preserving key of x) >> 16.  Positive x in [2^-24, 1.0078): q in [0xB380, 0xBF80], everything
+// smaller shares the bin below them; negative x mirrored: q in [0x407F, 0x4C7F], tiny negatives share the bin 0x4C80.
+constexpr int kPosBase = 0xB37F, kNegBase = 0x407F, kNegClamp = 0x4C80;
+constexpr int kNPos = 0xBF80 - kPosBase + 1;      // 3074 bins per sign
 
 struct Adam8Consts {
     float beta1, beta2, omb1, omb2, eps_c2, step_size, decay, grad_scale;
@@ -38,13 +47,27 @@ __device__ __forceinline__ int nearest_code(const float* __restrict__ e, float x
     return k - 256;
 }
 
-__global__ void __launch_bounds__(kThreads) adamw8bit_kernel(float* __restrict__ p, float* __restrict__ g, uint8_t* __restrict__ st1,
+__device__ __forceinline__ int lut_bin_signed(float x) {
+    const uint32_t u = __float_as_uint(x);
+    const int q = (int)((u ^ (uint32_t)(((int32_t)u >> 31) | (int32_t)0x80000000)) >> 16);     // negative: ~u, positive: u | 2^31
+    // (the outer clamps only matter for inf / NaN moments, i.e. a diverged run: they keep the table index in range)
+    return q >= 0x8000 ? min(max(q, kPosBase), 0xBF80) - kPosBase + kNPos : max(min(q, kNegClamp), kNegBase) - kNegBase;
+}
+__device__ __forceinline__ int lut_bin_unsigned(float x) {       // x >= 0
+    return min(max((int)(__float_as_uint(x) >> 16), kPosBase - 0x8000), 0xBF80 - 0x8000) - (kPosBase - 0x8000);
+}
+// the smallest value of a bin
+__device__ __forceinline__ float bin_low_pos(int bp) { return bp == 0 ? 0.f : __uint_as_float((uint32_t)(kPosBase + bp - 0x8000) << 16); }
+__device__ __forceinline__ float bin_low_neg(int b) { return __uint_as_float(((0xFFFFu - (uint32_t)(kNegBase + b)) << 16) | 0xFFFFu); }
+
+__global__ void __launch_bounds__(kThreads, 4) adamw8bit_kernel(float* __restrict__ p, float* __restrict__ g, uint8_t* __restrict__ st1,
                                                              uint8_t* __restrict__ st2, float* __restrict__ absmax1,
                                                              float* __restrict__ absmax2, const float* __restrict__ qmap1,
                                                              const float* __restrict__ qmap2, const int32_t* __restrict__ chunk_mode,
                                                              float* __restrict__ small_m, float* __restrict__ small_v,
                                                              bf16* __restrict__ wb, int64_t n, int64_t nblocks, Adam8Consts c) {
-    __shared__ float q1[256], q2[256], e1[256], e2[256];
+    __shared__ float q1[256], q2[256], e1[256], e2[256], m1[256], m2[256];
+    __shared__ uint8_t lut1[2 * kNPos + 4], lut2[kNPos + 6];
     __shared__ float red1[kThreads / 32], red2[kThreads / 32];
     const int tid = threadIdx.x;
     ptx::pdl_trigger();
@@ -52,6 +75,9 @@ __global__ void __launch_bounds__(kThreads) adamw8bit_kernel(float* __restrict__
     q1[tid] = __ldg(qmap1 + tid);
     q2[tid] = __ldg(qmap2 + tid);
     __syncthreads();
+    // sorted midpoints (m[255] = +inf: a compare past the end is false) and their breadth-first copy
+    m1[tid] = tid < 255 ? __fmul_rn(__fadd_rn(q1[tid], q1[tid + 1]), 0.5f) : __int_as_float(0x7f800000);
+    m2[tid] = tid < 255 ? __fmul_rn(__fadd_rn(q2[tid], q2[tid + 1]), 0.5f) : __int_as_float(0x7f800000);
     if (tid >= 1) {
         // BFS node tid at level L (2^L <= tid < 2^(L+1)), j-th of its level, holds the sorted midpoint of rank (2j + 1) 2^(7-L) - 1
         const int L = 31 - __clz(tid), j = tid - (1 << L);
@@ -62,6 +88,15 @@ __global__ void __launch_bounds__(kThreads) adamw8bit_kernel(float* __restrict__
         e1[0] = e2[0] = 0.f;
     }
     __syncthreads();
+    // lookup tables: number of midpoints below the low edge of every bin
+    for (int b = tid; b < 2 * kNPos; b += kThreads)
+        lut1[b] = (uint8_t)nearest_code(e1, b < kNPos ? bin_low_neg(b) : bin_low_pos(b - kNPos));
+    for (int b = tid; b < kNPos; b += kThreads) lut2[b] = (uint8_t)nearest_code(e2, bin_low_pos(b));
+    __syncthreads();
+    int dense = 0;
+    for (int b = tid; b < 2 * kNPos; b += kThreads) dense |= (b + 1 < 2 * kNPos ? (int)lut1[b + 1] : 255) - (int)lut1[b] > 2;
+    for (int b = tid; b < kNPos; b += kThreads) dense |= (b + 1 < kNPos ? (int)lut2[b + 1] : 255) - (int)lut2[b] > 2;
+    const bool slow = __syncthreads_or(dense) != 0;
     const int warp = tid >> 5, lane = tid & 31;
     for (int64_t blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
         const int64_t i0 = blk * kBlock + (int64_t)tid * 8;
@@ -141,14 +176,24 @@ __global__ void __launch_bounds__(kThreads) adamw8bit_kernel(float* __restrict__
         for (int w = 1; w < kThreads / 32; ++w) { n1 = fmaxf(n1, red1[w]); n2 = fmaxf(n2, red2[w]); }
         if (mode == kMode8bit) {
             uint32_t o1[2] = {0u, 0u}, o2[2] = {0u, 0u};
+            const float inv1 = n1 > 0.f ? __fdiv_rn(1.f, n1) : 0.f, inv2 = n2 > 0.f ? __fdiv_rn(1.f, n2) : 0.f;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                const float x1 = n1 > 0.f ? __fdiv_rn(S1[j], n1) : 0.f;
-                const float x2 = n2 > 0.f ? __fdiv_rn(S2[j], n2) : 0.f;
-                int c1 = nearest_code(e1, x1);
+                const float x1 = __fmul_rn(S1[j], inv1), x2 = __fmul_rn(S2[j], inv2);
+                int c1, c2;
+                if (!slow) {
+                    c1 = lut1[lut_bin_signed(x1)];
+                    c1 += x1 > m1[c1] ? 1 : 0;
+                    c1 += x1 > m1[c1] ? 1 : 0;
+                    c2 = lut2[lut_bin_unsigned(x2)];
+                    c2 += x2 > m2[c2] ? 1 : 0;
+                    c2 += x2 > m2[c2] ? 1 : 0;
+                } else {
+                    c1 = nearest_code(e1, x1);
+                    c2 = nearest_code(e2, x2);
+                }
                 // bitsandbytes: "make sure state1 term has still the same sign after quantization"
                 if ((__float_as_uint(q1[c1]) >> 31) != (__float_as_uint(S1[j]) >> 31)) c1 += S1[j] > 0.f ? 1 : -1;
-                const int c2 = nearest_code(e2, x2);
                 o1[j >> 2] |= (uint32_t)(c1 & 255) << (8 * (j & 3));
                 o2[j >> 2] |= (uint32_t)(c2 & 255) << (8 * (j & 3));
             }
@@ -192,7 +237,14 @@ extern "C" int b200sd_adamw8bit_step(float* param, float* grad, uint8_t* state1,
     c.grad_scale = grad_scale;
     c.zero_grad = zero_grad;
     const int64_t nblocks = (n + kBlock - 1) / kBlock;
-    int64_t grid = (int64_t)b200sd_num_sms() * 6;
+    // persistent grid: exactly the CTAs that are resident at once (a larger grid would run its tail at partial occupancy)
+    static int ctas_per_sm = 0;
+    if (ctas_per_sm == 0) {
+        int v = 0;
+        B200SD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, adamw8bit_kernel, kThreads, 0));
+        ctas_per_sm = v > 0 ? v : 1;
+    }
+    int64_t grid = (int64_t)b200sd_num_sms() * ctas_per_sm;
     if (grid > nblocks) grid = nblocks;
     B200SD_CUDA(b200sd_launch(adamw8bit_kernel, dim3((unsigned)grid), dim3(kThreads), 0, static_cast<cudaStream_t>(stream), param, grad,
                               state1, state2, absmax1, absmax2, qmap1, qmap2, chunk_mode, small_exp_avg, small_exp_avg_sq,

@@ -30,13 +30,26 @@ def _random_modes(n_chunks, gen):
     return mode
 
 
-@pytest.mark.parametrize("n,with_modes,wd", [(2048 * 5, False, 1e-2), (2048 * 37 + 64 * 7, True, 1e-2), (64 * 3, True, 0.0),
-                                             (2048 * 300 + 64, True, 0.1)])
-def test_adamw8bit_kernel_is_bit_exact_against_the_oracle(n, with_modes, wd):
+def _dense_code_books():
+    """arbitrary sorted 256-entry code books with ~3 midpoints per lookup-table bin in their upper octave: the kernel must notice
+    and take its generic eight-level search (the dynamic code books never do)"""
+    lin = torch.linspace
+    q1 = torch.cat([-lin(1, 0.5, 100), lin(-0.45, -0.01, 27), torch.zeros(1), lin(0.01, 0.45, 28), lin(0.5, 1, 100)])
+    q2 = torch.cat([torch.zeros(1), lin(0.001, 0.45, 55), lin(0.5, 1, 200)])
+    assert q1.numel() == 256 and q2.numel() == 256 and bool((q1[1:] > q1[:-1]).all()) and bool((q2[1:] > q2[:-1]).all())
+    return q1.float(), q2.float()
+
+
+@pytest.mark.parametrize("n,with_modes,wd,dense", [(2048 * 5, False, 1e-2, False), (2048 * 37 + 64 * 7, True, 1e-2, False),
+                                                   (64 * 3, True, 0.0, False), (2048 * 300 + 64, True, 0.1, False),
+                                                   (2048 * 9 + 64 * 3, True, 1e-2, True)])
+def test_adamw8bit_kernel_is_bit_exact_against_the_oracle(n, with_modes, wd, dense):
     from b200sd import ops
     gen = torch.Generator().manual_seed(n)
     mode = _random_modes(n // 64, gen) if with_modes else None
     ref = A.AdamW8bitRef(n, mode, lr=3e-3, betas=(0.9, 0.99), eps=1e-8, weight_decay=wd)
+    if dense:
+        ref.qmap1, ref.qmap2 = _dense_code_books()
     p_ref = torch.randn(n, generator=gen) * 0.1
     p = p_ref.clone().to(DEV)
     g_dev = torch.empty(n, device=DEV)
