@@ -16,6 +16,7 @@
 // 4 fit) ran at 2.66 TB/s = 41 % of the measured copy bandwidth (profiles/r02c_elementwise_with_optimizers_v1.json).
 #include <atomic>
 #include <cmath>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -25,7 +26,11 @@ extern std::atomic<long long> g_b200sd_launches;
 namespace {
 
 constexpr int kBlock = 2048;      // values per quantisation block
-constexpr int kThreads = 256;     // x 8 values per thread
+constexpr int kV = 4;             // values per thread
+constexpr int kThreads = kBlock / kV;     // 512: one CTA iteration = one quantisation block
+// resident CTAs per SM the kernel is compiled for: 3 -> 40 registers, 48 warps per SM; 4 -> 32 registers (24 B of spills), 64 warps.
+// B200SD_ADAM8_CTAS=3|4 selects at run time; the default is the faster one on B200 (profiles/r02c_adam8bit_variants.txt).
+constexpr int kDefaultCtasPerSm = 3;
 constexpr int kModeSkip = -2;     // chunk_mode: frozen parameter / padding -- untouched
 constexpr int kMode8bit = -1;     // chunk_mode: moments stored as codes; >= 0: offset into the compact fp32 moments
 // lookup-table bins: q = (order-preserving key of x) >> 16.  Positive x in [2^-24, 1.0078): q in [0xB380, 0xBF80], everything
@@ -60,32 +65,40 @@ __device__ __forceinline__ int lut_bin_unsigned(float x) {       // x >= 0
 __device__ __forceinline__ float bin_low_pos(int bp) { return bp == 0 ? 0.f : __uint_as_float((uint32_t)(kPosBase + bp - 0x8000) << 16); }
 __device__ __forceinline__ float bin_low_neg(int b) { return __uint_as_float(((0xFFFFu - (uint32_t)(kNegBase + b)) << 16) | 0xFFFFu); }
 
-__global__ void __launch_bounds__(kThreads, 4) adamw8bit_kernel(float* __restrict__ p, float* __restrict__ g, uint8_t* __restrict__ st1,
-                                                             uint8_t* __restrict__ st2, float* __restrict__ absmax1,
-                                                             float* __restrict__ absmax2, const float* __restrict__ qmap1,
-                                                             const float* __restrict__ qmap2, const int32_t* __restrict__ chunk_mode,
-                                                             float* __restrict__ small_m, float* __restrict__ small_v,
-                                                             bf16* __restrict__ wb, int64_t n, int64_t nblocks, Adam8Consts c) {
+template <int CTAS>
+__global__ void __launch_bounds__(kThreads, CTAS) adamw8bit_kernel(float* __restrict__ p, float* __restrict__ g,
+                                                                         uint8_t* __restrict__ st1, uint8_t* __restrict__ st2,
+                                                                         float* __restrict__ absmax1, float* __restrict__ absmax2,
+                                                                         const float* __restrict__ qmap1,
+                                                                         const float* __restrict__ qmap2,
+                                                                         const int32_t* __restrict__ chunk_mode,
+                                                                         float* __restrict__ small_m, float* __restrict__ small_v,
+                                                                         bf16* __restrict__ wb, int64_t n, int64_t nblocks,
+                                                                         Adam8Consts c) {
     __shared__ float q1[256], q2[256], e1[256], e2[256], m1[256], m2[256];
     __shared__ uint8_t lut1[2 * kNPos + 4], lut2[kNPos + 6];
     __shared__ float red1[kThreads / 32], red2[kThreads / 32];
     const int tid = threadIdx.x;
     ptx::pdl_trigger();
     ptx::pdl_wait();
-    q1[tid] = __ldg(qmap1 + tid);
-    q2[tid] = __ldg(qmap2 + tid);
+    if (tid < 256) {
+        q1[tid] = __ldg(qmap1 + tid);
+        q2[tid] = __ldg(qmap2 + tid);
+    }
     __syncthreads();
-    // sorted midpoints (m[255] = +inf: a compare past the end is false) and their breadth-first copy
-    m1[tid] = tid < 255 ? __fmul_rn(__fadd_rn(q1[tid], q1[tid + 1]), 0.5f) : __int_as_float(0x7f800000);
-    m2[tid] = tid < 255 ? __fmul_rn(__fadd_rn(q2[tid], q2[tid + 1]), 0.5f) : __int_as_float(0x7f800000);
-    if (tid >= 1) {
-        // BFS node tid at level L (2^L <= tid < 2^(L+1)), j-th of its level, holds the sorted midpoint of rank (2j + 1) 2^(7-L) - 1
-        const int L = 31 - __clz(tid), j = tid - (1 << L);
-        const int r = (2 * j + 1) * (1 << (7 - L)) - 1;
-        e1[tid] = __fmul_rn(__fadd_rn(q1[r], q1[r + 1]), 0.5f);
-        e2[tid] = __fmul_rn(__fadd_rn(q2[r], q2[r + 1]), 0.5f);
-    } else {
-        e1[0] = e2[0] = 0.f;
+    if (tid < 256) {
+        // sorted midpoints (m[255] = +inf: a compare past the end is false) and their breadth-first copy
+        m1[tid] = tid < 255 ? __fmul_rn(__fadd_rn(q1[tid], q1[tid + 1]), 0.5f) : __int_as_float(0x7f800000);
+        m2[tid] = tid < 255 ? __fmul_rn(__fadd_rn(q2[tid], q2[tid + 1]), 0.5f) : __int_as_float(0x7f800000);
+        if (tid >= 1) {
+            // BFS node tid at level L (2^L <= tid < 2^(L+1)), j-th of its level, holds the sorted midpoint of rank (2j + 1) 2^(7-L) - 1
+            const int L = 31 - __clz(tid), j = tid - (1 << L);
+            const int r = (2 * j + 1) * (1 << (7 - L)) - 1;
+            e1[tid] = __fmul_rn(__fadd_rn(q1[r], q1[r + 1]), 0.5f);
+            e2[tid] = __fmul_rn(__fadd_rn(q2[r], q2[r + 1]), 0.5f);
+        } else {
+            e1[0] = e2[0] = 0.f;
+        }
     }
     __syncthreads();
     // lookup tables: number of midpoints below the low edge of every bin
@@ -99,38 +112,35 @@ __global__ void __launch_bounds__(kThreads, 4) adamw8bit_kernel(float* __restric
     const bool slow = __syncthreads_or(dense) != 0;
     const int warp = tid >> 5, lane = tid & 31;
     for (int64_t blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
-        const int64_t i0 = blk * kBlock + (int64_t)tid * 8;
+        const int64_t i0 = blk * kBlock + (int64_t)tid * kV;
         int mode = kModeSkip;
         if (i0 < n) mode = chunk_mode ? __ldg(chunk_mode + (i0 >> 6)) : kMode8bit;
-        float P[8], S1[8], S2[8];
+        float S1[kV], S2[kV];
         float lmax1 = 0.f, lmax2 = 0.f;
         if (mode != kModeSkip) {
-            float G[8];
+            float P[kV], G[kV];
             {
-                const float4 a = reinterpret_cast<const float4*>(p + i0)[0], b = reinterpret_cast<const float4*>(p + i0)[1];
-                P[0] = a.x; P[1] = a.y; P[2] = a.z; P[3] = a.w; P[4] = b.x; P[5] = b.y; P[6] = b.z; P[7] = b.w;
-                const float4 ga = reinterpret_cast<const float4*>(g + i0)[0], gb = reinterpret_cast<const float4*>(g + i0)[1];
-                G[0] = ga.x; G[1] = ga.y; G[2] = ga.z; G[3] = ga.w; G[4] = gb.x; G[5] = gb.y; G[6] = gb.z; G[7] = gb.w;
+                const float4 a = *reinterpret_cast<const float4*>(p + i0), ga = *reinterpret_cast<const float4*>(g + i0);
+                P[0] = a.x; P[1] = a.y; P[2] = a.z; P[3] = a.w;
+                G[0] = ga.x; G[1] = ga.y; G[2] = ga.z; G[3] = ga.w;
             }
             int64_t so = 0;
             if (mode == kMode8bit) {
                 const float a1 = absmax1[blk], a2 = absmax2[blk];
-                const uint2 u1 = *reinterpret_cast<const uint2*>(st1 + i0), u2 = *reinterpret_cast<const uint2*>(st2 + i0);
+                const uint32_t u1 = *reinterpret_cast<const uint32_t*>(st1 + i0), u2 = *reinterpret_cast<const uint32_t*>(st2 + i0);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const uint32_t w1 = j < 4 ? u1.x : u1.y, w2 = j < 4 ? u2.x : u2.y;
-                    S1[j] = __fmul_rn(q1[(w1 >> (8 * (j & 3))) & 255u], a1);
-                    S2[j] = __fmul_rn(q2[(w2 >> (8 * (j & 3))) & 255u], a2);
+                for (int j = 0; j < kV; ++j) {
+                    S1[j] = __fmul_rn(q1[(u1 >> (8 * j)) & 255u], a1);
+                    S2[j] = __fmul_rn(q2[(u2 >> (8 * j)) & 255u], a2);
                 }
             } else {
                 so = (int64_t)mode + (i0 & 63);
-                const float4 a = reinterpret_cast<const float4*>(small_m + so)[0], b = reinterpret_cast<const float4*>(small_m + so)[1];
-                S1[0] = a.x; S1[1] = a.y; S1[2] = a.z; S1[3] = a.w; S1[4] = b.x; S1[5] = b.y; S1[6] = b.z; S1[7] = b.w;
-                const float4 va = reinterpret_cast<const float4*>(small_v + so)[0], vb = reinterpret_cast<const float4*>(small_v + so)[1];
-                S2[0] = va.x; S2[1] = va.y; S2[2] = va.z; S2[3] = va.w; S2[4] = vb.x; S2[5] = vb.y; S2[6] = vb.z; S2[7] = vb.w;
+                const float4 a = *reinterpret_cast<const float4*>(small_m + so), va = *reinterpret_cast<const float4*>(small_v + so);
+                S1[0] = a.x; S1[1] = a.y; S1[2] = a.z; S1[3] = a.w;
+                S2[0] = va.x; S2[1] = va.y; S2[2] = va.z; S2[3] = va.w;
             }
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
+            for (int j = 0; j < kV; ++j) {
                 const float gv = __fmul_rn(G[j], c.grad_scale);
                 S2[j] = __fadd_rn(__fmul_rn(S2[j], c.beta2), __fmul_rn(__fmul_rn(c.omb2, gv), gv));
                 S1[j] = __fadd_rn(__fmul_rn(S1[j], c.beta1), __fmul_rn(c.omb1, gv));
@@ -138,29 +148,18 @@ __global__ void __launch_bounds__(kThreads, 4) adamw8bit_kernel(float* __restric
                 P[j] = __fadd_rn(P[j], __fmul_rn(c.step_size, upd));
                 if (c.apply_decay) P[j] = __fmul_rn(P[j], c.decay);
             }
-            reinterpret_cast<float4*>(p + i0)[0] = make_float4(P[0], P[1], P[2], P[3]);
-            reinterpret_cast<float4*>(p + i0)[1] = make_float4(P[4], P[5], P[6], P[7]);
-            uint4 w;
-            w.x = pack_bf16x2(P[0], P[1]);
-            w.y = pack_bf16x2(P[2], P[3]);
-            w.z = pack_bf16x2(P[4], P[5]);
-            w.w = pack_bf16x2(P[6], P[7]);
-            *reinterpret_cast<uint4*>(wb + i0) = w;
-            if (c.zero_grad) {
-                reinterpret_cast<float4*>(g + i0)[0] = make_float4(0.f, 0.f, 0.f, 0.f);
-                reinterpret_cast<float4*>(g + i0)[1] = make_float4(0.f, 0.f, 0.f, 0.f);
-            }
+            *reinterpret_cast<float4*>(p + i0) = make_float4(P[0], P[1], P[2], P[3]);
+            *reinterpret_cast<uint2*>(wb + i0) = make_uint2(pack_bf16x2(P[0], P[1]), pack_bf16x2(P[2], P[3]));
+            if (c.zero_grad) *reinterpret_cast<float4*>(g + i0) = make_float4(0.f, 0.f, 0.f, 0.f);
             if (mode == kMode8bit) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
+                for (int j = 0; j < kV; ++j) {
                     lmax1 = fmaxf(lmax1, fabsf(S1[j]));
                     lmax2 = fmaxf(lmax2, fabsf(S2[j]));
                 }
             } else {
-                reinterpret_cast<float4*>(small_m + so)[0] = make_float4(S1[0], S1[1], S1[2], S1[3]);
-                reinterpret_cast<float4*>(small_m + so)[1] = make_float4(S1[4], S1[5], S1[6], S1[7]);
-                reinterpret_cast<float4*>(small_v + so)[0] = make_float4(S2[0], S2[1], S2[2], S2[3]);
-                reinterpret_cast<float4*>(small_v + so)[1] = make_float4(S2[4], S2[5], S2[6], S2[7]);
+                *reinterpret_cast<float4*>(small_m + so) = make_float4(S1[0], S1[1], S1[2], S1[3]);
+                *reinterpret_cast<float4*>(small_v + so) = make_float4(S2[0], S2[1], S2[2], S2[3]);
             }
         }
         // new absmax of the block: max over the threads that hold 8-bit moments (every thread takes part in the reduction)
@@ -175,10 +174,10 @@ __global__ void __launch_bounds__(kThreads, 4) adamw8bit_kernel(float* __restric
 #pragma unroll
         for (int w = 1; w < kThreads / 32; ++w) { n1 = fmaxf(n1, red1[w]); n2 = fmaxf(n2, red2[w]); }
         if (mode == kMode8bit) {
-            uint32_t o1[2] = {0u, 0u}, o2[2] = {0u, 0u};
+            uint32_t o1 = 0u, o2 = 0u;
             const float inv1 = n1 > 0.f ? __fdiv_rn(1.f, n1) : 0.f, inv2 = n2 > 0.f ? __fdiv_rn(1.f, n2) : 0.f;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
+            for (int j = 0; j < kV; ++j) {
                 const float x1 = __fmul_rn(S1[j], inv1), x2 = __fmul_rn(S2[j], inv2);
                 int c1, c2;
                 if (!slow) {
@@ -194,11 +193,11 @@ __global__ void __launch_bounds__(kThreads, 4) adamw8bit_kernel(float* __restric
                 }
                 // bitsandbytes: "make sure state1 term has still the same sign after quantization"
                 if ((__float_as_uint(q1[c1]) >> 31) != (__float_as_uint(S1[j]) >> 31)) c1 += S1[j] > 0.f ? 1 : -1;
-                o1[j >> 2] |= (uint32_t)(c1 & 255) << (8 * (j & 3));
-                o2[j >> 2] |= (uint32_t)(c2 & 255) << (8 * (j & 3));
+                o1 |= (uint32_t)(c1 & 255) << (8 * j);
+                o2 |= (uint32_t)(c2 & 255) << (8 * j);
             }
-            *reinterpret_cast<uint2*>(st1 + i0) = make_uint2(o1[0], o1[1]);
-            *reinterpret_cast<uint2*>(st2 + i0) = make_uint2(o2[0], o2[1]);
+            *reinterpret_cast<uint32_t*>(st1 + i0) = o1;
+            *reinterpret_cast<uint32_t*>(st2 + i0) = o2;
         }
         if (tid == 0) { absmax1[blk] = n1; absmax2[blk] = n2; }
         __syncthreads();      // red1 / red2 are rewritten by the next block
@@ -221,6 +220,7 @@ extern "C" int b200sd_adamw8bit_step(float* param, float* grad, uint8_t* state1,
                      reinterpret_cast<uintptr_t>(small_exp_avg) | reinterpret_cast<uintptr_t>(small_exp_avg_sq)) & 15) == 0 &&
                        ((reinterpret_cast<uintptr_t>(state1) | reinterpret_cast<uintptr_t>(state2)) & 7) == 0,
                    "adamw8bit_step: pointers must be 16-byte (codes: 8-byte) aligned");
+    static_assert(kV == 4 && kThreads * kV == kBlock, "one thread owns 4 consecutive values of a 2048-value block");
     B200SD_REQUIRE(chunk_mode == nullptr || (small_exp_avg && small_exp_avg_sq),
                    "adamw8bit_step: a chunk table needs the compact fp32 moment buffers of the small tensors");
     const double c1 = 1.0 - pow((double)beta1, (double)step);
@@ -238,17 +238,29 @@ extern "C" int b200sd_adamw8bit_step(float* param, float* grad, uint8_t* state1,
     c.zero_grad = zero_grad;
     const int64_t nblocks = (n + kBlock - 1) / kBlock;
     // persistent grid: exactly the CTAs that are resident at once (a larger grid would run its tail at partial occupancy)
-    static int ctas_per_sm = 0;
+    static const int variant = [] {
+        const char* e = getenv("B200SD_ADAM8_CTAS");
+        const int v = e ? atoi(e) : kDefaultCtasPerSm;
+        return v == 4 ? 4 : 3;
+    }();
+    static int resident[2] = {0, 0};
+    int& ctas_per_sm = resident[variant - 3];
     if (ctas_per_sm == 0) {
         int v = 0;
-        B200SD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, adamw8bit_kernel, kThreads, 0));
+        if (variant == 4) B200SD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, adamw8bit_kernel<4>, kThreads, 0));
+        else B200SD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, adamw8bit_kernel<3>, kThreads, 0));
         ctas_per_sm = v > 0 ? v : 1;
     }
     int64_t grid = (int64_t)b200sd_num_sms() * ctas_per_sm;
     if (grid > nblocks) grid = nblocks;
-    B200SD_CUDA(b200sd_launch(adamw8bit_kernel, dim3((unsigned)grid), dim3(kThreads), 0, static_cast<cudaStream_t>(stream), param, grad,
-                              state1, state2, absmax1, absmax2, qmap1, qmap2, chunk_mode, small_exp_avg, small_exp_avg_sq,
-                              static_cast<bf16*>(weights_bf16), n, nblocks, c));
+    if (variant == 4)
+        B200SD_CUDA(b200sd_launch(adamw8bit_kernel<4>, dim3((unsigned)grid), dim3(kThreads), 0, static_cast<cudaStream_t>(stream), param,
+                                  grad, state1, state2, absmax1, absmax2, qmap1, qmap2, chunk_mode, small_exp_avg, small_exp_avg_sq,
+                                  static_cast<bf16*>(weights_bf16), n, nblocks, c));
+    else
+        B200SD_CUDA(b200sd_launch(adamw8bit_kernel<3>, dim3((unsigned)grid), dim3(kThreads), 0, static_cast<cudaStream_t>(stream), param,
+                                  grad, state1, state2, absmax1, absmax2, qmap1, qmap2, chunk_mode, small_exp_avg, small_exp_avg_sq,
+                                  static_cast<bf16*>(weights_bf16), n, nblocks, c));
     COUNT_LAUNCH();
     B200SD_LAUNCH_CHECK();
     return B200SD_OK;
