@@ -8,9 +8,9 @@
 // to the nearest entry of the 256-value dynamic code book.  The code books live in shared memory once per CTA.  Nearest code =
 // number of code-book midpoints below x: a per-CTA lookup table indexed by the top 16 bits of x's order-preserving integer key
 // (sign, exponent, 7 mantissa bits: 128 bins per octave over 25 octaves) gives the count at the low edge of x's bin, two
-// compares against the sorted midpoints finish it (the dynamic code books put at most one midpoint into a bin; a code book
-// denser than two per bin switches the CTA to the generic eight-level search over the midpoints in breadth-first order, which
-// also builds the table).  Every product / sum is a separately rounded fp32 operation (__f*_rn) in the order of
+// compare against the sorted midpoints finishes it (the dynamic code books put at most one midpoint into a bin; the CTA checks
+// that and otherwise takes the generic eight-level search over the midpoints in breadth-first order, which also builds the
+// table).  Shared-memory reads per value: 2 to de-quantise, 4 to re-quantise.  Every product / sum is a separately rounded fp32 operation (__f*_rn) in the order of
 // oracle/adam8bit_ref.py, which makes the codes, the absmax tables and the parameters bit-identical to the CPU restatement.
 // v1 of this kernel (eight-level search per value, one IEEE division per value for the scaling, 6 CTAs per SM requested where
 // 4 fit) ran at 2.66 TB/s = 41 % of the measured copy bandwidth (profiles/r02c_elementwise_with_optimizers_v1.json).
@@ -106,10 +106,13 @@ __global__ void __launch_bounds__(kThreads, CTAS) adamw8bit_kernel(float* __rest
         lut1[b] = (uint8_t)nearest_code(e1, b < kNPos ? bin_low_neg(b) : bin_low_pos(b - kNPos));
     for (int b = tid; b < kNPos; b += kThreads) lut2[b] = (uint8_t)nearest_code(e2, bin_low_pos(b));
     __syncthreads();
-    int dense = 0;
-    for (int b = tid; b < 2 * kNPos; b += kThreads) dense |= (b + 1 < 2 * kNPos ? (int)lut1[b + 1] : 255) - (int)lut1[b] > 2;
-    for (int b = tid; b < kNPos; b += kThreads) dense |= (b + 1 < kNPos ? (int)lut2[b + 1] : 255) - (int)lut2[b] > 2;
-    const bool slow = __syncthreads_or(dense) != 0;
+    // the fast path needs at most one midpoint per bin (true of the dynamic code books) and, to know the sign of a first-moment
+    // code without reading it, an ascending code book whose sign-bit entries all come first; anything else -> generic search
+    int generic = tid < 255 && (__float_as_uint(q1[tid & 255]) >> 31) == 0 && (__float_as_uint(q1[(tid + 1) & 255]) >> 31) != 0;
+    for (int b = tid; b < 2 * kNPos; b += kThreads) generic |= (b + 1 < 2 * kNPos ? (int)lut1[b + 1] : 255) - (int)lut1[b] > 1;
+    for (int b = tid; b < kNPos; b += kThreads) generic |= (b + 1 < kNPos ? (int)lut2[b + 1] : 255) - (int)lut2[b] > 1;
+    const bool slow = __syncthreads_or(generic) != 0;
+    const int nneg = __syncthreads_count(tid < 256 && (__float_as_uint(q1[tid & 255]) >> 31) != 0);
     const int warp = tid >> 5, lane = tid & 31;
     for (int64_t blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
         const int64_t i0 = blk * kBlock + (int64_t)tid * kV;
@@ -180,19 +183,20 @@ __global__ void __launch_bounds__(kThreads, CTAS) adamw8bit_kernel(float* __rest
             for (int j = 0; j < kV; ++j) {
                 const float x1 = __fmul_rn(S1[j], inv1), x2 = __fmul_rn(S2[j], inv2);
                 int c1, c2;
+                bool code_neg;
                 if (!slow) {
                     c1 = lut1[lut_bin_signed(x1)];
                     c1 += x1 > m1[c1] ? 1 : 0;
-                    c1 += x1 > m1[c1] ? 1 : 0;
                     c2 = lut2[lut_bin_unsigned(x2)];
                     c2 += x2 > m2[c2] ? 1 : 0;
-                    c2 += x2 > m2[c2] ? 1 : 0;
+                    code_neg = c1 < nneg;
                 } else {
                     c1 = nearest_code(e1, x1);
                     c2 = nearest_code(e2, x2);
+                    code_neg = (__float_as_uint(q1[c1]) >> 31) != 0;
                 }
                 // bitsandbytes: "make sure state1 term has still the same sign after quantization"
-                if ((__float_as_uint(q1[c1]) >> 31) != (__float_as_uint(S1[j]) >> 31)) c1 += S1[j] > 0.f ? 1 : -1;
+                if (code_neg != ((__float_as_uint(S1[j]) >> 31) != 0)) c1 += S1[j] > 0.f ? 1 : -1;
                 o1 |= (uint32_t)(c1 & 255) << (8 * j);
                 o2 |= (uint32_t)(c2 & 255) << (8 * j);
             }

@@ -40,16 +40,26 @@ def _dense_code_books():
     return q1.float(), q2.float()
 
 
+def _medium_code_books():
+    """up to two midpoints per lookup-table bin (150 codes over [0.5, 1]: spacing 0.0033 against bins of 0.0039), a first-moment
+    book without a zero and with an odd number of negative codes: generic search again, different sign bookkeeping"""
+    lin = torch.linspace
+    q1 = torch.cat([-lin(1, 0.5, 75), lin(-0.4, -0.001, 16), lin(0.002, 0.4, 15), lin(0.5, 1, 150)])
+    q2 = torch.cat([torch.zeros(1), lin(1e-5, 0.45, 105), lin(0.5, 1, 150)])
+    assert q1.numel() == 256 and q2.numel() == 256 and bool((q1[1:] > q1[:-1]).all()) and bool((q2[1:] > q2[:-1]).all())
+    return q1.float(), q2.float()
+
+
 @pytest.mark.parametrize("n,with_modes,wd,dense", [(2048 * 5, False, 1e-2, False), (2048 * 37 + 64 * 7, True, 1e-2, False),
                                                    (64 * 3, True, 0.0, False), (2048 * 300 + 64, True, 0.1, False),
-                                                   (2048 * 9 + 64 * 3, True, 1e-2, True)])
+                                                   (2048 * 9 + 64 * 3, True, 1e-2, True), (2048 * 11 + 64, True, 0.0, "medium")])
 def test_adamw8bit_kernel_is_bit_exact_against_the_oracle(n, with_modes, wd, dense):
     from b200sd import ops
     gen = torch.Generator().manual_seed(n)
     mode = _random_modes(n // 64, gen) if with_modes else None
     ref = A.AdamW8bitRef(n, mode, lr=3e-3, betas=(0.9, 0.99), eps=1e-8, weight_decay=wd)
     if dense:
-        ref.qmap1, ref.qmap2 = _dense_code_books()
+        ref.qmap1, ref.qmap2 = _medium_code_books() if dense == "medium" else _dense_code_books()
     p_ref = torch.randn(n, generator=gen) * 0.1
     p = p_ref.clone().to(DEV)
     g_dev = torch.empty(n, device=DEV)
