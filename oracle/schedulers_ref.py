@@ -154,6 +154,17 @@ class PNDMSchedulerRef(_Base):
         return sample_coeff * sample - (a_p - a_t) * e / denom
 
 
+def pndm_prk_timesteps(sch: "PNDMSchedulerRef"):
+    """diffusers 0.7.2 scheduling_pndm.py `set_timesteps`, skip_prk_steps=False branch: (prk_timesteps, plms_timesteps)"""
+    n = sch.num_inference_steps
+    ratio = sch.num_train_timesteps // n
+    _t = (np.arange(0, n) * ratio).round() + sch.config.steps_offset
+    prk = np.array(_t[-sch.pndm_order:]).repeat(2) + np.tile(np.array([0, ratio // 2]), sch.pndm_order)
+    prk = (prk[:-1].repeat(2)[1:-1])[::-1].copy().astype(np.int64)
+    plms = _t[:-3][::-1].copy().astype(np.int64)
+    return prk, plms
+
+
 def pndm_prk_warmup(sch: "PNDMSchedulerRef", model, sample):
     """diffusers 0.7.2 scheduling_pndm.py `set_timesteps` (skip_prk_steps=False branch) + `step_prk`: the 12
     Runge-Kutta calls that precede PLMS when PRK is not skipped.  NOT on the reference path (utils.py:222-224 sets
@@ -162,10 +173,7 @@ def pndm_prk_warmup(sch: "PNDMSchedulerRef", model, sample):
     Leaves `sch` as diffusers would (3 saved eps, counter 12) and returns (sample, plms_timesteps)."""
     n = sch.num_inference_steps
     ratio = sch.num_train_timesteps // n
-    _t = (np.arange(0, n) * ratio).round() + sch.config.steps_offset
-    prk = np.array(_t[-sch.pndm_order:]).repeat(2) + np.tile(np.array([0, ratio // 2]), sch.pndm_order)
-    prk = (prk[:-1].repeat(2)[1:-1])[::-1].copy().astype(np.int64)
-    plms = _t[:-3][::-1].copy().astype(np.int64)
+    prk, plms = pndm_prk_timesteps(sch)
     cur_out, cur_sample, ets = 0, None, []
     for c, t in enumerate(prk):
         t = int(t)

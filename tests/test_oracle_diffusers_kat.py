@@ -244,3 +244,25 @@ def test_pndm_full_loop(variant):
     for t in plms_timesteps:
         sample = sch.step(dummy_model(sample, int(t)), int(t), sample).prev_sample
     _check_sched("pndm", variant, sample)
+
+
+def test_steps_offset_timestep_tables():
+    """the reference's PNDM pipelines run with steps_offset=1 (utils.py:222-224): diffusers' own tables for that setting, held
+    against the oracle AND the product's host-side scheduler"""
+    want = KAT["schedulers"]["steps_offset"]
+    sch = R.DDIMSchedulerRef(**{**SCHED_CFG, "steps_offset": 1})
+    sch.set_timesteps(5)
+    assert sch.timesteps.tolist() == want["ddim_5"]
+    warm = R.PNDMSchedulerRef(**{**SCHED_CFG, "skip_prk_steps": True, "steps_offset": 1})
+    warm.set_timesteps(10)
+    prk, plms = R.pndm_prk_timesteps(warm)
+    assert prk.tolist() + plms.tolist() == want["pndm_10_with_prk"]
+    from b200sd.schedulers import DDIMScheduler, PNDMScheduler
+    ours = DDIMScheduler(**{**SCHED_CFG, "clip_sample": False, "steps_offset": 1})
+    ours.set_timesteps(5)
+    assert ours.timesteps.tolist() == want["ddim_5"]
+    # PLMS-only (skip_prk_steps=True, what the reference uses): oracle and product agree on the table, whose 2nd-order start
+    # repeats the second timestep
+    ours = PNDMScheduler(**{**SCHED_CFG, "skip_prk_steps": True, "steps_offset": 1})
+    ours.set_timesteps(10)
+    assert ours.timesteps.tolist() == warm.timesteps.tolist() == [901, 801, 801, 701, 601, 501, 401, 301, 201, 101, 1]

@@ -263,3 +263,100 @@ def test_flat_adamw_is_a_torch_optimizer_driven_by_the_reference_lr_schedule(mon
     assert opt.lr == sched.get_last_lr()[0] < lrs[-1]
     with pytest.raises(ValueError):
         FlatAdamW(flat_b, lr=-1.0)
+
+
+def _oracle_adamw8bit_stand_in(monkeypatch):
+    """ops.adamw8bit_step is a CUDA kernel; on the CPU the oracle's step (the kernel is bit-exact against it on the GPU:
+    tests/test_optim8bit_gpu.py) stands in behind the same argument list, so FlatAdamW8bit's host logic -- chunk table, state
+    buffers, range-wise stepping, state_dict, rebind -- runs without a GPU."""
+    from b200sd import ops
+    from oracle import adam8bit_ref as A
+    calls = []
+
+    def adamw8bit_step(param, grad, state1, state2, absmax1, absmax2, qmap1, qmap2, chunk_mode, small_m, small_v, wb, lr, beta1, beta2,
+                       eps, weight_decay, step, grad_scale=1.0, zero_grad=False):
+        ref = A.AdamW8bitRef(param.numel(), chunk_mode, lr=lr, betas=(beta1, beta2), eps=eps, weight_decay=weight_decay)
+        assert torch.equal(ref.qmap1, qmap1) and torch.equal(ref.qmap2, qmap2)
+        ref.state1, ref.state2, ref.absmax1, ref.absmax2 = state1, state2, absmax1.clone(), absmax2.clone()
+        n_small = ref.small_m.numel()
+        ref.small_m, ref.small_v, ref.steps = small_m[:max(n_small, 0)], small_v[:max(n_small, 0)], step - 1
+        wb.copy_(torch.where((ref.chunk_mode != A.MODE_SKIP).repeat_interleave(64), ref.step(param, grad, grad_scale, zero_grad), wb))
+        absmax1.copy_(ref.absmax1)
+        absmax2.copy_(ref.absmax2)
+        calls.append(step)
+    monkeypatch.setattr(ops, "adamw8bit_step", adamw8bit_step)
+    return calls
+
+
+def test_flat_adamw8bit_host_logic(monkeypatch):
+    """Trainer(optim_bits=8) == bnb.optim.AdamW8bit(..., min_8bit_size=16384) (finetune_sd.py:300, 407-410): tensors below
+    16 384 elements keep fp32 moments at disjoint offsets of a compact buffer, frozen tensors are skipped, everything else is
+    8-bit; ~2 B of state per parameter; one launch per step, also in the trainers' range-by-range form; lr schedule, state_dict
+    (u8 codes stay u8) and rebind like FlatAdamW."""
+    from b200sd.train import FlatParams
+    from b200sd.trainer import FlatAdamW, FlatAdamW8bit, _make_optimizer
+    calls = _oracle_adamw8bit_stand_in(monkeypatch)
+    m = _tiny()
+    m.mark_weights_changed = lambda: None
+    m.conv_in.weight.requires_grad_(False)
+    flat = FlatParams(m, torch.device("cpu"))
+    flat.attach_grads()
+    opt = _make_optimizer(flat, 8, dict(lr=1e-3, betas=(0.9, 0.99), eps=1e-8, weight_decay=1e-2), 16384)
+    assert isinstance(opt, FlatAdamW8bit) and isinstance(opt, FlatAdamW) and isinstance(opt, torch.optim.Optimizer)
+    assert type(_make_optimizer(flat, 32, dict(lr=1e-3), 16384)) is FlatAdamW
+    with pytest.raises(ValueError):
+        _make_optimizer(flat, 16, {}, 16384)
+    # the chunk table
+    mode = opt.chunk_mode
+    assert mode.numel() == flat.total // 64 and mode.dtype == torch.int32
+    small_offsets = []
+    for r in flat.order:
+        chunks = mode[r.off // 64:(r.off + r.numel + 63) // 64]
+        if not r.param.requires_grad:
+            assert bool((chunks == -2).all())
+        elif r.numel < 16384:
+            assert bool((chunks >= 0).all()) and bool((chunks[1:] - chunks[:-1] == 64).all())
+            small_offsets += chunks.tolist()
+        else:
+            assert bool((chunks == -1).all())
+    assert len(set(small_offsets)) == len(small_offsets) and sorted(small_offsets) == list(range(0, 64 * len(small_offsets), 64))
+    st = opt.state[flat.master]
+    assert st["exp_avg"].numel() == 64 * len(small_offsets) and st["state1"].dtype == torch.uint8
+    assert st["absmax1"].numel() == (flat.total + 2047) // 2048
+    assert opt.state_bytes() < 2.5 * flat.total
+    # steps: one launch each, frozen parameter untouched, lr schedule applies
+    frozen = m.conv_in.weight.detach().clone()
+    w = m.down_blocks[0].resnets[0].conv1.weight
+    before = w.detach().clone()
+    sched = torch.optim.lr_scheduler.CosineAnnealingLR(opt, T_max=4, eta_min=1e-6)
+    gen = torch.Generator().manual_seed(0)
+    for it in range(3):
+        flat.grad.copy_(torch.randn(flat.total, generator=gen) * 1e-2)
+        if it == 1:
+            opt.begin_step()
+            opt.step_range(flat.total // 2 // 64 * 64, flat.total, grad_scale=0.5)
+            opt.step_range(0, flat.total // 2 // 64 * 64, grad_scale=0.5)
+            with pytest.raises(ValueError):
+                opt.step_range(0, 64, grad_scale=0.25)
+            opt.end_step()
+        else:
+            opt.step(grad_scale=0.5)
+        sched.step()
+    assert calls == [1, 2, 3] and opt.steps == 3 and opt.lr < 1e-3
+    assert torch.equal(m.conv_in.weight.detach(), frozen) and not torch.equal(w.detach(), before)
+    live = (mode != -2).repeat_interleave(64)
+    assert float(flat.grad[live].abs().max()) == 0.0 and int(st["state1"].max()) > 0 and float(st["exp_avg"].abs().max()) > 0
+    assert torch.equal(flat.wb[live], flat.master[live].bfloat16())
+    # state_dict round trip (torch casts floating state to the parameter's dtype: the codes must come back as u8, bit for bit)
+    sd = opt.state_dict()
+    opt2 = FlatAdamW8bit(flat, lr=1.0)
+    opt2.load_state_dict(sd)
+    st2 = opt2.state[flat.master]
+    assert opt2.steps == 3 and opt2.lr == opt.lr and st2["state1"].dtype == torch.uint8
+    assert all(torch.equal(st2[k], st[k]) for k in ("state1", "state2", "absmax1", "absmax2", "exp_avg", "exp_avg_sq"))
+    with pytest.raises(ValueError):
+        FlatAdamW(flat, lr=1e-3).load_state_dict(sd)             # an 8-bit state does not load into the fp32-moment optimizer
+    # rebuild of the flat buffers: same object, same state
+    codes = st["state1"].clone()
+    flat_b = FlatParams(m, torch.device("cpu"))
+    assert opt.rebind(flat_b) is opt and torch.equal(opt.state[flat_b.master]["state1"], codes) and opt.steps == 3
