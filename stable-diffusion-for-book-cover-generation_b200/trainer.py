@@ -128,16 +128,19 @@ class FlatAdamW(torch.optim.Optimizer):
     _state_dtypes = {"exp_avg": torch.float32, "exp_avg_sq": torch.float32}
 
     def load_state_dict(self, state_dict):
+        # validated BEFORE anything is replaced: a state that does not fit leaves this optimizer as it was
         want = {k: v.shape for k, v in self.state[self.flat.master].items() if torch.is_tensor(v)}
-        saved = {k: (v.dtype if torch.is_tensor(v) else None) for k, v in state_dict["state"].get(0, {}).items()}
-        super().load_state_dict(state_dict)       # torch casts every floating state tensor to the parameter's dtype / device
+        saved = state_dict["state"].get(0, {})
+        for k, shape in want.items():
+            v = saved.get(k)
+            if not torch.is_tensor(v) or v.shape != shape:
+                raise ValueError(f"optimizer state '{k}' does not fit this model's flat parameter buffer ({tuple(shape)})")
+            if v.dtype != self._state_dtypes[k]:
+                raise ValueError(f"optimizer state '{k}' was saved as {v.dtype}, expected {self._state_dtypes[k]}")
+        super().load_state_dict(state_dict)       # torch casts every state tensor to the parameter's dtype (u8 codes included)
         st = self.state[self.flat.master]
         st["step"] = int(st["step"])
-        for k, shape in want.items():
-            if k not in st or st[k].shape != shape:
-                raise ValueError(f"optimizer state '{k}' does not fit this model's flat parameter buffer ({tuple(shape)})")
-            if saved.get(k) != self._state_dtypes[k]:
-                raise ValueError(f"optimizer state '{k}' was saved as {saved.get(k)}, expected {self._state_dtypes[k]}")
+        for k in want:
             st[k] = st[k].to(device=self.flat.master.device, dtype=self._state_dtypes[k]).contiguous()
 
     def zero_grad(self, set_to_none: bool = True):

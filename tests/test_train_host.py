@@ -354,8 +354,10 @@ def test_flat_adamw8bit_host_logic(monkeypatch):
     st2 = opt2.state[flat.master]
     assert opt2.steps == 3 and opt2.lr == opt.lr and st2["state1"].dtype == torch.uint8
     assert all(torch.equal(st2[k], st[k]) for k in ("state1", "state2", "absmax1", "absmax2", "exp_avg", "exp_avg_sq"))
+    other = FlatAdamW(flat, lr=1e-3)
     with pytest.raises(ValueError):
-        FlatAdamW(flat, lr=1e-3).load_state_dict(sd)             # an 8-bit state does not load into the fp32-moment optimizer
+        other.load_state_dict(sd)                                # an 8-bit state does not load into the fp32-moment optimizer ...
+    assert other.lr == 1e-3 and other.steps == 0 and other.exp_avg.numel() == flat.total      # ... which stays as it was
     # rebuild of the flat buffers: same object, same state
     codes = st["state1"].clone()
     flat_b = FlatParams(m, torch.device("cpu"))
