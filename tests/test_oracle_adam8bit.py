@@ -108,3 +108,16 @@ def test_8bit_moments_follow_fp32_adamw_over_a_training_like_sequence():
     rel = float((moved8 - moved32).norm() / moved32.norm())
     assert cos >= 0.995 and rel <= 0.1, (cos, rel)            # measured 0.9986 / 0.053
     assert opt.state1.numel() + opt.state2.numel() + 4 * (opt.absmax1.numel() + opt.absmax2.numel()) < 2.01 * n   # ~2 B / parameter
+
+
+def test_committed_regression_vectors():
+    """tests/golden/adam8bit_oracle_kat.json (generated by the oracle itself: a regression guard, not a pin)"""
+    import importlib.util
+    import json
+    import os
+    here = os.path.join(os.path.dirname(__file__), "golden")
+    spec = importlib.util.spec_from_file_location("make_adam8bit_golden", os.path.join(here, "make_adam8bit_golden.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    want = json.load(open(os.path.join(here, "adam8bit_oracle_kat.json")))
+    assert mod.run() == want
